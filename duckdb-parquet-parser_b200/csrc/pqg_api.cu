@@ -1,0 +1,491 @@
+// pqg_api.cu -- implementation of the C-ABI in include/pqg.h: contexts, device images,
+// decode plans.  No CPU fallback: every compute entry point needs a CUDA device.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "pqg_internal.h"
+
+using namespace pqg;
+
+struct pqg_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 148;
+    bool profiling = false;
+    uint64_t launches = 0;
+    std::string err;
+};
+
+struct pqg_buf {
+    uint8_t* d = nullptr;
+    uint64_t size = 0;
+    bool owned = false;
+};
+
+struct pqg_plan {
+    const pqg_buf* image = nullptr;
+    std::vector<pqg_chunk_desc> chunks;
+    std::vector<pqg_page_desc> pages;
+    DevChunk* d_chunks = nullptr;
+    pqg_page_desc* d_pages = nullptr;
+    uint8_t* d_dict = nullptr;
+    size_t dict_bytes = 0;
+    bool any_dict = false, any_def = false, is_str = false, is_bool = false;
+    int phys = 0, width = 0;
+    uint64_t n_slots = 0;
+    uint8_t* d_values = nullptr;
+    uint32_t* d_validity = nullptr;
+    uint32_t* d_offsets = nullptr;
+    uint8_t* d_chars = nullptr;
+    uint64_t chars_cap = 0, chars_size = 0;
+    uint32_t* d_page_chars = nullptr;
+    uint32_t* d_page_char_base = nullptr;
+    uint64_t* d_bases = nullptr;  // n_chunks + 1 bases, then the grand total
+    uint64_t* h_bases = nullptr;  // pinned mirror
+    DevErr* d_err = nullptr;
+    DevErr* h_err = nullptr;      // pinned
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool timed = false;
+    pqg_timings tm{};
+    uint64_t bytes_in = 0, bytes_out = 0;
+    bool ran = false;
+};
+
+struct pqg_dfa; // pqg_regex_host.cpp
+
+static std::string g_create_err;
+
+static int fail(pqg_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->err = msg; else g_create_err = msg;
+    return code;
+}
+static int cuda_fail(pqg_ctx* ctx, cudaError_t e, const char* what) {
+    return fail(ctx, PQG_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CU(ctx, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(ctx, e_, #call); } while (0)
+
+extern "C" {
+
+int pqg_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int pqg_ctx_create(int device, void* stream, pqg_ctx** out) {
+    if (!out) return fail(nullptr, PQG_ERR_ARG, "pqg_ctx_create: out is NULL");
+    *out = nullptr;
+    int n = pqg_device_count();
+    if (n <= 0) return fail(nullptr, PQG_ERR_CUDA, "pqg_ctx_create: no CUDA device is available (this library has no CPU fallback)");
+    if (device < 0 || device >= n) return fail(nullptr, PQG_ERR_ARG, "pqg_ctx_create: bad device index");
+    pqg_ctx* c = new (std::nothrow) pqg_ctx();
+    if (!c) return fail(nullptr, PQG_ERR_NOMEM, "out of memory");
+    c->device = device;
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) { delete c; return cuda_fail(nullptr, e, "cudaSetDevice"); }
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) { delete c; return cuda_fail(nullptr, e, "cudaGetDeviceProperties"); }
+    if (prop.major < 10) {
+        delete c;
+        return fail(nullptr, PQG_ERR_CUDA, "pqg_ctx_create: this build targets sm_100a (Blackwell B200) only");
+    }
+    c->sm_count = prop.multiProcessorCount;
+    if (stream) { c->stream = static_cast<cudaStream_t>(stream); c->own_stream = false; }
+    else {
+        e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) { delete c; return cuda_fail(nullptr, e, "cudaStreamCreate"); }
+        c->own_stream = true;
+    }
+    *out = c;
+    return PQG_OK;
+}
+
+void pqg_ctx_destroy(pqg_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* pqg_last_error(const pqg_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+int pqg_ctx_sync(pqg_ctx* ctx) {
+    if (!ctx) return PQG_ERR_ARG;
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return PQG_OK;
+}
+
+int pqg_ctx_set_profiling(pqg_ctx* ctx, int on) {
+    if (!ctx) return PQG_ERR_ARG;
+    ctx->profiling = on != 0;
+    return PQG_OK;
+}
+
+uint64_t pqg_kernel_launches(const pqg_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+void* pqg_host_alloc(uint64_t size) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, size ? size : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void pqg_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+int pqg_upload(pqg_ctx* ctx, const void* host_bytes, uint64_t size, pqg_buf** out) {
+    if (!ctx || !out || (!host_bytes && size)) return fail(ctx, PQG_ERR_ARG, "pqg_upload: bad argument");
+    CU(ctx, cudaSetDevice(ctx->device));
+    pqg_buf* b = new (std::nothrow) pqg_buf();
+    if (!b) return fail(ctx, PQG_ERR_NOMEM, "out of memory");
+    cudaError_t e = cudaMalloc(&b->d, size + kImagePad);
+    if (e != cudaSuccess) { delete b; return cuda_fail(ctx, e, "cudaMalloc(image)"); }
+    b->size = size;
+    b->owned = true;
+    e = cudaMemsetAsync(b->d + size, 0, kImagePad, ctx->stream);
+    if (e == cudaSuccess && size) e = cudaMemcpyAsync(b->d, host_bytes, size, cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) { cudaFree(b->d); delete b; return cuda_fail(ctx, e, "cudaMemcpyAsync(image)"); }
+    *out = b;
+    return PQG_OK;
+}
+
+int pqg_buf_alloc(pqg_ctx* ctx, uint64_t size, pqg_buf** out) {
+    if (!ctx || !out) return fail(ctx, PQG_ERR_ARG, "pqg_buf_alloc: bad argument");
+    CU(ctx, cudaSetDevice(ctx->device));
+    pqg_buf* b = new (std::nothrow) pqg_buf();
+    if (!b) return fail(ctx, PQG_ERR_NOMEM, "out of memory");
+    cudaError_t e = cudaMalloc(&b->d, size + kImagePad);
+    if (e != cudaSuccess) { delete b; return cuda_fail(ctx, e, "cudaMalloc(image)"); }
+    b->size = size;
+    b->owned = true;
+    e = cudaMemsetAsync(b->d + size, 0, kImagePad, ctx->stream);
+    if (e != cudaSuccess) { cudaFree(b->d); delete b; return cuda_fail(ctx, e, "cudaMemsetAsync(image pad)"); }
+    *out = b;
+    return PQG_OK;
+}
+
+int pqg_buf_write(pqg_ctx* ctx, pqg_buf* buf, uint64_t dst_off, const void* host_bytes, uint64_t n) {
+    if (!ctx || !buf || (!host_bytes && n)) return fail(ctx, PQG_ERR_ARG, "pqg_buf_write: bad argument");
+    if (dst_off + n > buf->size) return fail(ctx, PQG_ERR_ARG, "pqg_buf_write: range outside the image");
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (n) CU(ctx, cudaMemcpyAsync(buf->d + dst_off, host_bytes, n, cudaMemcpyHostToDevice, ctx->stream));
+    return PQG_OK;
+}
+
+uint64_t pqg_buf_size(const pqg_buf* buf) { return buf ? buf->size : 0; }
+
+int pqg_wrap_device(pqg_ctx* ctx, const void* dev_ptr, uint64_t size, pqg_buf** out) {
+    if (!ctx || !out || !dev_ptr) return fail(ctx, PQG_ERR_ARG, "pqg_wrap_device: bad argument");
+    if (reinterpret_cast<uintptr_t>(dev_ptr) & 15u) return fail(ctx, PQG_ERR_ARG, "pqg_wrap_device: pointer must be 16-byte aligned");
+    pqg_buf* b = new (std::nothrow) pqg_buf();
+    if (!b) return fail(ctx, PQG_ERR_NOMEM, "out of memory");
+    b->d = const_cast<uint8_t*>(static_cast<const uint8_t*>(dev_ptr));
+    b->size = size;
+    b->owned = false;
+    *out = b;
+    return PQG_OK;
+}
+
+void pqg_buf_free(pqg_ctx* ctx, pqg_buf* buf) {
+    if (!buf) return;
+    if (ctx) cudaSetDevice(ctx->device);
+    if (buf->owned && buf->d) cudaFree(buf->d);
+    delete buf;
+}
+
+const void* pqg_buf_device_ptr(const pqg_buf* buf) { return buf ? buf->d : nullptr; }
+
+// ---------------------------------------------------------------------------------------------
+
+static int type_width(int phys) {
+    switch (phys) {
+        case PQG_BOOLEAN: return 1;
+        case PQG_INT32: case PQG_FLOAT: return 4;
+        case PQG_INT64: case PQG_DOUBLE: return 8;
+        case PQG_INT96: return 12;
+        default: return 0;
+    }
+}
+static uint8_t level_bw(int16_t m) { // ColumnReader::bit_width (column_reader.cpp:270-276)
+    uint8_t bw = 0;
+    int v = m;
+    while (v > 0) { bw++; v >>= 1; }
+    return bw;
+}
+
+void pqg_plan_destroy(pqg_ctx* ctx, pqg_plan* p) {
+    if (!p) return;
+    if (ctx) cudaSetDevice(ctx->device);
+    cudaFree(p->d_chunks); cudaFree(p->d_pages); cudaFree(p->d_dict); cudaFree(p->d_values);
+    cudaFree(p->d_validity); cudaFree(p->d_offsets); cudaFree(p->d_chars); cudaFree(p->d_page_chars);
+    cudaFree(p->d_page_char_base); cudaFree(p->d_bases); cudaFree(p->d_err);
+    if (p->h_bases) cudaFreeHost(p->h_bases);
+    if (p->h_err) cudaFreeHost(p->h_err);
+    for (auto& e : p->ev) if (e) cudaEventDestroy(e);
+    delete p;
+}
+
+int pqg_plan_create(pqg_ctx* ctx, const pqg_buf* image, const pqg_chunk_desc* chunks, uint32_t n_chunks,
+                    const pqg_page_desc* pages, uint32_t n_pages, pqg_plan** out) {
+    if (!ctx || !image || !out || (!chunks && n_chunks) || (!pages && n_pages))
+        return fail(ctx, PQG_ERR_ARG, "pqg_plan_create: bad argument");
+    *out = nullptr;
+    if (n_chunks == 0) return fail(ctx, PQG_ERR_ARG, "pqg_plan_create: no chunks");
+    CU(ctx, cudaSetDevice(ctx->device));
+    pqg_plan* p = new (std::nothrow) pqg_plan();
+    if (!p) return fail(ctx, PQG_ERR_NOMEM, "out of memory");
+    p->image = image;
+    p->chunks.assign(chunks, chunks + n_chunks);
+    p->pages.assign(pages, pages + n_pages);
+    p->phys = chunks[0].phys_type;
+    auto bail = [&](int code, const std::string& m) { pqg_plan_destroy(ctx, p); return fail(ctx, code, m); };
+    if (p->phys == PQG_FIXED_LEN_BYTE_ARRAY)
+        return bail(PQG_ERR_UNSUPPORTED, "FIXED_LEN_BYTE_ARRAY not supported without type_length");
+    if (p->phys < 0 || p->phys > PQG_FIXED_LEN_BYTE_ARRAY)
+        return bail(PQG_ERR_UNSUPPORTED, "Unsupported type: " + std::to_string(p->phys));
+    p->is_str = p->phys == PQG_BYTE_ARRAY;
+    p->is_bool = p->phys == PQG_BOOLEAN;
+    p->width = type_width(p->phys);
+
+    std::vector<DevChunk> dc(n_chunks);
+    size_t arena = 0;
+    uint64_t slots = 0;
+    for (uint32_t c = 0; c < n_chunks; c++) {
+        const pqg_chunk_desc& s = chunks[c];
+        if (s.phys_type != p->phys) return bail(PQG_ERR_ARG, "pqg_plan_create: chunks of one plan must share a physical type");
+        if (static_cast<uint64_t>(s.first_page) + s.n_pages > n_pages) return bail(PQG_ERR_ARG, "pqg_plan_create: chunk page range out of bounds");
+        DevChunk& d = dc[c];
+        std::memset(&d, 0, sizeof(d));
+        d.dict_off = s.dict_off; d.out_row_base = s.out_row_base; d.num_values = s.num_values;
+        d.dict_size = s.dict_size; d.dict_n = s.dict_num_values; d.first_page = s.first_page; d.n_pages = s.n_pages;
+        d.max_def = s.max_def; d.max_rep = s.max_rep; d.phys_type = s.phys_type; d.has_dict = s.has_dict;
+        d.def_bw = level_bw(s.max_def); d.rep_bw = level_bw(s.max_rep);
+        if (s.has_dict) {
+            if (s.dict_off + s.dict_size > image->size) return bail(PQG_ERR_ARG, "pqg_plan_create: dictionary page outside the image");
+            p->any_dict = true;
+            d.dict_arena_off = arena;
+            size_t ent = p->is_str ? 8 : static_cast<size_t>(p->width);
+            arena += (static_cast<size_t>(s.dict_num_values) * ent + 31) & ~size_t(15);
+            p->bytes_in += s.dict_size;
+        }
+        if (s.max_def > 0) p->any_def = true;
+        for (uint32_t q = s.first_page; q < s.first_page + s.n_pages; q++) {
+            if (pages[q].chunk_idx != c) return bail(PQG_ERR_ARG, "pqg_plan_create: pages of a chunk must be contiguous");
+            if (pages[q].payload_off + pages[q].payload_size > image->size) return bail(PQG_ERR_ARG, "pqg_plan_create: page outside the image");
+            p->bytes_in += pages[q].payload_size;
+        }
+        slots = std::max<uint64_t>(slots, s.out_row_base + s.num_values);
+    }
+    p->n_slots = slots;
+    p->dict_bytes = arena;
+
+    auto alloc = [&](void** ptr, size_t bytes) -> cudaError_t { return cudaMalloc(ptr, bytes ? bytes : 16); };
+    cudaError_t e;
+#define PA(ptr, bytes) if ((e = alloc(reinterpret_cast<void**>(&(ptr)), (bytes))) != cudaSuccess) { pqg_plan_destroy(ctx, p); return cuda_fail(ctx, e, "cudaMalloc(plan)"); }
+    PA(p->d_chunks, sizeof(DevChunk) * n_chunks);
+    PA(p->d_pages, sizeof(pqg_page_desc) * std::max<uint32_t>(n_pages, 1));
+    PA(p->d_err, sizeof(DevErr));
+    if (p->any_dict) PA(p->d_dict, arena + 64);
+    if (p->any_def) PA(p->d_validity, ((slots + 31) / 32 + 1) * 4);
+    if (p->is_str) {
+        PA(p->d_offsets, (slots + n_chunks + 1) * 4);
+        PA(p->d_page_chars, static_cast<size_t>(n_pages + 1) * 4);
+        PA(p->d_page_char_base, static_cast<size_t>(n_pages + 1) * 4);
+        PA(p->d_bases, (n_chunks + 2) * 8);
+        if ((e = cudaHostAlloc(reinterpret_cast<void**>(&p->h_bases), (n_chunks + 2) * 8, cudaHostAllocDefault)) != cudaSuccess) {
+            pqg_plan_destroy(ctx, p); return cuda_fail(ctx, e, "cudaHostAlloc");
+        }
+        std::memset(p->h_bases, 0, (n_chunks + 2) * 8);
+    } else {
+        PA(p->d_values, slots * p->width + 16);
+    }
+#undef PA
+    if ((e = cudaHostAlloc(reinterpret_cast<void**>(&p->h_err), sizeof(DevErr), cudaHostAllocDefault)) != cudaSuccess) {
+        pqg_plan_destroy(ctx, p); return cuda_fail(ctx, e, "cudaHostAlloc");
+    }
+    std::memset(p->h_err, 0, sizeof(DevErr));
+    e = cudaMemcpyAsync(p->d_chunks, dc.data(), sizeof(DevChunk) * n_chunks, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && n_pages)
+        e = cudaMemcpyAsync(p->d_pages, p->pages.data(), sizeof(pqg_page_desc) * n_pages, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { pqg_plan_destroy(ctx, p); return cuda_fail(ctx, e, "descriptor upload"); }
+    for (auto& ev : p->ev) {
+        if ((e = cudaEventCreate(&ev)) != cudaSuccess) { pqg_plan_destroy(ctx, p); return cuda_fail(ctx, e, "cudaEventCreate"); }
+    }
+    // algorithmic output bytes (SURVEY.md section 8 d)
+    if (!p->is_str) p->bytes_out = slots * p->width + (p->any_def ? (slots + 7) / 8 : 0);
+    *out = p;
+    return PQG_OK;
+}
+
+int pqg_plan_set_image(pqg_ctx* ctx, pqg_plan* plan, const pqg_buf* image) {
+    if (!ctx || !plan || !image) return fail(ctx, PQG_ERR_ARG, "pqg_plan_set_image: bad argument");
+    if (image->size < plan->image->size) return fail(ctx, PQG_ERR_ARG, "pqg_plan_set_image: image is smaller than the planned one");
+    plan->image = image;
+    return PQG_OK;
+}
+
+static DecodeParams make_params(const pqg_plan* p) {
+    DecodeParams P;
+    std::memset(&P, 0, sizeof(P));
+    P.image = p->image->d; P.image_size = p->image->size;
+    P.chunks = p->d_chunks; P.pages = p->d_pages;
+    P.page_begin = 0; P.page_end = static_cast<uint32_t>(p->pages.size());
+    P.n_chunks = static_cast<uint32_t>(p->chunks.size());
+    P.dict_arena = p->d_dict; P.values = p->d_values; P.validity = p->d_validity;
+    P.offsets = p->d_offsets; P.chars = p->d_chars;
+    P.page_chars = p->d_page_chars; P.page_char_base = p->d_page_char_base; P.err = p->d_err;
+    return P;
+}
+
+int pqg_plan_run(pqg_ctx* ctx, pqg_plan* p) {
+    if (!ctx || !p) return fail(ctx, PQG_ERR_ARG, "pqg_plan_run: bad argument");
+    CU(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const bool prof = ctx->profiling;
+    uint32_t launches = 0;
+    p->timed = prof;
+    if (prof) CU(ctx, cudaEventRecord(p->ev[0], s));
+    CU(ctx, cudaMemsetAsync(p->d_err, 0xFF, 8, s));
+    CU(ctx, cudaMemsetAsync(reinterpret_cast<uint8_t*>(p->d_err) + 8, 0, sizeof(DevErr) - 8, s));
+    if (p->d_validity) CU(ctx, cudaMemsetAsync(p->d_validity, 0, ((p->n_slots + 31) / 32 + 1) * 4, s));
+    DecodeParams P = make_params(p);
+    if (p->any_dict) {
+        CU(ctx, launch_dict_prepare(P, P.n_chunks, p->is_str ? 0 : p->width, s));
+        launches++;
+    }
+    if (prof) CU(ctx, cudaEventRecord(p->ev[1], s));
+    if (!p->is_str) {
+        if (P.page_end) { CU(ctx, launch_decode_fixed(P, p->width, p->is_bool, ctx->sm_count, s)); launches++; }
+        if (prof) { CU(ctx, cudaEventRecord(p->ev[2], s)); CU(ctx, cudaEventRecord(p->ev[3], s)); }
+    } else {
+        if (P.page_end) { CU(ctx, launch_str_sizes(P, ctx->sm_count, s)); launches++; }
+        CU(ctx, launch_str_scan(P, p->d_bases, s));
+        launches += 2;
+        CU(ctx, cudaMemcpyAsync(p->h_bases, p->d_bases, (P.n_chunks + 2) * 8, cudaMemcpyDeviceToHost, s));
+        if (prof) CU(ctx, cudaEventRecord(p->ev[2], s));
+        if (!p->ran || true) {
+            // the output size is data dependent: wait for the size pass, (re)allocate if needed
+            CU(ctx, cudaStreamSynchronize(s));
+            uint64_t total = p->h_bases[P.n_chunks + 1];
+            if (total > p->chars_cap || !p->d_chars) {
+                cudaFree(p->d_chars);
+                p->d_chars = nullptr;
+                CU(ctx, cudaMalloc(reinterpret_cast<void**>(&p->d_chars), total + 64));
+                p->chars_cap = total;
+            }
+            p->chars_size = total;
+            P.chars = p->d_chars;
+        }
+        if (P.page_end) { CU(ctx, launch_str_copy(P, ctx->sm_count, s)); launches++; }
+        if (prof) CU(ctx, cudaEventRecord(p->ev[3], s));
+    }
+    if (prof) CU(ctx, cudaEventRecord(p->ev[4], s));
+    p->tm.launches = launches;
+    ctx->launches += launches;
+    p->ran = true;
+    return PQG_OK;
+}
+
+int pqg_plan_finish(pqg_ctx* ctx, pqg_plan* p, pqg_page_error* err) {
+    if (!ctx || !p) return fail(ctx, PQG_ERR_ARG, "pqg_plan_finish: bad argument");
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaMemcpyAsync(p->h_err, p->d_err, sizeof(DevErr), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if (p->timed) {
+        cudaEventElapsedTime(&p->tm.dict_ms, p->ev[0], p->ev[1]);
+        if (p->is_str) {
+            cudaEventElapsedTime(&p->tm.str_size_ms, p->ev[1], p->ev[2]);
+            cudaEventElapsedTime(&p->tm.str_copy_ms, p->ev[2], p->ev[3]);
+            p->tm.fixed_ms = 0;
+        } else {
+            cudaEventElapsedTime(&p->tm.fixed_ms, p->ev[1], p->ev[2]);
+            p->tm.str_size_ms = p->tm.str_copy_ms = 0;
+        }
+        cudaEventElapsedTime(&p->tm.total_ms, p->ev[0], p->ev[4]);
+    }
+    if (p->is_str) {
+        uint64_t slots = p->n_slots;
+        p->bytes_out = p->chars_size + 4 * (slots + p->chunks.size()) + (p->any_def ? (slots + 7) / 8 : 0);
+    }
+    pqg_page_error pe{};
+    const DevErr& d = *p->h_err;
+    pe.count = d.count;
+    if (d.count) {
+        pe.page = static_cast<uint32_t>(d.key >> 32);
+        pe.code = static_cast<uint32_t>(d.key & 0xffffffffu);
+        if (d.d_page == pe.page) { pe.pos = d.d_pos; pe.need = d.d_need; pe.size = d.d_size; }
+    }
+    if (err) *err = pe;
+    if (pe.count) {
+        char msg[256];
+        if (pe.code == PQG_PAGE_TRUNCATED || pe.code == PQG_PAGE_DICT_TRUNCATED)
+            std::snprintf(msg, sizeof(msg), "ByteBuffer: read beyond end (pos=%u need=%u size=%u)", pe.pos, pe.need, pe.size);
+        else if (pe.code == PQG_PAGE_BAD_BIT_WIDTH)
+            std::snprintf(msg, sizeof(msg), "page %u: dictionary index bit width %u > 32 is not supported", pe.page, pe.need);
+        else if (pe.code == PQG_PAGE_BAD_RUN)
+            std::snprintf(msg, sizeof(msg), "page %u: zero-length RLE/bit-packed run (undefined in the reference decoder)", pe.page);
+        else if (pe.code == PQG_PAGE_CHARS_OVERFLOW)
+            std::snprintf(msg, sizeof(msg), "page %u: column chunk exceeds 4 GiB of string bytes", pe.page);
+        else
+            std::snprintf(msg, sizeof(msg), "page %u: decode error %u", pe.page, pe.code);
+        return fail(ctx, PQG_ERR_PAGE, msg);
+    }
+    return PQG_OK;
+}
+
+int pqg_plan_timings(const pqg_plan* plan, pqg_timings* out) {
+    if (!plan || !out) return PQG_ERR_ARG;
+    *out = plan->tm;
+    return PQG_OK;
+}
+
+uint64_t pqg_plan_num_slots(const pqg_plan* p) { return p ? p->n_slots : 0; }
+uint32_t pqg_plan_value_width(const pqg_plan* p) { return p ? static_cast<uint32_t>(p->width) : 0; }
+const void* pqg_plan_values(const pqg_plan* p) { return p ? p->d_values : nullptr; }
+const uint32_t* pqg_plan_validity(const pqg_plan* p) { return p ? p->d_validity : nullptr; }
+const uint32_t* pqg_plan_offsets(const pqg_plan* p) { return p ? p->d_offsets : nullptr; }
+const uint8_t* pqg_plan_chars(const pqg_plan* p) { return p ? p->d_chars : nullptr; }
+uint64_t pqg_plan_chars_size(const pqg_plan* p) { return p ? p->chars_size : 0; }
+uint64_t pqg_plan_bytes_in(const pqg_plan* p) { return p ? p->bytes_in : 0; }
+uint64_t pqg_plan_bytes_out(const pqg_plan* p) { return p ? p->bytes_out : 0; }
+
+int pqg_plan_char_bases(pqg_ctx* ctx, const pqg_plan* p, uint64_t* out, uint32_t n) {
+    if (!ctx || !p || !out) return fail(ctx, PQG_ERR_ARG, "pqg_plan_char_bases: bad argument");
+    if (!p->is_str || !p->ran) return fail(ctx, PQG_ERR_ARG, "pqg_plan_char_bases: not a decoded BYTE_ARRAY plan");
+    uint32_t have = static_cast<uint32_t>(p->chunks.size()) + 1;
+    for (uint32_t i = 0; i < n && i < have; i++) out[i] = p->h_bases[i];
+    return PQG_OK;
+}
+
+int pqg_plan_download(pqg_ctx* ctx, const pqg_plan* p, void* values, uint32_t* validity, uint32_t* offsets, uint8_t* chars) {
+    if (!ctx || !p) return fail(ctx, PQG_ERR_ARG, "pqg_plan_download: bad argument");
+    CU(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    if (values && p->d_values) CU(ctx, cudaMemcpyAsync(values, p->d_values, p->n_slots * p->width, cudaMemcpyDeviceToHost, s));
+    if (validity && p->d_validity) CU(ctx, cudaMemcpyAsync(validity, p->d_validity, ((p->n_slots + 31) / 32) * 4, cudaMemcpyDeviceToHost, s));
+    if (offsets && p->d_offsets) CU(ctx, cudaMemcpyAsync(offsets, p->d_offsets, (p->n_slots + p->chunks.size()) * 4, cudaMemcpyDeviceToHost, s));
+    if (chars && p->d_chars && p->chars_size) CU(ctx, cudaMemcpyAsync(chars, p->d_chars, p->chars_size, cudaMemcpyDeviceToHost, s));
+    return PQG_OK;
+}
+
+} // extern "C"
+
+// accessors for the other translation units (regex scan, chunk index)
+namespace pqg {
+DecodeParams plan_params(const pqg_plan* p) { return make_params(p); }
+cudaStream_t ctx_stream(const pqg_ctx* c) { return c->stream; }
+int ctx_sm_count(const pqg_ctx* c) { return c->sm_count; }
+int ctx_device(const pqg_ctx* c) { return c->device; }
+void ctx_add_launches(pqg_ctx* c, uint32_t n) { c->launches += n; }
+int ctx_fail(pqg_ctx* c, int code, const std::string& m) { return fail(c, code, m); }
+bool plan_is_str(const pqg_plan* p) { return p->is_str; }
+bool plan_ran(const pqg_plan* p) { return p->ran; }
+bool plan_any_dict(const pqg_plan* p) { return p->any_dict; }
+uint64_t plan_slots(const pqg_plan* p) { return p->n_slots; }
+const std::vector<pqg_chunk_desc>& plan_chunks(const pqg_plan* p) { return p->chunks; }
+const std::vector<pqg_page_desc>& plan_pages(const pqg_plan* p) { return p->pages; }
+} // namespace pqg

@@ -1,0 +1,574 @@
+// pqg_decode.cu -- sm_100a page-decode kernels (HBM-bound integer/byte work, no tensor cores).
+//
+//   k_dict_prepare   one CTA per column chunk: dictionary page -> aligned value table
+//                    (fixed width) or {start,len} entry table (BYTE_ARRAY).
+//                    Replaces ColumnReader::read_dictionary_page (column_reader.cpp:128-138).
+//   k_decode_fixed   one warp per data page: levels + PLAIN / dictionary values ->
+//                    values[] + validity bits.  Replaces read_data_page
+//                    (column_reader.cpp:140-225) and read_plain_value (:227-268) for
+//                    BOOLEAN / INT32 / INT64 / INT96 / FLOAT / DOUBLE.
+//   k_str_sizes      BYTE_ARRAY pass 1: string bytes per page.
+//   k_str_scan_*     exclusive scans: page bases inside a chunk, chunk bases in the column.
+//   k_str_copy       BYTE_ARRAY pass 2: Arrow-style offsets + chars.
+//
+// Grid sizing: CTAs take contiguous spans of the page table (so a CTA stages a chunk's
+// dictionary once); the grid is a multiple of the SM count when there is enough work.
+#include "pqg_page.cuh"
+
+namespace pqg {
+namespace {
+
+template <int W> struct Elem;
+template <> struct Elem<1> { using T = uint8_t; };
+template <> struct Elem<4> { using T = uint32_t; };
+template <> struct Elem<8> { using T = uint64_t; };
+struct U96 { uint32_t a, b, c; };
+template <> struct Elem<12> { using T = U96; };
+
+template <int W> __device__ __forceinline__ typename Elem<W>::T zero_val();
+template <> __device__ __forceinline__ uint8_t zero_val<1>() { return 0; }
+template <> __device__ __forceinline__ uint32_t zero_val<4>() { return 0; }
+template <> __device__ __forceinline__ uint64_t zero_val<8>() { return 0; }
+template <> __device__ __forceinline__ U96 zero_val<12>() { return U96{0, 0, 0}; }
+
+template <int W> __device__ __forceinline__ typename Elem<W>::T load_plain(const uint8_t* p);
+template <> __device__ __forceinline__ uint8_t load_plain<1>(const uint8_t* p) { return *p != 0; }
+template <> __device__ __forceinline__ uint32_t load_plain<4>(const uint8_t* p) { return ld32u(p); }
+template <> __device__ __forceinline__ uint64_t load_plain<8>(const uint8_t* p) { return ld64u(p); }
+template <> __device__ __forceinline__ U96 load_plain<12>(const uint8_t* p) {
+    return U96{ld32u(p), ld32u(p + 4), ld32u(p + 8)};
+}
+
+// ---------------------------------------------------------------------------------------------
+// dictionary preparation
+// ---------------------------------------------------------------------------------------------
+template <int W>
+__global__ void __launch_bounds__(256) k_dict_prepare(DecodeParams P) {
+    DevChunk& ck = P.chunks[blockIdx.x];
+    if (!ck.has_dict) { if (threadIdx.x == 0) ck.dict_ok_n = 0; return; }
+    const uint8_t* src = P.image + ck.dict_off;
+    uint8_t* dst = P.dict_arena + ck.dict_arena_off;
+    const uint32_t n = ck.dict_n, size = ck.dict_size;
+    if constexpr (W != 0) {
+        // PLAIN fixed width: read_plain_value per entry (column_reader.cpp:229-248,257-264)
+        uint32_t ok = min(n, size / W);
+        if (threadIdx.x == 0) {
+            ck.dict_ok_n = ok;
+            // the reference throws from ByteBuffer::check while reading entry `ok`
+            if (ok < n) report_error(P.err, ck.first_page, PQG_PAGE_DICT_TRUNCATED, ok * W, W, size);
+        }
+        typename Elem<W>::T* out = reinterpret_cast<typename Elem<W>::T*>(dst);
+        for (uint32_t i = threadIdx.x; i < ok; i += blockDim.x) out[i] = load_plain<W>(src + static_cast<size_t>(i) * W);
+    } else {
+        // BYTE_ARRAY: u32 length prefix + bytes (column_reader.cpp:249-253).  Entry table:
+        // {start (byte offset of the chars inside the dictionary payload), len}.
+        // TODO(perf): segment-parallel walk; one lane per dictionary for now.
+        uint2* ent = reinterpret_cast<uint2*>(dst);
+        if (threadIdx.x == 0) {
+            uint32_t pos = 0, k = 0;
+            for (; k < n; k++) {
+                if (static_cast<uint64_t>(pos) + 4 > size) { report_error(P.err, ck.first_page, PQG_PAGE_DICT_TRUNCATED, pos, 4, size); break; }
+                uint32_t len = ld32u(src + pos);
+                if (static_cast<uint64_t>(pos) + 4 + len > size) { report_error(P.err, ck.first_page, PQG_PAGE_DICT_TRUNCATED, pos + 4, len, size); break; }
+                ent[k] = make_uint2(pos + 4, len);
+                pos += 4 + len;
+            }
+            ck.dict_ok_n = k;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// PLAIN, REQUIRED, 4/8-byte values: the page payload IS the value array (shifted by the
+// payload's misalignment).  Straight global->global copy, 16-byte vectors.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 shift_bytes(uint4 a, uint4 b, uint32_t sh) {
+    // bytes sh..sh+15 of the 32-byte pair (a,b); sh is warp-uniform
+    uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint32_t bs = (sh & 3u) * 8u;
+    uint4 r;
+    switch (sh >> 2) {
+        case 0: r.x = __funnelshift_r(w[0], w[1], bs); r.y = __funnelshift_r(w[1], w[2], bs); r.z = __funnelshift_r(w[2], w[3], bs); r.w = __funnelshift_r(w[3], w[4], bs); break;
+        case 1: r.x = __funnelshift_r(w[1], w[2], bs); r.y = __funnelshift_r(w[2], w[3], bs); r.z = __funnelshift_r(w[3], w[4], bs); r.w = __funnelshift_r(w[4], w[5], bs); break;
+        case 2: r.x = __funnelshift_r(w[2], w[3], bs); r.y = __funnelshift_r(w[3], w[4], bs); r.z = __funnelshift_r(w[4], w[5], bs); r.w = __funnelshift_r(w[5], w[6], bs); break;
+        default: r.x = __funnelshift_r(w[3], w[4], bs); r.y = __funnelshift_r(w[4], w[5], bs); r.z = __funnelshift_r(w[5], w[6], bs); r.w = __funnelshift_r(w[6], w[7], bs); break;
+    }
+    return r;
+}
+
+template <int W>
+__device__ __forceinline__ void plain_copy(const DecodeParams& P, uint32_t q, const pqg_page_desc& pd) {
+    const uint32_t l = lane_id();
+    const uint32_t n = pd.num_values;
+    const uint64_t bytes = static_cast<uint64_t>(n) * W;
+    if (bytes > pd.payload_size) {
+        if (l == 0) report_error(P.err, q, PQG_PAGE_TRUNCATED, (pd.payload_size / W) * W, W, pd.payload_size);
+        return;
+    }
+    const uint8_t* src = P.image + pd.payload_off;
+    uint8_t* dst = P.values + pd.out_row_base * W;
+    // head: bring dst to a 16-byte boundary (a whole number of elements)
+    uint32_t head = static_cast<uint32_t>((16u - (reinterpret_cast<uintptr_t>(dst) & 15u)) & 15u);
+    if (head > bytes) head = static_cast<uint32_t>(bytes);
+    using T = typename Elem<W>::T;
+    if (l < head / W) reinterpret_cast<T*>(dst)[l] = load_plain<W>(src + l * W);
+    const uint8_t* s2 = src + head;
+    uint8_t* d2 = dst + head;
+    const uint32_t nvec = static_cast<uint32_t>((bytes - head) >> 4);
+    const uint32_t sh = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(s2) & 15u);
+    const uint8_t* a = s2 - sh;
+    if (sh == 0) {
+#pragma unroll 2
+        for (uint32_t j = l; j < nvec; j += 32) reinterpret_cast<uint4*>(d2)[j] = ldg_nc16(a + 16u * j);
+    } else {
+#pragma unroll 2
+        for (uint32_t j = l; j < nvec; j += 32) {
+            uint4 v0 = *reinterpret_cast<const uint4*>(a + 16u * j);      // cached: the next lane's
+            uint4 v1 = *reinterpret_cast<const uint4*>(a + 16u * j + 16); // v0 is this lane's v1
+            reinterpret_cast<uint4*>(d2)[j] = shift_bytes(v0, v1, sh);
+        }
+    }
+    const uint32_t done = head + (nvec << 4);
+    const uint32_t tail = static_cast<uint32_t>(bytes - done) / W;
+    if (l < tail) reinterpret_cast<T*>(dst + done)[l] = load_plain<W>(src + done + l * W);
+}
+
+// ---------------------------------------------------------------------------------------------
+// fixed-width data pages
+// ---------------------------------------------------------------------------------------------
+template <int W, bool BOOLP>
+__device__ __forceinline__ void decode_fixed_page(const DecodeParams& P, uint32_t q, const DevChunk& ck,
+                                                  const uint8_t* dictp, WarpScratch& ws) {
+    using T = typename Elem<W>::T;
+    const uint32_t l = lane_id();
+    const pqg_page_desc pd = P.pages[q];
+    if (pd.num_values == 0) return;
+    const bool dict_page = (pd.flags & PQG_PAGE_FLAG_DICT) && ck.has_dict;
+    if constexpr ((W == 4 || W == 8) && !BOOLP) {
+        if (!dict_page && ck.max_def <= 0 && ck.max_rep <= 0) { plain_copy<W>(P, q, pd); return; }
+    }
+    PageCtx c;
+    if (!page_begin(P, q, pd, ck, ws, c)) return;
+    const uint8_t* vals = c.pg + c.vals_pos;
+    const uint32_t vavail = c.size - c.vals_pos;
+    const uint32_t T_ = c.wide ? kTileWide : kTileNarrow;
+    const bool single = c.n <= T_;
+    const uint32_t dict_n = ck.dict_ok_n;
+    T* out = reinterpret_cast<T*>(P.values);
+    bool regular = false;
+    uint32_t nn_before = 0;
+    for (uint32_t ts = 0; ts < c.n; ts += T_) {
+        const uint32_t t = min(T_, c.n - ts);
+        uint32_t bad = 0;
+        const uint32_t nn = levels_tile(c.defw, ws, t, ck.max_def, single, &bad);
+        if (bad) { if (l == 0) report_error(P.err, q, bad); return; }
+        if (dict_page) {
+            if (ts == 0 && (single || !c.has_def)) regular = check_regular(c.idxw.s, c.idxw.len, c.bw, single ? nn : c.n);
+            if (!regular) {
+                indices_tile(c.idxw, ws, nn, c.wide, &bad);
+                if (bad) { if (l == 0) report_error(P.err, q, bad); return; }
+                __syncwarp();
+            }
+        } else if (BOOLP) {
+            uint32_t need = (nn_before + nn + 7) >> 3;
+            if (need > vavail) { if (l == 0) report_error(P.err, q, PQG_PAGE_TRUNCATED, c.size, 1, c.size); return; }
+        } else {
+            if (static_cast<uint64_t>(nn_before + nn) * W > vavail) {
+                if (l == 0) report_error(P.err, q, PQG_PAGE_TRUNCATED, c.vals_pos + (vavail / W) * W, W, c.size);
+                return;
+            }
+        }
+        // ---- emit: 32 absolute slots per step, aligned to validity words ----
+        const uint64_t abs0 = pd.out_row_base + ts;
+        const uint64_t gend = abs0 + t;
+        for (uint64_t g = abs0 & ~uint64_t(31); g < gend; g += 32) {
+            const int64_t s = static_cast<int64_t>(g + l) - static_cast<int64_t>(abs0);
+            const bool in = s >= 0 && s < static_cast<int64_t>(t);
+            bool valid = false;
+            uint32_t k = 0;
+            if (in) {
+                uint32_t wv = ws.valid[s >> 5];
+                valid = (wv >> (s & 31)) & 1u;
+                k = ws.rankbase[s >> 5] + __popc(wv & ((1u << (s & 31)) - 1u));
+            }
+            T v = zero_val<W>();
+            if (valid) {
+                if (dict_page) {
+                    uint32_t ix = regular ? regular_index(c.idxw.s, c.bw, nn_before + k) : idx_load(ws.idx, k, c.wide);
+                    if (ix < dict_n) v = reinterpret_cast<const T*>(dictp)[ix];
+                    else valid = false; // out-of-range index -> null (column_reader.cpp:190-194)
+                } else if (BOOLP) {
+                    uint32_t kk = nn_before + k;
+                    if constexpr (W == 1) v = (vals[kk >> 3] >> (kk & 7u)) & 1u;
+                } else {
+                    v = load_plain<W>(vals + static_cast<size_t>(nn_before + k) * W);
+                }
+            }
+            if (in) out[g + l] = v;
+            if (P.validity) {
+                uint32_t m = __ballot_sync(0xffffffffu, valid);
+                if (l == 0) {
+                    if (g >= abs0 && g + 32 <= gend) P.validity[g >> 5] = m;
+                    else if (m) atomicOr(&P.validity[g >> 5], m);
+                }
+            }
+        }
+        nn_before += nn;
+        __syncwarp();
+    }
+}
+
+template <int W, bool BOOLP>
+__global__ void __launch_bounds__(kThreadsPerCta) k_decode_fixed(DecodeParams P, uint32_t dict_smem) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    WarpScratch& ws = reinterpret_cast<WarpScratch*>(smem)[warp_id()];
+    uint8_t* sdict = smem + sizeof(WarpScratch) * kWarpsPerCta;
+    uint32_t p = P.page_begin + blockIdx.x * P.pages_per_cta;
+    const uint32_t p1 = min(P.page_end, p + P.pages_per_cta);
+    while (p < p1) { // one segment per column chunk inside this CTA's span
+        const DevChunk& ck = P.chunks[P.pages[p].chunk_idx];
+        const uint32_t seg_end = min(p1, ck.first_page + ck.n_pages);
+        const uint8_t* dictp = P.dict_arena + ck.dict_arena_off;
+        const uint32_t dbytes = ck.dict_ok_n * W;
+        if (ck.has_dict && dbytes && dbytes <= dict_smem) {
+            const uint4* s4 = reinterpret_cast<const uint4*>(dictp);
+            uint4* d4 = reinterpret_cast<uint4*>(sdict);
+            for (uint32_t i = threadIdx.x; i < (dbytes + 15u) / 16u; i += blockDim.x) d4[i] = s4[i];
+            __syncthreads();
+            dictp = sdict;
+        }
+        for (uint32_t q = p + warp_id(); q < seg_end; q += kWarpsPerCta) decode_fixed_page<W, BOOLP>(P, q, ck, dictp, ws);
+        __syncthreads();
+        p = seg_end;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// BYTE_ARRAY
+// ---------------------------------------------------------------------------------------------
+// Lane 0 walks `cnt` length-prefixed strings starting at byte `pos` of the value section and
+// records each prefix position in ws.idx (u16 when !wide).  Returns the end position in *pos.
+// TODO(perf): candidate-and-verify parallel walk for ASCII pages.
+__device__ __forceinline__ bool walk_strings(const uint8_t* vals, uint32_t vavail, uint32_t* pos_io, uint32_t cnt,
+                                             WarpScratch& ws, bool wide, bool record, uint32_t* epos, uint32_t* eneed) {
+    uint32_t ok = 1, pos = *pos_io;
+    if (lane_id() == 0) {
+        for (uint32_t k = 0; k < cnt; k++) {
+            if (static_cast<uint64_t>(pos) + 4 > vavail) { ok = 0; *epos = pos; *eneed = 4; break; }
+            uint32_t len = ld32u(vals + pos);
+            if (static_cast<uint64_t>(pos) + 4 + len > vavail) { ok = 0; *epos = pos + 4; *eneed = len; break; }
+            if (record) idx_store(ws.idx, k, pos, wide);
+            pos += 4 + len;
+        }
+    }
+    ok = __shfl_sync(0xffffffffu, ok, 0);
+    *pos_io = __shfl_sync(0xffffffffu, pos, 0);
+    *epos = __shfl_sync(0xffffffffu, *epos, 0);
+    *eneed = __shfl_sync(0xffffffffu, *eneed, 0);
+    __syncwarp();
+    return ok != 0;
+}
+
+template <bool COPY>
+__device__ __forceinline__ void decode_str_page(const DecodeParams& P, uint32_t q, const DevChunk& ck, WarpScratch& ws) {
+    const uint32_t l = lane_id();
+    const pqg_page_desc pd = P.pages[q];
+    if (pd.num_values == 0) { if (!COPY && l == 0) P.page_chars[q] = 0; return; }
+    PageCtx c;
+    if (!page_begin(P, q, pd, ck, ws, c)) { if (!COPY && l == 0) P.page_chars[q] = 0; return; }
+    const uint8_t* vals = c.pg + c.vals_pos;
+    const uint32_t vavail = c.size - c.vals_pos;
+    // plain pages keep prefix positions in ws.idx: u16 unless the page is large
+    const bool pwide = !c.dict && c.size > 65535u;
+    const bool wide = c.dict ? c.wide : pwide;
+    const uint32_t T_ = wide ? kTileWide : kTileNarrow;
+    const bool single = c.n <= T_;
+    const uint2* dent = reinterpret_cast<const uint2*>(P.dict_arena + ck.dict_arena_off);
+    const uint8_t* dchars = P.image + ck.dict_off;
+    const uint32_t dict_n = ck.dict_ok_n;
+    uint32_t* offs = COPY ? P.offsets + ck.out_row_base + (&ck - P.chunks) : nullptr; // chunk c owns [row_base + c, ...]
+    uint8_t* chars = COPY ? P.chars + ck.char_base : nullptr;
+    uint64_t page_bytes = 0;                       // running string bytes of this page
+    const uint32_t page_base = COPY ? P.page_char_base[q] : 0;
+    bool regular = false;
+    uint32_t nn_before = 0, wpos = 0;
+    for (uint32_t ts = 0; ts < c.n; ts += T_) {
+        const uint32_t t = min(T_, c.n - ts);
+        uint32_t bad = 0;
+        const uint32_t nn = levels_tile(c.defw, ws, t, ck.max_def, single, &bad);
+        if (bad) { if (l == 0) { report_error(P.err, q, bad); if (!COPY) P.page_chars[q] = 0; } return; }
+        uint32_t tile_pos0 = wpos;
+        if (c.dict) {
+            if (ts == 0 && (single || !c.has_def)) regular = check_regular(c.idxw.s, c.idxw.len, c.bw, single ? nn : c.n);
+            if (!regular) {
+                indices_tile(c.idxw, ws, nn, c.wide, &bad);
+                if (bad) { if (l == 0) { report_error(P.err, q, bad); if (!COPY) P.page_chars[q] = 0; } return; }
+                __syncwarp();
+            }
+        } else {
+            uint32_t epos = 0, eneed = 0;
+            if (!walk_strings(vals, vavail, &wpos, nn, ws, wide, COPY, &epos, &eneed)) {
+                if (l == 0) { report_error(P.err, q, PQG_PAGE_TRUNCATED, c.vals_pos + epos, eneed, c.size); if (!COPY) P.page_chars[q] = 0; }
+                return;
+            }
+        }
+        if (!COPY) {
+            if (c.dict) { // sum the lengths of the referenced dictionary entries
+                uint32_t sum = 0;
+                for (uint32_t k = l; k < nn; k += 32) {
+                    uint32_t ix = regular ? regular_index(c.idxw.s, c.bw, nn_before + k) : idx_load(ws.idx, k, c.wide);
+                    if (ix < dict_n) sum += dent[ix].y;
+                }
+                for (int d = 16; d; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+                page_bytes += sum;
+            } else {
+                page_bytes += (wpos - tile_pos0) - 4ull * nn;
+            }
+            nn_before += nn;
+            __syncwarp();
+            continue;
+        }
+        // ---- COPY: offsets, then chars, 32 slots per step ----
+        const uint64_t slot0 = (pd.out_row_base - ck.out_row_base) + ts; // chunk-relative slot
+        for (uint32_t g = 0; g < t; g += 32) {
+            const uint32_t s = g + l;
+            const bool in = s < t;
+            bool valid = false;
+            uint32_t k = 0;
+            if (in) {
+                uint32_t wv = ws.valid[s >> 5];
+                valid = (wv >> (s & 31)) & 1u;
+                k = ws.rankbase[s >> 5] + __popc(wv & ((1u << (s & 31)) - 1u));
+            }
+            uint32_t len = 0;
+            const uint8_t* sp = nullptr; // source bytes of this lane's string
+            if (valid) {
+                if (c.dict) {
+                    uint32_t ix = regular ? regular_index(c.idxw.s, c.bw, nn_before + k) : idx_load(ws.idx, k, c.wide);
+                    if (ix < dict_n) { uint2 e = dent[ix]; sp = dchars + e.x; len = e.y; }
+                    else valid = false;
+                } else {
+                    uint32_t pp = idx_load(ws.idx, k, wide);
+                    len = ld32u(vals + pp);
+                    sp = vals + pp + 4;
+                }
+            }
+            const uint32_t incl = warp_incl_scan(len);
+            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+            const uint64_t gbase = page_base + page_bytes;          // chunk-relative byte offset of this group
+            const uint32_t myoff = incl - len;                      // group-relative
+            if (in) offs[slot0 + s] = static_cast<uint32_t>(gbase + myoff);
+            if (P.validity) {
+                // validity words are indexed by absolute slot; groups are not word aligned in general
+                uint32_t m = __ballot_sync(0xffffffffu, valid);
+                uint64_t a0 = pd.out_row_base + ts + g;
+                uint32_t sh = static_cast<uint32_t>(a0 & 31u);
+                if (l == 0 && m) {
+                    atomicOr(&P.validity[a0 >> 5], m << sh);
+                    if (sh && (m >> (32u - sh))) atomicOr(&P.validity[(a0 >> 5) + 1], m >> (32u - sh));
+                }
+            }
+            // chars of the group: bytes [0,total) go to dstg; 4 output bytes per lane per step,
+            // each byte finds its owner lane by binary search over the lanes' offsets.
+            if (total) {
+                uint8_t* dstg = chars + gbase;
+                const uint32_t mis = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(dstg) & 3u);
+                const uint32_t nwords = (total + mis + 3u) >> 2;
+                const unsigned long long spl = reinterpret_cast<unsigned long long>(sp);
+                for (uint32_t wbase = 0; wbase < nwords; wbase += 32) {
+                    const uint32_t wj = wbase + l;
+                    const int64_t o0 = static_cast<int64_t>(wj) * 4 - mis; // group byte offset of this word's byte 0
+                    uint32_t word = 0, have = 0;
+                    // owner of byte max(o0,0): last lane with incl-len <= o and len > 0 ... search on incl
+                    uint32_t o = o0 < 0 ? 0u : static_cast<uint32_t>(o0);
+                    // smallest lane L with incl[L] > o
+                    uint32_t lo = 0, hi = 31;
+#pragma unroll
+                    for (int it = 0; it < 5; it++) {
+                        uint32_t mid = (lo + hi) >> 1;
+                        uint32_t im = __shfl_sync(0xffffffffu, incl, mid);
+                        if (im > o) hi = mid; else lo = mid + 1;
+                    }
+                    uint32_t L = lo;
+#pragma unroll
+                    for (int b = 0; b < 4; b++) {
+                        int64_t ob = o0 + b;
+                        bool act = wj < nwords && ob >= 0 && ob < static_cast<int64_t>(total);
+                        // advance the owner while this byte is past its end (all lanes shuffle)
+                        uint32_t iL = __shfl_sync(0xffffffffu, incl, L & 31u);
+                        while (__any_sync(0xffffffffu, act && static_cast<uint32_t>(ob) >= iL)) {
+                            if (act && static_cast<uint32_t>(ob) >= iL) L++;
+                            iL = __shfl_sync(0xffffffffu, incl, L & 31u);
+                        }
+                        uint32_t lenL = __shfl_sync(0xffffffffu, len, L & 31u);
+                        unsigned long long spL = __shfl_sync(0xffffffffu, spl, L & 31u);
+                        if (act) {
+                            uint32_t within = static_cast<uint32_t>(ob) - (iL - lenL);
+                            uint32_t ch = reinterpret_cast<const uint8_t*>(spL)[within];
+                            word |= ch << (8 * b);
+                            have |= 1u << b;
+                        }
+                    }
+                    if (have == 0xFu) *reinterpret_cast<uint32_t*>(dstg + o0) = word;
+                    else {
+#pragma unroll
+                        for (int b = 0; b < 4; b++) if (have & (1u << b)) dstg[o0 + b] = static_cast<uint8_t>(word >> (8 * b));
+                    }
+                }
+            }
+            page_bytes += total;
+        }
+        nn_before += nn;
+        __syncwarp();
+    }
+    if (!COPY) {
+        if (l == 0) {
+            if (page_bytes > 0xffffffffull) { report_error(P.err, q, PQG_PAGE_CHARS_OVERFLOW); page_bytes = 0; }
+            P.page_chars[q] = static_cast<uint32_t>(page_bytes);
+        }
+    } else {
+        // the last page of the chunk closes the Arrow offsets array
+        if (l == 0 && q + 1 == ck.first_page + ck.n_pages)
+            offs[(pd.out_row_base - ck.out_row_base) + c.n] = static_cast<uint32_t>(page_base + page_bytes);
+    }
+}
+
+template <bool COPY>
+__global__ void __launch_bounds__(kThreadsPerCta) k_str_pages(DecodeParams P) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    WarpScratch& ws = reinterpret_cast<WarpScratch*>(smem)[warp_id()];
+    uint32_t p = P.page_begin + blockIdx.x * P.pages_per_cta;
+    const uint32_t p1 = min(P.page_end, p + P.pages_per_cta);
+    for (uint32_t q = p + warp_id(); q < p1; q += kWarpsPerCta) {
+        const DevChunk& ck = P.chunks[P.pages[q].chunk_idx];
+        decode_str_page<COPY>(P, q, ck, ws);
+    }
+}
+
+// per chunk: exclusive scan of page_chars over the chunk's pages; chunk total -> char_base (temp)
+__global__ void __launch_bounds__(1024) k_str_scan_pages(DecodeParams P) {
+    __shared__ uint64_t wsum[32];
+    __shared__ uint64_t carry_s;
+    DevChunk& ck = P.chunks[blockIdx.x];
+    const uint32_t l = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < ck.n_pages; base += 1024) {
+        uint32_t i = base + threadIdx.x;
+        uint64_t v = i < ck.n_pages ? P.page_chars[ck.first_page + i] : 0;
+        uint64_t incl = v;
+        for (int d = 1; d < 32; d <<= 1) { uint64_t t = __shfl_up_sync(0xffffffffu, incl, d); if (l >= (uint32_t)d) incl += t; }
+        if (l == 31) wsum[w] = incl;
+        __syncthreads();
+        if (w == 0) {
+            uint64_t x = wsum[l], xi = x;
+            for (int d = 1; d < 32; d <<= 1) { uint64_t t = __shfl_up_sync(0xffffffffu, xi, d); if (l >= (uint32_t)d) xi += t; }
+            wsum[l] = xi - x;
+        }
+        __syncthreads();
+        uint64_t excl = carry_s + wsum[w] + incl - v;
+        if (i < ck.n_pages) {
+            if (excl + v > 0xffffffffull) { if (excl <= 0xffffffffull) report_error(P.err, ck.first_page + i, PQG_PAGE_CHARS_OVERFLOW); }
+            P.page_char_base[ck.first_page + i] = static_cast<uint32_t>(excl);
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) ck.char_base = carry_s; // chunk total for now
+}
+
+// single block: chunk totals -> exclusive chunk bases; grand total -> *total
+__global__ void k_str_scan_chunks(DecodeParams P, uint64_t* chunk_bases, uint64_t* total) {
+    if (threadIdx.x == 0) {
+        uint64_t acc = 0;
+        for (uint32_t c = 0; c < P.n_chunks; c++) {
+            uint64_t t = P.chunks[c].char_base;
+            P.chunks[c].char_base = acc;
+            chunk_bases[c] = acc;
+            acc += t;
+        }
+        chunk_bases[P.n_chunks] = acc;
+        *total = acc;
+    }
+}
+
+uint32_t grid_for(uint32_t n_pages, int sm_count, uint32_t* pages_per_cta, int ctas_per_sm) {
+    // contiguous spans; aim for ctas_per_sm * SMs CTAs, at least one page per warp and step
+    uint32_t target = static_cast<uint32_t>(sm_count) * ctas_per_sm * 4u;
+    uint32_t per = (n_pages + target - 1) / target;
+    if (per < kWarpsPerCta) per = kWarpsPerCta;
+    *pages_per_cta = per;
+    return (n_pages + per - 1) / per;
+}
+
+} // namespace
+
+size_t decode_smem_bytes(bool with_dict) {
+    return sizeof(WarpScratch) * kWarpsPerCta + (with_dict ? kMaxSmemDictBytes : 0);
+}
+
+cudaError_t launch_dict_prepare(const DecodeParams& p, uint32_t n_chunks, int width, cudaStream_t s) {
+    if (n_chunks == 0) return cudaSuccess;
+    switch (width) {
+        case 0: k_dict_prepare<0><<<n_chunks, 256, 0, s>>>(p); break;
+        case 1: k_dict_prepare<1><<<n_chunks, 256, 0, s>>>(p); break;
+        case 4: k_dict_prepare<4><<<n_chunks, 256, 0, s>>>(p); break;
+        case 8: k_dict_prepare<8><<<n_chunks, 256, 0, s>>>(p); break;
+        case 12: k_dict_prepare<12><<<n_chunks, 256, 0, s>>>(p); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+template <int W, bool BOOLP>
+static cudaError_t launch_fixed_t(DecodeParams p, bool with_dict, int sm_count, cudaStream_t s) {
+    const size_t smem = decode_smem_bytes(with_dict);
+    static bool attr_set[2] = {false, false};
+    if (!attr_set[with_dict]) {
+        cudaError_t e = cudaFuncSetAttribute(k_decode_fixed<W, BOOLP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             static_cast<int>(decode_smem_bytes(true)));
+        if (e != cudaSuccess) return e;
+        attr_set[with_dict] = true;
+    }
+    uint32_t n = p.page_end - p.page_begin;
+    if (n == 0) return cudaSuccess;
+    uint32_t grid = grid_for(n, sm_count, &p.pages_per_cta, with_dict ? 3 : 5);
+    k_decode_fixed<W, BOOLP><<<grid, kThreadsPerCta, smem, s>>>(p, with_dict ? kMaxSmemDictBytes : 0);
+    return cudaGetLastError();
+}
+
+// `boolean_plain`: BOOLEAN chunks (PLAIN pages are bit-packed; dictionary entries are bytes).
+cudaError_t launch_decode_fixed(const DecodeParams& p, int width, bool boolean_plain, int sm_count, cudaStream_t s) {
+    // dictionary staging is only worth its shared memory when some chunk has one
+    bool with_dict = p.dict_arena != nullptr;
+    if (boolean_plain) return launch_fixed_t<1, true>(p, with_dict, sm_count, s);
+    switch (width) {
+        case 4: return launch_fixed_t<4, false>(p, with_dict, sm_count, s);
+        case 8: return launch_fixed_t<8, false>(p, with_dict, sm_count, s);
+        case 12: return launch_fixed_t<12, false>(p, with_dict, sm_count, s);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+template <bool COPY>
+static cudaError_t launch_str_t(DecodeParams p, int sm_count, cudaStream_t s) {
+    const size_t smem = decode_smem_bytes(false);
+    uint32_t n = p.page_end - p.page_begin;
+    if (n == 0) return cudaSuccess;
+    uint32_t grid = grid_for(n, sm_count, &p.pages_per_cta, 5);
+    k_str_pages<COPY><<<grid, kThreadsPerCta, smem, s>>>(p);
+    return cudaGetLastError();
+}
+cudaError_t launch_str_sizes(const DecodeParams& p, int sm_count, cudaStream_t s) { return launch_str_t<false>(p, sm_count, s); }
+cudaError_t launch_str_copy(const DecodeParams& p, int sm_count, cudaStream_t s) { return launch_str_t<true>(p, sm_count, s); }
+
+// total_chars: device pointer to [n_chunks + 1 chunk bases][grand total]
+cudaError_t launch_str_scan(const DecodeParams& p, uint64_t* bases_and_total, cudaStream_t s) {
+    if (p.n_chunks == 0) return cudaSuccess;
+    k_str_scan_pages<<<p.n_chunks, 1024, 0, s>>>(p);
+    k_str_scan_chunks<<<1, 32, 0, s>>>(p, bases_and_total, bases_and_total + p.n_chunks + 1);
+    return cudaGetLastError();
+}
+
+} // namespace pqg

@@ -1,0 +1,392 @@
+// pqg_page.cuh -- warp-level building blocks shared by every page kernel.
+//
+// One warp owns one data page.  The page payload (<= kSlotBytes) is staged into the warp's
+// shared-memory slot as an exact byte image (16-byte aligned source rounded down, so the
+// page starts `payload_off & 15` bytes into the slot); larger pages are read in place from
+// global memory through the same code (generic pointers).
+//
+// Replaces, per page: read_data_page's level / index decoding
+// (reference src/reader/column_reader.cpp:143-182) and RleDecoder::get_batch
+// (reference include/reader/rle_decoder.hpp:17-95), restated as
+//   run discovery  -> a table of runs (lane 0 walks headers; two regular layouts are
+//                     recognised in parallel and need no walk at all),
+//   run expansion  -> one lane per run (long RLE runs: whole warp),
+//   slot emission  -> one lane per output slot, 32 slots per step, coalesced stores.
+#pragma once
+#include "pqg_internal.h"
+
+namespace pqg {
+
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
+__device__ __forceinline__ uint32_t warp_id() { return threadIdx.x >> 5; }
+
+// ---- unaligned little-endian loads built from aligned 32-bit words ---------------------
+// (valid for shared and global generic addresses; may touch up to 8 bytes past the field:
+// the shared slot and the image are padded for that)
+__device__ __forceinline__ uint32_t ld32u(const uint8_t* p) {
+    uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(a & ~uintptr_t(3));
+    return __funnelshift_r(q[0], q[1], static_cast<uint32_t>(a & 3) * 8);
+}
+__device__ __forceinline__ uint64_t ld64u(const uint8_t* p) {
+    uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(a & ~uintptr_t(3));
+    uint32_t sh = static_cast<uint32_t>(a & 3) * 8;
+    uint32_t w0 = q[0], w1 = q[1], w2 = q[2];
+    return (static_cast<uint64_t>(__funnelshift_r(w1, w2, sh)) << 32) | __funnelshift_r(w0, w1, sh);
+}
+// bw (0..32) bits at bit offset `bit` from base, LSB first (rle_decoder.hpp:55-65)
+__device__ __forceinline__ uint32_t ldbits(const uint8_t* base, uint32_t bit, uint32_t bw) {
+    uintptr_t a = reinterpret_cast<uintptr_t>(base + (bit >> 3));
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(a & ~uintptr_t(3));
+    uint32_t sh = static_cast<uint32_t>(a & 3) * 8 + (bit & 7); // 0..31, sh + bw <= 63
+    uint32_t v = __funnelshift_r(q[0], q[1], sh);
+    return bw >= 32 ? v : (v & ((1u << bw) - 1u));
+}
+// same, but bytes at or past `avail` read as zero (slow; only for runs that overhang)
+__device__ __noinline__ uint32_t ldbits_bounded(const uint8_t* base, uint32_t bit, uint32_t bw, uint32_t avail) {
+    uint64_t acc = 0;
+    uint32_t b0 = bit >> 3;
+    for (uint32_t i = 0; i < 5; i++) {
+        uint32_t b = b0 + i;
+        uint64_t byte = b < avail ? base[b] : 0;
+        acc |= byte << (8 * i);
+    }
+    acc >>= (bit & 7);
+    return bw >= 32 ? static_cast<uint32_t>(acc) : (static_cast<uint32_t>(acc) & ((1u << bw) - 1u));
+}
+
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
+    uint32_t l = lane_id();
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, v, d);
+        if (l >= static_cast<uint32_t>(d)) v += t;
+    }
+    return v;
+}
+
+__device__ __forceinline__ uint4 ldg_nc16(const uint8_t* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
+// ---- errors ------------------------------------------------------------------------------
+__device__ __forceinline__ void report_error(DevErr* e, uint32_t page, uint32_t code,
+                                             uint32_t pos = 0, uint32_t need = 0, uint32_t size = 0) {
+    // called by one lane
+    atomicAdd(&e->count, 1u);
+    unsigned long long key = (static_cast<unsigned long long>(page) << 32) | code;
+    unsigned long long old = atomicMin(&e->key, key);
+    if (key < old) { e->d_pos = pos; e->d_need = need; e->d_size = size; __threadfence(); e->d_page = page; }
+}
+
+// ---- per-warp scratch ----------------------------------------------------------------------
+struct __align__(16) WarpScratch {
+    uint8_t slot[kSlotAlloc];
+    uint32_t idx[kIdxWords];
+    uint32_t valid[32];
+    uint32_t rankbase[32];
+    uint32_t run_start[32];
+    uint32_t run_count[32]; // bit 31: literal (bit-packed) piece
+    uint32_t run_val[32];   // RLE value, or bit offset of the literal piece
+    uint32_t nruns;
+    uint32_t batch_total;
+    uint32_t pad[2];
+};
+
+// ---- run discovery: the sequential header walk (lane 0) ------------------------------------
+struct Walker {
+    const uint8_t* s;  // stream bytes
+    uint32_t len;      // header parsing bound (RleDecoder::size_)
+    uint32_t avail;    // bytes readable behind s (up to the page end)
+    uint32_t pos, bw;
+    uint32_t rem, lit, val, bit, next_pos;
+    uint32_t bad;
+};
+
+__device__ __forceinline__ void walker_init(Walker& w, const uint8_t* s, uint32_t len, uint32_t avail, uint32_t bw) {
+    w.s = s; w.len = len; w.avail = avail; w.pos = 0; w.bw = bw;
+    w.rem = 0; w.lit = 0; w.val = 0; w.bit = 0; w.next_pos = 0; w.bad = 0;
+}
+
+// Lane 0: append up to 32 run pieces covering `want` values to the scratch table.
+// Literal pieces are capped at 32 values so that one lane expands one piece.
+__device__ __forceinline__ void walker_fill(Walker& w, WarpScratch& ws, uint32_t want) {
+    uint32_t n = 0, produced = 0;
+    const uint8_t* s = w.s;
+    while (n < 32 && produced < want) {
+        if (w.rem == 0) {
+            if (w.pos >= w.len) { // stream exhausted: remaining outputs are 0 (rle_decoder.hpp:21-24)
+                ws.run_start[n] = produced; ws.run_count[n] = want - produced; ws.run_val[n] = 0;
+                n++; produced = want;
+                break;
+            }
+            uint32_t ind = 0, shift = 0;
+            while (w.pos < w.len) { // read_varint32 (rle_decoder.hpp:76-86)
+                uint32_t b = s[w.pos++];
+                if (shift < 32) ind |= (b & 0x7Fu) << shift;
+                if (!(b & 0x80u)) break;
+                shift += 7;
+            }
+            if (ind & 1u) {
+                w.rem = (ind >> 1) * 8u; w.lit = 1; w.bit = w.pos * 8u;
+                w.next_pos = w.pos + static_cast<uint32_t>((static_cast<uint64_t>(w.rem) * w.bw + 7) >> 3);
+            } else {
+                w.rem = ind >> 1; w.lit = 0;
+                uint32_t nb = (w.bw + 7) >> 3, v = 0;
+                for (uint32_t i = 0; i < nb && w.pos < w.len; i++) { // value bytes are not masked (:88-95)
+                    if (i < 4) v |= static_cast<uint32_t>(s[w.pos]) << (8 * i);
+                    w.pos++;
+                }
+                w.val = v;
+            }
+            if (w.rem == 0) { w.bad = PQG_PAGE_BAD_RUN; break; } // reference: undefined behaviour
+        }
+        uint32_t take = min(w.rem, want - produced);
+        if (w.lit) take = min(take, 32u);
+        ws.run_start[n] = produced;
+        ws.run_count[n] = take | (w.lit << 31);
+        ws.run_val[n] = w.lit ? w.bit : w.val;
+        n++; produced += take; w.rem -= take;
+        if (w.lit) { w.bit += take * w.bw; if (w.rem == 0) w.pos = w.next_pos; }
+    }
+    ws.nruns = n;
+    ws.batch_total = produced;
+}
+
+__device__ __forceinline__ void set_bits_range(uint32_t* words, uint32_t start, uint32_t cnt) {
+    uint32_t end = start + cnt; // cnt > 0
+    uint32_t w0 = start >> 5, w1 = (end - 1) >> 5;
+    for (uint32_t w = w0; w <= w1; w++) {
+        uint32_t lo = (w == w0) ? (start & 31u) : 0u;
+        uint32_t hi = (w == w1) ? (((end - 1) & 31u) + 1u) : 32u;
+        uint32_t m = (hi == 32u ? 0xffffffffu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u);
+        atomicOr(&words[w], m);
+    }
+}
+__device__ __forceinline__ void set_bits_word(uint32_t* words, uint32_t start, uint32_t m) {
+    if (!m) return;
+    uint32_t sh = start & 31u;
+    atomicOr(&words[start >> 5], m << sh);
+    if (sh && (m >> (32u - sh))) atomicOr(&words[(start >> 5) + 1], m >> (32u - sh));
+}
+
+// level >= max_def means "value present" (reference tests def < max_def for null)
+__device__ __forceinline__ bool level_present(uint32_t lv, int max_def) {
+    return static_cast<int>(static_cast<int16_t>(static_cast<uint16_t>(lv))) >= max_def;
+}
+
+// Decode the validity of the next t (<= 1024) slots into ws.valid / ws.rankbase.
+// Returns the number of present values in the tile; *bad receives walker errors.
+__device__ __forceinline__ uint32_t levels_tile(Walker& w, WarpScratch& ws, uint32_t t, int max_def,
+                                                bool first_single_tile, uint32_t* bad) {
+    const uint32_t l = lane_id();
+    if (max_def <= 0) {
+        uint32_t lo = l * 32u;
+        uint32_t m = (lo >= t) ? 0u : ((t - lo >= 32u) ? 0xffffffffu : ((1u << (t - lo)) - 1u));
+        ws.valid[l] = m;
+        ws.rankbase[l] = lo < t ? lo : t;
+        __syncwarp();
+        return t;
+    }
+    ws.valid[l] = 0;
+    __syncwarp();
+    bool done = false;
+    // Regular layout: every run is <varint < 128><1 value byte>, i.e. RLE runs shorter than
+    // 64 with a 1-byte level -- what the reference writer emits for scattered nulls
+    // (src/writer/parquet_writer.cpp:103-135).  Verified in parallel (by induction over the
+    // even bytes), then expanded with one lane per run and no sequential walk.
+    if (first_single_tile && w.bw <= 8 && w.len >= 2 && !(w.len & 1u) && w.len <= w.avail) {
+        const uint8_t* s = w.s;
+        uint32_t nr = w.len >> 1;
+        bool ok = true;
+        for (uint32_t r = l; r < nr; r += 32) { uint32_t b = s[2 * r]; ok = ok && ((b & 0x81u) == 0u) && b != 0u; }
+        if (__all_sync(0xffffffffu, ok)) {
+            uint32_t carry = 0;
+            for (uint32_t base = 0; base < nr && carry < t; base += 32) {
+                uint32_t r = base + l;
+                uint32_t cnt = 0, val = 0;
+                if (r < nr) { cnt = s[2 * r] >> 1; val = s[2 * r + 1]; }
+                uint32_t incl = warp_incl_scan(cnt);
+                uint32_t start = carry + incl - cnt;
+                if (cnt && start < t && level_present(val, max_def)) set_bits_range(ws.valid, start, min(cnt, t - start));
+                carry += __shfl_sync(0xffffffffu, incl, 31);
+            }
+            w.pos = w.len; // consumed (a short stream leaves the remaining slots null)
+            done = true;
+        }
+    }
+    uint32_t produced = 0;
+    uint32_t bw = __shfl_sync(0xffffffffu, w.bw, 0);
+    uint32_t avail = __shfl_sync(0xffffffffu, w.avail, 0);
+    unsigned long long sp = __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(w.s), 0);
+    const uint8_t* s = reinterpret_cast<const uint8_t*>(sp);
+    while (!done && produced < t) {
+        if (l == 0) walker_fill(w, ws, t - produced);
+        __syncwarp();
+        uint32_t nruns = ws.nruns, total = ws.batch_total;
+        uint32_t wbad = __shfl_sync(0xffffffffu, w.bad, 0);
+        if (wbad) { *bad = wbad; return 0; }
+        if (l < nruns) {
+            uint32_t rc = ws.run_count[l], start = produced + ws.run_start[l], v = ws.run_val[l];
+            uint32_t cnt = rc & 0x7fffffffu;
+            if (!(rc >> 31)) {
+                if (cnt && level_present(v, max_def)) set_bits_range(ws.valid, start, cnt);
+            } else if (cnt) {
+                uint32_t m = 0;
+                bool inb = ((static_cast<uint64_t>(v) + static_cast<uint64_t>(cnt) * bw + 7) >> 3) <= avail;
+                if (inb && bw == 1 && max_def == 1) {
+                    m = ldbits(s, v, cnt); // the packed bits ARE the validity bits
+                } else {
+                    for (uint32_t j = 0; j < cnt; j++) {
+                        uint32_t lv = inb ? ldbits(s, v + j * bw, bw) : ldbits_bounded(s, v + j * bw, bw, avail);
+                        if (level_present(lv, max_def)) m |= 1u << j;
+                    }
+                }
+                set_bits_word(ws.valid, start, m);
+            }
+        }
+        produced += total;
+        __syncwarp();
+    }
+    __syncwarp();
+    uint32_t c = __popc(ws.valid[l]);
+    uint32_t incl = warp_incl_scan(c);
+    ws.rankbase[l] = incl - c;
+    __syncwarp();
+    return __shfl_sync(0xffffffffu, incl, 31);
+}
+
+__device__ __forceinline__ void idx_store(uint32_t* buf, uint32_t k, uint32_t v, bool wide) {
+    if (wide) buf[k] = v;
+    else reinterpret_cast<uint16_t*>(buf)[k] = static_cast<uint16_t>(v);
+}
+__device__ __forceinline__ uint32_t idx_load(const uint32_t* buf, uint32_t k, bool wide) {
+    return wide ? buf[k] : static_cast<uint32_t>(reinterpret_cast<const uint16_t*>(buf)[k]);
+}
+
+// Decode the next `cnt` dictionary indices of the stream into ws.idx[0..cnt).
+// `wide` = indices may need more than 16 bits (bw > 16): cnt <= 512, else cnt <= 1024.
+__device__ __forceinline__ void indices_tile(Walker& w, WarpScratch& ws, uint32_t cnt_total, bool wide, uint32_t* bad) {
+    const uint32_t l = lane_id();
+    uint32_t produced = 0;
+    uint32_t bw = __shfl_sync(0xffffffffu, w.bw, 0);
+    uint32_t avail = __shfl_sync(0xffffffffu, w.avail, 0);
+    unsigned long long sp = __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(w.s), 0);
+    const uint8_t* s = reinterpret_cast<const uint8_t*>(sp);
+    while (produced < cnt_total) {
+        if (l == 0) walker_fill(w, ws, cnt_total - produced);
+        __syncwarp();
+        uint32_t nruns = ws.nruns, total = ws.batch_total;
+        uint32_t wbad = __shfl_sync(0xffffffffu, w.bad, 0);
+        if (wbad) { *bad = wbad; return; }
+        uint32_t rc = 0, start = 0, v = 0;
+        if (l < nruns) { rc = ws.run_count[l]; start = produced + ws.run_start[l]; v = ws.run_val[l]; }
+        uint32_t cnt = rc & 0x7fffffffu;
+        bool lit = rc >> 31;
+        if (cnt && lit) {
+            bool inb = ((static_cast<uint64_t>(v) + static_cast<uint64_t>(cnt) * bw + 7) >> 3) <= avail;
+            for (uint32_t j = 0; j < cnt; j++) {
+                uint32_t x = inb ? ldbits(s, v + j * bw, bw) : ldbits_bounded(s, v + j * bw, bw, avail);
+                idx_store(ws.idx, start + j, x, wide);
+            }
+        } else if (cnt && cnt <= 32) {
+            for (uint32_t j = 0; j < cnt; j++) idx_store(ws.idx, start + j, v, wide);
+        }
+        // long RLE runs: the whole warp fills them
+        uint32_t longm = __ballot_sync(0xffffffffu, cnt > 32 && !lit);
+        while (longm) {
+            int r = __ffs(longm) - 1;
+            longm &= longm - 1;
+            uint32_t rs = __shfl_sync(0xffffffffu, start, r);
+            uint32_t rn = __shfl_sync(0xffffffffu, cnt, r);
+            uint32_t rv = __shfl_sync(0xffffffffu, v, r);
+            for (uint32_t j = l; j < rn; j += 32) idx_store(ws.idx, rs + j, rv, wide);
+        }
+        produced += total;
+        __syncwarp();
+    }
+}
+
+// All runs are single bit-packed groups "03 <bw bytes>" (what RleBpEncoder emits for data
+// without 4-fold repeats, include/writer/rle_bp_encoder.hpp:93-98): group g starts at byte
+// g * (1 + bw).  Verified in parallel; then every lane can address its own value directly.
+__device__ __forceinline__ bool check_regular(const uint8_t* s, uint32_t len, uint32_t bw, uint32_t count) {
+    if (count == 0) return true;
+    uint32_t groups = (count + 7) >> 3;
+    if (static_cast<uint64_t>(groups) * (1u + bw) > len) return false;
+    bool ok = true;
+    for (uint32_t g = lane_id(); g < groups; g += 32) ok = ok && (s[g * (1u + bw)] == 0x03u);
+    return __all_sync(0xffffffffu, ok);
+}
+__device__ __forceinline__ uint32_t regular_index(const uint8_t* s, uint32_t bw, uint32_t k) {
+    uint32_t g = k >> 3;
+    return ldbits(s, ((g * (1u + bw) + 1u) << 3) + (k & 7u) * bw, bw);
+}
+
+// ---- page prolog -----------------------------------------------------------------------------
+struct PageCtx {
+    const uint8_t* pg;   // payload bytes (shared slot or global)
+    uint32_t size;
+    uint32_t n;          // num_values (level entries)
+    uint32_t vals_pos;   // byte position of the value section inside the payload
+    uint32_t bw;         // dictionary index bit width
+    bool dict;           // indices into the chunk dictionary
+    bool has_def;
+    bool wide;
+    Walker defw, idxw;
+};
+
+// Stage the payload and parse [def levels][rep levels][bit width] like read_data_page
+// (column_reader.cpp:143-182).  Returns false (after reporting) when the page is unusable.
+__device__ __forceinline__ bool page_begin(const DecodeParams& P, uint32_t q, const pqg_page_desc& pd,
+                                           const DevChunk& ck, WarpScratch& ws, PageCtx& c) {
+    const uint32_t l = lane_id();
+    c.size = pd.payload_size;
+    c.n = pd.num_values;
+    c.dict = (pd.flags & PQG_PAGE_FLAG_DICT) && ck.has_dict;
+    c.has_def = ck.max_def > 0;
+    const uint8_t* src = P.image + pd.payload_off;
+    if (c.size <= static_cast<uint32_t>(kSlotBytes)) {
+        uint32_t shift = static_cast<uint32_t>(pd.payload_off & 15u);
+        const uint8_t* a = src - shift;
+        uint32_t nvec = (shift + c.size + 15u) >> 4;
+        uint4* dst = reinterpret_cast<uint4*>(ws.slot);
+        for (uint32_t j = l; j < nvec; j += 32) dst[j] = ldg_nc16(a + 16u * j);
+        __syncwarp();
+        c.pg = ws.slot + shift;
+    } else {
+        c.pg = src;
+    }
+    uint32_t pos = 0;
+    if (c.has_def) {
+        if (c.size < 4) { if (l == 0) report_error(P.err, q, PQG_PAGE_TRUNCATED, 0, 4, c.size); return false; }
+        uint32_t def_len = ld32u(c.pg);
+        if (def_len > c.size - 4) { if (l == 0) report_error(P.err, q, PQG_PAGE_TRUNCATED, 4, def_len, c.size); return false; }
+        walker_init(c.defw, c.pg + 4, def_len, c.size - 4, ck.def_bw);
+        pos = 4 + def_len;
+    }
+    if (ck.max_rep > 0) { // decoded by the reference, then unused (:157-164): skipped here
+        if (c.size - pos < 4) { if (l == 0) report_error(P.err, q, PQG_PAGE_TRUNCATED, pos, 4, c.size); return false; }
+        uint32_t rep_len = ld32u(c.pg + pos);
+        pos += 4;
+        if (rep_len > c.size - pos) { if (l == 0) report_error(P.err, q, PQG_PAGE_TRUNCATED, pos, rep_len, c.size); return false; }
+        pos += rep_len;
+    }
+    c.bw = 0;
+    if (c.dict) {
+        if (pos >= c.size) { if (l == 0) report_error(P.err, q, PQG_PAGE_TRUNCATED, pos, 1, c.size); return false; }
+        c.bw = c.pg[pos];
+        pos++;
+        if (c.bw > 32) { if (l == 0) report_error(P.err, q, PQG_PAGE_BAD_BIT_WIDTH, pos, c.bw, c.size); return false; }
+        walker_init(c.idxw, c.pg + pos, c.size - pos, c.size - pos, c.bw);
+    }
+    c.vals_pos = pos;
+    c.wide = c.dict && c.bw > 16;
+    return true;
+}
+
+} // namespace pqg

@@ -1,0 +1,291 @@
+// pqg_reader_c.cpp -- extern "C" surface of the host reader (include/pqg_reader.h).
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "pq_reader.hpp"
+#include "pq_scan.hpp"
+#include "pqg_reader.h"
+
+using namespace pqg;
+
+struct pqr_reader { ParquetReader r; };
+
+static thread_local std::string g_err;
+
+template <typename F>
+static auto guarded(F&& f, decltype(f()) on_error) -> decltype(f()) {
+    try { return f(); }
+    catch (const std::exception& e) { g_err = e.what(); return on_error; }
+    catch (...) { g_err = "unknown error"; return on_error; }
+}
+
+static void dump_values(const std::vector<Value>& v, pqr_valdump* out) {
+    int64_t n = static_cast<int64_t>(v.size());
+    out->n = n;
+    out->is_null = static_cast<uint8_t*>(std::calloc(n + 1, 1));
+    out->vidx = static_cast<uint8_t*>(std::calloc(n + 1, 1));
+    out->fixed = static_cast<uint64_t*>(std::calloc(n + 1, 8));
+    out->str_off = static_cast<uint64_t*>(std::calloc(n + 1, 8));
+    uint64_t total = 0;
+    for (const Value& x : v) if (x.data.index() == 5) total += std::get<std::string>(x.data).size();
+    out->chars = static_cast<uint8_t*>(std::malloc(total + 1));
+    out->chars_len = static_cast<int64_t>(total);
+    uint64_t pos = 0;
+    for (int64_t i = 0; i < n; i++) {
+        const Value& x = v[i];
+        out->is_null[i] = x.is_null;
+        out->vidx[i] = static_cast<uint8_t>(x.data.index());
+        out->str_off[i] = pos;
+        uint64_t bits = 0;
+        switch (x.data.index()) {
+            case 0: bits = std::get<bool>(x.data); break;
+            case 1: { uint32_t u; std::memcpy(&u, &std::get<int32_t>(x.data), 4); bits = u; break; }
+            case 2: std::memcpy(&bits, &std::get<int64_t>(x.data), 8); break;
+            case 3: { uint32_t u; std::memcpy(&u, &std::get<float>(x.data), 4); bits = u; break; }
+            case 4: std::memcpy(&bits, &std::get<double>(x.data), 8); break;
+            case 5: {
+                const std::string& s = std::get<std::string>(x.data);
+                std::memcpy(out->chars + pos, s.data(), s.size());
+                pos += s.size();
+                break;
+            }
+        }
+        out->fixed[i] = bits;
+    }
+    out->str_off[n] = pos;
+}
+
+extern "C" {
+
+const char* pqr_last_error(void) { return g_err.c_str(); }
+
+pqr_reader* pqr_open(const char* path, int device) {
+    return guarded([&]() -> pqr_reader* {
+        auto* h = new pqr_reader();
+        h->r.set_device(device);
+        if (!h->r.open(path)) { g_err = h->r.open_error(); delete h; return nullptr; }
+        return h;
+    }, nullptr);
+}
+
+pqr_reader* pqr_open_memory(const uint8_t* data, uint64_t size, int device) {
+    return guarded([&]() -> pqr_reader* {
+        auto* h = new pqr_reader();
+        h->r.set_device(device);
+        if (!h->r.open_memory(data, size)) { g_err = h->r.open_error(); delete h; return nullptr; }
+        return h;
+    }, nullptr);
+}
+
+void pqr_close(pqr_reader* r) { delete r; }
+
+int64_t pqr_num_rows(const pqr_reader* r) { return r->r.num_rows(); }
+int64_t pqr_num_row_groups(const pqr_reader* r) { return static_cast<int64_t>(r->r.num_row_groups()); }
+int64_t pqr_num_columns(const pqr_reader* r) { return static_cast<int64_t>(r->r.num_columns()); }
+int64_t pqr_num_pages(const pqr_reader* r) { return static_cast<int64_t>(r->r.num_pages()); }
+int64_t pqr_row_group_num_rows(const pqr_reader* r, int rg) {
+    return guarded([&]() -> int64_t { return r->r.metadata().row_groups.at(rg).num_rows; }, -1);
+}
+double pqr_page_scan_seconds(const pqr_reader* r) { return r->r.page_scan_seconds(); }
+uint64_t pqr_file_size(const pqr_reader* r) { return r->r.file_size(); }
+
+int pqr_column_info(const pqr_reader* r, int col, pqr_colinfo* out) {
+    return guarded([&]() -> int {
+        const ColumnInfo& ci = r->r.column(static_cast<size_t>(col));
+        std::memset(out, 0, sizeof(*out));
+        std::strncpy(out->name, ci.name.c_str(), sizeof(out->name) - 1);
+        out->type = static_cast<int32_t>(ci.type);
+        out->column_index = ci.column_index;
+        out->max_def_level = ci.max_def_level;
+        out->max_rep_level = ci.max_rep_level;
+        out->repetition = ci.repetition ? static_cast<int32_t>(*ci.repetition) : -1;
+        out->converted = ci.converted_type ? static_cast<int32_t>(*ci.converted_type) : -1;
+        return 0;
+    }, -1);
+}
+
+int pqr_find_column(const pqr_reader* r, const char* name) { return r->r.find_column(name); }
+
+int pqr_schema_string(const pqr_reader* r, char* buf, int64_t cap) {
+    std::string s = r->r.schema_string();
+    if (static_cast<int64_t>(s.size()) + 1 > cap) return -1;
+    std::memcpy(buf, s.c_str(), s.size() + 1);
+    return static_cast<int>(s.size());
+}
+
+int64_t pqr_page_index(const pqr_reader* r, pqr_page_entry* out, int64_t cap) {
+    int64_t n = static_cast<int64_t>(r->r.num_pages());
+    for (int64_t i = 0; i < n && i < cap; i++) {
+        const PageIndexEntry& e = r->r.page_index_entry(static_cast<size_t>(i));
+        out[i] = {e.data_offset, e.data_size, e.row_group_idx, e.column_idx};
+    }
+    return n;
+}
+
+int64_t pqr_read_page_data(const pqr_reader* r, int64_t id, uint8_t* buf, int64_t cap) {
+    return guarded([&]() -> int64_t {
+        auto d = r->r.read_page_data(static_cast<size_t>(id));
+        if (static_cast<int64_t>(d.size()) > cap) { g_err = "buffer too small"; return -2; }
+        std::memcpy(buf, d.data(), d.size());
+        return static_cast<int64_t>(d.size());
+    }, -1);
+}
+
+int64_t pqr_read_pages_chunk(const pqr_reader* r, int64_t s, int64_t e, int64_t max_bytes, uint8_t* buf, int64_t cap) {
+    return guarded([&]() -> int64_t {
+        auto d = r->r.read_pages_chunk(static_cast<size_t>(s), static_cast<size_t>(e), static_cast<size_t>(max_bytes));
+        if (static_cast<int64_t>(d.size()) > cap) { g_err = "buffer too small"; return -2; }
+        std::memcpy(buf, d.data(), d.size());
+        return static_cast<int64_t>(d.size());
+    }, -1);
+}
+
+int pqr_read_column_by_idx(pqr_reader* r, int rg, int col, pqr_valdump* out) {
+    return guarded([&]() -> int { dump_values(r->r.read_column_by_idx(rg, col), out); return 0; }, -1);
+}
+int pqr_read_column(pqr_reader* r, const char* name, pqr_valdump* out) {
+    return guarded([&]() -> int { dump_values(r->r.read_column(name), out); return 0; }, -1);
+}
+int pqr_read_column_rg(pqr_reader* r, const char* name, int64_t rg, pqr_valdump* out) {
+    return guarded([&]() -> int { dump_values(r->r.read_column(name, static_cast<size_t>(rg)), out); return 0; }, -1);
+}
+
+// Drives the mirror of ColumnReader exactly like the reference's README shows: a
+// read_range callback over the reader plus the chunk's metadata.
+int pqr_read_pages(pqr_reader* r, int rg, int col, pqr_pagedump* out) {
+    return guarded([&]() -> int {
+        ParquetReader& pr = r->r;
+        const ColumnInfo& ci = pr.column(static_cast<size_t>(col));
+        const ColumnChunk& chunk = pr.metadata().row_groups.at(rg).columns.at(ci.column_index);
+        ColumnReader cr([&pr](size_t o, size_t l) { return pr.read_range(o, l); }, chunk, ci.type,
+                        ci.max_def_level, ci.max_rep_level);
+        std::vector<PageResult> pages = cr.read_pages();
+        int64_t np = static_cast<int64_t>(pages.size());
+        out->n_pages = np;
+        out->page_num = static_cast<int32_t*>(std::calloc(np + 1, 4));
+        out->page_type = static_cast<int32_t*>(std::calloc(np + 1, 4));
+        out->num_values = static_cast<int32_t*>(std::calloc(np + 1, 4));
+        out->first_value = static_cast<int64_t*>(std::calloc(np + 1, 8));
+        std::vector<Value> all;
+        for (int64_t p = 0; p < np; p++) {
+            out->page_num[p] = pages[p].page_num;
+            out->page_type[p] = static_cast<int32_t>(pages[p].type);
+            out->num_values[p] = pages[p].num_values;
+            out->first_value[p] = static_cast<int64_t>(all.size());
+            for (auto& v : pages[p].values) all.push_back(std::move(v));
+        }
+        out->first_value[np] = static_cast<int64_t>(all.size());
+        dump_values(all, &out->values);
+        return 0;
+    }, -1);
+}
+
+int pqr_string_iterator_dump(pqr_reader* r, const char* name, pqr_strdump* out) {
+    return guarded([&]() -> int {
+        StringColumnIterator it = r->r.column_iterator(name);
+        std::vector<uint64_t> pos, off;
+        std::string chars;
+        off.push_back(0);
+        while (it.has_next()) {
+            auto [p, len, ptr] = it.next();
+            pos.push_back(p);
+            chars.append(ptr, len);
+            off.push_back(chars.size());
+        }
+        out->n = static_cast<int64_t>(pos.size());
+        out->pos = static_cast<uint64_t*>(std::malloc((pos.size() + 1) * 8));
+        out->off = static_cast<uint64_t*>(std::malloc(off.size() * 8));
+        out->chars = static_cast<uint8_t*>(std::malloc(chars.size() + 1));
+        std::memcpy(out->pos, pos.data(), pos.size() * 8);
+        std::memcpy(out->off, off.data(), off.size() * 8);
+        std::memcpy(out->chars, chars.data(), chars.size());
+        return 0;
+    }, -1);
+}
+
+void pqr_valdump_free(pqr_valdump* d) {
+    std::free(d->is_null); std::free(d->vidx); std::free(d->fixed); std::free(d->str_off); std::free(d->chars);
+    std::memset(d, 0, sizeof(*d));
+}
+void pqr_pagedump_free(pqr_pagedump* d) {
+    std::free(d->page_num); std::free(d->page_type); std::free(d->num_values); std::free(d->first_value);
+    pqr_valdump_free(&d->values);
+    std::memset(d, 0, sizeof(*d));
+}
+void pqr_strdump_free(pqr_strdump* d) {
+    std::free(d->pos); std::free(d->off); std::free(d->chars);
+    std::memset(d, 0, sizeof(*d));
+}
+
+struct ColumnarOwner {
+    DecodedColumn d;
+    std::vector<uint64_t> row_base;
+};
+
+int pqr_read_columnar(pqr_reader* r, int col, int rg, pqr_columnar* out) {
+    return guarded([&]() -> int {
+        auto* o = new ColumnarOwner();
+        try { o->d = r->r.read_column_columnar(col, rg); } catch (...) { delete o; throw; }
+        for (const auto& c : o->d.chunks) o->row_base.push_back(c.out_row_base);
+        const DecodedColumn& d = o->d;
+        std::memset(out, 0, sizeof(*out));
+        out->type = static_cast<int32_t>(d.type);
+        out->width = d.width;
+        out->num_slots = d.num_slots;
+        out->has_validity = d.has_validity;
+        out->n_chunks = static_cast<uint32_t>(d.chunks.size());
+        out->values = d.values.data();
+        out->validity = d.validity.data();
+        out->offsets = d.offsets.data();
+        out->char_bases = d.char_bases.data();
+        out->chars = d.chars.data();
+        out->chars_size = d.chars.size();
+        out->chunk_row_base = o->row_base.data();
+        out->bytes_in = d.bytes_in;
+        out->bytes_out = d.bytes_out;
+        out->kernel_ms = d.kernel_ms;
+        out->owner = o;
+        return 0;
+    }, -1);
+}
+void pqr_columnar_free(pqr_columnar* c) {
+    if (c && c->owner) delete static_cast<ColumnarOwner*>(c->owner);
+    if (c) std::memset(c, 0, sizeof(*c));
+}
+
+int pqr_column_tables(const pqr_reader* r, int col, int rg, pqr_tables* out) {
+    return guarded([&]() -> int {
+        if (col < 0 || col >= static_cast<int>(r->r.num_columns())) throw std::runtime_error("Invalid column index");
+        if (rg >= static_cast<int>(r->r.num_row_groups())) throw std::runtime_error("Invalid row group index");
+        ColumnTables t = r->r.column_tables(col, rg);
+        out->n_chunks = static_cast<uint32_t>(t.chunks.size());
+        out->n_pages = static_cast<uint32_t>(t.pages.size());
+        out->total_slots = t.total_slots;
+        out->chunks = static_cast<pqg_chunk_desc*>(std::malloc(sizeof(pqg_chunk_desc) * (t.chunks.size() + 1)));
+        out->pages = static_cast<pqg_page_desc*>(std::malloc(sizeof(pqg_page_desc) * (t.pages.size() + 1)));
+        std::memcpy(out->chunks, t.chunks.data(), sizeof(pqg_chunk_desc) * t.chunks.size());
+        std::memcpy(out->pages, t.pages.data(), sizeof(pqg_page_desc) * t.pages.size());
+        return 0;
+    }, -1);
+}
+void pqr_tables_free(pqr_tables* t) {
+    if (!t) return;
+    std::free(t->chunks); std::free(t->pages);
+    std::memset(t, 0, sizeof(*t));
+}
+
+int64_t pqr_chunk_index(pqr_reader* r, const char* name, uint64_t chunk_size, uint64_t* tuple_to_chunk, int64_t num_rows) {
+    return guarded([&]() -> int64_t { return chunk_index(r->r, name, chunk_size, tuple_to_chunk, num_rows); }, -1);
+}
+int64_t pqr_regex_prune(pqr_reader* r, int col, const char* pattern, int neg, uint8_t* bits, int64_t cap, float* kernel_ms) {
+    return guarded([&]() -> int64_t { return regex_prune(r->r, col, pattern, neg != 0, bits, cap, kernel_ms); }, -1);
+}
+int64_t pqr_page_chunk_index(pqr_reader* r, int col, uint64_t chunk_size, uint32_t* page_chunk, uint32_t* page_off,
+                             uint32_t* chunk_first_page, int64_t cap, int64_t* first_global_page, int64_t* n_col_pages) {
+    return guarded([&]() -> int64_t {
+        return page_chunk_index(r->r, col, chunk_size, page_chunk, page_off, chunk_first_page, cap, first_global_page, n_col_pages);
+    }, -1);
+}
+
+} // extern "C"

@@ -1,0 +1,140 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Every decode goes through the
+C-ABI library (libpqg.so: host reader -> descriptor tables -> CUDA kernels) and is compared
+slot by slot -- null flag, variant alternative, payload bits, string bytes -- with the
+oracle (oracle/liboracle.so) and, where present, with the unmodified reference itself
+(oracle/_ref/libpqref.so) on files written by the reference's own writer."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import to_values
+from oraclelib import BYTE_ARRAY
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_gpu_present(pq):
+    assert pq.device_count() > 0, "no CUDA device: the product has no CPU fallback"
+
+
+def test_golden_vectors(pq):
+    """committed reference outputs (tests/golden/make_golden.py) -- needs neither oracle nor _ref"""
+    z = np.load(os.path.join(GOLD, "mixed.npz"))
+    r = pq.Reader(os.path.join(GOLD, "mixed.parquet"))
+    nrg, nc = (int(x) for x in z["shape"])
+    assert np.array_equal(r.page_index(), z["page_index"])
+    for c in range(nc):
+        ci = r.column_info(c)
+        for rg in range(nrg):
+            got = r.read_column_by_idx(rg, c)
+            p = f"rg{rg}_col{c}_"
+            for k in ("is_null", "vidx", "fixed", "str_off", "chars"):
+                assert np.array_equal(got[k], z[p + k]), (ci["name"], rg, k)
+            pg = r.read_pages(rg, c)
+            assert np.array_equal(np.stack([pg["page_num"], pg["page_type"], pg["num_values"]]), z[f"rg{rg}_col{c}_pages"])
+        if ci["type"] == BYTE_ARRAY:
+            pos, off, _ = r.string_iterator(ci["name"])
+            assert np.array_equal(pos, z[f"col{c}_iter_pos"]) and np.array_equal(off, z[f"col{c}_iter_off"])
+    r.close()
+
+
+def test_read_column_matches_oracle_and_reference(pq, oracle, files):
+    import oraclelib
+    ref = oraclelib.Ref() if oraclelib.Ref.available() else None
+    for name, path in files.items():
+        r = pq.Reader(path)
+        ho = oracle.open(path)
+        hr = ref.open(path) if ref else None
+        try:
+            for c in range(r.num_columns):
+                ci = r.column_info(c)
+                for rg in range(r.num_row_groups):
+                    got = to_values(r.read_column_by_idx(rg, c))
+                    d = got.diff(oracle.read_column_by_idx(ho, rg, c))
+                    assert d is None, (name, ci["name"], rg, d)
+                    if hr:
+                        d = got.diff(ref.read_column_by_idx(hr, rg, c))
+                        assert d is None, ("vs reference", name, ci["name"], rg, d)
+                whole = to_values(r.read_column(ci["name"]))
+                assert whole.diff(oracle.read_column(ho, ci["name"])) is None, (name, ci["name"])
+                one = to_values(r.read_column(ci["name"], rg=r.num_row_groups - 1))
+                assert one.diff(oracle.read_column_by_idx(ho, r.num_row_groups - 1, c)) is None
+        finally:
+            oracle.close(ho)
+            if hr:
+                ref.close(hr)
+            r.close()
+
+
+def test_read_pages_matches_oracle(pq, oracle, files):
+    for name, path in files.items():
+        r = pq.Reader(path)
+        ho = oracle.open(path)
+        try:
+            for c in range(r.num_columns):
+                for rg in range(r.num_row_groups):
+                    a, b = r.read_pages(rg, c), oracle.read_pages(ho, rg, c)
+                    assert np.array_equal(a["page_num"], b.page_num) and np.array_equal(a["page_type"], b.page_type)
+                    assert np.array_equal(a["num_values"], b.num_values) and np.array_equal(a["first_value"], b.first_value)
+                    assert to_values(a["values"]).diff(b.values) is None, (name, c, rg)
+        finally:
+            oracle.close(ho)
+            r.close()
+
+
+def test_string_iterator_matches_oracle(pq, oracle, files):
+    for name, path in files.items():
+        r = pq.Reader(path)
+        ho = oracle.open(path)
+        try:
+            for c in range(r.num_columns):
+                ci = r.column_info(c)
+                if ci["type"] != BYTE_ARRAY:
+                    continue
+                a, b = r.string_iterator(ci["name"]), oracle.string_iterator(ho, ci["name"])
+                for x, y in zip(a, b):
+                    assert np.array_equal(x, y), (name, ci["name"])
+        finally:
+            oracle.close(ho)
+            r.close()
+
+
+def test_columnar_api_is_consistent_with_values(pq, files):
+    """the Value-free columnar result carries the same information"""
+    path = files["golden_mixed"]
+    r = pq.Reader(path)
+    for c in range(r.num_columns):
+        ci = r.column_info(c)
+        col = r.read_columnar(c, -1)
+        vals = r.read_column(ci["name"])
+        n = col["num_slots"]
+        assert n == len(vals["is_null"])
+        valid = np.ones(n, dtype=bool)
+        if col["has_validity"]:
+            valid = ((col["validity"][np.arange(n) >> 5] >> (np.arange(n) & 31).astype(np.uint32)) & 1).astype(bool)
+        assert np.array_equal(~valid, vals["is_null"].astype(bool))
+        if ci["type"] == BYTE_ARRAY:
+            lens = np.diff(vals["str_off"].astype(np.int64))
+            got = []
+            for k in range(col["n_chunks"]):
+                base = int(col["chunk_row_base"][k])
+                end = int(col["chunk_row_base"][k + 1]) if k + 1 < col["n_chunks"] else n
+                off = col["offsets"][base + k: end + k + 1].astype(np.int64)
+                got.append(np.diff(off))
+                chars = col["chars"][int(col["char_bases"][k]) + int(off[0]): int(col["char_bases"][k]) + int(off[-1])]
+                exp = vals["chars"][int(vals["str_off"][base]): int(vals["str_off"][end])]
+                assert np.array_equal(chars, exp)
+            assert np.array_equal(np.concatenate(got), lens)
+        else:
+            w = col["width"]
+            raw = col["values"].reshape(n, w)
+            if w <= 8:
+                pad = np.zeros((n, 8), dtype=np.uint8)
+                pad[:, :w] = raw
+                bits = pad.view(np.uint64).reshape(n)
+                assert np.array_equal(bits[valid], vals["fixed"][valid])
+                assert not bits[~valid].any()
+    r.close()
