@@ -1,0 +1,401 @@
+#!/usr/bin/env python
+"""bench.py -- decoded input-page GB/s of the B200 Parquet page decoder (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W          # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W  # the reference's CPU ColumnReader
+
+Workload (BASELINE.json configs[1], SURVEY.md section 8 d "Config 2"): a 100 M-row file as
+10 row groups x 10 M rows with 7 columns -- INT64 PLAIN, DOUBLE PLAIN, INT64 dictionary with
+2^8 / 2^12 / 2^16 / 2^20 distinct keys (index bit widths 8 / 12 / 16 / 20) and DOUBLE
+dictionary with 2^16 keys -- produced by the workload generator, which is byte-identical to the
+reference's ParquetWriter (tests/test_gen_cpu.py).  One step = one decode of all 7 columns.
+
+  value      Sigma page payload bytes (data + dictionary pages) / device time, image resident in
+             HBM, K steps timed with CUDA events on the decoder's stream, max over ranks.
+  e2e        same metric through the reference-facing reader API (pqr_* C-ABI) with HOST buffers:
+             every step uploads the column chunks from pinned host memory and reads the
+             decoded columns back to the host.
+  roofline   dominant kernel (k_decode_fixed): (bytes_in + bytes_out) of its launches / their
+             CUDA-event durations inside the timed steps, against MEASURED_PEAKS.json hbm_gbs.
+  cpu_baseline / --impl reference
+             the UNMODIFIED reference (oracle/_ref/libpqref.so, compiled from /root/reference
+             sources) reading a bounded sample (the first row groups of the same data, written
+             as its own file) with one ParquetReader per host thread.
+
+N > 1 (torchrun): every rank decodes its own 100 M-row shard (row groups are independent; no
+data-path collective), "scaling": "weak"; value = total bytes / max-over-ranks time.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "decoded_page_GBps"
+UNIT = "GB/s"
+WORKLOAD = "cfg2: 100M-row INT64/DOUBLE PLAIN + dictionary bw 8/12/16/20, 10 row groups x 10M rows"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ── workload ────────────────────────────────────────────────────────────────────────────
+def cfg2_specs():
+    I64, F64, REQ = 2, 5, 0
+    return [("i64_plain", I64, REQ, -1), ("f64_plain", F64, REQ, -1), ("i64_d8", I64, REQ, -1),
+            ("i64_d12", I64, REQ, -1), ("i64_d16", I64, REQ, -1), ("i64_d20", I64, REQ, -1),
+            ("f64_d16", F64, REQ, -1)]
+
+
+def cfg2_columns(rows, seed):
+    """SURVEY.md 8(d) Config 2: uniform 64-bit ints, uniform [0,1) doubles, dictionary keys
+    k * 2654435761 (int64) / k * 0.37 (double) with k uniform in [0, 2^b)."""
+    rng = np.random.default_rng(seed)
+    cols = [dict(fixed=rng.integers(-2**63, 2**63 - 1, size=rows, dtype=np.int64)),
+            dict(fixed=rng.random(rows))]
+    for b in (8, 12, 16, 20):
+        k = rng.integers(0, 1 << b, size=rows, dtype=np.int64)
+        cols.append(dict(fixed=k * 2654435761))
+    k = rng.integers(0, 1 << 16, size=rows, dtype=np.int64)
+    cols.append(dict(fixed=k.astype(np.float64) * 0.37))
+    return cols
+
+
+def rg_split(rows, rg_rows):
+    out = [rg_rows] * (rows // rg_rows)
+    if rows % rg_rows:
+        out.append(rows % rg_rows)
+    return out
+
+
+def build_file(pq, rows, rg_rows, seed):
+    t0 = time.time()
+    cols = cfg2_columns(rows, seed)
+    t1 = time.time()
+    g = pq.generate(cfg2_specs(), cols, rg_split(rows, rg_rows))
+    t2 = time.time()
+    log(f"[bench] synthetic columns {t1 - t0:.1f}s, writer-identical encode {t2 - t1:.1f}s, file {g.size / 1e9:.3f} GB")
+    return g, cols
+
+
+# ── clocks ──────────────────────────────────────────────────────────────────────────────
+class ClockSampler:
+    """SM clock + throttle reasons sampled through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.stop_flag, self.thread = [], set(), False, None
+        self.max_mhz = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # NVML missing: report that, never fake numbers
+            self.nv = None
+            self.err = str(e)
+
+    def _loop(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40,
+                 "sw_thermal_slowdown": 0x20, "hw_power_brake_slowdown": 0x80, "sync_boost": 0x10}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def start(self):
+        if self.nv:
+            self.thread = threading.Thread(target=self._loop, daemon=True)
+            self.thread.start()
+
+    def stop(self):
+        self.stop_flag = True
+        if self.thread:
+            self.thread.join()
+        if not self.nv:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "error": "nvml unavailable"}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ── CPU arm: the unmodified reference ───────────────────────────────────────────────────
+def ref_sample_file(pq, cols, rows, rg_rows, n_rgs, path):
+    """first n_rgs row groups of the same data, as their own (writer-identical) file"""
+    take = min(rows, rg_rows * n_rgs)
+    sub = [dict(fixed=c["fixed"][:take]) for c in cols]
+    g = pq.generate(cfg2_specs(), sub, rg_split(take, rg_rows))
+    g.write(path)
+    size = g.size
+    g.free()
+    return take, size
+
+
+def payload_bytes_of(pq, path):
+    r = pq.Reader(path)
+    idx = r.page_index()
+    total = int(idx[:, 1].sum())
+    # dictionary pages are not in the page index: add them from the descriptor tables
+    for c in range(r.num_columns):
+        chunks, nc, _, _, _ = r.column_tables(c, -1)
+        total += sum(int(chunks[i].dict_size) for i in range(nc) if chunks[i].has_dict)
+    r.close()
+    return total
+
+
+def cpu_reference_run(pq, cols, rows, rg_rows, sample_rgs, steps, warmup, threads):
+    import oraclelib
+    if not oraclelib.Ref.available():
+        raise RuntimeError("oracle/_ref/libpqref.so is missing (built by __graft_entry__.build() where /root/reference exists)")
+    ref = oraclelib.Ref()
+    d = "/dev/shm" if os.path.isdir("/dev/shm") else "/tmp"
+    path = os.path.join(d, f"pqg_bench_ref_{os.getpid()}.parquet")
+    take, _ = ref_sample_file(pq, cols, rows, rg_rows, sample_rgs, path)
+    try:
+        payload = payload_bytes_of(pq, path)
+        n_rg = len(rg_split(take, rg_rows))
+        items = [(rg, c) for rg in range(n_rg) for c in range(len(cols))]
+        rgs = [i[0] for i in items]
+        cs = [i[1] for i in items]
+        times = []
+        for s in range(warmup + steps):
+            t, nv = ref.time_read_chunks(path, rgs, cs, threads)
+            assert nv == take * len(cols), (nv, take)
+            if s >= warmup:
+                times.append(t)
+    finally:
+        os.unlink(path)
+    mean = sum(times) / len(times)
+    return dict(value=payload / mean / 1e9, seconds=mean, payload=payload, rows=take, values=take * len(cols),
+                threads=threads, sample=f"first {n_rg} row group(s) = {take} rows x {len(cols)} columns of the same data "
+                                        f"({payload / 1e6:.0f} MB payload), ParquetReader::read_column_by_idx per chunk, "
+                                        f"one reader per thread, page cache warm")
+
+
+# ── GPU arm ─────────────────────────────────────────────────────────────────────────────
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--rows", type=int, default=100_000_000)
+    ap.add_argument("--rg-rows", type=int, default=10_000_000)
+    ap.add_argument("--cpu-sample-rgs", type=int, default=4)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    warmup = max(a.warmup, 3) if a.impl == "b200" else a.warmup
+    config = {"workload": WORKLOAD, "rows_per_gpu": a.rows, "row_group_rows": a.rg_rows, "columns": [s[0] for s in cfg2_specs()],
+              "l2": "inputs (2.6 GB) and outputs (5.6 GB) per step exceed the 126 MB L2; no flush needed",
+              "sharding": "one process per GPU, each decodes its own row-group shard; no collective on the data path"}
+    import pqb200 as pq
+    pq.lib()
+    cores = os.cpu_count() or 1
+
+    if a.impl == "reference":
+        if rank != 0:
+            return 0
+        # the sample only needs the first row groups: do not generate the whole file
+        take = min(a.rows, a.rg_rows * a.cpu_sample_rgs)
+        cols = cfg2_columns(take, 1234)
+        r = cpu_reference_run(pq, cols, take, a.rg_rows, a.cpu_sample_rgs, a.steps, a.warmup, cores)
+        line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+                "warmup": a.warmup, "ms_per_step": r["seconds"] * 1e3, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "int64/f64 bit moves", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["threads"], "kind": "reference", "sample": r["sample"]},
+                "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line), flush=True)
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py: no CUDA device; this framework has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    gen, cols = build_file(pq, a.rows, a.rg_rows, 1234 + rank)
+    size = gen.size
+    # pinned host image of the file (what an application would have read / mapped)
+    host = torch.empty(size + 64, dtype=torch.uint8, pin_memory=True)
+    gen.emit(host.data_ptr(), size)
+    gen.free()
+
+    # host side of the boundary: footer + page headers -> flat descriptor tables (timed apart)
+    t0 = time.time()
+    reader = pq.Reader.from_pointer(host.data_ptr(), size, device=local)
+    open_s = time.time() - t0
+    ncols = reader.num_columns
+    n_pages = reader.num_pages
+    tables = [reader.column_tables(c, -1) for c in range(ncols)]
+
+    # ---- kernel arm: image resident in HBM --------------------------------------------
+    stream = torch.cuda.Stream()
+    ctx = pq.Context(local, stream.cuda_stream)
+    t0 = time.time()
+    dev_img = torch.empty(size + 64, dtype=torch.uint8, device="cuda")
+    h2d0, h2d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        h2d0.record()
+        dev_img[:size].copy_(host[:size], non_blocking=True)
+        dev_img[size:].zero_()
+        h2d1.record()
+    stream.synchronize()
+    h2d_ms = h2d0.elapsed_time(h2d1)
+    image = ctx.wrap_device(dev_img.data_ptr(), size)
+    plans = [ctx.plan(image, t) for t in tables]
+    bytes_in = sum(p.bytes_in for p in plans)
+    ctx.set_profiling(True)
+
+    def step():
+        for p in plans:
+            p.run()
+
+    for _ in range(warmup):
+        step()
+    for p in plans:
+        p.finish()
+    bytes_out = sum(p.bytes_out for p in plans)
+    launches0 = ctx.launches
+    sampler = ClockSampler(local)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    sampler.start()
+    with torch.cuda.stream(stream):
+        ev0.record()
+        for _ in range(a.steps):
+            step()
+        ev1.record()
+    stream.synchronize()
+    barrier()
+    clocks = sampler.stop()
+    launches = ctx.launches - launches0
+    for p in plans:
+        p.finish()  # raises on any page error
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / a.steps
+    value = bytes_in * world / (ms_per_step * 1e-3) / 1e9
+
+    # dominant kernel: k_decode_fixed, one launch per column; CUDA events around every launch
+    # of the timed steps (the last <= 8 runs of each plan are kept)
+    tm = [p.timings_avg(min(a.steps, 8)) for p in plans]
+    k_ms = sum(t["fixed_ms"] for t in tm)
+    k_bytes = bytes_in + bytes_out
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = k_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "k_decode_fixed<8,false>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)",
+                "algorithmic_bytes_per_step": k_bytes, "kernel_ms_per_step": k_ms, "launches_per_step": len(plans),
+                "kernel_share_of_step": k_ms / ms_per_step if ms_per_step else None,
+                "per_column": [{"column": s[0], "ms": t["fixed_ms"], "dict_ms": t["dict_ms"],
+                                "GBps_in_plus_out": (p.bytes_in + p.bytes_out) / (t["fixed_ms"] * 1e-3) / 1e9 if t["fixed_ms"] > 0 else None}
+                               for s, t, p in zip(cfg2_specs(), tm, plans)]}
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        roofline["traffic"] = tr.get("dram_bytes_per_step")
+        roofline["traffic_source"] = tr.get("source")
+    except Exception:
+        pass
+
+    for p in plans:
+        p.destroy()
+    ctx.buf_free(image)
+    del dev_img
+    torch.cuda.empty_cache()
+
+    # ---- e2e arm: host buffers in, host columns out, through the reader C-ABI ---------
+    e2e_steps = max(1, min(a.e2e_steps, a.steps))
+    d2h_bytes = h2d_bytes = 0
+
+    def e2e_step(check=False):
+        nonlocal d2h_bytes, h2d_bytes
+        d2h_bytes = h2d_bytes = 0
+        for c in range(ncols):
+            col = reader.read_columnar(c, -1)
+            d2h_bytes += col["values"].nbytes + col["validity"].nbytes + col["offsets"].nbytes + col["chars"].nbytes
+            h2d_bytes += col["bytes_in"]
+            if check:
+                got = col["values"].view(np.uint64)
+                exp = np.ascontiguousarray(cols[c]["fixed"]).view(np.uint64)
+                if not np.array_equal(got, exp):
+                    raise AssertionError(f"bench parity check failed on column {c}")
+
+    e2e_step(check=True)  # warm-up + bit-exact check against the generator's input columns
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    if world > 1:
+        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e = {"value": bytes_in * world / e2e_s / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
+           "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
+           "api": "pqr_open_memory + pqr_read_columnar per column (host image in, host columnar buffers out)",
+           "parity": "decoded columns bit-identical to the generator's input arrays (checked on the warm-up step)"}
+    reader.close()
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int64/f64 bit moves", "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e,
+            "gpu_launches": int(launches), "roofline": roofline,
+            "bytes": {"payload_in_per_step": int(bytes_in), "decoded_out_per_step": int(bytes_out), "pages": int(n_pages),
+                      "values_per_step": a.rows * ncols},
+            "ingest": {"host_open_page_scan_s": open_s, "h2d_ms": h2d_ms, "h2d_GBps": size / (h2d_ms * 1e-3) / 1e9 if h2d_ms else None},
+            "frac_of_hbm_peak_in_plus_out": (bytes_in + bytes_out) * world / (ms_per_step * 1e-3) / 1e9 / (peak * world)}
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        try:
+            r = cpu_reference_run(pq, cols, a.rows, a.rg_rows, a.cpu_sample_rgs, 1, 0, cores)
+            line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["threads"], "kind": "reference",
+                                    "sample": r["sample"], "seconds": r["seconds"], "Mvalues_per_s": r["values"] / r["seconds"] / 1e6}
+        except Exception as e:
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": cores, "kind": "reference", "sample": f"unavailable: {e}"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -90,6 +90,11 @@ class Columnar(C.Structure):
                 ("kernel_ms", C.c_float), ("owner", C.c_void_p)]
 
 
+class GenCol(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("type", C.c_int32), ("repetition", C.c_int32), ("converted", C.c_int32),
+                ("fixed", C.c_void_p), ("str_off", C.c_void_p), ("chars", C.c_void_p), ("is_null", C.c_void_p)]
+
+
 class Tables(C.Structure):
     _fields_ = [("n_chunks", C.c_uint32), ("n_pages", C.c_uint32), ("chunks", C.POINTER(ChunkDesc)),
                 ("pages", C.POINTER(PageDesc)), ("total_slots", C.c_uint64)]
@@ -100,7 +105,7 @@ PQG_SYMBOLS = [
     "pqg_ctx_create", "pqg_ctx_destroy", "pqg_last_error", "pqg_ctx_sync", "pqg_ctx_set_profiling", "pqg_device_count",
     "pqg_kernel_launches", "pqg_upload", "pqg_wrap_device", "pqg_buf_alloc", "pqg_buf_write", "pqg_buf_size",
     "pqg_buf_free", "pqg_buf_device_ptr", "pqg_host_alloc", "pqg_host_free", "pqg_plan_create", "pqg_plan_destroy",
-    "pqg_plan_set_image", "pqg_plan_run", "pqg_plan_finish", "pqg_plan_timings", "pqg_plan_num_slots",
+    "pqg_plan_set_image", "pqg_plan_run", "pqg_plan_finish", "pqg_plan_timings", "pqg_plan_timings_avg", "pqg_plan_num_slots",
     "pqg_plan_value_width", "pqg_plan_values", "pqg_plan_validity", "pqg_plan_offsets", "pqg_plan_chars",
     "pqg_plan_chars_size", "pqg_plan_char_bases", "pqg_plan_bytes_in", "pqg_plan_bytes_out", "pqg_plan_download",
     "pqg_regex_compile", "pqg_dfa_free", "pqg_dfa_num_states", "pqg_dfa_match_host", "pqg_regex_scan",
@@ -115,6 +120,8 @@ PQR_SYMBOLS = [
     "pqr_columnar_free", "pqr_column_tables", "pqr_tables_free", "pqr_chunk_index", "pqr_regex_prune",
     "pqr_page_chunk_index",
 ]
+
+PQGEN_SYMBOLS = ["pqgen_last_error", "pqgen_encode", "pqgen_size", "pqgen_emit", "pqgen_write_file", "pqgen_free"]
 
 _lib = None
 
@@ -161,6 +168,7 @@ def _declare(L):
     d("pqg_plan_run", i32, vp, vp)
     d("pqg_plan_finish", i32, vp, vp, C.POINTER(PageError))
     d("pqg_plan_timings", i32, vp, C.POINTER(Timings))
+    d("pqg_plan_timings_avg", i32, vp, u32, C.POINTER(Timings), C.POINTER(u32))
     d("pqg_plan_num_slots", u64, vp)
     d("pqg_plan_value_width", u32, vp)
     for n in ("pqg_plan_values", "pqg_plan_validity", "pqg_plan_offsets", "pqg_plan_chars"):
@@ -177,6 +185,13 @@ def _declare(L):
     d("pqg_regex_scan", i32, vp, vp, vp, i32, vp, C.POINTER(C.c_float))
     d("pqg_chunk_index", i32, vp, vp, u64, u64, vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(C.c_float))
     d("pqg_page_chunk_index", i32, vp, vp, u32, u64, vp, vp, vp, u32, C.POINTER(u32))
+
+    d("pqgen_last_error", cp)
+    d("pqgen_encode", vp, C.POINTER(GenCol), i32, vp, i32, i32)
+    d("pqgen_size", u64, vp)
+    d("pqgen_emit", i32, vp, vp, u64)
+    d("pqgen_write_file", i32, vp, cp)
+    d("pqgen_free", None, vp)
 
     d("pqr_last_error", cp)
     d("pqr_open", vp, cp, i32)
@@ -474,6 +489,12 @@ class Plan:
         return dict(dict_ms=t.dict_ms, fixed_ms=t.fixed_ms, str_size_ms=t.str_size_ms, str_copy_ms=t.str_copy_ms,
                     total_ms=t.total_ms, launches=t.launches)
 
+    def timings_avg(self, last_n=0):
+        t, n = Timings(), C.c_uint32(0)
+        lib().pqg_plan_timings_avg(self.h, last_n, C.byref(t), C.byref(n))
+        return dict(dict_ms=t.dict_ms, fixed_ms=t.fixed_ms, str_size_ms=t.str_size_ms, str_copy_ms=t.str_copy_ms,
+                    total_ms=t.total_ms, launches=t.launches, runs=n.value)
+
     num_slots = property(lambda s: lib().pqg_plan_num_slots(s.h))
     width = property(lambda s: lib().pqg_plan_value_width(s.h))
     bytes_in = property(lambda s: lib().pqg_plan_bytes_in(s.h))
@@ -514,3 +535,79 @@ def regex_compile(pattern):
 def dfa_match_host(dfa, text):
     t = np.frombuffer(bytes(text) + b"\0", dtype=np.uint8)
     return lib().pqg_dfa_match_host(dfa, t.ctypes.data, len(text))
+
+
+_WIDTH = {BOOLEAN: 1, INT32: 4, FLOAT: 4, INT64: 8, DOUBLE: 8}
+
+
+class Generated:
+    """A parquet file image produced by the workload generator (include/pqg_gen.h)."""
+
+    def __init__(self, job):
+        self.job = job
+        self.size = lib().pqgen_size(job)
+
+    def emit(self, dst_ptr, cap):
+        if lib().pqgen_emit(self.job, dst_ptr, cap) != 0:
+            raise PqgError(lib().pqgen_last_error().decode())
+
+    def to_numpy(self):
+        out = np.empty(self.size, dtype=np.uint8)
+        self.emit(out.ctypes.data, out.size)
+        return out
+
+    def write(self, path):
+        if lib().pqgen_write_file(self.job, path.encode()) != 0:
+            raise PqgError(lib().pqgen_last_error().decode())
+        return path
+
+    def free(self):
+        if self.job:
+            lib().pqgen_free(self.job)
+            self.job = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def generate(specs, columns, rg_rows, threads=0):
+    """specs: [(name, type, repetition, converted|-1)]; columns: one dict per column over ALL
+    rows of the file: dict(fixed=array[, is_null=uint8[]]) or dict(str_off=uint64[n+1],
+    chars=uint8[][, is_null]); `fixed` may be the natural dtype (int32/float32/int64/float64/
+    uint8) or one uint64 per row holding the payload bits (tests/oraclelib.fixed_col)."""
+    n = len(specs)
+    arr = (GenCol * n)()
+    hold = []
+    for i, ((name, t, rep, conv), col) in enumerate(zip(specs, columns)):
+        nb = name.encode()
+        hold.append(nb)
+        isn = col.get("is_null")
+        if isn is not None:
+            isn = np.ascontiguousarray(isn, dtype=np.uint8)
+            hold.append(isn)
+        g = GenCol(nb, t, rep, conv, None, None, None, isn.ctypes.data if isn is not None else None)
+        if t == BYTE_ARRAY:
+            so = np.ascontiguousarray(col["str_off"], dtype=np.uint64)
+            ch = np.ascontiguousarray(col["chars"], dtype=np.uint8)
+            if ch.size == 0:
+                ch = np.zeros(1, dtype=np.uint8)
+            hold += [so, ch]
+            g.str_off, g.chars = so.ctypes.data, ch.ctypes.data
+        else:
+            w = _WIDTH[t]
+            fx = np.ascontiguousarray(col["fixed"])
+            if fx.dtype.itemsize != w:  # one uint64 of payload bits per row -> natural width
+                fx = fx.astype(np.uint64).astype({1: np.uint8, 4: np.uint32, 8: np.uint64}[w])
+            if fx.size == 0:
+                fx = np.zeros(1, dtype=fx.dtype)
+            hold.append(fx)
+            g.fixed = fx.ctypes.data
+        arr[i] = g
+    rg = np.ascontiguousarray(rg_rows, dtype=np.int64)
+    job = lib().pqgen_encode(arr, n, rg.ctypes.data, len(rg), threads)
+    if not job:
+        raise PqgError(lib().pqgen_last_error().decode())
+    return Generated(job)

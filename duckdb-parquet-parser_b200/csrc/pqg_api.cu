@@ -49,9 +49,13 @@ struct pqg_plan {
     uint64_t* h_bases = nullptr;  // pinned mirror
     DevErr* d_err = nullptr;
     DevErr* h_err = nullptr;      // pinned
-    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    static constexpr int kTimingSlots = 8;   // ring: the last 8 profiled runs keep their events
+    cudaEvent_t evr[kTimingSlots][5] = {};
+    cudaEvent_t* ev = evr[0];                // events of the current run
+    uint64_t runs_timed = 0;
     bool timed = false;
     pqg_timings tm{};
+    uint32_t last_launches = 0;
     uint64_t bytes_in = 0, bytes_out = 0;
     bool ran = false;
 };
@@ -224,7 +228,7 @@ void pqg_plan_destroy(pqg_ctx* ctx, pqg_plan* p) {
     cudaFree(p->d_page_char_base); cudaFree(p->d_bases); cudaFree(p->d_err);
     if (p->h_bases) cudaFreeHost(p->h_bases);
     if (p->h_err) cudaFreeHost(p->h_err);
-    for (auto& e : p->ev) if (e) cudaEventDestroy(e);
+    for (auto& slot : p->evr) for (auto& e : slot) if (e) cudaEventDestroy(e);
     delete p;
 }
 
@@ -312,7 +316,7 @@ int pqg_plan_create(pqg_ctx* ctx, const pqg_buf* image, const pqg_chunk_desc* ch
         e = cudaMemcpyAsync(p->d_pages, p->pages.data(), sizeof(pqg_page_desc) * n_pages, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) { pqg_plan_destroy(ctx, p); return cuda_fail(ctx, e, "descriptor upload"); }
-    for (auto& ev : p->ev) {
+    for (auto& slot : p->evr) for (auto& ev : slot) {
         if ((e = cudaEventCreate(&ev)) != cudaSuccess) { pqg_plan_destroy(ctx, p); return cuda_fail(ctx, e, "cudaEventCreate"); }
     }
     // algorithmic output bytes (SURVEY.md section 8 d)
@@ -348,6 +352,7 @@ int pqg_plan_run(pqg_ctx* ctx, pqg_plan* p) {
     const bool prof = ctx->profiling;
     uint32_t launches = 0;
     p->timed = prof;
+    if (prof) { p->ev = p->evr[p->runs_timed % pqg_plan::kTimingSlots]; p->runs_timed++; }
     if (prof) CU(ctx, cudaEventRecord(p->ev[0], s));
     CU(ctx, cudaMemsetAsync(p->d_err, 0xFF, 8, s));
     CU(ctx, cudaMemsetAsync(reinterpret_cast<uint8_t*>(p->d_err) + 8, 0, sizeof(DevErr) - 8, s));
@@ -385,9 +390,23 @@ int pqg_plan_run(pqg_ctx* ctx, pqg_plan* p) {
     }
     if (prof) CU(ctx, cudaEventRecord(p->ev[4], s));
     p->tm.launches = launches;
+    p->last_launches = launches;
     ctx->launches += launches;
     p->ran = true;
     return PQG_OK;
+}
+
+static void elapsed_of(const pqg_plan* p, cudaEvent_t* ev, pqg_timings* tm) {
+    cudaEventElapsedTime(&tm->dict_ms, ev[0], ev[1]);
+    if (p->is_str) {
+        cudaEventElapsedTime(&tm->str_size_ms, ev[1], ev[2]);
+        cudaEventElapsedTime(&tm->str_copy_ms, ev[2], ev[3]);
+        tm->fixed_ms = 0;
+    } else {
+        cudaEventElapsedTime(&tm->fixed_ms, ev[1], ev[2]);
+        tm->str_size_ms = tm->str_copy_ms = 0;
+    }
+    cudaEventElapsedTime(&tm->total_ms, ev[0], ev[4]);
 }
 
 int pqg_plan_finish(pqg_ctx* ctx, pqg_plan* p, pqg_page_error* err) {
@@ -395,18 +414,7 @@ int pqg_plan_finish(pqg_ctx* ctx, pqg_plan* p, pqg_page_error* err) {
     CU(ctx, cudaSetDevice(ctx->device));
     CU(ctx, cudaMemcpyAsync(p->h_err, p->d_err, sizeof(DevErr), cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
-    if (p->timed) {
-        cudaEventElapsedTime(&p->tm.dict_ms, p->ev[0], p->ev[1]);
-        if (p->is_str) {
-            cudaEventElapsedTime(&p->tm.str_size_ms, p->ev[1], p->ev[2]);
-            cudaEventElapsedTime(&p->tm.str_copy_ms, p->ev[2], p->ev[3]);
-            p->tm.fixed_ms = 0;
-        } else {
-            cudaEventElapsedTime(&p->tm.fixed_ms, p->ev[1], p->ev[2]);
-            p->tm.str_size_ms = p->tm.str_copy_ms = 0;
-        }
-        cudaEventElapsedTime(&p->tm.total_ms, p->ev[0], p->ev[4]);
-    }
+    if (p->timed) elapsed_of(p, p->ev, &p->tm);
     if (p->is_str) {
         uint64_t slots = p->n_slots;
         p->bytes_out = p->chars_size + 4 * (slots + p->chunks.size()) + (p->any_def ? (slots + 7) / 8 : 0);
@@ -440,6 +448,29 @@ int pqg_plan_finish(pqg_ctx* ctx, pqg_plan* p, pqg_page_error* err) {
 int pqg_plan_timings(const pqg_plan* plan, pqg_timings* out) {
     if (!plan || !out) return PQG_ERR_ARG;
     *out = plan->tm;
+    return PQG_OK;
+}
+
+int pqg_plan_timings_avg(const pqg_plan* plan, uint32_t last_n, pqg_timings* out, uint32_t* n_used) {
+    if (!plan || !out) return PQG_ERR_ARG;
+    pqg_timings acc{};
+    uint32_t n = 0;
+    uint64_t have = plan->runs_timed < (uint64_t)pqg_plan::kTimingSlots ? plan->runs_timed : (uint64_t)pqg_plan::kTimingSlots;
+    if (last_n == 0 || last_n > have) last_n = static_cast<uint32_t>(have);
+    for (uint32_t i = 0; i < last_n; i++) {
+        uint64_t run = plan->runs_timed - 1 - i;
+        cudaEvent_t* ev = const_cast<cudaEvent_t*>(plan->evr[run % pqg_plan::kTimingSlots]);
+        if (cudaEventQuery(ev[4]) != cudaSuccess) { cudaGetLastError(); continue; }
+        pqg_timings t{};
+        elapsed_of(plan, ev, &t);
+        acc.dict_ms += t.dict_ms; acc.fixed_ms += t.fixed_ms; acc.str_size_ms += t.str_size_ms;
+        acc.str_copy_ms += t.str_copy_ms; acc.total_ms += t.total_ms;
+        n++;
+    }
+    if (n) { acc.dict_ms /= n; acc.fixed_ms /= n; acc.str_size_ms /= n; acc.str_copy_ms /= n; acc.total_ms /= n; }
+    acc.launches = plan->last_launches;
+    *out = acc;
+    if (n_used) *n_used = n;
     return PQG_OK;
 }
 

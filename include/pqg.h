@@ -159,6 +159,9 @@ PQG_API int pqg_plan_run(pqg_ctx* ctx, pqg_plan* plan);
 /* wait for the run and report page errors; PQG_ERR_PAGE when err->count > 0 */
 PQG_API int pqg_plan_finish(pqg_ctx* ctx, pqg_plan* plan, pqg_page_error* err);
 PQG_API int pqg_plan_timings(const pqg_plan* plan, pqg_timings* out);
+/* mean over the last `last_n` (0 = all kept, at most 8) profiled runs whose events have
+ * completed; no synchronisation between runs is needed to collect them */
+PQG_API int pqg_plan_timings_avg(const pqg_plan* plan, uint32_t last_n, pqg_timings* out, uint32_t* n_used);
 
 /* Output layout (device memory owned by the plan), n = total slots of the column:
  *   values   : n * width bytes, width = 1 BOOLEAN, 4 INT32/FLOAT, 8 INT64/DOUBLE, 12 INT96;
