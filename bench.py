@@ -15,7 +15,7 @@ reference's ParquetWriter (tests/test_gen_cpu.py).  One step = one decode of all
   e2e        same metric through the reference-facing reader API (pqr_* C-ABI) with HOST buffers:
              every step uploads the column chunks from pinned host memory and reads the
              decoded columns back to the host.
-  roofline   dominant kernel (k_decode_fixed): (bytes_in + bytes_out) of its launches / their
+  roofline   dominant kernel (k_fixed_tiles): (bytes_in + bytes_out) of its launches / their
              CUDA-event durations inside the timed steps, against MEASURED_PEAKS.json hbm_gbs.
   cpu_baseline / --impl reference
              the UNMODIFIED reference (oracle/_ref/libpqref.so, compiled from /root/reference
@@ -199,7 +199,7 @@ def main():
     ap.add_argument("--rows", type=int, default=100_000_000)
     ap.add_argument("--rg-rows", type=int, default=10_000_000)
     ap.add_argument("--cpu-sample-rgs", type=int, default=4)
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -308,7 +308,7 @@ def main():
     ms_per_step = ms / a.steps
     value = bytes_in * world / (ms_per_step * 1e-3) / 1e9
 
-    # dominant kernel: k_decode_fixed, one launch per column; CUDA events around every launch
+    # dominant kernel: k_fixed_tiles, one launch per column; CUDA events around every launch
     # of the timed steps (the last <= 8 runs of each plan are kept)
     tm = [p.timings_avg(min(a.steps, 8)) for p in plans]
     k_ms = sum(t["fixed_ms"] for t in tm)
@@ -320,12 +320,13 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = k_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "k_decode_fixed<8,false>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "k_fixed_tiles<8> (TMA-staged page tiles)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)",
                 "algorithmic_bytes_per_step": k_bytes, "kernel_ms_per_step": k_ms, "launches_per_step": len(plans),
                 "kernel_share_of_step": k_ms / ms_per_step if ms_per_step else None,
-                "per_column": [{"column": s[0], "ms": t["fixed_ms"], "dict_ms": t["dict_ms"],
+                "general_kernel_ms_per_step": sum(t["general_ms"] for t in tm), "dict_prepare_ms_per_step": sum(t["dict_ms"] for t in tm),
+                "per_column": [{"column": s[0], "ms": t["fixed_ms"], "dict_ms": t["dict_ms"], "general_ms": t["general_ms"],
                                 "GBps_in_plus_out": (p.bytes_in + p.bytes_out) / (t["fixed_ms"] * 1e-3) / 1e9 if t["fixed_ms"] > 0 else None}
                                for s, t, p in zip(cfg2_specs(), tm, plans)]}
     try:
@@ -342,37 +343,47 @@ def main():
     torch.cuda.empty_cache()
 
     # ---- e2e arm: host buffers in, host columns out, through the reader C-ABI ---------
+    # pqr_read_columns_into: per row group H2D -> decode -> D2H on three streams; the decoded
+    # columns land in caller-owned pinned host buffers.  Every step moves the file bytes up and
+    # the decoded columns down again; only descriptor tables / device buffers are kept.
     e2e_steps = max(1, min(a.e2e_steps, a.steps))
-    d2h_bytes = h2d_bytes = 0
+    outs = [torch.empty(a.rows, dtype=torch.int64, pin_memory=True) for _ in range(ncols)]
+    dsts = [(o.data_ptr(), o.numel() * 8, None, 0) for o in outs]
+    stats = None
 
-    def e2e_step(check=False):
-        nonlocal d2h_bytes, h2d_bytes
-        d2h_bytes = h2d_bytes = 0
-        for c in range(ncols):
-            col = reader.read_columnar(c, -1)
-            d2h_bytes += col["values"].nbytes + col["validity"].nbytes + col["offsets"].nbytes + col["chars"].nbytes
-            h2d_bytes += col["bytes_in"]
-            if check:
-                got = col["values"].view(np.uint64)
-                exp = np.ascontiguousarray(cols[c]["fixed"]).view(np.uint64)
-                if not np.array_equal(got, exp):
-                    raise AssertionError(f"bench parity check failed on column {c}")
+    def e2e_step():
+        nonlocal stats
+        stats = reader.read_columns_into(list(range(ncols)), dsts, -1)
 
-    e2e_step(check=True)  # warm-up + bit-exact check against the generator's input columns
+    for _ in range(2):
+        e2e_step()  # warm-up (builds and caches the plans)
+    for c in range(ncols):  # bit-exact check against the generator's input columns
+        got = outs[c].numpy().view(np.uint64)
+        exp = np.ascontiguousarray(cols[c]["fixed"]).view(np.uint64)
+        if not np.array_equal(got, exp):
+            raise AssertionError(f"bench parity check failed on column {c}")
+        outs[c].zero_()
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         e2e_step()
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
+    for c in range(ncols):
+        if not np.array_equal(outs[c].numpy().view(np.uint64)[-4096:], np.ascontiguousarray(cols[c]["fixed"]).view(np.uint64)[-4096:]):
+            raise AssertionError(f"bench parity check (timed step) failed on column {c}")
     if world > 1:
         t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
+    h2d_bytes = sum(s["h2d_bytes"] for s in stats)
+    d2h_bytes = sum(s["d2h_bytes"] for s in stats)
     e2e = {"value": bytes_in * world / e2e_s / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
            "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
-           "api": "pqr_open_memory + pqr_read_columnar per column (host image in, host columnar buffers out)",
-           "parity": "decoded columns bit-identical to the generator's input arrays (checked on the warm-up step)"}
+           "api": "pqr_open_memory + pqr_read_columns_into (pinned host file image in, pinned host columnar buffers out; "
+                  "H2D/decode/D2H pipelined per row group)",
+           "parity": "decoded columns bit-identical to the generator's input arrays (full check after warm-up, tail check after the timed steps)",
+           "pcie_GBps": {"h2d": h2d_bytes / e2e_s / 1e9, "d2h": d2h_bytes / e2e_s / 1e9}}
     reader.close()
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": warmup,

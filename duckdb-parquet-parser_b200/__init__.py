@@ -52,7 +52,7 @@ class PageError(C.Structure):
 
 class Timings(C.Structure):
     _fields_ = [("dict_ms", C.c_float), ("fixed_ms", C.c_float), ("str_size_ms", C.c_float),
-                ("str_copy_ms", C.c_float), ("total_ms", C.c_float), ("launches", C.c_uint32)]
+                ("str_copy_ms", C.c_float), ("total_ms", C.c_float), ("launches", C.c_uint32), ("general_ms", C.c_float)]
 
 
 class ValDump(C.Structure):
@@ -95,6 +95,19 @@ class GenCol(C.Structure):
                 ("fixed", C.c_void_p), ("str_off", C.c_void_p), ("chars", C.c_void_p), ("is_null", C.c_void_p)]
 
 
+class Dst(C.Structure):
+    _fields_ = [("values", C.c_void_p), ("values_cap", C.c_uint64), ("validity", C.c_void_p), ("validity_cap", C.c_uint64)]
+
+
+class ReadStats(C.Structure):
+    _fields_ = [("num_slots", C.c_uint64), ("width", C.c_uint32), ("has_validity", C.c_int32), ("bytes_in", C.c_uint64),
+                ("bytes_out", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+
+
+class H2dRange(C.Structure):
+    _fields_ = [("host", C.c_void_p), ("image_off", C.c_uint64), ("len", C.c_uint64), ("chunk", C.c_uint32), ("reserved", C.c_uint32)]
+
+
 class Tables(C.Structure):
     _fields_ = [("n_chunks", C.c_uint32), ("n_pages", C.c_uint32), ("chunks", C.POINTER(ChunkDesc)),
                 ("pages", C.POINTER(PageDesc)), ("total_slots", C.c_uint64)]
@@ -105,7 +118,7 @@ PQG_SYMBOLS = [
     "pqg_ctx_create", "pqg_ctx_destroy", "pqg_last_error", "pqg_ctx_sync", "pqg_ctx_set_profiling", "pqg_device_count",
     "pqg_kernel_launches", "pqg_upload", "pqg_wrap_device", "pqg_buf_alloc", "pqg_buf_write", "pqg_buf_size",
     "pqg_buf_free", "pqg_buf_device_ptr", "pqg_host_alloc", "pqg_host_free", "pqg_plan_create", "pqg_plan_destroy",
-    "pqg_plan_set_image", "pqg_plan_run", "pqg_plan_finish", "pqg_plan_timings", "pqg_plan_timings_avg", "pqg_plan_num_slots",
+    "pqg_plan_set_image", "pqg_plan_run", "pqg_plan_run_pipelined", "pqg_plan_finish", "pqg_plan_timings", "pqg_plan_timings_avg", "pqg_plan_num_slots",
     "pqg_plan_value_width", "pqg_plan_values", "pqg_plan_validity", "pqg_plan_offsets", "pqg_plan_chars",
     "pqg_plan_chars_size", "pqg_plan_char_bases", "pqg_plan_bytes_in", "pqg_plan_bytes_out", "pqg_plan_download",
     "pqg_regex_compile", "pqg_dfa_free", "pqg_dfa_num_states", "pqg_dfa_match_host", "pqg_regex_scan",
@@ -117,7 +130,7 @@ PQR_SYMBOLS = [
     "pqr_schema_string", "pqr_page_scan_seconds", "pqr_file_size", "pqr_page_index", "pqr_read_page_data",
     "pqr_read_pages_chunk", "pqr_read_column_by_idx", "pqr_read_column", "pqr_read_column_rg", "pqr_read_pages",
     "pqr_string_iterator_dump", "pqr_valdump_free", "pqr_pagedump_free", "pqr_strdump_free", "pqr_read_columnar",
-    "pqr_columnar_free", "pqr_column_tables", "pqr_tables_free", "pqr_chunk_index", "pqr_regex_prune",
+    "pqr_columnar_free", "pqr_read_columns_into", "pqr_release_plans", "pqr_column_tables", "pqr_tables_free", "pqr_chunk_index", "pqr_regex_prune",
     "pqr_page_chunk_index",
 ]
 
@@ -166,6 +179,7 @@ def _declare(L):
     d("pqg_plan_destroy", None, vp, vp)
     d("pqg_plan_set_image", i32, vp, vp, vp)
     d("pqg_plan_run", i32, vp, vp)
+    d("pqg_plan_run_pipelined", i32, vp, vp, vp, C.POINTER(H2dRange), u32, vp, vp)
     d("pqg_plan_finish", i32, vp, vp, C.POINTER(PageError))
     d("pqg_plan_timings", i32, vp, C.POINTER(Timings))
     d("pqg_plan_timings_avg", i32, vp, u32, C.POINTER(Timings), C.POINTER(u32))
@@ -218,6 +232,8 @@ def _declare(L):
     d("pqr_strdump_free", None, C.POINTER(StrDump))
     d("pqr_read_columnar", i32, vp, i32, i32, C.POINTER(Columnar))
     d("pqr_columnar_free", None, C.POINTER(Columnar))
+    d("pqr_read_columns_into", i32, vp, C.POINTER(C.c_int32), i32, i32, C.POINTER(Dst), C.POINTER(ReadStats))
+    d("pqr_release_plans", None, vp)
     d("pqr_column_tables", i32, vp, i32, i32, C.POINTER(Tables))
     d("pqr_tables_free", None, C.POINTER(Tables))
     d("pqr_chunk_index", i64, vp, cp, u64, vp, i64)
@@ -378,6 +394,23 @@ class Reader:
         lib().pqr_columnar_free(C.byref(c))
         return out
 
+    def read_columns_into(self, cols, dsts, rg=-1):
+        """Streaming read of fixed-width columns into caller-owned host buffers.
+        dsts: per column (values_ptr, values_cap_bytes, validity_ptr | None, validity_cap_words).
+        Returns per-column stats dicts."""
+        n = len(cols)
+        ci = (C.c_int32 * n)(*cols)
+        ds = (Dst * n)()
+        for i, (vp_, vc, mp, mc) in enumerate(dsts):
+            ds[i] = Dst(vp_, vc, mp, mc)
+        st = (ReadStats * n)()
+        self._check(lib().pqr_read_columns_into(self.h, ci, n, rg, ds, st))
+        return [dict(num_slots=s.num_slots, width=s.width, has_validity=bool(s.has_validity), bytes_in=s.bytes_in,
+                     bytes_out=s.bytes_out, h2d_bytes=s.h2d_bytes, d2h_bytes=s.d2h_bytes) for s in st]
+
+    def release_plans(self):
+        lib().pqr_release_plans(self.h)
+
     def column_tables(self, col, rg=-1):
         """(ctypes array of ChunkDesc, ctypes array of PageDesc, total_slots), file offsets."""
         t = Tables()
@@ -487,13 +520,13 @@ class Plan:
         t = Timings()
         lib().pqg_plan_timings(self.h, C.byref(t))
         return dict(dict_ms=t.dict_ms, fixed_ms=t.fixed_ms, str_size_ms=t.str_size_ms, str_copy_ms=t.str_copy_ms,
-                    total_ms=t.total_ms, launches=t.launches)
+                    total_ms=t.total_ms, launches=t.launches, general_ms=t.general_ms)
 
     def timings_avg(self, last_n=0):
         t, n = Timings(), C.c_uint32(0)
         lib().pqg_plan_timings_avg(self.h, last_n, C.byref(t), C.byref(n))
         return dict(dict_ms=t.dict_ms, fixed_ms=t.fixed_ms, str_size_ms=t.str_size_ms, str_copy_ms=t.str_copy_ms,
-                    total_ms=t.total_ms, launches=t.launches, runs=n.value)
+                    total_ms=t.total_ms, launches=t.launches, general_ms=t.general_ms, runs=n.value)
 
     num_slots = property(lambda s: lib().pqg_plan_num_slots(s.h))
     width = property(lambda s: lib().pqg_plan_value_width(s.h))

@@ -15,6 +15,7 @@ struct pqg_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    cudaStream_t h2d = nullptr, d2h = nullptr; // copy-in / copy-out streams of the pipelined path (lazy)
     int sm_count = 148;
     bool profiling = false;
     uint64_t launches = 0;
@@ -35,6 +36,17 @@ struct pqg_plan {
     pqg_page_desc* d_pages = nullptr;
     uint8_t* d_dict = nullptr;
     size_t dict_bytes = 0;
+    TileDesc* d_tiles = nullptr;      // fast path: TMA-staged page tiles (fixed-width plans)
+    uint32_t n_tiles = 0;
+    uint32_t* d_slow_pages = nullptr; // pages for the general kernel: host-listed, then device-appended
+    uint32_t n_slow_host = 0;
+    uint32_t dict_smem = 0;
+    uint32_t max_dict_blocks = 1;
+    std::vector<uint32_t> chunk_tile_begin;  // n_chunks + 1: tiles of chunk c = [begin[c], begin[c+1])
+    std::vector<uint32_t> chunk_slow_begin;  // n_chunks + 1: host-listed slow pages of chunk c
+    std::vector<cudaEvent_t> pipe_ev;        // pipelined path: 2 events per chunk (H2D done, decode done)
+    cudaEvent_t ev_idle = nullptr;           // last decode of the previous run (guards the image buffer)
+    bool pipelined_in_flight = false;
     bool any_dict = false, any_def = false, is_str = false, is_bool = false;
     int phys = 0, width = 0;
     uint64_t n_slots = 0;
@@ -114,6 +126,8 @@ void pqg_ctx_destroy(pqg_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->h2d) cudaStreamDestroy(ctx->h2d);
+    if (ctx->d2h) cudaStreamDestroy(ctx->d2h);
     delete ctx;
 }
 
@@ -121,7 +135,10 @@ const char* pqg_last_error(const pqg_ctx* ctx) { return ctx ? ctx->err.c_str() :
 
 int pqg_ctx_sync(pqg_ctx* ctx) {
     if (!ctx) return PQG_ERR_ARG;
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (ctx->h2d) CU(ctx, cudaStreamSynchronize(ctx->h2d));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->d2h) CU(ctx, cudaStreamSynchronize(ctx->d2h));
     return PQG_OK;
 }
 
@@ -225,10 +242,12 @@ void pqg_plan_destroy(pqg_ctx* ctx, pqg_plan* p) {
     if (ctx) cudaSetDevice(ctx->device);
     cudaFree(p->d_chunks); cudaFree(p->d_pages); cudaFree(p->d_dict); cudaFree(p->d_values);
     cudaFree(p->d_validity); cudaFree(p->d_offsets); cudaFree(p->d_chars); cudaFree(p->d_page_chars);
-    cudaFree(p->d_page_char_base); cudaFree(p->d_bases); cudaFree(p->d_err);
+    cudaFree(p->d_page_char_base); cudaFree(p->d_bases); cudaFree(p->d_err); cudaFree(p->d_tiles); cudaFree(p->d_slow_pages);
     if (p->h_bases) cudaFreeHost(p->h_bases);
     if (p->h_err) cudaFreeHost(p->h_err);
     for (auto& slot : p->evr) for (auto& e : slot) if (e) cudaEventDestroy(e);
+    for (auto& e : p->pipe_ev) if (e) cudaEventDestroy(e);
+    if (p->ev_idle) cudaEventDestroy(p->ev_idle);
     delete p;
 }
 
@@ -286,6 +305,48 @@ int pqg_plan_create(pqg_ctx* ctx, const pqg_buf* image, const pqg_chunk_desc* ch
     p->n_slots = slots;
     p->dict_bytes = arena;
 
+    // fixed-width plans: cut tileable chunks into TMA tiles, list everything else for the
+    // general kernel
+    std::vector<TileDesc> tiles;
+    std::vector<uint32_t> slow;
+    if (!p->is_str) {
+        uint32_t max_dict_n = 0;
+        for (uint32_t c = 0; c < n_chunks; c++) {
+            const pqg_chunk_desc& s = chunks[c];
+            p->chunk_tile_begin.push_back(static_cast<uint32_t>(tiles.size()));
+            p->chunk_slow_begin.push_back(static_cast<uint32_t>(slow.size()));
+            if (s.has_dict) max_dict_n = std::max(max_dict_n, s.dict_num_values);
+            const bool tileable = chunk_is_tileable(s.phys_type, s.max_def, s.max_rep);
+            if (tileable && s.has_dict) {
+                uint64_t db = (static_cast<uint64_t>(s.dict_num_values) * p->width + 15) & ~uint64_t(15);
+                if (db <= static_cast<uint64_t>(kMaxSmemDictBytes)) p->dict_smem = std::max<uint32_t>(p->dict_smem, static_cast<uint32_t>(db));
+            }
+            TileDesc cur{};
+            uint64_t cur_end = 0;
+            auto flush = [&]() { if (cur.n_pages) { cur.byte_len = static_cast<uint32_t>(((cur_end + 15) & ~uint64_t(15)) - cur.byte_lo); tiles.push_back(cur); cur = TileDesc{}; } };
+            for (uint32_t q = s.first_page; q < s.first_page + s.n_pages; q++) {
+                const pqg_page_desc& pg = pages[q];
+                if (pg.num_values == 0) continue;
+                const uint64_t lo = pg.payload_off & ~uint64_t(15), end = pg.payload_off + pg.payload_size;
+                if (!tileable || ((end + 15) & ~uint64_t(15)) - lo > static_cast<uint64_t>(kTileBytes)) { flush(); slow.push_back(q); continue; }
+                if (cur.n_pages) {
+                    const bool fits = cur.n_pages < static_cast<uint32_t>(kTilePages) && pg.payload_off >= cur.byte_lo &&
+                                      ((end + 15) & ~uint64_t(15)) - cur.byte_lo <= static_cast<uint64_t>(kTileBytes) && q == cur.first_page + cur.n_pages;
+                    if (!fits) flush();
+                }
+                if (!cur.n_pages) { cur.byte_lo = lo; cur.first_page = q; cur.chunk_idx = c; cur_end = end; }
+                cur.n_pages++;
+                cur_end = std::max(cur_end, end);
+            }
+            flush();
+        }
+        p->chunk_tile_begin.push_back(static_cast<uint32_t>(tiles.size()));
+        p->chunk_slow_begin.push_back(static_cast<uint32_t>(slow.size()));
+        p->n_tiles = static_cast<uint32_t>(tiles.size());
+        p->n_slow_host = static_cast<uint32_t>(slow.size());
+        p->max_dict_blocks = std::max<uint32_t>(1, std::min<uint32_t>(64, (max_dict_n + 2047) / 2048));
+    }
+
     auto alloc = [&](void** ptr, size_t bytes) -> cudaError_t { return cudaMalloc(ptr, bytes ? bytes : 16); };
     cudaError_t e;
 #define PA(ptr, bytes) if ((e = alloc(reinterpret_cast<void**>(&(ptr)), (bytes))) != cudaSuccess) { pqg_plan_destroy(ctx, p); return cuda_fail(ctx, e, "cudaMalloc(plan)"); }
@@ -293,6 +354,10 @@ int pqg_plan_create(pqg_ctx* ctx, const pqg_buf* image, const pqg_chunk_desc* ch
     PA(p->d_pages, sizeof(pqg_page_desc) * std::max<uint32_t>(n_pages, 1));
     PA(p->d_err, sizeof(DevErr));
     if (p->any_dict) PA(p->d_dict, arena + 64);
+    if (!p->is_str) {
+        PA(p->d_tiles, sizeof(TileDesc) * std::max<size_t>(tiles.size(), 1));
+        PA(p->d_slow_pages, sizeof(uint32_t) * (static_cast<size_t>(n_pages) + 1));
+    }
     if (p->any_def) PA(p->d_validity, ((slots + 31) / 32 + 1) * 4);
     if (p->is_str) {
         PA(p->d_offsets, (slots + n_chunks + 1) * 4);
@@ -314,6 +379,10 @@ int pqg_plan_create(pqg_ctx* ctx, const pqg_buf* image, const pqg_chunk_desc* ch
     e = cudaMemcpyAsync(p->d_chunks, dc.data(), sizeof(DevChunk) * n_chunks, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess && n_pages)
         e = cudaMemcpyAsync(p->d_pages, p->pages.data(), sizeof(pqg_page_desc) * n_pages, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && !tiles.empty())
+        e = cudaMemcpyAsync(p->d_tiles, tiles.data(), sizeof(TileDesc) * tiles.size(), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && !slow.empty())
+        e = cudaMemcpyAsync(p->d_slow_pages, slow.data(), sizeof(uint32_t) * slow.size(), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) { pqg_plan_destroy(ctx, p); return cuda_fail(ctx, e, "descriptor upload"); }
     for (auto& slot : p->evr) for (auto& ev : slot) {
@@ -342,7 +411,39 @@ static DecodeParams make_params(const pqg_plan* p) {
     P.dict_arena = p->d_dict; P.values = p->d_values; P.validity = p->d_validity;
     P.offsets = p->d_offsets; P.chars = p->d_chars;
     P.page_chars = p->d_page_chars; P.page_char_base = p->d_page_char_base; P.err = p->d_err;
+    P.tiles = p->d_tiles; P.tile_lo = 0; P.tile_hi = p->n_tiles; P.dict_smem = p->dict_smem;
+    P.slow_lo = 0; P.slow_hi = p->n_slow_host; P.n_slow_host = p->n_slow_host; P.slow_pages = p->d_slow_pages;
+    P.chunk_lo = 0;
     return P;
+}
+
+// reset of the error record + work counters at the start of a run
+static cudaError_t reset_err(pqg_plan* p, cudaStream_t s) {
+    cudaError_t e = cudaMemsetAsync(p->d_err, 0xFF, 8, s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(reinterpret_cast<uint8_t*>(p->d_err) + 8, 0, sizeof(DevErr) - 8, s);
+    return e;
+}
+
+// decode of chunks [c0, c1) of a fixed-width plan on stream s; returns kernels launched or -1
+static int fixed_subrun(pqg_ctx* ctx, pqg_plan* p, uint32_t c0, uint32_t c1, bool reset_counters, cudaStream_t s, cudaError_t* err,
+                        cudaEvent_t ev_tiles_begin = nullptr, cudaEvent_t ev_tiles_end = nullptr) {
+    DecodeParams P = make_params(p);
+    int launches = 0;
+    cudaError_t e = cudaSuccess;
+    if (reset_counters) e = cudaMemsetAsync(&p->d_err->slow_count, 0, 8, s);
+    P.chunk_lo = c0;
+    P.tile_lo = p->chunk_tile_begin[c0]; P.tile_hi = p->chunk_tile_begin[c1];
+    P.slow_lo = p->chunk_slow_begin[c0]; P.slow_hi = p->chunk_slow_begin[c1];
+    bool any_dict = false;
+    for (uint32_t c = c0; c < c1; c++) any_dict = any_dict || p->chunks[c].has_dict;
+    if (e == cudaSuccess && any_dict) { e = launch_dict_prepare(P, c1 - c0, p->width, p->max_dict_blocks, s); launches++; }
+    if (e == cudaSuccess && ev_tiles_begin) e = cudaEventRecord(ev_tiles_begin, s);
+    if (e == cudaSuccess && P.tile_hi > P.tile_lo) { e = launch_fixed_tiles(P, p->width, ctx->sm_count, s); launches++; }
+    if (e == cudaSuccess && ev_tiles_end) e = cudaEventRecord(ev_tiles_end, s);
+    // the general kernel takes the host-listed pages plus whatever the tile kernel handed over
+    if (e == cudaSuccess && (P.slow_hi > P.slow_lo || P.tile_hi > P.tile_lo)) { e = launch_decode_fixed(P, p->width, p->is_bool, ctx->sm_count, s); launches++; }
+    *err = e;
+    return e == cudaSuccess ? launches : -1;
 }
 
 int pqg_plan_run(pqg_ctx* ctx, pqg_plan* p) {
@@ -354,19 +455,22 @@ int pqg_plan_run(pqg_ctx* ctx, pqg_plan* p) {
     p->timed = prof;
     if (prof) { p->ev = p->evr[p->runs_timed % pqg_plan::kTimingSlots]; p->runs_timed++; }
     if (prof) CU(ctx, cudaEventRecord(p->ev[0], s));
-    CU(ctx, cudaMemsetAsync(p->d_err, 0xFF, 8, s));
-    CU(ctx, cudaMemsetAsync(reinterpret_cast<uint8_t*>(p->d_err) + 8, 0, sizeof(DevErr) - 8, s));
+    CU(ctx, reset_err(p, s));
     if (p->d_validity) CU(ctx, cudaMemsetAsync(p->d_validity, 0, ((p->n_slots + 31) / 32 + 1) * 4, s));
     DecodeParams P = make_params(p);
-    if (p->any_dict) {
-        CU(ctx, launch_dict_prepare(P, P.n_chunks, p->is_str ? 0 : p->width, s));
-        launches++;
-    }
-    if (prof) CU(ctx, cudaEventRecord(p->ev[1], s));
     if (!p->is_str) {
-        if (P.page_end) { CU(ctx, launch_decode_fixed(P, p->width, p->is_bool, ctx->sm_count, s)); launches++; }
-        if (prof) { CU(ctx, cudaEventRecord(p->ev[2], s)); CU(ctx, cudaEventRecord(p->ev[3], s)); }
+        // ev0 .. ev1 dictionary preparation, ev1 .. ev2 the tile kernel, ev2 .. ev3 the general kernel
+        cudaError_t ce = cudaSuccess;
+        int n = fixed_subrun(ctx, p, 0, P.n_chunks, false, s, &ce, prof ? p->ev[1] : nullptr, prof ? p->ev[2] : nullptr);
+        if (n < 0) return cuda_fail(ctx, ce, "decode launch");
+        launches += static_cast<uint32_t>(n);
+        if (prof) CU(ctx, cudaEventRecord(p->ev[3], s));
     } else {
+        if (p->any_dict) {
+            CU(ctx, launch_dict_prepare(P, P.n_chunks, 0, 1, s));
+            launches++;
+        }
+        if (prof) CU(ctx, cudaEventRecord(p->ev[1], s));
         if (P.page_end) { CU(ctx, launch_str_sizes(P, ctx->sm_count, s)); launches++; }
         CU(ctx, launch_str_scan(P, p->d_bases, s));
         launches += 2;
@@ -402,8 +506,10 @@ static void elapsed_of(const pqg_plan* p, cudaEvent_t* ev, pqg_timings* tm) {
         cudaEventElapsedTime(&tm->str_size_ms, ev[1], ev[2]);
         cudaEventElapsedTime(&tm->str_copy_ms, ev[2], ev[3]);
         tm->fixed_ms = 0;
+        tm->general_ms = 0;
     } else {
         cudaEventElapsedTime(&tm->fixed_ms, ev[1], ev[2]);
+        cudaEventElapsedTime(&tm->general_ms, ev[2], ev[3]);
         tm->str_size_ms = tm->str_copy_ms = 0;
     }
     cudaEventElapsedTime(&tm->total_ms, ev[0], ev[4]);
@@ -414,6 +520,10 @@ int pqg_plan_finish(pqg_ctx* ctx, pqg_plan* p, pqg_page_error* err) {
     CU(ctx, cudaSetDevice(ctx->device));
     CU(ctx, cudaMemcpyAsync(p->h_err, p->d_err, sizeof(DevErr), cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if (p->pipelined_in_flight) { // the copy-out stream carries this plan's last D2H
+        if (ctx->d2h) CU(ctx, cudaStreamSynchronize(ctx->d2h));
+        p->pipelined_in_flight = false;
+    }
     if (p->timed) elapsed_of(p, p->ev, &p->tm);
     if (p->is_str) {
         uint64_t slots = p->n_slots;
@@ -445,6 +555,65 @@ int pqg_plan_finish(pqg_ctx* ctx, pqg_plan* p, pqg_page_error* err) {
     return PQG_OK;
 }
 
+int pqg_plan_run_pipelined(pqg_ctx* ctx, pqg_plan* p, pqg_buf* image, const pqg_h2d_range* ranges, uint32_t n_ranges,
+                           void* host_values, uint32_t* host_validity) {
+    if (!ctx || !p || !image || (!ranges && n_ranges)) return fail(ctx, PQG_ERR_ARG, "pqg_plan_run_pipelined: bad argument");
+    if (p->is_str) return fail(ctx, PQG_ERR_UNSUPPORTED, "pqg_plan_run_pipelined: BYTE_ARRAY plans need the size pass first; use pqg_plan_run");
+    if (image != p->image || !image->owned) return fail(ctx, PQG_ERR_ARG, "pqg_plan_run_pipelined: image must be the plan's own pqg_buf_alloc buffer");
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->h2d) CU(ctx, cudaStreamCreateWithFlags(&ctx->h2d, cudaStreamNonBlocking));
+    if (!ctx->d2h) CU(ctx, cudaStreamCreateWithFlags(&ctx->d2h, cudaStreamNonBlocking));
+    const uint32_t nc = static_cast<uint32_t>(p->chunks.size());
+    if (p->pipe_ev.empty()) {
+        p->pipe_ev.assign(2 * static_cast<size_t>(nc), nullptr);
+        for (auto& e : p->pipe_ev) CU(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        CU(ctx, cudaEventCreateWithFlags(&p->ev_idle, cudaEventDisableTiming));
+        CU(ctx, cudaEventRecord(p->ev_idle, ctx->stream));
+    }
+    for (uint32_t i = 0; i < n_ranges; i++) {
+        if (ranges[i].chunk >= nc || (i && ranges[i].chunk < ranges[i - 1].chunk) || ranges[i].image_off + ranges[i].len > image->size)
+            return fail(ctx, PQG_ERR_ARG, "pqg_plan_run_pipelined: ranges must be sorted by chunk and lie inside the image");
+    }
+    cudaStream_t s = ctx->stream;
+    const bool prof = ctx->profiling;
+    p->timed = prof;
+    if (prof) { p->ev = p->evr[p->runs_timed % pqg_plan::kTimingSlots]; p->runs_timed++; CU(ctx, cudaEventRecord(p->ev[0], s)); CU(ctx, cudaEventRecord(p->ev[1], s)); }
+    CU(ctx, reset_err(p, s));
+    if (p->d_validity) CU(ctx, cudaMemsetAsync(p->d_validity, 0, ((p->n_slots + 31) / 32 + 1) * 4, s));
+    // the image buffer is overwritten: wait for the kernels of the previous run of this plan
+    CU(ctx, cudaStreamWaitEvent(ctx->h2d, p->ev_idle, 0));
+    uint32_t launches = 0, r = 0;
+    for (uint32_t c = 0; c < nc; c++) {
+        for (; r < n_ranges && ranges[r].chunk == c; r++)
+            if (ranges[r].len) CU(ctx, cudaMemcpyAsync(image->d + ranges[r].image_off, ranges[r].host, ranges[r].len, cudaMemcpyHostToDevice, ctx->h2d));
+        cudaEvent_t ev_in = p->pipe_ev[2 * c], ev_k = p->pipe_ev[2 * c + 1];
+        CU(ctx, cudaEventRecord(ev_in, ctx->h2d));
+        CU(ctx, cudaStreamWaitEvent(s, ev_in, 0));
+        cudaError_t ce = cudaSuccess;
+        int n = fixed_subrun(ctx, p, c, c + 1, true, s, &ce);
+        if (n < 0) return cuda_fail(ctx, ce, "decode launch");
+        launches += static_cast<uint32_t>(n);
+        CU(ctx, cudaEventRecord(ev_k, s));
+        CU(ctx, cudaStreamWaitEvent(ctx->d2h, ev_k, 0));
+        const pqg_chunk_desc& ck = p->chunks[c];
+        if (host_values && ck.num_values)
+            CU(ctx, cudaMemcpyAsync(static_cast<uint8_t*>(host_values) + ck.out_row_base * p->width, p->d_values + ck.out_row_base * p->width,
+                                    ck.num_values * p->width, cudaMemcpyDeviceToHost, ctx->d2h));
+        if (host_validity && p->d_validity && ck.num_values) {
+            uint64_t w0 = ck.out_row_base >> 5, w1 = (ck.out_row_base + ck.num_values + 31) >> 5;
+            CU(ctx, cudaMemcpyAsync(host_validity + w0, p->d_validity + w0, (w1 - w0) * 4, cudaMemcpyDeviceToHost, ctx->d2h));
+        }
+    }
+    CU(ctx, cudaEventRecord(p->ev_idle, s));
+    if (prof) { CU(ctx, cudaEventRecord(p->ev[2], s)); CU(ctx, cudaEventRecord(p->ev[3], s)); CU(ctx, cudaEventRecord(p->ev[4], s)); }
+    p->tm.launches = launches;
+    p->last_launches = launches;
+    ctx->launches += launches;
+    p->ran = true;
+    p->pipelined_in_flight = true;
+    return PQG_OK;
+}
+
 int pqg_plan_timings(const pqg_plan* plan, pqg_timings* out) {
     if (!plan || !out) return PQG_ERR_ARG;
     *out = plan->tm;
@@ -464,10 +633,10 @@ int pqg_plan_timings_avg(const pqg_plan* plan, uint32_t last_n, pqg_timings* out
         pqg_timings t{};
         elapsed_of(plan, ev, &t);
         acc.dict_ms += t.dict_ms; acc.fixed_ms += t.fixed_ms; acc.str_size_ms += t.str_size_ms;
-        acc.str_copy_ms += t.str_copy_ms; acc.total_ms += t.total_ms;
+        acc.str_copy_ms += t.str_copy_ms; acc.total_ms += t.total_ms; acc.general_ms += t.general_ms;
         n++;
     }
-    if (n) { acc.dict_ms /= n; acc.fixed_ms /= n; acc.str_size_ms /= n; acc.str_copy_ms /= n; acc.total_ms /= n; }
+    if (n) { acc.dict_ms /= n; acc.fixed_ms /= n; acc.str_size_ms /= n; acc.str_copy_ms /= n; acc.total_ms /= n; acc.general_ms /= n; }
     acc.launches = plan->last_launches;
     *out = acc;
     if (n_used) *n_used = n;

@@ -44,27 +44,30 @@ template <> __device__ __forceinline__ U96 load_plain<12>(const uint8_t* p) {
 // ---------------------------------------------------------------------------------------------
 template <int W>
 __global__ void __launch_bounds__(256) k_dict_prepare(DecodeParams P) {
-    DevChunk& ck = P.chunks[blockIdx.x];
-    if (!ck.has_dict) { if (threadIdx.x == 0) ck.dict_ok_n = 0; return; }
+    // grid: (blocks per chunk, chunks)
+    DevChunk& ck = P.chunks[P.chunk_lo + blockIdx.y];
+    const bool first = blockIdx.x == 0 && threadIdx.x == 0;
+    if (!ck.has_dict) { if (first) ck.dict_ok_n = 0; return; }
     const uint8_t* src = P.image + ck.dict_off;
     uint8_t* dst = P.dict_arena + ck.dict_arena_off;
     const uint32_t n = ck.dict_n, size = ck.dict_size;
     if constexpr (W != 0) {
         // PLAIN fixed width: read_plain_value per entry (column_reader.cpp:229-248,257-264)
         uint32_t ok = min(n, size / W);
-        if (threadIdx.x == 0) {
+        if (first) {
             ck.dict_ok_n = ok;
             // the reference throws from ByteBuffer::check while reading entry `ok`
             if (ok < n) report_error(P.err, ck.first_page, PQG_PAGE_DICT_TRUNCATED, ok * W, W, size);
         }
         typename Elem<W>::T* out = reinterpret_cast<typename Elem<W>::T*>(dst);
-        for (uint32_t i = threadIdx.x; i < ok; i += blockDim.x) out[i] = load_plain<W>(src + static_cast<size_t>(i) * W);
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < ok; i += gridDim.x * blockDim.x)
+            out[i] = load_plain<W>(src + static_cast<size_t>(i) * W);
     } else {
         // BYTE_ARRAY: u32 length prefix + bytes (column_reader.cpp:249-253).  Entry table:
         // {start (byte offset of the chars inside the dictionary payload), len}.
         // TODO(perf): segment-parallel walk; one lane per dictionary for now.
         uint2* ent = reinterpret_cast<uint2*>(dst);
-        if (threadIdx.x == 0) {
+        if (first) {
             uint32_t pos = 0, k = 0;
             for (; k < n; k++) {
                 if (static_cast<uint64_t>(pos) + 4 > size) { report_error(P.err, ck.first_page, PQG_PAGE_DICT_TRUNCATED, pos, 4, size); break; }
@@ -218,28 +221,24 @@ __device__ __forceinline__ void decode_fixed_page(const DecodeParams& P, uint32_
     }
 }
 
+// The general kernel: every page shape, one warp per page, pages taken from the slow list
+// (listed by the host for OPTIONAL / BOOLEAN / INT96 / oversized pages, appended by the tile
+// kernel for the rest) through a work-stealing cursor.
 template <int W, bool BOOLP>
-__global__ void __launch_bounds__(kThreadsPerCta) k_decode_fixed(DecodeParams P, uint32_t dict_smem) {
+__global__ void __launch_bounds__(kThreadsPerCta) k_decode_fixed(DecodeParams P) {
     extern __shared__ __align__(16) uint8_t smem[];
     WarpScratch& ws = reinterpret_cast<WarpScratch*>(smem)[warp_id()];
-    uint8_t* sdict = smem + sizeof(WarpScratch) * kWarpsPerCta;
-    uint32_t p = P.page_begin + blockIdx.x * P.pages_per_cta;
-    const uint32_t p1 = min(P.page_end, p + P.pages_per_cta);
-    while (p < p1) { // one segment per column chunk inside this CTA's span
-        const DevChunk& ck = P.chunks[P.pages[p].chunk_idx];
-        const uint32_t seg_end = min(p1, ck.first_page + ck.n_pages);
-        const uint8_t* dictp = P.dict_arena + ck.dict_arena_off;
-        const uint32_t dbytes = ck.dict_ok_n * W;
-        if (ck.has_dict && dbytes && dbytes <= dict_smem) {
-            const uint4* s4 = reinterpret_cast<const uint4*>(dictp);
-            uint4* d4 = reinterpret_cast<uint4*>(sdict);
-            for (uint32_t i = threadIdx.x; i < (dbytes + 15u) / 16u; i += blockDim.x) d4[i] = s4[i];
-            __syncthreads();
-            dictp = sdict;
-        }
-        for (uint32_t q = p + warp_id(); q < seg_end; q += kWarpsPerCta) decode_fixed_page<W, BOOLP>(P, q, ck, dictp, ws);
-        __syncthreads();
-        p = seg_end;
+    const uint32_t n_host = P.slow_hi - P.slow_lo;
+    const uint32_t total = n_host + P.err->slow_count;
+    for (;;) {
+        uint32_t i = 0;
+        if (lane_id() == 0) i = atomicAdd(&P.err->slow_cursor, 1u);
+        i = __shfl_sync(0xffffffffu, i, 0);
+        if (i >= total) break;
+        const uint32_t q = i < n_host ? P.slow_pages[P.slow_lo + i] : P.slow_pages[P.n_slow_host + (i - n_host)];
+        const DevChunk& ck = P.chunks[P.pages[q].chunk_idx];
+        decode_fixed_page<W, BOOLP>(P, q, ck, P.dict_arena + ck.dict_arena_off, ws);
+        __syncwarp();
     }
 }
 
@@ -508,45 +507,41 @@ size_t decode_smem_bytes(bool with_dict) {
     return sizeof(WarpScratch) * kWarpsPerCta + (with_dict ? kMaxSmemDictBytes : 0);
 }
 
-cudaError_t launch_dict_prepare(const DecodeParams& p, uint32_t n_chunks, int width, cudaStream_t s) {
+cudaError_t launch_dict_prepare(const DecodeParams& p, uint32_t n_chunks, int width, uint32_t max_dict_blocks, cudaStream_t s) {
     if (n_chunks == 0) return cudaSuccess;
+    dim3 grid(width == 0 ? 1u : max_dict_blocks, n_chunks);
     switch (width) {
-        case 0: k_dict_prepare<0><<<n_chunks, 256, 0, s>>>(p); break;
-        case 1: k_dict_prepare<1><<<n_chunks, 256, 0, s>>>(p); break;
-        case 4: k_dict_prepare<4><<<n_chunks, 256, 0, s>>>(p); break;
-        case 8: k_dict_prepare<8><<<n_chunks, 256, 0, s>>>(p); break;
-        case 12: k_dict_prepare<12><<<n_chunks, 256, 0, s>>>(p); break;
+        case 0: k_dict_prepare<0><<<grid, 256, 0, s>>>(p); break;
+        case 1: k_dict_prepare<1><<<grid, 256, 0, s>>>(p); break;
+        case 4: k_dict_prepare<4><<<grid, 256, 0, s>>>(p); break;
+        case 8: k_dict_prepare<8><<<grid, 256, 0, s>>>(p); break;
+        case 12: k_dict_prepare<12><<<grid, 256, 0, s>>>(p); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
 }
 
 template <int W, bool BOOLP>
-static cudaError_t launch_fixed_t(DecodeParams p, bool with_dict, int sm_count, cudaStream_t s) {
-    const size_t smem = decode_smem_bytes(with_dict);
-    static bool attr_set[2] = {false, false};
-    if (!attr_set[with_dict]) {
-        cudaError_t e = cudaFuncSetAttribute(k_decode_fixed<W, BOOLP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             static_cast<int>(decode_smem_bytes(true)));
-        if (e != cudaSuccess) return e;
-        attr_set[with_dict] = true;
-    }
-    uint32_t n = p.page_end - p.page_begin;
-    if (n == 0) return cudaSuccess;
-    uint32_t grid = grid_for(n, sm_count, &p.pages_per_cta, with_dict ? 3 : 5);
-    k_decode_fixed<W, BOOLP><<<grid, kThreadsPerCta, smem, s>>>(p, with_dict ? kMaxSmemDictBytes : 0);
+static cudaError_t launch_fixed_t(DecodeParams p, int sm_count, uint32_t slow_hint, cudaStream_t s) {
+    const size_t smem = decode_smem_bytes(false);
+    cudaError_t e = cudaFuncSetAttribute(k_decode_fixed<W, BOOLP>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    // persistent CTAs over the work-stealing list; the list length is only known on the
+    // device (the tile kernel appends to it), so size the grid for the host-known part
+    uint32_t want = (slow_hint + kWarpsPerCta - 1) / kWarpsPerCta;
+    uint32_t cap = static_cast<uint32_t>(sm_count) * 4u;
+    uint32_t grid = want < static_cast<uint32_t>(sm_count) ? static_cast<uint32_t>(sm_count) : (want > cap ? cap : want);
+    k_decode_fixed<W, BOOLP><<<grid, kThreadsPerCta, smem, s>>>(p);
     return cudaGetLastError();
 }
 
 // `boolean_plain`: BOOLEAN chunks (PLAIN pages are bit-packed; dictionary entries are bytes).
 cudaError_t launch_decode_fixed(const DecodeParams& p, int width, bool boolean_plain, int sm_count, cudaStream_t s) {
-    // dictionary staging is only worth its shared memory when some chunk has one
-    bool with_dict = p.dict_arena != nullptr;
-    if (boolean_plain) return launch_fixed_t<1, true>(p, with_dict, sm_count, s);
+    if (boolean_plain) return launch_fixed_t<1, true>(p, sm_count, p.slow_hi - p.slow_lo, s);
     switch (width) {
-        case 4: return launch_fixed_t<4, false>(p, with_dict, sm_count, s);
-        case 8: return launch_fixed_t<8, false>(p, with_dict, sm_count, s);
-        case 12: return launch_fixed_t<12, false>(p, with_dict, sm_count, s);
+        case 4: return launch_fixed_t<4, false>(p, sm_count, p.slow_hi - p.slow_lo, s);
+        case 8: return launch_fixed_t<8, false>(p, sm_count, p.slow_hi - p.slow_lo, s);
+        case 12: return launch_fixed_t<12, false>(p, sm_count, p.slow_hi - p.slow_lo, s);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -17,6 +17,10 @@ constexpr int kTileNarrow = 1024;         // slots per tile when indices fit 16 
 constexpr int kTileWide = 512;
 constexpr int kMaxSmemDictBytes = 32 * 1024; // dictionaries up to this size are staged per CTA
 constexpr int kImagePad = 64;             // readable bytes required past the image end
+// TMA-staged tile pipeline of the fast fixed-width kernel (pqg_tiles.cu)
+constexpr int kTileBytes = 8192;          // image bytes per tile (16-byte aligned range covering whole pages)
+constexpr int kTilePages = 8;             // pages per tile (one per warp)
+constexpr int kTileStages = 4;            // ring depth per CTA
 
 // Device-side chunk record (built by the host API from pqg_chunk_desc).
 struct DevChunk {
@@ -38,12 +42,27 @@ struct DevChunk {
     uint32_t dict_ok_n;      // dictionary entries that parsed (written by the prepare kernel)
 };
 
-// First failing page (lowest page-table index) of a run.
+// First failing page (lowest page-table index) of a run, plus the per-run work counters
+// (one memset resets everything).
 struct DevErr {
     unsigned long long key;  // (page << 32) | code, atomicMin; ~0 = none
     uint32_t count;
     uint32_t d_page, d_pos, d_need, d_size; // details, valid when d_page == key >> 32
+    uint32_t bad_index;      // out-of-range dictionary indices seen in REQUIRED chunks
     uint32_t pad;
+    // work counters, reset before every (sub-)run: keep them last and together
+    uint32_t slow_count;     // pages the tile kernel handed to the general kernel
+    uint32_t slow_cursor;    // work-stealing cursor of the general kernel
+};
+
+// A run of consecutive pages of one chunk whose bytes are staged with one bulk copy.
+struct __align__(32) TileDesc {
+    uint64_t byte_lo;        // image offset, multiple of 16
+    uint32_t byte_len;       // multiple of 16, <= kTileBytes
+    uint32_t first_page;
+    uint32_t n_pages;        // <= kTilePages
+    uint32_t chunk_idx;
+    uint32_t pad[2];
 };
 
 struct DecodeParams {
@@ -63,11 +82,23 @@ struct DecodeParams {
     uint32_t* page_chars;    // BYTE_ARRAY pass 1 output: string bytes per page
     uint32_t* page_char_base;// exclusive prefix inside the chunk
     DevErr* err;
+    // fixed-width plans: fast tiles + the list of pages for the general kernel
+    const TileDesc* tiles;
+    uint32_t tile_lo, tile_hi; // tile range of this launch (a chunk range of the plan)
+    uint32_t tiles_per_cta;
+    uint32_t dict_smem;      // bytes of shared memory reserved for a staged dictionary
+    uint32_t slow_lo, slow_hi; // host-listed slow pages of this launch: slow_pages[slow_lo, slow_hi)
+    uint32_t n_slow_host;    // device-appended slow pages start at slow_pages[n_slow_host]
+    uint32_t* slow_pages;    // capacity: every page of the plan
+    uint32_t chunk_lo;       // first chunk of this launch (dictionary preparation)
 };
 
 // launchers (pqg_decode.cu)
-cudaError_t launch_dict_prepare(const DecodeParams& p, uint32_t n_chunks, int width, cudaStream_t s);
+cudaError_t launch_dict_prepare(const DecodeParams& p, uint32_t n_chunks, int width, uint32_t max_dict_blocks, cudaStream_t s);
 cudaError_t launch_decode_fixed(const DecodeParams& p, int width, bool boolean_plain, int sm_count, cudaStream_t s);
+// fast path (pqg_tiles.cu): PLAIN / regular-dictionary pages of REQUIRED 4- and 8-byte chunks
+cudaError_t launch_fixed_tiles(const DecodeParams& p, int width, int sm_count, cudaStream_t s);
+bool chunk_is_tileable(int phys_type, int max_def, int max_rep);
 cudaError_t launch_str_sizes(const DecodeParams& p, int sm_count, cudaStream_t s);
 cudaError_t launch_str_scan(const DecodeParams& p, uint64_t* total_chars, cudaStream_t s);
 cudaError_t launch_str_copy(const DecodeParams& p, int sm_count, cudaStream_t s);

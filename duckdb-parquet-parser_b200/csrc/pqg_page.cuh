@@ -44,7 +44,7 @@ __device__ __forceinline__ uint32_t ldbits(const uint8_t* base, uint32_t bit, ui
     return bw >= 32 ? v : (v & ((1u << bw) - 1u));
 }
 // same, but bytes at or past `avail` read as zero (slow; only for runs that overhang)
-__device__ __noinline__ uint32_t ldbits_bounded(const uint8_t* base, uint32_t bit, uint32_t bw, uint32_t avail) {
+static __device__ __noinline__ uint32_t ldbits_bounded(const uint8_t* base, uint32_t bit, uint32_t bw, uint32_t avail) {
     uint64_t acc = 0;
     uint32_t b0 = bit >> 3;
     for (uint32_t i = 0; i < 5; i++) {

@@ -1,0 +1,241 @@
+// pqg_tiles.cu -- the fast fixed-width decode kernel: TMA-staged page tiles.
+//
+// Covers what the reference's writer emits for REQUIRED INT32/INT64/FLOAT/DOUBLE chunks
+// (src/writer/parquet_writer.cpp:376-460):
+//   PLAIN pages          payload = the value array        (reader: column_reader.cpp:213-222,227-248)
+//   dictionary pages     u8 bit width + single bit-packed groups "03 <bw bytes>"
+//                        (reader: column_reader.cpp:174-196 over rle_decoder.hpp:55-65)
+// Anything else found in a tile (RLE runs inside the index stream, out-of-range indices,
+// truncated pages, bit width > 32) is NOT decoded here: the page is appended to the slow
+// list and the general kernel (pqg_decode.cu) handles it right after, with full error
+// reporting.  OPTIONAL / BOOLEAN / INT96 chunks and pages larger than a tile never enter a
+// tile (the host lists them for the general kernel directly).
+//
+// Data movement (HBM-bound, no tensor cores):
+//   * the plan's host side cuts every chunk into tiles: <= 8 consecutive pages whose bytes
+//     (page headers in between included -- pages of a chunk are contiguous in the file) fit
+//     8 KB.  One elected thread stages tile bytes + the tile's 8 page descriptors into a
+//     4-deep shared-memory ring with cp.async.bulk (1-D TMA, UBLKCP) completing on an
+//     mbarrier; 8 warps decode one page each out of shared memory.  No register staging,
+//     loads stay 3 tiles ahead of the math.
+//   * a dictionary that fits (<= 32 KB of values) is staged once per chunk with the same
+//     bulk copy; larger ones are gathered from L2 (the 126 MB L2 holds even the 8 MB
+//     dictionary of a 2^20-key chunk; outputs are written with streaming stores so they do
+//     not evict it).
+//   * outputs: 8 or 4 bytes per lane, consecutive lanes -> consecutive slots (coalesced).
+#include "pqg_page.cuh"
+
+namespace pqg {
+namespace {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// 1-D bulk copy global -> shared (TMA); dst/src 16-byte aligned, bytes a multiple of 16
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra LAB_DONE;\n"
+        "bra LAB_WAIT;\n"
+        "LAB_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+template <int W> struct FElem;
+template <> struct FElem<4> { using T = uint32_t; };
+template <> struct FElem<8> { using T = uint64_t; };
+
+template <int W> __device__ __forceinline__ typename FElem<W>::T ld_elem(const uint8_t* p);
+template <> __device__ __forceinline__ uint32_t ld_elem<4>(const uint8_t* p) { return ld32u(p); }
+template <> __device__ __forceinline__ uint64_t ld_elem<8>(const uint8_t* p) { return ld64u(p); }
+
+template <typename T> __device__ __forceinline__ void st_stream(T* p, T v);
+template <> __device__ __forceinline__ void st_stream<uint32_t>(uint32_t* p, uint32_t v) { __stcs(p, v); }
+template <> __device__ __forceinline__ void st_stream<uint64_t>(uint64_t* p, uint64_t v) {
+    __stcs(reinterpret_cast<unsigned long long*>(p), static_cast<unsigned long long>(v));
+}
+
+constexpr int kStageBytes = kTileBytes + 16 + kTilePages * static_cast<int>(sizeof(pqg_page_desc));
+constexpr int kBarBytes = 64 + kTileStages * 32; // kTileStages + 1 mbarriers, then per-stage tile meta
+
+struct TileMeta { uint64_t byte_lo; uint32_t first_page; uint32_t n_pages; uint32_t chunk_idx; uint32_t pad; };
+
+__device__ __forceinline__ void to_slow(const DecodeParams& P, uint32_t q) {
+    // one lane
+    uint32_t k = atomicAdd(&P.err->slow_count, 1u);
+    P.slow_pages[P.n_slow_host + k] = q;
+}
+
+// One warp decodes one page out of the staged tile.  `pg` = first payload byte (shared).
+template <int W>
+__device__ __forceinline__ void fast_page(const DecodeParams& P, uint32_t q, const pqg_page_desc& pd, const uint8_t* pg,
+                                          bool chunk_has_dict, const uint8_t* dictp, uint32_t dict_n, bool dict_in_smem) {
+    using T = typename FElem<W>::T;
+    const uint32_t l = lane_id();
+    const uint32_t n = pd.num_values, size = pd.payload_size;
+    if (n == 0) return;
+    T* out = reinterpret_cast<T*>(P.values) + pd.out_row_base;
+    if (!((pd.flags & PQG_PAGE_FLAG_DICT) && chunk_has_dict)) {
+        // PLAIN: read_plain_value per slot == a shifted copy
+        if (static_cast<uint64_t>(n) * W > size) { if (l == 0) to_slow(P, q); return; }
+        uint32_t e = l;
+        for (; e + 96 < n; e += 128) {
+            T v0 = ld_elem<W>(pg + static_cast<size_t>(e) * W);
+            T v1 = ld_elem<W>(pg + static_cast<size_t>(e + 32) * W);
+            T v2 = ld_elem<W>(pg + static_cast<size_t>(e + 64) * W);
+            T v3 = ld_elem<W>(pg + static_cast<size_t>(e + 96) * W);
+            st_stream<T>(out + e, v0); st_stream<T>(out + e + 32, v1);
+            st_stream<T>(out + e + 64, v2); st_stream<T>(out + e + 96, v3);
+        }
+        for (; e < n; e += 32) st_stream<T>(out + e, ld_elem<W>(pg + static_cast<size_t>(e) * W));
+        return;
+    }
+    // dictionary indices: u8 bit width, then the RLE / bit-packed hybrid stream
+    if (size < 1) { if (l == 0) to_slow(P, q); return; }
+    const uint32_t bw = pg[0];
+    const uint8_t* s = pg + 1;
+    if (bw > 32 || !check_regular(s, size - 1, bw, n)) { if (l == 0) to_slow(P, q); return; }
+    const T* dict = reinterpret_cast<const T*>(dictp);
+    bool bad = false;
+    uint32_t v = l;
+    for (; v + 96 < n; v += 128) {
+        uint32_t i0 = regular_index(s, bw, v), i1 = regular_index(s, bw, v + 32);
+        uint32_t i2 = regular_index(s, bw, v + 64), i3 = regular_index(s, bw, v + 96);
+        bad = bad || i0 >= dict_n || i1 >= dict_n || i2 >= dict_n || i3 >= dict_n;
+        T x0 = 0, x1 = 0, x2 = 0, x3 = 0;
+        if (dict_in_smem) {
+            if (i0 < dict_n) x0 = dict[i0]; if (i1 < dict_n) x1 = dict[i1];
+            if (i2 < dict_n) x2 = dict[i2]; if (i3 < dict_n) x3 = dict[i3];
+        } else {
+            if (i0 < dict_n) x0 = __ldg(dict + i0); if (i1 < dict_n) x1 = __ldg(dict + i1);
+            if (i2 < dict_n) x2 = __ldg(dict + i2); if (i3 < dict_n) x3 = __ldg(dict + i3);
+        }
+        st_stream<T>(out + v, x0); st_stream<T>(out + v + 32, x1);
+        st_stream<T>(out + v + 64, x2); st_stream<T>(out + v + 96, x3);
+    }
+    for (; v < n; v += 32) {
+        uint32_t i0 = regular_index(s, bw, v);
+        T x0 = 0;
+        if (i0 < dict_n) x0 = dict_in_smem ? dict[i0] : __ldg(dict + i0); else bad = true;
+        st_stream<T>(out + v, x0);
+    }
+    // an out-of-range index is a NULL in the reference (column_reader.cpp:190-194): the
+    // general kernel redoes the page with the validity semantics
+    if (__any_sync(0xffffffffu, bad) && l == 0) { to_slow(P, q); atomicAdd(&P.err->bad_index, 1u); }
+}
+
+template <int W>
+__global__ void __launch_bounds__(kThreadsPerCta, 3) k_fixed_tiles(const DecodeParams P) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);                    // [kTileStages] tiles, [kTileStages] dictionary
+    TileMeta* meta = reinterpret_cast<TileMeta*>(smem + 64);               // [kTileStages]
+    uint8_t* ring = smem + kBarBytes;
+    uint8_t* sdict = ring + kTileStages * kStageBytes;
+    const uint32_t t0 = P.tile_lo + blockIdx.x * P.tiles_per_cta;
+    const uint32_t t1 = min(P.tile_hi, t0 + P.tiles_per_cta);
+    if (t0 >= t1) return;
+    const uint32_t tid = threadIdx.x;
+    if (tid == 0) {
+        for (int i = 0; i <= kTileStages; i++) mbar_init(&full[i], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    auto issue = [&](uint32_t t, const TileDesc& td) { // thread 0
+        const uint32_t st = (t - t0) % kTileStages;
+        uint8_t* dst = ring + st * kStageBytes;
+        meta[st] = TileMeta{td.byte_lo, td.first_page, td.n_pages, td.chunk_idx, 0};
+        const uint32_t pbytes = td.n_pages * static_cast<uint32_t>(sizeof(pqg_page_desc));
+        mbar_expect_tx(&full[st], td.byte_len + pbytes);
+        bulk_g2s(dst, P.image + td.byte_lo, td.byte_len, &full[st]);
+        bulk_g2s(dst + kTileBytes + 16, P.pages + td.first_page, pbytes, &full[st]);
+    };
+    if (tid == 0) {
+        for (uint32_t t = t0; t < min(t1, t0 + kTileStages); t++) issue(t, P.tiles[t]);
+    }
+    uint32_t cur_chunk = 0xffffffffu, dict_n = 0, dict_phase = 0;
+    const uint8_t* dictp = nullptr;
+    bool has_dict = false, dict_in_smem = false;
+    for (uint32_t t = t0; t < t1; t++) {
+        TileDesc nxt{};
+        const bool refill = tid == 0 && t + kTileStages < t1;
+        if (refill) nxt = P.tiles[t + kTileStages]; // in flight while the pages are decoded
+        const uint32_t st = (t - t0) % kTileStages;
+        mbar_wait(&full[st], ((t - t0) / kTileStages) & 1u);
+        const uint8_t* tile = ring + st * kStageBytes;
+        const TileMeta tm = meta[st];
+        if (tm.chunk_idx != cur_chunk) { // uniform across the CTA
+            cur_chunk = tm.chunk_idx;
+            const DevChunk& ck = P.chunks[cur_chunk];
+            has_dict = ck.has_dict;
+            dict_n = ck.dict_ok_n;
+            dictp = P.dict_arena + ck.dict_arena_off;
+            dict_in_smem = false;
+            const uint32_t dbytes = (dict_n * W + 15u) & ~15u;
+            if (has_dict && dbytes && dbytes <= P.dict_smem) {
+                __syncthreads(); // nobody reads the previous dictionary any more
+                if (tid == 0) { mbar_expect_tx(&full[kTileStages], dbytes); bulk_g2s(sdict, dictp, dbytes, &full[kTileStages]); }
+                mbar_wait(&full[kTileStages], dict_phase);
+                dict_phase ^= 1;
+                dictp = sdict;
+                dict_in_smem = true;
+            }
+        }
+        const pqg_page_desc* pds = reinterpret_cast<const pqg_page_desc*>(tile + kTileBytes + 16);
+        for (uint32_t j = warp_id(); j < tm.n_pages; j += kWarpsPerCta) {
+            const pqg_page_desc pd = pds[j];
+            fast_page<W>(P, tm.first_page + j, pd, tile + (pd.payload_off - tm.byte_lo), has_dict, dictp, dict_n, dict_in_smem);
+        }
+        __syncthreads(); // stage st is free again
+        if (refill) issue(t + kTileStages, nxt);
+    }
+}
+
+} // namespace
+
+bool chunk_is_tileable(int phys_type, int max_def, int max_rep) {
+    const bool w48 = phys_type == PQG_INT32 || phys_type == PQG_FLOAT || phys_type == PQG_INT64 || phys_type == PQG_DOUBLE;
+    return w48 && max_def <= 0 && max_rep <= 0;
+}
+
+template <int W>
+static cudaError_t launch_tiles_t(DecodeParams p, int sm_count, cudaStream_t s) {
+    const size_t smem = kBarBytes + static_cast<size_t>(kTileStages) * kStageBytes + p.dict_smem;
+    // (attributes are per device: set on every launch, it is cheap)
+    cudaError_t e = cudaFuncSetAttribute(k_fixed_tiles<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    // contiguous tile spans per CTA (a CTA stages a chunk's dictionary once); two waves of
+    // resident CTAs when there is enough work
+    int resident = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k_fixed_tiles<W>, kThreadsPerCta, smem);
+    if (resident < 1) resident = 1;
+    uint32_t target = static_cast<uint32_t>(sm_count) * static_cast<uint32_t>(resident) * 2u;
+    const uint32_t n_tiles = p.tile_hi - p.tile_lo;
+    uint32_t per = (n_tiles + target - 1) / target;
+    if (per < 4) per = 4;
+    p.tiles_per_cta = per;
+    const uint32_t grid = (n_tiles + per - 1) / per;
+    k_fixed_tiles<W><<<grid, kThreadsPerCta, smem, s>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fixed_tiles(const DecodeParams& p, int width, int sm_count, cudaStream_t s) {
+    if (p.tile_hi <= p.tile_lo) return cudaSuccess;
+    if (width == 4) return launch_tiles_t<4>(p, sm_count, s);
+    if (width == 8) return launch_tiles_t<8>(p, sm_count, s);
+    return cudaErrorInvalidValue;
+}
+
+} // namespace pqg

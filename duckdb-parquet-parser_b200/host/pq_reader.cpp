@@ -452,12 +452,8 @@ ColumnTables ParquetReader::column_tables(int col_idx, int row_group_idx) const 
     return t;
 }
 
-DecodedColumn ParquetReader::read_column_columnar(int col_idx, int row_group_idx) {
-    if (row_group_idx >= static_cast<int>(metadata_.row_groups.size())) throw std::runtime_error("Invalid row group index");
-    if (col_idx < 0 || col_idx >= static_cast<int>(columns_.size())) throw std::runtime_error("Invalid column index");
-    const ColumnInfo& ci = columns_[static_cast<size_t>(col_idx)];
-    ColumnTables t = column_tables(col_idx, row_group_idx);
-    // upload only this column's byte ranges, packed; rebase the tables onto the packed image
+// this column's byte ranges, packed (one range per table chunk); rebases the tables onto the packed image
+static PackedImage pack_column(ColumnTables& t, uint64_t file_size) {
     PackedImage img;
     for (pqg_chunk_desc& c : t.chunks) {
         uint64_t lo = c.has_dict ? c.dict_off : UINT64_MAX, hi = c.has_dict ? c.dict_off + c.dict_size : 0;
@@ -465,15 +461,117 @@ DecodedColumn ParquetReader::read_column_columnar(int col_idx, int row_group_idx
             lo = std::min(lo, t.pages[q].payload_off);
             hi = std::max(hi, t.pages[q].payload_off + t.pages[q].payload_size);
         }
-        if (hi > file_size_) throw std::runtime_error("ByteBuffer: read beyond end (pos=" + std::to_string(lo) + " need=" +
-                                                      std::to_string(hi - lo) + " size=" + std::to_string(file_size_) + ")");
+        if (lo == UINT64_MAX) { lo = 0; hi = 0; }
+        if (hi > file_size) throw std::runtime_error("ByteBuffer: read beyond end (pos=" + std::to_string(lo) + " need=" +
+                                                     std::to_string(hi - lo) + " size=" + std::to_string(file_size) + ")");
         uint64_t dst = img.add(lo, hi - lo);
         int64_t delta = static_cast<int64_t>(dst) - static_cast<int64_t>(lo);
         if (c.has_dict) c.dict_off = static_cast<uint64_t>(static_cast<int64_t>(c.dict_off) + delta);
         for (uint32_t q = c.first_page; q < c.first_page + c.n_pages; q++)
             t.pages[q].payload_off = static_cast<uint64_t>(static_cast<int64_t>(t.pages[q].payload_off) + delta);
     }
+    return img;
+}
+
+DecodedColumn ParquetReader::read_column_columnar(int col_idx, int row_group_idx) {
+    if (row_group_idx >= static_cast<int>(metadata_.row_groups.size())) throw std::runtime_error("Invalid row group index");
+    if (col_idx < 0 || col_idx >= static_cast<int>(columns_.size())) throw std::runtime_error("Invalid column index");
+    const ColumnInfo& ci = columns_[static_cast<size_t>(col_idx)];
+    ColumnTables t = column_tables(col_idx, row_group_idx);
+    PackedImage img = pack_column(t, file_size_);
     return decode_packed(Device::get(device_), data_, img, t, ci.type);
+}
+
+// ── pipelined reads with cached plans ───────────────────────────────────────────────────
+struct CachedPlan {
+    ColumnTables t;
+    PackedImage img;
+    std::vector<pqg_h2d_range> ranges;
+    pqg_ctx* ctx = nullptr;
+    pqg_buf* buf = nullptr;
+    pqg_plan* plan = nullptr;
+    ParquetType type = ParquetType::INT32;
+    uint32_t width = 0;
+    uint64_t h2d_bytes = 0;
+    ~CachedPlan() {
+        if (plan) pqg_plan_destroy(ctx, plan);
+        if (buf) pqg_buf_free(ctx, buf);
+    }
+};
+
+CachedPlan& ParquetReader::cached_plan(int col_idx, int row_group_idx) {
+    if (row_group_idx >= static_cast<int>(metadata_.row_groups.size())) throw std::runtime_error("Invalid row group index");
+    if (col_idx < 0 || col_idx >= static_cast<int>(columns_.size())) throw std::runtime_error("Invalid column index");
+    auto key = std::make_pair(col_idx, row_group_idx < 0 ? -1 : row_group_idx);
+    auto it = plans_.find(key);
+    if (it != plans_.end()) return *it->second;
+    auto cp = std::make_unique<CachedPlan>();
+    cp->type = columns_[static_cast<size_t>(col_idx)].type;
+    static const uint32_t widths[] = {1, 4, 8, 12, 4, 8, 0, 0};
+    cp->width = widths[static_cast<int>(cp->type) & 7];
+    cp->t = column_tables(col_idx, row_group_idx);
+    cp->img = pack_column(cp->t, file_size_);
+    cp->ctx = Device::get(device_).ctx();
+    if (cp->t.chunks.empty()) { auto& ref = *cp; plans_[key] = std::move(cp); return ref; }
+    if (pqg_buf_alloc(cp->ctx, cp->img.size, &cp->buf) != PQG_OK) throw_ctx(cp->ctx, "device image");
+    if (pqg_plan_create(cp->ctx, cp->buf, cp->t.chunks.data(), static_cast<uint32_t>(cp->t.chunks.size()), cp->t.pages.data(),
+                        static_cast<uint32_t>(cp->t.pages.size()), &cp->plan) != PQG_OK)
+        throw std::runtime_error(pqg_last_error(cp->ctx));
+    for (size_t c = 0; c < cp->img.ranges.size(); c++) {
+        const Range& r = cp->img.ranges[c];
+        cp->ranges.push_back(pqg_h2d_range{data_ + r.src_off, r.dst_off, r.len, static_cast<uint32_t>(c), 0});
+        cp->h2d_bytes += r.len;
+    }
+    auto& ref = *cp;
+    plans_[key] = std::move(cp);
+    return ref;
+}
+
+void ParquetReader::release_plans() { plans_.clear(); }
+
+void ParquetReader::read_columns_into(const int* col_idx, int n_cols, int row_group_idx, const ColumnDst* dsts, ColumnReadStats* stats) {
+    if (n_cols < 0 || (n_cols && (!col_idx || !dsts))) throw std::runtime_error("read_columns_into: bad argument");
+    std::vector<CachedPlan*> cps;
+    for (int i = 0; i < n_cols; i++) {
+        CachedPlan& cp = cached_plan(col_idx[i], row_group_idx);
+        if (cp.type == ParquetType::BYTE_ARRAY || cp.width == 0)
+            throw std::runtime_error("read_columns_into: fixed-width columns only (use read_column_columnar for BYTE_ARRAY)");
+        const uint64_t need = cp.t.total_slots * cp.width;
+        if (dsts[i].values_cap < need || (need && !dsts[i].values)) throw std::runtime_error("read_columns_into: values buffer too small");
+        cps.push_back(&cp);
+    }
+    // enqueue every column (asynchronous), then wait column by column
+    for (int i = 0; i < n_cols; i++) {
+        CachedPlan& cp = *cps[static_cast<size_t>(i)];
+        if (!cp.plan) continue;
+        const bool has_validity = pqg_plan_validity(cp.plan) != nullptr;
+        uint32_t* vdst = nullptr;
+        if (has_validity && dsts[i].validity) {
+            if (dsts[i].validity_cap < (cp.t.total_slots + 31) / 32) throw std::runtime_error("read_columns_into: validity buffer too small");
+            vdst = dsts[i].validity;
+        }
+        if (pqg_plan_run_pipelined(cp.ctx, cp.plan, cp.buf, cp.ranges.data(), static_cast<uint32_t>(cp.ranges.size()),
+                                   dsts[i].values, vdst) != PQG_OK) throw_ctx(cp.ctx, "decode");
+    }
+    std::string first_error;
+    for (int i = 0; i < n_cols; i++) {
+        CachedPlan& cp = *cps[static_cast<size_t>(i)];
+        ColumnReadStats st;
+        st.num_slots = cp.t.total_slots;
+        st.width = cp.width;
+        if (cp.plan) {
+            pqg_page_error pe;
+            int rc = pqg_plan_finish(cp.ctx, cp.plan, &pe);
+            if (rc != PQG_OK && first_error.empty()) first_error = pqg_last_error(cp.ctx);
+            st.has_validity = pqg_plan_validity(cp.plan) != nullptr;
+            st.bytes_in = pqg_plan_bytes_in(cp.plan);
+            st.bytes_out = pqg_plan_bytes_out(cp.plan);
+            st.h2d_bytes = cp.h2d_bytes;
+            st.d2h_bytes = cp.t.total_slots * cp.width + (st.has_validity && dsts[i].validity ? ((cp.t.total_slots + 31) / 32) * 4 : 0);
+        }
+        if (stats) stats[i] = st;
+    }
+    if (!first_error.empty()) throw std::runtime_error(first_error);
 }
 
 std::vector<Value> ParquetReader::read_column(const std::string& col_name, size_t row_group_idx) {

@@ -12,6 +12,7 @@
 // reference spends ~78 % of its time copying Values.
 #pragma once
 #include <functional>
+#include <map>
 #include <memory>
 #include <string>
 #include <tuple>
@@ -123,6 +124,23 @@ private:
 };
 
 class ParquetReader;
+struct CachedPlan; // pq_reader.cpp: descriptor tables + device image + decode plan of one column
+
+// Destination of a pipelined column read (caller-owned host memory; pinned memory keeps the
+// device->host copies asynchronous).
+struct ColumnDst {
+    void* values = nullptr;          // num_slots * width bytes
+    uint64_t values_cap = 0;         // bytes available behind `values`
+    uint32_t* validity = nullptr;    // ceil(num_slots / 32) words, or nullptr
+    uint64_t validity_cap = 0;       // words available behind `validity`
+};
+struct ColumnReadStats {
+    uint64_t num_slots = 0;
+    uint32_t width = 0;
+    int32_t has_validity = 0;
+    uint64_t bytes_in = 0, bytes_out = 0;   // algorithmic payload / output bytes
+    uint64_t h2d_bytes = 0, d2h_bytes = 0;  // bytes actually copied each way
+};
 
 class StringColumnIterator {
 public:
@@ -186,6 +204,12 @@ public:
     // columnar variants: row_group_idx < 0 = all row groups
     DecodedColumn read_column_columnar(int col_idx, int row_group_idx = -1);
     ColumnTables column_tables(int col_idx, int row_group_idx = -1) const;
+    // Streaming read of fixed-width columns from the (host) file image into caller-owned host
+    // buffers: per row group H2D -> decode -> D2H on three streams, all requested columns in
+    // one pipeline.  Descriptor tables, the device image and the plan of a column are built on
+    // first use and kept until release_plans() / close.  row_group_idx < 0 = all row groups.
+    void read_columns_into(const int* col_idx, int n_cols, int row_group_idx, const ColumnDst* dsts, ColumnReadStats* stats);
+    void release_plans();
 
     StringColumnIterator column_iterator(const std::string& col_name);
 
@@ -227,6 +251,8 @@ private:
     std::vector<PageIndexEntry> page_index_;
     std::vector<std::vector<std::vector<PageRecord>>> chunk_pages_; // [rg][chunk column]
     std::vector<std::vector<size_t>> chunk_first_page_;              // [rg][chunk column] -> global id
+    std::map<std::pair<int, int>, std::unique_ptr<CachedPlan>> plans_; // (column, row group | -1)
+    CachedPlan& cached_plan(int col_idx, int row_group_idx);
 };
 
 } // namespace pqg

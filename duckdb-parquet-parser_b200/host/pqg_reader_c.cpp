@@ -249,6 +249,20 @@ int pqr_read_columnar(pqr_reader* r, int col, int rg, pqr_columnar* out) {
         return 0;
     }, -1);
 }
+int pqr_read_columns_into(pqr_reader* r, const int32_t* cols, int32_t n_cols, int32_t rg, const pqr_dst* dsts, pqr_read_stats* stats) {
+    return guarded([&]() -> int {
+        std::vector<int> ci(cols, cols + (n_cols > 0 ? n_cols : 0));
+        std::vector<ColumnDst> d(ci.size());
+        std::vector<ColumnReadStats> st(ci.size());
+        for (size_t i = 0; i < ci.size(); i++) d[i] = ColumnDst{dsts[i].values, dsts[i].values_cap, dsts[i].validity, dsts[i].validity_cap};
+        r->r.read_columns_into(ci.data(), static_cast<int>(ci.size()), rg, d.data(), st.data());
+        if (stats) for (size_t i = 0; i < ci.size(); i++)
+            stats[i] = pqr_read_stats{st[i].num_slots, st[i].width, st[i].has_validity, st[i].bytes_in, st[i].bytes_out, st[i].h2d_bytes, st[i].d2h_bytes};
+        return 0;
+    }, -1);
+}
+void pqr_release_plans(pqr_reader* r) { if (r) r->r.release_plans(); }
+
 void pqr_columnar_free(pqr_columnar* c) {
     if (c && c->owner) delete static_cast<ColumnarOwner*>(c->owner);
     if (c) std::memset(c, 0, sizeof(*c));

@@ -114,11 +114,12 @@ typedef struct pqg_dfa pqg_dfa;   /* host-compiled regex automaton */
  * stream (milliseconds); only recorded after pqg_ctx_set_profiling(ctx, 1). */
 typedef struct pqg_timings {
     float dict_ms;    /* dictionary preparation */
-    float fixed_ms;   /* fixed-width page decode (PLAIN copy + dictionary gather + levels) */
+    float fixed_ms;   /* fixed-width plans: the TMA tile kernel (PLAIN copy + regular dictionary pages) */
     float str_size_ms;/* string pass 1: per-page byte totals + scan */
     float str_copy_ms;/* string pass 2: offsets + chars */
     float total_ms;
     uint32_t launches;/* kernels launched by the run */
+    float general_ms; /* fixed-width plans: the general kernel (levels, RLE runs, big pages) */
 } pqg_timings;
 
 /* ---- context ------------------------------------------------------------------------- */
@@ -156,6 +157,25 @@ PQG_API int pqg_plan_set_image(pqg_ctx* ctx, pqg_plan* plan, const pqg_buf* imag
 /* enqueue the decode on the context's stream.  Asynchronous, except that the first run of
  * a BYTE_ARRAY plan waits for the size pass to learn the output size. */
 PQG_API int pqg_plan_run(pqg_ctx* ctx, pqg_plan* plan);
+/* Pipelined decode of a fixed-width plan straight from HOST memory into HOST memory.  For every
+ * chunk of the plan, in table order: H2D of the chunk's byte ranges on the context's copy-in
+ * stream -> decode of that chunk on the compute stream -> D2H of its rows (and validity words) on
+ * the copy-out stream, chained by events, so both transfer directions overlap the kernels.
+ * `image` must be the plan's image and come from pqg_buf_alloc; `ranges` (sorted by chunk)
+ * name the host bytes of each chunk and where they go in the image.  host_values /
+ * host_validity (may be NULL) receive the decoded column; pinned memory keeps the copies
+ * asynchronous.  Returns after enqueueing: several plans can be in flight on one context;
+ * pqg_plan_finish waits for this plan and reports page errors.  BYTE_ARRAY plans are refused
+ * (PQG_ERR_UNSUPPORTED): their output size needs the size pass first. */
+typedef struct pqg_h2d_range {
+    const void* host;    /* source bytes */
+    uint64_t image_off;  /* destination offset in the plan's image */
+    uint64_t len;
+    uint32_t chunk;      /* table chunk the bytes belong to */
+    uint32_t reserved;
+} pqg_h2d_range;
+PQG_API int pqg_plan_run_pipelined(pqg_ctx* ctx, pqg_plan* plan, pqg_buf* image, const pqg_h2d_range* ranges,
+                                   uint32_t n_ranges, void* host_values, uint32_t* host_validity);
 /* wait for the run and report page errors; PQG_ERR_PAGE when err->count > 0 */
 PQG_API int pqg_plan_finish(pqg_ctx* ctx, pqg_plan* plan, pqg_page_error* err);
 PQG_API int pqg_plan_timings(const pqg_plan* plan, pqg_timings* out);

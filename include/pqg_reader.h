@@ -140,6 +140,22 @@ PQG_API void pqr_columnar_free(pqr_columnar* c);
 PQG_API int pqr_column_tables(const pqr_reader* r, int col, int rg, pqr_tables* out);
 PQG_API void pqr_tables_free(pqr_tables* t);
 
+/* Streaming read of fixed-width columns (the fast path of ParquetReader::read_column for callers
+ * that take columnar buffers instead of std::vector<Value>): host file image in, caller-owned
+ * host buffers out, H2D / decode / D2H pipelined per row group over all requested columns.
+ * Plans (descriptor tables + device buffers) are cached per column until pqr_release_plans. */
+typedef struct pqr_dst {
+    void* values; uint64_t values_cap;        /* bytes */
+    uint32_t* validity; uint64_t validity_cap; /* 32-bit words; may be NULL / 0 */
+} pqr_dst;
+typedef struct pqr_read_stats {
+    uint64_t num_slots; uint32_t width; int32_t has_validity;
+    uint64_t bytes_in, bytes_out, h2d_bytes, d2h_bytes;
+} pqr_read_stats;
+PQG_API int pqr_read_columns_into(pqr_reader* r, const int32_t* cols, int32_t n_cols, int32_t rg,
+                                  const pqr_dst* dsts, pqr_read_stats* stats);
+PQG_API void pqr_release_plans(pqr_reader* r);
+
 /* chunk-index prototype (src/main.cpp:21-32): tuple_to_chunk has num_rows entries;
  * returns "Total chunks" */
 PQG_API int64_t pqr_chunk_index(pqr_reader* r, const char* name, uint64_t chunk_size,

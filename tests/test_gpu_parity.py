@@ -138,3 +138,47 @@ def test_columnar_api_is_consistent_with_values(pq, files):
                 assert np.array_equal(bits[valid], vals["fixed"][valid])
                 assert not bits[~valid].any()
     r.close()
+
+
+def test_read_columns_into_pipelined_matches_read_column(pq, files):
+    """streaming path (cached plans, per-row-group H2D -> decode -> D2H) == the Value path,
+    twice in a row (the second call reuses the cached plans and device buffers)"""
+    for name in ("fixed_plain", "fixed_dict", "golden_mixed"):
+        if name not in files:
+            continue
+        r = pq.Reader(files[name])
+        cols = [c for c in range(r.num_columns) if r.column_info(c)["type"] in (pq.INT32, pq.INT64, pq.FLOAT, pq.DOUBLE)]
+        n = r.num_rows
+        for rep in range(2):
+            vals = [np.full(n * 8 + 16, 0xAB, dtype=np.uint8) for _ in cols]
+            vmask = [np.zeros((n + 31) // 32 + 1, dtype=np.uint32) for _ in cols]
+            st = r.read_columns_into(cols, [(v.ctypes.data, v.size, m.ctypes.data, m.size) for v, m in zip(vals, vmask)])
+            for c, v, m, s_ in zip(cols, vals, vmask, st):
+                exp = r.read_column(r.column_info(c)["name"])
+                w = s_["width"]
+                assert s_["num_slots"] == n
+                valid = ~exp["is_null"].astype(bool)
+                if s_["has_validity"]:
+                    got_valid = ((m[np.arange(n) >> 5] >> (np.arange(n) & 31).astype(np.uint32)) & 1).astype(bool)
+                    assert np.array_equal(got_valid, valid), (name, c, rep)
+                else:
+                    assert valid.all()
+                raw = v[: n * w].reshape(n, w)
+                pad = np.zeros((n, 8), dtype=np.uint8)
+                pad[:, :w] = raw
+                bits = pad.view(np.uint64).reshape(n)
+                assert np.array_equal(bits[valid], exp["fixed"][valid]), (name, c, rep)
+                assert not bits[~valid].any()
+                assert (v[n * w:] == 0xAB).all()  # nothing written past the column
+        # one row group only
+        rg = r.num_row_groups - 1
+        nr = r.row_group_num_rows(rg)
+        c = cols[0]
+        v = np.zeros(nr * 8, dtype=np.uint8)
+        st = r.read_columns_into([c], [(v.ctypes.data, v.size, None, 0)], rg=rg)
+        exp = r.read_column(r.column_info(c)["name"], rg=rg)
+        w = st[0]["width"]
+        pad = np.zeros((nr, 8), dtype=np.uint8)
+        pad[:, :w] = v[: nr * w].reshape(nr, w)
+        assert np.array_equal(pad.view(np.uint64).reshape(nr)[~exp["is_null"].astype(bool)], exp["fixed"][~exp["is_null"].astype(bool)])
+        r.close()
