@@ -685,6 +685,7 @@ int ctx_fail(pqg_ctx* c, int code, const std::string& m) { return fail(c, code, 
 bool plan_is_str(const pqg_plan* p) { return p->is_str; }
 bool plan_ran(const pqg_plan* p) { return p->ran; }
 bool plan_any_dict(const pqg_plan* p) { return p->any_dict; }
+size_t plan_dict_arena_bytes(const pqg_plan* p) { return p->dict_bytes; }
 uint64_t plan_slots(const pqg_plan* p) { return p->n_slots; }
 const std::vector<pqg_chunk_desc>& plan_chunks(const pqg_plan* p) { return p->chunks; }
 const std::vector<pqg_page_desc>& plan_pages(const pqg_plan* p) { return p->pages; }

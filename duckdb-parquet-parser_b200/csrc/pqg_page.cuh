@@ -327,6 +327,30 @@ __device__ __forceinline__ uint32_t regular_index(const uint8_t* s, uint32_t bw,
     return ldbits(s, ((g * (1u + bw) + 1u) << 3) + (k & 7u) * bw, bw);
 }
 
+// ---- BYTE_ARRAY PLAIN: length-prefix walk -----------------------------------------------------
+// Lane 0 walks `cnt` length-prefixed strings starting at byte `pos` of the value section and
+// records each prefix position in ws.idx (u16 when !wide).  Returns the end position in *pos.
+// TODO(perf): candidate-and-verify parallel walk for ASCII pages.
+__device__ __forceinline__ bool walk_strings(const uint8_t* vals, uint32_t vavail, uint32_t* pos_io, uint32_t cnt,
+                                             WarpScratch& ws, bool wide, bool record, uint32_t* epos, uint32_t* eneed) {
+    uint32_t ok = 1, pos = *pos_io;
+    if (lane_id() == 0) {
+        for (uint32_t k = 0; k < cnt; k++) {
+            if (static_cast<uint64_t>(pos) + 4 > vavail) { ok = 0; *epos = pos; *eneed = 4; break; }
+            uint32_t len = ld32u(vals + pos);
+            if (static_cast<uint64_t>(pos) + 4 + len > vavail) { ok = 0; *epos = pos + 4; *eneed = len; break; }
+            if (record) idx_store(ws.idx, k, pos, wide);
+            pos += 4 + len;
+        }
+    }
+    ok = __shfl_sync(0xffffffffu, ok, 0);
+    *pos_io = __shfl_sync(0xffffffffu, pos, 0);
+    *epos = __shfl_sync(0xffffffffu, *epos, 0);
+    *eneed = __shfl_sync(0xffffffffu, *eneed, 0);
+    __syncwarp();
+    return ok != 0;
+}
+
 // ---- page prolog -----------------------------------------------------------------------------
 struct PageCtx {
     const uint8_t* pg;   // payload bytes (shared slot or global)

@@ -1,8 +1,658 @@
-// pqg_scan.cu -- regex page scan and chunk-index kernels (implemented next).
+// pqg_scan.cu -- regex page-pruning scan and the greedy chunk indexes.
+//
+//   k_regex_dict     one lane per dictionary entry: predicate of the entry
+//   k_regex_pages    one warp per data page: OR over the page's non-null values of
+//                    (neg ? !match : match); PLAIN pages run the DFA over the page bytes staged
+//                    in shared memory (one lane per string), dictionary pages look the
+//                    predicate of their indices up.  Replaces the parser's
+//                    --regex-column/--regex/--neg-regex mode (reference README.md:54-64; source
+//                    absent, frozen spec SURVEY.md 8 a-19).
+//   chain engine     greedy ">= chunk_size closes the chunk" chunking over a weight sequence
+//                    (src/main.cpp:21-32 tuple level; README.md:66-72 page level): device-wide
+//                    exclusive scan of the weights, then the cut chain c' = first prefix value
+//                    >= c + chunk_size.  The chain is sequential by nature; it is broken up by
+//                    speculation: weight space is cut into tiles of 64 chunk sizes, every slot
+//                    that can be the first cut of a tile (prefix in [tile, tile + chunk_size])
+//                    walks the tile in parallel, the host stitches the tiles (one lookup per
+//                    tile) and a last pass materialises cuts and chunk ids.
+#include <algorithm>
 #include <cstdio>
-#include "pqg_internal.h"
-extern "C" {
-int pqg_regex_scan(pqg_ctx*, pqg_plan*, const pqg_dfa*, int, uint32_t*, float*) { return PQG_ERR_UNSUPPORTED; }
-int pqg_chunk_index(pqg_ctx*, pqg_plan*, uint64_t, uint64_t, uint32_t*, uint64_t*, uint64_t*, float*) { return PQG_ERR_UNSUPPORTED; }
-int pqg_page_chunk_index(pqg_ctx*, const uint32_t*, uint32_t, uint64_t, uint32_t*, uint32_t*, uint32_t*, uint32_t, uint32_t*) { return PQG_ERR_UNSUPPORTED; }
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "pq_regex.hpp"
+#include "pqg_page.cuh"
+
+struct pqg_ctx;
+struct pqg_plan;
+
+namespace pqg {
+// accessors implemented in pqg_api.cu
+DecodeParams plan_params(const pqg_plan* p);
+cudaStream_t ctx_stream(const pqg_ctx* c);
+int ctx_sm_count(const pqg_ctx* c);
+int ctx_device(const pqg_ctx* c);
+void ctx_add_launches(pqg_ctx* c, uint32_t n);
+int ctx_fail(pqg_ctx* c, int code, const std::string& m);
+bool plan_is_str(const pqg_plan* p);
+bool plan_ran(const pqg_plan* p);
+bool plan_any_dict(const pqg_plan* p);
+uint64_t plan_slots(const pqg_plan* p);
+const std::vector<pqg_chunk_desc>& plan_chunks(const pqg_plan* p);
+const std::vector<pqg_page_desc>& plan_pages(const pqg_plan* p);
+size_t plan_dict_arena_bytes(const pqg_plan* p);
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// regex
+// ---------------------------------------------------------------------------------------------
+struct DfaDev {
+    const uint16_t* trans; // wide: [n_states][256]; else [n_states][n_classes]
+    const uint8_t* cls;    // byte -> class (class-indexed tables only)
+    const uint8_t* accept; // [n_states]
+    uint32_t n_states, n_classes, start, dead;
+    uint32_t wide;         // transition table indexed by the byte itself
+    uint32_t table_bytes;  // bytes of trans
+    uint32_t in_smem;      // tables are staged in shared memory
+};
+
+// state 0 is the absorbing accept, `dead` the absorbing reject (host compiler, pq_regex.cpp)
+__device__ __forceinline__ bool dfa_run(const DfaDev& D, const uint16_t* trans, const uint8_t* cls, const uint8_t* accept,
+                                        const uint8_t* text, uint32_t len) {
+    uint32_t s = D.start;
+    if (D.wide) {
+        for (uint32_t i = 0; i < len && s != 0 && s != D.dead; i++) s = trans[s * 256u + text[i]];
+    } else {
+        for (uint32_t i = 0; i < len && s != 0 && s != D.dead; i++) s = trans[s * D.n_classes + cls[text[i]]];
+    }
+    return accept[s] != 0;
 }
+
+struct RegexParams {
+    DecodeParams P;
+    DfaDev D;
+    uint8_t* dict_match;  // per dictionary entry (arena entry index): predicate (neg applied)
+    uint32_t* page_bits;  // bit per page-table entry
+    int neg;
+};
+
+__global__ void __launch_bounds__(256) k_regex_dict(RegexParams R) {
+    const DevChunk& ck = R.P.chunks[blockIdx.y];
+    if (!ck.has_dict) return;
+    const uint2* ent = reinterpret_cast<const uint2*>(R.P.dict_arena + ck.dict_arena_off);
+    uint8_t* out = R.dict_match + ck.dict_arena_off / 8;
+    const uint8_t* chars = R.P.image + ck.dict_off;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < ck.dict_ok_n; i += gridDim.x * blockDim.x) {
+        uint2 e = ent[i];
+        bool m = dfa_run(R.D, R.D.trans, R.D.cls, R.D.accept, chars + e.x, e.y);
+        out[i] = (R.neg ? !m : m) ? 1 : 0;
+    }
+}
+
+__device__ __forceinline__ bool regex_page(const RegexParams& R, const uint16_t* trans, const uint8_t* cls, const uint8_t* accept,
+                                           uint32_t q, const DevChunk& ck, WarpScratch& ws) {
+    const DecodeParams& P = R.P;
+    const uint32_t l = lane_id();
+    const pqg_page_desc pd = P.pages[q];
+    if (pd.num_values == 0) return false;
+    PageCtx c;
+    if (!page_begin(P, q, pd, ck, ws, c)) return false;
+    const uint8_t* vals = c.pg + c.vals_pos;
+    const uint32_t vavail = c.size - c.vals_pos;
+    const bool pwide = !c.dict && c.size > 65535u;
+    const bool wide = c.dict ? c.wide : pwide;
+    const uint32_t T_ = wide ? kTileWide : kTileNarrow;
+    const bool single = c.n <= T_;
+    const uint32_t dict_n = ck.dict_ok_n;
+    const uint8_t* dmatch = R.dict_match + ck.dict_arena_off / 8;
+    bool regular = false, hit = false;
+    uint32_t nn_before = 0, wpos = 0;
+    for (uint32_t ts = 0; ts < c.n; ts += T_) {
+        const uint32_t t = min(T_, c.n - ts);
+        uint32_t bad = 0;
+        const uint32_t nn = levels_tile(c.defw, ws, t, ck.max_def, single, &bad);
+        if (bad) { if (l == 0) report_error(P.err, q, bad); return false; }
+        if (c.dict) {
+            if (ts == 0 && (single || !c.has_def)) regular = check_regular(c.idxw.s, c.idxw.len, c.bw, single ? nn : c.n);
+            if (!regular) {
+                indices_tile(c.idxw, ws, nn, c.wide, &bad);
+                if (bad) { if (l == 0) report_error(P.err, q, bad); return false; }
+                __syncwarp();
+            }
+            for (uint32_t k = l; k < nn; k += 32) {
+                uint32_t ix = regular ? regular_index(c.idxw.s, c.bw, nn_before + k) : idx_load(ws.idx, k, c.wide);
+                if (ix < dict_n && dmatch[ix]) hit = true; // out-of-range index: no value (null / dropped)
+            }
+        } else {
+            uint32_t epos = 0, eneed = 0;
+            if (!walk_strings(vals, vavail, &wpos, nn, ws, wide, true, &epos, &eneed)) {
+                if (l == 0) report_error(P.err, q, PQG_PAGE_TRUNCATED, c.vals_pos + epos, eneed, c.size);
+                return false;
+            }
+            for (uint32_t k = l; k < nn; k += 32) {
+                uint32_t pp = idx_load(ws.idx, k, wide);
+                uint32_t len = ld32u(vals + pp);
+                bool m = dfa_run(R.D, trans, cls, accept, vals + pp + 4, len);
+                if (R.neg ? !m : m) hit = true;
+            }
+        }
+        nn_before += nn;
+        __syncwarp();
+        if (__any_sync(0xffffffffu, hit)) return true; // the page bit is an OR: stop early
+    }
+    return __any_sync(0xffffffffu, hit);
+}
+
+__global__ void __launch_bounds__(kThreadsPerCta) k_regex_pages(RegexParams R) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    WarpScratch& ws = reinterpret_cast<WarpScratch*>(smem)[warp_id()];
+    uint8_t* stab = smem + sizeof(WarpScratch) * kWarpsPerCta;
+    const uint16_t* trans = R.D.trans;
+    const uint8_t* cls = R.D.cls;
+    const uint8_t* accept = R.D.accept;
+    if (R.D.in_smem) {
+        // tables: [trans][cls 256][accept n_states]
+        const uint32_t total = R.D.table_bytes + 256u + R.D.n_states;
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(R.D.trans); // the three tables are contiguous on the device
+        for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) stab[i] = src[i];
+        __syncthreads();
+        trans = reinterpret_cast<const uint16_t*>(stab);
+        cls = stab + R.D.table_bytes;
+        accept = cls + 256;
+    }
+    const DecodeParams& P = R.P;
+    uint32_t p = P.page_begin + blockIdx.x * P.pages_per_cta;
+    const uint32_t p1 = min(P.page_end, p + P.pages_per_cta);
+    for (uint32_t q = p + warp_id(); q < p1; q += kWarpsPerCta) {
+        const DevChunk& ck = P.chunks[P.pages[q].chunk_idx];
+        bool hit = regex_page(R, trans, cls, accept, q, ck, ws);
+        if (hit && lane_id() == 0) atomicOr(&R.page_bits[q >> 5], 1u << (q & 31u));
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// weights + device-wide exclusive scan
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t dec_digits(uint32_t v) { // length of std::to_string(v)
+    uint32_t d = 1;
+    while (v >= 10u) { v /= 10u; d++; }
+    return d;
+}
+
+// weight of slot i: tuple level = decimal digits of the length + the length for non-null strings
+struct StrWeights {
+    const uint32_t* offsets;   // plan offsets (chunk c owns [row_base_c + c, ...])
+    const uint32_t* validity;  // may be null
+    const uint64_t* chunk_row_base; // n_chunks + 1 (device)
+    uint32_t n_chunks;
+    __device__ uint32_t operator()(uint64_t i) const {
+        if (validity && !((validity[i >> 5] >> (i & 31)) & 1u)) return 0;
+        uint32_t lo = 0, hi = n_chunks; // chunk of slot i
+        while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (chunk_row_base[mid] <= i) lo = mid; else hi = mid; }
+        const uint32_t* off = offsets + i + lo;
+        uint32_t len = off[1] - off[0];
+        return dec_digits(len) + len;
+    }
+};
+struct ArrWeights {
+    const uint32_t* w;
+    __device__ uint32_t operator()(uint64_t i) const { return w[i]; }
+};
+
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 8; // per thread
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+__device__ __forceinline__ uint64_t block_excl_scan(uint64_t v, uint64_t* total_out) {
+    __shared__ uint64_t wsum[kScanThreads / 32];
+    const uint32_t l = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint64_t incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint64_t t = __shfl_up_sync(0xffffffffu, incl, d); if (l >= static_cast<uint32_t>(d)) incl += t; }
+    if (l == 31) wsum[w] = incl;
+    __syncthreads();
+    uint64_t base = 0, total = 0;
+#pragma unroll
+    for (int i = 0; i < kScanThreads / 32; i++) { uint64_t x = wsum[i]; if (i < static_cast<int>(w)) base += x; total += x; }
+    __syncthreads();
+    *total_out = total;
+    return base + incl - v;
+}
+
+template <class Src>
+__global__ void __launch_bounds__(kScanThreads) k_scan_reduce(Src src, uint64_t n, uint64_t* block_sums) {
+    const uint64_t base = static_cast<uint64_t>(blockIdx.x) * kScanTile;
+    uint64_t sum = 0;
+    for (int j = 0; j < kScanItems; j++) {
+        uint64_t i = base + static_cast<uint64_t>(j) * kScanThreads + threadIdx.x;
+        if (i < n) sum += src(i);
+    }
+    uint64_t total;
+    block_excl_scan(sum, &total);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+// single block: exclusive scan of the block sums in place; grand total -> sums[nb]
+__global__ void __launch_bounds__(kScanThreads) k_scan_sums(uint64_t* sums, uint64_t nb) {
+    __shared__ uint64_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint64_t b0 = 0; b0 < nb; b0 += kScanThreads) {
+        uint64_t i = b0 + threadIdx.x;
+        uint64_t v = i < nb ? sums[i] : 0, total;
+        uint64_t ex = block_excl_scan(v, &total);
+        if (i < nb) sums[i] = carry + ex;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) sums[nb] = carry;
+}
+
+// P[i] = exclusive prefix of the weights, P[n] = total
+template <class Src>
+__global__ void __launch_bounds__(kScanThreads) k_scan_write(Src src, uint64_t n, const uint64_t* block_sums, uint64_t* P) {
+    const uint64_t base = static_cast<uint64_t>(blockIdx.x) * kScanTile + static_cast<uint64_t>(threadIdx.x) * kScanItems;
+    uint32_t w[kScanItems];
+    uint64_t sum = 0;
+#pragma unroll
+    for (int j = 0; j < kScanItems; j++) { uint64_t i = base + j; w[j] = i < n ? src(i) : 0; sum += w[j]; }
+    uint64_t total;
+    uint64_t ex = block_sums[blockIdx.x] + block_excl_scan(sum, &total);
+#pragma unroll
+    for (int j = 0; j < kScanItems; j++) { uint64_t i = base + j; if (i < n) P[i] = ex; ex += w[j]; }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == kScanThreads - 1) P[n] = block_sums[gridDim.x]; // grand total
+}
+
+// ---------------------------------------------------------------------------------------------
+// the cut chain
+// ---------------------------------------------------------------------------------------------
+// first slot k in [0, n) with P[k] >= x, else n
+__device__ __forceinline__ uint64_t lower_bound_P(const uint64_t* P, uint64_t n, uint64_t x) {
+    uint64_t lo = 0, hi = n;
+    while (lo < hi) { uint64_t mid = (lo + hi) >> 1; if (P[mid] < x) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+// same, knowing P[k] < x: gallop forward from k (cuts are a chunk size apart: a short hop)
+__device__ __forceinline__ uint64_t lower_bound_from(const uint64_t* P, uint64_t n, uint64_t k, uint64_t x) {
+    uint64_t lo = k, step = 1, hi = k + 1;
+    while (hi < n && P[hi] < x) { lo = hi; step <<= 1; hi = min(n, hi + step); }
+    while (lo + 1 < hi) { uint64_t mid = (lo + hi) >> 1; if (P[mid] < x) lo = mid; else hi = mid; }
+    return hi;
+}
+
+constexpr uint32_t kChainTileChunks = 64; // a weight-space tile spans this many chunk sizes
+
+// per weight-space tile t: klo[t] = first slot with P >= t*L, ncand[t] = candidate first cuts
+__global__ void k_chain_tiles(const uint64_t* P, uint64_t n, uint64_t S, uint64_t L, uint64_t T, uint64_t* klo, uint32_t* ncand) {
+    uint64_t t = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t > T) return;
+    if (t == T) { klo[T] = n; return; }
+    // candidates: slots a .. b inclusive, a = first slot with P >= t*L, b = first slot with P >= t*L + S
+    uint64_t a = lower_bound_P(P, n, t * L);
+    klo[t] = a;
+    uint64_t cnt = 0;
+    if (a < n) {
+        uint64_t b = P[a] >= t * L + S ? a : lower_bound_from(P, n, a, t * L + S);
+        cnt = b < n ? b - a + 1 : n - a;
+    }
+    ncand[t] = static_cast<uint32_t>(cnt);
+}
+
+// every candidate of every tile walks its tile: number of cuts inside, first cut after it
+__global__ void __launch_bounds__(128) k_chain_walk(const uint64_t* P, uint64_t n, uint64_t S, uint64_t L, const uint64_t* klo,
+                                                     const uint32_t* ncand, const uint64_t* cand_base, uint64_t* res_exit, uint32_t* res_cnt) {
+    const uint64_t t = blockIdx.x;
+    const uint64_t end = (t + 1) * L;
+    for (uint32_t j = threadIdx.x; j < ncand[t]; j += blockDim.x) {
+        uint64_t k = klo[t] + j;
+        uint32_t cnt = 0;
+        while (k < n) {
+            uint64_t pk = P[k];
+            if (pk >= end) break;
+            cnt++;
+            k = lower_bound_from(P, n, k, pk + S);
+        }
+        res_exit[cand_base[t] + j] = k;
+        res_cnt[cand_base[t] + j] = cnt;
+    }
+}
+
+// first cut of the sequence: first slot with carry_in + P >= S
+__global__ void k_chain_entry(const uint64_t* P, uint64_t n, uint64_t x0, uint64_t* out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) { out[0] = lower_bound_P(P, n, x0); out[1] = P[n]; }
+}
+
+// materialise the cuts: tile t walks from its true entry
+__global__ void k_chain_emit(const uint64_t* P, uint64_t n, uint64_t S, uint64_t L, uint64_t T, const uint64_t* tile_entry,
+                             const uint64_t* tile_base, uint64_t* cuts) {
+    uint64_t t = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    uint64_t k = tile_entry[t], o = tile_base[t];
+    const uint64_t end = (t + 1) * L;
+    if (k >= n || P[k] < t * L) return; // no cut starts in this tile
+    while (k < n) {
+        uint64_t pk = P[k];
+        if (pk >= end) break;
+        cuts[o++] = k;
+        k = lower_bound_from(P, n, k, pk + S);
+    }
+}
+
+// ids[i] = number of cuts at slots <= i (0 for zero-weight slots when mask_zero)
+template <class Src>
+__global__ void __launch_bounds__(256) k_chain_ids(Src src, uint64_t n, const uint64_t* cuts, uint64_t n_cuts, bool mask_zero, uint32_t* ids) {
+    __shared__ uint64_t first;
+    const uint64_t b0 = static_cast<uint64_t>(blockIdx.x) * 2048u;
+    if (threadIdx.x == 0) { // cuts <= b0
+        uint64_t lo = 0, hi = n_cuts;
+        while (lo < hi) { uint64_t mid = (lo + hi) >> 1; if (cuts[mid] <= b0) lo = mid + 1; else hi = mid; }
+        first = lo;
+    }
+    __syncthreads();
+    for (uint32_t j = threadIdx.x; j < 2048u; j += blockDim.x) {
+        uint64_t i = b0 + j;
+        if (i >= n) break;
+        // cuts are distinct slots: at most j + 1 of them lie in (b0, i]
+        uint64_t lo = first, hi = min(n_cuts, first + j + 1);
+        while (lo < hi) { uint64_t mid = (lo + hi) >> 1; if (cuts[mid] <= i) lo = mid + 1; else hi = mid; }
+        const uint64_t c = lo;
+        ids[i] = (mask_zero && src(i) == 0) ? 0u : static_cast<uint32_t>(c);
+    }
+}
+
+// page-level extras: byte offset of every page inside its chunk
+__global__ void k_page_offsets(const uint64_t* P, uint64_t n, const uint32_t* ids, const uint64_t* cuts, uint32_t* off) {
+    uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t id = ids[i];
+    off[i] = static_cast<uint32_t>(P[i] - (id ? P[cuts[id - 1]] : 0));
+}
+__global__ void k_narrow(const uint64_t* in, uint64_t n, uint32_t* out) {
+    uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = static_cast<uint32_t>(in[i]);
+}
+__global__ void k_chunk_row_bases(const DevChunk* chunks, uint32_t n_chunks, uint64_t n_slots, uint64_t* out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_chunks) out[i] = chunks[i].out_row_base;
+    if (i == n_chunks) out[i] = n_slots;
+}
+
+struct DevMem { // frees on scope exit
+    std::vector<void*> ptrs;
+    ~DevMem() { for (void* p : ptrs) cudaFree(p); }
+    template <class T> cudaError_t alloc(T** out, size_t count) {
+        void* p = nullptr;
+        cudaError_t e = cudaMalloc(&p, std::max<size_t>(count * sizeof(T), 16));
+        if (e == cudaSuccess) { ptrs.push_back(p); *out = static_cast<T*>(p); }
+        return e;
+    }
+};
+
+struct ChainOut {
+    uint64_t n_cuts = 0, total = 0, last_cut_P = 0;
+    uint64_t* d_P = nullptr;     // n + 1
+    uint64_t* d_cuts = nullptr;  // n_cuts
+    uint32_t launches = 0;
+};
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return e_; } while (0)
+
+// Greedy chunking of the weight sequence src(0..n): d_ids[i] = chunk id (shard local, the
+// open chunk carried in is id 0).  Synchronises the stream (the stitch runs on the host).
+template <class Src>
+cudaError_t run_chain(Src src, uint64_t n, uint64_t S, uint64_t carry_in, bool mask_zero, uint32_t* d_ids, DevMem& mem, ChainOut& out,
+                      cudaStream_t s) {
+    const uint64_t nb = (n + kScanTile - 1) / kScanTile;
+    uint64_t* d_sums = nullptr;
+    CK(mem.alloc(&d_sums, nb + 2));
+    CK(mem.alloc(&out.d_P, n + 1));
+    if (nb) {
+        k_scan_reduce<Src><<<static_cast<unsigned>(nb), kScanThreads, 0, s>>>(src, n, d_sums);
+        k_scan_sums<<<1, kScanThreads, 0, s>>>(d_sums, nb);
+        k_scan_write<Src><<<static_cast<unsigned>(nb), kScanThreads, 0, s>>>(src, n, d_sums, out.d_P);
+        out.launches += 3;
+    } else {
+        CK(cudaMemsetAsync(out.d_P, 0, 8, s));
+    }
+    const uint64_t x0 = carry_in >= S ? 0 : S - carry_in;
+    uint64_t* d_entry = nullptr;
+    CK(mem.alloc(&d_entry, 2));
+    k_chain_entry<<<1, 32, 0, s>>>(out.d_P, n, x0, d_entry);
+    out.launches++;
+    uint64_t h_entry[2];
+    CK(cudaMemcpyAsync(h_entry, d_entry, 16, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    out.total = h_entry[1];
+    const uint64_t L = S * kChainTileChunks;
+    const uint64_t T = out.total / L + 1;
+    uint64_t* d_klo = nullptr; uint32_t* d_ncand = nullptr;
+    CK(mem.alloc(&d_klo, T + 1));
+    CK(mem.alloc(&d_ncand, T + 1));
+    k_chain_tiles<<<static_cast<unsigned>((T + 1 + 127) / 128), 128, 0, s>>>(out.d_P, n, S, L, T, d_klo, d_ncand);
+    out.launches++;
+    std::vector<uint64_t> klo(T + 1);
+    std::vector<uint32_t> ncand(T);
+    CK(cudaMemcpyAsync(klo.data(), d_klo, (T + 1) * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(ncand.data(), d_ncand, T * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    std::vector<uint64_t> cand_base(T + 1, 0);
+    for (uint64_t t = 0; t < T; t++) cand_base[t + 1] = cand_base[t] + ncand[t];
+    const uint64_t n_cand = cand_base[T];
+    uint64_t* d_cand_base = nullptr; uint64_t* d_exit = nullptr; uint32_t* d_cnt = nullptr;
+    CK(mem.alloc(&d_cand_base, T + 1));
+    CK(mem.alloc(&d_exit, n_cand));
+    CK(mem.alloc(&d_cnt, n_cand));
+    CK(cudaMemcpyAsync(d_cand_base, cand_base.data(), (T + 1) * 8, cudaMemcpyHostToDevice, s));
+    k_chain_walk<<<static_cast<unsigned>(T), 128, 0, s>>>(out.d_P, n, S, L, d_klo, d_ncand, d_cand_base, d_exit, d_cnt);
+    out.launches++;
+    std::vector<uint64_t> r_exit(n_cand);
+    std::vector<uint32_t> r_cnt(n_cand);
+    if (n_cand) {
+        CK(cudaMemcpyAsync(r_exit.data(), d_exit, n_cand * 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(r_cnt.data(), d_cnt, n_cand * 4, cudaMemcpyDeviceToHost, s));
+    }
+    CK(cudaStreamSynchronize(s));
+    // stitch: one lookup per tile
+    std::vector<uint64_t> tile_entry(T), tile_base(T + 1, 0);
+    uint64_t e = h_entry[0];
+    for (uint64_t t = 0; t < T; t++) {
+        tile_entry[t] = e;
+        tile_base[t + 1] = tile_base[t];
+        if (e < n && e >= klo[t] && e < klo[t + 1]) {
+            uint64_t j = e - klo[t];
+            if (j >= ncand[t]) return cudaErrorAssert; // cannot happen: an entry is always a candidate
+            tile_base[t + 1] += r_cnt[cand_base[t] + j];
+            e = r_exit[cand_base[t] + j];
+        }
+    }
+    out.n_cuts = tile_base[T];
+    uint64_t* d_tile_entry = nullptr; uint64_t* d_tile_base = nullptr;
+    CK(mem.alloc(&d_tile_entry, T));
+    CK(mem.alloc(&d_tile_base, T + 1));
+    CK(mem.alloc(&out.d_cuts, out.n_cuts));
+    CK(cudaMemcpyAsync(d_tile_entry, tile_entry.data(), T * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_tile_base, tile_base.data(), (T + 1) * 8, cudaMemcpyHostToDevice, s));
+    k_chain_emit<<<static_cast<unsigned>((T + 127) / 128), 128, 0, s>>>(out.d_P, n, S, L, T, d_tile_entry, d_tile_base, out.d_cuts);
+    out.launches++;
+    if (n && d_ids) {
+        k_chain_ids<Src><<<static_cast<unsigned>((n + 2047) / 2048), 256, 0, s>>>(src, n, out.d_cuts, out.n_cuts, mask_zero, d_ids);
+        out.launches++;
+    }
+    if (out.n_cuts) {
+        uint64_t last_slot = 0;
+        CK(cudaMemcpyAsync(&last_slot, out.d_cuts + out.n_cuts - 1, 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        CK(cudaMemcpyAsync(&out.last_cut_P, out.d_P + last_slot, 8, cudaMemcpyDeviceToHost, s));
+    }
+    CK(cudaStreamSynchronize(s));
+    return cudaGetLastError();
+}
+
+} // namespace
+} // namespace pqg
+
+using namespace pqg;
+
+#define CUF(ctx, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return ctx_fail(ctx, PQG_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
+
+extern "C" {
+
+int pqg_regex_scan(pqg_ctx* ctx, pqg_plan* plan, const pqg_dfa* dfa, int neg, uint32_t* page_bits, float* kernel_ms) {
+    if (!ctx || !plan || !dfa || !page_bits) return ctx_fail(ctx, PQG_ERR_ARG, "pqg_regex_scan: bad argument");
+    if (!plan_is_str(plan)) return ctx_fail(ctx, PQG_ERR_ARG, "pqg_regex_scan: the plan must describe a BYTE_ARRAY column");
+    CUF(ctx, cudaSetDevice(ctx_device(ctx)));
+    cudaStream_t s = ctx_stream(ctx);
+    const CompiledDfa& d = dfa_tables(dfa);
+    DecodeParams P = plan_params(plan);
+    const uint32_t n_pages = P.page_end;
+    const size_t words = (static_cast<size_t>(n_pages) + 31) / 32;
+    std::memset(page_bits, 0, words * 4);
+    if (n_pages == 0) { if (kernel_ms) *kernel_ms = 0; return PQG_OK; }
+    // device tables: [trans][cls 256][accept]; byte-indexed transitions when they stay small
+    const bool wide = static_cast<size_t>(d.n_states) * 256 * 2 <= 40 * 1024;
+    std::vector<uint8_t> blob;
+    const uint32_t table_bytes = wide ? d.n_states * 512u : static_cast<uint32_t>(d.trans.size() * 2);
+    blob.resize(static_cast<size_t>(table_bytes) + 256 + d.n_states);
+    uint16_t* tr = reinterpret_cast<uint16_t*>(blob.data());
+    if (wide) {
+        for (uint32_t st = 0; st < d.n_states; st++)
+            for (uint32_t b = 0; b < 256; b++) tr[st * 256u + b] = d.trans[static_cast<size_t>(st) * d.n_classes + d.cls[b]];
+    } else {
+        std::memcpy(tr, d.trans.data(), d.trans.size() * 2);
+    }
+    std::memcpy(blob.data() + table_bytes, d.cls, 256);
+    std::memcpy(blob.data() + table_bytes + 256, d.accept.data(), d.n_states);
+    DevMem mem;
+    uint8_t* d_blob = nullptr; uint8_t* d_dmatch = nullptr; uint32_t* d_bits = nullptr;
+    CUF(ctx, mem.alloc(&d_blob, blob.size() + 16));
+    CUF(ctx, mem.alloc(&d_dmatch, plan_dict_arena_bytes(plan) / 8 + 16));
+    CUF(ctx, mem.alloc(&d_bits, words + 1));
+    CUF(ctx, cudaMemcpyAsync(d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice, s));
+    CUF(ctx, cudaMemsetAsync(d_bits, 0, (words + 1) * 4, s));
+    CUF(ctx, cudaMemsetAsync(P.err, 0xFF, 8, s));
+    CUF(ctx, cudaMemsetAsync(reinterpret_cast<uint8_t*>(P.err) + 8, 0, sizeof(DevErr) - 8, s));
+    RegexParams R;
+    R.P = P;
+    R.D.trans = reinterpret_cast<const uint16_t*>(d_blob);
+    R.D.cls = d_blob + table_bytes;
+    R.D.accept = d_blob + table_bytes + 256;
+    R.D.n_states = d.n_states; R.D.n_classes = d.n_classes; R.D.start = d.start; R.D.dead = d.dead;
+    R.D.wide = wide; R.D.table_bytes = table_bytes;
+    const size_t tab_smem = static_cast<size_t>(table_bytes) + 256 + d.n_states;
+    R.D.in_smem = tab_smem <= 48 * 1024;
+    R.dict_match = d_dmatch; R.page_bits = d_bits; R.neg = neg ? 1 : 0;
+    cudaEvent_t e0, e1;
+    CUF(ctx, cudaEventCreate(&e0));
+    CUF(ctx, cudaEventCreate(&e1));
+    uint32_t launches = 0;
+    CUF(ctx, cudaEventRecord(e0, s));
+    if (plan_any_dict(plan)) {
+        CUF(ctx, launch_dict_prepare(P, P.n_chunks, 0, 1, s));
+        k_regex_dict<<<dim3(64, P.n_chunks), 256, 0, s>>>(R);
+        launches += 2;
+    }
+    const size_t smem = decode_smem_bytes(false) + (R.D.in_smem ? ((tab_smem + 15) & ~size_t(15)) : 0);
+    CUF(ctx, cudaFuncSetAttribute(k_regex_pages, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    uint32_t target = static_cast<uint32_t>(ctx_sm_count(ctx)) * 16u;
+    uint32_t per = (n_pages + target - 1) / target;
+    if (per < static_cast<uint32_t>(kWarpsPerCta)) per = kWarpsPerCta;
+    R.P.pages_per_cta = per;
+    k_regex_pages<<<(n_pages + per - 1) / per, kThreadsPerCta, smem, s>>>(R);
+    launches++;
+    CUF(ctx, cudaEventRecord(e1, s));
+    CUF(ctx, cudaGetLastError());
+    DevErr herr;
+    CUF(ctx, cudaMemcpyAsync(page_bits, d_bits, words * 4, cudaMemcpyDeviceToHost, s));
+    CUF(ctx, cudaMemcpyAsync(&herr, P.err, sizeof(DevErr), cudaMemcpyDeviceToHost, s));
+    CUF(ctx, cudaStreamSynchronize(s));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (kernel_ms) *kernel_ms = ms;
+    ctx_add_launches(ctx, launches);
+    if (herr.count) {
+        char msg[160];
+        std::snprintf(msg, sizeof(msg), "regex scan: page %u failed to decode (code %u)", static_cast<uint32_t>(herr.key >> 32),
+                      static_cast<uint32_t>(herr.key & 0xffffffffu));
+        return ctx_fail(ctx, PQG_ERR_PAGE, msg);
+    }
+    return PQG_OK;
+}
+
+int pqg_chunk_index(pqg_ctx* ctx, pqg_plan* plan, uint64_t chunk_size, uint64_t carry_in, uint32_t* tuple_to_chunk,
+                    uint64_t* n_chunks, uint64_t* carry_out, float* kernel_ms) {
+    if (!ctx || !plan) return ctx_fail(ctx, PQG_ERR_ARG, "pqg_chunk_index: bad argument");
+    if (chunk_size == 0) return ctx_fail(ctx, PQG_ERR_ARG, "pqg_chunk_index: chunk_size must be > 0");
+    if (!plan_is_str(plan) || !plan_ran(plan)) return ctx_fail(ctx, PQG_ERR_ARG, "pqg_chunk_index: needs a decoded BYTE_ARRAY plan (pqg_plan_run + pqg_plan_finish first)");
+    CUF(ctx, cudaSetDevice(ctx_device(ctx)));
+    cudaStream_t s = ctx_stream(ctx);
+    DecodeParams P = plan_params(plan);
+    const uint64_t n = plan_slots(plan);
+    DevMem mem;
+    uint64_t* d_rb = nullptr; uint32_t* d_ids = nullptr;
+    CUF(ctx, mem.alloc(&d_rb, P.n_chunks + 2));
+    CUF(ctx, mem.alloc(&d_ids, n + 1));
+    cudaEvent_t e0, e1;
+    CUF(ctx, cudaEventCreate(&e0));
+    CUF(ctx, cudaEventCreate(&e1));
+    CUF(ctx, cudaEventRecord(e0, s));
+    k_chunk_row_bases<<<(P.n_chunks + 1 + 127) / 128, 128, 0, s>>>(P.chunks, P.n_chunks, n, d_rb);
+    StrWeights src{P.offsets, P.validity, d_rb, P.n_chunks};
+    ChainOut out;
+    cudaError_t ce = run_chain(src, n, chunk_size, carry_in, true, d_ids, mem, out, s);
+    if (ce != cudaSuccess) return ctx_fail(ctx, PQG_ERR_CUDA, std::string("chunk index: ") + cudaGetErrorString(ce));
+    CUF(ctx, cudaEventRecord(e1, s));
+    if (tuple_to_chunk && n) CUF(ctx, cudaMemcpyAsync(tuple_to_chunk, d_ids, n * 4, cudaMemcpyDeviceToHost, s));
+    CUF(ctx, cudaStreamSynchronize(s));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (kernel_ms) *kernel_ms = ms;
+    if (n_chunks) *n_chunks = out.n_cuts + 1;
+    if (carry_out) *carry_out = out.n_cuts ? out.total - out.last_cut_P : carry_in + out.total;
+    ctx_add_launches(ctx, out.launches + 1);
+    return PQG_OK;
+}
+
+int pqg_page_chunk_index(pqg_ctx* ctx, const uint32_t* page_sizes, uint32_t n_pages, uint64_t chunk_size, uint32_t* page_chunk,
+                         uint32_t* page_off, uint32_t* chunk_first_page, uint32_t cap, uint32_t* n_chunks) {
+    if (!ctx || (!page_sizes && n_pages)) return ctx_fail(ctx, PQG_ERR_ARG, "pqg_page_chunk_index: bad argument");
+    if (chunk_size == 0) return ctx_fail(ctx, PQG_ERR_ARG, "pqg_page_chunk_index: chunk_size must be > 0");
+    if (n_chunks) *n_chunks = 0;
+    if (n_pages == 0) return PQG_OK;
+    CUF(ctx, cudaSetDevice(ctx_device(ctx)));
+    cudaStream_t s = ctx_stream(ctx);
+    DevMem mem;
+    uint32_t* d_w = nullptr; uint32_t* d_ids = nullptr; uint32_t* d_off = nullptr; uint32_t* d_first = nullptr;
+    CUF(ctx, mem.alloc(&d_w, n_pages));
+    CUF(ctx, mem.alloc(&d_ids, n_pages));
+    CUF(ctx, mem.alloc(&d_off, n_pages));
+    CUF(ctx, cudaMemcpyAsync(d_w, page_sizes, static_cast<size_t>(n_pages) * 4, cudaMemcpyHostToDevice, s));
+    ArrWeights src{d_w};
+    ChainOut out;
+    // the first page never closes a chunk (there is nothing to close): carry_in = 0
+    cudaError_t ce = run_chain(src, n_pages, chunk_size, 0, false, d_ids, mem, out, s);
+    if (ce != cudaSuccess) return ctx_fail(ctx, PQG_ERR_CUDA, std::string("page chunk index: ") + cudaGetErrorString(ce));
+    k_page_offsets<<<(n_pages + 255) / 256, 256, 0, s>>>(out.d_P, n_pages, d_ids, out.d_cuts, d_off);
+    if (page_chunk) CUF(ctx, cudaMemcpyAsync(page_chunk, d_ids, static_cast<size_t>(n_pages) * 4, cudaMemcpyDeviceToHost, s));
+    if (page_off) CUF(ctx, cudaMemcpyAsync(page_off, d_off, static_cast<size_t>(n_pages) * 4, cudaMemcpyDeviceToHost, s));
+    if (chunk_first_page && cap) {
+        chunk_first_page[0] = 0;
+        uint64_t take = std::min<uint64_t>(out.n_cuts, cap - 1);
+        if (take) {
+            CUF(ctx, mem.alloc(&d_first, take));
+            k_narrow<<<static_cast<unsigned>((take + 255) / 256), 256, 0, s>>>(out.d_cuts, take, d_first);
+            CUF(ctx, cudaMemcpyAsync(chunk_first_page + 1, d_first, take * 4, cudaMemcpyDeviceToHost, s));
+        }
+    }
+    CUF(ctx, cudaStreamSynchronize(s));
+    if (n_chunks) *n_chunks = static_cast<uint32_t>(out.n_cuts + 1);
+    ctx_add_launches(ctx, out.launches + 2);
+    return PQG_OK;
+}
+
+} // extern "C"

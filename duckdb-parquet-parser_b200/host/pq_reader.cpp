@@ -529,6 +529,15 @@ CachedPlan& ParquetReader::cached_plan(int col_idx, int row_group_idx) {
 
 void ParquetReader::release_plans() { plans_.clear(); }
 
+ParquetReader::DevicePlan ParquetReader::device_plan(int col_idx, int row_group_idx, bool upload) {
+    CachedPlan& cp = cached_plan(col_idx, row_group_idx);
+    if (upload && cp.buf) {
+        for (const pqg_h2d_range& r : cp.ranges)
+            if (pqg_buf_write(cp.ctx, cp.buf, r.image_off, r.host, r.len) != PQG_OK) throw_ctx(cp.ctx, "upload");
+    }
+    return DevicePlan{cp.ctx, cp.buf, cp.plan, static_cast<uint32_t>(cp.t.pages.size()), static_cast<uint32_t>(cp.t.chunks.size())};
+}
+
 void ParquetReader::read_columns_into(const int* col_idx, int n_cols, int row_group_idx, const ColumnDst* dsts, ColumnReadStats* stats) {
     if (n_cols < 0 || (n_cols && (!col_idx || !dsts))) throw std::runtime_error("read_columns_into: bad argument");
     std::vector<CachedPlan*> cps;

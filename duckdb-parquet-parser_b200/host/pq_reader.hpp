@@ -210,6 +210,11 @@ public:
     // first use and kept until release_plans() / close.  row_group_idx < 0 = all row groups.
     void read_columns_into(const int* col_idx, int n_cols, int row_group_idx, const ColumnDst* dsts, ColumnReadStats* stats);
     void release_plans();
+    // The cached device-side state of a column: descriptor tables, device image, decode plan.
+    // upload = true copies the column's bytes into the device image (synchronously ordered on
+    // the context's stream).  plan is null for a column without pages.
+    struct DevicePlan { pqg_ctx* ctx; pqg_buf* image; pqg_plan* plan; uint32_t n_pages; uint32_t n_chunks; };
+    DevicePlan device_plan(int col_idx, int row_group_idx, bool upload);
 
     StringColumnIterator column_iterator(const std::string& col_name);
 

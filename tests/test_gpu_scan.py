@@ -1,0 +1,141 @@
+"""GPU parity tests of the regex page-pruning scan and the 4 KB chunk
+indexes (a-18 tuple level: reference src/main.cpp:21-32; a-20 page level), through the C-ABI,
+against the oracle (oracle/regex_oracle.c backtracking matcher over the reference-order
+values; the loop of src/main.cpp restated in oracle/pq_oracle.c)."""
+import numpy as np
+import pytest
+
+from oraclelib import BYTE_ARRAY
+
+pytestmark = pytest.mark.gpu
+
+PATTERNS = [
+    r"^[a-z0-9._]+@[a-z0-9.]+\.com$",      # BASELINE config 4
+    r"@mail7",                               # unanchored literal
+    r"^user1[0-9]*@",
+    r"example\.com!!$",
+    r"^$",                                   # matches only empty strings
+    r"Berlin|Dublin",
+    r"city_0000[0-4]",
+    r"(ab|cd)+x?y{2,3}",
+    r"[^a-z]",
+    r".",
+    r"\d{9}",
+]
+
+
+def string_columns(r):
+    return [c for c in range(r.num_columns) if r.column_info(c)["type"] == BYTE_ARRAY]
+
+
+def test_regex_prune_matches_oracle(pq, oracle, files):
+    for name, path in files.items():
+        r = pq.Reader(path)
+        ho = oracle.open(path)
+        try:
+            for c in string_columns(r):
+                for pat in PATTERNS:
+                    for neg in (False, True):
+                        got, ms = r.regex_prune(c, pat, neg)
+                        exp = oracle.regex_prune(ho, c, pat, neg)
+                        assert got.shape == exp.shape, (name, c, pat)
+                        assert np.array_equal(got, exp), (name, r.column_info(c)["name"], pat, neg, int(np.nonzero(got != exp)[0][0]))
+        finally:
+            oracle.close(ho)
+            r.close()
+
+
+def test_regex_rejects_unsupported_and_non_string(pq, files):
+    r = pq.Reader(files["golden_mixed"])
+    sc = string_columns(r)[0]
+    for bad in (r"(a)\1", r"(?=a)b", r"a{2,1}", r"[z-a]", r"("):
+        with pytest.raises(pq.PqgError):
+            r.regex_prune(sc, bad)
+    other = [c for c in range(r.num_columns) if c not in string_columns(r)][0]
+    with pytest.raises(pq.PqgError):
+        r.regex_prune(other, "a")
+    r.close()
+
+
+def test_chunk_index_matches_oracle(pq, oracle, files):
+    for name, path in files.items():
+        r = pq.Reader(path)
+        ho = oracle.open(path)
+        try:
+            for c in string_columns(r):
+                cname = r.column_info(c)["name"]
+                for cs in (4096, 1, 100, 1 << 20):
+                    got, n = r.chunk_index(cname, cs)
+                    exp, ne = oracle.chunk_index(ho, cname, cs)
+                    assert n == ne, (name, cname, cs, n, ne)
+                    assert np.array_equal(got, exp), (name, cname, cs, int(np.nonzero(got != exp)[0][0]))
+        finally:
+            oracle.close(ho)
+            r.close()
+
+
+def test_chunk_index_errors(pq, files):
+    r = pq.Reader(files["golden_mixed"])
+    with pytest.raises(pq.PqgError, match="Column not found"):
+        r.chunk_index("nope")
+    other = [c for c in range(r.num_columns) if c not in string_columns(r)][0]
+    with pytest.raises(pq.PqgError, match="is not BYTE_ARRAY"):
+        r.chunk_index(r.column_info(other)["name"])
+    r.close()
+
+
+def test_page_chunk_index_matches_oracle(pq, oracle, files):
+    for name, path in files.items():
+        r = pq.Reader(path)
+        ho = oracle.open(path)
+        try:
+            for c in range(r.num_columns):
+                for cs in (4096, 1000, 1 << 16):
+                    a = r.page_chunk_index(c, cs)
+                    b = oracle.page_chunk_index(ho, c, cs)
+                    for x, y, what in zip(a, b, ("page_chunk", "page_off", "chunk_first_page")):
+                        assert np.array_equal(x, y), (name, c, cs, what)
+        finally:
+            oracle.close(ho)
+            r.close()
+
+
+def test_chunk_index_shards_stitch_like_one_run(pq, oracle, files):
+    """multi-GPU recipe on one GPU: decode row groups as separate shards, chain them with
+    carry_in / carry_out, compare with the single-shard answer (host gather of offsets)."""
+    import ctypes as C
+    path = files.get("strings", files["golden_mixed"])
+    r = pq.Reader(path)
+    L = pq.lib()
+    ctx = pq.Context(0)
+    img = np.fromfile(path, dtype=np.uint8)
+    buf = ctx.upload(img.ctypes.data, img.size)
+    try:
+        for c in string_columns(r):
+            cname = r.column_info(c)["name"]
+            whole, n_whole = r.chunk_index(cname, 4096)
+            carry, base, pieces = 0, 0, []
+            for rg in range(r.num_row_groups):
+                plan = ctx.plan(buf, r.column_tables(c, rg))
+                plan.run()
+                plan.finish()
+                n = plan.num_slots
+                ids = np.zeros(n + 1, dtype=np.uint32)
+                nch, cout, ms = C.c_uint64(0), C.c_uint64(0), C.c_float(0)
+                rc = L.pqg_chunk_index(ctx.h, plan.h, 4096, carry, ids.ctypes.data, C.byref(nch), C.byref(cout), C.byref(ms))
+                assert rc == 0, ctx.err()
+                valid_ids = ids[:n].astype(np.uint64)
+                nz = r.read_column(cname, rg=rg)["is_null"].astype(bool)
+                valid_ids[~nz] += np.uint64(base)
+                valid_ids[nz] = 0
+                pieces.append(valid_ids)
+                base += nch.value - 1
+                carry = cout.value
+                plan.destroy()
+            got = np.concatenate(pieces)
+            assert base + 1 == n_whole, (cname, base + 1, n_whole)
+            assert np.array_equal(got, whole), cname
+    finally:
+        ctx.buf_free(buf)
+        ctx.close()
+        r.close()
