@@ -322,8 +322,16 @@ __global__ void __launch_bounds__(128) k_chain_walk(const uint64_t* P, uint64_t 
 }
 
 // first cut of the sequence: first slot with carry_in + P >= S
-__global__ void k_chain_entry(const uint64_t* P, uint64_t n, uint64_t x0, uint64_t* out) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) { out[0] = lower_bound_P(P, n, x0); out[1] = P[n]; }
+// out[2] = number of slots that can still start a chunk: with zero-weight (null) slots masked,
+// the slots behind the last weighted one never do (the reference only cuts when a value follows)
+__global__ void k_chain_entry(const uint64_t* P, uint64_t n, uint64_t x0, bool mask_zero, uint64_t* out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        const uint64_t total = P[n];
+        const uint64_t n_eff = mask_zero ? lower_bound_P(P, n, total) : n;
+        out[0] = lower_bound_P(P, n_eff, x0);
+        out[1] = total;
+        out[2] = n_eff;
+    }
 }
 
 // materialise the cuts: tile t walks from its true entry
@@ -420,13 +428,15 @@ cudaError_t run_chain(Src src, uint64_t n, uint64_t S, uint64_t carry_in, bool m
     }
     const uint64_t x0 = carry_in >= S ? 0 : S - carry_in;
     uint64_t* d_entry = nullptr;
-    CK(mem.alloc(&d_entry, 2));
-    k_chain_entry<<<1, 32, 0, s>>>(out.d_P, n, x0, d_entry);
+    CK(mem.alloc(&d_entry, 3));
+    k_chain_entry<<<1, 32, 0, s>>>(out.d_P, n, x0, mask_zero, d_entry);
     out.launches++;
-    uint64_t h_entry[2];
-    CK(cudaMemcpyAsync(h_entry, d_entry, 16, cudaMemcpyDeviceToHost, s));
+    uint64_t h_entry[3];
+    CK(cudaMemcpyAsync(h_entry, d_entry, 24, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     out.total = h_entry[1];
+    const uint64_t n_all = n;
+    n = h_entry[2]; // the chain only sees slots that can start a chunk
     const uint64_t L = S * kChainTileChunks;
     const uint64_t T = out.total / L + 1;
     uint64_t* d_klo = nullptr; uint32_t* d_ncand = nullptr;
@@ -478,8 +488,8 @@ cudaError_t run_chain(Src src, uint64_t n, uint64_t S, uint64_t carry_in, bool m
     CK(cudaMemcpyAsync(d_tile_base, tile_base.data(), (T + 1) * 8, cudaMemcpyHostToDevice, s));
     k_chain_emit<<<static_cast<unsigned>((T + 127) / 128), 128, 0, s>>>(out.d_P, n, S, L, T, d_tile_entry, d_tile_base, out.d_cuts);
     out.launches++;
-    if (n && d_ids) {
-        k_chain_ids<Src><<<static_cast<unsigned>((n + 2047) / 2048), 256, 0, s>>>(src, n, out.d_cuts, out.n_cuts, mask_zero, d_ids);
+    if (n_all && d_ids) {
+        k_chain_ids<Src><<<static_cast<unsigned>((n_all + 2047) / 2048), 256, 0, s>>>(src, n_all, out.d_cuts, out.n_cuts, mask_zero, d_ids);
         out.launches++;
     }
     if (out.n_cuts) {
