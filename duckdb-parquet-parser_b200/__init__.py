@@ -131,7 +131,7 @@ PQR_SYMBOLS = [
     "pqr_read_pages_chunk", "pqr_read_column_by_idx", "pqr_read_column", "pqr_read_column_rg", "pqr_read_pages",
     "pqr_string_iterator_dump", "pqr_valdump_free", "pqr_pagedump_free", "pqr_strdump_free", "pqr_read_columnar",
     "pqr_columnar_free", "pqr_read_columns_into", "pqr_release_plans", "pqr_column_tables", "pqr_tables_free", "pqr_chunk_index", "pqr_regex_prune",
-    "pqr_page_chunk_index",
+    "pqr_page_chunk_index", "pqr_shard_row_groups", "pqr_regex_prune_rgs", "pqr_chunk_index_rgs", "pqr_read_columns_into_rgs",
 ]
 
 PQGEN_SYMBOLS = ["pqgen_last_error", "pqgen_encode", "pqgen_size", "pqgen_emit", "pqgen_write_file", "pqgen_free"]
@@ -197,7 +197,7 @@ def _declare(L):
     d("pqg_dfa_num_states", u32, vp)
     d("pqg_dfa_match_host", i32, vp, vp, u64)
     d("pqg_regex_scan", i32, vp, vp, vp, i32, vp, C.POINTER(C.c_float))
-    d("pqg_chunk_index", i32, vp, vp, u64, u64, vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(C.c_float))
+    d("pqg_chunk_index", i32, vp, vp, u64, u64, u32, vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(C.c_float))
     d("pqg_page_chunk_index", i32, vp, vp, u32, u64, vp, vp, vp, u32, C.POINTER(u32))
 
     d("pqgen_last_error", cp)
@@ -234,6 +234,10 @@ def _declare(L):
     d("pqr_columnar_free", None, C.POINTER(Columnar))
     d("pqr_read_columns_into", i32, vp, C.POINTER(C.c_int32), i32, i32, C.POINTER(Dst), C.POINTER(ReadStats))
     d("pqr_release_plans", None, vp)
+    d("pqr_shard_row_groups", i32, vp, i32, i32, C.POINTER(C.c_int32))
+    d("pqr_regex_prune_rgs", i64, vp, i32, i64, i64, cp, i32, vp, i64, C.POINTER(C.c_float))
+    d("pqr_chunk_index_rgs", i64, vp, cp, i64, i64, u64, u64, u32, vp, i64, C.POINTER(u64))
+    d("pqr_read_columns_into_rgs", i32, vp, C.POINTER(C.c_int32), i32, i64, i64, C.POINTER(Dst), C.POINTER(ReadStats))
     d("pqr_column_tables", i32, vp, i32, i32, C.POINTER(Tables))
     d("pqr_tables_free", None, C.POINTER(Tables))
     d("pqr_chunk_index", i64, vp, cp, u64, vp, i64)
@@ -405,6 +409,40 @@ class Reader:
             ds[i] = Dst(vp_, vc, mp, mc)
         st = (ReadStats * n)()
         self._check(lib().pqr_read_columns_into(self.h, ci, n, rg, ds, st))
+        return [dict(num_slots=s.num_slots, width=s.width, has_validity=bool(s.has_validity), bytes_in=s.bytes_in,
+                     bytes_out=s.bytes_out, h2d_bytes=s.h2d_bytes, d2h_bytes=s.d2h_bytes) for s in st]
+
+    def shard_row_groups(self, col, n_shards):
+        out = (C.c_int32 * (n_shards + 1))()
+        self._check(lib().pqr_shard_row_groups(self.h, col, n_shards, out))
+        return list(out)
+
+    def regex_prune_rgs(self, col, rg_begin, rg_end, pattern, neg=False):
+        if isinstance(pattern, str):
+            pattern = pattern.encode()
+        cap = max(self.num_pages, 1)
+        bits = np.zeros(cap, dtype=np.uint8)
+        ms = C.c_float(0)
+        n = self._check(lib().pqr_regex_prune_rgs(self.h, col, rg_begin, rg_end, pattern, int(neg), bits.ctypes.data, cap, C.byref(ms)))
+        return bits[:n], ms.value
+
+    def chunk_index_rgs(self, name, rg_begin, rg_end, chunk_size=4096, carry_in=0, id_base=0):
+        """-> (chunk ids of the shard's rows: id_base + local id, nulls 0; shard chunk count; carry_out)"""
+        rows = sum(self.row_group_num_rows(rg) for rg in range(rg_begin, rg_end))
+        ids = np.zeros(rows + 1, dtype=np.uint32)
+        carry = C.c_uint64(0)
+        n = self._check(lib().pqr_chunk_index_rgs(self.h, name.encode(), rg_begin, rg_end, chunk_size, carry_in, id_base,
+                                                  ids.ctypes.data, ids.size, C.byref(carry)))
+        return ids[:rows], n, carry.value
+
+    def read_columns_into_rgs(self, cols, dsts, rg_begin, rg_end):
+        n = len(cols)
+        ci = (C.c_int32 * n)(*cols)
+        ds = (Dst * n)()
+        for i, (vp_, vc, mp, mc) in enumerate(dsts):
+            ds[i] = Dst(vp_, vc, mp, mc)
+        st = (ReadStats * n)()
+        self._check(lib().pqr_read_columns_into_rgs(self.h, ci, n, rg_begin, rg_end, ds, st))
         return [dict(num_slots=s.num_slots, width=s.width, has_validity=bool(s.has_validity), bytes_in=s.bytes_in,
                      bytes_out=s.bytes_out, h2d_bytes=s.h2d_bytes, d2h_bytes=s.d2h_bytes) for s in st]
 

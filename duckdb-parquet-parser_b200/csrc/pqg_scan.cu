@@ -352,7 +352,7 @@ __global__ void k_chain_emit(const uint64_t* P, uint64_t n, uint64_t S, uint64_t
 
 // ids[i] = number of cuts at slots <= i (0 for zero-weight slots when mask_zero)
 template <class Src>
-__global__ void __launch_bounds__(256) k_chain_ids(Src src, uint64_t n, const uint64_t* cuts, uint64_t n_cuts, bool mask_zero, uint32_t* ids) {
+__global__ void __launch_bounds__(256) k_chain_ids(Src src, uint64_t n, const uint64_t* cuts, uint64_t n_cuts, bool mask_zero, uint32_t id_base, uint32_t* ids) {
     __shared__ uint64_t first;
     const uint64_t b0 = static_cast<uint64_t>(blockIdx.x) * 2048u;
     if (threadIdx.x == 0) { // cuts <= b0
@@ -368,7 +368,7 @@ __global__ void __launch_bounds__(256) k_chain_ids(Src src, uint64_t n, const ui
         uint64_t lo = first, hi = min(n_cuts, first + j + 1);
         while (lo < hi) { uint64_t mid = (lo + hi) >> 1; if (cuts[mid] <= i) lo = mid + 1; else hi = mid; }
         const uint64_t c = lo;
-        ids[i] = (mask_zero && src(i) == 0) ? 0u : static_cast<uint32_t>(c);
+        ids[i] = (mask_zero && src(i) == 0) ? 0u : id_base + static_cast<uint32_t>(c);
     }
 }
 
@@ -412,8 +412,8 @@ struct ChainOut {
 // Greedy chunking of the weight sequence src(0..n): d_ids[i] = chunk id (shard local, the
 // open chunk carried in is id 0).  Synchronises the stream (the stitch runs on the host).
 template <class Src>
-cudaError_t run_chain(Src src, uint64_t n, uint64_t S, uint64_t carry_in, bool mask_zero, uint32_t* d_ids, DevMem& mem, ChainOut& out,
-                      cudaStream_t s) {
+cudaError_t run_chain(Src src, uint64_t n, uint64_t S, uint64_t carry_in, bool mask_zero, uint32_t id_base, uint32_t* d_ids, DevMem& mem,
+                      ChainOut& out, cudaStream_t s) {
     const uint64_t nb = (n + kScanTile - 1) / kScanTile;
     uint64_t* d_sums = nullptr;
     CK(mem.alloc(&d_sums, nb + 2));
@@ -489,7 +489,7 @@ cudaError_t run_chain(Src src, uint64_t n, uint64_t S, uint64_t carry_in, bool m
     k_chain_emit<<<static_cast<unsigned>((T + 127) / 128), 128, 0, s>>>(out.d_P, n, S, L, T, d_tile_entry, d_tile_base, out.d_cuts);
     out.launches++;
     if (n_all && d_ids) {
-        k_chain_ids<Src><<<static_cast<unsigned>((n_all + 2047) / 2048), 256, 0, s>>>(src, n_all, out.d_cuts, out.n_cuts, mask_zero, d_ids);
+        k_chain_ids<Src><<<static_cast<unsigned>((n_all + 2047) / 2048), 256, 0, s>>>(src, n_all, out.d_cuts, out.n_cuts, mask_zero, id_base, d_ids);
         out.launches++;
     }
     if (out.n_cuts) {
@@ -593,7 +593,7 @@ int pqg_regex_scan(pqg_ctx* ctx, pqg_plan* plan, const pqg_dfa* dfa, int neg, ui
     return PQG_OK;
 }
 
-int pqg_chunk_index(pqg_ctx* ctx, pqg_plan* plan, uint64_t chunk_size, uint64_t carry_in, uint32_t* tuple_to_chunk,
+int pqg_chunk_index(pqg_ctx* ctx, pqg_plan* plan, uint64_t chunk_size, uint64_t carry_in, uint32_t id_base, uint32_t* tuple_to_chunk,
                     uint64_t* n_chunks, uint64_t* carry_out, float* kernel_ms) {
     if (!ctx || !plan) return ctx_fail(ctx, PQG_ERR_ARG, "pqg_chunk_index: bad argument");
     if (chunk_size == 0) return ctx_fail(ctx, PQG_ERR_ARG, "pqg_chunk_index: chunk_size must be > 0");
@@ -613,7 +613,7 @@ int pqg_chunk_index(pqg_ctx* ctx, pqg_plan* plan, uint64_t chunk_size, uint64_t 
     k_chunk_row_bases<<<(P.n_chunks + 1 + 127) / 128, 128, 0, s>>>(P.chunks, P.n_chunks, n, d_rb);
     StrWeights src{P.offsets, P.validity, d_rb, P.n_chunks};
     ChainOut out;
-    cudaError_t ce = run_chain(src, n, chunk_size, carry_in, true, d_ids, mem, out, s);
+    cudaError_t ce = run_chain(src, n, chunk_size, carry_in, true, id_base, d_ids, mem, out, s);
     if (ce != cudaSuccess) return ctx_fail(ctx, PQG_ERR_CUDA, std::string("chunk index: ") + cudaGetErrorString(ce));
     CUF(ctx, cudaEventRecord(e1, s));
     if (tuple_to_chunk && n) CUF(ctx, cudaMemcpyAsync(tuple_to_chunk, d_ids, n * 4, cudaMemcpyDeviceToHost, s));
@@ -645,7 +645,7 @@ int pqg_page_chunk_index(pqg_ctx* ctx, const uint32_t* page_sizes, uint32_t n_pa
     ArrWeights src{d_w};
     ChainOut out;
     // the first page never closes a chunk (there is nothing to close): carry_in = 0
-    cudaError_t ce = run_chain(src, n_pages, chunk_size, 0, false, d_ids, mem, out, s);
+    cudaError_t ce = run_chain(src, n_pages, chunk_size, 0, false, 0, d_ids, mem, out, s);
     if (ce != cudaSuccess) return ctx_fail(ctx, PQG_ERR_CUDA, std::string("page chunk index: ") + cudaGetErrorString(ce));
     k_page_offsets<<<(n_pages + 255) / 256, 256, 0, s>>>(out.d_P, n_pages, d_ids, out.d_cuts, d_off);
     if (page_chunk) CUF(ctx, cudaMemcpyAsync(page_chunk, d_ids, static_cast<size_t>(n_pages) * 4, cudaMemcpyDeviceToHost, s));

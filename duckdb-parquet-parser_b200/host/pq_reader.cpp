@@ -16,6 +16,7 @@
 #include <mutex>
 #include <sstream>
 #include <thread>
+#include <tuple>
 
 namespace pqg {
 
@@ -436,11 +437,16 @@ std::string ParquetReader::schema_string() const {
 }
 
 ColumnTables ParquetReader::column_tables(int col_idx, int row_group_idx) const {
+    size_t rg0 = row_group_idx < 0 ? 0 : static_cast<size_t>(row_group_idx);
+    size_t rg1 = row_group_idx < 0 ? metadata_.row_groups.size() : rg0 + 1;
+    return column_tables_range(col_idx, rg0, rg1);
+}
+
+ColumnTables ParquetReader::column_tables_range(int col_idx, size_t rg0, size_t rg1) const {
     // tables against FILE offsets (image byte 0 = file byte 0)
     ColumnTables t;
     const ColumnInfo& ci = columns_.at(static_cast<size_t>(col_idx));
-    size_t rg0 = row_group_idx < 0 ? 0 : static_cast<size_t>(row_group_idx);
-    size_t rg1 = row_group_idx < 0 ? metadata_.row_groups.size() : rg0 + 1;
+    if (rg1 > metadata_.row_groups.size() || rg0 > rg1) throw std::runtime_error("Invalid row group index");
     for (size_t rg = rg0; rg < rg1; rg++) {
         const ColumnChunk& chunk = metadata_.row_groups[rg].columns.at(static_cast<size_t>(ci.column_index));
         if (!chunk.meta_data) throw std::runtime_error("ColumnChunk has no metadata");
@@ -501,15 +507,22 @@ struct CachedPlan {
 
 CachedPlan& ParquetReader::cached_plan(int col_idx, int row_group_idx) {
     if (row_group_idx >= static_cast<int>(metadata_.row_groups.size())) throw std::runtime_error("Invalid row group index");
+    size_t rg0 = row_group_idx < 0 ? 0 : static_cast<size_t>(row_group_idx);
+    size_t rg1 = row_group_idx < 0 ? metadata_.row_groups.size() : rg0 + 1;
+    return cached_plan_range(col_idx, rg0, rg1);
+}
+
+CachedPlan& ParquetReader::cached_plan_range(int col_idx, size_t rg0, size_t rg1) {
+    if (rg1 > metadata_.row_groups.size() || rg0 > rg1) throw std::runtime_error("Invalid row group index");
     if (col_idx < 0 || col_idx >= static_cast<int>(columns_.size())) throw std::runtime_error("Invalid column index");
-    auto key = std::make_pair(col_idx, row_group_idx < 0 ? -1 : row_group_idx);
+    auto key = std::make_tuple(col_idx, rg0, rg1);
     auto it = plans_.find(key);
     if (it != plans_.end()) return *it->second;
     auto cp = std::make_unique<CachedPlan>();
     cp->type = columns_[static_cast<size_t>(col_idx)].type;
     static const uint32_t widths[] = {1, 4, 8, 12, 4, 8, 0, 0};
     cp->width = widths[static_cast<int>(cp->type) & 7];
-    cp->t = column_tables(col_idx, row_group_idx);
+    cp->t = column_tables_range(col_idx, rg0, rg1);
     cp->img = pack_column(cp->t, file_size_);
     cp->ctx = Device::get(device_).ctx();
     if (cp->t.chunks.empty()) { auto& ref = *cp; plans_[key] = std::move(cp); return ref; }
@@ -530,7 +543,41 @@ CachedPlan& ParquetReader::cached_plan(int col_idx, int row_group_idx) {
 void ParquetReader::release_plans() { plans_.clear(); }
 
 ParquetReader::DevicePlan ParquetReader::device_plan(int col_idx, int row_group_idx, bool upload) {
-    CachedPlan& cp = cached_plan(col_idx, row_group_idx);
+    if (row_group_idx >= static_cast<int>(metadata_.row_groups.size())) throw std::runtime_error("Invalid row group index");
+    size_t rg0 = row_group_idx < 0 ? 0 : static_cast<size_t>(row_group_idx);
+    size_t rg1 = row_group_idx < 0 ? metadata_.row_groups.size() : rg0 + 1;
+    return device_plan_range(col_idx, rg0, rg1, upload);
+}
+
+std::vector<int32_t> ParquetReader::shard_row_groups(int col_idx, int n_shards) const {
+    if (n_shards < 1) throw std::runtime_error("shard_row_groups: n_shards must be >= 1");
+    if (col_idx >= static_cast<int>(columns_.size())) throw std::runtime_error("Invalid column index");
+    const size_t nrg = metadata_.row_groups.size();
+    std::vector<uint64_t> bytes(nrg, 0);
+    uint64_t total = 0;
+    for (size_t rg = 0; rg < nrg; rg++) {
+        const auto& cols = metadata_.row_groups[rg].columns;
+        for (size_t c = 0; c < cols.size(); c++) {
+            if (col_idx >= 0 && static_cast<int>(c) != columns_[static_cast<size_t>(col_idx)].column_index) continue;
+            if (cols[c].meta_data) bytes[rg] += static_cast<uint64_t>(std::max<int64_t>(cols[c].meta_data->total_compressed_size, 0));
+        }
+        total += bytes[rg];
+    }
+    // boundary s = first row group whose byte prefix reaches s/n of the total (contiguous, ordered)
+    std::vector<int32_t> out(static_cast<size_t>(n_shards) + 1, static_cast<int32_t>(nrg));
+    out[0] = 0;
+    uint64_t acc = 0;
+    size_t rg = 0;
+    for (int s = 1; s < n_shards; s++) {
+        const double target = static_cast<double>(total) * s / n_shards;
+        while (rg < nrg && static_cast<double>(acc) + bytes[rg] * 0.5 < target) acc += bytes[rg++];
+        out[static_cast<size_t>(s)] = static_cast<int32_t>(rg);
+    }
+    return out;
+}
+
+ParquetReader::DevicePlan ParquetReader::device_plan_range(int col_idx, size_t rg0, size_t rg1, bool upload) {
+    CachedPlan& cp = cached_plan_range(col_idx, rg0, rg1);
     if (upload && cp.buf) {
         for (const pqg_h2d_range& r : cp.ranges)
             if (pqg_buf_write(cp.ctx, cp.buf, r.image_off, r.host, r.len) != PQG_OK) throw_ctx(cp.ctx, "upload");
@@ -539,10 +586,17 @@ ParquetReader::DevicePlan ParquetReader::device_plan(int col_idx, int row_group_
 }
 
 void ParquetReader::read_columns_into(const int* col_idx, int n_cols, int row_group_idx, const ColumnDst* dsts, ColumnReadStats* stats) {
+    if (row_group_idx >= static_cast<int>(metadata_.row_groups.size())) throw std::runtime_error("Invalid row group index");
+    size_t rg0 = row_group_idx < 0 ? 0 : static_cast<size_t>(row_group_idx);
+    size_t rg1 = row_group_idx < 0 ? metadata_.row_groups.size() : rg0 + 1;
+    read_columns_into_range(col_idx, n_cols, rg0, rg1, dsts, stats);
+}
+
+void ParquetReader::read_columns_into_range(const int* col_idx, int n_cols, size_t rg0, size_t rg1, const ColumnDst* dsts, ColumnReadStats* stats) {
     if (n_cols < 0 || (n_cols && (!col_idx || !dsts))) throw std::runtime_error("read_columns_into: bad argument");
     std::vector<CachedPlan*> cps;
     for (int i = 0; i < n_cols; i++) {
-        CachedPlan& cp = cached_plan(col_idx[i], row_group_idx);
+        CachedPlan& cp = cached_plan_range(col_idx[i], rg0, rg1);
         if (cp.type == ParquetType::BYTE_ARRAY || cp.width == 0)
             throw std::runtime_error("read_columns_into: fixed-width columns only (use read_column_columnar for BYTE_ARRAY)");
         const uint64_t need = cp.t.total_slots * cp.width;

@@ -204,17 +204,23 @@ public:
     // columnar variants: row_group_idx < 0 = all row groups
     DecodedColumn read_column_columnar(int col_idx, int row_group_idx = -1);
     ColumnTables column_tables(int col_idx, int row_group_idx = -1) const;
+    ColumnTables column_tables_range(int col_idx, size_t rg_begin, size_t rg_end) const; // row groups [begin, end)
     // Streaming read of fixed-width columns from the (host) file image into caller-owned host
     // buffers: per row group H2D -> decode -> D2H on three streams, all requested columns in
     // one pipeline.  Descriptor tables, the device image and the plan of a column are built on
     // first use and kept until release_plans() / close.  row_group_idx < 0 = all row groups.
     void read_columns_into(const int* col_idx, int n_cols, int row_group_idx, const ColumnDst* dsts, ColumnReadStats* stats);
+    void read_columns_into_range(const int* col_idx, int n_cols, size_t rg_begin, size_t rg_end, const ColumnDst* dsts, ColumnReadStats* stats);
     void release_plans();
     // The cached device-side state of a column: descriptor tables, device image, decode plan.
     // upload = true copies the column's bytes into the device image (synchronously ordered on
     // the context's stream).  plan is null for a column without pages.
     struct DevicePlan { pqg_ctx* ctx; pqg_buf* image; pqg_plan* plan; uint32_t n_pages; uint32_t n_chunks; };
     DevicePlan device_plan(int col_idx, int row_group_idx, bool upload);
+    DevicePlan device_plan_range(int col_idx, size_t rg_begin, size_t rg_end, bool upload);
+    // contiguous split of the row groups over n_shards, balanced by the byte size of the column's
+    // chunks (col_idx < 0: of all columns); returns n_shards + 1 boundaries (multi-GPU sharding)
+    std::vector<int32_t> shard_row_groups(int col_idx, int n_shards) const;
 
     StringColumnIterator column_iterator(const std::string& col_name);
 
@@ -256,8 +262,9 @@ private:
     std::vector<PageIndexEntry> page_index_;
     std::vector<std::vector<std::vector<PageRecord>>> chunk_pages_; // [rg][chunk column]
     std::vector<std::vector<size_t>> chunk_first_page_;              // [rg][chunk column] -> global id
-    std::map<std::pair<int, int>, std::unique_ptr<CachedPlan>> plans_; // (column, row group | -1)
+    std::map<std::tuple<int, size_t, size_t>, std::unique_ptr<CachedPlan>> plans_; // (column, row groups [begin, end))
     CachedPlan& cached_plan(int col_idx, int row_group_idx);
+    CachedPlan& cached_plan_range(int col_idx, size_t rg_begin, size_t rg_end);
 };
 
 } // namespace pqg

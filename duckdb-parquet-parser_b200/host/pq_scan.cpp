@@ -28,6 +28,11 @@ int string_column(ParquetReader& r, const std::string& col_name) {
 } // namespace
 
 int64_t regex_prune(ParquetReader& r, int col, const std::string& pattern, bool neg, uint8_t* bits, int64_t cap, float* kernel_ms) {
+    return regex_prune_rgs(r, col, 0, r.num_row_groups(), pattern, neg, bits, cap, kernel_ms);
+}
+
+int64_t regex_prune_rgs(ParquetReader& r, int col, size_t rg_begin, size_t rg_end, const std::string& pattern, bool neg,
+                        uint8_t* bits, int64_t cap, float* kernel_ms) {
     if (col < 0 || col >= static_cast<int>(r.num_columns())) throw std::runtime_error("Invalid column index");
     const ColumnInfo& ci = r.column(static_cast<size_t>(col));
     if (ci.type != ParquetType::BYTE_ARRAY)
@@ -35,7 +40,7 @@ int64_t regex_prune(ParquetReader& r, int col, const std::string& pattern, bool 
     DfaGuard g;
     char err[512] = {0};
     if (pqg_regex_compile(pattern.c_str(), &g.d, err, sizeof(err)) != PQG_OK) throw std::runtime_error(err);
-    ParquetReader::DevicePlan dp = r.device_plan(col, -1, true);
+    ParquetReader::DevicePlan dp = r.device_plan_range(col, rg_begin, rg_end, true);
     if (kernel_ms) *kernel_ms = 0;
     if (!dp.plan) return 0;
     std::vector<uint32_t> words((static_cast<size_t>(dp.n_pages) + 31) / 32 + 1, 0);
@@ -45,21 +50,32 @@ int64_t regex_prune(ParquetReader& r, int col, const std::string& pattern, bool 
     return static_cast<int64_t>(dp.n_pages);
 }
 
-int64_t chunk_index(ParquetReader& r, const std::string& col_name, uint64_t chunk_size, uint64_t* tuple_to_chunk, int64_t num_rows) {
+int64_t chunk_index_rgs(ParquetReader& r, const std::string& col_name, size_t rg_begin, size_t rg_end, uint64_t chunk_size,
+                        uint64_t carry_in, uint32_t id_base, uint32_t* ids, int64_t cap, uint64_t* carry_out) {
     int col = string_column(r, col_name);
-    for (int64_t i = 0; i < num_rows; i++) tuple_to_chunk[i] = 0;
-    ParquetReader::DevicePlan dp = r.device_plan(col, -1, true);
-    if (!dp.plan) return 1; // no values: chunk 0 only
+    if (carry_out) *carry_out = carry_in;
+    ParquetReader::DevicePlan dp = r.device_plan_range(col, rg_begin, rg_end, true);
+    if (!dp.plan) return 1; // no values: the open chunk only
     if (pqg_plan_run(dp.ctx, dp.plan) != PQG_OK) throw std::runtime_error(pqg_last_error(dp.ctx));
     pqg_page_error pe;
     if (pqg_plan_finish(dp.ctx, dp.plan, &pe) != PQG_OK) throw std::runtime_error(pqg_last_error(dp.ctx));
     const uint64_t n = pqg_plan_num_slots(dp.plan);
-    std::vector<uint32_t> ids(n + 1);
+    if (static_cast<uint64_t>(cap) < n) throw std::runtime_error("chunk_index: output buffer too small");
     uint64_t n_chunks = 0, carry = 0;
-    if (pqg_chunk_index(dp.ctx, dp.plan, chunk_size, 0, ids.data(), &n_chunks, &carry, nullptr) != PQG_OK)
+    if (pqg_chunk_index(dp.ctx, dp.plan, chunk_size, carry_in, id_base, ids, &n_chunks, &carry, nullptr) != PQG_OK)
         throw std::runtime_error(pqg_last_error(dp.ctx));
-    for (uint64_t i = 0; i < n && static_cast<int64_t>(i) < num_rows; i++) tuple_to_chunk[i] = ids[i];
+    if (carry_out) *carry_out = carry;
     return static_cast<int64_t>(n_chunks);
+}
+
+int64_t chunk_index(ParquetReader& r, const std::string& col_name, uint64_t chunk_size, uint64_t* tuple_to_chunk, int64_t num_rows) {
+    string_column(r, col_name);
+    for (int64_t i = 0; i < num_rows; i++) tuple_to_chunk[i] = 0;
+    std::vector<uint32_t> ids(static_cast<size_t>(r.num_rows()) + 1);
+    uint64_t carry = 0;
+    int64_t n_chunks = chunk_index_rgs(r, col_name, 0, r.num_row_groups(), chunk_size, 0, 0, ids.data(), static_cast<int64_t>(ids.size()), &carry);
+    for (int64_t i = 0; i < num_rows && i < r.num_rows(); i++) tuple_to_chunk[i] = ids[static_cast<size_t>(i)];
+    return n_chunks;
 }
 
 int64_t page_chunk_index(ParquetReader& r, int col, uint64_t chunk_size, uint32_t* page_chunk, uint32_t* page_off,

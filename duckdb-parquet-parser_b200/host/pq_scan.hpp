@@ -21,6 +21,17 @@ int64_t regex_prune(ParquetReader& r, int col, const std::string& pattern, bool 
 int64_t chunk_index(ParquetReader& r, const std::string& col_name, uint64_t chunk_size,
                     uint64_t* tuple_to_chunk, int64_t num_rows);
 
+// ── multi-GPU shards: the same operations over the row groups [rg_begin, rg_end) ──────────
+// bits[] covers only the shard's pages (concatenate the shards in order to get the column's
+// bitmap: pages are numbered in row-group order).
+int64_t regex_prune_rgs(ParquetReader& r, int col, size_t rg_begin, size_t rg_end, const std::string& pattern, bool neg,
+                        uint8_t* bits, int64_t cap, float* kernel_ms);
+// tuple_to_chunk_local[i] for the shard's rows (shard-local chunk ids: 0 = the chunk left open by
+// the previous shard); carry_in = bytes in that open chunk.  Returns the shard's chunk count
+// (ids used = 0 .. count-1); the next shard's ids start at (sum of counts - 1 per shard).
+int64_t chunk_index_rgs(ParquetReader& r, const std::string& col_name, size_t rg_begin, size_t rg_end, uint64_t chunk_size,
+                        uint64_t carry_in, uint32_t id_base, uint32_t* tuple_to_chunk_local, int64_t cap, uint64_t* carry_out);
+
 int64_t page_chunk_index(ParquetReader& r, int col, uint64_t chunk_size, uint32_t* page_chunk,
                          uint32_t* page_off, uint32_t* chunk_first_page, int64_t cap,
                          int64_t* first_global_page, int64_t* n_col_pages);

@@ -261,7 +261,43 @@ int pqr_read_columns_into(pqr_reader* r, const int32_t* cols, int32_t n_cols, in
         return 0;
     }, -1);
 }
+int pqr_read_columns_into_rgs(pqr_reader* r, const int32_t* cols, int32_t n_cols, int64_t rg_begin, int64_t rg_end, const pqr_dst* dsts,
+                              pqr_read_stats* stats) {
+    return guarded([&]() -> int {
+        if (rg_begin < 0 || rg_end < rg_begin) throw std::runtime_error("Invalid row group index");
+        std::vector<int> ci(cols, cols + (n_cols > 0 ? n_cols : 0));
+        std::vector<ColumnDst> d(ci.size());
+        std::vector<ColumnReadStats> st(ci.size());
+        for (size_t i = 0; i < ci.size(); i++) d[i] = ColumnDst{dsts[i].values, dsts[i].values_cap, dsts[i].validity, dsts[i].validity_cap};
+        r->r.read_columns_into_range(ci.data(), static_cast<int>(ci.size()), static_cast<size_t>(rg_begin), static_cast<size_t>(rg_end), d.data(), st.data());
+        if (stats) for (size_t i = 0; i < ci.size(); i++)
+            stats[i] = pqr_read_stats{st[i].num_slots, st[i].width, st[i].has_validity, st[i].bytes_in, st[i].bytes_out, st[i].h2d_bytes, st[i].d2h_bytes};
+        return 0;
+    }, -1);
+}
 void pqr_release_plans(pqr_reader* r) { if (r) r->r.release_plans(); }
+
+int pqr_shard_row_groups(const pqr_reader* r, int col, int n_shards, int32_t* out_begin) {
+    return guarded([&]() -> int {
+        auto v = r->r.shard_row_groups(col, n_shards);
+        for (size_t i = 0; i < v.size(); i++) out_begin[i] = v[i];
+        return 0;
+    }, -1);
+}
+int64_t pqr_regex_prune_rgs(pqr_reader* r, int col, int64_t rg_begin, int64_t rg_end, const char* pattern, int neg, uint8_t* bits,
+                            int64_t cap, float* kernel_ms) {
+    return guarded([&]() -> int64_t {
+        if (rg_begin < 0 || rg_end < rg_begin) throw std::runtime_error("Invalid row group index");
+        return regex_prune_rgs(r->r, col, static_cast<size_t>(rg_begin), static_cast<size_t>(rg_end), pattern, neg != 0, bits, cap, kernel_ms);
+    }, -1);
+}
+int64_t pqr_chunk_index_rgs(pqr_reader* r, const char* name, int64_t rg_begin, int64_t rg_end, uint64_t chunk_size, uint64_t carry_in,
+                            uint32_t id_base, uint32_t* ids, int64_t cap, uint64_t* carry_out) {
+    return guarded([&]() -> int64_t {
+        if (rg_begin < 0 || rg_end < rg_begin) throw std::runtime_error("Invalid row group index");
+        return chunk_index_rgs(r->r, name, static_cast<size_t>(rg_begin), static_cast<size_t>(rg_end), chunk_size, carry_in, id_base, ids, cap, carry_out);
+    }, -1);
+}
 
 void pqr_columnar_free(pqr_columnar* c) {
     if (c && c->owner) delete static_cast<ColumnarOwner*>(c->owner);

@@ -226,12 +226,13 @@ PQG_API int pqg_regex_scan(pqg_ctx* ctx, pqg_plan* plan, const pqg_dfa* dfa, int
 /* Tuple-level map over a decoded BYTE_ARRAY plan (run + finish first): weight of a
  * non-null value = decimal digits of its length + its length; greedy chunks close at
  * >= chunk_size.  `carry_in` = bytes already in the open chunk when this shard starts
- * (0 on the first shard; multi-GPU shards are stitched by the host from `carry_out` /
- * chunk counts).  tuple_to_chunk: HOST array of num_slots uint32 (nulls 0, chunk ids are
- * shard-local starting at 0).  n_chunks = chunk_id_of_last_value + 1. */
+ * (0 on the first shard; multi-GPU shards are chained by the host through `carry_out` and
+ * chunk counts).  tuple_to_chunk: HOST array of num_slots uint32: id_base + shard-local chunk
+ * id for non-null values (local id 0 = the open chunk carried in), 0 for nulls.
+ * n_chunks = local id of the last value + 1; the next shard's id_base = id_base + n_chunks - 1. */
 PQG_API int pqg_chunk_index(pqg_ctx* ctx, pqg_plan* plan, uint64_t chunk_size, uint64_t carry_in,
-                            uint32_t* tuple_to_chunk, uint64_t* n_chunks, uint64_t* carry_out,
-                            float* kernel_ms);
+                            uint32_t id_base, uint32_t* tuple_to_chunk, uint64_t* n_chunks,
+                            uint64_t* carry_out, float* kernel_ms);
 /* Page-level map (index_test): pages packed greedily by payload size in page-table order.
  * HOST outputs: page_chunk[n_pages], page_off[n_pages], chunk_first_page[cap]. */
 PQG_API int pqg_page_chunk_index(pqg_ctx* ctx, const uint32_t* page_sizes, uint32_t n_pages,

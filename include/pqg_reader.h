@@ -169,6 +169,23 @@ PQG_API int64_t pqr_page_chunk_index(pqr_reader* r, int col, uint64_t chunk_size
                                      uint32_t* page_off, uint32_t* chunk_first_page, int64_t cap,
                                      int64_t* first_global_page, int64_t* n_col_pages);
 
+/* ---- multi-GPU sharding (row groups are independent: no device-side collective) ----------
+ * One reader per GPU / process; every shard handles a contiguous run of row groups; the host
+ * concatenates page bitmaps in shard order and chains the chunk index through carry_in /
+ * carry_out (SURVEY.md section 8 e). */
+/* out_begin: n_shards + 1 row-group boundaries, balanced by the byte size of the column's chunks
+ * (col < 0: all columns) */
+PQG_API int pqr_shard_row_groups(const pqr_reader* r, int col, int n_shards, int32_t* out_begin);
+PQG_API int64_t pqr_regex_prune_rgs(pqr_reader* r, int col, int64_t rg_begin, int64_t rg_end, const char* pattern, int neg,
+                                    uint8_t* bits, int64_t cap, float* kernel_ms);
+/* ids: id_base + shard-local chunk id for the shard's non-null rows (local 0 = the chunk the
+ * previous shard left open), 0 for nulls; returns the shard's chunk count n (next shard:
+ * id_base + n - 1, carry_in = carry_out), <0 on error */
+PQG_API int64_t pqr_chunk_index_rgs(pqr_reader* r, const char* name, int64_t rg_begin, int64_t rg_end, uint64_t chunk_size,
+                                    uint64_t carry_in, uint32_t id_base, uint32_t* ids, int64_t cap, uint64_t* carry_out);
+PQG_API int pqr_read_columns_into_rgs(pqr_reader* r, const int32_t* cols, int32_t n_cols, int64_t rg_begin, int64_t rg_end,
+                                      const pqr_dst* dsts, pqr_read_stats* stats);
+
 #ifdef __cplusplus
 }
 #endif

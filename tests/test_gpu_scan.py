@@ -122,13 +122,9 @@ def test_chunk_index_shards_stitch_like_one_run(pq, oracle, files):
                 n = plan.num_slots
                 ids = np.zeros(n + 1, dtype=np.uint32)
                 nch, cout, ms = C.c_uint64(0), C.c_uint64(0), C.c_float(0)
-                rc = L.pqg_chunk_index(ctx.h, plan.h, 4096, carry, ids.ctypes.data, C.byref(nch), C.byref(cout), C.byref(ms))
+                rc = L.pqg_chunk_index(ctx.h, plan.h, 4096, carry, base, ids.ctypes.data, C.byref(nch), C.byref(cout), C.byref(ms))
                 assert rc == 0, ctx.err()
-                valid_ids = ids[:n].astype(np.uint64)
-                nz = r.read_column(cname, rg=rg)["is_null"].astype(bool)
-                valid_ids[~nz] += np.uint64(base)
-                valid_ids[nz] = 0
-                pieces.append(valid_ids)
+                pieces.append(ids[:n].astype(np.uint64))
                 base += nch.value - 1
                 carry = cout.value
                 plan.destroy()
