@@ -26,9 +26,10 @@ PQG_OK, PQG_ERR_CUDA, PQG_ERR_ARG, PQG_ERR_UNSUPPORTED, PQG_ERR_PAGE, PQG_ERR_RE
 
 def build(verbose=False):
     """Compile libpqg.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
-    r = subprocess.run(["make", "-C", PKG_DIR, "-j8"], capture_output=not verbose, text=True)
-    if r.returncode != 0:
-        raise RuntimeError("building libpqg.so failed:\n" + (r.stdout or "") + (r.stderr or ""))
+    for target in ([], ["tools"]):
+        r = subprocess.run(["make", "-C", PKG_DIR, "-j8"] + target, capture_output=not verbose, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("building libpqg.so failed:\n" + (r.stdout or "") + (r.stderr or ""))
     return LIB_PATH
 
 

@@ -135,3 +135,36 @@ def test_chunk_index_shards_stitch_like_one_run(pq, oracle, files):
         ctx.buf_free(buf)
         ctx.close()
         r.close()
+
+
+def test_cli_tools(pq, oracle, files):
+    """bin/parser (--regex-column / --chunk-index) and bin/index_test print the oracle's numbers"""
+    import os
+    import re
+    import subprocess
+    bindir = os.path.join(pq.PKG_DIR, "bin")
+    path = files["golden_mixed"]
+    ho = oracle.open(path)
+    try:
+        col = oracle.find_column(ho, "email")
+        out = subprocess.run([os.path.join(bindir, "parser"), path, "--regex-column", "email", "--regex",
+                              r"^[a-z0-9._]+@[a-z0-9.]+\.com$", "--neg-regex"], capture_output=True, text=True, timeout=120)
+        assert out.returncode == 0, out.stderr
+        bits = oracle.regex_prune(ho, col, r"^[a-z0-9._]+@[a-z0-9.]+\.com$", True)
+        assert int(re.search(r"Pages scanned: (\d+)", out.stdout).group(1)) == len(bits)
+        assert int(re.search(r"Pages prunable: (\d+)", out.stdout).group(1)) == int((bits == 0).sum())
+        out = subprocess.run([os.path.join(bindir, "parser"), path, "--chunk-index", "email"], capture_output=True, text=True, timeout=120)
+        assert out.returncode == 0, out.stderr
+        _, n = oracle.chunk_index(ho, "email", 4096)
+        assert f"Total tuples: {oracle.num_rows(ho)}" in out.stdout and f"Total chunks: {n}" in out.stdout
+        out = subprocess.run([os.path.join(bindir, "index_test"), path, "email"], capture_output=True, text=True, timeout=120)
+        assert out.returncode == 0, out.stderr + out.stdout
+        _, _, cf = oracle.page_chunk_index(ho, col, 4096)
+        assert f"Total chunks: {len(cf)}" in out.stdout and "Lookup self-check: ok" in out.stdout
+        out = subprocess.run([os.path.join(bindir, "parser"), path, "--regex-column", "email", "--regex", r"(a)\1"],
+                             capture_output=True, text=True, timeout=120)
+        assert out.returncode != 0 and "regex" in out.stderr
+        out = subprocess.run([os.path.join(bindir, "parser"), path], capture_output=True, text=True, timeout=120)
+        assert out.returncode == 0 and "email" in out.stdout and "data pages" in out.stdout
+    finally:
+        oracle.close(ho)
