@@ -354,10 +354,8 @@ int pqg_plan_create(pqg_ctx* ctx, const pqg_buf* image, const pqg_chunk_desc* ch
     PA(p->d_pages, sizeof(pqg_page_desc) * std::max<uint32_t>(n_pages, 1));
     PA(p->d_err, sizeof(DevErr));
     if (p->any_dict) PA(p->d_dict, arena + 64);
-    if (!p->is_str) {
-        PA(p->d_tiles, sizeof(TileDesc) * std::max<size_t>(tiles.size(), 1));
-        PA(p->d_slow_pages, sizeof(uint32_t) * (static_cast<size_t>(n_pages) + 1));
-    }
+    PA(p->d_slow_pages, sizeof(uint32_t) * (static_cast<size_t>(n_pages) + 1));
+    if (!p->is_str) PA(p->d_tiles, sizeof(TileDesc) * std::max<size_t>(tiles.size(), 1));
     if (p->any_def) PA(p->d_validity, ((slots + 31) / 32 + 1) * 4);
     if (p->is_str) {
         PA(p->d_offsets, (slots + n_chunks + 1) * 4);

@@ -282,8 +282,15 @@ __device__ __forceinline__ void decode_str_page(const DecodeParams& P, uint32_t 
                 __syncwarp();
             }
         } else {
+            // parallel length-prefix discovery first (text pages); sequential walk otherwise
+            bool found = false;
+            if (single && !wide) {
+                uint32_t endp = 0;
+                found = find_headers(vals, vavail, nn, reinterpret_cast<uint16_t*>(ws.idx), static_cast<uint32_t>(kIdxWords) * 2u, &endp);
+                if (found) wpos = endp;
+            }
             uint32_t epos = 0, eneed = 0;
-            if (!walk_strings(vals, vavail, &wpos, nn, ws, wide, COPY, &epos, &eneed)) {
+            if (!found && !walk_strings(vals, vavail, &wpos, nn, ws, wide, COPY, &epos, &eneed)) {
                 if (l == 0) { report_error(P.err, q, PQG_PAGE_TRUNCATED, c.vals_pos + epos, eneed, c.size); if (!COPY) P.page_chars[q] = 0; }
                 return;
             }

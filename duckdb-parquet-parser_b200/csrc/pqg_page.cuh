@@ -351,6 +351,75 @@ __device__ __forceinline__ bool walk_strings(const uint8_t* vals, uint32_t vavai
     return ok != 0;
 }
 
+// ---- BYTE_ARRAY PLAIN: parallel length-prefix discovery --------------------------------------
+// A length prefix of a string shorter than 64 KiB is <lo, hi, 0, 0>: candidates are the byte
+// positions whose bytes +2 and +3 are zero and whose string stays inside the value section.
+// Every lane scans its 1/32 of the section (zero-byte bit tricks, 4 positions per step), the
+// candidates are compacted in order (warp prefix sum of the per-lane counts) into `out` (u16
+// positions), and the chain is verified in parallel: cand[0] == 0, cand[i] + 4 + len ==
+// cand[i+1], the nn-th string ends inside the section.  On text pages the candidates are exactly
+// the prefixes; anything else (strings of 0-3 bytes producing false candidates, NUL-heavy
+// binary data, strings >= 64 KiB) fails the check and the caller falls back to the sequential
+// walk.  Returns the end position of the nn-th string in *end_pos.
+__device__ __forceinline__ uint64_t zero_byte_mask64(uint64_t v) { // bit 8i+7 set iff byte i == 0 (exact)
+    const uint64_t m = 0x7f7f7f7f7f7f7f7full;
+    return ~(((v & m) + m) | v | m);
+}
+__device__ __forceinline__ bool find_headers(const uint8_t* vals, uint32_t vavail, uint32_t nn, uint16_t* out, uint32_t cap,
+                                             uint32_t* end_pos) {
+    const uint32_t l = lane_id();
+    if (nn == 0) { *end_pos = 0; return true; }
+    if (vavail < 4u || vavail > 65535u || nn > cap) return false;
+    const uint32_t last = vavail - 4u;                 // last position a prefix can start at
+    uint32_t R = (last / 32u + 4u) & ~3u;              // positions per lane, multiple of 4
+    const uint32_t p0 = l * R, p1 = min(p0 + R, last + 1u);
+    uint32_t cnt = 0;
+    for (uint32_t p = p0; p < p1; p += 4) {
+        uint64_t v = static_cast<uint64_t>(ld32u(vals + p)) | (static_cast<uint64_t>(ld32u(vals + p + 4)) << 32);
+        uint64_t z = zero_byte_mask64(v);
+        uint32_t zz = static_cast<uint32_t>((z & (z >> 8)) >> 16); // bit 8k+7: bytes k+2 and k+3 are zero
+        zz &= 0x80808080u;
+        while (zz) {
+            uint32_t k = (__ffs(zz) - 1) >> 3;
+            zz &= zz - 1;
+            uint32_t pos = p + k;
+            uint32_t len = static_cast<uint32_t>(v >> (8 * k)) & 0xffffu;
+            if (pos < p1 && pos + 4u + len <= vavail) cnt++;
+        }
+    }
+    const uint32_t incl = warp_incl_scan(cnt);
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total < nn || total > cap) return false;
+    uint32_t w = incl - cnt;
+    for (uint32_t p = p0; p < p1; p += 4) {
+        uint64_t v = static_cast<uint64_t>(ld32u(vals + p)) | (static_cast<uint64_t>(ld32u(vals + p + 4)) << 32);
+        uint64_t z = zero_byte_mask64(v);
+        uint32_t zz = static_cast<uint32_t>((z & (z >> 8)) >> 16) & 0x80808080u;
+        while (zz) {
+            uint32_t k = (__ffs(zz) - 1) >> 3;
+            zz &= zz - 1;
+            uint32_t pos = p + k;
+            uint32_t len = static_cast<uint32_t>(v >> (8 * k)) & 0xffffu;
+            if (pos < p1 && pos + 4u + len <= vavail) out[w++] = static_cast<uint16_t>(pos);
+        }
+    }
+    __syncwarp();
+    bool ok = true;
+    uint32_t endp = 0;
+    for (uint32_t i = l; i < nn; i += 32) {
+        uint32_t c = out[i];
+        uint32_t nx = c + 4u + (ld32u(vals + c) & 0xffffu);
+        if (i == 0 && c != 0) ok = false;
+        if (i + 1 < nn) { if (out[i + 1] != nx) ok = false; }
+        else endp = nx;
+    }
+    ok = __all_sync(0xffffffffu, ok);
+    endp = __reduce_max_sync(0xffffffffu, endp);
+    *end_pos = endp;
+    __syncwarp();
+    return ok;
+}
+
 // ---- page prolog -----------------------------------------------------------------------------
 struct PageCtx {
     const uint8_t* pg;   // payload bytes (shared slot or global)
