@@ -309,15 +309,17 @@ int pqg_plan_create(pqg_ctx* ctx, const pqg_buf* image, const pqg_chunk_desc* ch
     // general kernel
     std::vector<TileDesc> tiles;
     std::vector<uint32_t> slow;
-    if (!p->is_str) {
+    {
         uint32_t max_dict_n = 0;
         for (uint32_t c = 0; c < n_chunks; c++) {
             const pqg_chunk_desc& s = chunks[c];
             p->chunk_tile_begin.push_back(static_cast<uint32_t>(tiles.size()));
             p->chunk_slow_begin.push_back(static_cast<uint32_t>(slow.size()));
             if (s.has_dict) max_dict_n = std::max(max_dict_n, s.dict_num_values);
-            const bool tileable = chunk_is_tileable(s.phys_type, s.max_def, s.max_rep);
-            if (tileable && s.has_dict) {
+            // strings: every flat chunk is tiled (the regex scan runs on tiles; the page kernels
+            // classify pages themselves); fixed width: REQUIRED 4/8-byte chunks only
+            const bool tileable = p->is_str ? s.max_rep <= 0 : chunk_is_tileable(s.phys_type, s.max_def, s.max_rep);
+            if (tileable && s.has_dict && !p->is_str) {
                 uint64_t db = (static_cast<uint64_t>(s.dict_num_values) * p->width + 15) & ~uint64_t(15);
                 if (db <= static_cast<uint64_t>(kMaxSmemDictBytes)) p->dict_smem = std::max<uint32_t>(p->dict_smem, static_cast<uint32_t>(db));
             }
@@ -355,7 +357,7 @@ int pqg_plan_create(pqg_ctx* ctx, const pqg_buf* image, const pqg_chunk_desc* ch
     PA(p->d_err, sizeof(DevErr));
     if (p->any_dict) PA(p->d_dict, arena + 64);
     PA(p->d_slow_pages, sizeof(uint32_t) * (static_cast<size_t>(n_pages) + 1));
-    if (!p->is_str) PA(p->d_tiles, sizeof(TileDesc) * std::max<size_t>(tiles.size(), 1));
+    PA(p->d_tiles, sizeof(TileDesc) * std::max<size_t>(tiles.size(), 1));
     if (p->any_def) PA(p->d_validity, ((slots + 31) / 32 + 1) * 4);
     if (p->is_str) {
         PA(p->d_offsets, (slots + n_chunks + 1) * 4);

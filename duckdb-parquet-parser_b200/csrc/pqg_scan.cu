@@ -17,12 +17,13 @@
 //                    tile) and a last pass materialises cuts and chunk ids.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
 
 #include "pq_regex.hpp"
-#include "pqg_page.cuh"
+#include "pqg_tilepipe.cuh"
 
 struct pqg_ctx;
 struct pqg_plan;
@@ -152,7 +153,9 @@ __device__ __forceinline__ void stage_tables(const RegexParams& R, uint8_t* stab
     if (R.D.in_smem) {
         const uint32_t total = R.D.table_bytes + 256u + R.D.n_states;
         const uint8_t* src = reinterpret_cast<const uint8_t*>(R.D.trans); // the three tables are contiguous on the device
-        for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) stab[i] = src[i];
+        // 16-byte vectors (both sides are 16-byte aligned; the device blob is padded)
+        for (uint32_t i = threadIdx.x; i < (total + 15u) / 16u; i += blockDim.x)
+            reinterpret_cast<uint4*>(stab)[i] = reinterpret_cast<const uint4*>(src)[i];
         __syncthreads();
         trans = reinterpret_cast<const uint16_t*>(stab);
         cls = stab + R.D.table_bytes;
@@ -163,18 +166,19 @@ __device__ __forceinline__ void stage_tables(const RegexParams& R, uint8_t* stab
 // The general scan: every page shape, pages taken from the slow list (appended by the fast
 // kernel) through a work-stealing cursor.
 __global__ void __launch_bounds__(kThreadsPerCta) k_regex_pages(RegexParams R) {
-    extern __shared__ __align__(16) uint8_t smem[];
+    extern __shared__ __align__(128) uint8_t smem[];
     WarpScratch& ws = reinterpret_cast<WarpScratch*>(smem)[warp_id()];
     const uint16_t* trans; const uint8_t* cls; const uint8_t* accept;
     stage_tables(R, smem + sizeof(WarpScratch) * kWarpsPerCta, trans, cls, accept);
     const DecodeParams& P = R.P;
-    const uint32_t total = P.err->slow_count;
+    const uint32_t n_host = P.slow_hi - P.slow_lo;
+    const uint32_t total = n_host + P.err->slow_count;
     for (;;) {
         uint32_t i = 0;
         if (lane_id() == 0) i = atomicAdd(&P.err->slow_cursor, 1u);
         i = __shfl_sync(0xffffffffu, i, 0);
         if (i >= total) break;
-        const uint32_t q = P.slow_pages[P.n_slow_host + i];
+        const uint32_t q = i < n_host ? P.slow_pages[P.slow_lo + i] : P.slow_pages[P.n_slow_host + (i - n_host)];
         const DevChunk& ck = P.chunks[P.pages[q].chunk_idx];
         bool hit = regex_page(R, trans, cls, accept, q, ck, ws);
         if (hit && lane_id() == 0) atomicOr(&R.page_bits[q >> 5], 1u << (q & 31u));
@@ -187,103 +191,94 @@ __global__ void __launch_bounds__(kThreadsPerCta) k_regex_pages(RegexParams R) {
 // length-prefix discovery, then one lane per string through the DFA) or single-group
 // bit-packed dictionary indices (predicate looked up per index).  Everything else goes to
 // the slow list.
-struct __align__(16) RxScratch {
-    uint8_t slot[kSlotAlloc];
-    uint16_t cand[1024];
-};
-
 __device__ __forceinline__ void rx_to_slow(const DecodeParams& P, uint32_t q) {
     uint32_t k = atomicAdd(&P.err->slow_count, 1u);
     P.slow_pages[P.n_slow_host + k] = q;
 }
 
-__global__ void __launch_bounds__(kThreadsPerCta, 5) k_regex_fast(RegexParams R) {
-    extern __shared__ __align__(16) uint8_t smem[];
-    RxScratch& ws = reinterpret_cast<RxScratch*>(smem)[warp_id()];
+constexpr uint32_t kRxCand = 1024; // length-prefix candidates per page (u16 positions)
+
+__global__ void __launch_bounds__(kThreadsPerCta, 4) k_regex_tiles(RegexParams R) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint16_t* cand = reinterpret_cast<uint16_t*>(smem + kTilePipeBytes) + warp_id() * kRxCand;
     const uint16_t* trans; const uint8_t* cls; const uint8_t* accept;
-    stage_tables(R, smem + sizeof(RxScratch) * kWarpsPerCta, trans, cls, accept);
+    stage_tables(R, smem + kTilePipeBytes + kWarpsPerCta * kRxCand * 2, trans, cls, accept);
     const DecodeParams& P = R.P;
     const uint32_t l = lane_id();
-    uint32_t p = P.page_begin + blockIdx.x * P.pages_per_cta;
-    const uint32_t p1 = min(P.page_end, p + P.pages_per_cta);
-    for (uint32_t q = p + warp_id(); q < p1; q += kWarpsPerCta) {
-        const pqg_page_desc pd = P.pages[q];
-        const DevChunk& ck = P.chunks[pd.chunk_idx];
-        const uint32_t n = pd.num_values, size = pd.payload_size;
-        if (n == 0) continue;
-        __syncwarp();
-        if (size > static_cast<uint32_t>(kSlotBytes) || ck.max_rep > 0 || ck.max_def > 1) { if (l == 0) rx_to_slow(P, q); continue; }
-        // stage the payload (16-byte vectors, source rounded down to its alignment)
-        const uint8_t* src = P.image + pd.payload_off;
-        const uint32_t shift = static_cast<uint32_t>(pd.payload_off & 15u);
-        {
-            const uint32_t nvec = (shift + size + 15u) >> 4;
-            uint4* dst = reinterpret_cast<uint4*>(ws.slot);
-            for (uint32_t j = l; j < nvec; j += 32) dst[j] = ldg_nc16(src - shift + 16u * j);
-        }
-        __syncwarp();
-        const uint8_t* pg = ws.slot + shift;
-        uint32_t pos = 0, nn = n;
-        bool slow = false;
-        if (ck.max_def == 1) {
-            // definition levels: <varint < 128><level byte> RLE runs only, else the general scan
-            uint32_t def_len = size >= 4 ? ld32u(pg) : 0xffffffffu;
-            if (size < 4 || def_len > size - 4 || (def_len & 1u)) slow = true;
-            else {
-                const uint8_t* s = pg + 4;
-                const uint32_t nr = def_len >> 1;
-                bool ok = true;
-                uint32_t carry = 0, present = 0;
-                for (uint32_t base = 0; base < nr && carry < n; base += 32) {
-                    uint32_t r = base + l, cnt = 0, val = 0;
-                    if (r < nr) { uint32_t b = s[2 * r]; ok = ok && ((b & 0x81u) == 0u) && b != 0u; cnt = b >> 1; val = s[2 * r + 1]; }
-                    uint32_t incl = warp_incl_scan(cnt);
-                    uint32_t start = carry + incl - cnt;
-                    if (cnt && start < n && val >= 1u) present += min(cnt, n - start);
-                    carry += __shfl_sync(0xffffffffu, incl, 31);
-                }
-                if (!__all_sync(0xffffffffu, ok)) slow = true;
-                nn = __reduce_add_sync(0xffffffffu, present);
-                pos = 4 + def_len;
-            }
-        }
-        bool hit = false;
-        if (!slow) {
-            if ((pd.flags & PQG_PAGE_FLAG_DICT) && ck.has_dict) {
-                const uint32_t bw = pos < size ? pg[pos] : 99u;
-                if (bw > 32u || !check_regular(pg + pos + 1, size - pos - 1, bw, nn)) slow = true;
+    int max_def = 0;
+    bool has_dict = false;
+    uint32_t dict_n = 0;
+    const uint8_t* dmatch = nullptr;
+    tile_pipeline(P, smem,
+        [&](uint32_t chunk, uint64_t*, uint32_t&) {
+            const DevChunk& ck = P.chunks[chunk];
+            max_def = ck.max_def; has_dict = ck.has_dict; dict_n = ck.dict_ok_n;
+            dmatch = R.dict_match + ck.dict_arena_off / 8;
+        },
+        [&](uint32_t q, const pqg_page_desc& pd, const uint8_t* pg) {
+            const uint32_t n = pd.num_values, size = pd.payload_size;
+            if (n == 0) return;
+            if (max_def > 1) { if (l == 0) rx_to_slow(P, q); return; }
+            uint32_t pos = 0, nn = n;
+            bool slow = false;
+            if (max_def == 1) {
+                // definition levels: <varint < 128><level byte> RLE runs only, else the general scan
+                uint32_t def_len = size >= 4 ? ld32u(pg) : 0xffffffffu;
+                if (size < 4 || def_len > size - 4 || (def_len & 1u)) slow = true;
                 else {
-                    const uint8_t* dmatch = R.dict_match + ck.dict_arena_off / 8;
-                    const uint32_t dict_n = ck.dict_ok_n;
-                    for (uint32_t k0 = 0; k0 < nn && !hit; k0 += 32) {
-                        uint32_t k = k0 + l;
-                        bool h = false;
-                        if (k < nn) { uint32_t ix = regular_index(pg + pos + 1, bw, k); h = ix < dict_n && dmatch[ix]; }
-                        hit = __any_sync(0xffffffffu, h);
+                    const uint8_t* s = pg + 4;
+                    const uint32_t nr = def_len >> 1;
+                    bool ok = true;
+                    uint32_t carry = 0, present = 0;
+                    for (uint32_t base = 0; base < nr && carry < n; base += 32) {
+                        uint32_t r = base + l, cnt = 0, val = 0;
+                        if (r < nr) { uint32_t b = s[2 * r]; ok = ok && ((b & 0x81u) == 0u) && b != 0u; cnt = b >> 1; val = s[2 * r + 1]; }
+                        uint32_t incl = warp_incl_scan(cnt);
+                        uint32_t start = carry + incl - cnt;
+                        if (cnt && start < n && val >= 1u) present += min(cnt, n - start);
+                        carry += __shfl_sync(0xffffffffu, incl, 31);
                     }
+                    if (!__all_sync(0xffffffffu, ok)) slow = true;
+                    nn = __reduce_add_sync(0xffffffffu, present);
+                    pos = 4 + def_len;
                 }
-            } else {
-                const uint8_t* vals = pg + pos;
-                uint32_t endp = 0;
-                if (!find_headers(vals, size - pos, nn, ws.cand, 1024u, &endp)) slow = true;
-                else {
-                    for (uint32_t k0 = 0; k0 < nn && !hit; k0 += 32) {
-                        uint32_t k = k0 + l;
-                        bool h = false;
-                        if (k < nn) {
-                            uint32_t c = ws.cand[k];
-                            uint32_t len = ld32u(vals + c) & 0xffffu;
-                            bool m = dfa_run(R.D, trans, cls, accept, vals + c + 4, len);
-                            h = R.neg ? !m : m;
+            }
+            bool hit = false;
+            if (!slow) {
+                if ((pd.flags & PQG_PAGE_FLAG_DICT) && has_dict) {
+                    const uint32_t bw = pos < size ? pg[pos] : 99u;
+                    if (bw > 32u || !check_regular(pg + pos + 1, size - pos - 1, bw, nn)) slow = true;
+                    else {
+                        for (uint32_t k0 = 0; k0 < nn && !hit; k0 += 32) {
+                            uint32_t k = k0 + l;
+                            bool h = false;
+                            if (k < nn) { uint32_t ix = regular_index(pg + pos + 1, bw, k); h = ix < dict_n && dmatch[ix]; }
+                            hit = __any_sync(0xffffffffu, h);
                         }
-                        hit = __any_sync(0xffffffffu, h);
+                    }
+                } else {
+                    const uint8_t* vals = pg + pos;
+                    uint32_t endp = 0;
+                    if (!find_headers(vals, size - pos, nn, cand, kRxCand, &endp)) slow = true;
+                    else {
+                        for (uint32_t k0 = 0; k0 < nn && !hit; k0 += 32) {
+                            uint32_t k = k0 + l;
+                            bool h = false;
+                            if (k < nn) {
+                                uint32_t c = cand[k];
+                                uint32_t len = ld32u(vals + c) & 0xffffu;
+                                bool m = dfa_run(R.D, trans, cls, accept, vals + c + 4, len);
+                                h = R.neg ? !m : m;
+                            }
+                            hit = __any_sync(0xffffffffu, h);
+                        }
                     }
                 }
             }
-        }
-        if (slow) { if (l == 0) rx_to_slow(P, q); continue; }
-        if (hit && l == 0) atomicOr(&R.page_bits[q >> 5], 1u << (q & 31u));
-    }
+            __syncwarp();
+            if (slow) { if (l == 0) rx_to_slow(P, q); return; }
+            if (hit && l == 0) atomicOr(&R.page_bits[q >> 5], 1u << (q & 31u));
+        });
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -679,18 +674,20 @@ int pqg_regex_scan(pqg_ctx* ctx, pqg_plan* plan, const pqg_dfa* dfa, int neg, ui
         launches += 2;
     }
     const size_t tab_pad = R.D.in_smem ? ((tab_smem + 15) & ~size_t(15)) : 0;
-    const size_t smem_fast = sizeof(RxScratch) * kWarpsPerCta + tab_pad;
+    const size_t smem_fast = static_cast<size_t>(kTilePipeBytes) + kWarpsPerCta * kRxCand * 2 + tab_pad;
     const size_t smem_slow = decode_smem_bytes(false) + tab_pad;
-    CUF(ctx, cudaFuncSetAttribute(k_regex_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_fast)));
+    CUF(ctx, cudaFuncSetAttribute(k_regex_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_fast)));
     CUF(ctx, cudaFuncSetAttribute(k_regex_pages, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_slow)));
-    uint32_t target = static_cast<uint32_t>(ctx_sm_count(ctx)) * 20u;
-    uint32_t per = (n_pages + target - 1) / target;
-    if (per < static_cast<uint32_t>(kWarpsPerCta)) per = kWarpsPerCta;
-    R.P.pages_per_cta = per;
-    R.P.n_slow_host = 0; // the slow list of a scan holds only what the fast kernel hands over
-    k_regex_fast<<<(n_pages + per - 1) / per, kThreadsPerCta, smem_fast, s>>>(R);
+    if (R.P.tile_hi > R.P.tile_lo) {
+        int resident = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k_regex_tiles, kThreadsPerCta, smem_fast);
+        const uint32_t grid = tile_grid(R.P.tile_hi - R.P.tile_lo, ctx_sm_count(ctx), resident, &R.P.tiles_per_cta);
+        k_regex_tiles<<<grid, kThreadsPerCta, smem_fast, s>>>(R);
+        launches++;
+    }
+    // host-listed (oversized) pages + whatever the tile kernel handed over
     k_regex_pages<<<static_cast<unsigned>(ctx_sm_count(ctx)) * 2u, kThreadsPerCta, smem_slow, s>>>(R);
-    launches += 2;
+    launches++;
     CUF(ctx, cudaEventRecord(e1, s));
     CUF(ctx, cudaGetLastError());
     DevErr herr;
@@ -702,6 +699,7 @@ int pqg_regex_scan(pqg_ctx* ctx, pqg_plan* plan, const pqg_dfa* dfa, int neg, ui
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     if (kernel_ms) *kernel_ms = ms;
     ctx_add_launches(ctx, launches);
+    if (std::getenv("PQG_DEBUG")) std::fprintf(stderr, "[pqg] regex scan: %u pages, %u through the general kernel, %.3f ms\n", n_pages, herr.slow_count, ms);
     if (herr.count) {
         char msg[160];
         std::snprintf(msg, sizeof(msg), "regex scan: page %u failed to decode (code %u)", static_cast<uint32_t>(herr.key >> 32),

@@ -1,0 +1,110 @@
+// pqg_tilepipe.cuh -- the TMA-staged page-tile pipeline shared by the tile kernels.
+//
+// The plan's host side cuts every chunk into tiles (TileDesc): <= kTilePages consecutive pages
+// whose bytes (page headers in between included) fit kTileBytes.  A CTA owns a contiguous run
+// of tiles.  One elected thread stages tile bytes + the tile's page descriptors into a
+// kTileStages-deep shared-memory ring with cp.async.bulk (1-D TMA, SASS UBLKCP) completing on
+// an mbarrier per stage; the CTA's warps take one page each out of shared memory; a
+// __syncthreads frees the stage and the elected thread refills it kTileStages tiles ahead.
+// No register staging, no per-warp global latency chain (descriptor -> chunk -> payload).
+#pragma once
+#include "pqg_page.cuh"
+
+namespace pqg {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// 1-D bulk copy global -> shared (TMA); dst/src 16-byte aligned, bytes a multiple of 16
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra LAB_DONE;\n"
+        "bra LAB_WAIT;\n"
+        "LAB_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+constexpr int kStageBytes = kTileBytes + 16 + kTilePages * static_cast<int>(sizeof(pqg_page_desc));
+constexpr int kBarBytes = 64 + kTileStages * 32; // kTileStages + 1 mbarriers, then per-stage tile meta
+constexpr int kTilePipeBytes = kBarBytes + kTileStages * kStageBytes; // shared memory of the pipeline itself
+
+struct TileMeta { uint64_t byte_lo; uint32_t first_page; uint32_t n_pages; uint32_t chunk_idx; uint32_t pad; };
+
+// Runs the pipeline over the CTA's tiles.  `smem` = kTilePipeBytes of 128-byte aligned shared
+// memory.  on_chunk(chunk_idx, extra_bar, phase&) is called by all threads (CTA-uniform) when
+// the chunk changes -- it may __syncthreads and stage per-chunk data with a bulk copy on
+// extra_bar.  on_page(q, pd, payload) is called by one warp per page.
+template <class OnChunk, class OnPage>
+__device__ __forceinline__ void tile_pipeline(const DecodeParams& P, uint8_t* smem, OnChunk&& on_chunk, OnPage&& on_page) {
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);          // [kTileStages] tiles, [kTileStages] per-chunk staging
+    TileMeta* meta = reinterpret_cast<TileMeta*>(smem + 64);     // [kTileStages]
+    uint8_t* ring = smem + kBarBytes;
+    const uint32_t t0 = P.tile_lo + blockIdx.x * P.tiles_per_cta;
+    const uint32_t t1 = min(P.tile_hi, t0 + P.tiles_per_cta);
+    const uint32_t tid = threadIdx.x;
+    if (tid == 0) {
+        for (int i = 0; i <= kTileStages; i++) mbar_init(&full[i], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (t0 >= t1) return;
+    auto issue = [&](uint32_t t, const TileDesc& td) { // thread 0
+        const uint32_t st = (t - t0) % kTileStages;
+        uint8_t* dst = ring + st * kStageBytes;
+        meta[st] = TileMeta{td.byte_lo, td.first_page, td.n_pages, td.chunk_idx, 0};
+        const uint32_t pbytes = td.n_pages * static_cast<uint32_t>(sizeof(pqg_page_desc));
+        mbar_expect_tx(&full[st], td.byte_len + pbytes);
+        bulk_g2s(dst, P.image + td.byte_lo, td.byte_len, &full[st]);
+        bulk_g2s(dst + kTileBytes + 16, P.pages + td.first_page, pbytes, &full[st]);
+    };
+    if (tid == 0) {
+        for (uint32_t t = t0; t < min(t1, t0 + kTileStages); t++) issue(t, P.tiles[t]);
+    }
+    uint32_t cur_chunk = 0xffffffffu, extra_phase = 0;
+    for (uint32_t t = t0; t < t1; t++) {
+        TileDesc nxt{};
+        const bool refill = tid == 0 && t + kTileStages < t1;
+        if (refill) nxt = P.tiles[t + kTileStages]; // in flight while the pages are decoded
+        const uint32_t st = (t - t0) % kTileStages;
+        mbar_wait(&full[st], ((t - t0) / kTileStages) & 1u);
+        const uint8_t* tile = ring + st * kStageBytes;
+        const TileMeta tm = meta[st];
+        if (tm.chunk_idx != cur_chunk) { // uniform across the CTA
+            cur_chunk = tm.chunk_idx;
+            on_chunk(cur_chunk, &full[kTileStages], extra_phase);
+        }
+        const pqg_page_desc* pds = reinterpret_cast<const pqg_page_desc*>(tile + kTileBytes + 16);
+        for (uint32_t j = warp_id(); j < tm.n_pages; j += kWarpsPerCta) {
+            const pqg_page_desc pd = pds[j];
+            on_page(tm.first_page + j, pd, tile + (pd.payload_off - tm.byte_lo));
+        }
+        __syncthreads(); // stage st is free again
+        if (refill) issue(t + kTileStages, nxt);
+    }
+}
+
+// grid sizing shared by the tile kernels: contiguous tile spans, two waves of resident CTAs
+inline uint32_t tile_grid(uint32_t n_tiles, int sm_count, int resident, uint32_t* tiles_per_cta) {
+    if (resident < 1) resident = 1;
+    uint32_t target = static_cast<uint32_t>(sm_count) * static_cast<uint32_t>(resident) * 2u;
+    uint32_t per = (n_tiles + target - 1) / target;
+    if (per < 4) per = 4;
+    *tiles_per_cta = per;
+    return (n_tiles + per - 1) / per;
+}
+
+} // namespace pqg

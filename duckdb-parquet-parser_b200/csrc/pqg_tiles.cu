@@ -23,36 +23,10 @@
 //     dictionary of a 2^20-key chunk; outputs are written with streaming stores so they do
 //     not evict it).
 //   * outputs: 8 or 4 bytes per lane, consecutive lanes -> consecutive slots (coalesced).
-#include "pqg_page.cuh"
+#include "pqg_tilepipe.cuh"
 
 namespace pqg {
 namespace {
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-// 1-D bulk copy global -> shared (TMA); dst/src 16-byte aligned, bytes a multiple of 16
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra LAB_DONE;\n"
-        "bra LAB_WAIT;\n"
-        "LAB_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
 
 template <int W> struct FElem;
 template <> struct FElem<4> { using T = uint32_t; };
@@ -67,11 +41,6 @@ template <> __device__ __forceinline__ void st_stream<uint32_t>(uint32_t* p, uin
 template <> __device__ __forceinline__ void st_stream<uint64_t>(uint64_t* p, uint64_t v) {
     __stcs(reinterpret_cast<unsigned long long*>(p), static_cast<unsigned long long>(v));
 }
-
-constexpr int kStageBytes = kTileBytes + 16 + kTilePages * static_cast<int>(sizeof(pqg_page_desc));
-constexpr int kBarBytes = 64 + kTileStages * 32; // kTileStages + 1 mbarriers, then per-stage tile meta
-
-struct TileMeta { uint64_t byte_lo; uint32_t first_page; uint32_t n_pages; uint32_t chunk_idx; uint32_t pad; };
 
 __device__ __forceinline__ void to_slow(const DecodeParams& P, uint32_t q) {
     // one lane
@@ -140,45 +109,13 @@ __device__ __forceinline__ void fast_page(const DecodeParams& P, uint32_t q, con
 template <int W>
 __global__ void __launch_bounds__(kThreadsPerCta, 3) k_fixed_tiles(const DecodeParams P) {
     extern __shared__ __align__(128) uint8_t smem[];
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem);                    // [kTileStages] tiles, [kTileStages] dictionary
-    TileMeta* meta = reinterpret_cast<TileMeta*>(smem + 64);               // [kTileStages]
-    uint8_t* ring = smem + kBarBytes;
-    uint8_t* sdict = ring + kTileStages * kStageBytes;
-    const uint32_t t0 = P.tile_lo + blockIdx.x * P.tiles_per_cta;
-    const uint32_t t1 = min(P.tile_hi, t0 + P.tiles_per_cta);
-    if (t0 >= t1) return;
-    const uint32_t tid = threadIdx.x;
-    if (tid == 0) {
-        for (int i = 0; i <= kTileStages; i++) mbar_init(&full[i], 1);
-        fence_mbar_init();
-    }
-    __syncthreads();
-    auto issue = [&](uint32_t t, const TileDesc& td) { // thread 0
-        const uint32_t st = (t - t0) % kTileStages;
-        uint8_t* dst = ring + st * kStageBytes;
-        meta[st] = TileMeta{td.byte_lo, td.first_page, td.n_pages, td.chunk_idx, 0};
-        const uint32_t pbytes = td.n_pages * static_cast<uint32_t>(sizeof(pqg_page_desc));
-        mbar_expect_tx(&full[st], td.byte_len + pbytes);
-        bulk_g2s(dst, P.image + td.byte_lo, td.byte_len, &full[st]);
-        bulk_g2s(dst + kTileBytes + 16, P.pages + td.first_page, pbytes, &full[st]);
-    };
-    if (tid == 0) {
-        for (uint32_t t = t0; t < min(t1, t0 + kTileStages); t++) issue(t, P.tiles[t]);
-    }
-    uint32_t cur_chunk = 0xffffffffu, dict_n = 0, dict_phase = 0;
+    uint8_t* sdict = smem + kTilePipeBytes;
+    uint32_t dict_n = 0;
     const uint8_t* dictp = nullptr;
     bool has_dict = false, dict_in_smem = false;
-    for (uint32_t t = t0; t < t1; t++) {
-        TileDesc nxt{};
-        const bool refill = tid == 0 && t + kTileStages < t1;
-        if (refill) nxt = P.tiles[t + kTileStages]; // in flight while the pages are decoded
-        const uint32_t st = (t - t0) % kTileStages;
-        mbar_wait(&full[st], ((t - t0) / kTileStages) & 1u);
-        const uint8_t* tile = ring + st * kStageBytes;
-        const TileMeta tm = meta[st];
-        if (tm.chunk_idx != cur_chunk) { // uniform across the CTA
-            cur_chunk = tm.chunk_idx;
-            const DevChunk& ck = P.chunks[cur_chunk];
+    tile_pipeline(P, smem,
+        [&](uint32_t chunk, uint64_t* bar, uint32_t& phase) {
+            const DevChunk& ck = P.chunks[chunk];
             has_dict = ck.has_dict;
             dict_n = ck.dict_ok_n;
             dictp = P.dict_arena + ck.dict_arena_off;
@@ -186,21 +123,16 @@ __global__ void __launch_bounds__(kThreadsPerCta, 3) k_fixed_tiles(const DecodeP
             const uint32_t dbytes = (dict_n * W + 15u) & ~15u;
             if (has_dict && dbytes && dbytes <= P.dict_smem) {
                 __syncthreads(); // nobody reads the previous dictionary any more
-                if (tid == 0) { mbar_expect_tx(&full[kTileStages], dbytes); bulk_g2s(sdict, dictp, dbytes, &full[kTileStages]); }
-                mbar_wait(&full[kTileStages], dict_phase);
-                dict_phase ^= 1;
+                if (threadIdx.x == 0) { mbar_expect_tx(bar, dbytes); bulk_g2s(sdict, dictp, dbytes, bar); }
+                mbar_wait(bar, phase);
+                phase ^= 1;
                 dictp = sdict;
                 dict_in_smem = true;
             }
-        }
-        const pqg_page_desc* pds = reinterpret_cast<const pqg_page_desc*>(tile + kTileBytes + 16);
-        for (uint32_t j = warp_id(); j < tm.n_pages; j += kWarpsPerCta) {
-            const pqg_page_desc pd = pds[j];
-            fast_page<W>(P, tm.first_page + j, pd, tile + (pd.payload_off - tm.byte_lo), has_dict, dictp, dict_n, dict_in_smem);
-        }
-        __syncthreads(); // stage st is free again
-        if (refill) issue(t + kTileStages, nxt);
-    }
+        },
+        [&](uint32_t q, const pqg_page_desc& pd, const uint8_t* pg) {
+            fast_page<W>(P, q, pd, pg, has_dict, dictp, dict_n, dict_in_smem);
+        });
 }
 
 } // namespace
@@ -212,21 +144,14 @@ bool chunk_is_tileable(int phys_type, int max_def, int max_rep) {
 
 template <int W>
 static cudaError_t launch_tiles_t(DecodeParams p, int sm_count, cudaStream_t s) {
-    const size_t smem = kBarBytes + static_cast<size_t>(kTileStages) * kStageBytes + p.dict_smem;
+    const size_t smem = static_cast<size_t>(kTilePipeBytes) + p.dict_smem;
     // (attributes are per device: set on every launch, it is cheap)
     cudaError_t e = cudaFuncSetAttribute(k_fixed_tiles<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
-    // contiguous tile spans per CTA (a CTA stages a chunk's dictionary once); two waves of
-    // resident CTAs when there is enough work
+    // contiguous tile spans per CTA (a CTA stages a chunk's dictionary once)
     int resident = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k_fixed_tiles<W>, kThreadsPerCta, smem);
-    if (resident < 1) resident = 1;
-    uint32_t target = static_cast<uint32_t>(sm_count) * static_cast<uint32_t>(resident) * 2u;
-    const uint32_t n_tiles = p.tile_hi - p.tile_lo;
-    uint32_t per = (n_tiles + target - 1) / target;
-    if (per < 4) per = 4;
-    p.tiles_per_cta = per;
-    const uint32_t grid = (n_tiles + per - 1) / per;
+    const uint32_t grid = tile_grid(p.tile_hi - p.tile_lo, sm_count, resident, &p.tiles_per_cta);
     k_fixed_tiles<W><<<grid, kThreadsPerCta, smem, s>>>(p);
     return cudaGetLastError();
 }
