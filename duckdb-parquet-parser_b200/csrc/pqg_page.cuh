@@ -361,55 +361,94 @@ __device__ __forceinline__ bool walk_strings(const uint8_t* vals, uint32_t vavai
 // the prefixes; anything else (strings of 0-3 bytes producing false candidates, NUL-heavy
 // binary data, strings >= 64 KiB) fails the check and the caller falls back to the sequential
 // walk.  Returns the end position of the nn-th string in *end_pos.
-__device__ __forceinline__ uint64_t zero_byte_mask64(uint64_t v) { // bit 8i+7 set iff byte i == 0 (exact)
-    const uint64_t m = 0x7f7f7f7f7f7f7f7full;
-    return ~(((v & m) + m) | v | m);
+// Word loaders: the scan below reads ALIGNED 32-bit words of the buffer behind the value
+// section; shared memory gets explicit ld.shared (no generic-address overhead).
+struct SmemWords {
+    uint32_t base; // shared-state-space address of the aligned word 0
+    __device__ __forceinline__ uint32_t operator()(uint32_t wi) const {
+        uint32_t v;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(base + 4u * wi));
+        return v;
+    }
+};
+struct GenericWords {
+    const uint32_t* base;
+    __device__ __forceinline__ uint32_t operator()(uint32_t wi) const { return base[wi]; }
+};
+__device__ __forceinline__ uint32_t zero_byte_mask32(uint32_t w) { // bit 8i+7 set iff byte i == 0 (exact)
+    return ~(((w & 0x7f7f7f7fu) + 0x7f7f7f7fu) | w | 0x7f7f7f7fu);
 }
-__device__ __forceinline__ bool find_headers(const uint8_t* vals, uint32_t vavail, uint32_t nn, uint16_t* out, uint32_t cap,
-                                             uint32_t* end_pos) {
+// u16 at byte position apos of the word stream
+template <class LD>
+__device__ __forceinline__ uint32_t ld16_at(const LD& ld, uint32_t apos) {
+    uint32_t wi = apos >> 2, sh = (apos & 3u) * 8u;
+    uint32_t w0 = ld(wi);
+    uint32_t w1 = sh > 16u ? ld(wi + 1) : 0u;
+    return __funnelshift_r(w0, w1, sh) & 0xffffu;
+}
+
+// `ld` addresses aligned words; the value section starts `o` (0..3) bytes into word 0.
+// Per lane: one pass over R <= 64 byte positions building a 64-bit candidate mask with
+// branch-free zero-byte tricks (1 load + ~10 ALU ops per 4 positions), then the (1-3) candidates
+// of the lane are range-checked and kept in registers; warp prefix sum; ordered write; parallel
+// chain verification.
+template <class LD>
+__device__ __forceinline__ bool find_headers_w(const LD& ld, uint32_t o, uint32_t vavail, uint32_t nn, uint16_t* out, uint32_t cap,
+                                               uint32_t* end_pos) {
     const uint32_t l = lane_id();
     if (nn == 0) { *end_pos = 0; return true; }
     if (vavail < 4u || vavail > 65535u || nn > cap) return false;
-    const uint32_t last = vavail - 4u;                 // last position a prefix can start at
-    uint32_t R = (last / 32u + 4u) & ~3u;              // positions per lane, multiple of 4
-    const uint32_t p0 = l * R, p1 = min(p0 + R, last + 1u);
-    uint32_t cnt = 0;
-    for (uint32_t p = p0; p < p1; p += 4) {
-        uint64_t v = static_cast<uint64_t>(ld32u(vals + p)) | (static_cast<uint64_t>(ld32u(vals + p + 4)) << 32);
-        uint64_t z = zero_byte_mask64(v);
-        uint32_t zz = static_cast<uint32_t>((z & (z >> 8)) >> 16); // bit 8k+7: bytes k+2 and k+3 are zero
-        zz &= 0x80808080u;
-        while (zz) {
-            uint32_t k = (__ffs(zz) - 1) >> 3;
-            zz &= zz - 1;
-            uint32_t pos = p + k;
-            uint32_t len = static_cast<uint32_t>(v >> (8 * k)) & 0xffffu;
-            if (pos < p1 && pos + 4u + len <= vavail) cnt++;
+    const uint32_t last = vavail - 4u;                      // last vals-relative position of a prefix
+    const uint32_t R = ((o + last) / 32u + 4u) & ~3u;       // A-space positions per lane, multiple of 4
+    if (R > 64u) return false;
+    const uint32_t a0 = l * R;                              // first A-space position of this lane
+    uint32_t lo = 0, hi = 0;
+    if (a0 <= o + last) {
+        const uint32_t w0i = a0 >> 2, steps = R >> 2;
+        uint32_t z0 = zero_byte_mask32(ld(w0i));
+        for (uint32_t i = 0; i < steps; i++) {
+            uint32_t z1 = zero_byte_mask32(ld(w0i + i + 1));
+            // bit 8k+7 of zz: bytes k+2 and k+3 (of the 8-byte window) are zero
+            uint32_t zz = __funnelshift_r(z0, z1, 16) & __funnelshift_r(z0, z1, 24);
+            uint32_t nib = ((((zz >> 7) & 0x01010101u) * 0x01020408u) >> 24) & 0xfu;
+            if (i < 8) lo |= nib << (4u * i); else hi |= nib << (4u * (i - 8u));
+            z0 = z1;
         }
     }
+    // keep A-space positions inside [o, o + last]
+    uint64_t mask = (static_cast<uint64_t>(hi) << 32) | lo;
+    if (a0 < o) mask &= ~0ull << (o - a0);                  // o - a0 <= 3
+    if (a0 + 63u > o + last) { uint32_t keep = o + last >= a0 ? o + last - a0 + 1u : 0u; mask &= keep >= 64u ? ~0ull : ((1ull << keep) - 1ull); }
+    uint32_t c[4] = {0, 0, 0, 0};
+    uint32_t cnt = 0;
+    bool over = false;
+    while (mask) {
+        uint32_t j = __ffsll(static_cast<long long>(mask)) - 1;
+        mask &= mask - 1;
+        uint32_t apos = a0 + j;
+        uint32_t len = ld16_at(ld, apos);
+        uint32_t pos = apos - o;
+        if (pos + 4u + len <= vavail) {
+            if (cnt == 0) c[0] = pos; else if (cnt == 1) c[1] = pos; else if (cnt == 2) c[2] = pos; else if (cnt == 3) c[3] = pos; else over = true;
+            cnt++;
+        }
+    }
+    if (__any_sync(0xffffffffu, over)) return false;
     const uint32_t incl = warp_incl_scan(cnt);
     const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
     if (total < nn || total > cap) return false;
-    uint32_t w = incl - cnt;
-    for (uint32_t p = p0; p < p1; p += 4) {
-        uint64_t v = static_cast<uint64_t>(ld32u(vals + p)) | (static_cast<uint64_t>(ld32u(vals + p + 4)) << 32);
-        uint64_t z = zero_byte_mask64(v);
-        uint32_t zz = static_cast<uint32_t>((z & (z >> 8)) >> 16) & 0x80808080u;
-        while (zz) {
-            uint32_t k = (__ffs(zz) - 1) >> 3;
-            zz &= zz - 1;
-            uint32_t pos = p + k;
-            uint32_t len = static_cast<uint32_t>(v >> (8 * k)) & 0xffffu;
-            if (pos < p1 && pos + 4u + len <= vavail) out[w++] = static_cast<uint16_t>(pos);
-        }
-    }
+    const uint32_t w = incl - cnt;
+    if (cnt > 0) out[w] = static_cast<uint16_t>(c[0]);
+    if (cnt > 1) out[w + 1] = static_cast<uint16_t>(c[1]);
+    if (cnt > 2) out[w + 2] = static_cast<uint16_t>(c[2]);
+    if (cnt > 3) out[w + 3] = static_cast<uint16_t>(c[3]);
     __syncwarp();
     bool ok = true;
     uint32_t endp = 0;
     for (uint32_t i = l; i < nn; i += 32) {
-        uint32_t c = out[i];
-        uint32_t nx = c + 4u + (ld32u(vals + c) & 0xffffu);
-        if (i == 0 && c != 0) ok = false;
+        uint32_t ci = out[i];
+        uint32_t nx = ci + 4u + ld16_at(ld, ci + o);
+        if (i == 0 && ci != 0) ok = false;
         if (i + 1 < nn) { if (out[i + 1] != nx) ok = false; }
         else endp = nx;
     }
@@ -418,6 +457,14 @@ __device__ __forceinline__ bool find_headers(const uint8_t* vals, uint32_t vavai
     *end_pos = endp;
     __syncwarp();
     return ok;
+}
+
+// generic-pointer front end (shared slot or global memory)
+__device__ __forceinline__ bool find_headers(const uint8_t* vals, uint32_t vavail, uint32_t nn, uint16_t* out, uint32_t cap,
+                                             uint32_t* end_pos) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(vals);
+    GenericWords ld{reinterpret_cast<const uint32_t*>(a & ~uintptr_t(3))};
+    return find_headers_w(ld, static_cast<uint32_t>(a & 3u), vavail, nn, out, cap, end_pos);
 }
 
 // ---- page prolog -----------------------------------------------------------------------------

@@ -57,18 +57,51 @@ struct DfaDev {
     uint32_t wide;         // transition table indexed by the byte itself
     uint32_t table_bytes;  // bytes of trans
     uint32_t in_smem;      // tables are staged in shared memory
+    uint32_t scaled;       // wide table staged in shared memory: the word-wise fast DFA loop applies
 };
 
 // state 0 is the absorbing accept, `dead` the absorbing reject (host compiler, pq_regex.cpp)
 __device__ __forceinline__ bool dfa_run(const DfaDev& D, const uint16_t* trans, const uint8_t* cls, const uint8_t* accept,
                                         const uint8_t* text, uint32_t len) {
     uint32_t s = D.start;
-    if (D.wide) {
-        for (uint32_t i = 0; i < len && s != 0 && s != D.dead; i++) s = trans[s * 256u + text[i]];
+    if (D.wide) { // byte-indexed table, entries pre-scaled by 256
+        const uint32_t dead = D.dead << 8;
+        s <<= 8;
+        for (uint32_t i = 0; i < len && s != 0 && s != dead; i++) s = trans[s + text[i]];
+        return accept[s >> 8] != 0;
     } else {
         for (uint32_t i = 0; i < len && s != 0 && s != D.dead; i++) s = trans[s * D.n_classes + cls[text[i]]];
     }
     return accept[s] != 0;
+}
+
+// Byte-indexed table with PRE-SCALED entries (next state * 256), shared memory only: one add and
+// one ld.shared per byte, text taken from aligned words, absorbing states tested once per word.
+template <class LD>
+__device__ __forceinline__ bool dfa_run_scaled(const DfaDev& D, uint32_t trans_s, const uint8_t* accept, const LD& ld, uint32_t apos,
+                                               uint32_t len) {
+    uint32_t s = D.start << 8;
+    const uint32_t dead = D.dead << 8; // D.dead == 0xffffffff (none) never equals a scaled state
+    uint32_t wi = apos >> 2;
+    uint32_t skip = apos & 3u;
+    uint32_t w = ld(wi) >> (skip * 8u);
+    uint32_t n = min(4u - skip, len), i = 0;
+    for (;;) {
+#pragma unroll
+        for (uint32_t b = 0; b < 4; b++) {
+            if (b < n) {
+                uint32_t nxt;
+                asm volatile("ld.shared.u16 %0, [%1];" : "=r"(nxt) : "r"(trans_s + 2u * (s + (w & 0xffu))));
+                s = nxt;
+                w >>= 8;
+            }
+        }
+        i += n;
+        if (i >= len || s == 0u || s == dead) break;
+        w = ld(++wi);
+        n = min(4u, len - i);
+    }
+    return accept[s >> 8] != 0;
 }
 
 struct RegexParams {
@@ -205,6 +238,7 @@ __global__ void __launch_bounds__(kThreadsPerCta, 4) k_regex_tiles(RegexParams R
     stage_tables(R, smem + kTilePipeBytes + kWarpsPerCta * kRxCand * 2, trans, cls, accept);
     const DecodeParams& P = R.P;
     const uint32_t l = lane_id();
+    const uint32_t trans_s = smem_u32(trans); // meaningful when the tables are staged (R.D.scaled implies it)
     int max_def = 0;
     bool has_dict = false;
     uint32_t dict_n = 0;
@@ -258,16 +292,20 @@ __global__ void __launch_bounds__(kThreadsPerCta, 4) k_regex_tiles(RegexParams R
                     }
                 } else {
                     const uint8_t* vals = pg + pos;
+                    const uint32_t va = smem_u32(vals);
+                    const SmemWords ld{va & ~3u};
+                    const uint32_t o = va & 3u;
                     uint32_t endp = 0;
-                    if (!find_headers(vals, size - pos, nn, cand, kRxCand, &endp)) slow = true;
+                    if (!find_headers_w(ld, o, size - pos, nn, cand, kRxCand, &endp)) slow = true;
                     else {
                         for (uint32_t k0 = 0; k0 < nn && !hit; k0 += 32) {
                             uint32_t k = k0 + l;
                             bool h = false;
                             if (k < nn) {
                                 uint32_t c = cand[k];
-                                uint32_t len = ld32u(vals + c) & 0xffffu;
-                                bool m = dfa_run(R.D, trans, cls, accept, vals + c + 4, len);
+                                uint32_t len = ld16_at(ld, c + o);
+                                bool m = R.D.scaled ? dfa_run_scaled(R.D, trans_s, accept, ld, c + o + 4u, len)
+                                                    : dfa_run(R.D, trans, cls, accept, vals + c + 4, len);
                                 h = R.neg ? !m : m;
                             }
                             hit = __any_sync(0xffffffffu, h);
@@ -631,14 +669,15 @@ int pqg_regex_scan(pqg_ctx* ctx, pqg_plan* plan, const pqg_dfa* dfa, int neg, ui
     std::memset(page_bits, 0, words * 4);
     if (n_pages == 0) { if (kernel_ms) *kernel_ms = 0; return PQG_OK; }
     // device tables: [trans][cls 256][accept]; byte-indexed transitions when they stay small
-    const bool wide = static_cast<size_t>(d.n_states) * 256 * 2 <= 40 * 1024;
+    const bool wide = static_cast<size_t>(d.n_states) * 256 * 2 <= 40 * 1024 && d.n_states < 255;
     std::vector<uint8_t> blob;
     const uint32_t table_bytes = wide ? d.n_states * 512u : static_cast<uint32_t>(d.trans.size() * 2);
     blob.resize(static_cast<size_t>(table_bytes) + 256 + d.n_states);
     uint16_t* tr = reinterpret_cast<uint16_t*>(blob.data());
     if (wide) {
         for (uint32_t st = 0; st < d.n_states; st++)
-            for (uint32_t b = 0; b < 256; b++) tr[st * 256u + b] = d.trans[static_cast<size_t>(st) * d.n_classes + d.cls[b]];
+            for (uint32_t b = 0; b < 256; b++) // entries pre-scaled: next state * 256
+                tr[st * 256u + b] = static_cast<uint16_t>(d.trans[static_cast<size_t>(st) * d.n_classes + d.cls[b]] << 8);
     } else {
         std::memcpy(tr, d.trans.data(), d.trans.size() * 2);
     }
@@ -662,6 +701,7 @@ int pqg_regex_scan(pqg_ctx* ctx, pqg_plan* plan, const pqg_dfa* dfa, int neg, ui
     R.D.wide = wide; R.D.table_bytes = table_bytes;
     const size_t tab_smem = static_cast<size_t>(table_bytes) + 256 + d.n_states;
     R.D.in_smem = tab_smem <= 48 * 1024;
+    R.D.scaled = wide && R.D.in_smem;
     R.dict_match = d_dmatch; R.page_bits = d_bits; R.neg = neg ? 1 : 0;
     cudaEvent_t e0, e1;
     CUF(ctx, cudaEventCreate(&e0));
