@@ -2,6 +2,7 @@
 // decode plans.  No CPU fallback: every compute entry point needs a CUDA device.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -42,6 +43,7 @@ struct pqg_plan {
     uint32_t n_slow_host = 0;
     uint32_t dict_smem = 0;
     uint32_t max_dict_blocks = 1;
+    uint32_t cluster_size = 0, part_shift = 0; // DSMEM dictionary mode (0 = off)
     std::vector<uint32_t> chunk_tile_begin;  // n_chunks + 1: tiles of chunk c = [begin[c], begin[c+1])
     std::vector<uint32_t> chunk_slow_begin;  // n_chunks + 1: host-listed slow pages of chunk c
     std::vector<cudaEvent_t> pipe_ev;        // pipelined path: 2 events per chunk (H2D done, decode done)
@@ -347,6 +349,19 @@ int pqg_plan_create(pqg_ctx* ctx, const pqg_buf* image, const pqg_chunk_desc* ch
         p->n_tiles = static_cast<uint32_t>(tiles.size());
         p->n_slow_host = static_cast<uint32_t>(slow.size());
         p->max_dict_blocks = std::max<uint32_t>(1, std::min<uint32_t>(64, (max_dict_n + 2047) / 2048));
+        // dictionaries beyond one CTA's shared memory but within a cluster's: DSMEM mode
+        // (PQG_NO_CLUSTER=1 keeps the L2 gather, for A/B measurements)
+        if (!p->is_str && (p->width == 4 || p->width == 8) && !std::getenv("PQG_NO_CLUSTER")) {
+            const uint64_t dict_bytes = static_cast<uint64_t>(max_dict_n) * p->width;
+            if (dict_bytes > static_cast<uint64_t>(kMaxSmemDictBytes) && dict_bytes <= 8ull * 64 * 1024) {
+                uint32_t cs = 2;
+                while (cs < 8 && dict_bytes > static_cast<uint64_t>(cs) * 64 * 1024) cs <<= 1;
+                uint32_t per = (max_dict_n + cs - 1) / cs, sh = 0;
+                while ((1u << sh) < per) sh++;
+                p->cluster_size = cs;
+                p->part_shift = sh;
+            }
+        }
     }
 
     auto alloc = [&](void** ptr, size_t bytes) -> cudaError_t { return cudaMalloc(ptr, bytes ? bytes : 16); };
@@ -414,6 +429,7 @@ static DecodeParams make_params(const pqg_plan* p) {
     P.tiles = p->d_tiles; P.tile_lo = 0; P.tile_hi = p->n_tiles; P.dict_smem = p->dict_smem;
     P.slow_lo = 0; P.slow_hi = p->n_slow_host; P.n_slow_host = p->n_slow_host; P.slow_pages = p->d_slow_pages;
     P.chunk_lo = 0;
+    P.cluster_size = p->cluster_size; P.part_shift = p->part_shift;
     return P;
 }
 
@@ -438,7 +454,16 @@ static int fixed_subrun(pqg_ctx* ctx, pqg_plan* p, uint32_t c0, uint32_t c1, boo
     for (uint32_t c = c0; c < c1; c++) any_dict = any_dict || p->chunks[c].has_dict;
     if (e == cudaSuccess && any_dict) { e = launch_dict_prepare(P, c1 - c0, p->width, p->max_dict_blocks, s); launches++; }
     if (e == cudaSuccess && ev_tiles_begin) e = cudaEventRecord(ev_tiles_begin, s);
-    if (e == cudaSuccess && P.tile_hi > P.tile_lo) { e = launch_fixed_tiles(P, p->width, ctx->sm_count, s); launches++; }
+    if (e == cudaSuccess && P.tile_hi > P.tile_lo) {
+        if (p->cluster_size) { // one launch per chunk: a cluster holds one dictionary
+            for (uint32_t c = c0; c < c1 && e == cudaSuccess; c++) {
+                DecodeParams Pc = P;
+                Pc.chunk_lo = c;
+                Pc.tile_lo = p->chunk_tile_begin[c]; Pc.tile_hi = p->chunk_tile_begin[c + 1];
+                if (Pc.tile_hi > Pc.tile_lo) { e = launch_fixed_tiles_cluster(Pc, p->width, ctx->sm_count, s); launches++; }
+            }
+        } else { e = launch_fixed_tiles(P, p->width, ctx->sm_count, s); launches++; }
+    }
     if (e == cudaSuccess && ev_tiles_end) e = cudaEventRecord(ev_tiles_end, s);
     // the general kernel takes the host-listed pages plus whatever the tile kernel handed over
     if (e == cudaSuccess && (P.slow_hi > P.slow_lo || P.tile_hi > P.tile_lo)) { e = launch_decode_fixed(P, p->width, p->is_bool, ctx->sm_count, s); launches++; }

@@ -91,6 +91,8 @@ struct DecodeParams {
     uint32_t n_slow_host;    // device-appended slow pages start at slow_pages[n_slow_host]
     uint32_t* slow_pages;    // capacity: every page of the plan
     uint32_t chunk_lo;       // first chunk of this launch (dictionary preparation)
+    uint32_t cluster_size;   // > 0: large dictionaries are spread over a cluster's shared memories
+    uint32_t part_shift;     // log2 of the dictionary entries per CTA of the cluster
 };
 
 // launchers (pqg_decode.cu)
@@ -98,6 +100,7 @@ cudaError_t launch_dict_prepare(const DecodeParams& p, uint32_t n_chunks, int wi
 cudaError_t launch_decode_fixed(const DecodeParams& p, int width, bool boolean_plain, int sm_count, cudaStream_t s);
 // fast path (pqg_tiles.cu): PLAIN / regular-dictionary pages of REQUIRED 4- and 8-byte chunks
 cudaError_t launch_fixed_tiles(const DecodeParams& p, int width, int sm_count, cudaStream_t s);
+cudaError_t launch_fixed_tiles_cluster(const DecodeParams& p, int width, int sm_count, cudaStream_t s); // one chunk per launch
 bool chunk_is_tileable(int phys_type, int max_def, int max_rep);
 cudaError_t launch_str_sizes(const DecodeParams& p, int sm_count, cudaStream_t s);
 cudaError_t launch_str_scan(const DecodeParams& p, uint64_t* total_chars, cudaStream_t s);

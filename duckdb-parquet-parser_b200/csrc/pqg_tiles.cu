@@ -48,10 +48,29 @@ __device__ __forceinline__ void to_slow(const DecodeParams& P, uint32_t q) {
     P.slow_pages[P.n_slow_host + k] = q;
 }
 
+// A dictionary spread over the shared memories of a thread-block cluster: entry ix lives in
+// CTA (ix >> shift) at byte (ix & mask) * W of that CTA's part.
+struct ClusterDict { uint32_t base, shift, mask; };
+
+template <typename T> __device__ __forceinline__ T dsmem_ld(uint32_t local_addr, uint32_t rank);
+template <> __device__ __forceinline__ uint64_t dsmem_ld<uint64_t>(uint32_t local_addr, uint32_t rank) {
+    uint32_t ra; uint64_t v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_addr), "r"(rank));
+    asm volatile("ld.shared::cluster.u64 %0, [%1];" : "=l"(v) : "r"(ra));
+    return v;
+}
+template <> __device__ __forceinline__ uint32_t dsmem_ld<uint32_t>(uint32_t local_addr, uint32_t rank) {
+    uint32_t ra, v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_addr), "r"(rank));
+    asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(ra));
+    return v;
+}
+
 // One warp decodes one page out of the staged tile.  `pg` = first payload byte (shared).
-template <int W>
+template <int W, bool CLUSTER = false>
 __device__ __forceinline__ void fast_page(const DecodeParams& P, uint32_t q, const pqg_page_desc& pd, const uint8_t* pg,
-                                          bool chunk_has_dict, const uint8_t* dictp, uint32_t dict_n, bool dict_in_smem) {
+                                          bool chunk_has_dict, const uint8_t* dictp, uint32_t dict_n, bool dict_in_smem,
+                                          ClusterDict cd = ClusterDict{0, 0, 0}) {
     using T = typename FElem<W>::T;
     const uint32_t l = lane_id();
     const uint32_t n = pd.num_values, size = pd.payload_size;
@@ -78,27 +97,27 @@ __device__ __forceinline__ void fast_page(const DecodeParams& P, uint32_t q, con
     const uint8_t* s = pg + 1;
     if (bw > 32 || !check_regular(s, size - 1, bw, n)) { if (l == 0) to_slow(P, q); return; }
     const T* dict = reinterpret_cast<const T*>(dictp);
+    auto get = [&](uint32_t ix) -> T {
+        if constexpr (CLUSTER) return dsmem_ld<T>(cd.base + (ix & cd.mask) * W, ix >> cd.shift);
+        else return dict_in_smem ? dict[ix] : __ldg(dict + ix);
+    };
     bool bad = false;
     uint32_t v = l;
     for (; v + 96 < n; v += 128) {
         uint32_t i0 = regular_index(s, bw, v), i1 = regular_index(s, bw, v + 32);
         uint32_t i2 = regular_index(s, bw, v + 64), i3 = regular_index(s, bw, v + 96);
         bad = bad || i0 >= dict_n || i1 >= dict_n || i2 >= dict_n || i3 >= dict_n;
-        T x0 = 0, x1 = 0, x2 = 0, x3 = 0;
-        if (dict_in_smem) {
-            if (i0 < dict_n) x0 = dict[i0]; if (i1 < dict_n) x1 = dict[i1];
-            if (i2 < dict_n) x2 = dict[i2]; if (i3 < dict_n) x3 = dict[i3];
-        } else {
-            if (i0 < dict_n) x0 = __ldg(dict + i0); if (i1 < dict_n) x1 = __ldg(dict + i1);
-            if (i2 < dict_n) x2 = __ldg(dict + i2); if (i3 < dict_n) x3 = __ldg(dict + i3);
-        }
+        T x0 = i0 < dict_n ? get(i0) : T(0);
+        T x1 = i1 < dict_n ? get(i1) : T(0);
+        T x2 = i2 < dict_n ? get(i2) : T(0);
+        T x3 = i3 < dict_n ? get(i3) : T(0);
         st_stream<T>(out + v, x0); st_stream<T>(out + v + 32, x1);
         st_stream<T>(out + v + 64, x2); st_stream<T>(out + v + 96, x3);
     }
     for (; v < n; v += 32) {
         uint32_t i0 = regular_index(s, bw, v);
         T x0 = 0;
-        if (i0 < dict_n) x0 = dict_in_smem ? dict[i0] : __ldg(dict + i0); else bad = true;
+        if (i0 < dict_n) x0 = get(i0); else bad = true;
         st_stream<T>(out + v, x0);
     }
     // an out-of-range index is a NULL in the reference (column_reader.cpp:190-194): the
@@ -135,6 +154,50 @@ __global__ void __launch_bounds__(kThreadsPerCta, 3) k_fixed_tiles(const DecodeP
         });
 }
 
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// Same pipeline, for ONE chunk whose dictionary is too large for one CTA's shared memory but
+// fits the cluster's: every CTA of the cluster keeps 1/CS of the dictionary (bulk copy) and
+// gathers through distributed shared memory (mapa + ld.shared::cluster) instead of L1TEX/L2 --
+// a random 8-byte global gather costs one L1TEX wavefront and one 32-byte L2 sector per value
+// and tops out near 2 TB/s of decoded output; DSMEM serves it next to the SMs.
+template <int W>
+__global__ void __launch_bounds__(kThreadsPerCta, 2) k_fixed_tiles_cluster(const DecodeParams P) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t* dbar = reinterpret_cast<uint64_t*>(smem + kTilePipeBytes);
+    uint8_t* sdict = smem + kTilePipeBytes + 16;
+    const uint32_t rank = cluster_ctarank();
+    const DevChunk& ck = P.chunks[P.chunk_lo];
+    const bool has_dict = ck.has_dict;
+    const uint32_t dict_n = ck.dict_ok_n;
+    const uint32_t part = 1u << P.part_shift;
+    const uint32_t first = rank * part;
+    const uint32_t cnt = (has_dict && first < dict_n) ? min(part, dict_n - first) : 0u;
+    const uint32_t dbytes = (cnt * W + 15u) & ~15u;
+    if (threadIdx.x == 0) {
+        mbar_init(dbar, 1);
+        fence_mbar_init();
+        if (dbytes) {
+            mbar_expect_tx(dbar, dbytes);
+            bulk_g2s(sdict, P.dict_arena + ck.dict_arena_off + static_cast<size_t>(first) * W, dbytes, dbar);
+        }
+    }
+    __syncthreads();
+    if (dbytes) mbar_wait(dbar, 0);
+    cluster_sync_all(); // every part of the dictionary is in place
+    const ClusterDict cd{smem_u32(sdict), P.part_shift, part - 1u};
+    tile_pipeline(P, smem,
+        [&](uint32_t, uint64_t*, uint32_t&) {},
+        [&](uint32_t q, const pqg_page_desc& pd, const uint8_t* pg) {
+            fast_page<W, true>(P, q, pd, pg, has_dict, nullptr, dict_n, false, cd);
+        });
+    cluster_sync_all(); // nobody may leave while a peer can still read its part
+}
+
 } // namespace
 
 bool chunk_is_tileable(int phys_type, int max_def, int max_rep) {
@@ -154,6 +217,42 @@ static cudaError_t launch_tiles_t(DecodeParams p, int sm_count, cudaStream_t s) 
     const uint32_t grid = tile_grid(p.tile_hi - p.tile_lo, sm_count, resident, &p.tiles_per_cta);
     k_fixed_tiles<W><<<grid, kThreadsPerCta, smem, s>>>(p);
     return cudaGetLastError();
+}
+
+template <int W>
+static cudaError_t launch_cluster_t(DecodeParams p, int sm_count, cudaStream_t s) {
+    const uint32_t cs = p.cluster_size;
+    const size_t smem = static_cast<size_t>(kTilePipeBytes) + 16 + (static_cast<size_t>(W) << p.part_shift);
+    cudaError_t e = cudaFuncSetAttribute(k_fixed_tiles_cluster<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    const uint32_t n_tiles = p.tile_hi - p.tile_lo;
+    // resident CTAs: 2 per SM by shared memory at most; one wave of clusters, spans of >= 4 tiles
+    uint32_t ctas = static_cast<uint32_t>(sm_count) * (smem <= 100 * 1024 ? 2u : 1u);
+    ctas = (ctas / cs) * cs;
+    uint32_t per = (n_tiles + ctas - 1) / ctas;
+    if (per < 4) per = 4;
+    uint32_t grid = (n_tiles + per - 1) / per;
+    grid = ((grid + cs - 1) / cs) * cs;
+    p.tiles_per_cta = per;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreadsPerCta);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, k_fixed_tiles_cluster<W>, p);
+}
+
+// one launch per chunk: the cluster holds exactly one dictionary
+cudaError_t launch_fixed_tiles_cluster(const DecodeParams& p, int width, int sm_count, cudaStream_t s) {
+    if (p.tile_hi <= p.tile_lo) return cudaSuccess;
+    if (width == 4) return launch_cluster_t<4>(p, sm_count, s);
+    if (width == 8) return launch_cluster_t<8>(p, sm_count, s);
+    return cudaErrorInvalidValue;
 }
 
 cudaError_t launch_fixed_tiles(const DecodeParams& p, int width, int sm_count, cudaStream_t s) {
