@@ -406,13 +406,17 @@ __device__ __forceinline__ bool find_headers_w(const LD& ld, uint32_t o, uint32_
     if (a0 <= o + last) {
         const uint32_t w0i = a0 >> 2, steps = R >> 2;
         uint32_t z0 = zero_byte_mask32(ld(w0i));
-        for (uint32_t i = 0; i < steps; i++) {
-            uint32_t z1 = zero_byte_mask32(ld(w0i + i + 1));
-            // bit 8k+7 of zz: bytes k+2 and k+3 (of the 8-byte window) are zero
-            uint32_t zz = __funnelshift_r(z0, z1, 16) & __funnelshift_r(z0, z1, 24);
-            uint32_t nib = ((((zz >> 7) & 0x01010101u) * 0x01020408u) >> 24) & 0xfu;
-            if (i < 8) lo |= nib << (4u * i); else hi |= nib << (4u * (i - 8u));
-            z0 = z1;
+        // steps <= 16 and warp-uniform: unrolled with constant shifts
+#pragma unroll
+        for (uint32_t i = 0; i < 16; i++) {
+            if (i < steps) {
+                uint32_t z1 = zero_byte_mask32(ld(w0i + i + 1));
+                // bit 8k+7 of zz: bytes k+2 and k+3 (of the 8-byte window) are zero
+                uint32_t zz = __funnelshift_r(z0, z1, 16) & __funnelshift_r(z0, z1, 24);
+                uint32_t nib = (((zz >> 7) & 0x01010101u) * 0x01020408u) >> 24; // 4 flags -> bits 0..3
+                if (i < 8) lo |= nib << (4u * i); else hi |= nib << (4u * (i - 8u));
+                z0 = z1;
+            }
         }
     }
     // keep A-space positions inside [o, o + last]

@@ -1,0 +1,221 @@
+"""Hand-built pages through the C-ABI (pqg_plan_create / run / finish / download): dictionary
+index streams at EVERY bit width 1..32 (reference encoder output, mixed RLE + bit-packed runs,
+multi-group literal runs as foreign writers emit them), definition-level streams, truncated
+pages and bad runs -> per-page error codes.  Expected values come from the oracle's restatement
+of RleDecoder::get_batch (include/reader/rle_decoder.hpp:17-95)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def varint(x):
+    out = bytearray()
+    while x >= 0x80:
+        out.append((x & 0x7F) | 0x80)
+        x >>= 7
+    out.append(x)
+    return bytes(out)
+
+
+def bitpack(vals, bw):
+    acc, bits, out = 0, 0, bytearray()
+    for v in vals:
+        acc |= int(v) << bits
+        bits += bw
+        while bits >= 8:
+            out.append(acc & 0xFF)
+            acc >>= 8
+            bits -= 8
+    if bits:
+        out.append(acc & 0xFF)
+    return bytes(out)
+
+
+def foreign_stream(vals, bw, rng):
+    """RLE / bit-packed hybrid the way pyarrow-style writers emit it: literal runs of several
+    groups of 8, RLE runs of any length"""
+    out, i, n = bytearray(), 0, len(vals)
+    while i < n:
+        if rng.random() < 0.4:
+            run = int(rng.integers(1, 70))
+            run = min(run, n - i)
+            v = int(vals[i])
+            out += varint(run << 1) + int(v).to_bytes((bw + 7) // 8, "little")
+            vals[i:i + run] = v
+            i += run
+        else:
+            groups = int(rng.integers(1, 6))
+            cnt = min(groups * 8, n - i)
+            groups = (cnt + 7) // 8
+            chunk = list(vals[i:i + cnt]) + [0] * (groups * 8 - cnt)
+            out += varint((groups << 1) | 1) + bitpack(chunk, bw)
+            i += cnt
+    return bytes(out)
+
+
+class Builder:
+    """one image = [dictionary payload][page payloads...]; one chunk; INT64 values"""
+
+    def __init__(self, pq, dict_vals, max_def=0):
+        self.pq, self.max_def = pq, max_def
+        self.img = bytearray(np.asarray(dict_vals, dtype=np.int64).tobytes()) if dict_vals is not None else bytearray()
+        self.dict_n = 0 if dict_vals is None else len(dict_vals)
+        self.dict_size = len(self.img)
+        self.pages = []
+        self.rows = 0
+
+    def add_page(self, payload, num_values, dict_page=True, misalign=0):
+        self.img += b"\xEE" * misalign
+        self.pages.append((len(self.img), len(payload), num_values, dict_page, self.rows))
+        self.img += payload
+        self.rows += num_values
+
+    def run(self, expect_error=None):
+        pq = self.pq
+        ctx = pq.Context(0)
+        img = np.frombuffer(bytes(self.img) + b"\0" * 64, dtype=np.uint8)
+        buf = ctx.upload(img.ctypes.data, len(self.img))
+        ck = (pq.ChunkDesc * 1)()
+        ck[0] = pq.ChunkDesc(0, 0, self.rows, self.dict_size, self.dict_n, 0, len(self.pages), 0, 0, self.max_def, 0, pq.INT64,
+                             1 if self.dict_n else 0, (C.c_uint8 * 2)(0, 0))
+        pg = (pq.PageDesc * max(len(self.pages), 1))()
+        for i, (off, size, nv, dp, row) in enumerate(self.pages):
+            pg[i] = pq.PageDesc(off, row, size, nv, 0, 1 if dp else 0)
+        plan = ctx.plan(buf, (ck, 1, pg, len(self.pages), self.rows))
+        plan.run()
+        try:
+            if expect_error is not None:
+                pe = pq.PageError()
+                rc = pq.lib().pqg_plan_finish(ctx.h, plan.h, C.byref(pe))
+                assert rc == pq.PQG_ERR_PAGE, ctx.err()
+                assert pe.code == expect_error[0] and pe.page == expect_error[1], (pe.code, pe.page, ctx.err())
+                return None, None, ctx.err()
+            plan.finish()
+            vals = np.zeros(self.rows, dtype=np.int64)
+            valid = np.zeros((self.rows + 31) // 32 + 1, dtype=np.uint32)
+            plan.download(values=vals.ctypes.data, validity=valid.ctypes.data if self.max_def else None)
+            ctx.sync()
+            v = None
+            if self.max_def:
+                v = ((valid[np.arange(self.rows) >> 5] >> (np.arange(self.rows) & 31).astype(np.uint32)) & 1).astype(bool)
+            return vals, v, None
+        finally:
+            plan.destroy()
+            ctx.buf_free(buf)
+            ctx.close()
+
+
+@pytest.mark.parametrize("bw", list(range(1, 33)))
+def test_dictionary_index_streams_every_bit_width(pq, oracle, ref, bw):
+    rng = np.random.default_rng(bw)
+    dict_n = min(1 << min(bw, 14), 5000)
+    dict_vals = rng.integers(-2**62, 2**62, size=dict_n, dtype=np.int64)
+    b = Builder(pq, dict_vals)
+    expected = []
+    hi = min(1 << bw, dict_n)
+    for page, n in enumerate((1, 7, 8, 9, 341, 512, 1024, 1500, 3000)):
+        idx = rng.integers(0, hi, size=n).astype(np.uint32)
+        if page % 3 == 1:
+            idx[: n // 2] = idx[0]  # long RLE run at the front
+        if page % 2 == 0:
+            stream = bytes(ref.rle_encode(idx, bw))  # the reference's own encoder: single groups of 8
+        else:
+            stream = foreign_stream(idx, bw, rng)  # (mutates idx for its RLE runs)
+        dec = oracle.rle_decode_i32(np.frombuffer(stream, dtype=np.uint8), bw, n)
+        assert np.array_equal(dec.astype(np.uint32), idx)
+        b.add_page(bytes([bw]) + stream, n, misalign=page % 5)
+        expected.append(dict_vals[idx])
+    vals, _, _ = b.run()
+    assert np.array_equal(vals, np.concatenate(expected)), bw
+
+
+def test_optional_levels_and_out_of_range_indices_become_nulls(pq, oracle):
+    rng = np.random.default_rng(5)
+    dict_vals = np.arange(100, dtype=np.int64) * 11 + 1
+    b = Builder(pq, dict_vals, max_def=1)
+    exp_vals, exp_valid = [], []
+    for page, n in enumerate((5, 64, 1000, 1024, 2500)):
+        present = rng.random(n) < (0.7 if page != 1 else 1.0)
+        if page == 2:
+            present[:] = False  # an all-null page
+        # definition levels: bit-packed literal runs (foreign style) on odd pages, RLE runs otherwise
+        lv = present.astype(np.uint32)
+        if page % 2:
+            groups = (n + 7) // 8
+            def_stream = varint((groups << 1) | 1) + bitpack(list(lv) + [0] * (groups * 8 - n), 1)
+        else:
+            def_stream, i = bytearray(), 0
+            while i < n:
+                j = i
+                while j < n and lv[j] == lv[i]:
+                    j += 1
+                def_stream += varint((j - i) << 1) + bytes([int(lv[i])])
+                i = j
+            def_stream = bytes(def_stream)
+        nn = int(present.sum())
+        idx = rng.integers(0, 100, size=nn).astype(np.uint32)
+        if nn > 3:
+            idx[1] = 100  # out of range -> null (column_reader.cpp:190-194)
+            idx[3] = 127
+        stream = foreign_stream(idx.copy(), 7, rng) if page % 2 else bytes(_enc(idx, 7))
+        dec = oracle.rle_decode_i32(np.frombuffer(stream, dtype=np.uint8), 7, nn).astype(np.uint32)
+        payload = len(def_stream).to_bytes(4, "little") + def_stream + bytes([7]) + stream
+        b.add_page(payload, n, misalign=page)
+        v = np.zeros(n, dtype=np.int64)
+        ok = present.copy()
+        slots = np.nonzero(present)[0]
+        good = dec < 100
+        v[slots[good]] = dict_vals[dec[good]]
+        ok[slots[~good]] = False
+        exp_vals.append(v)
+        exp_valid.append(ok)
+    vals, valid, _ = b.run()
+    assert np.array_equal(valid, np.concatenate(exp_valid))
+    assert np.array_equal(vals, np.concatenate(exp_vals))
+
+
+def _enc(idx, bw):
+    """single bit-packed groups of 8 ("03 <bw bytes>"), zero padded: the reference writer's layout
+    for data without 4-fold repeats"""
+    out = bytearray()
+    for i in range(0, len(idx), 8):
+        g = list(idx[i:i + 8]) + [0] * (8 - len(idx[i:i + 8]))
+        out += b"\x03" + bitpack(g, bw)
+    return bytes(out)
+
+
+def test_page_errors(pq):
+    dict_vals = np.arange(16, dtype=np.int64)
+    # truncated PLAIN page: 10 values announced, 5 present -> ByteBuffer-style error on page 1
+    b = Builder(pq, None)
+    b.add_page(np.arange(8, dtype=np.int64).tobytes(), 8, dict_page=False)
+    b.add_page(np.arange(5, dtype=np.int64).tobytes(), 10, dict_page=False)
+    _, _, msg = b.run(expect_error=(pq.lib() and 1, 1))
+    assert "ByteBuffer: read beyond end" in msg
+    # bit width 33
+    b = Builder(pq, dict_vals)
+    b.add_page(bytes([4]) + _enc(np.arange(8, dtype=np.uint32), 4), 8)
+    b.add_page(bytes([33]) + b"\x03" + b"\0" * 33, 8)
+    b.run(expect_error=(2, 1))
+    # zero-length RLE run: undefined behaviour in the reference -> explicit error
+    b = Builder(pq, dict_vals)
+    b.add_page(bytes([4]) + b"\x00\x01" + _enc(np.arange(8, dtype=np.uint32), 4), 8)
+    b.run(expect_error=(3, 0))
+    # definition-level section longer than the page
+    b = Builder(pq, dict_vals, max_def=1)
+    b.add_page((500).to_bytes(4, "little") + b"\x10\x01", 8)
+    b.run(expect_error=(1, 0))
+
+
+def test_short_streams_zero_fill_like_the_reference(pq, oracle):
+    """RleDecoder returns zeros once the data is exhausted (rle_decoder.hpp:21-24)"""
+    dict_vals = np.arange(8, dtype=np.int64) + 100
+    b = Builder(pq, dict_vals)
+    stream = _enc(np.array([1, 2, 3, 4, 5, 6, 7, 0], dtype=np.uint32), 3)
+    b.add_page(bytes([3]) + stream, 20)  # 8 values encoded, 20 announced
+    vals, _, _ = b.run()
+    dec = oracle.rle_decode_i32(np.frombuffer(stream, dtype=np.uint8), 3, 20)
+    assert np.array_equal(vals, dict_vals[dec])

@@ -14,17 +14,18 @@ GOLD = os.path.join(ROOT, "tests", "golden")
 
 def declared(header):
     text = open(os.path.join(ROOT, "include", header)).read()
-    return sorted(set(re.findall(r"PQG_API[^;(]*?\b(pq[gr]_\w+)\s*\(", text)))
+    return sorted(set(re.findall(r"PQG_API[^;(]*?\b(pq(?:g|r|gen)_\w+)\s*\(", text)))
 
 
 def test_library_exports_every_declared_symbol(pq):
     L = ctypes.CDLL(pq.LIB_PATH)
-    names = declared("pqg.h") + declared("pqg_reader.h")
+    names = declared("pqg.h") + declared("pqg_reader.h") + declared("pqg_gen.h")
     assert len(names) > 60
     for n in names:
         assert hasattr(L, n), f"{n} declared in include/ but not exported by libpqg.so"
     assert sorted(pq.PQG_SYMBOLS) == declared("pqg.h")
     assert sorted(pq.PQR_SYMBOLS) == declared("pqg_reader.h")
+    assert sorted(pq.PQGEN_SYMBOLS) == declared("pqg_gen.h")
 
 
 def test_no_device_means_loud_failure(pq):
