@@ -43,7 +43,7 @@ template <> __device__ __forceinline__ U96 load_plain<12>(const uint8_t* p) {
 // dictionary preparation
 // ---------------------------------------------------------------------------------------------
 template <int W>
-__global__ void __launch_bounds__(256) k_dict_prepare(DecodeParams P) {
+__global__ void __launch_bounds__(1024) k_dict_prepare(DecodeParams P) {
     // grid: (blocks per chunk, chunks)
     DevChunk& ck = P.chunks[P.chunk_lo + blockIdx.y];
     const bool first = blockIdx.x == 0 && threadIdx.x == 0;
@@ -65,9 +65,57 @@ __global__ void __launch_bounds__(256) k_dict_prepare(DecodeParams P) {
     } else {
         // BYTE_ARRAY: u32 length prefix + bytes (column_reader.cpp:249-253).  Entry table:
         // {start (byte offset of the chars inside the dictionary payload), len}.
-        // TODO(perf): segment-parallel walk; one lane per dictionary for now.
+        // Parallel: every thread scans a contiguous slice of the payload for prefix candidates
+        // (bytes +2 and +3 zero, string inside the payload), block prefix sum, ordered write,
+        // chain verification.  Falls back to one sequential walk when the check fails (entries
+        // shorter than 4 bytes, NUL-heavy binary strings, strings >= 64 KiB).
         uint2* ent = reinterpret_cast<uint2*>(dst);
-        if (first) {
+        __shared__ uint32_t s_warp[32];
+        __shared__ uint32_t s_ok, s_total;
+        const uint32_t tid = threadIdx.x, nthr = blockDim.x;
+        bool ok_scan = size >= 4 && n > 0;
+        const uint32_t last = ok_scan ? size - 4 : 0;
+        const uint32_t per = ((last / nthr) + 4u) & ~3u;
+        const uint32_t p0 = tid * per, p1 = ok_scan ? min(p0 + per, last + 1u) : 0u;
+        auto is_cand = [&](uint32_t p, uint32_t* len_out) {
+            uint32_t v = ld32u(src + p);
+            *len_out = v;
+            return (v >> 16) == 0u && static_cast<uint64_t>(p) + 4u + v <= size;
+        };
+        uint32_t cnt = 0;
+        for (uint32_t p = p0; p < p1; p++) { uint32_t ln; if (is_cand(p, &ln)) cnt++; }
+        // block exclusive scan of cnt
+        uint32_t incl = warp_incl_scan(cnt);
+        if ((tid & 31u) == 31u) s_warp[tid >> 5] = incl;
+        __syncthreads();
+        if (tid < 32) {
+            uint32_t v = tid < (nthr >> 5) ? s_warp[tid] : 0u;
+            uint32_t iv = warp_incl_scan(v);
+            s_warp[tid] = iv - v;
+            if (tid == 31) s_total = iv;
+        }
+        if (tid == 0) s_ok = 1;
+        __syncthreads();
+        uint32_t w = s_warp[tid >> 5] + incl - cnt;
+        const uint32_t total = s_total;
+        if (total >= n && ok_scan) {
+            for (uint32_t p = p0; p < p1; p++) {
+                uint32_t ln;
+                if (is_cand(p, &ln)) { if (w < n) ent[w] = make_uint2(p + 4u, ln); w++; }
+            }
+            __syncthreads();
+            bool ok = true;
+            for (uint32_t i = tid; i < n; i += nthr) {
+                uint2 e = ent[i];
+                uint32_t want = i == 0 ? 4u : ent[i - 1].x + ent[i - 1].y + 4u;
+                if (e.x != want) ok = false;
+            }
+            if (!ok) atomicExch(&s_ok, 0u);
+            __syncthreads();
+        } else if (tid == 0) s_ok = 0;
+        __syncthreads();
+        if (s_ok) { if (first) ck.dict_ok_n = n; }
+        else if (first) {
             uint32_t pos = 0, k = 0;
             for (; k < n; k++) {
                 if (static_cast<uint64_t>(pos) + 4 > size) { report_error(P.err, ck.first_page, PQG_PAGE_DICT_TRUNCATED, pos, 4, size); break; }
@@ -351,51 +399,35 @@ __device__ __forceinline__ void decode_str_page(const DecodeParams& P, uint32_t 
                     if (sh && (m >> (32u - sh))) atomicOr(&P.validity[(a0 >> 5) + 1], m >> (32u - sh));
                 }
             }
-            // chars of the group: bytes [0,total) go to dstg; 4 output bytes per lane per step,
-            // each byte finds its owner lane by binary search over the lanes' offsets.
+            // chars of the group: bytes [0,total) go to dstg.
             if (total) {
                 uint8_t* dstg = chars + gbase;
-                const uint32_t mis = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(dstg) & 3u);
-                const uint32_t nwords = (total + mis + 3u) >> 2;
-                const unsigned long long spl = reinterpret_cast<unsigned long long>(sp);
-                for (uint32_t wbase = 0; wbase < nwords; wbase += 32) {
-                    const uint32_t wj = wbase + l;
-                    const int64_t o0 = static_cast<int64_t>(wj) * 4 - mis; // group byte offset of this word's byte 0
-                    uint32_t word = 0, have = 0;
-                    // owner of byte max(o0,0): last lane with incl-len <= o and len > 0 ... search on incl
-                    uint32_t o = o0 < 0 ? 0u : static_cast<uint32_t>(o0);
-                    // smallest lane L with incl[L] > o
-                    uint32_t lo = 0, hi = 31;
-#pragma unroll
-                    for (int it = 0; it < 5; it++) {
-                        uint32_t mid = (lo + hi) >> 1;
-                        uint32_t im = __shfl_sync(0xffffffffu, incl, mid);
-                        if (im > o) hi = mid; else lo = mid + 1;
-                    }
-                    uint32_t L = lo;
-#pragma unroll
-                    for (int b = 0; b < 4; b++) {
-                        int64_t ob = o0 + b;
-                        bool act = wj < nwords && ob >= 0 && ob < static_cast<int64_t>(total);
-                        // advance the owner while this byte is past its end (all lanes shuffle)
-                        uint32_t iL = __shfl_sync(0xffffffffu, incl, L & 31u);
-                        while (__any_sync(0xffffffffu, act && static_cast<uint32_t>(ob) >= iL)) {
-                            if (act && static_cast<uint32_t>(ob) >= iL) L++;
-                            iL = __shfl_sync(0xffffffffu, incl, L & 31u);
-                        }
-                        uint32_t lenL = __shfl_sync(0xffffffffu, len, L & 31u);
-                        unsigned long long spL = __shfl_sync(0xffffffffu, spl, L & 31u);
-                        if (act) {
-                            uint32_t within = static_cast<uint32_t>(ob) - (iL - lenL);
-                            uint32_t ch = reinterpret_cast<const uint8_t*>(spL)[within];
-                            word |= ch << (8 * b);
-                            have |= 1u << b;
-                        }
-                    }
-                    if (have == 0xFu) *reinterpret_cast<uint32_t*>(dstg + o0) = word;
-                    else {
-#pragma unroll
-                        for (int b = 0; b < 4; b++) if (have & (1u << b)) dstg[o0 + b] = static_cast<uint8_t>(word >> (8 * b));
+                const uint32_t maxlen = __reduce_max_sync(0xffffffffu, len);
+                if (maxlen <= static_cast<uint32_t>(kStageMaxLen)) {
+                    // short strings: every lane copies its own string into the warp's staging
+                    // buffer (same 16-byte phase as the destination), then the warp flushes the
+                    // contiguous bytes with aligned 16-byte vectors
+                    const uint32_t mis = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(dstg) & 15u);
+                    uint8_t* st = ws.stage + mis;
+                    for (uint32_t b = 0; b < maxlen; b++) if (b < len) st[myoff + b] = sp[b];
+                    __syncwarp();
+                    const uint32_t head = min(total, (16u - mis) & 15u);
+                    if (l < head) dstg[l] = st[l];
+                    const uint32_t body = (total - head) >> 4;
+                    for (uint32_t j = l; j < body; j += 32)
+                        *reinterpret_cast<uint4*>(dstg + head + 16u * j) = *reinterpret_cast<const uint4*>(st + head + 16u * j);
+                    const uint32_t done = head + 16u * body;
+                    if (l < total - done) dstg[done + l] = st[done + l];
+                    __syncwarp();
+                } else {
+                    // long strings: the whole warp copies one string at a time, 32 consecutive bytes per step
+                    const unsigned long long spl = reinterpret_cast<unsigned long long>(sp);
+                    for (int k = 0; k < 32; k++) {
+                        const uint32_t lk = __shfl_sync(0xffffffffu, len, k);
+                        if (!lk) continue;
+                        const uint8_t* sk = reinterpret_cast<const uint8_t*>(__shfl_sync(0xffffffffu, spl, k));
+                        uint8_t* dk = dstg + __shfl_sync(0xffffffffu, myoff, k);
+                        for (uint32_t b = l; b < lk; b += 32) dk[b] = sk[b];
                     }
                 }
             }
@@ -495,7 +527,7 @@ cudaError_t launch_dict_prepare(const DecodeParams& p, uint32_t n_chunks, int wi
     if (n_chunks == 0) return cudaSuccess;
     dim3 grid(width == 0 ? 1u : max_dict_blocks, n_chunks);
     switch (width) {
-        case 0: k_dict_prepare<0><<<grid, 256, 0, s>>>(p); break;
+        case 0: k_dict_prepare<0><<<grid, 1024, 0, s>>>(p); break; // strings: one 1024-thread CTA per dictionary
         case 1: k_dict_prepare<1><<<grid, 256, 0, s>>>(p); break;
         case 4: k_dict_prepare<4><<<grid, 256, 0, s>>>(p); break;
         case 8: k_dict_prepare<8><<<grid, 256, 0, s>>>(p); break;

@@ -16,6 +16,8 @@ constexpr int kIdxWords = 512;            // per-warp index scratch: 1024 x u16 
 constexpr int kTileNarrow = 1024;         // slots per tile when indices fit 16 bits
 constexpr int kTileWide = 512;
 constexpr int kMaxSmemDictBytes = 32 * 1024; // dictionaries up to this size are staged per CTA
+constexpr int kStageMaxLen = 48;          // strings up to this length go through the per-warp staging buffer
+constexpr int kStageBytes32 = 32 * kStageMaxLen + 32; // 32 strings + alignment phase (multiple of 16)
 constexpr int kImagePad = 64;             // readable bytes required past the image end
 // TMA-staged tile pipeline of the fast fixed-width kernel (pqg_tiles.cu)
 constexpr int kTileBytes = 8192;          // image bytes per tile (16-byte aligned range covering whole pages)

@@ -95,6 +95,7 @@ struct __align__(16) WarpScratch {
     uint32_t nruns;
     uint32_t batch_total;
     uint32_t pad[2];
+    uint8_t stage[kStageBytes32]; // BYTE_ARRAY copy pass: the chars of 32 short strings, flushed with aligned vectors
 };
 
 // ---- run discovery: the sequential header walk (lane 0) ------------------------------------
