@@ -567,6 +567,8 @@ static cudaError_t launch_str_t(DecodeParams p, int sm_count, cudaStream_t s) {
     const size_t smem = decode_smem_bytes(false);
     uint32_t n = p.page_end - p.page_begin;
     if (n == 0) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(k_str_pages<COPY>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
     uint32_t grid = grid_for(n, sm_count, &p.pages_per_cta, 5);
     k_str_pages<COPY><<<grid, kThreadsPerCta, smem, s>>>(p);
     return cudaGetLastError();
