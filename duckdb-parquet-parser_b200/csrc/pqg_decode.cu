@@ -65,57 +65,71 @@ __global__ void __launch_bounds__(1024) k_dict_prepare(DecodeParams P) {
     } else {
         // BYTE_ARRAY: u32 length prefix + bytes (column_reader.cpp:249-253).  Entry table:
         // {start (byte offset of the chars inside the dictionary payload), len}.
-        // Parallel: every thread scans a contiguous slice of the payload for prefix candidates
-        // (bytes +2 and +3 zero, string inside the payload), block prefix sum, ordered write,
-        // chain verification.  Falls back to one sequential walk when the check fails (entries
-        // shorter than 4 bytes, NUL-heavy binary strings, strings >= 64 KiB).
+        // The prefix chain is sequential by format; it is cut into one segment per thread:
+        //   1. every thread picks the first position of its segment that LOOKS like a prefix
+        //      eight links deep (string inside the payload, and so for its 8 successors), and
+        //      walks the chain from there to the end of its segment (count, end position);
+        //   2. one thread links the segments: a segment's start must be exactly where the
+        //      previous walk ended, otherwise the speculation failed (exactness check);
+        //   3. every thread walks its segment again and writes its entries at its base index.
+        // On any failed link (or a truncated dictionary) one thread walks the whole page like
+        // the reference does, with the reference's error reporting.
         uint2* ent = reinterpret_cast<uint2*>(dst);
-        __shared__ uint32_t s_warp[32];
-        __shared__ uint32_t s_ok, s_total;
+        constexpr uint32_t kNone = 0xffffffffu;
+        __shared__ uint32_t s_start[1024], s_end[1024], s_cnt[1024], s_base[1024];
+        __shared__ uint32_t s_ok;
         const uint32_t tid = threadIdx.x, nthr = blockDim.x;
-        bool ok_scan = size >= 4 && n > 0;
-        const uint32_t last = ok_scan ? size - 4 : 0;
-        const uint32_t per = ((last / nthr) + 4u) & ~3u;
-        const uint32_t p0 = tid * per, p1 = ok_scan ? min(p0 + per, last + 1u) : 0u;
-        auto is_cand = [&](uint32_t p, uint32_t* len_out) {
-            uint32_t v = ld32u(src + p);
-            *len_out = v;
-            return (v >> 16) == 0u && static_cast<uint64_t>(p) + 4u + v <= size;
+        auto next_of = [&](uint32_t p) -> uint32_t { // position after the string whose prefix is at p, kNone if it does not fit
+            if (static_cast<uint64_t>(p) + 4u > size) return kNone;
+            uint32_t len = ld32u(src + p);
+            uint64_t e = static_cast<uint64_t>(p) + 4u + len;
+            return e <= size ? static_cast<uint32_t>(e) : kNone;
         };
-        uint32_t cnt = 0;
-        for (uint32_t p = p0; p < p1; p++) { uint32_t ln; if (is_cand(p, &ln)) cnt++; }
-        // block exclusive scan of cnt
-        uint32_t incl = warp_incl_scan(cnt);
-        if ((tid & 31u) == 31u) s_warp[tid >> 5] = incl;
-        __syncthreads();
-        if (tid < 32) {
-            uint32_t v = tid < (nthr >> 5) ? s_warp[tid] : 0u;
-            uint32_t iv = warp_incl_scan(v);
-            s_warp[tid] = iv - v;
-            if (tid == 31) s_total = iv;
+        const uint32_t seg = max(64u, (size + nthr - 1) / nthr);
+        const uint32_t lo = tid * seg, hi = min(size, lo + seg);
+        uint32_t start = kNone, endp = kNone, cnt = 0;
+        if (lo < size && n > 0) {
+            if (tid == 0) start = 0;
+            else {
+                for (uint32_t p = lo; p < hi && start == kNone; p++) {
+                    uint32_t q = p;
+                    int depth = 0;
+                    for (; depth < 8; depth++) { q = next_of(q); if (q == kNone) break; if (q == size) { depth = 8; break; } }
+                    if (depth >= 8) start = p;
+                }
+            }
+            if (start != kNone) {
+                uint32_t p = start;
+                while (p < hi) { uint32_t q = next_of(p); if (q == kNone) break; cnt++; p = q; }
+                endp = p; // first chain position >= hi, or the position where the chain broke
+            }
         }
-        if (tid == 0) s_ok = 1;
+        s_start[tid] = start; s_end[tid] = endp; s_cnt[tid] = cnt;
         __syncthreads();
-        uint32_t w = s_warp[tid >> 5] + incl - cnt;
-        const uint32_t total = s_total;
-        if (total >= n && ok_scan) {
-            for (uint32_t p = p0; p < p1; p++) {
-                uint32_t ln;
-                if (is_cand(p, &ln)) { if (w < n) ent[w] = make_uint2(p + 4u, ln); w++; }
+        if (tid == 0) {
+            uint32_t cur = 0, base = 0, ok = n > 0 ? 1u : 0u;
+            for (uint32_t t = 0; t < nthr; t++) {
+                s_base[t] = kNone; // kNone: the segment writes nothing
+                const uint32_t tlo = t * seg, thi = min(size, tlo + seg);
+                if (!ok || base >= n || tlo >= size) continue;
+                if (cur >= thi) continue;                       // a string spans the whole segment
+                if (s_start[t] != cur) { ok = 0; continue; }    // speculation failed
+                s_base[t] = base;
+                base += s_cnt[t];
+                cur = s_end[t];
+                if (cur < thi && base < n) ok = 0;              // the chain broke before n entries: truncated page
             }
-            __syncthreads();
-            bool ok = true;
-            for (uint32_t i = tid; i < n; i += nthr) {
-                uint2 e = ent[i];
-                uint32_t want = i == 0 ? 4u : ent[i - 1].x + ent[i - 1].y + 4u;
-                if (e.x != want) ok = false;
-            }
-            if (!ok) atomicExch(&s_ok, 0u);
-            __syncthreads();
-        } else if (tid == 0) s_ok = 0;
+            if (base < n) ok = 0;
+            s_ok = ok;
+        }
         __syncthreads();
-        if (s_ok) { if (first) ck.dict_ok_n = n; }
-        else if (first) {
+        if (s_ok) {
+            if (s_base[tid] != kNone) {
+                uint32_t p = s_start[tid], k = s_base[tid];
+                while (p < hi && k < n) { uint32_t q = next_of(p); if (q == kNone) break; ent[k++] = make_uint2(p + 4u, q - p - 4u); p = q; }
+            }
+            if (first) ck.dict_ok_n = n;
+        } else if (first) {
             uint32_t pos = 0, k = 0;
             for (; k < n; k++) {
                 if (static_cast<uint64_t>(pos) + 4 > size) { report_error(P.err, ck.first_page, PQG_PAGE_DICT_TRUNCATED, pos, 4, size); break; }
