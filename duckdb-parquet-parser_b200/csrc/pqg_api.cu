@@ -432,6 +432,7 @@ static DecodeParams make_params(const pqg_plan* p) {
     P.slow_lo = 0; P.slow_hi = p->n_slow_host; P.n_slow_host = p->n_slow_host; P.slow_pages = p->d_slow_pages;
     P.chunk_lo = 0;
     P.cluster_size = p->cluster_size; P.part_shift = p->part_shift;
+    { static const uint32_t gm = [] { const char* e = std::getenv("PQG_GATHER"); return e ? static_cast<uint32_t>(std::atoi(e)) : 1u; }(); P.gather_mode = gm; } // ld.global.cg measured 2-3 % ahead
     return P;
 }
 

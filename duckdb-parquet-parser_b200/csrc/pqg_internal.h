@@ -95,6 +95,7 @@ struct DecodeParams {
     uint32_t chunk_lo;       // first chunk of this launch (dictionary preparation)
     uint32_t cluster_size;   // > 0: large dictionaries are spread over a cluster's shared memories
     uint32_t part_shift;     // log2 of the dictionary entries per CTA of the cluster
+    uint32_t gather_mode;    // cache operator of the global dictionary gather (A/B switch)
 };
 
 // launchers (pqg_decode.cu)

@@ -66,6 +66,24 @@ template <> __device__ __forceinline__ uint32_t dsmem_ld<uint32_t>(uint32_t loca
     return v;
 }
 
+// random dictionary gather from global memory; the cache operator is selectable for A/B runs
+// (PQG_GATHER=0 ld.global.nc, 1 ld.global.cg = L2 only, 2 ld.global.nc.L1::no_allocate)
+template <typename T> __device__ __forceinline__ T ldg_gather(const T* p, uint32_t mode);
+template <> __device__ __forceinline__ uint64_t ldg_gather<uint64_t>(const uint64_t* p, uint32_t mode) {
+    uint64_t v;
+    if (mode == 1) asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    else if (mode == 2) asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    else v = __ldg(reinterpret_cast<const unsigned long long*>(p));
+    return v;
+}
+template <> __device__ __forceinline__ uint32_t ldg_gather<uint32_t>(const uint32_t* p, uint32_t mode) {
+    uint32_t v;
+    if (mode == 1) asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    else if (mode == 2) asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    else v = __ldg(p);
+    return v;
+}
+
 // One warp decodes one page out of the staged tile.  `pg` = first payload byte (shared).
 template <int W, bool CLUSTER = false>
 __device__ __forceinline__ void fast_page(const DecodeParams& P, uint32_t q, const pqg_page_desc& pd, const uint8_t* pg,
@@ -99,7 +117,7 @@ __device__ __forceinline__ void fast_page(const DecodeParams& P, uint32_t q, con
     const T* dict = reinterpret_cast<const T*>(dictp);
     auto get = [&](uint32_t ix) -> T {
         if constexpr (CLUSTER) return dsmem_ld<T>(cd.base + (ix & cd.mask) * W, ix >> cd.shift);
-        else return dict_in_smem ? dict[ix] : __ldg(dict + ix);
+        else return dict_in_smem ? dict[ix] : ldg_gather<T>(dict + ix, P.gather_mode);
     };
     bool bad = false;
     uint32_t v = l;
