@@ -353,7 +353,7 @@ int pqg_plan_create(pqg_ctx* ctx, const pqg_buf* image, const pqg_chunk_desc* ch
         // MEASURED SLOWER on B200 (100 M random 8-byte gathers: 1.68 ms through
         // ld.shared::cluster with 8-CTA clusters vs 0.50 ms through L1TEX/L2, profiles/README.md),
         // so it is opt-in (PQG_CLUSTER_DICT=1) and kept for A/B measurements only.
-        if (!p->is_str && (p->width == 4 || p->width == 8) && std::getenv("PQG_CLUSTER_DICT")) {
+        if (!p->is_str && !p->any_def && (p->width == 4 || p->width == 8) && std::getenv("PQG_CLUSTER_DICT")) {
             const uint64_t dict_bytes = static_cast<uint64_t>(max_dict_n) * p->width;
             if (dict_bytes > static_cast<uint64_t>(kMaxSmemDictBytes) && dict_bytes <= 8ull * 64 * 1024) {
                 uint32_t cs = 2;

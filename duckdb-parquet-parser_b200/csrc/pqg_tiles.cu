@@ -28,6 +28,8 @@
 namespace pqg {
 namespace {
 
+constexpr int kLevelScratchBytes = kWarpsPerCta * 64 * 4; // validity image + rank bases per warp
+
 template <int W> struct FElem;
 template <> struct FElem<4> { using T = uint32_t; };
 template <> struct FElem<8> { using T = uint64_t; };
@@ -143,17 +145,103 @@ __device__ __forceinline__ void fast_page(const DecodeParams& P, uint32_t q, con
     if (__any_sync(0xffffffffu, bad) && l == 0) { to_slow(P, q); atomicAdd(&P.err->bad_index, 1u); }
 }
 
+// OPTIONAL (max_def == 1) pages: definition levels as the writer emits them -- RLE runs
+// <varint < 128><level byte> only (src/writer/parquet_writer.cpp:103-135) -- are verified and
+// expanded in parallel (one lane per run, warp prefix sum of the run lengths, bit ranges OR-ed
+// into a per-warp validity image), ranks come from popcounts, and every lane then emits one
+// slot per step: its value (PLAIN shifted load or dictionary lookup) or 0, plus the validity
+// word by ballot.  Out-of-range dictionary indices become nulls right here
+// (column_reader.cpp:190-194).  Anything else (bit-packed levels, > 1024 slots, ...) -> slow list.
+template <int W>
+__device__ __forceinline__ void fast_page_opt(const DecodeParams& P, uint32_t q, const pqg_page_desc& pd, const uint8_t* pg,
+                                              bool chunk_has_dict, const uint8_t* dictp, uint32_t dict_n, bool dict_in_smem,
+                                              uint32_t* vwords, uint32_t* rankbase) {
+    using T = typename FElem<W>::T;
+    const uint32_t l = lane_id();
+    const uint32_t n = pd.num_values, size = pd.payload_size;
+    if (n == 0) return;
+    if (n > 1024u || size < 4u) { if (l == 0) to_slow(P, q); return; }
+    const uint32_t def_len = ld32u(pg);
+    if (def_len > size - 4u || (def_len & 1u)) { if (l == 0) to_slow(P, q); return; }
+    const uint8_t* s = pg + 4;
+    const uint32_t nr = def_len >> 1;
+    vwords[l] = 0;
+    __syncwarp();
+    bool ok = true;
+    uint32_t carry = 0;
+    for (uint32_t base = 0; base < nr && carry < n; base += 32) {
+        const uint32_t r = base + l;
+        uint32_t cnt = 0, val = 0;
+        if (r < nr) { const uint32_t b = s[2 * r]; ok = ok && ((b & 0x81u) == 0u) && b != 0u; cnt = b >> 1; val = s[2 * r + 1]; }
+        const uint32_t incl = warp_incl_scan(cnt);
+        const uint32_t start = carry + incl - cnt;
+        if (cnt && start < n && val >= 1u) set_bits_range(vwords, start, min(cnt, n - start));
+        carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (!__all_sync(0xffffffffu, ok)) { if (l == 0) to_slow(P, q); return; }
+    __syncwarp();
+    const uint32_t c = __popc(vwords[l]);
+    const uint32_t incl = warp_incl_scan(c);
+    rankbase[l] = incl - c;
+    const uint32_t nn = __shfl_sync(0xffffffffu, incl, 31);
+    __syncwarp();
+    uint32_t pos = 4u + def_len;
+    const bool dict_page = (pd.flags & PQG_PAGE_FLAG_DICT) && chunk_has_dict;
+    uint32_t bw = 0;
+    const uint8_t* vals = pg + pos;
+    if (dict_page) {
+        if (pos >= size) { if (l == 0) to_slow(P, q); return; }
+        bw = pg[pos];
+        vals = pg + pos + 1;
+        if (bw > 32u || !check_regular(vals, size - pos - 1u, bw, nn)) { if (l == 0) to_slow(P, q); return; }
+    } else if (static_cast<uint64_t>(nn) * W > size - pos) { if (l == 0) to_slow(P, q); return; }
+    const T* dict = reinterpret_cast<const T*>(dictp);
+    T* out = reinterpret_cast<T*>(P.values);
+    const uint64_t abs0 = pd.out_row_base, gend = abs0 + n;
+    for (uint64_t g = abs0 & ~uint64_t(31); g < gend; g += 32) {
+        const int64_t sr = static_cast<int64_t>(g + l) - static_cast<int64_t>(abs0);
+        const bool in = sr >= 0 && sr < static_cast<int64_t>(n);
+        bool valid = false;
+        uint32_t k = 0;
+        if (in) {
+            const uint32_t wv = vwords[sr >> 5];
+            valid = (wv >> (sr & 31)) & 1u;
+            k = rankbase[sr >> 5] + __popc(wv & ((1u << (sr & 31)) - 1u));
+        }
+        T v = 0;
+        if (valid) {
+            if (dict_page) {
+                const uint32_t ix = regular_index(vals, bw, k);
+                if (ix < dict_n) v = dict_in_smem ? dict[ix] : ldg_gather<T>(dict + ix, P.gather_mode);
+                else valid = false;
+            } else {
+                v = ld_elem<W>(vals + static_cast<size_t>(k) * W);
+            }
+        }
+        if (in) st_stream<T>(out + g + l, v);
+        const uint32_t m = __ballot_sync(0xffffffffu, valid);
+        if (l == 0) {
+            if (g >= abs0 && g + 32 <= gend) P.validity[g >> 5] = m;
+            else if (m) atomicOr(&P.validity[g >> 5], m);
+        }
+    }
+    __syncwarp();
+}
+
 template <int W>
 __global__ void __launch_bounds__(kThreadsPerCta, 3) k_fixed_tiles(const DecodeParams P) {
     extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t* sdict = smem + kTilePipeBytes;
+    uint32_t* vwords = reinterpret_cast<uint32_t*>(smem + kTilePipeBytes) + warp_id() * 64; // per warp: 32 validity words + 32 rank bases
+    uint8_t* sdict = smem + kTilePipeBytes + kLevelScratchBytes;
     uint32_t dict_n = 0;
     const uint8_t* dictp = nullptr;
     bool has_dict = false, dict_in_smem = false;
+    int max_def = 0;
     tile_pipeline(P, smem,
         [&](uint32_t chunk, uint64_t* bar, uint32_t& phase) {
             const DevChunk& ck = P.chunks[chunk];
             has_dict = ck.has_dict;
+            max_def = ck.max_def;
             dict_n = ck.dict_ok_n;
             dictp = P.dict_arena + ck.dict_arena_off;
             dict_in_smem = false;
@@ -168,7 +256,8 @@ __global__ void __launch_bounds__(kThreadsPerCta, 3) k_fixed_tiles(const DecodeP
             }
         },
         [&](uint32_t q, const pqg_page_desc& pd, const uint8_t* pg) {
-            fast_page<W>(P, q, pd, pg, has_dict, dictp, dict_n, dict_in_smem);
+            if (max_def <= 0) fast_page<W>(P, q, pd, pg, has_dict, dictp, dict_n, dict_in_smem);
+            else fast_page_opt<W>(P, q, pd, pg, has_dict, dictp, dict_n, dict_in_smem, vwords, vwords + 32);
         });
 }
 
@@ -220,12 +309,12 @@ __global__ void __launch_bounds__(kThreadsPerCta, 2) k_fixed_tiles_cluster(const
 
 bool chunk_is_tileable(int phys_type, int max_def, int max_rep) {
     const bool w48 = phys_type == PQG_INT32 || phys_type == PQG_FLOAT || phys_type == PQG_INT64 || phys_type == PQG_DOUBLE;
-    return w48 && max_def <= 0 && max_rep <= 0;
+    return w48 && max_def <= 1 && max_rep <= 0;
 }
 
 template <int W>
 static cudaError_t launch_tiles_t(DecodeParams p, int sm_count, cudaStream_t s) {
-    const size_t smem = static_cast<size_t>(kTilePipeBytes) + p.dict_smem;
+    const size_t smem = static_cast<size_t>(kTilePipeBytes) + kLevelScratchBytes + p.dict_smem;
     // (attributes are per device: set on every launch, it is cheap)
     cudaError_t e = cudaFuncSetAttribute(k_fixed_tiles<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
