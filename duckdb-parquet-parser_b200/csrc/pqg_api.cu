@@ -559,6 +559,9 @@ int pqg_plan_finish(pqg_ctx* ctx, pqg_plan* p, pqg_page_error* err) {
     }
     pqg_page_error pe{};
     const DevErr& d = *p->h_err;
+    if (std::getenv("PQG_DEBUG"))
+        std::fprintf(stderr, "[pqg] plan: %zu pages, %u tiles, %u host-listed slow pages, %u handed over by the tile kernel (last sub-run), bad_index %u\n",
+                     p->pages.size(), p->n_tiles, p->n_slow_host, d.slow_count, d.bad_index);
     pe.count = d.count;
     if (d.count) {
         pe.page = static_cast<uint32_t>(d.key >> 32);

@@ -221,6 +221,7 @@ __device__ __forceinline__ void decode_fixed_page(const DecodeParams& P, uint32_
     const uint32_t dict_n = ck.dict_ok_n;
     T* out = reinterpret_cast<T*>(P.values);
     bool regular = false;
+    RegStream rs{};
     uint32_t nn_before = 0;
     for (uint32_t ts = 0; ts < c.n; ts += T_) {
         const uint32_t t = min(T_, c.n - ts);
@@ -228,7 +229,7 @@ __device__ __forceinline__ void decode_fixed_page(const DecodeParams& P, uint32_
         const uint32_t nn = levels_tile(c.defw, ws, t, ck.max_def, single, &bad);
         if (bad) { if (l == 0) report_error(P.err, q, bad); return; }
         if (dict_page) {
-            if (ts == 0 && (single || !c.has_def)) regular = check_regular(c.idxw.s, c.idxw.len, c.bw, single ? nn : c.n);
+            if (ts == 0 && (single || !c.has_def)) regular = check_regular2(c.idxw.s, c.idxw.len, c.bw, single ? nn : c.n, &rs);
             if (!regular) {
                 indices_tile(c.idxw, ws, nn, c.wide, &bad);
                 if (bad) { if (l == 0) report_error(P.err, q, bad); return; }
@@ -259,7 +260,7 @@ __device__ __forceinline__ void decode_fixed_page(const DecodeParams& P, uint32_
             T v = zero_val<W>();
             if (valid) {
                 if (dict_page) {
-                    uint32_t ix = regular ? regular_index(c.idxw.s, c.bw, nn_before + k) : idx_load(ws.idx, k, c.wide);
+                    uint32_t ix = regular ? regular_index2(rs, nn_before + k) : idx_load(ws.idx, k, c.wide);
                     if (ix < dict_n) v = reinterpret_cast<const T*>(dictp)[ix];
                     else valid = false; // out-of-range index -> null (column_reader.cpp:190-194)
                 } else if (BOOLP) {
@@ -329,6 +330,7 @@ __device__ __forceinline__ void decode_str_page(const DecodeParams& P, uint32_t 
     uint64_t page_bytes = 0;                       // running string bytes of this page
     const uint32_t page_base = COPY ? P.page_char_base[q] : 0;
     bool regular = false;
+    RegStream rs{};
     uint32_t nn_before = 0, wpos = 0;
     for (uint32_t ts = 0; ts < c.n; ts += T_) {
         const uint32_t t = min(T_, c.n - ts);
@@ -337,7 +339,7 @@ __device__ __forceinline__ void decode_str_page(const DecodeParams& P, uint32_t 
         if (bad) { if (l == 0) { report_error(P.err, q, bad); if (!COPY) P.page_chars[q] = 0; } return; }
         uint32_t tile_pos0 = wpos;
         if (c.dict) {
-            if (ts == 0 && (single || !c.has_def)) regular = check_regular(c.idxw.s, c.idxw.len, c.bw, single ? nn : c.n);
+            if (ts == 0 && (single || !c.has_def)) regular = check_regular2(c.idxw.s, c.idxw.len, c.bw, single ? nn : c.n, &rs);
             if (!regular) {
                 indices_tile(c.idxw, ws, nn, c.wide, &bad);
                 if (bad) { if (l == 0) { report_error(P.err, q, bad); if (!COPY) P.page_chars[q] = 0; } return; }
@@ -361,7 +363,7 @@ __device__ __forceinline__ void decode_str_page(const DecodeParams& P, uint32_t 
             if (c.dict) { // sum the lengths of the referenced dictionary entries
                 uint32_t sum = 0;
                 for (uint32_t k = l; k < nn; k += 32) {
-                    uint32_t ix = regular ? regular_index(c.idxw.s, c.bw, nn_before + k) : idx_load(ws.idx, k, c.wide);
+                    uint32_t ix = regular ? regular_index2(rs, nn_before + k) : idx_load(ws.idx, k, c.wide);
                     if (ix < dict_n) sum += dent[ix].y;
                 }
                 for (int d = 16; d; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
@@ -389,7 +391,7 @@ __device__ __forceinline__ void decode_str_page(const DecodeParams& P, uint32_t 
             const uint8_t* sp = nullptr; // source bytes of this lane's string
             if (valid) {
                 if (c.dict) {
-                    uint32_t ix = regular ? regular_index(c.idxw.s, c.bw, nn_before + k) : idx_load(ws.idx, k, c.wide);
+                    uint32_t ix = regular ? regular_index2(rs, nn_before + k) : idx_load(ws.idx, k, c.wide);
                     if (ix < dict_n) { uint2 e = dent[ix]; sp = dchars + e.x; len = e.y; }
                     else valid = false;
                 } else {

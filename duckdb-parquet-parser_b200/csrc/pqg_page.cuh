@@ -328,6 +328,44 @@ __device__ __forceinline__ uint32_t regular_index(const uint8_t* s, uint32_t bw,
     return ldbits(s, ((g * (1u + bw) + 1u) << 3) + (k & 7u) * bw, bw);
 }
 
+// The writer's index stream in full generality of RleBpEncoder for data without 4-fold
+// repeats (include/writer/rle_bp_encoder.hpp:49-61,93-106): floor(count / 8) single bit-packed
+// groups "03 <bw bytes>", then for the last count % 8 values EITHER one more zero-padded group OR
+// -- when the trailing values are all equal -- one RLE run "<r << 1> <ceil(bw/8) value bytes>"
+// (FinishWrite flushes a pending run of 1..3 equal values as RLE).
+struct RegStream {
+    const uint8_t* s;
+    uint32_t bw;
+    uint32_t tail_start; // first value index served by the trailing RLE run (count: none)
+    uint32_t tail_val;
+};
+__device__ __forceinline__ bool check_regular2(const uint8_t* s, uint32_t len, uint32_t bw, uint32_t count, RegStream* out) {
+    out->s = s; out->bw = bw; out->tail_start = count; out->tail_val = 0;
+    if (count == 0) return true;
+    const uint32_t G = count >> 3, r = count & 7u, gs = 1u + bw;
+    if (static_cast<uint64_t>(G) * gs > len) return false;
+    bool ok = true;
+    for (uint32_t g = lane_id(); g < G; g += 32) ok = ok && (s[g * gs] == 0x03u);
+    if (r) {
+        const uint32_t p = G * gs;
+        if (p >= len) ok = false;
+        else {
+            const uint32_t h = s[p], nb = (bw + 7u) >> 3;
+            if (h == 0x03u && p + gs <= len) { /* padded group */ }
+            else if (h == (r << 1) && p + 1u + nb <= len) {
+                uint32_t v = 0;
+                for (uint32_t i = 0; i < nb && i < 4u; i++) v |= static_cast<uint32_t>(s[p + 1u + i]) << (8u * i);
+                out->tail_start = G * 8u;
+                out->tail_val = v; // not masked, like the reference (rle_decoder.hpp:88-95)
+            } else ok = false;
+        }
+    }
+    return __all_sync(0xffffffffu, ok);
+}
+__device__ __forceinline__ uint32_t regular_index2(const RegStream& rs, uint32_t k) {
+    return k >= rs.tail_start ? rs.tail_val : regular_index(rs.s, rs.bw, k);
+}
+
 // ---- BYTE_ARRAY PLAIN: length-prefix walk -----------------------------------------------------
 // Lane 0 walks `cnt` length-prefixed strings starting at byte `pos` of the value section and
 // records each prefix position in ws.idx (u16 when !wide).  Returns the end position in *pos.

@@ -142,6 +142,7 @@ __device__ __forceinline__ bool regex_page(const RegexParams& R, const uint16_t*
     const uint32_t dict_n = ck.dict_ok_n;
     const uint8_t* dmatch = R.dict_match + ck.dict_arena_off / 8;
     bool regular = false, hit = false;
+    RegStream rs{};
     uint32_t nn_before = 0, wpos = 0;
     for (uint32_t ts = 0; ts < c.n; ts += T_) {
         const uint32_t t = min(T_, c.n - ts);
@@ -149,14 +150,14 @@ __device__ __forceinline__ bool regex_page(const RegexParams& R, const uint16_t*
         const uint32_t nn = levels_tile(c.defw, ws, t, ck.max_def, single, &bad);
         if (bad) { if (l == 0) report_error(P.err, q, bad); return false; }
         if (c.dict) {
-            if (ts == 0 && (single || !c.has_def)) regular = check_regular(c.idxw.s, c.idxw.len, c.bw, single ? nn : c.n);
+            if (ts == 0 && (single || !c.has_def)) regular = check_regular2(c.idxw.s, c.idxw.len, c.bw, single ? nn : c.n, &rs);
             if (!regular) {
                 indices_tile(c.idxw, ws, nn, c.wide, &bad);
                 if (bad) { if (l == 0) report_error(P.err, q, bad); return false; }
                 __syncwarp();
             }
             for (uint32_t k = l; k < nn; k += 32) {
-                uint32_t ix = regular ? regular_index(c.idxw.s, c.bw, nn_before + k) : idx_load(ws.idx, k, c.wide);
+                uint32_t ix = regular ? regular_index2(rs, nn_before + k) : idx_load(ws.idx, k, c.wide);
                 if (ix < dict_n && dmatch[ix]) hit = true; // out-of-range index: no value (null / dropped)
             }
         } else {
@@ -281,12 +282,13 @@ __global__ void __launch_bounds__(kThreadsPerCta, 4) k_regex_tiles(RegexParams R
             if (!slow) {
                 if ((pd.flags & PQG_PAGE_FLAG_DICT) && has_dict) {
                     const uint32_t bw = pos < size ? pg[pos] : 99u;
-                    if (bw > 32u || !check_regular(pg + pos + 1, size - pos - 1, bw, nn)) slow = true;
+                    RegStream rs;
+                    if (bw > 32u || !check_regular2(pg + pos + 1, size - pos - 1, bw, nn, &rs)) slow = true;
                     else {
                         for (uint32_t k0 = 0; k0 < nn && !hit; k0 += 32) {
                             uint32_t k = k0 + l;
                             bool h = false;
-                            if (k < nn) { uint32_t ix = regular_index(pg + pos + 1, bw, k); h = ix < dict_n && dmatch[ix]; }
+                            if (k < nn) { uint32_t ix = regular_index2(rs, k); h = ix < dict_n && dmatch[ix]; }
                             hit = __any_sync(0xffffffffu, h);
                         }
                     }

@@ -115,7 +115,8 @@ __device__ __forceinline__ void fast_page(const DecodeParams& P, uint32_t q, con
     if (size < 1) { if (l == 0) to_slow(P, q); return; }
     const uint32_t bw = pg[0];
     const uint8_t* s = pg + 1;
-    if (bw > 32 || !check_regular(s, size - 1, bw, n)) { if (l == 0) to_slow(P, q); return; }
+    RegStream rs;
+    if (bw > 32 || !check_regular2(s, size - 1, bw, n, &rs)) { if (l == 0) to_slow(P, q); return; }
     const T* dict = reinterpret_cast<const T*>(dictp);
     auto get = [&](uint32_t ix) -> T {
         if constexpr (CLUSTER) return dsmem_ld<T>(cd.base + (ix & cd.mask) * W, ix >> cd.shift);
@@ -124,8 +125,8 @@ __device__ __forceinline__ void fast_page(const DecodeParams& P, uint32_t q, con
     bool bad = false;
     uint32_t v = l;
     for (; v + 96 < n; v += 128) {
-        uint32_t i0 = regular_index(s, bw, v), i1 = regular_index(s, bw, v + 32);
-        uint32_t i2 = regular_index(s, bw, v + 64), i3 = regular_index(s, bw, v + 96);
+        uint32_t i0 = regular_index2(rs, v), i1 = regular_index2(rs, v + 32);
+        uint32_t i2 = regular_index2(rs, v + 64), i3 = regular_index2(rs, v + 96);
         bad = bad || i0 >= dict_n || i1 >= dict_n || i2 >= dict_n || i3 >= dict_n;
         T x0 = i0 < dict_n ? get(i0) : T(0);
         T x1 = i1 < dict_n ? get(i1) : T(0);
@@ -135,7 +136,7 @@ __device__ __forceinline__ void fast_page(const DecodeParams& P, uint32_t q, con
         st_stream<T>(out + v + 64, x2); st_stream<T>(out + v + 96, x3);
     }
     for (; v < n; v += 32) {
-        uint32_t i0 = regular_index(s, bw, v);
+        uint32_t i0 = regular_index2(rs, v);
         T x0 = 0;
         if (i0 < dict_n) x0 = get(i0); else bad = true;
         st_stream<T>(out + v, x0);
@@ -188,12 +189,13 @@ __device__ __forceinline__ void fast_page_opt(const DecodeParams& P, uint32_t q,
     uint32_t pos = 4u + def_len;
     const bool dict_page = (pd.flags & PQG_PAGE_FLAG_DICT) && chunk_has_dict;
     uint32_t bw = 0;
+    RegStream rs{};
     const uint8_t* vals = pg + pos;
     if (dict_page) {
         if (pos >= size) { if (l == 0) to_slow(P, q); return; }
         bw = pg[pos];
         vals = pg + pos + 1;
-        if (bw > 32u || !check_regular(vals, size - pos - 1u, bw, nn)) { if (l == 0) to_slow(P, q); return; }
+        if (bw > 32u || !check_regular2(vals, size - pos - 1u, bw, nn, &rs)) { if (l == 0) to_slow(P, q); return; }
     } else if (static_cast<uint64_t>(nn) * W > size - pos) { if (l == 0) to_slow(P, q); return; }
     const T* dict = reinterpret_cast<const T*>(dictp);
     T* out = reinterpret_cast<T*>(P.values);
@@ -211,7 +213,7 @@ __device__ __forceinline__ void fast_page_opt(const DecodeParams& P, uint32_t q,
         T v = 0;
         if (valid) {
             if (dict_page) {
-                const uint32_t ix = regular_index(vals, bw, k);
+                const uint32_t ix = regular_index2(rs, k);
                 if (ix < dict_n) v = dict_in_smem ? dict[ix] : ldg_gather<T>(dict + ix, P.gather_mode);
                 else valid = false;
             } else {
