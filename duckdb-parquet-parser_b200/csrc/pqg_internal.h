@@ -22,7 +22,8 @@ constexpr int kImagePad = 64;             // readable bytes required past the im
 // TMA-staged tile pipeline of the fast fixed-width kernel (pqg_tiles.cu)
 constexpr int kTileBytes = 8192;          // image bytes per tile (16-byte aligned range covering whole pages)
 constexpr int kTilePages = 8;             // pages per tile (one per warp)
-constexpr int kTileStages = 4;            // ring depth per CTA
+constexpr int kTileStages = 2;            // ring depth per CTA (measured: 2 x 8 KB beats 3-4 stages and 16 KB tiles: the shared-memory
+                                          // carve-out eats L1, which the large-dictionary gathers and the PLAIN copy both feel)
 
 // Device-side chunk record (built by the host API from pqg_chunk_desc).
 struct DevChunk {
