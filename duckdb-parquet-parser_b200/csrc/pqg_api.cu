@@ -44,6 +44,7 @@ struct pqg_plan {
     uint32_t dict_smem = 0;
     uint32_t max_dict_blocks = 1;
     uint32_t cluster_size = 0, part_shift = 0; // DSMEM dictionary mode (0 = off)
+    uint32_t tile_bytes = kTileBytes;
     std::vector<uint32_t> chunk_tile_begin;  // n_chunks + 1: tiles of chunk c = [begin[c], begin[c+1])
     std::vector<uint32_t> chunk_slow_begin;  // n_chunks + 1: host-listed slow pages of chunk c
     std::vector<cudaEvent_t> pipe_ev;        // pipelined path: 2 events per chunk (H2D done, decode done)
@@ -312,6 +313,9 @@ int pqg_plan_create(pqg_ctx* ctx, const pqg_buf* image, const pqg_chunk_desc* ch
     std::vector<TileDesc> tiles;
     std::vector<uint32_t> slow;
     {
+        // OPTIONAL fixed-width pages carry ~0.9 level bytes per slot: larger tiles keep 8 pages (= 8 warps) per tile
+        p->tile_bytes = (!p->is_str && p->any_def) ? kTileBytesLarge : kTileBytes;
+        const uint64_t tile_cap = p->tile_bytes;
         uint32_t max_dict_n = 0;
         for (uint32_t c = 0; c < n_chunks; c++) {
             const pqg_chunk_desc& s = chunks[c];
@@ -332,10 +336,10 @@ int pqg_plan_create(pqg_ctx* ctx, const pqg_buf* image, const pqg_chunk_desc* ch
                 const pqg_page_desc& pg = pages[q];
                 if (pg.num_values == 0) continue;
                 const uint64_t lo = pg.payload_off & ~uint64_t(15), end = pg.payload_off + pg.payload_size;
-                if (!tileable || ((end + 15) & ~uint64_t(15)) - lo > static_cast<uint64_t>(kTileBytes)) { flush(); slow.push_back(q); continue; }
+                if (!tileable || ((end + 15) & ~uint64_t(15)) - lo > tile_cap) { flush(); slow.push_back(q); continue; }
                 if (cur.n_pages) {
                     const bool fits = cur.n_pages < static_cast<uint32_t>(kTilePages) && pg.payload_off >= cur.byte_lo &&
-                                      ((end + 15) & ~uint64_t(15)) - cur.byte_lo <= static_cast<uint64_t>(kTileBytes) && q == cur.first_page + cur.n_pages;
+                                      ((end + 15) & ~uint64_t(15)) - cur.byte_lo <= tile_cap && q == cur.first_page + cur.n_pages;
                     if (!fits) flush();
                 }
                 if (!cur.n_pages) { cur.byte_lo = lo; cur.first_page = q; cur.chunk_idx = c; cur_end = end; }
@@ -431,7 +435,7 @@ static DecodeParams make_params(const pqg_plan* p) {
     P.tiles = p->d_tiles; P.tile_lo = 0; P.tile_hi = p->n_tiles; P.dict_smem = p->dict_smem;
     P.slow_lo = 0; P.slow_hi = p->n_slow_host; P.n_slow_host = p->n_slow_host; P.slow_pages = p->d_slow_pages;
     P.chunk_lo = 0;
-    P.cluster_size = p->cluster_size; P.part_shift = p->part_shift;
+    P.cluster_size = p->cluster_size; P.part_shift = p->part_shift; P.tile_bytes = p->tile_bytes;
     { static const uint32_t gm = [] { const char* e = std::getenv("PQG_GATHER"); return e ? static_cast<uint32_t>(std::atoi(e)) : 1u; }(); P.gather_mode = gm; } // ld.global.cg measured 2-3 % ahead
     return P;
 }

@@ -21,6 +21,7 @@ constexpr int kStageBytes32 = 32 * kStageMaxLen + 32; // 32 strings + alignment 
 constexpr int kImagePad = 64;             // readable bytes required past the image end
 // TMA-staged tile pipeline of the fast fixed-width kernel (pqg_tiles.cu)
 constexpr int kTileBytes = 8192;          // image bytes per tile (16-byte aligned range covering whole pages)
+constexpr int kTileBytesLarge = 16384;     // tiles of OPTIONAL fixed-width plans (level bytes make their pages ~1.8 KB: 8 pages per tile)
 constexpr int kTilePages = 8;             // pages per tile (one per warp)
 constexpr int kTileStages = 2;            // ring depth per CTA (measured: 2 x 8 KB beats 3-4 stages and 16 KB tiles: the shared-memory
                                           // carve-out eats L1, which the large-dictionary gathers and the PLAIN copy both feel)
@@ -97,6 +98,7 @@ struct DecodeParams {
     uint32_t cluster_size;   // > 0: large dictionaries are spread over a cluster's shared memories
     uint32_t part_shift;     // log2 of the dictionary entries per CTA of the cluster
     uint32_t gather_mode;    // cache operator of the global dictionary gather (A/B switch)
+    uint32_t tile_bytes;     // tile size the plan's tiles were cut for (kTileBytes / kTileBytesLarge)
 };
 
 // launchers (pqg_decode.cu)

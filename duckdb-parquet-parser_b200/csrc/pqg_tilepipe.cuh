@@ -38,18 +38,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
-constexpr int kStageBytes = kTileBytes + 16 + kTilePages * static_cast<int>(sizeof(pqg_page_desc));
+// TB = image bytes per tile (kTileBytes, or kTileBytesLarge for plans whose pages are fat)
+__host__ __device__ constexpr int tile_stage_bytes(int TB) { return TB + 16 + kTilePages * static_cast<int>(sizeof(pqg_page_desc)); }
 constexpr int kBarBytes = 64 + kTileStages * 32; // kTileStages + 1 mbarriers, then per-stage tile meta
-constexpr int kTilePipeBytes = kBarBytes + kTileStages * kStageBytes; // shared memory of the pipeline itself
+__host__ __device__ constexpr int tile_pipe_bytes(int TB) { return kBarBytes + kTileStages * tile_stage_bytes(TB); } // shared memory of the pipeline itself
+constexpr int kTilePipeBytes = tile_pipe_bytes(kTileBytes);
 
 struct TileMeta { uint64_t byte_lo; uint32_t first_page; uint32_t n_pages; uint32_t chunk_idx; uint32_t pad; };
 
-// Runs the pipeline over the CTA's tiles.  `smem` = kTilePipeBytes of 128-byte aligned shared
+// Runs the pipeline over the CTA's tiles.  `smem` = tile_pipe_bytes(TB) of 128-byte aligned shared
 // memory.  on_chunk(chunk_idx, extra_bar, phase&) is called by all threads (CTA-uniform) when
 // the chunk changes -- it may __syncthreads and stage per-chunk data with a bulk copy on
 // extra_bar.  on_page(q, pd, payload) is called by one warp per page.
-template <class OnChunk, class OnPage>
+template <int TB = kTileBytes, class OnChunk, class OnPage>
 __device__ __forceinline__ void tile_pipeline(const DecodeParams& P, uint8_t* smem, OnChunk&& on_chunk, OnPage&& on_page) {
+    constexpr int kStageBytes = tile_stage_bytes(TB);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);          // [kTileStages] tiles, [kTileStages] per-chunk staging
     TileMeta* meta = reinterpret_cast<TileMeta*>(smem + 64);     // [kTileStages]
     uint8_t* ring = smem + kBarBytes;
@@ -69,7 +72,7 @@ __device__ __forceinline__ void tile_pipeline(const DecodeParams& P, uint8_t* sm
         const uint32_t pbytes = td.n_pages * static_cast<uint32_t>(sizeof(pqg_page_desc));
         mbar_expect_tx(&full[st], td.byte_len + pbytes);
         bulk_g2s(dst, P.image + td.byte_lo, td.byte_len, &full[st]);
-        bulk_g2s(dst + kTileBytes + 16, P.pages + td.first_page, pbytes, &full[st]);
+        bulk_g2s(dst + TB + 16, P.pages + td.first_page, pbytes, &full[st]);
     };
     if (tid == 0) {
         for (uint32_t t = t0; t < min(t1, t0 + kTileStages); t++) issue(t, P.tiles[t]);
@@ -87,7 +90,7 @@ __device__ __forceinline__ void tile_pipeline(const DecodeParams& P, uint8_t* sm
             cur_chunk = tm.chunk_idx;
             on_chunk(cur_chunk, &full[kTileStages], extra_phase);
         }
-        const pqg_page_desc* pds = reinterpret_cast<const pqg_page_desc*>(tile + kTileBytes + 16);
+        const pqg_page_desc* pds = reinterpret_cast<const pqg_page_desc*>(tile + TB + 16);
         for (uint32_t j = warp_id(); j < tm.n_pages; j += kWarpsPerCta) {
             const pqg_page_desc pd = pds[j];
             on_page(tm.first_page + j, pd, tile + (pd.payload_off - tm.byte_lo));

@@ -230,16 +230,16 @@ __device__ __forceinline__ void fast_page_opt(const DecodeParams& P, uint32_t q,
     __syncwarp();
 }
 
-template <int W>
+template <int W, int TB>
 __global__ void __launch_bounds__(kThreadsPerCta, 3) k_fixed_tiles(const DecodeParams P) {
     extern __shared__ __align__(128) uint8_t smem[];
-    uint32_t* vwords = reinterpret_cast<uint32_t*>(smem + kTilePipeBytes) + warp_id() * 64; // per warp: 32 validity words + 32 rank bases
-    uint8_t* sdict = smem + kTilePipeBytes + kLevelScratchBytes;
+    uint32_t* vwords = reinterpret_cast<uint32_t*>(smem + tile_pipe_bytes(TB)) + warp_id() * 64; // per warp: 32 validity words + 32 rank bases
+    uint8_t* sdict = smem + tile_pipe_bytes(TB) + kLevelScratchBytes;
     uint32_t dict_n = 0;
     const uint8_t* dictp = nullptr;
     bool has_dict = false, dict_in_smem = false;
     int max_def = 0;
-    tile_pipeline(P, smem,
+    tile_pipeline<TB>(P, smem,
         [&](uint32_t chunk, uint64_t* bar, uint32_t& phase) {
             const DevChunk& ck = P.chunks[chunk];
             has_dict = ck.has_dict;
@@ -314,17 +314,17 @@ bool chunk_is_tileable(int phys_type, int max_def, int max_rep) {
     return w48 && max_def <= 1 && max_rep <= 0;
 }
 
-template <int W>
+template <int W, int TB>
 static cudaError_t launch_tiles_t(DecodeParams p, int sm_count, cudaStream_t s) {
-    const size_t smem = static_cast<size_t>(kTilePipeBytes) + kLevelScratchBytes + p.dict_smem;
+    const size_t smem = static_cast<size_t>(tile_pipe_bytes(TB)) + kLevelScratchBytes + p.dict_smem;
     // (attributes are per device: set on every launch, it is cheap)
-    cudaError_t e = cudaFuncSetAttribute(k_fixed_tiles<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    cudaError_t e = cudaFuncSetAttribute(k_fixed_tiles<W, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
     // contiguous tile spans per CTA (a CTA stages a chunk's dictionary once)
     int resident = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k_fixed_tiles<W>, kThreadsPerCta, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k_fixed_tiles<W, TB>, kThreadsPerCta, smem);
     const uint32_t grid = tile_grid(p.tile_hi - p.tile_lo, sm_count, resident, &p.tiles_per_cta);
-    k_fixed_tiles<W><<<grid, kThreadsPerCta, smem, s>>>(p);
+    k_fixed_tiles<W, TB><<<grid, kThreadsPerCta, smem, s>>>(p);
     return cudaGetLastError();
 }
 
@@ -366,8 +366,9 @@ cudaError_t launch_fixed_tiles_cluster(const DecodeParams& p, int width, int sm_
 
 cudaError_t launch_fixed_tiles(const DecodeParams& p, int width, int sm_count, cudaStream_t s) {
     if (p.tile_hi <= p.tile_lo) return cudaSuccess;
-    if (width == 4) return launch_tiles_t<4>(p, sm_count, s);
-    if (width == 8) return launch_tiles_t<8>(p, sm_count, s);
+    const bool large = p.tile_bytes == static_cast<uint32_t>(kTileBytesLarge);
+    if (width == 4) return large ? launch_tiles_t<4, kTileBytesLarge>(p, sm_count, s) : launch_tiles_t<4, kTileBytes>(p, sm_count, s);
+    if (width == 8) return large ? launch_tiles_t<8, kTileBytesLarge>(p, sm_count, s) : launch_tiles_t<8, kTileBytes>(p, sm_count, s);
     return cudaErrorInvalidValue;
 }
 
