@@ -166,18 +166,46 @@ __device__ __forceinline__ void fast_page_opt(const DecodeParams& P, uint32_t q,
     if (def_len > size - 4u || (def_len & 1u)) { if (l == 0) to_slow(P, q); return; }
     const uint8_t* s = pg + 4;
     const uint32_t nr = def_len >> 1;
+    // Validity image without shared-memory atomics: every run boundary where the level flips
+    // sets ONE toggle bit at the run's first slot (lanes that hit the same word are combined
+    // with match.any + redux.or, one lane writes); the levels are then the prefix XOR of the
+    // toggle bits (5 shift-xors inside a word, parity carried across words by a warp scan).
     vwords[l] = 0;
     __syncwarp();
     bool ok = true;
-    uint32_t carry = 0;
+    uint32_t carry = 0, last_lv = 0;
     for (uint32_t base = 0; base < nr && carry < n; base += 32) {
         const uint32_t r = base + l;
-        uint32_t cnt = 0, val = 0;
-        if (r < nr) { const uint32_t b = s[2 * r]; ok = ok && ((b & 0x81u) == 0u) && b != 0u; cnt = b >> 1; val = s[2 * r + 1]; }
+        uint32_t cnt = 0, lv = 0;
+        if (r < nr) { const uint32_t b = s[2 * r]; ok = ok && ((b & 0x81u) == 0u) && b != 0u; cnt = b >> 1; lv = s[2 * r + 1] >= 1u ? 1u : 0u; }
         const uint32_t incl = warp_incl_scan(cnt);
         const uint32_t start = carry + incl - cnt;
-        if (cnt && start < n && val >= 1u) set_bits_range(vwords, start, min(cnt, n - start));
+        uint32_t prev = __shfl_up_sync(0xffffffffu, lv, 1);
+        if (l == 0) prev = last_lv;
+        const bool tog = r < nr && start < n && lv != prev;
+        const uint32_t key = tog ? (start >> 5) : (0x100u + l);
+        const uint32_t grp = __match_any_sync(0xffffffffu, key);
+        const uint32_t orv = __reduce_or_sync(grp, tog ? (1u << (start & 31u)) : 0u);
+        if (tog && l == static_cast<uint32_t>(__ffs(grp) - 1)) vwords[start >> 5] ^= orv;
+        const uint32_t last_lane = min(31u, nr - 1u - base);
+        last_lv = __shfl_sync(0xffffffffu, lv, last_lane);
         carry += __shfl_sync(0xffffffffu, incl, 31);
+        __syncwarp();
+    }
+    // a stream that ends early leaves the remaining slots at level 0 (rle_decoder.hpp:21-24)
+    if (l == 0 && last_lv == 1u && carry < n) vwords[carry >> 5] ^= 1u << (carry & 31u);
+    __syncwarp();
+    {
+        uint32_t t = vwords[l];
+        const uint32_t par = __popc(t) & 1u;
+        t ^= t << 1; t ^= t << 2; t ^= t << 4; t ^= t << 8; t ^= t << 16;
+        uint32_t px = par; // inclusive xor-scan of the word parities
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, px, d); if (l >= static_cast<uint32_t>(d)) px ^= o; }
+        if ((px ^ par) & 1u) t = ~t; // odd number of toggles before this word
+        const uint32_t lo = l * 32u; // slots beyond n are not part of the page
+        t &= lo >= n ? 0u : (n - lo >= 32u ? 0xffffffffu : ((1u << (n - lo)) - 1u));
+        vwords[l] = t;
     }
     if (!__all_sync(0xffffffffu, ok)) { if (l == 0) to_slow(P, q); return; }
     __syncwarp();
