@@ -183,7 +183,7 @@ __device__ __forceinline__ void fast_page_opt(const DecodeParams& P, uint32_t q,
         uint32_t prev = __shfl_up_sync(0xffffffffu, lv, 1);
         if (l == 0) prev = last_lv;
         const bool tog = r < nr && start < n && lv != prev;
-        const uint32_t key = tog ? (start >> 5) : (0x100u + l);
+        const uint32_t key = tog ? (start >> 5) : 0xffffu; // few distinct keys: match.any costs one round per distinct value
         const uint32_t grp = __match_any_sync(0xffffffffu, key);
         const uint32_t orv = __reduce_or_sync(grp, tog ? (1u << (start & 31u)) : 0u);
         if (tog && l == static_cast<uint32_t>(__ffs(grp) - 1)) vwords[start >> 5] ^= orv;
@@ -226,33 +226,47 @@ __device__ __forceinline__ void fast_page_opt(const DecodeParams& P, uint32_t q,
         if (bw > 32u || !check_regular2(vals, size - pos - 1u, bw, nn, &rs)) { if (l == 0) to_slow(P, q); return; }
     } else if (static_cast<uint64_t>(nn) * W > size - pos) { if (l == 0) to_slow(P, q); return; }
     const T* dict = reinterpret_cast<const T*>(dictp);
-    T* out = reinterpret_cast<T*>(P.values);
-    const uint64_t abs0 = pd.out_row_base, gend = abs0 + n;
-    for (uint64_t g = abs0 & ~uint64_t(31); g < gend; g += 32) {
-        const int64_t sr = static_cast<int64_t>(g + l) - static_cast<int64_t>(abs0);
-        const bool in = sr >= 0 && sr < static_cast<int64_t>(n);
+    // emission: 32 absolute slots per step, aligned to validity words; 32-bit arithmetic only
+    const uint32_t head = static_cast<uint32_t>(pd.out_row_base & 31u); // slots of the first word owned by the previous page
+    T* outp = reinterpret_cast<T*>(P.values) + (pd.out_row_base - head);
+    uint32_t* vp = P.validity + (pd.out_row_base >> 5);
+    const uint32_t total = head + n;
+    // index stream as aligned shared-memory words
+    const uint32_t va = smem_u32(vals);
+    const SmemWords ldw{va & ~3u};
+    const uint32_t bit0 = (va & 3u) * 8u;
+    const uint32_t gs = 1u + bw, imask = bw >= 32u ? 0xffffffffu : ((1u << bw) - 1u);
+    for (uint32_t j = 0, wj = 0; j < total; j += 32, wj++) {
+        const uint32_t sl = j + l;
+        const bool in = sl >= head && sl < total;
+        const uint32_t sr = sl - head;
         bool valid = false;
         uint32_t k = 0;
         if (in) {
             const uint32_t wv = vwords[sr >> 5];
-            valid = (wv >> (sr & 31)) & 1u;
-            k = rankbase[sr >> 5] + __popc(wv & ((1u << (sr & 31)) - 1u));
+            valid = (wv >> (sr & 31u)) & 1u;
+            k = rankbase[sr >> 5] + __popc(wv & ((1u << (sr & 31u)) - 1u));
         }
         T v = 0;
         if (valid) {
             if (dict_page) {
-                const uint32_t ix = regular_index2(rs, k);
+                uint32_t ix;
+                if (k >= rs.tail_start) ix = rs.tail_val;
+                else {
+                    const uint32_t bit = bit0 + (((k >> 3) * gs + 1u) << 3) + (k & 7u) * bw;
+                    ix = __funnelshift_r(ldw(bit >> 5), ldw((bit >> 5) + 1u), bit & 31u) & imask;
+                }
                 if (ix < dict_n) v = dict_in_smem ? dict[ix] : ldg_gather<T>(dict + ix, P.gather_mode);
                 else valid = false;
             } else {
-                v = ld_elem<W>(vals + static_cast<size_t>(k) * W);
+                v = ld_elem<W>(vals + k * W);
             }
         }
-        if (in) st_stream<T>(out + g + l, v);
+        if (in) st_stream<T>(outp + sl, v);
         const uint32_t m = __ballot_sync(0xffffffffu, valid);
         if (l == 0) {
-            if (g >= abs0 && g + 32 <= gend) P.validity[g >> 5] = m;
-            else if (m) atomicOr(&P.validity[g >> 5], m);
+            if (j >= head && j + 32u <= total) vp[wj] = m;
+            else if (m) atomicOr(&vp[wj], m);
         }
     }
     __syncwarp();
