@@ -15,7 +15,7 @@
 //   * the plan's host side cuts every chunk into tiles: <= 8 consecutive pages whose bytes
 //     (page headers in between included -- pages of a chunk are contiguous in the file) fit
 //     8 KB.  One elected thread stages tile bytes + the tile's 8 page descriptors into a
-//     4-deep shared-memory ring with cp.async.bulk (1-D TMA, UBLKCP) completing on an
+//     kTileStages-deep shared-memory ring with cp.async.bulk (1-D TMA, UBLKCP) completing on an
 //     mbarrier; 8 warps decode one page each out of shared memory.  No register staging,
 //     loads stay 3 tiles ahead of the math.
 //   * a dictionary that fits (<= 32 KB of values) is staged once per chunk with the same
