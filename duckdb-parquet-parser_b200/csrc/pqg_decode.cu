@@ -425,7 +425,23 @@ __device__ __forceinline__ void decode_str_page(const DecodeParams& P, uint32_t 
                     // contiguous bytes with aligned 16-byte vectors
                     const uint32_t mis = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(dstg) & 15u);
                     uint8_t* st = ws.stage + mis;
-                    for (uint32_t b = 0; b < maxlen; b++) if (b < len) st[myoff + b] = sp[b];
+                    // all loads first (the compiler cannot prove that the staging stores do not
+                    // alias the source, and would otherwise serialise one L2 round trip per byte)
+                    uint32_t wbuf[kStageMaxLen / 4];
+                    const uint32_t nw = (len + 3u) >> 2, nwmax = (maxlen + 3u) >> 2;
+#pragma unroll
+                    for (uint32_t i = 0; i < static_cast<uint32_t>(kStageMaxLen / 4); i++)
+                        wbuf[i] = (i < nwmax && i < nw) ? ld32u(sp + 4u * i) : 0u;
+#pragma unroll
+                    for (uint32_t i = 0; i < static_cast<uint32_t>(kStageMaxLen / 4); i++) {
+                        if (i < nwmax) {
+                            const uint32_t w = wbuf[i], b = 4u * i;
+                            if (b < len) st[myoff + b] = static_cast<uint8_t>(w);
+                            if (b + 1u < len) st[myoff + b + 1u] = static_cast<uint8_t>(w >> 8);
+                            if (b + 2u < len) st[myoff + b + 2u] = static_cast<uint8_t>(w >> 16);
+                            if (b + 3u < len) st[myoff + b + 3u] = static_cast<uint8_t>(w >> 24);
+                        }
+                    }
                     __syncwarp();
                     const uint32_t head = min(total, (16u - mis) & 15u);
                     if (l < head) dstg[l] = st[l];

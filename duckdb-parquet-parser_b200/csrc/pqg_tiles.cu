@@ -272,8 +272,11 @@ __device__ __forceinline__ void fast_page_opt(const DecodeParams& P, uint32_t q,
     __syncwarp();
 }
 
-template <int W, int TB>
-__global__ void __launch_bounds__(kThreadsPerCta, 3) k_fixed_tiles(const DecodeParams P) {
+// OPT = the plan has OPTIONAL chunks.  The REQUIRED-only instantiation stays at <= 64 registers
+// (4 CTAs/SM); carrying the level code costs 8 more and a whole CTA per SM (measured: PLAIN
+// 0.262 -> 0.284 ms, dictionary bw 8 0.177 -> 0.203 ms per 100 M values).
+template <int W, int TB, bool OPT>
+__global__ void __launch_bounds__(kThreadsPerCta, OPT ? 3 : 4) k_fixed_tiles(const DecodeParams P) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint32_t* vwords = reinterpret_cast<uint32_t*>(smem + tile_pipe_bytes(TB)) + warp_id() * 64; // per warp: 32 validity words + 32 rank bases
     uint8_t* sdict = smem + tile_pipe_bytes(TB) + kLevelScratchBytes;
@@ -300,8 +303,10 @@ __global__ void __launch_bounds__(kThreadsPerCta, 3) k_fixed_tiles(const DecodeP
             }
         },
         [&](uint32_t q, const pqg_page_desc& pd, const uint8_t* pg) {
-            if (max_def <= 0) fast_page<W>(P, q, pd, pg, has_dict, dictp, dict_n, dict_in_smem);
-            else fast_page_opt<W>(P, q, pd, pg, has_dict, dictp, dict_n, dict_in_smem, vwords, vwords + 32);
+            if constexpr (OPT) {
+                if (max_def > 0) { fast_page_opt<W>(P, q, pd, pg, has_dict, dictp, dict_n, dict_in_smem, vwords, vwords + 32); return; }
+            }
+            fast_page<W>(P, q, pd, pg, has_dict, dictp, dict_n, dict_in_smem);
         });
 }
 
@@ -356,17 +361,17 @@ bool chunk_is_tileable(int phys_type, int max_def, int max_rep) {
     return w48 && max_def <= 1 && max_rep <= 0;
 }
 
-template <int W, int TB>
+template <int W, int TB, bool OPT>
 static cudaError_t launch_tiles_t(DecodeParams p, int sm_count, cudaStream_t s) {
     const size_t smem = static_cast<size_t>(tile_pipe_bytes(TB)) + kLevelScratchBytes + p.dict_smem;
     // (attributes are per device: set on every launch, it is cheap)
-    cudaError_t e = cudaFuncSetAttribute(k_fixed_tiles<W, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    cudaError_t e = cudaFuncSetAttribute(k_fixed_tiles<W, TB, OPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
     // contiguous tile spans per CTA (a CTA stages a chunk's dictionary once)
     int resident = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k_fixed_tiles<W, TB>, kThreadsPerCta, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k_fixed_tiles<W, TB, OPT>, kThreadsPerCta, smem);
     const uint32_t grid = tile_grid(p.tile_hi - p.tile_lo, sm_count, resident, &p.tiles_per_cta);
-    k_fixed_tiles<W, TB><<<grid, kThreadsPerCta, smem, s>>>(p);
+    k_fixed_tiles<W, TB, OPT><<<grid, kThreadsPerCta, smem, s>>>(p);
     return cudaGetLastError();
 }
 
@@ -408,9 +413,10 @@ cudaError_t launch_fixed_tiles_cluster(const DecodeParams& p, int width, int sm_
 
 cudaError_t launch_fixed_tiles(const DecodeParams& p, int width, int sm_count, cudaStream_t s) {
     if (p.tile_hi <= p.tile_lo) return cudaSuccess;
-    const bool large = p.tile_bytes == static_cast<uint32_t>(kTileBytesLarge);
-    if (width == 4) return large ? launch_tiles_t<4, kTileBytesLarge>(p, sm_count, s) : launch_tiles_t<4, kTileBytes>(p, sm_count, s);
-    if (width == 8) return large ? launch_tiles_t<8, kTileBytesLarge>(p, sm_count, s) : launch_tiles_t<8, kTileBytes>(p, sm_count, s);
+    // plans with OPTIONAL chunks: 16 KB tiles + the level code; REQUIRED-only plans: the lean kernel
+    const bool opt = p.tile_bytes == static_cast<uint32_t>(kTileBytesLarge);
+    if (width == 4) return opt ? launch_tiles_t<4, kTileBytesLarge, true>(p, sm_count, s) : launch_tiles_t<4, kTileBytes, false>(p, sm_count, s);
+    if (width == 8) return opt ? launch_tiles_t<8, kTileBytesLarge, true>(p, sm_count, s) : launch_tiles_t<8, kTileBytes, false>(p, sm_count, s);
     return cudaErrorInvalidValue;
 }
 

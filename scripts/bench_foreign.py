@@ -1,0 +1,48 @@
+"""Decode throughput on pyarrow-written files (uncompressed, data page v1): INT64 PLAIN and
+dictionary columns with 64 KB and 1 MB pages -- the pages exceed the 8 KB tiles, so they run
+through the general kernel (one warp per page).  usage: python scripts/bench_foreign.py [rows]"""
+import json
+import os
+import sys
+import tempfile
+
+import numpy as np
+import pyarrow as pa
+import pyarrow.parquet as pqa
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import pqb200 as pq
+
+rows = int(sys.argv[1]) if len(sys.argv) > 1 else 10_000_000
+rng = np.random.default_rng(2)
+t = pa.table({"plain": pa.array(rng.integers(-2**60, 2**60, size=rows), type=pa.int64()),
+              "dict": pa.array(rng.integers(0, 4096, size=rows) * 977, type=pa.int64())})
+out = []
+for page in (8 * 1024, 64 * 1024, 1 << 20):
+    with tempfile.TemporaryDirectory() as d:
+        p = os.path.join(d, "f.parquet")
+        pqa.write_table(t, p, compression="NONE", data_page_version="1.0", write_statistics=False, data_page_size=page,
+                        row_group_size=rows // 4, use_dictionary=["dict"])
+        img = np.fromfile(p, dtype=np.uint8)
+    r = pq.Reader(data=img)
+    ctx = pq.Context(0)
+    buf = ctx.upload(img.ctypes.data, img.size)
+    ctx.set_profiling(True)
+    for c in range(2):
+        plan = ctx.plan(buf, r.column_tables(c, -1))
+        for _ in range(4):
+            plan.run()
+            plan.finish()
+        tm = plan.timings_avg(3)
+        vals = np.zeros(rows, dtype=np.int64)
+        plan.download(values=vals.ctypes.data)
+        ctx.sync()
+        assert np.array_equal(vals, t.column(c).to_numpy()), (page, c)
+        out.append({"page_bytes": page, "column": t.column_names[c], "pages": r.column_tables(c, -1)[3], "ms": tm["total_ms"],
+                    "tiles_ms": tm["fixed_ms"], "general_ms": tm["general_ms"],
+                    "in_plus_out_GBps": (plan.bytes_in + plan.bytes_out) / tm["total_ms"] / 1e6})
+        plan.destroy()
+    ctx.buf_free(buf)
+    ctx.close()
+    r.close()
+print(json.dumps({"rows": rows, "results": out}, indent=1))
