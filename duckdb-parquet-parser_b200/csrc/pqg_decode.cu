@@ -308,6 +308,22 @@ __global__ void __launch_bounds__(kThreadsPerCta) k_decode_fixed(DecodeParams P)
 // ---------------------------------------------------------------------------------------------
 // BYTE_ARRAY
 // ---------------------------------------------------------------------------------------------
+// copy one string of at most 4 * NW bytes: NW unaligned word loads, then byte stores
+template <int NW>
+__device__ __forceinline__ void stage_string(uint8_t* dst, const uint8_t* sp, uint32_t len) {
+    uint32_t wbuf[NW];
+#pragma unroll
+    for (int i = 0; i < NW; i++) wbuf[i] = 4u * i < len ? ld32u(sp + 4 * i) : 0u;
+#pragma unroll
+    for (int i = 0; i < NW; i++) {
+        const uint32_t w = wbuf[i], b = 4u * i;
+        if (b < len) dst[b] = static_cast<uint8_t>(w);
+        if (b + 1u < len) dst[b + 1u] = static_cast<uint8_t>(w >> 8);
+        if (b + 2u < len) dst[b + 2u] = static_cast<uint8_t>(w >> 16);
+        if (b + 3u < len) dst[b + 3u] = static_cast<uint8_t>(w >> 24);
+    }
+}
+
 template <bool COPY>
 __device__ __forceinline__ void decode_str_page(const DecodeParams& P, uint32_t q, const DevChunk& ck, WarpScratch& ws) {
     const uint32_t l = lane_id();
@@ -426,22 +442,11 @@ __device__ __forceinline__ void decode_str_page(const DecodeParams& P, uint32_t 
                     const uint32_t mis = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(dstg) & 15u);
                     uint8_t* st = ws.stage + mis;
                     // all loads first (the compiler cannot prove that the staging stores do not
-                    // alias the source, and would otherwise serialise one L2 round trip per byte)
-                    uint32_t wbuf[kStageMaxLen / 4];
-                    const uint32_t nw = (len + 3u) >> 2, nwmax = (maxlen + 3u) >> 2;
-#pragma unroll
-                    for (uint32_t i = 0; i < static_cast<uint32_t>(kStageMaxLen / 4); i++)
-                        wbuf[i] = (i < nwmax && i < nw) ? ld32u(sp + 4u * i) : 0u;
-#pragma unroll
-                    for (uint32_t i = 0; i < static_cast<uint32_t>(kStageMaxLen / 4); i++) {
-                        if (i < nwmax) {
-                            const uint32_t w = wbuf[i], b = 4u * i;
-                            if (b < len) st[myoff + b] = static_cast<uint8_t>(w);
-                            if (b + 1u < len) st[myoff + b + 1u] = static_cast<uint8_t>(w >> 8);
-                            if (b + 2u < len) st[myoff + b + 2u] = static_cast<uint8_t>(w >> 16);
-                            if (b + 3u < len) st[myoff + b + 3u] = static_cast<uint8_t>(w >> 24);
-                        }
-                    }
+                    // alias the source, and would otherwise serialise one L2 round trip per byte);
+                    // unrolled for the warp's longest string: 4, 8 or 12 words
+                    if (maxlen <= 16u) stage_string<4>(st + myoff, sp, len);
+                    else if (maxlen <= 32u) stage_string<8>(st + myoff, sp, len);
+                    else stage_string<kStageMaxLen / 4>(st + myoff, sp, len);
                     __syncwarp();
                     const uint32_t head = min(total, (16u - mis) & 15u);
                     if (l < head) dstg[l] = st[l];
