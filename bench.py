@@ -48,6 +48,17 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# stdout carries exactly ONE line: the JSON result.  Libraries (NCCL prints its version banner
+# on stdout, ...) are redirected to stderr by pointing fd 1 at fd 2 for the whole run.
+_REAL_STDOUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line):
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
+
 # ── workload ────────────────────────────────────────────────────────────────────────────
 def cfg2_specs():
     I64, F64, REQ = 2, 5, 0
@@ -341,7 +352,7 @@ def main():
                 "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["threads"], "kind": "reference", "sample": r["sample"]},
                 "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line), flush=True)
+        emit(line)
         return 0
 
     import torch
@@ -520,7 +531,7 @@ def main():
         except Exception as e:
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": cores, "kind": "reference", "sample": f"unavailable: {e}"}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -115,6 +115,14 @@ int pqg_ctx_create(int device, void* stream, pqg_ctx** out) {
         return fail(nullptr, PQG_ERR_CUDA, "pqg_ctx_create: this build targets sm_100a (Blackwell B200) only");
     }
     c->sm_count = prop.multiProcessorCount;
+    { // scratch of the scan / chunk-index calls comes from the stream-ordered pool: keep freed blocks cached
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t keep = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    }
     if (stream) { c->stream = static_cast<cudaStream_t>(stream); c->own_stream = false; }
     else {
         e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);

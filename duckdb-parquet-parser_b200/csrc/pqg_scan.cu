@@ -537,12 +537,14 @@ __global__ void k_chunk_row_bases(const DevChunk* chunks, uint32_t n_chunks, uin
     if (i == n_chunks) out[i] = n_slots;
 }
 
-struct DevMem { // frees on scope exit
+struct DevMem { // stream-ordered scratch (the device's memory pool keeps freed blocks); frees on scope exit
+    cudaStream_t stream = nullptr;
     std::vector<void*> ptrs;
-    ~DevMem() { for (void* p : ptrs) cudaFree(p); }
+    explicit DevMem(cudaStream_t s) : stream(s) {}
+    ~DevMem() { for (void* p : ptrs) cudaFreeAsync(p, stream); }
     template <class T> cudaError_t alloc(T** out, size_t count) {
         void* p = nullptr;
-        cudaError_t e = cudaMalloc(&p, std::max<size_t>(count * sizeof(T), 16));
+        cudaError_t e = cudaMallocAsync(&p, std::max<size_t>(count * sizeof(T), 16), stream);
         if (e == cudaSuccess) { ptrs.push_back(p); *out = static_cast<T*>(p); }
         return e;
     }
@@ -685,7 +687,7 @@ int pqg_regex_scan(pqg_ctx* ctx, pqg_plan* plan, const pqg_dfa* dfa, int neg, ui
     }
     std::memcpy(blob.data() + table_bytes, d.cls, 256);
     std::memcpy(blob.data() + table_bytes + 256, d.accept.data(), d.n_states);
-    DevMem mem;
+    DevMem mem(s);
     uint8_t* d_blob = nullptr; uint8_t* d_dmatch = nullptr; uint32_t* d_bits = nullptr;
     CUF(ctx, mem.alloc(&d_blob, blob.size() + 16));
     CUF(ctx, mem.alloc(&d_dmatch, plan_dict_arena_bytes(plan) / 8 + 16));
@@ -760,7 +762,7 @@ int pqg_chunk_index(pqg_ctx* ctx, pqg_plan* plan, uint64_t chunk_size, uint64_t 
     cudaStream_t s = ctx_stream(ctx);
     DecodeParams P = plan_params(plan);
     const uint64_t n = plan_slots(plan);
-    DevMem mem;
+    DevMem mem(s);
     uint64_t* d_rb = nullptr; uint32_t* d_ids = nullptr;
     CUF(ctx, mem.alloc(&d_rb, P.n_chunks + 2));
     CUF(ctx, mem.alloc(&d_ids, n + 1));
@@ -794,7 +796,7 @@ int pqg_page_chunk_index(pqg_ctx* ctx, const uint32_t* page_sizes, uint32_t n_pa
     if (n_pages == 0) return PQG_OK;
     CUF(ctx, cudaSetDevice(ctx_device(ctx)));
     cudaStream_t s = ctx_stream(ctx);
-    DevMem mem;
+    DevMem mem(s);
     uint32_t* d_w = nullptr; uint32_t* d_ids = nullptr; uint32_t* d_off = nullptr; uint32_t* d_first = nullptr;
     CUF(ctx, mem.alloc(&d_w, n_pages));
     CUF(ctx, mem.alloc(&d_ids, n_pages));

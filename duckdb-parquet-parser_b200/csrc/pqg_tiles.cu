@@ -38,6 +38,14 @@ template <int W> __device__ __forceinline__ typename FElem<W>::T ld_elem(const u
 template <> __device__ __forceinline__ uint32_t ld_elem<4>(const uint8_t* p) { return ld32u(p); }
 template <> __device__ __forceinline__ uint64_t ld_elem<8>(const uint8_t* p) { return ld64u(p); }
 
+template <typename T> __device__ __forceinline__ T lds_elem(uint32_t saddr);
+template <> __device__ __forceinline__ uint32_t lds_elem<uint32_t>(uint32_t saddr) {
+    uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr)); return v;
+}
+template <> __device__ __forceinline__ uint64_t lds_elem<uint64_t>(uint32_t saddr) {
+    uint64_t v; asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(saddr)); return v;
+}
+
 template <typename T> __device__ __forceinline__ void st_stream(T* p, T v);
 template <> __device__ __forceinline__ void st_stream<uint32_t>(uint32_t* p, uint32_t v) { __stcs(p, v); }
 template <> __device__ __forceinline__ void st_stream<uint64_t>(uint64_t* p, uint64_t v) {
@@ -118,15 +126,27 @@ __device__ __forceinline__ void fast_page(const DecodeParams& P, uint32_t q, con
     RegStream rs;
     if (bw > 32 || !check_regular2(s, size - 1, bw, n, &rs)) { if (l == 0) to_slow(P, q); return; }
     const T* dict = reinterpret_cast<const T*>(dictp);
+    const uint32_t dict_s = dict_in_smem ? smem_u32(dictp) : 0u;
     auto get = [&](uint32_t ix) -> T {
         if constexpr (CLUSTER) return dsmem_ld<T>(cd.base + (ix & cd.mask) * W, ix >> cd.shift);
-        else return dict_in_smem ? dict[ix] : ldg_gather<T>(dict + ix, P.gather_mode);
+        else return dict_in_smem ? lds_elem<T>(dict_s + ix * W) : ldg_gather<T>(dict + ix, P.gather_mode);
+    };
+    // index bits straight from aligned shared-memory words; value v sits in group v >> 3 at
+    // bit ((v >> 3) * (1 + bw) + 1) * 8 + (v & 7) * bw of the stream: +32 values = +4 groups
+    const uint32_t sa = smem_u32(s);
+    const SmemWords ldw{sa & ~3u};
+    const uint32_t gs = 1u + bw, imask = bw >= 32u ? 0xffffffffu : ((1u << bw) - 1u);
+    uint32_t bit = (sa & 3u) * 8u + (((l >> 3) * gs + 1u) << 3) + (l & 7u) * bw;
+    const uint32_t step32 = 32u * gs;
+    auto index_at = [&](uint32_t bitpos, uint32_t k) -> uint32_t {
+        const uint32_t ix = __funnelshift_r(ldw(bitpos >> 5), ldw((bitpos >> 5) + 1u), bitpos & 31u) & imask;
+        return k >= rs.tail_start ? rs.tail_val : ix;
     };
     bool bad = false;
     uint32_t v = l;
-    for (; v + 96 < n; v += 128) {
-        uint32_t i0 = regular_index2(rs, v), i1 = regular_index2(rs, v + 32);
-        uint32_t i2 = regular_index2(rs, v + 64), i3 = regular_index2(rs, v + 96);
+    for (; v + 96 < n; v += 128, bit += 4u * step32) {
+        const uint32_t i0 = index_at(bit, v), i1 = index_at(bit + step32, v + 32);
+        const uint32_t i2 = index_at(bit + 2u * step32, v + 64), i3 = index_at(bit + 3u * step32, v + 96);
         bad = bad || i0 >= dict_n || i1 >= dict_n || i2 >= dict_n || i3 >= dict_n;
         T x0 = i0 < dict_n ? get(i0) : T(0);
         T x1 = i1 < dict_n ? get(i1) : T(0);
@@ -135,8 +155,8 @@ __device__ __forceinline__ void fast_page(const DecodeParams& P, uint32_t q, con
         st_stream<T>(out + v, x0); st_stream<T>(out + v + 32, x1);
         st_stream<T>(out + v + 64, x2); st_stream<T>(out + v + 96, x3);
     }
-    for (; v < n; v += 32) {
-        uint32_t i0 = regular_index2(rs, v);
+    for (; v < n; v += 32, bit += step32) {
+        const uint32_t i0 = index_at(bit, v);
         T x0 = 0;
         if (i0 < dict_n) x0 = get(i0); else bad = true;
         st_stream<T>(out + v, x0);

@@ -182,3 +182,41 @@ def test_read_columns_into_pipelined_matches_read_column(pq, files):
         pad[:, :w] = v[: nr * w].reshape(nr, w)
         assert np.array_equal(pad.view(np.uint64).reshape(nr)[~exp["is_null"].astype(bool)], exp["fixed"][~exp["is_null"].astype(bool)])
         r.close()
+
+
+def test_config1_full_size_against_the_reference(pq, oracle, tmp_path):
+    """BASELINE.json configs[0] at full size: 1 M rows, INT32 REQUIRED PLAIN `id` + OPTIONAL
+    BYTE_ARRAY `city` (8 names, 30 % nulls).  File from the workload generator (byte-identical to
+    the reference writer, tests/test_gen_cpu.py); expected values from the UNMODIFIED reference
+    where oracle/_ref is present, else from the oracle."""
+    import fixtures
+    import oraclelib
+    from oraclelib import BYTE_ARRAY as BA, INT32, OPTIONAL, REQUIRED, UTF8
+    n = 1_000_000
+    rng = np.random.default_rng(42)
+    idx = rng.integers(0, len(fixtures.CITIES), size=n)
+    lens = np.array([len(c) for c in fixtures.CITIES], dtype=np.uint64)[idx]
+    off = np.zeros(n + 1, dtype=np.uint64)
+    np.cumsum(lens, out=off[1:])
+    chars = np.frombuffer(b"".join(fixtures.CITIES[i] for i in idx), dtype=np.uint8)
+    isn = (rng.integers(0, 10, size=n) < 3).astype(np.uint8)
+    specs = [("id", INT32, REQUIRED, -1), ("city", BA, OPTIONAL, UTF8)]
+    g = pq.generate(specs, [dict(fixed=np.arange(n, dtype=np.int32)), dict(str_off=off, chars=chars, is_null=isn)], [n])
+    path = g.write(str(tmp_path / "cfg1.parquet"))
+    g.free()
+    r = pq.Reader(path)
+    src = oraclelib.Ref() if oraclelib.Ref.available() else oracle
+    h = src.open(path)
+    try:
+        # page geometry of SURVEY.md 8(d) "Config 1": 3907 PLAIN pages of 256 values, 977 dictionary data pages of 1024
+        assert r.num_pages == 3907 + 977
+        for name in ("id", "city"):
+            got = to_values(r.read_column(name))
+            d = got.diff(src.read_column(h, name))
+            assert d is None, (name, d)
+        t2c, nch = r.chunk_index("city", 4096)
+        e2c, ench = src.chunk_index(h, "city", 4096)
+        assert nch == ench and np.array_equal(t2c, e2c)
+    finally:
+        src.close(h)
+        r.close()
