@@ -50,13 +50,21 @@ def log(*a):
 
 # stdout carries exactly ONE line: the JSON result.  Libraries (NCCL prints its version banner
 # on stdout, ...) are redirected to stderr by pointing fd 1 at fd 2 for the whole run.
-_REAL_STDOUT = os.fdopen(os.dup(1), "w")
-os.dup2(2, 1)
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """called first thing in main() (not at import: scripts/ reuse this module's workloads)"""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
 
 
 def emit(line):
-    _REAL_STDOUT.write(json.dumps(line) + "\n")
-    _REAL_STDOUT.flush()
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 # ── workload ────────────────────────────────────────────────────────────────────────────
@@ -316,6 +324,7 @@ def cpu_reference_run(pq, cols, rows, rg_rows, sample_rgs, steps, warmup, thread
 
 # ── GPU arm ─────────────────────────────────────────────────────────────────────────────
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
