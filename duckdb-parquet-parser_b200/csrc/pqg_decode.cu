@@ -486,7 +486,7 @@ __device__ __forceinline__ void decode_str_page(const DecodeParams& P, uint32_t 
 }
 
 template <bool COPY>
-__global__ void __launch_bounds__(kThreadsPerCta) k_str_pages(DecodeParams P) {
+__global__ void __launch_bounds__(kThreadsPerCta, 3) k_str_pages(DecodeParams P) {
     extern __shared__ __align__(16) uint8_t smem[];
     WarpScratch& ws = reinterpret_cast<WarpScratch*>(smem)[warp_id()];
     uint32_t p = P.page_begin + blockIdx.x * P.pages_per_cta;
