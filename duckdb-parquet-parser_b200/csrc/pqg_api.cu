@@ -511,8 +511,6 @@ int pqg_plan_run(pqg_ctx* ctx, pqg_plan* p) {
             launches++;
         }
         if (prof) CU(ctx, cudaEventRecord(p->ev[1], s));
-        // pages without values are in no tile: their byte count must read 0 in the scans
-        CU(ctx, cudaMemsetAsync(p->d_page_chars, 0, (static_cast<size_t>(P.page_end) + 1) * 4, s));
         if (P.page_end) { CU(ctx, launch_str_sizes(P, ctx->sm_count, s)); launches++; }
         CU(ctx, launch_str_scan(P, p->d_bases, s));
         launches += 2;

@@ -13,7 +13,7 @@
 //
 // Grid sizing: CTAs take contiguous spans of the page table (so a CTA stages a chunk's
 // dictionary once); the grid is a multiple of the SM count when there is enough work.
-#include "pqg_tilepipe.cuh"
+#include "pqg_page.cuh"
 
 namespace pqg {
 namespace {
@@ -289,7 +289,7 @@ __device__ __forceinline__ void decode_fixed_page(const DecodeParams& P, uint32_
 // kernel for the rest) through a work-stealing cursor.
 template <int W, bool BOOLP>
 __global__ void __launch_bounds__(kThreadsPerCta) k_decode_fixed(DecodeParams P) {
-    extern __shared__ __align__(128) uint8_t smem[];
+    extern __shared__ __align__(16) uint8_t smem[];
     WarpScratch& ws = reinterpret_cast<WarpScratch*>(smem)[warp_id()];
     const uint32_t n_host = P.slow_hi - P.slow_lo;
     const uint32_t total = n_host + P.err->slow_count;
@@ -325,12 +325,12 @@ __device__ __forceinline__ void stage_string(uint8_t* dst, const uint8_t* sp, ui
 }
 
 template <bool COPY>
-__device__ __forceinline__ void decode_str_page(const DecodeParams& P, uint32_t q, const pqg_page_desc& pd, const DevChunk& ck,
-                                                WarpScratch& ws, const uint8_t* staged = nullptr) {
+__device__ __forceinline__ void decode_str_page(const DecodeParams& P, uint32_t q, const DevChunk& ck, WarpScratch& ws) {
     const uint32_t l = lane_id();
+    const pqg_page_desc pd = P.pages[q];
     if (pd.num_values == 0) { if (!COPY && l == 0) P.page_chars[q] = 0; return; }
     PageCtx c;
-    if (!page_begin(P, q, pd, ck, ws, c, staged)) { if (!COPY && l == 0) P.page_chars[q] = 0; return; }
+    if (!page_begin(P, q, pd, ck, ws, c)) { if (!COPY && l == 0) P.page_chars[q] = 0; return; }
     const uint8_t* vals = c.pg + c.vals_pos;
     const uint32_t vavail = c.size - c.vals_pos;
     // plain pages keep prefix positions in ws.idx: u16 unless the page is large
@@ -366,13 +366,7 @@ __device__ __forceinline__ void decode_str_page(const DecodeParams& P, uint32_t 
             bool found = false;
             if (single && !wide) {
                 uint32_t endp = 0;
-                if (staged) { // shared memory: explicit ld.shared word loads
-                    const uint32_t va = smem_u32(vals);
-                    found = find_headers_w(SmemWords{va & ~3u}, va & 3u, vavail, nn, reinterpret_cast<uint16_t*>(ws.idx),
-                                           static_cast<uint32_t>(kIdxWords) * 2u, &endp);
-                } else {
-                    found = find_headers(vals, vavail, nn, reinterpret_cast<uint16_t*>(ws.idx), static_cast<uint32_t>(kIdxWords) * 2u, &endp);
-                }
+                found = find_headers(vals, vavail, nn, reinterpret_cast<uint16_t*>(ws.idx), static_cast<uint32_t>(kIdxWords) * 2u, &endp);
                 if (found) wpos = endp;
             }
             uint32_t epos = 0, eneed = 0;
@@ -491,32 +485,16 @@ __device__ __forceinline__ void decode_str_page(const DecodeParams& P, uint32_t 
     }
 }
 
-// pages that do not fit a tile (host-listed): one warp per page, payload staged per warp or read in place
 template <bool COPY>
 __global__ void __launch_bounds__(kThreadsPerCta, 3) k_str_pages(DecodeParams P) {
-    extern __shared__ __align__(128) uint8_t smem[];
+    extern __shared__ __align__(16) uint8_t smem[];
     WarpScratch& ws = reinterpret_cast<WarpScratch*>(smem)[warp_id()];
-    const uint32_t n = P.slow_hi - P.slow_lo;
-    for (uint32_t i = blockIdx.x * kWarpsPerCta + warp_id(); i < n; i += gridDim.x * kWarpsPerCta) {
-        const uint32_t q = P.slow_pages[P.slow_lo + i];
-        const pqg_page_desc pd = P.pages[q];
-        decode_str_page<COPY>(P, q, pd, P.chunks[pd.chunk_idx], ws);
-        __syncwarp();
+    uint32_t p = P.page_begin + blockIdx.x * P.pages_per_cta;
+    const uint32_t p1 = min(P.page_end, p + P.pages_per_cta);
+    for (uint32_t q = p + warp_id(); q < p1; q += kWarpsPerCta) {
+        const DevChunk& ck = P.chunks[P.pages[q].chunk_idx];
+        decode_str_page<COPY>(P, q, ck, ws);
     }
-}
-
-// the common case: pages staged by the TMA tile pipeline, one warp per page
-template <bool COPY>
-__global__ void __launch_bounds__(kThreadsPerCta, 3) k_str_tiles(DecodeParams P) {
-    extern __shared__ __align__(128) uint8_t smem[];
-    WarpScratch& ws = *reinterpret_cast<WarpScratch*>(smem + kTilePipeBytes + warp_id() * kWarpScratchNoSlot);
-    const DevChunk* ck = nullptr;
-    tile_pipeline(P, smem,
-        [&](uint32_t chunk, uint64_t*, uint32_t&) { ck = &P.chunks[chunk]; },
-        [&](uint32_t q, const pqg_page_desc& pd, const uint8_t* pg) {
-            decode_str_page<COPY>(P, q, pd, *ck, ws, pg);
-            __syncwarp();
-        });
 }
 
 // per chunk: exclusive scan of page_chars over the chunk's pages; chunk total -> char_base (temp)
@@ -567,6 +545,14 @@ __global__ void k_str_scan_chunks(DecodeParams P, uint64_t* chunk_bases, uint64_
     }
 }
 
+uint32_t grid_for(uint32_t n_pages, int sm_count, uint32_t* pages_per_cta, int ctas_per_sm) {
+    // contiguous spans; aim for ctas_per_sm * SMs CTAs, at least one page per warp and step
+    uint32_t target = static_cast<uint32_t>(sm_count) * ctas_per_sm * 4u;
+    uint32_t per = (n_pages + target - 1) / target;
+    if (per < kWarpsPerCta) per = kWarpsPerCta;
+    *pages_per_cta = per;
+    return (n_pages + per - 1) / per;
+}
 
 } // namespace
 
@@ -615,29 +601,14 @@ cudaError_t launch_decode_fixed(const DecodeParams& p, int width, bool boolean_p
 
 template <bool COPY>
 static cudaError_t launch_str_t(DecodeParams p, int sm_count, cudaStream_t s) {
-    if (p.tile_hi > p.tile_lo) {
-        const size_t smem = static_cast<size_t>(kTilePipeBytes) + static_cast<size_t>(kWarpsPerCta) * kWarpScratchNoSlot;
-        cudaError_t e = cudaFuncSetAttribute(k_str_tiles<COPY>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        if (e != cudaSuccess) return e;
-        int resident = 1;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k_str_tiles<COPY>, kThreadsPerCta, smem);
-        const uint32_t grid = tile_grid(p.tile_hi - p.tile_lo, sm_count, resident, &p.tiles_per_cta);
-        k_str_tiles<COPY><<<grid, kThreadsPerCta, smem, s>>>(p);
-        e = cudaGetLastError();
-        if (e != cudaSuccess) return e;
-    }
-    if (p.slow_hi > p.slow_lo) {
-        const size_t smem = decode_smem_bytes(false);
-        cudaError_t e = cudaFuncSetAttribute(k_str_pages<COPY>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        if (e != cudaSuccess) return e;
-        const uint32_t n = p.slow_hi - p.slow_lo;
-        uint32_t grid = (n + kWarpsPerCta - 1) / kWarpsPerCta;
-        const uint32_t cap = static_cast<uint32_t>(sm_count) * 12u;
-        if (grid > cap) grid = cap;
-        k_str_pages<COPY><<<grid, kThreadsPerCta, smem, s>>>(p);
-        return cudaGetLastError();
-    }
-    return cudaSuccess;
+    const size_t smem = decode_smem_bytes(false);
+    uint32_t n = p.page_end - p.page_begin;
+    if (n == 0) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(k_str_pages<COPY>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    uint32_t grid = grid_for(n, sm_count, &p.pages_per_cta, 5);
+    k_str_pages<COPY><<<grid, kThreadsPerCta, smem, s>>>(p);
+    return cudaGetLastError();
 }
 cudaError_t launch_str_sizes(const DecodeParams& p, int sm_count, cudaStream_t s) { return launch_str_t<false>(p, sm_count, s); }
 cudaError_t launch_str_copy(const DecodeParams& p, int sm_count, cudaStream_t s) { return launch_str_t<true>(p, sm_count, s); }

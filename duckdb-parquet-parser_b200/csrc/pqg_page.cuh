@@ -13,8 +13,6 @@
 //   run expansion  -> one lane per run (long RLE runs: whole warp),
 //   slot emission  -> one lane per output slot, 32 slots per step, coalesced stores.
 #pragma once
-#include <cstddef>
-
 #include "pqg_internal.h"
 
 namespace pqg {
@@ -87,6 +85,7 @@ __device__ __forceinline__ void report_error(DevErr* e, uint32_t page, uint32_t 
 
 // ---- per-warp scratch ----------------------------------------------------------------------
 struct __align__(16) WarpScratch {
+    uint8_t slot[kSlotAlloc];
     uint32_t idx[kIdxWords];
     uint32_t valid[32];
     uint32_t rankbase[32];
@@ -97,10 +96,7 @@ struct __align__(16) WarpScratch {
     uint32_t batch_total;
     uint32_t pad[2];
     uint8_t stage[kStageBytes32]; // BYTE_ARRAY copy pass: the chars of 32 short strings, flushed with aligned vectors
-    uint8_t slot[kSlotAlloc];     // LAST: kernels fed by the tile pipeline allocate the struct without it
 };
-constexpr int kWarpScratchNoSlot = (static_cast<int>(offsetof(WarpScratch, slot)) + 15) & ~15;
-
 
 // ---- run discovery: the sequential header walk (lane 0) ------------------------------------
 struct Walker {
@@ -530,16 +526,14 @@ struct PageCtx {
 // Stage the payload and parse [def levels][rep levels][bit width] like read_data_page
 // (column_reader.cpp:143-182).  Returns false (after reporting) when the page is unusable.
 __device__ __forceinline__ bool page_begin(const DecodeParams& P, uint32_t q, const pqg_page_desc& pd,
-                                           const DevChunk& ck, WarpScratch& ws, PageCtx& c, const uint8_t* staged = nullptr) {
+                                           const DevChunk& ck, WarpScratch& ws, PageCtx& c) {
     const uint32_t l = lane_id();
     c.size = pd.payload_size;
     c.n = pd.num_values;
     c.dict = (pd.flags & PQG_PAGE_FLAG_DICT) && ck.has_dict;
     c.has_def = ck.max_def > 0;
     const uint8_t* src = P.image + pd.payload_off;
-    if (staged) { // the tile pipeline already brought the payload into shared memory
-        c.pg = staged;
-    } else if (c.size <= static_cast<uint32_t>(kSlotBytes)) {
+    if (c.size <= static_cast<uint32_t>(kSlotBytes)) {
         uint32_t shift = static_cast<uint32_t>(pd.payload_off & 15u);
         const uint8_t* a = src - shift;
         uint32_t nvec = (shift + c.size + 15u) >> 4;
