@@ -33,6 +33,8 @@ struct pqg_plan {
     const pqg_buf* image = nullptr;
     std::vector<pqg_chunk_desc> chunks;
     std::vector<pqg_page_desc> pages;
+    std::vector<pqg_page_desc> virt_pages;   // device page table = pages + virt_pages (slices of oversized PLAIN pages)
+    std::vector<uint32_t> virt_parent;       // page-table index each virtual page was cut from
     DevChunk* d_chunks = nullptr;
     pqg_page_desc* d_pages = nullptr;
     uint8_t* d_dict = nullptr;
@@ -340,11 +342,8 @@ int pqg_plan_create(pqg_ctx* ctx, const pqg_buf* image, const pqg_chunk_desc* ch
             TileDesc cur{};
             uint64_t cur_end = 0;
             auto flush = [&]() { if (cur.n_pages) { cur.byte_len = static_cast<uint32_t>(((cur_end + 15) & ~uint64_t(15)) - cur.byte_lo); tiles.push_back(cur); cur = TileDesc{}; } };
-            for (uint32_t q = s.first_page; q < s.first_page + s.n_pages; q++) {
-                const pqg_page_desc& pg = pages[q];
-                if (pg.num_values == 0) continue;
+            auto place = [&](uint32_t q, const pqg_page_desc& pg) { // q: device page-table index
                 const uint64_t lo = pg.payload_off & ~uint64_t(15), end = pg.payload_off + pg.payload_size;
-                if (!tileable || ((end + 15) & ~uint64_t(15)) - lo > tile_cap) { flush(); slow.push_back(q); continue; }
                 if (cur.n_pages) {
                     const bool fits = cur.n_pages < static_cast<uint32_t>(kTilePages) && pg.payload_off >= cur.byte_lo &&
                                       ((end + 15) & ~uint64_t(15)) - cur.byte_lo <= tile_cap && q == cur.first_page + cur.n_pages;
@@ -353,6 +352,33 @@ int pqg_plan_create(pqg_ctx* ctx, const pqg_buf* image, const pqg_chunk_desc* ch
                 if (!cur.n_pages) { cur.byte_lo = lo; cur.first_page = q; cur.chunk_idx = c; cur_end = end; }
                 cur.n_pages++;
                 cur_end = std::max(cur_end, end);
+            };
+            for (uint32_t q = s.first_page; q < s.first_page + s.n_pages; q++) {
+                const pqg_page_desc& pg = pages[q];
+                if (pg.num_values == 0) continue;
+                const uint64_t lo = pg.payload_off & ~uint64_t(15), end = pg.payload_off + pg.payload_size;
+                const bool too_big = ((end + 15) & ~uint64_t(15)) - lo > tile_cap;
+                if (tileable && too_big && !p->is_str && s.max_def <= 0 && !((pg.flags & PQG_PAGE_FLAG_DICT) && s.has_dict)) {
+                    // an oversized PLAIN REQUIRED page (foreign writers: 64 KB .. 1 MB) is the
+                    // concatenation of smaller ones: cut it into 1 KB virtual pages, 8 per tile
+                    const uint32_t W = static_cast<uint32_t>(p->width), sub_vals = 1024u / W;
+                    uint32_t remaining = pg.num_values, size_left = pg.payload_size;
+                    uint64_t off = pg.payload_off, row = pg.out_row_base;
+                    while (remaining) {
+                        const uint32_t nv = std::min(remaining, sub_vals);
+                        uint32_t bytes = std::min(size_left, nv * W); // a truncated page shows up in its last slices
+                        pqg_page_desc v = pg;
+                        v.payload_off = off; v.out_row_base = row; v.payload_size = bytes; v.num_values = nv;
+                        const uint32_t vq = n_pages + static_cast<uint32_t>(p->virt_pages.size());
+                        p->virt_pages.push_back(v);
+                        p->virt_parent.push_back(q);
+                        place(vq, v);
+                        off += bytes; size_left -= bytes; row += nv; remaining -= nv;
+                    }
+                    continue;
+                }
+                if (!tileable || too_big) { flush(); slow.push_back(q); continue; }
+                place(q, pg);
             }
             flush();
         }
@@ -382,10 +408,10 @@ int pqg_plan_create(pqg_ctx* ctx, const pqg_buf* image, const pqg_chunk_desc* ch
     cudaError_t e;
 #define PA(ptr, bytes) if ((e = alloc(reinterpret_cast<void**>(&(ptr)), (bytes))) != cudaSuccess) { pqg_plan_destroy(ctx, p); return cuda_fail(ctx, e, "cudaMalloc(plan)"); }
     PA(p->d_chunks, sizeof(DevChunk) * n_chunks);
-    PA(p->d_pages, sizeof(pqg_page_desc) * std::max<uint32_t>(n_pages, 1));
+    PA(p->d_pages, sizeof(pqg_page_desc) * std::max<size_t>(static_cast<size_t>(n_pages) + p->virt_pages.size(), 1));
     PA(p->d_err, sizeof(DevErr));
     if (p->any_dict) PA(p->d_dict, arena + 64);
-    PA(p->d_slow_pages, sizeof(uint32_t) * (static_cast<size_t>(n_pages) + 1));
+    PA(p->d_slow_pages, sizeof(uint32_t) * (static_cast<size_t>(n_pages) + p->virt_pages.size() + 1));
     PA(p->d_tiles, sizeof(TileDesc) * std::max<size_t>(tiles.size(), 1));
     if (p->any_def) PA(p->d_validity, ((slots + 31) / 32 + 1) * 4);
     if (p->is_str) {
@@ -408,6 +434,8 @@ int pqg_plan_create(pqg_ctx* ctx, const pqg_buf* image, const pqg_chunk_desc* ch
     e = cudaMemcpyAsync(p->d_chunks, dc.data(), sizeof(DevChunk) * n_chunks, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess && n_pages)
         e = cudaMemcpyAsync(p->d_pages, p->pages.data(), sizeof(pqg_page_desc) * n_pages, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && !p->virt_pages.empty())
+        e = cudaMemcpyAsync(p->d_pages + n_pages, p->virt_pages.data(), sizeof(pqg_page_desc) * p->virt_pages.size(), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess && !tiles.empty())
         e = cudaMemcpyAsync(p->d_tiles, tiles.data(), sizeof(TileDesc) * tiles.size(), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess && !slow.empty())
@@ -577,8 +605,11 @@ int pqg_plan_finish(pqg_ctx* ctx, pqg_plan* p, pqg_page_error* err) {
     pe.count = d.count;
     if (d.count) {
         pe.page = static_cast<uint32_t>(d.key >> 32);
+        const uint32_t raw_page = pe.page;
+        if (pe.page >= p->pages.size() && pe.page - p->pages.size() < p->virt_parent.size())
+            pe.page = p->virt_parent[pe.page - p->pages.size()]; // a slice of an oversized page: report the page
         pe.code = static_cast<uint32_t>(d.key & 0xffffffffu);
-        if (d.d_page == pe.page) { pe.pos = d.d_pos; pe.need = d.d_need; pe.size = d.d_size; }
+        if (d.d_page == raw_page) { pe.pos = d.d_pos; pe.need = d.d_need; pe.size = d.d_size; }
     }
     if (err) *err = pe;
     if (pe.count) {

@@ -219,3 +219,22 @@ def test_short_streams_zero_fill_like_the_reference(pq, oracle):
     vals, _, _ = b.run()
     dec = oracle.rle_decode_i32(np.frombuffer(stream, dtype=np.uint8), 3, 20)
     assert np.array_equal(vals, dict_vals[dec])
+
+
+def test_oversized_plain_pages_are_split_and_errors_name_the_page(pq):
+    """a 100 KB PLAIN REQUIRED page (foreign writers) runs as 1 KB virtual slices on the tile
+    kernel; a truncated one still reports the ORIGINAL page index"""
+    rng = np.random.default_rng(9)
+    big = rng.integers(-2**62, 2**62, size=12_345, dtype=np.int64)
+    small = rng.integers(-2**62, 2**62, size=100, dtype=np.int64)
+    b = Builder(pq, None)
+    b.add_page(small.tobytes(), len(small), dict_page=False, misalign=3)
+    b.add_page(big.tobytes(), len(big), dict_page=False, misalign=5)
+    b.add_page(small.tobytes(), len(small), dict_page=False, misalign=1)
+    vals, _, _ = b.run()
+    assert np.array_equal(vals, np.concatenate([small, big, small]))
+    b = Builder(pq, None)
+    b.add_page(small.tobytes(), len(small), dict_page=False)
+    b.add_page(big.tobytes()[:-8], len(big), dict_page=False)  # one value short
+    _, _, msg = b.run(expect_error=(1, 1))
+    assert "ByteBuffer: read beyond end" in msg
