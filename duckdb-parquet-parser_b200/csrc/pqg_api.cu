@@ -508,8 +508,21 @@ static int fixed_subrun(pqg_ctx* ctx, pqg_plan* p, uint32_t c0, uint32_t c1, boo
         } else { e = launch_fixed_tiles(P, p->width, ctx->sm_count, s); launches++; }
     }
     if (e == cudaSuccess && ev_tiles_end) e = cudaEventRecord(ev_tiles_end, s);
-    // the general kernel takes the host-listed pages plus whatever the tile kernel handed over
-    if (e == cudaSuccess && (P.slow_hi > P.slow_lo || P.tile_hi > P.tile_lo)) { e = launch_decode_fixed(P, p->width, p->is_bool, ctx->sm_count, s); launches++; }
+    // host-listed pages (oversized, or of chunks the tile kernel does not take) of 4/8-byte plans:
+    // one CTA per page first; what that kernel cannot take joins the slow list
+    bool host_list_taken = false;
+    if (e == cudaSuccess && P.slow_hi > P.slow_lo && !p->is_bool && (p->width == 4 || p->width == 8)) {
+        e = launch_big_pages(P, p->width, ctx->sm_count, s);
+        launches++;
+        host_list_taken = true;
+    }
+    // the general kernel takes what is left of the host list plus whatever the other kernels handed over
+    if (e == cudaSuccess && (P.slow_hi > P.slow_lo || P.tile_hi > P.tile_lo)) {
+        DecodeParams Pg = P;
+        if (host_list_taken) Pg.slow_hi = Pg.slow_lo;
+        e = launch_decode_fixed(Pg, p->width, p->is_bool, ctx->sm_count, s);
+        launches++;
+    }
     *err = e;
     return e == cudaSuccess ? launches : -1;
 }

@@ -1,0 +1,233 @@
+// pqg_bigpage.cu -- oversized fixed-width pages: one CTA per page.
+//
+// Foreign writers (pyarrow, DuckDB, ...) emit 64 KB .. 1 MB data pages with tens of thousands
+// of values; the reference's own writer never does (include/writer/parquet_writer.hpp:35).
+// One warp per page, as the general kernel works, leaves such files with a few hundred warps
+// of work.  Here the whole CTA takes the page (reference semantics: read_data_page,
+// src/reader/column_reader.cpp:140-225):
+//   * definition levels: handled when the page has none, or when the first RLE run covers
+//     the whole page with the maximum level (a column without nulls in this page -- what
+//     nullable-by-default writers produce most of the time);
+//   * PLAIN values: CTA-wide shifted 16-byte vector copy;
+//   * dictionary indices: the RLE / bit-packed hybrid stream is staged through shared memory
+//     in 48 KB chunks; ONE thread walks the run headers of the chunk into a run table
+//     (start value, kind, bit offset or value) -- the run-boundary scan -- and all threads
+//     expand the runs in parallel (binary search of the value's run, bit extraction,
+//     dictionary gather, coalesced stores).
+// Pages this kernel does not take (nulls present, nested levels, bit width > 32, bad runs,
+// out-of-range indices, truncation) are handed to the general kernel through the slow list,
+// which also does all error reporting.
+#include "pqg_page.cuh"
+
+namespace pqg {
+namespace {
+
+constexpr int kBigThreads = 256;
+constexpr int kBigChunk = 48 * 1024;   // staged stream bytes per step
+constexpr int kBigRuns = 1024;         // run-table entries per step
+
+template <int W> struct BElem;
+template <> struct BElem<4> { using T = uint32_t; };
+template <> struct BElem<8> { using T = uint64_t; };
+template <int W> __device__ __forceinline__ typename BElem<W>::T ld_val(const uint8_t* p);
+template <> __device__ __forceinline__ uint32_t ld_val<4>(const uint8_t* p) { return ld32u(p); }
+template <> __device__ __forceinline__ uint64_t ld_val<8>(const uint8_t* p) { return ld64u(p); }
+
+struct BigSmem {
+    uint32_t run_first[kBigRuns + 1]; // first value index of run r (run_first[n_runs] = end)
+    uint32_t run_data[kBigRuns];      // literal: bit offset inside the staged chunk; RLE: the value
+    uint8_t run_lit[kBigRuns];
+    uint32_t n_runs, next_pos, next_val, status; // status: 0 ok, 1 hand the page over
+    uint32_t flag;
+    __align__(16) uint8_t chunk[kBigChunk + 32];
+};
+
+__device__ __forceinline__ void hand_over(const DecodeParams& P, uint32_t q) {
+    uint32_t k = atomicAdd(&P.err->slow_count, 1u);
+    P.slow_pages[P.n_slow_host + k] = q;
+}
+
+template <int W>
+__global__ void __launch_bounds__(kBigThreads) k_big_pages(const DecodeParams P) {
+    using T = typename BElem<W>::T;
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    BigSmem& S = *reinterpret_cast<BigSmem*>(smem_raw);
+    const uint32_t tid = threadIdx.x;
+    const uint32_t n_host = P.slow_hi - P.slow_lo;
+    for (uint32_t it = blockIdx.x; it < n_host; it += gridDim.x) {
+        const uint32_t q = P.slow_pages[P.slow_lo + it];
+        const pqg_page_desc pd = P.pages[q];
+        const DevChunk& ck = P.chunks[pd.chunk_idx];
+        const uint32_t n = pd.num_values, size = pd.payload_size;
+        if (n == 0) continue;
+        const uint8_t* pg = P.image + pd.payload_off;
+        __syncthreads();
+        // ---- levels: none, or one RLE run of the maximum level covering the page ----
+        if (tid == 0) {
+            uint32_t st = 0, pos = 0;
+            if (ck.max_rep > 0 || ck.max_def > 1) st = 1;
+            else if (ck.max_def == 1) {
+                if (size < 4) st = 1;
+                else {
+                    const uint32_t def_len = ld32u(pg);
+                    if (def_len > size - 4 || def_len < 2) st = 1;
+                    else {
+                        uint32_t ind = 0, shift = 0, p = 4;
+                        while (p < 4 + def_len) { uint32_t b = pg[p++]; if (shift < 32) ind |= (b & 0x7Fu) << shift; if (!(b & 0x80u)) break; shift += 7; }
+                        if ((ind & 1u) || (ind >> 1) < n || p >= 4 + def_len || pg[p] != 1u) st = 1; // not "all present"
+                        pos = 4 + def_len;
+                    }
+                }
+            }
+            S.status = st; S.next_pos = pos;
+        }
+        __syncthreads();
+        if (S.status) { if (tid == 0) hand_over(P, q); continue; }
+        uint32_t pos = S.next_pos;
+        const bool dict_page = (pd.flags & PQG_PAGE_FLAG_DICT) && ck.has_dict;
+        T* out = reinterpret_cast<T*>(P.values) + pd.out_row_base;
+        bool ok = true;
+        if (!dict_page) {
+            // ---- PLAIN: shifted copy, 16-byte vectors once the destination is aligned ----
+            if (static_cast<uint64_t>(n) * W > size - pos) { if (tid == 0) hand_over(P, q); continue; }
+            const uint8_t* src = pg + pos;
+            const uint64_t bytes = static_cast<uint64_t>(n) * W;
+            uint8_t* dst = reinterpret_cast<uint8_t*>(out);
+            uint32_t head = static_cast<uint32_t>((16u - (reinterpret_cast<uintptr_t>(dst) & 15u)) & 15u);
+            if (head > bytes) head = static_cast<uint32_t>(bytes);
+            if (tid < head / W) out[tid] = ld_val<W>(src + tid * W);
+            const uint8_t* s2 = src + head;
+            uint8_t* d2 = dst + head;
+            const uint32_t nvec = static_cast<uint32_t>((bytes - head) >> 4);
+            const uint32_t sh = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(s2) & 15u);
+            const uint8_t* a = s2 - sh;
+            const uint32_t bs = (sh & 3u) * 8u, ws = sh >> 2;
+            for (uint32_t j = tid; j < nvec; j += kBigThreads) {
+                const uint4 v0 = ldg_nc16(a + 16u * j);
+                uint4 r = v0;
+                if (sh) {
+                    const uint4 v1 = ldg_nc16(a + 16u * j + 16);
+                    const uint32_t w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+                    r.x = __funnelshift_r(w[ws], w[ws + 1], bs); r.y = __funnelshift_r(w[ws + 1], w[ws + 2], bs);
+                    r.z = __funnelshift_r(w[ws + 2], w[ws + 3], bs); r.w = __funnelshift_r(w[ws + 3], w[ws + 4], bs);
+                }
+                __stcs(reinterpret_cast<uint4*>(d2) + j, r);
+            }
+            const uint32_t done = head + (nvec << 4);
+            const uint32_t tail = static_cast<uint32_t>(bytes - done) / W;
+            if (tid < tail) reinterpret_cast<T*>(dst + done)[tid] = ld_val<W>(src + done + tid * W);
+        } else {
+            // ---- dictionary indices: staged chunks, run table by one thread, parallel expansion ----
+            if (pos >= size) { if (tid == 0) hand_over(P, q); continue; }
+            const uint32_t bw = pg[pos];
+            pos++;
+            if (bw > 32) { if (tid == 0) hand_over(P, q); continue; }
+            const uint8_t* stream = pg + pos;
+            const uint32_t slen = size - pos;
+            const T* dict = reinterpret_cast<const T*>(P.dict_arena + ck.dict_arena_off);
+            const uint32_t dict_n = ck.dict_ok_n;
+            const uint32_t nb = (bw + 7u) >> 3;
+            uint32_t spos = 0, vdone = 0; // stream position of the next run header, values decoded so far
+            while (vdone < n && ok) {
+                // stage [spos, spos + kBigChunk) of the stream
+                const uint32_t take = min(static_cast<uint32_t>(kBigChunk), slen - min(slen, spos));
+                {
+                    const uint8_t* g = stream + spos;
+                    const uint32_t mis = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(g) & 15u);
+                    // chunk[] keeps the 16-byte phase of the source: byte i of the stream slice sits at chunk[mis + i]
+                    const uint32_t nvec = (mis + take + 15u) >> 4;
+                    for (uint32_t j = tid; j < nvec; j += kBigThreads)
+                        reinterpret_cast<uint4*>(S.chunk)[j] = ldg_nc16(g - mis + 16u * j);
+                    if (tid == 0) S.flag = mis;
+                }
+                __syncthreads();
+                const uint8_t* cb = S.chunk + S.flag;
+                if (tid == 0) {
+                    // run-boundary scan of the chunk (RleDecoder::next_counts, rle_decoder.hpp:37-53)
+                    uint32_t p = 0, v = vdone, r = 0, st = 0;
+                    while (r < static_cast<uint32_t>(kBigRuns) && v < n) {
+                        if (spos + p >= slen) { // stream exhausted: the remaining values read as index 0 (:21-24)
+                            S.run_first[r] = v; S.run_data[r] = 0; S.run_lit[r] = 0; r++; v = n; break;
+                        }
+                        uint32_t ind = 0, shift = 0, hp = p;
+                        bool complete = false;
+                        while (hp < take) { uint32_t b = cb[hp++]; if (shift < 32) ind |= (b & 0x7Fu) << shift; if (!(b & 0x80u)) { complete = true; break; } shift += 7; }
+                        if (!complete) break; // header continues in the next chunk (or the stream is cut: next staging decides)
+                        if (ind & 1u) {
+                            const uint64_t cnt = static_cast<uint64_t>(ind >> 1) * 8u;
+                            const uint64_t dbytes = (cnt * bw + 7u) >> 3;
+                            if (cnt == 0) { st = 1; break; }
+                            if (hp + dbytes > take) { if (p == 0) st = 1; break; } // does not fit this chunk: restage from this header
+                            S.run_first[r] = v; S.run_data[r] = hp * 8u; S.run_lit[r] = 1; r++;
+                            v += cnt < static_cast<uint64_t>(n - v) ? static_cast<uint32_t>(cnt) : (n - v);
+                            p = hp + static_cast<uint32_t>(dbytes);
+                        } else {
+                            const uint32_t cnt = ind >> 1;
+                            if (cnt == 0) { st = 1; break; }
+                            if (hp + nb > take) { if (p == 0) st = 1; break; }
+                            uint32_t val = 0;
+                            for (uint32_t i = 0; i < nb && i < 4u; i++) val |= static_cast<uint32_t>(cb[hp + i]) << (8u * i);
+                            S.run_first[r] = v; S.run_data[r] = val; S.run_lit[r] = 0; r++;
+                            v += min(cnt, n - v);
+                            p = hp + nb;
+                        }
+                    }
+                    if (r == 0 && st == 0) st = 1; // no progress (a header cut by the end of the page): general kernel
+                    S.run_first[r] = v;
+                    S.n_runs = r; S.next_pos = spos + p; S.next_val = v; S.status = st;
+                }
+                __syncthreads();
+                if (S.status) { ok = false; break; }
+                const uint32_t nr = S.n_runs, vend = S.next_val;
+                const uint32_t imask = bw >= 32u ? 0xffffffffu : ((1u << bw) - 1u);
+                for (uint32_t v = vdone + tid; v < vend; v += kBigThreads) {
+                    uint32_t lo = 0, hi = nr; // run with run_first[r] <= v < run_first[r + 1]
+                    while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (S.run_first[mid] <= v) lo = mid; else hi = mid; }
+                    uint32_t ix;
+                    if (S.run_lit[lo]) ix = ldbits(cb, S.run_data[lo] + (v - S.run_first[lo]) * bw, bw) & imask;
+                    else ix = S.run_data[lo];
+                    T x = 0;
+                    if (ix < dict_n) x = __ldg(dict + ix); else ok = false; // NULL in the reference: general kernel redoes the page
+                    __stcs(out + v, x);
+                }
+                ok = __syncthreads_and(ok);
+                vdone = vend;
+                spos = S.next_pos;
+            }
+            if (!ok) { if (tid == 0) hand_over(P, q); continue; }
+        }
+        // ---- validity: every slot of the page is present ----
+        if (P.validity && ck.max_def > 0) {
+            const uint64_t a0 = pd.out_row_base, a1 = a0 + n;
+            const uint64_t w0 = a0 >> 5, w1 = (a1 - 1) >> 5;
+            for (uint64_t w = w0 + tid; w <= w1; w += kBigThreads) {
+                uint32_t m = 0xffffffffu;
+                if (w == w0) m &= ~0u << (a0 & 31u);
+                if (w == w1 && (a1 & 31u)) m &= (1u << (a1 & 31u)) - 1u;
+                if (m == 0xffffffffu) P.validity[w] = m; else atomicOr(&P.validity[w], m);
+            }
+        }
+    }
+}
+
+} // namespace
+
+cudaError_t launch_big_pages(const DecodeParams& p, int width, int sm_count, cudaStream_t s) {
+    const uint32_t n = p.slow_hi - p.slow_lo;
+    if (n == 0) return cudaSuccess;
+    const size_t smem = sizeof(BigSmem);
+    const uint32_t grid = n < static_cast<uint32_t>(sm_count) * 4u ? n : static_cast<uint32_t>(sm_count) * 4u;
+    cudaError_t e;
+    if (width == 4) {
+        e = cudaFuncSetAttribute(k_big_pages<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e != cudaSuccess) return e;
+        k_big_pages<4><<<grid, kBigThreads, smem, s>>>(p);
+    } else if (width == 8) {
+        e = cudaFuncSetAttribute(k_big_pages<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e != cudaSuccess) return e;
+        k_big_pages<8><<<grid, kBigThreads, smem, s>>>(p);
+    } else return cudaErrorInvalidValue;
+    return cudaGetLastError();
+}
+
+} // namespace pqg

@@ -108,6 +108,8 @@ cudaError_t launch_decode_fixed(const DecodeParams& p, int width, bool boolean_p
 cudaError_t launch_fixed_tiles(const DecodeParams& p, int width, int sm_count, cudaStream_t s);
 cudaError_t launch_fixed_tiles_cluster(const DecodeParams& p, int width, int sm_count, cudaStream_t s); // one chunk per launch
 bool chunk_is_tileable(int phys_type, int max_def, int max_rep);
+// oversized pages of 4/8-byte plans: one CTA per page (pqg_bigpage.cu); what it cannot take goes to the slow list
+cudaError_t launch_big_pages(const DecodeParams& p, int width, int sm_count, cudaStream_t s);
 cudaError_t launch_str_sizes(const DecodeParams& p, int sm_count, cudaStream_t s);
 cudaError_t launch_str_scan(const DecodeParams& p, uint64_t* total_chars, cudaStream_t s);
 cudaError_t launch_str_copy(const DecodeParams& p, int sm_count, cudaStream_t s);
