@@ -96,17 +96,17 @@ template <> __device__ __forceinline__ uint32_t ldg_gather<uint32_t>(const uint3
 
 // One warp decodes one page out of the staged tile.  `pg` = first payload byte (shared).
 template <int W, bool CLUSTER = false>
-__device__ __forceinline__ void fast_page(const DecodeParams& P, uint32_t q, const pqg_page_desc& pd, const uint8_t* pg,
+__device__ __forceinline__ bool fast_page(const DecodeParams& P, uint32_t q, const pqg_page_desc& pd, const uint8_t* pg,
                                           bool chunk_has_dict, const uint8_t* dictp, uint32_t dict_n, bool dict_in_smem,
                                           ClusterDict cd = ClusterDict{0, 0, 0}) {
     using T = typename FElem<W>::T;
     const uint32_t l = lane_id();
     const uint32_t n = pd.num_values, size = pd.payload_size;
-    if (n == 0) return;
+    if (n == 0) return true;
     T* out = reinterpret_cast<T*>(P.values) + pd.out_row_base;
     if (!((pd.flags & PQG_PAGE_FLAG_DICT) && chunk_has_dict)) {
         // PLAIN: read_plain_value per slot == a shifted copy
-        if (static_cast<uint64_t>(n) * W > size) { if (l == 0) to_slow(P, q); return; }
+        if (static_cast<uint64_t>(n) * W > size) { if (l == 0) to_slow(P, q); return false; }
         uint32_t e = l;
         for (; e + 96 < n; e += 128) {
             T v0 = ld_elem<W>(pg + static_cast<size_t>(e) * W);
@@ -117,14 +117,14 @@ __device__ __forceinline__ void fast_page(const DecodeParams& P, uint32_t q, con
             st_stream<T>(out + e + 64, v2); st_stream<T>(out + e + 96, v3);
         }
         for (; e < n; e += 32) st_stream<T>(out + e, ld_elem<W>(pg + static_cast<size_t>(e) * W));
-        return;
+        return true;
     }
     // dictionary indices: u8 bit width, then the RLE / bit-packed hybrid stream
-    if (size < 1) { if (l == 0) to_slow(P, q); return; }
+    if (size < 1) { if (l == 0) to_slow(P, q); return false; }
     const uint32_t bw = pg[0];
     const uint8_t* s = pg + 1;
     RegStream rs;
-    if (bw > 32 || !check_regular2(s, size - 1, bw, n, &rs)) { if (l == 0) to_slow(P, q); return; }
+    if (bw > 32 || !check_regular2(s, size - 1, bw, n, &rs)) { if (l == 0) to_slow(P, q); return false; }
     const T* dict = reinterpret_cast<const T*>(dictp);
     const uint32_t dict_s = dict_in_smem ? smem_u32(dictp) : 0u;
     auto get = [&](uint32_t ix) -> T {
@@ -163,7 +163,9 @@ __device__ __forceinline__ void fast_page(const DecodeParams& P, uint32_t q, con
     }
     // an out-of-range index is a NULL in the reference (column_reader.cpp:190-194): the
     // general kernel redoes the page with the validity semantics
-    if (__any_sync(0xffffffffu, bad) && l == 0) { to_slow(P, q); atomicAdd(&P.err->bad_index, 1u); }
+    const bool any_bad = __any_sync(0xffffffffu, bad);
+    if (any_bad && l == 0) { to_slow(P, q); atomicAdd(&P.err->bad_index, 1u); }
+    return !any_bad;
 }
 
 // OPTIONAL (max_def == 1) pages: definition levels as the writer emits them -- RLE runs
@@ -181,9 +183,30 @@ __device__ __forceinline__ void fast_page_opt(const DecodeParams& P, uint32_t q,
     const uint32_t l = lane_id();
     const uint32_t n = pd.num_values, size = pd.payload_size;
     if (n == 0) return;
-    if (n > 1024u || size < 4u) { if (l == 0) to_slow(P, q); return; }
+    if (size < 4u) { if (l == 0) to_slow(P, q); return; }
     const uint32_t def_len = ld32u(pg);
-    if (def_len > size - 4u || (def_len & 1u)) { if (l == 0) to_slow(P, q); return; }
+    if (def_len > size - 4u) { if (l == 0) to_slow(P, q); return; }
+    // a page without nulls (nullable-by-default writers): ONE RLE run of level 1 covering all
+    // n slots -- decode it as a REQUIRED page and set its validity range
+    if (def_len >= 2u) {
+        uint32_t ind = 0, shift = 0, hp = 0;
+        while (hp < def_len) { const uint32_t b = pg[4u + hp++]; if (shift < 32) ind |= (b & 0x7Fu) << shift; if (!(b & 0x80u)) break; shift += 7; }
+        if (!(ind & 1u) && (ind >> 1) >= n && hp < def_len && pg[4u + hp] == 1u) {
+            pqg_page_desc pv = pd;
+            pv.payload_size = size - 4u - def_len;
+            if (!fast_page<W>(P, q, pv, pg + 4u + def_len, chunk_has_dict, dictp, dict_n, dict_in_smem)) return; // the general kernel redoes it
+            const uint64_t a0 = pd.out_row_base, a1 = a0 + n;
+            const uint64_t w0 = a0 >> 5, w1 = (a1 - 1) >> 5;
+            for (uint64_t w = w0 + l; w <= w1; w += 32) {
+                uint32_t m = 0xffffffffu;
+                if (w == w0) m &= ~0u << (a0 & 31u);
+                if (w == w1 && (a1 & 31u)) m &= (1u << (a1 & 31u)) - 1u;
+                if (m == 0xffffffffu) P.validity[w] = m; else atomicOr(&P.validity[w], m);
+            }
+            return;
+        }
+    }
+    if (n > 1024u || (def_len & 1u)) { if (l == 0) to_slow(P, q); return; }
     const uint8_t* s = pg + 4;
     const uint32_t nr = def_len >> 1;
     // Validity image without shared-memory atomics: every run boundary where the level flips
