@@ -25,6 +25,7 @@ namespace {
 constexpr int kBigThreads = 256;
 constexpr int kBigChunk = 48 * 1024;   // staged stream bytes per step
 constexpr int kBigRuns = 1024;         // run-table entries per step
+constexpr int kBigSlots = 131072;      // slots per page the null-aware path can hold (validity image + ranks in shared memory)
 
 template <int W> struct BElem;
 template <> struct BElem<4> { using T = uint32_t; };
@@ -38,13 +39,69 @@ struct BigSmem {
     uint32_t run_data[kBigRuns];      // literal: bit offset inside the staged chunk; RLE: the value
     uint8_t run_lit[kBigRuns];
     uint32_t n_runs, next_pos, next_val, status; // status: 0 ok, 1 hand the page over
-    uint32_t flag;
+    uint32_t flag, all_valid, nn, lo_slot, hi_slot;
+    uint32_t pv[kBigSlots / 32];      // page-relative validity words (pages with nulls)
+    uint32_t rb[kBigSlots / 32 + 1];  // rank of the first slot of every word (exclusive popcount prefix)
     __align__(16) uint8_t chunk[kBigChunk + 32];
 };
 
 __device__ __forceinline__ void hand_over(const DecodeParams& P, uint32_t q) {
     uint32_t k = atomicAdd(&P.err->slow_count, 1u);
     P.slow_pages[P.n_slow_host + k] = q;
+}
+
+// stage `take` bytes of a stream slice into S.chunk keeping the source's 16-byte phase; returns the phase
+__device__ __forceinline__ const uint8_t* stage_slice(BigSmem& S, const uint8_t* g, uint32_t take) {
+    const uint32_t mis = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(g) & 15u);
+    const uint32_t nvec = (mis + take + 15u) >> 4;
+    for (uint32_t j = threadIdx.x; j < nvec; j += kBigThreads) reinterpret_cast<uint4*>(S.chunk)[j] = ldg_nc16(g - mis + 16u * j);
+    __syncthreads();
+    return S.chunk + mis;
+}
+
+// Run-boundary scan of a staged slice by ONE thread (RleDecoder::next_counts,
+// rle_decoder.hpp:37-53): fills the run table for values [v0, ...) until the table or the slice
+// is full.  spos = stream position of cb[0], slen = stream length.
+__device__ __forceinline__ void scan_runs(BigSmem& S, const uint8_t* cb, uint32_t take, uint32_t bw, uint32_t n, uint32_t v0,
+                                          uint32_t spos, uint32_t slen) {
+    const uint32_t nb = (bw + 7u) >> 3;
+    uint32_t p = 0, v = v0, r = 0, st = 0;
+    while (r < static_cast<uint32_t>(kBigRuns) && v < n) {
+        if (spos + p >= slen) { // stream exhausted: the remaining values read as 0 (:21-24)
+            S.run_first[r] = v; S.run_data[r] = 0; S.run_lit[r] = 0; r++; v = n; break;
+        }
+        uint32_t ind = 0, shift = 0, hp = p;
+        bool complete = false;
+        while (hp < take) { uint32_t b = cb[hp++]; if (shift < 32) ind |= (b & 0x7Fu) << shift; if (!(b & 0x80u)) { complete = true; break; } shift += 7; }
+        if (!complete) break; // the header continues in the next slice
+        if (ind & 1u) {
+            const uint64_t cnt = static_cast<uint64_t>(ind >> 1) * 8u;
+            const uint64_t dbytes = (cnt * bw + 7u) >> 3;
+            if (cnt == 0) { st = 1; break; }
+            if (hp + dbytes > take) { if (p == 0) st = 1; break; } // does not fit: restage from this header
+            S.run_first[r] = v; S.run_data[r] = hp * 8u; S.run_lit[r] = 1; r++;
+            v += cnt < static_cast<uint64_t>(n - v) ? static_cast<uint32_t>(cnt) : (n - v);
+            p = hp + static_cast<uint32_t>(dbytes);
+        } else {
+            const uint32_t cnt = ind >> 1;
+            if (cnt == 0) { st = 1; break; }
+            if (hp + nb > take) { if (p == 0) st = 1; break; }
+            uint32_t val = 0;
+            for (uint32_t i = 0; i < nb && i < 4u; i++) val |= static_cast<uint32_t>(cb[hp + i]) << (8u * i);
+            S.run_first[r] = v; S.run_data[r] = val; S.run_lit[r] = 0; r++;
+            v += min(cnt, n - v);
+            p = hp + nb;
+        }
+    }
+    if (r == 0 && st == 0) st = 1; // no progress: the general kernel decides
+    S.run_first[r] = v;
+    S.n_runs = r; S.next_pos = spos + p; S.next_val = v; S.status = st;
+}
+
+__device__ __forceinline__ uint32_t find_run(const BigSmem& S, uint32_t nr, uint32_t v) {
+    uint32_t lo = 0, hi = nr; // run with run_first[r] <= v < run_first[r + 1]
+    while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (S.run_first[mid] <= v) lo = mid; else hi = mid; }
+    return lo;
 }
 
 template <int W>
@@ -62,62 +119,130 @@ __global__ void __launch_bounds__(kBigThreads) k_big_pages(const DecodeParams P)
         if (n == 0) continue;
         const uint8_t* pg = P.image + pd.payload_off;
         __syncthreads();
-        // ---- levels: none, or one RLE run of the maximum level covering the page ----
+        // ---- levels ----
+        // none / one RLE run of the maximum level covering the page: every slot present;
+        // otherwise (max_def == 1): validity image + ranks in shared memory
         if (tid == 0) {
-            uint32_t st = 0, pos = 0;
+            uint32_t st = 0, pos = 0, allv = 1;
             if (ck.max_rep > 0 || ck.max_def > 1) st = 1;
             else if (ck.max_def == 1) {
                 if (size < 4) st = 1;
                 else {
                     const uint32_t def_len = ld32u(pg);
-                    if (def_len > size - 4 || def_len < 2) st = 1;
+                    if (def_len > size - 4) st = 1;
                     else {
                         uint32_t ind = 0, shift = 0, p = 4;
                         while (p < 4 + def_len) { uint32_t b = pg[p++]; if (shift < 32) ind |= (b & 0x7Fu) << shift; if (!(b & 0x80u)) break; shift += 7; }
-                        if ((ind & 1u) || (ind >> 1) < n || p >= 4 + def_len || pg[p] != 1u) st = 1; // not "all present"
+                        if (def_len < 2 || (ind & 1u) || (ind >> 1) < n || p >= 4 + def_len || pg[p] != 1u) allv = 0;
+                        if (!allv && (n > static_cast<uint32_t>(kBigSlots) || def_len > static_cast<uint32_t>(kBigChunk))) st = 1;
                         pos = 4 + def_len;
                     }
                 }
             }
-            S.status = st; S.next_pos = pos;
+            S.status = st; S.next_pos = pos; S.all_valid = allv; S.nn = n;
         }
         __syncthreads();
         if (S.status) { if (tid == 0) hand_over(P, q); continue; }
         uint32_t pos = S.next_pos;
+        const bool all_valid = S.all_valid != 0;
+        const uint32_t nwords = (n + 31u) >> 5;
+        bool ok = true;
+        if (!all_valid) {
+            // definition levels (bit width 1) -> page-relative validity words
+            const uint32_t def_len = pos - 4u;
+            for (uint32_t w = tid; w < nwords; w += kBigThreads) S.pv[w] = 0;
+            const uint8_t* cb = stage_slice(S, pg + 4, def_len);
+            uint32_t spos = 0, vdone = 0;
+            while (vdone < n && ok) {
+                if (tid == 0) scan_runs(S, cb + spos, def_len - spos, 1u, n, vdone, spos, def_len);
+                __syncthreads();
+                if (S.status) { ok = false; break; }
+                const uint32_t nr = S.n_runs, vend = S.next_val;
+                const uint8_t* rb_base = cb + spos; // literal bit offsets are relative to the scanned slice
+                for (uint32_t w = (vdone >> 5) + tid; w <= ((vend - 1u) >> 5); w += kBigThreads) {
+                    uint32_t sl = max(w * 32u, vdone);
+                    const uint32_t hi = min(w * 32u + 32u, vend);
+                    uint32_t bits = 0, r = find_run(S, nr, sl);
+                    while (sl < hi) {
+                        const uint32_t rend = S.run_first[r + 1];
+                        const uint32_t cnt = min(hi, rend) - sl;
+                        uint32_t m;
+                        if (S.run_lit[r]) m = ldbits(rb_base, S.run_data[r] + (sl - S.run_first[r]), cnt);
+                        else m = S.run_data[r] >= 1u ? (cnt >= 32u ? 0xffffffffu : ((1u << cnt) - 1u)) : 0u;
+                        bits |= m << (sl & 31u);
+                        sl += cnt;
+                        r++;
+                    }
+                    if (bits) atomicOr(&S.pv[w], bits);
+                }
+                __syncthreads();
+                vdone = vend;
+                spos = S.next_pos;
+            }
+            if (!ok) { __syncthreads(); if (tid == 0) hand_over(P, q); continue; }
+            // ranks: exclusive prefix of the word popcounts (256 threads x up to 16 words)
+            {
+                const uint32_t per = (nwords + kBigThreads - 1) / kBigThreads;
+                const uint32_t w0 = tid * per, w1 = min(nwords, w0 + per);
+                uint32_t sum = 0;
+                for (uint32_t w = w0; w < w1; w++) sum += __popc(S.pv[w]);
+                __shared__ uint32_t wsum[kBigThreads / 32];
+                const uint32_t l = tid & 31u, wp = tid >> 5;
+                uint32_t incl = warp_incl_scan(sum);
+                if (l == 31) wsum[wp] = incl;
+                __syncthreads();
+                uint32_t base = 0, total = 0;
+                for (uint32_t i = 0; i < kBigThreads / 32; i++) { uint32_t x = wsum[i]; if (i < wp) base += x; total += x; }
+                uint32_t run = base + incl - sum;
+                for (uint32_t w = w0; w < w1; w++) { S.rb[w] = run; run += __popc(S.pv[w]); }
+                if (tid == 0) { S.rb[nwords] = total; S.nn = total; }
+                __syncthreads();
+            }
+        }
+        const uint32_t nn = S.nn;
         const bool dict_page = (pd.flags & PQG_PAGE_FLAG_DICT) && ck.has_dict;
         T* out = reinterpret_cast<T*>(P.values) + pd.out_row_base;
-        bool ok = true;
         if (!dict_page) {
-            // ---- PLAIN: shifted copy, 16-byte vectors once the destination is aligned ----
-            if (static_cast<uint64_t>(n) * W > size - pos) { if (tid == 0) hand_over(P, q); continue; }
+            if (static_cast<uint64_t>(nn) * W > size - pos) { if (tid == 0) hand_over(P, q); continue; }
             const uint8_t* src = pg + pos;
-            const uint64_t bytes = static_cast<uint64_t>(n) * W;
-            uint8_t* dst = reinterpret_cast<uint8_t*>(out);
-            uint32_t head = static_cast<uint32_t>((16u - (reinterpret_cast<uintptr_t>(dst) & 15u)) & 15u);
-            if (head > bytes) head = static_cast<uint32_t>(bytes);
-            if (tid < head / W) out[tid] = ld_val<W>(src + tid * W);
-            const uint8_t* s2 = src + head;
-            uint8_t* d2 = dst + head;
-            const uint32_t nvec = static_cast<uint32_t>((bytes - head) >> 4);
-            const uint32_t sh = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(s2) & 15u);
-            const uint8_t* a = s2 - sh;
-            const uint32_t bs = (sh & 3u) * 8u, ws = sh >> 2;
-            for (uint32_t j = tid; j < nvec; j += kBigThreads) {
-                const uint4 v0 = ldg_nc16(a + 16u * j);
-                uint4 r = v0;
-                if (sh) {
-                    const uint4 v1 = ldg_nc16(a + 16u * j + 16);
-                    const uint32_t w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-                    r.x = __funnelshift_r(w[ws], w[ws + 1], bs); r.y = __funnelshift_r(w[ws + 1], w[ws + 2], bs);
-                    r.z = __funnelshift_r(w[ws + 2], w[ws + 3], bs); r.w = __funnelshift_r(w[ws + 3], w[ws + 4], bs);
+            if (all_valid) {
+                // ---- PLAIN, no nulls: shifted copy, 16-byte vectors once the destination is aligned ----
+                const uint64_t bytes = static_cast<uint64_t>(n) * W;
+                uint8_t* dst = reinterpret_cast<uint8_t*>(out);
+                uint32_t head = static_cast<uint32_t>((16u - (reinterpret_cast<uintptr_t>(dst) & 15u)) & 15u);
+                if (head > bytes) head = static_cast<uint32_t>(bytes);
+                if (tid < head / W) out[tid] = ld_val<W>(src + tid * W);
+                const uint8_t* s2 = src + head;
+                uint8_t* d2 = dst + head;
+                const uint32_t nvec = static_cast<uint32_t>((bytes - head) >> 4);
+                const uint32_t sh = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(s2) & 15u);
+                const uint8_t* a = s2 - sh;
+                const uint32_t bs = (sh & 3u) * 8u, ws = sh >> 2;
+                for (uint32_t j = tid; j < nvec; j += kBigThreads) {
+                    const uint4 v0 = ldg_nc16(a + 16u * j);
+                    uint4 r = v0;
+                    if (sh) {
+                        const uint4 v1 = ldg_nc16(a + 16u * j + 16);
+                        const uint32_t w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+                        r.x = __funnelshift_r(w[ws], w[ws + 1], bs); r.y = __funnelshift_r(w[ws + 1], w[ws + 2], bs);
+                        r.z = __funnelshift_r(w[ws + 2], w[ws + 3], bs); r.w = __funnelshift_r(w[ws + 3], w[ws + 4], bs);
+                    }
+                    __stcs(reinterpret_cast<uint4*>(d2) + j, r);
                 }
-                __stcs(reinterpret_cast<uint4*>(d2) + j, r);
+                const uint32_t done = head + (nvec << 4);
+                const uint32_t tail = static_cast<uint32_t>(bytes - done) / W;
+                if (tid < tail) reinterpret_cast<T*>(dst + done)[tid] = ld_val<W>(src + done + tid * W);
+            } else {
+                // ---- PLAIN with nulls: slot -> rank -> value ----
+                for (uint32_t sl = tid; sl < n; sl += kBigThreads) {
+                    const uint32_t wv = S.pv[sl >> 5];
+                    T x = 0;
+                    if ((wv >> (sl & 31u)) & 1u) x = ld_val<W>(src + static_cast<size_t>(S.rb[sl >> 5] + __popc(wv & ((1u << (sl & 31u)) - 1u))) * W);
+                    __stcs(out + sl, x);
+                }
             }
-            const uint32_t done = head + (nvec << 4);
-            const uint32_t tail = static_cast<uint32_t>(bytes - done) / W;
-            if (tid < tail) reinterpret_cast<T*>(dst + done)[tid] = ld_val<W>(src + done + tid * W);
         } else {
-            // ---- dictionary indices: staged chunks, run table by one thread, parallel expansion ----
+            // ---- dictionary indices: staged slices, run table by one thread, parallel expansion ----
             if (pos >= size) { if (tid == 0) hand_over(P, q); continue; }
             const uint32_t bw = pg[pos];
             pos++;
@@ -126,85 +251,71 @@ __global__ void __launch_bounds__(kBigThreads) k_big_pages(const DecodeParams P)
             const uint32_t slen = size - pos;
             const T* dict = reinterpret_cast<const T*>(P.dict_arena + ck.dict_arena_off);
             const uint32_t dict_n = ck.dict_ok_n;
-            const uint32_t nb = (bw + 7u) >> 3;
-            uint32_t spos = 0, vdone = 0; // stream position of the next run header, values decoded so far
-            while (vdone < n && ok) {
-                // stage [spos, spos + kBigChunk) of the stream
+            const uint32_t imask = bw >= 32u ? 0xffffffffu : ((1u << bw) - 1u);
+            uint32_t spos = 0, vdone = 0, slot_lo = 0; // next run header, values decoded, slots emitted
+            if (nn == 0) { for (uint32_t sl = tid; sl < n; sl += kBigThreads) __stcs(out + sl, T(0)); }
+            while (vdone < nn && ok) {
                 const uint32_t take = min(static_cast<uint32_t>(kBigChunk), slen - min(slen, spos));
-                {
-                    const uint8_t* g = stream + spos;
-                    const uint32_t mis = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(g) & 15u);
-                    // chunk[] keeps the 16-byte phase of the source: byte i of the stream slice sits at chunk[mis + i]
-                    const uint32_t nvec = (mis + take + 15u) >> 4;
-                    for (uint32_t j = tid; j < nvec; j += kBigThreads)
-                        reinterpret_cast<uint4*>(S.chunk)[j] = ldg_nc16(g - mis + 16u * j);
-                    if (tid == 0) S.flag = mis;
-                }
-                __syncthreads();
-                const uint8_t* cb = S.chunk + S.flag;
+                const uint8_t* cb = stage_slice(S, stream + spos, take);
                 if (tid == 0) {
-                    // run-boundary scan of the chunk (RleDecoder::next_counts, rle_decoder.hpp:37-53)
-                    uint32_t p = 0, v = vdone, r = 0, st = 0;
-                    while (r < static_cast<uint32_t>(kBigRuns) && v < n) {
-                        if (spos + p >= slen) { // stream exhausted: the remaining values read as index 0 (:21-24)
-                            S.run_first[r] = v; S.run_data[r] = 0; S.run_lit[r] = 0; r++; v = n; break;
-                        }
-                        uint32_t ind = 0, shift = 0, hp = p;
-                        bool complete = false;
-                        while (hp < take) { uint32_t b = cb[hp++]; if (shift < 32) ind |= (b & 0x7Fu) << shift; if (!(b & 0x80u)) { complete = true; break; } shift += 7; }
-                        if (!complete) break; // header continues in the next chunk (or the stream is cut: next staging decides)
-                        if (ind & 1u) {
-                            const uint64_t cnt = static_cast<uint64_t>(ind >> 1) * 8u;
-                            const uint64_t dbytes = (cnt * bw + 7u) >> 3;
-                            if (cnt == 0) { st = 1; break; }
-                            if (hp + dbytes > take) { if (p == 0) st = 1; break; } // does not fit this chunk: restage from this header
-                            S.run_first[r] = v; S.run_data[r] = hp * 8u; S.run_lit[r] = 1; r++;
-                            v += cnt < static_cast<uint64_t>(n - v) ? static_cast<uint32_t>(cnt) : (n - v);
-                            p = hp + static_cast<uint32_t>(dbytes);
-                        } else {
-                            const uint32_t cnt = ind >> 1;
-                            if (cnt == 0) { st = 1; break; }
-                            if (hp + nb > take) { if (p == 0) st = 1; break; }
-                            uint32_t val = 0;
-                            for (uint32_t i = 0; i < nb && i < 4u; i++) val |= static_cast<uint32_t>(cb[hp + i]) << (8u * i);
-                            S.run_first[r] = v; S.run_data[r] = val; S.run_lit[r] = 0; r++;
-                            v += min(cnt, n - v);
-                            p = hp + nb;
-                        }
-                    }
-                    if (r == 0 && st == 0) st = 1; // no progress (a header cut by the end of the page): general kernel
-                    S.run_first[r] = v;
-                    S.n_runs = r; S.next_pos = spos + p; S.next_val = v; S.status = st;
+                    scan_runs(S, cb, take, bw, nn, vdone, spos, slen);
+                    // slots of this batch: up to (excluding) the slot of value next_val; the last batch takes the rest
+                    uint32_t hi_slot = n;
+                    if (!all_valid && S.next_val < nn) {
+                        uint32_t lo = 0, hi = nwords; // last word with rb[w] <= next_val
+                        while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (S.rb[mid] <= S.next_val) lo = mid; else hi = mid; }
+                        uint32_t need = S.next_val - S.rb[lo], wv = S.pv[lo], b = 0;
+                        for (; b < 32; b++) { if ((wv >> b) & 1u) { if (need == 0) break; need--; } }
+                        hi_slot = lo * 32u + b;
+                    } else if (all_valid) hi_slot = S.next_val;
+                    S.hi_slot = hi_slot;
                 }
                 __syncthreads();
                 if (S.status) { ok = false; break; }
-                const uint32_t nr = S.n_runs, vend = S.next_val;
-                const uint32_t imask = bw >= 32u ? 0xffffffffu : ((1u << bw) - 1u);
-                for (uint32_t v = vdone + tid; v < vend; v += kBigThreads) {
-                    uint32_t lo = 0, hi = nr; // run with run_first[r] <= v < run_first[r + 1]
-                    while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (S.run_first[mid] <= v) lo = mid; else hi = mid; }
-                    uint32_t ix;
-                    if (S.run_lit[lo]) ix = ldbits(cb, S.run_data[lo] + (v - S.run_first[lo]) * bw, bw) & imask;
-                    else ix = S.run_data[lo];
+                const uint32_t nr = S.n_runs, vend = S.next_val, slot_hi = S.hi_slot;
+                for (uint32_t sl = slot_lo + tid; sl < slot_hi; sl += kBigThreads) {
+                    uint32_t v = sl;
+                    bool valid = true;
+                    if (!all_valid) {
+                        const uint32_t wv = S.pv[sl >> 5];
+                        valid = (wv >> (sl & 31u)) & 1u;
+                        v = S.rb[sl >> 5] + __popc(wv & ((1u << (sl & 31u)) - 1u));
+                    }
                     T x = 0;
-                    if (ix < dict_n) x = __ldg(dict + ix); else ok = false; // NULL in the reference: general kernel redoes the page
-                    __stcs(out + v, x);
+                    if (valid) {
+                        const uint32_t r = find_run(S, nr, v);
+                        const uint32_t ix = S.run_lit[r] ? (ldbits(cb, S.run_data[r] + (v - S.run_first[r]) * bw, bw) & imask) : S.run_data[r];
+                        if (ix < dict_n) x = __ldg(dict + ix); else ok = false; // NULL in the reference: the general kernel redoes the page
+                    }
+                    __stcs(out + sl, x);
                 }
                 ok = __syncthreads_and(ok);
                 vdone = vend;
+                slot_lo = slot_hi;
                 spos = S.next_pos;
             }
             if (!ok) { if (tid == 0) hand_over(P, q); continue; }
         }
-        // ---- validity: every slot of the page is present ----
+        // ---- validity ----
         if (P.validity && ck.max_def > 0) {
-            const uint64_t a0 = pd.out_row_base, a1 = a0 + n;
-            const uint64_t w0 = a0 >> 5, w1 = (a1 - 1) >> 5;
-            for (uint64_t w = w0 + tid; w <= w1; w += kBigThreads) {
-                uint32_t m = 0xffffffffu;
-                if (w == w0) m &= ~0u << (a0 & 31u);
-                if (w == w1 && (a1 & 31u)) m &= (1u << (a1 & 31u)) - 1u;
-                if (m == 0xffffffffu) P.validity[w] = m; else atomicOr(&P.validity[w], m);
+            const uint64_t a0 = pd.out_row_base;
+            if (all_valid) {
+                const uint64_t a1 = a0 + n, w0 = a0 >> 5, w1 = (a1 - 1) >> 5;
+                for (uint64_t w = w0 + tid; w <= w1; w += kBigThreads) {
+                    uint32_t m = 0xffffffffu;
+                    if (w == w0) m &= ~0u << (a0 & 31u);
+                    if (w == w1 && (a1 & 31u)) m &= (1u << (a1 & 31u)) - 1u;
+                    if (m == 0xffffffffu) P.validity[w] = m; else atomicOr(&P.validity[w], m);
+                }
+            } else {
+                const uint32_t sh = static_cast<uint32_t>(a0 & 31u);
+                uint32_t* gv = P.validity + (a0 >> 5);
+                for (uint32_t w = tid; w < nwords; w += kBigThreads) {
+                    const uint32_t m = S.pv[w];
+                    if (!m) continue;
+                    atomicOr(&gv[w], m << sh);
+                    if (sh && (m >> (32u - sh))) atomicOr(&gv[w + 1], m >> (32u - sh));
+                }
             }
         }
     }
