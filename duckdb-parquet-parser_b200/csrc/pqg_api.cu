@@ -557,7 +557,7 @@ int pqg_plan_run(pqg_ctx* ctx, pqg_plan* p) {
         launches += 2;
         CU(ctx, cudaMemcpyAsync(p->h_bases, p->d_bases, (P.n_chunks + 2) * 8, cudaMemcpyDeviceToHost, s));
         if (prof) CU(ctx, cudaEventRecord(p->ev[2], s));
-        if (!p->ran || true) {
+        {
             // the output size is data dependent: wait for the size pass, (re)allocate if needed
             CU(ctx, cudaStreamSynchronize(s));
             uint64_t total = p->h_bases[P.n_chunks + 1];
