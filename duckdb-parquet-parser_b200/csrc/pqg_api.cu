@@ -47,6 +47,10 @@ struct pqg_plan {
     uint32_t max_dict_blocks = 1;
     uint32_t cluster_size = 0, part_shift = 0; // DSMEM dictionary mode (0 = off)
     uint32_t tile_bytes = kTileBytes;
+    // BYTE_ARRAY plans whose pages are all PLAIN REQUIRED: byte counts from the page headers
+    // (payload - 4 * values), scans on the host, no size pass and no mid-run synchronisation;
+    // the copy pass verifies every page and the plan falls back to the size pass on a mismatch
+    bool host_sizes = false, force_exact = false;
     std::vector<uint32_t> chunk_tile_begin;  // n_chunks + 1: tiles of chunk c = [begin[c], begin[c+1])
     std::vector<uint32_t> chunk_slow_begin;  // n_chunks + 1: host-listed slow pages of chunk c
     std::vector<cudaEvent_t> pipe_ev;        // pipelined path: 2 events per chunk (H2D done, decode done)
@@ -404,6 +408,31 @@ int pqg_plan_create(pqg_ctx* ctx, const pqg_buf* image, const pqg_chunk_desc* ch
         }
     }
 
+    std::vector<uint32_t> h_page_chars, h_page_base;
+    if (p->is_str && n_pages && !std::getenv("PQG_EXACT_SIZES")) {
+        bool all = true;
+        h_page_chars.assign(n_pages + 1, 0);
+        h_page_base.assign(n_pages + 1, 0);
+        uint64_t col_total = 0;
+        for (uint32_t c = 0; c < n_chunks && all; c++) {
+            const pqg_chunk_desc& s = chunks[c];
+            if (s.max_def > 0 || s.max_rep > 0) { all = false; break; }
+            uint64_t acc = 0;
+            for (uint32_t q = s.first_page; q < s.first_page + s.n_pages; q++) {
+                const pqg_page_desc& pg = pages[q];
+                if (((pg.flags & PQG_PAGE_FLAG_DICT) && s.has_dict) || static_cast<uint64_t>(pg.num_values) * 4 > pg.payload_size) { all = false; break; }
+                const uint32_t bytes = pg.num_values ? pg.payload_size - 4u * pg.num_values : 0u;
+                h_page_chars[q] = bytes;
+                h_page_base[q] = static_cast<uint32_t>(acc);
+                acc += bytes;
+                if (acc > 0xffffffffull) { all = false; break; }
+            }
+            dc[c].char_base = col_total;
+            col_total += acc;
+        }
+        p->host_sizes = all;
+        if (all) p->chars_size = col_total;
+    }
     auto alloc = [&](void** ptr, size_t bytes) -> cudaError_t { return cudaMalloc(ptr, bytes ? bytes : 16); };
     cudaError_t e;
 #define PA(ptr, bytes) if ((e = alloc(reinterpret_cast<void**>(&(ptr)), (bytes))) != cudaSuccess) { pqg_plan_destroy(ctx, p); return cuda_fail(ctx, e, "cudaMalloc(plan)"); }
@@ -423,6 +452,15 @@ int pqg_plan_create(pqg_ctx* ctx, const pqg_buf* image, const pqg_chunk_desc* ch
             pqg_plan_destroy(ctx, p); return cuda_fail(ctx, e, "cudaHostAlloc");
         }
         std::memset(p->h_bases, 0, (n_chunks + 2) * 8);
+        if (p->host_sizes) {
+            for (uint32_t c = 0; c < n_chunks; c++) p->h_bases[c] = dc[c].char_base;
+            p->h_bases[n_chunks] = p->h_bases[n_chunks + 1] = p->chars_size;
+            PA(p->d_chars, p->chars_size + 64);
+            p->chars_cap = p->chars_size;
+            if ((e = cudaMemcpyAsync(p->d_page_chars, h_page_chars.data(), static_cast<size_t>(n_pages) * 4, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess ||
+                (e = cudaMemcpyAsync(p->d_page_char_base, h_page_base.data(), static_cast<size_t>(n_pages) * 4, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess ||
+                (e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) { pqg_plan_destroy(ctx, p); return cuda_fail(ctx, e, "page size upload"); }
+        }
     } else {
         PA(p->d_values, slots * p->width + 16);
     }
@@ -546,6 +584,12 @@ int pqg_plan_run(pqg_ctx* ctx, pqg_plan* p) {
         if (n < 0) return cuda_fail(ctx, ce, "decode launch");
         launches += static_cast<uint32_t>(n);
         if (prof) CU(ctx, cudaEventRecord(p->ev[3], s));
+    } else if (p->host_sizes && !p->force_exact) {
+        // byte counts, page bases and chunk bases are known from the page headers: copy pass only
+        if (prof) { CU(ctx, cudaEventRecord(p->ev[1], s)); CU(ctx, cudaEventRecord(p->ev[2], s)); }
+        P.check_layout = 1;
+        if (P.page_end) { CU(ctx, launch_str_copy(P, ctx->sm_count, s)); launches++; }
+        if (prof) CU(ctx, cudaEventRecord(p->ev[3], s));
     } else {
         if (p->any_dict) {
             CU(ctx, launch_dict_prepare(P, P.n_chunks, 0, 1, s));
@@ -625,6 +669,13 @@ int pqg_plan_finish(pqg_ctx* ctx, pqg_plan* p, pqg_page_error* err) {
         if (d.d_page == raw_page) { pe.pos = d.d_pos; pe.need = d.d_need; pe.size = d.d_size; }
     }
     if (err) *err = pe;
+    if (pe.count && pe.code == PQG_PAGE_LAYOUT && p->host_sizes && !p->force_exact) {
+        // a PLAIN page carries bytes beyond its values: redo the column with the size pass
+        p->force_exact = true;
+        int rc = pqg_plan_run(ctx, p);
+        if (rc != PQG_OK) return rc;
+        return pqg_plan_finish(ctx, p, err);
+    }
     if (pe.count) {
         char msg[256];
         if (pe.code == PQG_PAGE_TRUNCATED || pe.code == PQG_PAGE_DICT_TRUNCATED)

@@ -479,6 +479,9 @@ __device__ __forceinline__ void decode_str_page(const DecodeParams& P, uint32_t 
             P.page_chars[q] = static_cast<uint32_t>(page_bytes);
         }
     } else {
+        // byte counts taken from the page headers (no size pass) hold only if the page is exactly its values
+        if (P.check_layout && !c.dict && l == 0 && page_bytes != static_cast<uint64_t>(vavail) - 4ull * nn_before)
+            report_error(P.err, q, PQG_PAGE_LAYOUT);
         // the last page of the chunk closes the Arrow offsets array
         if (l == 0 && q + 1 == ck.first_page + ck.n_pages)
             offs[(pd.out_row_base - ck.out_row_base) + c.n] = static_cast<uint32_t>(page_base + page_bytes);

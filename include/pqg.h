@@ -56,7 +56,8 @@ enum {
     PQG_PAGE_BAD_BIT_WIDTH = 2, /* dictionary index bit width > 32 */
     PQG_PAGE_BAD_RUN = 3,       /* zero-length RLE run / empty literal run: reference UB */
     PQG_PAGE_DICT_TRUNCATED = 4,/* dictionary page shorter than its entries */
-    PQG_PAGE_CHARS_OVERFLOW = 5 /* a column chunk decodes to >= 4 GiB of string bytes */
+    PQG_PAGE_CHARS_OVERFLOW = 5,/* a column chunk decodes to >= 4 GiB of string bytes */
+    PQG_PAGE_LAYOUT = 6         /* internal: a PLAIN string page is not exactly its values (the plan re-runs with the size pass) */
 };
 
 /* Physical types: reference enum ParquetType (include/common.hpp:16-25). */

@@ -238,3 +238,52 @@ def test_oversized_plain_pages_are_split_and_errors_name_the_page(pq):
     b.add_page(big.tobytes()[:-8], len(big), dict_page=False)  # one value short
     _, _, msg = b.run(expect_error=(1, 1))
     assert "ByteBuffer: read beyond end" in msg
+
+
+def _string_plan(pq, pages, n_each):
+    """pages: list of payload bytes of PLAIN REQUIRED BYTE_ARRAY pages; -> (offsets, chars) of the decode"""
+    img = bytearray()
+    descs = []
+    row = 0
+    for pay, n in zip(pages, n_each):
+        img += b"\xAA" * (len(descs) % 3)
+        descs.append((len(img), len(pay), n, row))
+        img += pay
+        row += n
+    ctx = pq.Context(0)
+    arr = np.frombuffer(bytes(img) + b"\0" * 64, dtype=np.uint8)
+    buf = ctx.upload(arr.ctypes.data, len(img))
+    ck = (pq.ChunkDesc * 1)()
+    ck[0] = pq.ChunkDesc(0, 0, row, 0, 0, 0, len(descs), 0, 0, 0, 0, pq.BYTE_ARRAY, 0, (C.c_uint8 * 2)(0, 0))
+    pg = (pq.PageDesc * len(descs))()
+    for i, (off, size, n, r0) in enumerate(descs):
+        pg[i] = pq.PageDesc(off, r0, size, n, 0, 0)
+    plan = ctx.plan(buf, (ck, 1, pg, len(descs), row))
+    try:
+        for _ in range(2):  # the second run reuses whatever mode the first one settled on
+            plan.run()
+            plan.finish()
+            offs = np.zeros(row + 1, dtype=np.uint32)
+            chars = np.zeros(max(plan.chars_size, 1), dtype=np.uint8)
+            plan.download(offsets=offs.ctypes.data, chars=chars.ctypes.data)
+            ctx.sync()
+        return offs, chars[:plan.chars_size].tobytes()
+    finally:
+        plan.destroy()
+        ctx.buf_free(buf)
+        ctx.close()
+
+
+def test_plain_string_pages_with_trailing_bytes_fall_back_to_the_size_pass(pq):
+    """byte counts normally come from the page headers (payload - 4 * values); a page that
+    carries bytes beyond its values (legal for the reference: it reads n values and stops) must
+    make the plan fall back to the exact size pass and still decode correctly"""
+    def page(strs, trailing=b""):
+        return b"".join(len(s).to_bytes(4, "little") + s for s in strs) + trailing
+    a = [b"alpha", b"", b"beta-gamma", b"x" * 70]
+    b = [b"delta", b"epsilon" * 9, b"z"]
+    for trailing in (b"", b"JUNKJUNK"):
+        offs, chars = _string_plan(pq, [page(a), page(b, trailing), page(a)], [len(a), len(b), len(a)])
+        exp = a + b + a
+        assert chars == b"".join(exp)
+        assert offs.tolist() == np.concatenate([[0], np.cumsum([len(s) for s in exp])]).tolist()
