@@ -54,6 +54,16 @@ def run(name, col, rep):
         rc = L.pqg_chunk_index(ctx.h, plan.h, 4096, 0, 0, ids.ctypes.data, ctypes.byref(nch), ctypes.byref(cout), ctypes.byref(ms))
         assert rc == 0, ctx.err()
         cms.append(ms.value)
+    # regex page pruning on the same device-resident column
+    rx = {}
+    for pat in ("^[A-Za-z]+_?0*[0-9]+_x$", "@mail7[0-9]{2}\\."):
+        dfa = pq.regex_compile(pat)
+        bits = np.zeros((t[3] + 31) // 32 + 1, dtype=np.uint32)
+        for _ in range(3):
+            rc = L.pqg_regex_scan(ctx.h, plan.h, dfa, 0, bits.ctypes.data, ctypes.byref(ms))
+            assert rc == 0, ctx.err()
+        L.pqg_dfa_free(dfa)
+        rx[pat] = {"ms": ms.value, "Mpages_per_s": t[3] / ms.value / 1e3, "pages_hit": int(sum(bin(int(x)).count("1") for x in bits))}
     t0 = time.perf_counter()
     pc, po, cf = r.page_chunk_index(0, 4096)
     page_s = time.perf_counter() - t0
@@ -62,7 +72,7 @@ def run(name, col, rep):
     out = {"workload": name, "rows": rows, "pages": t[3], "bytes_in": bi, "bytes_out": bo,
            "decode_ms": dec_ms, "size_pass_ms": tm["str_size_ms"], "copy_pass_ms": tm["str_copy_ms"], "dict_prepare_ms": tm["dict_ms"],
            "decoded_page_GBps": bi / dec_ms / 1e6, "in_plus_out_GBps": (bi + bo) / dec_ms / 1e6, "frac_of_hbm_peak": (bi + bo) / dec_ms / 1e6 / peak,
-           "chunk_index_ms": min(cms), "chunks": int(nch.value), "page_chunk_index_wall_ms": page_s * 1e3, "page_chunks": int(len(cf))}
+           "chunk_index_ms": min(cms), "chunks": int(nch.value), "page_chunk_index_wall_ms": page_s * 1e3, "page_chunks": int(len(cf)), "regex": rx}
     plan.destroy()
     ctx.buf_free(buf)
     ctx.close()
