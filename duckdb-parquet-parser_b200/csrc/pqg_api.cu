@@ -543,7 +543,29 @@ static int fixed_subrun(pqg_ctx* ctx, pqg_plan* p, uint32_t c0, uint32_t c1, boo
                 Pc.tile_lo = p->chunk_tile_begin[c]; Pc.tile_hi = p->chunk_tile_begin[c + 1];
                 if (Pc.tile_hi > Pc.tile_lo) { e = launch_fixed_tiles_cluster(Pc, p->width, ctx->sm_count, s); launches++; }
             }
-        } else { e = launch_fixed_tiles(P, p->width, ctx->sm_count, s); launches++; }
+        } else {
+            // Dictionaries too large for shared memory are gathered from L2: keep the dictionaries of
+            // the chunks that are in flight together within ~48 MB (a 1 M-entry INT64 dictionary is
+            // 8 MB per chunk; with every chunk of a 320 M-row column in one launch the 126 MB L2
+            // thrashed and the gather fell from 2.2 to 1.1 TB/s) -- one launch per chunk group.
+            uint32_t g0 = c0;
+            while (g0 < c1 && e == cudaSuccess) {
+                uint64_t dict_bytes = 0;
+                uint32_t g1 = g0;
+                while (g1 < c1) {
+                    const pqg_chunk_desc& ck = p->chunks[g1];
+                    const uint64_t db = ck.has_dict ? static_cast<uint64_t>(ck.dict_num_values) * p->width : 0;
+                    const bool in_smem = db <= static_cast<uint64_t>(kMaxSmemDictBytes);
+                    if (g1 > g0 && !in_smem && dict_bytes + db > (48ull << 20)) break;
+                    if (!in_smem) dict_bytes += db;
+                    g1++;
+                }
+                DecodeParams Pg = P;
+                Pg.tile_lo = p->chunk_tile_begin[g0]; Pg.tile_hi = p->chunk_tile_begin[g1];
+                if (Pg.tile_hi > Pg.tile_lo) { e = launch_fixed_tiles(Pg, p->width, ctx->sm_count, s); launches++; }
+                g0 = g1;
+            }
+        }
     }
     if (e == cudaSuccess && ev_tiles_end) e = cudaEventRecord(ev_tiles_end, s);
     // host-listed pages (oversized, or of chunks the tile kernel does not take) of 4/8-byte plans:
