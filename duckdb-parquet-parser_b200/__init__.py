@@ -118,7 +118,7 @@ class Tables(C.Structure):
 PQG_SYMBOLS = [
     "pqg_ctx_create", "pqg_ctx_destroy", "pqg_last_error", "pqg_ctx_sync", "pqg_ctx_set_profiling", "pqg_device_count",
     "pqg_kernel_launches", "pqg_upload", "pqg_wrap_device", "pqg_buf_alloc", "pqg_buf_write", "pqg_buf_size",
-    "pqg_buf_free", "pqg_buf_device_ptr", "pqg_host_alloc", "pqg_host_free", "pqg_plan_create", "pqg_plan_destroy",
+    "pqg_buf_free", "pqg_buf_device_ptr", "pqg_host_alloc", "pqg_host_free", "pqg_plan_create", "pqg_plan_create_dict_indices", "pqg_plan_destroy",
     "pqg_plan_set_image", "pqg_plan_run", "pqg_plan_run_pipelined", "pqg_plan_finish", "pqg_plan_timings", "pqg_plan_timings_avg", "pqg_plan_num_slots",
     "pqg_plan_value_width", "pqg_plan_values", "pqg_plan_validity", "pqg_plan_offsets", "pqg_plan_chars",
     "pqg_plan_chars_size", "pqg_plan_char_bases", "pqg_plan_bytes_in", "pqg_plan_bytes_out", "pqg_plan_download",
@@ -131,7 +131,7 @@ PQR_SYMBOLS = [
     "pqr_schema_string", "pqr_page_scan_seconds", "pqr_file_size", "pqr_page_index", "pqr_read_page_data",
     "pqr_read_pages_chunk", "pqr_read_column_by_idx", "pqr_read_column", "pqr_read_column_rg", "pqr_read_pages",
     "pqr_string_iterator_dump", "pqr_valdump_free", "pqr_pagedump_free", "pqr_strdump_free", "pqr_read_columnar",
-    "pqr_columnar_free", "pqr_read_columns_into", "pqr_release_plans", "pqr_column_tables", "pqr_tables_free", "pqr_chunk_index", "pqr_regex_prune",
+    "pqr_columnar_free", "pqr_read_columns_into", "pqr_read_dictionary_indices_into", "pqr_chunk_dictionary", "pqr_release_plans", "pqr_column_tables", "pqr_tables_free", "pqr_chunk_index", "pqr_regex_prune",
     "pqr_page_chunk_index", "pqr_shard_row_groups", "pqr_regex_prune_rgs", "pqr_chunk_index_rgs", "pqr_read_columns_into_rgs",
 ]
 
@@ -177,6 +177,7 @@ def _declare(L):
     d("pqg_host_alloc", vp, u64)
     d("pqg_host_free", None, vp)
     d("pqg_plan_create", i32, vp, vp, C.POINTER(ChunkDesc), u32, C.POINTER(PageDesc), u32, C.POINTER(vp))
+    d("pqg_plan_create_dict_indices", i32, vp, vp, C.POINTER(ChunkDesc), u32, C.POINTER(PageDesc), u32, C.POINTER(vp))
     d("pqg_plan_destroy", None, vp, vp)
     d("pqg_plan_set_image", i32, vp, vp, vp)
     d("pqg_plan_run", i32, vp, vp)
@@ -234,6 +235,8 @@ def _declare(L):
     d("pqr_read_columnar", i32, vp, i32, i32, C.POINTER(Columnar))
     d("pqr_columnar_free", None, C.POINTER(Columnar))
     d("pqr_read_columns_into", i32, vp, C.POINTER(C.c_int32), i32, i32, C.POINTER(Dst), C.POINTER(ReadStats))
+    d("pqr_read_dictionary_indices_into", i32, vp, i32, i64, i64, C.POINTER(Dst), C.POINTER(ReadStats))
+    d("pqr_chunk_dictionary", i32, vp, i32, i64, vp, i64, vp, i64, C.POINTER(i64), C.POINTER(i64))
     d("pqr_release_plans", None, vp)
     d("pqr_shard_row_groups", i32, vp, i32, i32, C.POINTER(C.c_int32))
     d("pqr_regex_prune_rgs", i64, vp, i32, i64, i64, cp, i32, vp, i64, C.POINTER(C.c_float))
@@ -446,6 +449,29 @@ class Reader:
         self._check(lib().pqr_read_columns_into_rgs(self.h, ci, n, rg_begin, rg_end, ds, st))
         return [dict(num_slots=s.num_slots, width=s.width, has_validity=bool(s.has_validity), bytes_in=s.bytes_in,
                      bytes_out=s.bytes_out, h2d_bytes=s.h2d_bytes, d2h_bytes=s.d2h_bytes) for s in st]
+
+    def read_dictionary_indices(self, col, rg_begin=0, rg_end=None, out=None, validity=None):
+        """dictionary-form read: (uint32 indices per slot, validity words | None, stats)"""
+        if rg_end is None:
+            rg_end = self.num_row_groups
+        rows = sum(self.row_group_num_rows(rg) for rg in range(rg_begin, rg_end))
+        idx = out if out is not None else np.zeros(rows, dtype=np.uint32)
+        val = validity if validity is not None else np.zeros((rows + 31) // 32 + 1, dtype=np.uint32)
+        ds = Dst(idx.ctypes.data, idx.nbytes, val.ctypes.data, val.size)
+        st = ReadStats()
+        self._check(lib().pqr_read_dictionary_indices_into(self.h, col, rg_begin, rg_end, C.byref(ds), C.byref(st)))
+        stats = dict(num_slots=st.num_slots, width=st.width, has_validity=bool(st.has_validity), bytes_in=st.bytes_in,
+                     bytes_out=st.bytes_out, h2d_bytes=st.h2d_bytes, d2h_bytes=st.d2h_bytes)
+        return idx[:rows], (val if st.has_validity else None), stats
+
+    def chunk_dictionary(self, col, rg):
+        """(offsets uint32[n+1], chars bytes) of the dictionary page of (row group, column)"""
+        n, nb = C.c_int64(0), C.c_int64(0)
+        self._check(lib().pqr_chunk_dictionary(self.h, col, rg, None, 0, None, 0, C.byref(n), C.byref(nb)))
+        off = np.zeros(n.value + 1, dtype=np.uint32)
+        ch = np.zeros(max(nb.value, 1), dtype=np.uint8)
+        self._check(lib().pqr_chunk_dictionary(self.h, col, rg, off.ctypes.data, off.size, ch.ctypes.data, ch.size, C.byref(n), C.byref(nb)))
+        return off, ch[:nb.value].tobytes()
 
     def release_plans(self):
         lib().pqr_release_plans(self.h)

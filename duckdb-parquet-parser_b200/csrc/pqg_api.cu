@@ -51,6 +51,7 @@ struct pqg_plan {
     // (payload - 4 * values), scans on the host, no size pass and no mid-run synchronisation;
     // the copy pass verifies every page and the plan falls back to the size pass on a mismatch
     bool host_sizes = false, force_exact = false;
+    bool identity = false; // dictionary-form output of a BYTE_ARRAY column: uint32 dictionary indices per slot
     std::vector<uint32_t> chunk_tile_begin;  // n_chunks + 1: tiles of chunk c = [begin[c], begin[c+1])
     std::vector<uint32_t> chunk_slow_begin;  // n_chunks + 1: host-listed slow pages of chunk c
     std::vector<cudaEvent_t> pipe_ev;        // pipelined path: 2 events per chunk (H2D done, decode done)
@@ -268,8 +269,21 @@ void pqg_plan_destroy(pqg_ctx* ctx, pqg_plan* p) {
     delete p;
 }
 
+static int plan_create_impl(pqg_ctx* ctx, const pqg_buf* image, const pqg_chunk_desc* chunks, uint32_t n_chunks,
+                            const pqg_page_desc* pages, uint32_t n_pages, bool dict_indices, pqg_plan** out);
+
 int pqg_plan_create(pqg_ctx* ctx, const pqg_buf* image, const pqg_chunk_desc* chunks, uint32_t n_chunks,
                     const pqg_page_desc* pages, uint32_t n_pages, pqg_plan** out) {
+    return plan_create_impl(ctx, image, chunks, n_chunks, pages, n_pages, false, out);
+}
+
+int pqg_plan_create_dict_indices(pqg_ctx* ctx, const pqg_buf* image, const pqg_chunk_desc* chunks, uint32_t n_chunks,
+                                 const pqg_page_desc* pages, uint32_t n_pages, pqg_plan** out) {
+    return plan_create_impl(ctx, image, chunks, n_chunks, pages, n_pages, true, out);
+}
+
+static int plan_create_impl(pqg_ctx* ctx, const pqg_buf* image, const pqg_chunk_desc* chunks, uint32_t n_chunks,
+                            const pqg_page_desc* pages, uint32_t n_pages, bool dict_indices, pqg_plan** out) {
     if (!ctx || !image || !out || (!chunks && n_chunks) || (!pages && n_pages))
         return fail(ctx, PQG_ERR_ARG, "pqg_plan_create: bad argument");
     *out = nullptr;
@@ -289,6 +303,19 @@ int pqg_plan_create(pqg_ctx* ctx, const pqg_buf* image, const pqg_chunk_desc* ch
     p->is_str = p->phys == PQG_BYTE_ARRAY;
     p->is_bool = p->phys == PQG_BOOLEAN;
     p->width = type_width(p->phys);
+    if (dict_indices) {
+        // dictionary-form output (Arrow DictionaryArray style): the column must be dictionary-encoded
+        // throughout; the plan then is a 4-byte fixed-width plan whose "dictionary" is the identity
+        if (!p->is_str) return bail(PQG_ERR_ARG, "pqg_plan_create_dict_indices: BYTE_ARRAY columns only");
+        for (uint32_t c = 0; c < n_chunks; c++) {
+            if (chunks[c].n_pages && !chunks[c].has_dict) return bail(PQG_ERR_UNSUPPORTED, "column chunk has no dictionary page: not dictionary-encoded throughout");
+            for (uint32_t q = chunks[c].first_page; q < chunks[c].first_page + chunks[c].n_pages && q < n_pages; q++)
+                if (!(pages[q].flags & PQG_PAGE_FLAG_DICT)) return bail(PQG_ERR_UNSUPPORTED, "column falls back to PLAIN pages: not dictionary-encoded throughout");
+        }
+        p->is_str = false;
+        p->identity = true;
+        p->width = 4;
+    }
 
     std::vector<DevChunk> dc(n_chunks);
     size_t arena = 0;
@@ -305,11 +332,15 @@ int pqg_plan_create(pqg_ctx* ctx, const pqg_buf* image, const pqg_chunk_desc* ch
         d.def_bw = level_bw(s.max_def); d.rep_bw = level_bw(s.max_rep);
         if (s.has_dict) {
             if (s.dict_off + s.dict_size > image->size) return bail(PQG_ERR_ARG, "pqg_plan_create: dictionary page outside the image");
-            p->any_dict = true;
-            d.dict_arena_off = arena;
-            size_t ent = p->is_str ? 8 : static_cast<size_t>(p->width);
-            arena += (static_cast<size_t>(s.dict_num_values) * ent + 31) & ~size_t(15);
             p->bytes_in += s.dict_size;
+            if (p->identity) {
+                d.dict_ok_n = s.dict_num_values; // the indices ARE the output: no prepared dictionary on the device
+            } else {
+                p->any_dict = true;
+                d.dict_arena_off = arena;
+                size_t ent = p->is_str ? 8 : static_cast<size_t>(p->width);
+                arena += (static_cast<size_t>(s.dict_num_values) * ent + 31) & ~size_t(15);
+            }
         }
         if (s.max_def > 0) p->any_def = true;
         for (uint32_t q = s.first_page; q < s.first_page + s.n_pages; q++) {
@@ -338,8 +369,9 @@ int pqg_plan_create(pqg_ctx* ctx, const pqg_buf* image, const pqg_chunk_desc* ch
             if (s.has_dict) max_dict_n = std::max(max_dict_n, s.dict_num_values);
             // strings: every flat chunk is tiled (the regex scan runs on tiles; the page kernels
             // classify pages themselves); fixed width: REQUIRED 4/8-byte chunks only
-            const bool tileable = p->is_str ? s.max_rep <= 0 : chunk_is_tileable(s.phys_type, s.max_def, s.max_rep);
-            if (tileable && s.has_dict && !p->is_str) {
+            const bool tileable = p->is_str ? s.max_rep <= 0
+                                 : (p->identity ? (s.max_def <= 1 && s.max_rep <= 0) : chunk_is_tileable(s.phys_type, s.max_def, s.max_rep));
+            if (tileable && s.has_dict && !p->is_str && !p->identity) {
                 uint64_t db = (static_cast<uint64_t>(s.dict_num_values) * p->width + 15) & ~uint64_t(15);
                 if (db <= static_cast<uint64_t>(kMaxSmemDictBytes)) p->dict_smem = std::max<uint32_t>(p->dict_smem, static_cast<uint32_t>(db));
             }
@@ -510,6 +542,7 @@ static DecodeParams make_params(const pqg_plan* p) {
     P.slow_lo = 0; P.slow_hi = p->n_slow_host; P.n_slow_host = p->n_slow_host; P.slow_pages = p->d_slow_pages;
     P.chunk_lo = 0;
     P.cluster_size = p->cluster_size; P.part_shift = p->part_shift; P.tile_bytes = p->tile_bytes;
+    P.identity_dict = p->identity ? 1u : 0u;
     { static const uint32_t gm = [] { const char* e = std::getenv("PQG_GATHER"); return e ? static_cast<uint32_t>(std::atoi(e)) : 1u; }(); P.gather_mode = gm; } // ld.global.cg measured 2-3 % ahead
     return P;
 }

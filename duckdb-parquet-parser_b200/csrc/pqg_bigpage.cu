@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(kBigThreads) k_big_pages(const DecodeParams P)
                     if (valid) {
                         const uint32_t r = find_run(S, nr, v);
                         const uint32_t ix = S.run_lit[r] ? (ldbits(cb, S.run_data[r] + (v - S.run_first[r]) * bw, bw) & imask) : S.run_data[r];
-                        if (ix < dict_n) x = __ldg(dict + ix); else ok = false; // NULL in the reference: the general kernel redoes the page
+                        if (ix < dict_n) x = P.identity_dict ? static_cast<T>(ix) : __ldg(dict + ix); else ok = false; // NULL in the reference: the general kernel redoes the page
                     }
                     __stcs(out + sl, x);
                 }

@@ -201,6 +201,13 @@ __device__ __forceinline__ void plain_copy(const DecodeParams& P, uint32_t q, co
 // ---------------------------------------------------------------------------------------------
 // fixed-width data pages
 // ---------------------------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ T dict_value(const DecodeParams& P, const uint8_t* dictp, uint32_t ix) {
+    return reinterpret_cast<const T*>(dictp)[ix];
+}
+template <> __device__ __forceinline__ uint32_t dict_value<uint32_t>(const DecodeParams& P, const uint8_t* dictp, uint32_t ix) {
+    return P.identity_dict ? ix : reinterpret_cast<const uint32_t*>(dictp)[ix]; // dictionary-form output keeps the index
+}
+
 template <int W, bool BOOLP>
 __device__ __forceinline__ void decode_fixed_page(const DecodeParams& P, uint32_t q, const DevChunk& ck,
                                                   const uint8_t* dictp, WarpScratch& ws) {
@@ -261,7 +268,7 @@ __device__ __forceinline__ void decode_fixed_page(const DecodeParams& P, uint32_
             if (valid) {
                 if (dict_page) {
                     uint32_t ix = regular ? regular_index2(rs, nn_before + k) : idx_load(ws.idx, k, c.wide);
-                    if (ix < dict_n) v = reinterpret_cast<const T*>(dictp)[ix];
+                    if (ix < dict_n) v = dict_value<T>(P, dictp, ix);
                     else valid = false; // out-of-range index -> null (column_reader.cpp:190-194)
                 } else if (BOOLP) {
                     uint32_t kk = nn_before + k;

@@ -129,7 +129,7 @@ __device__ __forceinline__ bool fast_page(const DecodeParams& P, uint32_t q, con
     const uint32_t dict_s = dict_in_smem ? smem_u32(dictp) : 0u;
     auto get = [&](uint32_t ix) -> T {
         if constexpr (CLUSTER) return dsmem_ld<T>(cd.base + (ix & cd.mask) * W, ix >> cd.shift);
-        else return dict_in_smem ? lds_elem<T>(dict_s + ix * W) : ldg_gather<T>(dict + ix, P.gather_mode);
+        else return P.identity_dict ? static_cast<T>(ix) : (dict_in_smem ? lds_elem<T>(dict_s + ix * W) : ldg_gather<T>(dict + ix, P.gather_mode));
     };
     // index bits straight from aligned shared-memory words; value v sits in group v >> 3 at
     // bit ((v >> 3) * (1 + bw) + 1) * 8 + (v & 7) * bw of the stream: +32 values = +4 groups
@@ -299,7 +299,7 @@ __device__ __forceinline__ void fast_page_opt(const DecodeParams& P, uint32_t q,
                     const uint32_t bit = bit0 + (((k >> 3) * gs + 1u) << 3) + (k & 7u) * bw;
                     ix = __funnelshift_r(ldw(bit >> 5), ldw((bit >> 5) + 1u), bit & 31u) & imask;
                 }
-                if (ix < dict_n) v = dict_in_smem ? dict[ix] : ldg_gather<T>(dict + ix, P.gather_mode);
+                if (ix < dict_n) v = P.identity_dict ? static_cast<T>(ix) : (dict_in_smem ? dict[ix] : ldg_gather<T>(dict + ix, P.gather_mode));
                 else valid = false;
             } else {
                 v = ld_elem<W>(vals + k * W);

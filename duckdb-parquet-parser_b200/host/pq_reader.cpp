@@ -512,10 +512,10 @@ CachedPlan& ParquetReader::cached_plan(int col_idx, int row_group_idx) {
     return cached_plan_range(col_idx, rg0, rg1);
 }
 
-CachedPlan& ParquetReader::cached_plan_range(int col_idx, size_t rg0, size_t rg1) {
+CachedPlan& ParquetReader::cached_plan_range(int col_idx, size_t rg0, size_t rg1, bool dict_indices) {
     if (rg1 > metadata_.row_groups.size() || rg0 > rg1) throw std::runtime_error("Invalid row group index");
     if (col_idx < 0 || col_idx >= static_cast<int>(columns_.size())) throw std::runtime_error("Invalid column index");
-    auto key = std::make_tuple(col_idx, rg0, rg1);
+    auto key = std::make_tuple(col_idx, rg0, rg1, dict_indices ? 1 : 0);
     auto it = plans_.find(key);
     if (it != plans_.end()) return *it->second;
     auto cp = std::make_unique<CachedPlan>();
@@ -527,9 +527,11 @@ CachedPlan& ParquetReader::cached_plan_range(int col_idx, size_t rg0, size_t rg1
     cp->ctx = Device::get(device_).ctx();
     if (cp->t.chunks.empty()) { auto& ref = *cp; plans_[key] = std::move(cp); return ref; }
     if (pqg_buf_alloc(cp->ctx, cp->img.size, &cp->buf) != PQG_OK) throw_ctx(cp->ctx, "device image");
-    if (pqg_plan_create(cp->ctx, cp->buf, cp->t.chunks.data(), static_cast<uint32_t>(cp->t.chunks.size()), cp->t.pages.data(),
-                        static_cast<uint32_t>(cp->t.pages.size()), &cp->plan) != PQG_OK)
+    auto create = dict_indices ? pqg_plan_create_dict_indices : pqg_plan_create;
+    if (create(cp->ctx, cp->buf, cp->t.chunks.data(), static_cast<uint32_t>(cp->t.chunks.size()), cp->t.pages.data(),
+               static_cast<uint32_t>(cp->t.pages.size()), &cp->plan) != PQG_OK)
         throw std::runtime_error(pqg_last_error(cp->ctx));
+    if (dict_indices) cp->width = 4;
     for (size_t c = 0; c < cp->img.ranges.size(); c++) {
         const Range& r = cp->img.ranges[c];
         cp->ranges.push_back(pqg_h2d_range{data_ + r.src_off, r.dst_off, r.len, static_cast<uint32_t>(c), 0});
@@ -592,19 +594,9 @@ void ParquetReader::read_columns_into(const int* col_idx, int n_cols, int row_gr
     read_columns_into_range(col_idx, n_cols, rg0, rg1, dsts, stats);
 }
 
-void ParquetReader::read_columns_into_range(const int* col_idx, int n_cols, size_t rg0, size_t rg1, const ColumnDst* dsts, ColumnReadStats* stats) {
-    if (n_cols < 0 || (n_cols && (!col_idx || !dsts))) throw std::runtime_error("read_columns_into: bad argument");
-    std::vector<CachedPlan*> cps;
-    for (int i = 0; i < n_cols; i++) {
-        CachedPlan& cp = cached_plan_range(col_idx[i], rg0, rg1);
-        if (cp.type == ParquetType::BYTE_ARRAY || cp.width == 0)
-            throw std::runtime_error("read_columns_into: fixed-width columns only (use read_column_columnar for BYTE_ARRAY)");
-        const uint64_t need = cp.t.total_slots * cp.width;
-        if (dsts[i].values_cap < need || (need && !dsts[i].values)) throw std::runtime_error("read_columns_into: values buffer too small");
-        cps.push_back(&cp);
-    }
+void ParquetReader::run_pipelined(const std::vector<CachedPlan*>& cps, const ColumnDst* dsts, ColumnReadStats* stats) {
     // enqueue every column (asynchronous), then wait column by column
-    for (int i = 0; i < n_cols; i++) {
+    for (int i = 0; i < static_cast<int>(cps.size()); i++) {
         CachedPlan& cp = *cps[static_cast<size_t>(i)];
         if (!cp.plan) continue;
         const bool has_validity = pqg_plan_validity(cp.plan) != nullptr;
@@ -617,7 +609,7 @@ void ParquetReader::read_columns_into_range(const int* col_idx, int n_cols, size
                                    dsts[i].values, vdst) != PQG_OK) throw_ctx(cp.ctx, "decode");
     }
     std::string first_error;
-    for (int i = 0; i < n_cols; i++) {
+    for (int i = 0; i < static_cast<int>(cps.size()); i++) {
         CachedPlan& cp = *cps[static_cast<size_t>(i)];
         ColumnReadStats st;
         st.num_slots = cp.t.total_slots;
@@ -635,6 +627,59 @@ void ParquetReader::read_columns_into_range(const int* col_idx, int n_cols, size
         if (stats) stats[i] = st;
     }
     if (!first_error.empty()) throw std::runtime_error(first_error);
+}
+
+void ParquetReader::read_dictionary_indices_into(int col_idx, size_t rg0, size_t rg1, const ColumnDst& dst, ColumnReadStats* stats) {
+    if (col_idx < 0 || col_idx >= static_cast<int>(columns_.size())) throw std::runtime_error("Invalid column index");
+    const ColumnInfo& ci = columns_[static_cast<size_t>(col_idx)];
+    if (ci.type != ParquetType::BYTE_ARRAY)
+        throw std::runtime_error("Column '" + ci.name + "' is not BYTE_ARRAY (type: " + parquet_type_name(ci.type) + ")");
+    CachedPlan& cp = cached_plan_range(col_idx, rg0, rg1, true);
+    const uint64_t need = cp.t.total_slots * 4;
+    if (dst.values_cap < need || (need && !dst.values)) throw std::runtime_error("read_dictionary_indices_into: indices buffer too small");
+    std::vector<CachedPlan*> cps{&cp};
+    run_pipelined(cps, &dst, stats);
+}
+
+void ParquetReader::chunk_dictionary(int col_idx, size_t rg, std::vector<uint32_t>& offsets, std::vector<uint8_t>& chars) const {
+    offsets.assign(1, 0);
+    chars.clear();
+    if (col_idx < 0 || col_idx >= static_cast<int>(columns_.size())) throw std::runtime_error("Invalid column index");
+    if (rg >= metadata_.row_groups.size()) throw std::runtime_error("Invalid row group index");
+    const ColumnInfo& ci = columns_[static_cast<size_t>(col_idx)];
+    if (ci.type != ParquetType::BYTE_ARRAY)
+        throw std::runtime_error("Column '" + ci.name + "' is not BYTE_ARRAY (type: " + parquet_type_name(ci.type) + ")");
+    for (const PageRecord& r : chunk_pages_[rg][static_cast<size_t>(ci.column_index)]) {
+        if (r.type != PageType::DICTIONARY_PAGE) continue;
+        // a later dictionary page replaces the earlier one (reference column_reader.cpp:48-54); chunks
+        // that switch dictionaries are split by the descriptor tables -- report the last one here
+        offsets.assign(1, 0);
+        chars.clear();
+        uint64_t pos = r.payload_off, end = r.payload_off + r.payload_size;
+        for (int32_t k = 0; k < r.num_values; k++) {
+            if (pos + 4 > end) throw std::runtime_error("ByteBuffer: read beyond end (pos=" + std::to_string(pos - r.payload_off) + " need=4 size=" + std::to_string(r.payload_size) + ")");
+            uint32_t len;
+            std::memcpy(&len, data_ + pos, 4);
+            if (pos + 4 + len > end) throw std::runtime_error("ByteBuffer: read beyond end (pos=" + std::to_string(pos + 4 - r.payload_off) + " need=" + std::to_string(len) + " size=" + std::to_string(r.payload_size) + ")");
+            chars.insert(chars.end(), data_ + pos + 4, data_ + pos + 4 + len);
+            offsets.push_back(static_cast<uint32_t>(chars.size()));
+            pos += 4 + len;
+        }
+    }
+}
+
+void ParquetReader::read_columns_into_range(const int* col_idx, int n_cols, size_t rg0, size_t rg1, const ColumnDst* dsts, ColumnReadStats* stats) {
+    if (n_cols < 0 || (n_cols && (!col_idx || !dsts))) throw std::runtime_error("read_columns_into: bad argument");
+    std::vector<CachedPlan*> cps;
+    for (int i = 0; i < n_cols; i++) {
+        CachedPlan& cp = cached_plan_range(col_idx[i], rg0, rg1);
+        if (cp.type == ParquetType::BYTE_ARRAY || cp.width == 0)
+            throw std::runtime_error("read_columns_into: fixed-width columns only (use read_column_columnar for BYTE_ARRAY)");
+        const uint64_t need = cp.t.total_slots * cp.width;
+        if (dsts[i].values_cap < need || (need && !dsts[i].values)) throw std::runtime_error("read_columns_into: values buffer too small");
+        cps.push_back(&cp);
+    }
+    run_pipelined(cps, dsts, stats);
 }
 
 std::vector<Value> ParquetReader::read_column(const std::string& col_name, size_t row_group_idx) {

@@ -211,6 +211,13 @@ public:
     // first use and kept until release_plans() / close.  row_group_idx < 0 = all row groups.
     void read_columns_into(const int* col_idx, int n_cols, int row_group_idx, const ColumnDst* dsts, ColumnReadStats* stats);
     void read_columns_into_range(const int* col_idx, int n_cols, size_t rg_begin, size_t rg_end, const ColumnDst* dsts, ColumnReadStats* stats);
+    // Dictionary-form read of a BYTE_ARRAY column that is dictionary-encoded throughout (late
+    // materialisation): uint32 dictionary indices per slot (0 for nulls) + validity, pipelined like
+    // read_columns_into.  Throws "... not dictionary-encoded throughout" otherwise.  The strings
+    // of slot i are entry indices[i] of chunk_dictionary(row group of i).
+    void read_dictionary_indices_into(int col_idx, size_t rg_begin, size_t rg_end, const ColumnDst& dst, ColumnReadStats* stats);
+    // the dictionary page of one column chunk, parsed on the host: n + 1 offsets into chars
+    void chunk_dictionary(int col_idx, size_t rg, std::vector<uint32_t>& offsets, std::vector<uint8_t>& chars) const;
     void release_plans();
     // The cached device-side state of a column: descriptor tables, device image, decode plan.
     // upload = true copies the column's bytes into the device image (synchronously ordered on
@@ -262,9 +269,10 @@ private:
     std::vector<PageIndexEntry> page_index_;
     std::vector<std::vector<std::vector<PageRecord>>> chunk_pages_; // [rg][chunk column]
     std::vector<std::vector<size_t>> chunk_first_page_;              // [rg][chunk column] -> global id
-    std::map<std::tuple<int, size_t, size_t>, std::unique_ptr<CachedPlan>> plans_; // (column, row groups [begin, end))
+    std::map<std::tuple<int, size_t, size_t, int>, std::unique_ptr<CachedPlan>> plans_; // (column, row groups [begin, end), dictionary form)
     CachedPlan& cached_plan(int col_idx, int row_group_idx);
-    CachedPlan& cached_plan_range(int col_idx, size_t rg_begin, size_t rg_end);
+    CachedPlan& cached_plan_range(int col_idx, size_t rg_begin, size_t rg_end, bool dict_indices = false);
+    void run_pipelined(const std::vector<CachedPlan*>& cps, const ColumnDst* dsts, ColumnReadStats* stats);
 };
 
 } // namespace pqg

@@ -275,6 +275,36 @@ int pqr_read_columns_into_rgs(pqr_reader* r, const int32_t* cols, int32_t n_cols
         return 0;
     }, -1);
 }
+int pqr_read_dictionary_indices_into(pqr_reader* r, int32_t col, int64_t rg_begin, int64_t rg_end, const pqr_dst* dst, pqr_read_stats* stats) {
+    return guarded([&]() -> int {
+        if (rg_begin < 0 || rg_end < rg_begin || !dst) throw std::runtime_error("Invalid row group index");
+        ColumnReadStats st;
+        r->r.read_dictionary_indices_into(col, static_cast<size_t>(rg_begin), static_cast<size_t>(rg_end),
+                                          ColumnDst{dst->values, dst->values_cap, dst->validity, dst->validity_cap}, &st);
+        if (stats) *stats = pqr_read_stats{st.num_slots, st.width, st.has_validity, st.bytes_in, st.bytes_out, st.h2d_bytes, st.d2h_bytes};
+        return 0;
+    }, -1);
+}
+int pqr_chunk_dictionary(const pqr_reader* r, int32_t col, int64_t rg, uint32_t* offsets, int64_t offsets_cap, uint8_t* chars,
+                         int64_t chars_cap, int64_t* n_entries, int64_t* n_bytes) {
+    return guarded([&]() -> int {
+        if (rg < 0) throw std::runtime_error("Invalid row group index");
+        std::vector<uint32_t> off;
+        std::vector<uint8_t> ch;
+        r->r.chunk_dictionary(col, static_cast<size_t>(rg), off, ch);
+        if (n_entries) *n_entries = static_cast<int64_t>(off.size()) - 1;
+        if (n_bytes) *n_bytes = static_cast<int64_t>(ch.size());
+        if (offsets) {
+            if (offsets_cap < static_cast<int64_t>(off.size())) throw std::runtime_error("pqr_chunk_dictionary: offsets buffer too small");
+            std::memcpy(offsets, off.data(), off.size() * 4);
+        }
+        if (chars && !ch.empty()) {
+            if (chars_cap < static_cast<int64_t>(ch.size())) throw std::runtime_error("pqr_chunk_dictionary: chars buffer too small");
+            std::memcpy(chars, ch.data(), ch.size());
+        }
+        return 0;
+    }, -1);
+}
 void pqr_release_plans(pqr_reader* r) { if (r) r->r.release_plans(); }
 
 int pqr_shard_row_groups(const pqr_reader* r, int col, int n_shards, int32_t* out_begin) {

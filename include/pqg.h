@@ -152,6 +152,16 @@ PQG_API void pqg_host_free(void* p);
 PQG_API int pqg_plan_create(pqg_ctx* ctx, const pqg_buf* image, const pqg_chunk_desc* chunks,
                             uint32_t n_chunks, const pqg_page_desc* pages, uint32_t n_pages,
                             pqg_plan** out);
+/* Dictionary-form output of a BYTE_ARRAY column that is dictionary-encoded throughout (late
+ * materialisation, Arrow DictionaryArray style): the plan behaves like a 4-byte fixed-width plan
+ * whose values are the uint32 DICTIONARY INDEX of every slot (0 for nulls, validity as usual;
+ * an index beyond its chunk's dictionary is a null, like the reference treats it).  The
+ * dictionaries themselves are the chunks' dictionary pages, which the caller already has.
+ * All fixed-width entry points apply (run, run_pipelined, download).  PQG_ERR_UNSUPPORTED when
+ * some chunk has no dictionary or falls back to PLAIN pages. */
+PQG_API int pqg_plan_create_dict_indices(pqg_ctx* ctx, const pqg_buf* image, const pqg_chunk_desc* chunks,
+                                         uint32_t n_chunks, const pqg_page_desc* pages, uint32_t n_pages,
+                                         pqg_plan** out);
 PQG_API void pqg_plan_destroy(pqg_ctx* ctx, pqg_plan* plan);
 /* re-point a plan at another resident image with the same layout (pipelined ingest) */
 PQG_API int pqg_plan_set_image(pqg_ctx* ctx, pqg_plan* plan, const pqg_buf* image);

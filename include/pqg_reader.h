@@ -154,6 +154,16 @@ typedef struct pqr_read_stats {
 } pqr_read_stats;
 PQG_API int pqr_read_columns_into(pqr_reader* r, const int32_t* cols, int32_t n_cols, int32_t rg,
                                   const pqr_dst* dsts, pqr_read_stats* stats);
+/* Dictionary-form read (late materialisation) of a BYTE_ARRAY column that is dictionary-encoded
+ * throughout: uint32 dictionary index per slot (0 for nulls) + validity, pipelined like
+ * pqr_read_columns_into; the string of slot i is entry indices[i] of the dictionary of i's row
+ * group (pqr_chunk_dictionary, parsed on the host from the dictionary page).  Fails with
+ * "... not dictionary-encoded throughout" for columns with PLAIN pages. */
+PQG_API int pqr_read_dictionary_indices_into(pqr_reader* r, int32_t col, int64_t rg_begin, int64_t rg_end,
+                                             const pqr_dst* dst, pqr_read_stats* stats);
+/* offsets: n_entries + 1 uint32 into chars; pass NULL buffers to query the sizes first */
+PQG_API int pqr_chunk_dictionary(const pqr_reader* r, int32_t col, int64_t rg, uint32_t* offsets, int64_t offsets_cap,
+                                 uint8_t* chars, int64_t chars_cap, int64_t* n_entries, int64_t* n_bytes);
 PQG_API void pqr_release_plans(pqr_reader* r);
 
 /* chunk-index prototype (src/main.cpp:21-32): tuple_to_chunk has num_rows entries;

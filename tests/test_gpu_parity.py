@@ -220,3 +220,44 @@ def test_config1_full_size_against_the_reference(pq, oracle, tmp_path):
     finally:
         src.close(h)
         r.close()
+
+
+def test_dictionary_form_read_reconstructs_the_strings(pq, oracle, files):
+    """late materialisation: uint32 dictionary indices per slot + the chunk dictionaries give
+    back exactly the strings (and nulls) of read_column; columns with PLAIN pages are refused"""
+    seen_dict = seen_plain = 0
+    for name, path in files.items():
+        r = pq.Reader(path)
+        try:
+            for c in range(r.num_columns):
+                ci = r.column_info(c)
+                if ci["type"] != BYTE_ARRAY:
+                    continue
+                try:
+                    idx, val, st = r.read_dictionary_indices(c)
+                except pq.PqgError as e:
+                    assert "not dictionary-encoded throughout" in str(e), str(e)
+                    seen_plain += 1
+                    continue
+                seen_dict += 1
+                exp = r.read_column(ci["name"])
+                n = len(exp["is_null"])
+                assert st["num_slots"] == n and st["width"] == 4
+                valid = np.ones(n, dtype=bool)
+                if val is not None:
+                    valid = ((val[np.arange(n) >> 5] >> (np.arange(n) & 31).astype(np.uint32)) & 1).astype(bool)
+                assert np.array_equal(~valid, exp["is_null"].astype(bool)), (name, ci["name"])
+                assert not idx[~valid].any()
+                row = 0
+                exp_off, exp_chars = exp["str_off"].astype(np.int64), exp["chars"].tobytes()
+                for rg in range(r.num_row_groups):
+                    nr = r.row_group_num_rows(rg)
+                    off, chars = r.chunk_dictionary(c, rg)
+                    for i in list(range(row, min(row + 200, row + nr))) + [row + nr - 1]:
+                        if valid[i]:
+                            k = int(idx[i])
+                            assert chars[off[k]:off[k + 1]] == exp_chars[exp_off[i]:exp_off[i + 1]], (name, ci["name"], i)
+                    row += nr
+        finally:
+            r.close()
+    assert seen_dict >= 3 and seen_plain >= 2
