@@ -565,7 +565,7 @@ static int fixed_subrun(pqg_ctx* ctx, pqg_plan* p, uint32_t c0, uint32_t c1, boo
     P.tile_lo = p->chunk_tile_begin[c0]; P.tile_hi = p->chunk_tile_begin[c1];
     P.slow_lo = p->chunk_slow_begin[c0]; P.slow_hi = p->chunk_slow_begin[c1];
     bool any_dict = false;
-    for (uint32_t c = c0; c < c1; c++) any_dict = any_dict || p->chunks[c].has_dict;
+    for (uint32_t c = c0; c < c1 && !p->identity; c++) any_dict = any_dict || p->chunks[c].has_dict; // dictionary-form plans keep no device dictionary
     if (e == cudaSuccess && any_dict) { e = launch_dict_prepare(P, c1 - c0, p->width, p->max_dict_blocks, s); launches++; }
     if (e == cudaSuccess && ev_tiles_begin) e = cudaEventRecord(ev_tiles_begin, s);
     if (e == cudaSuccess && P.tile_hi > P.tile_lo) {
