@@ -167,8 +167,7 @@ def regex_bench(pq, ctx_device, stream, steps, warmup, peak, rows, rg_rows):
         orc = oraclelib.Oracle()
         take = min(rows, rg_rows)
         sub = dict(str_off=col["str_off"][:take + 1], chars=col["chars"][:take * 33])
-        d = "/dev/shm" if os.path.isdir("/dev/shm") else "/tmp"
-        path = os.path.join(d, f"pqg_bench_regex_{os.getpid()}.parquet")
+        path = os.path.join(scratch_dir(1 << 30), f"pqg_bench_regex_{os.getpid()}.parquet")
         gg = pq.generate(specs, [sub], [take])
         gg.write(path)
         gg.free()
@@ -201,6 +200,19 @@ def regex_bench(pq, ctx_device, stream, steps, warmup, peak, rows, rg_rows):
     reader.close()
     del dev_img
     return res
+
+
+def scratch_dir(need_bytes):
+    """RAM-backed scratch for the CPU arm's sample file when it has room (page cache warm either way)"""
+    import shutil
+    import tempfile
+    for d in ("/dev/shm", tempfile.gettempdir()):
+        try:
+            if os.path.isdir(d) and shutil.disk_usage(d).free > need_bytes:
+                return d
+        except OSError:
+            pass
+    return tempfile.gettempdir()
 
 
 def rg_split(rows, rg_rows):
@@ -298,8 +310,7 @@ def cpu_reference_run(pq, cols, rows, rg_rows, sample_rgs, steps, warmup, thread
     if not oraclelib.Ref.available():
         raise RuntimeError("oracle/_ref/libpqref.so is missing (built by __graft_entry__.build() where /root/reference exists)")
     ref = oraclelib.Ref()
-    d = "/dev/shm" if os.path.isdir("/dev/shm") else "/tmp"
-    path = os.path.join(d, f"pqg_bench_ref_{os.getpid()}.parquet")
+    path = os.path.join(scratch_dir(3 << 30), f"pqg_bench_ref_{os.getpid()}.parquet")
     take, _ = ref_sample_file(pq, cols, rows, rg_rows, sample_rgs, path)
     try:
         payload = payload_bytes_of(pq, path)
