@@ -269,47 +269,60 @@ __device__ __forceinline__ void fast_page_opt(const DecodeParams& P, uint32_t q,
         if (bw > 32u || !check_regular2(vals, size - pos - 1u, bw, nn, &rs)) { if (l == 0) to_slow(P, q); return; }
     } else if (static_cast<uint64_t>(nn) * W > size - pos) { if (l == 0) to_slow(P, q); return; }
     const T* dict = reinterpret_cast<const T*>(dictp);
-    // emission: 32 absolute slots per step, aligned to validity words; 32-bit arithmetic only
-    const uint32_t head = static_cast<uint32_t>(pd.out_row_base & 31u); // slots of the first word owned by the previous page
-    T* outp = reinterpret_cast<T*>(P.values) + (pd.out_row_base - head);
-    uint32_t* vp = P.validity + (pd.out_row_base >> 5);
-    const uint32_t total = head + n;
-    // index stream as aligned shared-memory words
+    // emission: 64 page-relative slots per step, two adjacent slots per lane (one 16-byte store
+    // for 8-byte values); the validity image is written to global memory afterwards in one step
+    T* outp = reinterpret_cast<T*>(P.values) + pd.out_row_base;
+    const bool pair_aligned = (reinterpret_cast<uintptr_t>(outp) & (2 * W - 1)) == 0;
     const uint32_t va = smem_u32(vals);
     const SmemWords ldw{va & ~3u};
     const uint32_t bit0 = (va & 3u) * 8u;
     const uint32_t gs = 1u + bw, imask = bw >= 32u ? 0xffffffffu : ((1u << bw) - 1u);
-    for (uint32_t j = 0, wj = 0; j < total; j += 32, wj++) {
-        const uint32_t sl = j + l;
-        const bool in = sl >= head && sl < total;
-        const uint32_t sr = sl - head;
-        bool valid = false;
-        uint32_t k = 0;
-        if (in) {
-            const uint32_t wv = vwords[sr >> 5];
-            valid = (wv >> (sr & 31u)) & 1u;
-            k = rankbase[sr >> 5] + __popc(wv & ((1u << (sr & 31u)) - 1u));
+    auto value_of = [&](uint32_t k, bool* bad) -> T {
+        if (!dict_page) return ld_elem<W>(vals + k * W);
+        uint32_t ix;
+        if (k >= rs.tail_start) ix = rs.tail_val;
+        else {
+            const uint32_t bit = bit0 + (((k >> 3) * gs + 1u) << 3) + (k & 7u) * bw;
+            ix = __funnelshift_r(ldw(bit >> 5), ldw((bit >> 5) + 1u), bit & 31u) & imask;
         }
-        T v = 0;
-        if (valid) {
-            if (dict_page) {
-                uint32_t ix;
-                if (k >= rs.tail_start) ix = rs.tail_val;
-                else {
-                    const uint32_t bit = bit0 + (((k >> 3) * gs + 1u) << 3) + (k & 7u) * bw;
-                    ix = __funnelshift_r(ldw(bit >> 5), ldw((bit >> 5) + 1u), bit & 31u) & imask;
-                }
-                if (ix < dict_n) v = P.identity_dict ? static_cast<T>(ix) : (dict_in_smem ? dict[ix] : ldg_gather<T>(dict + ix, P.gather_mode));
-                else valid = false;
+        if (ix >= dict_n) { *bad = true; return T(0); } // NULL in the reference (column_reader.cpp:190-194)
+        return P.identity_dict ? static_cast<T>(ix) : (dict_in_smem ? dict[ix] : ldg_gather<T>(dict + ix, P.gather_mode));
+    };
+    for (uint32_t j = 0; j < n; j += 64) {
+        const uint32_t s0 = j + 2u * l;
+        if (s0 < n) {
+            const uint32_t wv = vwords[s0 >> 5], b = s0 & 31u;
+            const bool v0 = (wv >> b) & 1u, v1 = (s0 + 1u < n) && ((wv >> (b + 1u)) & 1u);
+            const uint32_t k0 = rankbase[s0 >> 5] + __popc(wv & ((1u << b) - 1u));
+            bool bad0 = false, bad1 = false;
+            const T x0 = v0 ? value_of(k0, &bad0) : T(0);
+            const T x1 = v1 ? value_of(k0 + (v0 ? 1u : 0u), &bad1) : T(0);
+            if (bad0 | bad1) atomicAnd(&vwords[s0 >> 5], ~((bad0 ? 1u : 0u) << b | (bad1 ? 2u : 0u) << b));
+            if (s0 + 1u < n && pair_aligned) {
+                if constexpr (W == 8) { __stcs(reinterpret_cast<ulonglong2*>(outp + s0), make_ulonglong2(x0, x1)); }
+                else { __stcs(reinterpret_cast<uint2*>(outp + s0), make_uint2(x0, x1)); }
             } else {
-                v = ld_elem<W>(vals + k * W);
+                st_stream<T>(outp + s0, x0);
+                if (s0 + 1u < n) st_stream<T>(outp + s0 + 1u, x1);
             }
         }
-        if (in) st_stream<T>(outp + sl, v);
-        const uint32_t m = __ballot_sync(0xffffffffu, valid);
-        if (l == 0) {
-            if (j >= head && j + 32u <= total) vp[wj] = m;
-            else if (m) atomicOr(&vp[wj], m);
+    }
+    __syncwarp();
+    // validity: the page's image shifted to its position in the column's bitmap, one word per lane
+    {
+        const uint32_t head = static_cast<uint32_t>(pd.out_row_base & 31u), nwords = (n + 31u) >> 5;
+        uint32_t* vp = P.validity + (pd.out_row_base >> 5);
+        const uint32_t cur = l < nwords ? vwords[l] : 0u;
+        const uint32_t prev = (l > 0 && l <= nwords) ? vwords[l - 1] : 0u;
+        const uint32_t gw = head ? ((cur << head) | (prev >> (32u - head))) : cur;
+        const uint32_t total = head + n, gwords = (total + 31u) >> 5;
+        if (l < gwords) {
+            const bool full = (l > 0 || head == 0) && (l + 1u) * 32u <= total;
+            if (full) vp[l] = gw; else if (gw) atomicOr(&vp[l], gw);
+        }
+        if (l == 0 && gwords > 32u) { // head pushes the last bits into a 33rd word
+            const uint32_t last = vwords[31] >> (32u - head);
+            if (last) atomicOr(&vp[32], last);
         }
     }
     __syncwarp();
