@@ -94,6 +94,28 @@ template <> __device__ __forceinline__ uint32_t ldg_gather<uint32_t>(const uint3
     return v;
 }
 
+// How a dictionary index turns into a value -- resolved ONCE per page and compiled into the
+// inner loops (a run-time choice per value cost ~18 instructions and divergent branches):
+enum { kDictIdent = 0, kDictSmem = 1, kDictGlobal = 2, kDictCluster = 3 };
+template <int M> struct ModeTag { static constexpr int value = M; };
+struct DictRef { const void* gptr; uint32_t saddr; ClusterDict cd; };
+template <typename T, int W, int MODE>
+__device__ __forceinline__ T dict_get(const DictRef& d, uint32_t ix) {
+    if constexpr (MODE == kDictIdent) return static_cast<T>(ix);
+    else if constexpr (MODE == kDictSmem) return lds_elem<T>(d.saddr + ix * W);
+    else if constexpr (MODE == kDictCluster) return dsmem_ld<T>(d.cd.base + (ix & d.cd.mask) * W, ix >> d.cd.shift);
+    else return ldg_gather<T>(static_cast<const T*>(d.gptr) + ix, 1u); // ld.global.cg
+}
+template <class F>
+__device__ __forceinline__ void with_dict_mode(int mode, F&& f) {
+    switch (mode) {
+        case kDictIdent: f(ModeTag<kDictIdent>{}); break;
+        case kDictSmem: f(ModeTag<kDictSmem>{}); break;
+        case kDictCluster: f(ModeTag<kDictCluster>{}); break;
+        default: f(ModeTag<kDictGlobal>{}); break;
+    }
+}
+
 // One warp decodes one page out of the staged tile.  `pg` = first payload byte (shared).
 template <int W, bool CLUSTER = false>
 __device__ __forceinline__ bool fast_page(const DecodeParams& P, uint32_t q, const pqg_page_desc& pd, const uint8_t* pg,
@@ -125,44 +147,41 @@ __device__ __forceinline__ bool fast_page(const DecodeParams& P, uint32_t q, con
     const uint8_t* s = pg + 1;
     RegStream rs;
     if (bw > 32 || !check_regular2(s, size - 1, bw, n, &rs)) { if (l == 0) to_slow(P, q); return false; }
-    const T* dict = reinterpret_cast<const T*>(dictp);
-    const uint32_t dict_s = dict_in_smem ? smem_u32(dictp) : 0u;
-    auto get = [&](uint32_t ix) -> T {
-        if constexpr (CLUSTER) return dsmem_ld<T>(cd.base + (ix & cd.mask) * W, ix >> cd.shift);
-        else return P.identity_dict ? static_cast<T>(ix) : (dict_in_smem ? lds_elem<T>(dict_s + ix * W) : ldg_gather<T>(dict + ix, P.gather_mode));
-    };
+    const DictRef dref{dictp, dict_in_smem ? smem_u32(dictp) : 0u, cd};
+    const int mode = CLUSTER ? kDictCluster : (P.identity_dict ? kDictIdent : (dict_in_smem ? kDictSmem : kDictGlobal));
     // index bits straight from aligned shared-memory words; value v sits in group v >> 3 at
     // bit ((v >> 3) * (1 + bw) + 1) * 8 + (v & 7) * bw of the stream: +32 values = +4 groups
     const uint32_t sa = smem_u32(s);
     const SmemWords ldw{sa & ~3u};
     const uint32_t gs = 1u + bw, imask = bw >= 32u ? 0xffffffffu : ((1u << bw) - 1u);
-    uint32_t bit = (sa & 3u) * 8u + (((l >> 3) * gs + 1u) << 3) + (l & 7u) * bw;
+    const uint32_t bit_l = (sa & 3u) * 8u + (((l >> 3) * gs + 1u) << 3) + (l & 7u) * bw;
     const uint32_t step32 = 32u * gs;
-    auto index_at = [&](uint32_t bitpos, uint32_t k) -> uint32_t {
-        const uint32_t ix = __funnelshift_r(ldw(bitpos >> 5), ldw((bitpos >> 5) + 1u), bitpos & 31u) & imask;
-        return k >= rs.tail_start ? rs.tail_val : ix;
-    };
     bool bad = false;
-    uint32_t v = l;
-    for (; v + 96 < n; v += 128, bit += 4u * step32) {
-        const uint32_t i0 = index_at(bit, v), i1 = index_at(bit + step32, v + 32);
-        const uint32_t i2 = index_at(bit + 2u * step32, v + 64), i3 = index_at(bit + 3u * step32, v + 96);
-        bad = bad || i0 >= dict_n || i1 >= dict_n || i2 >= dict_n || i3 >= dict_n;
-        T x0 = i0 < dict_n ? get(i0) : T(0);
-        T x1 = i1 < dict_n ? get(i1) : T(0);
-        T x2 = i2 < dict_n ? get(i2) : T(0);
-        T x3 = i3 < dict_n ? get(i3) : T(0);
-        st_stream<T>(out + v, x0); st_stream<T>(out + v + 32, x1);
-        st_stream<T>(out + v + 64, x2); st_stream<T>(out + v + 96, x3);
-    }
-    for (; v < n; v += 32, bit += step32) {
-        const uint32_t i0 = index_at(bit, v);
-        T x0 = 0;
-        if (i0 < dict_n) x0 = get(i0); else bad = true;
-        st_stream<T>(out + v, x0);
-    }
-    // an out-of-range index is a NULL in the reference (column_reader.cpp:190-194): the
-    // general kernel redoes the page with the validity semantics
+    with_dict_mode(mode, [&](auto tag) {
+        constexpr int MODE = decltype(tag)::value;
+        auto index_at = [&](uint32_t bitpos, uint32_t k) -> uint32_t {
+            const uint32_t ix = __funnelshift_r(ldw(bitpos >> 5), ldw((bitpos >> 5) + 1u), bitpos & 31u) & imask;
+            return k >= rs.tail_start ? rs.tail_val : ix;
+        };
+        uint32_t bit = bit_l, v = l;
+        for (; v + 96 < n; v += 128, bit += 4u * step32) {
+            const uint32_t i0 = index_at(bit, v), i1 = index_at(bit + step32, v + 32);
+            const uint32_t i2 = index_at(bit + 2u * step32, v + 64), i3 = index_at(bit + 3u * step32, v + 96);
+            bad = bad || i0 >= dict_n || i1 >= dict_n || i2 >= dict_n || i3 >= dict_n;
+            // (an out-of-range index reads entry 0 instead of branching: the page is redone anyway)
+            const T x0 = dict_get<T, W, MODE>(dref, i0 < dict_n ? i0 : 0u);
+            const T x1 = dict_get<T, W, MODE>(dref, i1 < dict_n ? i1 : 0u);
+            const T x2 = dict_get<T, W, MODE>(dref, i2 < dict_n ? i2 : 0u);
+            const T x3 = dict_get<T, W, MODE>(dref, i3 < dict_n ? i3 : 0u);
+            st_stream<T>(out + v, x0); st_stream<T>(out + v + 32, x1);
+            st_stream<T>(out + v + 64, x2); st_stream<T>(out + v + 96, x3);
+        }
+        for (; v < n; v += 32, bit += step32) {
+            const uint32_t i0 = index_at(bit, v);
+            bad = bad || i0 >= dict_n;
+            st_stream<T>(out + v, dict_get<T, W, MODE>(dref, i0 < dict_n ? i0 : 0u));
+        }
+    });
     const bool any_bad = __any_sync(0xffffffffu, bad);
     if (any_bad && l == 0) { to_slow(P, q); atomicAdd(&P.err->bad_index, 1u); }
     return !any_bad;
@@ -268,45 +287,55 @@ __device__ __forceinline__ void fast_page_opt(const DecodeParams& P, uint32_t q,
         vals = pg + pos + 1;
         if (bw > 32u || !check_regular2(vals, size - pos - 1u, bw, nn, &rs)) { if (l == 0) to_slow(P, q); return; }
     } else if (static_cast<uint64_t>(nn) * W > size - pos) { if (l == 0) to_slow(P, q); return; }
-    const T* dict = reinterpret_cast<const T*>(dictp);
     // emission: 64 page-relative slots per step, two adjacent slots per lane (one 16-byte store
-    // for 8-byte values); the validity image is written to global memory afterwards in one step
+    // for 8-byte values); the validity image is written to global memory afterwards in one step.
+    // Branch-free per value: null lanes compute with a clamped rank and discard the result.
     T* outp = reinterpret_cast<T*>(P.values) + pd.out_row_base;
     const bool pair_aligned = (reinterpret_cast<uintptr_t>(outp) & (2 * W - 1)) == 0;
     const uint32_t va = smem_u32(vals);
     const SmemWords ldw{va & ~3u};
     const uint32_t bit0 = (va & 3u) * 8u;
     const uint32_t gs = 1u + bw, imask = bw >= 32u ? 0xffffffffu : ((1u << bw) - 1u);
-    auto value_of = [&](uint32_t k, bool* bad) -> T {
-        if (!dict_page) return ld_elem<W>(vals + k * W);
-        uint32_t ix;
-        if (k >= rs.tail_start) ix = rs.tail_val;
-        else {
-            const uint32_t bit = bit0 + (((k >> 3) * gs + 1u) << 3) + (k & 7u) * bw;
-            ix = __funnelshift_r(ldw(bit >> 5), ldw((bit >> 5) + 1u), bit & 31u) & imask;
-        }
-        if (ix >= dict_n) { *bad = true; return T(0); } // NULL in the reference (column_reader.cpp:190-194)
-        return P.identity_dict ? static_cast<T>(ix) : (dict_in_smem ? dict[ix] : ldg_gather<T>(dict + ix, P.gather_mode));
-    };
-    for (uint32_t j = 0; j < n; j += 64) {
-        const uint32_t s0 = j + 2u * l;
-        if (s0 < n) {
-            const uint32_t wv = vwords[s0 >> 5], b = s0 & 31u;
-            const bool v0 = (wv >> b) & 1u, v1 = (s0 + 1u < n) && ((wv >> (b + 1u)) & 1u);
-            const uint32_t k0 = rankbase[s0 >> 5] + __popc(wv & ((1u << b) - 1u));
-            bool bad0 = false, bad1 = false;
-            const T x0 = v0 ? value_of(k0, &bad0) : T(0);
-            const T x1 = v1 ? value_of(k0 + (v0 ? 1u : 0u), &bad1) : T(0);
-            if (bad0 | bad1) atomicAnd(&vwords[s0 >> 5], ~((bad0 ? 1u : 0u) << b | (bad1 ? 2u : 0u) << b));
-            if (s0 + 1u < n && pair_aligned) {
-                if constexpr (W == 8) { __stcs(reinterpret_cast<ulonglong2*>(outp + s0), make_ulonglong2(x0, x1)); }
-                else { __stcs(reinterpret_cast<uint2*>(outp + s0), make_uint2(x0, x1)); }
+    const uint32_t kmax = nn ? nn - 1u : 0u;
+    const DictRef dref{dictp, dict_in_smem ? smem_u32(dictp) : 0u, ClusterDict{0, 0, 0}};
+    const int mode = !dict_page ? -1 : (P.identity_dict ? kDictIdent : (dict_in_smem ? kDictSmem : kDictGlobal));
+    auto emit = [&](auto tag) {
+        constexpr int MODE = decltype(tag)::value; // -1: PLAIN
+        auto value_of = [&](uint32_t k, bool valid, bool* bad) -> T {
+            if constexpr (MODE < 0) {
+                return valid ? ld_elem<W>(vals + k * W) : T(0);
             } else {
-                st_stream<T>(outp + s0, x0);
-                if (s0 + 1u < n) st_stream<T>(outp + s0 + 1u, x1);
+                const uint32_t bit = bit0 + (((k >> 3) * gs + 1u) << 3) + (k & 7u) * bw;
+                uint32_t ix = __funnelshift_r(ldw(bit >> 5), ldw((bit >> 5) + 1u), bit & 31u) & imask;
+                ix = k >= rs.tail_start ? rs.tail_val : ix;
+                const bool in_range = ix < dict_n;
+                *bad = valid && !in_range; // NULL in the reference (column_reader.cpp:190-194)
+                const T x = dict_get<T, W, MODE>(dref, in_range ? ix : 0u);
+                return (valid && in_range) ? x : T(0);
+            }
+        };
+        for (uint32_t j = 0; j < n; j += 64) {
+            const uint32_t s0 = j + 2u * l;
+            if (s0 < n) {
+                const uint32_t wv = vwords[s0 >> 5], b = s0 & 31u;
+                const bool v0 = (wv >> b) & 1u, v1 = (s0 + 1u < n) && ((wv >> (b + 1u)) & 1u);
+                const uint32_t k0 = rankbase[s0 >> 5] + __popc(wv & ((1u << b) - 1u));
+                bool bad0 = false, bad1 = false;
+                const T x0 = value_of(min(k0, kmax), v0, &bad0);
+                const T x1 = value_of(min(k0 + (v0 ? 1u : 0u), kmax), v1, &bad1);
+                if (bad0 | bad1) atomicAnd(&vwords[s0 >> 5], ~((bad0 ? 1u : 0u) << b | (bad1 ? 2u : 0u) << b));
+                if (s0 + 1u < n && pair_aligned) {
+                    if constexpr (W == 8) { __stcs(reinterpret_cast<ulonglong2*>(outp + s0), make_ulonglong2(x0, x1)); }
+                    else { __stcs(reinterpret_cast<uint2*>(outp + s0), make_uint2(x0, x1)); }
+                } else {
+                    st_stream<T>(outp + s0, x0);
+                    if (s0 + 1u < n) st_stream<T>(outp + s0 + 1u, x1);
+                }
             }
         }
-    }
+    };
+    if (mode < 0) emit(ModeTag<-1>{});
+    else with_dict_mode(mode, emit);
     __syncwarp();
     // validity: the page's image shifted to its position in the column's bitmap, one word per lane
     {
