@@ -81,6 +81,16 @@ def col_str_dict(rng, n, nkeys, null_frac=0.3):
     return strings_to_col([b"city_%06d_x" % i for i in idx], nulls(rng, n, null_frac))
 
 
+SHORTS = [b"", b"a", b"bb", b"\x00\x00\x00", b"ccc", b"abcdabcdabcd", b"\x03", b"zz\x00"]
+
+
+def col_str_short_dict(rng, n, null_frac=0.2):
+    """dictionary of empty / 1-3 byte / NUL-bearing strings: defeats the length-prefix
+    speculation (false candidates) -> the sequential fallbacks must produce the same result"""
+    idx = rng.integers(0, len(SHORTS), size=n)
+    return strings_to_col([SHORTS[i] for i in idx], nulls(rng, n, null_frac))
+
+
 def col_email(rng, n, null_frac=0.0, noise_frac=0.2):
     out = []
     u = rng.integers(0, 10**9, size=n)
@@ -166,9 +176,9 @@ def standard_files():
     add("strings",
         [("city", BYTE_ARRAY, OPTIONAL, UTF8), ("s64k", BYTE_ARRAY, OPTIONAL, UTF8),
          ("email", BYTE_ARRAY, REQUIRED, UTF8), ("emailn", BYTE_ARRAY, OPTIONAL, UTF8),
-         ("wild", BYTE_ARRAY, OPTIONAL, -1), ("allnull", BYTE_ARRAY, OPTIONAL, UTF8)],
+         ("wild", BYTE_ARRAY, OPTIONAL, -1), ("allnull", BYTE_ARRAY, OPTIONAL, UTF8), ("shorts", BYTE_ARRAY, OPTIONAL, -1)],
         lambda rng: [[col_city(rng, n), col_str_dict(rng, n, 3000), col_email(rng, n), col_email(rng, n, 0.3),
-                      col_str_varlen(rng, n), strings_to_col([b""] * n, np.ones(n, dtype=np.uint8))]
+                      col_str_varlen(rng, n), strings_to_col([b""] * n, np.ones(n, dtype=np.uint8)), col_str_short_dict(rng, n)]
                      for n in (30000, 4321)])
     add("bools",
         [("b", BOOLEAN, REQUIRED, -1), ("bn", BOOLEAN, OPTIONAL, -1)],

@@ -261,3 +261,39 @@ def test_dictionary_form_read_reconstructs_the_strings(pq, oracle, files):
         finally:
             r.close()
     assert seen_dict >= 3 and seen_plain >= 2
+
+
+def test_large_string_dictionary(pq, oracle, tmp_path):
+    """a 70 K-entry BYTE_ARRAY dictionary (1.2 MB dictionary page: the segmented speculative walk of
+    k_dict_prepare with 1024 segments), OPTIONAL with 30 % nulls, two row groups"""
+    from oraclelib import BYTE_ARRAY as BA, OPTIONAL, UTF8
+    rng = np.random.default_rng(17)
+    n, nkeys = 400_000, 70_000
+    keys = np.frombuffer(b"".join(b"city_%06d_x" % i for i in range(nkeys)), dtype=np.uint8).reshape(nkeys, 13)
+    idx = rng.integers(0, nkeys, size=2 * n)
+    col = dict(str_off=np.arange(2 * n + 1, dtype=np.uint64) * 13, chars=keys[idx].reshape(-1),
+               is_null=(rng.random(2 * n) < 0.3).astype(np.uint8))
+    g = pq.generate([("s", BA, OPTIONAL, UTF8)], [col], [n, n])
+    path = g.write(str(tmp_path / "bigdict.parquet"))
+    g.free()
+    r = pq.Reader(path)
+    h = oracle.open(path)
+    try:
+        chunks, nc, _, _, _ = r.column_tables(0, -1)
+        assert nc == 2 and all(chunks[i].has_dict and chunks[i].dict_num_values > 60_000 for i in range(nc))
+        got = to_values(r.read_column("s"))
+        assert got.diff(oracle.read_column(h, "s")) is None
+        bits, _ = r.regex_prune(0, r"^city_0000[0-9]{2}_x$")
+        assert np.array_equal(bits, oracle.regex_prune(h, 0, r"^city_0000[0-9]{2}_x$", False))
+        ix, val, _ = r.read_dictionary_indices(0)
+        off, chars = r.chunk_dictionary(0, 1)
+        exp = oracle.read_column_by_idx(h, 1, 0)
+        valid = ((val[np.arange(2 * n) >> 5] >> (np.arange(2 * n) & 31).astype(np.uint32)) & 1).astype(bool)[n:]
+        assert np.array_equal(~valid, exp.is_null.astype(bool))
+        for i in range(0, n, 997):
+            if valid[i]:
+                k = int(ix[n + i])
+                assert chars[off[k]:off[k + 1]] == exp.string(i)
+    finally:
+        oracle.close(h)
+        r.close()
