@@ -268,7 +268,7 @@ def test_large_string_dictionary(pq, oracle, tmp_path):
     k_dict_prepare with 1024 segments), OPTIONAL with 30 % nulls, two row groups"""
     from oraclelib import BYTE_ARRAY as BA, OPTIONAL, UTF8
     rng = np.random.default_rng(17)
-    n, nkeys = 400_000, 70_000
+    n, nkeys = 600_000, 70_000  # distinct <= non_null / 5 keeps the chunk dictionary-encoded
     keys = np.frombuffer(b"".join(b"city_%06d_x" % i for i in range(nkeys)), dtype=np.uint8).reshape(nkeys, 13)
     idx = rng.integers(0, nkeys, size=2 * n)
     col = dict(str_off=np.arange(2 * n + 1, dtype=np.uint64) * 13, chars=keys[idx].reshape(-1),
