@@ -409,31 +409,42 @@ struct SmemWords {
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(base + 4u * wi));
         return v;
     }
+    __device__ __forceinline__ uint32_t u16at(uint32_t apos) const { // unaligned u16 at byte apos
+        uint32_t b0, b1;
+        asm volatile("ld.shared.u8 %0, [%2];\n\tld.shared.u8 %1, [%2+1];" : "=r"(b0), "=r"(b1) : "r"(base + apos));
+        return b0 | (b1 << 8);
+    }
 };
 struct GenericWords {
     const uint32_t* base;
     __device__ __forceinline__ uint32_t operator()(uint32_t wi) const { return base[wi]; }
+    __device__ __forceinline__ uint32_t u16at(uint32_t apos) const {
+        const uint8_t* b = reinterpret_cast<const uint8_t*>(base) + apos;
+        return static_cast<uint32_t>(b[0]) | (static_cast<uint32_t>(b[1]) << 8);
+    }
 };
 __device__ __forceinline__ uint32_t zero_byte_mask32(uint32_t w) { // bit 8i+7 set iff byte i == 0 (exact)
     return ~(((w & 0x7f7f7f7fu) + 0x7f7f7f7fu) | w | 0x7f7f7f7fu);
 }
 // u16 at byte position apos of the word stream
 template <class LD>
-__device__ __forceinline__ uint32_t ld16_at(const LD& ld, uint32_t apos) {
-    uint32_t wi = apos >> 2, sh = (apos & 3u) * 8u;
-    uint32_t w0 = ld(wi);
-    uint32_t w1 = sh > 16u ? ld(wi + 1) : 0u;
-    return __funnelshift_r(w0, w1, sh) & 0xffffu;
-}
+__device__ __forceinline__ uint32_t ld16_at(const LD& ld, uint32_t apos) { return ld.u16at(apos); }
 
-// `ld` addresses aligned words; the value section starts `o` (0..3) bytes into word 0.
-// Per lane: one pass over R <= 64 byte positions building a 64-bit candidate mask with
-// branch-free zero-byte tricks (1 load + ~10 ALU ops per 4 positions), then the (1-3) candidates
-// of the lane are range-checked and kept in registers; warp prefix sum; ordered write; parallel
-// chain verification.
+// `ld` addresses aligned words; the value section starts `o` (0..3) bytes into word 0 ("A-space"
+// = byte positions counted from word 0).  Lane l owns the R <= 64 A-space positions from l * R.
+//  1. candidate flags, 4 positions per step: zero-byte masks of two neighbouring words, funnel
+//     shifted so that bit 8k+7 says "bytes k+2 and k+3 are zero", accumulated with one shift + one
+//     LOP3 per step into two 32-bit words; flag of position 4i+k (i = step, k = byte) sits at bit
+//     8k+i of its word.
+//  2. a flag whose successor position is flagged too is dropped: the byte before a prefix
+//     <len, 0, 0, 0> of a string shorter than 256 bytes is always such a shadow.  (Dropping is a
+//     heuristic only: whatever survives is verified as an exact chain below.)
+//  3. the 1-4 survivors per lane are range-checked against their own length and kept sorted in
+//     registers; warp prefix sum; ordered write; parallel chain verification.
+// *lane_pos / *lane_len (optional) return cand[lane] and its length for lane < nn.
 template <class LD>
 __device__ __forceinline__ bool find_headers_w(const LD& ld, uint32_t o, uint32_t vavail, uint32_t nn, uint16_t* out, uint32_t cap,
-                                               uint32_t* end_pos) {
+                                               uint32_t* end_pos, uint32_t* lane_pos = nullptr, uint32_t* lane_len = nullptr) {
     const uint32_t l = lane_id();
     if (nn == 0) { *end_pos = 0; return true; }
     if (vavail < 4u || vavail > 65535u || nn > cap) return false;
@@ -442,38 +453,47 @@ __device__ __forceinline__ bool find_headers_w(const LD& ld, uint32_t o, uint32_
     if (R > 64u) return false;
     const uint32_t a0 = l * R;                              // first A-space position of this lane
     uint32_t lo = 0, hi = 0;
+    const uint32_t steps = R >> 2;                          // 1..16, warp-uniform
     if (a0 <= o + last) {
-        const uint32_t w0i = a0 >> 2, steps = R >> 2;
+        const uint32_t w0i = a0 >> 2;
         uint32_t z0 = zero_byte_mask32(ld(w0i));
-        // steps <= 16 and warp-uniform: unrolled with constant shifts
 #pragma unroll
         for (uint32_t i = 0; i < 16; i++) {
-            if (i < steps) {
-                uint32_t z1 = zero_byte_mask32(ld(w0i + i + 1));
-                // bit 8k+7 of zz: bytes k+2 and k+3 (of the 8-byte window) are zero
-                uint32_t zz = __funnelshift_r(z0, z1, 16) & __funnelshift_r(z0, z1, 24);
-                uint32_t nib = (((zz >> 7) & 0x01010101u) * 0x01020408u) >> 24; // 4 flags -> bits 0..3
-                if (i < 8) lo |= nib << (4u * i); else hi |= nib << (4u * (i - 8u));
-                z0 = z1;
-            }
+            if (i >= steps) break;
+            const uint32_t z1 = zero_byte_mask32(ld(w0i + i + 1));
+            const uint32_t zz = __funnelshift_r(z0, z1, 16) & __funnelshift_r(z0, z1, 24);
+            if (i < 8) lo = (lo >> 1) | zz; else hi = (hi >> 1) | zz;
+            z0 = z1;
         }
+        lo >>= 8u - min(steps, 8u);
+        if (steps > 8u) hi >>= 16u - steps;
+        // drop flags whose successor position is flagged (bit + 8 inside a step, bit - 23 across steps)
+        const uint32_t slo = (lo >> 8) | ((lo & 0xfeu) << 23) | (hi << 31);
+        const uint32_t shi = (hi >> 8) | ((hi & 0xfeu) << 23);
+        lo &= ~slo;
+        hi &= ~shi;
     }
-    // keep A-space positions inside [o, o + last]
-    uint64_t mask = (static_cast<uint64_t>(hi) << 32) | lo;
-    if (a0 < o) mask &= ~0ull << (o - a0);                  // o - a0 <= 3
-    if (a0 + 63u > o + last) { uint32_t keep = o + last >= a0 ? o + last - a0 + 1u : 0u; mask &= keep >= 64u ? ~0ull : ((1ull << keep) - 1ull); }
-    uint32_t c[4] = {0, 0, 0, 0};
+    uint32_t c0 = 0xffffffffu, c1 = 0xffffffffu, c2 = 0xffffffffu, c3 = 0xffffffffu;
     uint32_t cnt = 0;
     bool over = false;
-    while (mask) {
-        uint32_t j = __ffsll(static_cast<long long>(mask)) - 1;
-        mask &= mask - 1;
-        uint32_t apos = a0 + j;
-        uint32_t len = ld16_at(ld, apos);
-        uint32_t pos = apos - o;
-        if (pos + 4u + len <= vavail) {
-            if (cnt == 0) c[0] = pos; else if (cnt == 1) c[1] = pos; else if (cnt == 2) c[2] = pos; else if (cnt == 3) c[3] = pos; else over = true;
-            cnt++;
+#pragma unroll
+    for (uint32_t half = 0; half < 2; half++) {
+        uint32_t m = half ? hi : lo;
+        while (m) {
+            const uint32_t b = __ffs(static_cast<int>(m)) - 1;
+            m &= m - 1;
+            const uint32_t apos = a0 + half * 32u + (((b & 7u) << 2) | (b >> 3));
+            const uint32_t pos = apos - o;                  // wraps (and fails `<= last`) in front of the section
+            const uint32_t len = ld.u16at(apos);
+            if (pos <= last && pos + 4u + len <= vavail) {
+                uint32_t v = pos, t;                        // sorted insert; what falls off the end is an overflow
+                t = min(c0, v); v = max(c0, v); c0 = t;
+                t = min(c1, v); v = max(c1, v); c1 = t;
+                t = min(c2, v); v = max(c2, v); c2 = t;
+                t = min(c3, v); v = max(c3, v); c3 = t;
+                over = over || v != 0xffffffffu;
+                cnt++;
+            }
         }
     }
     if (__any_sync(0xffffffffu, over)) return false;
@@ -481,16 +501,18 @@ __device__ __forceinline__ bool find_headers_w(const LD& ld, uint32_t o, uint32_
     const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
     if (total < nn || total > cap) return false;
     const uint32_t w = incl - cnt;
-    if (cnt > 0) out[w] = static_cast<uint16_t>(c[0]);
-    if (cnt > 1) out[w + 1] = static_cast<uint16_t>(c[1]);
-    if (cnt > 2) out[w + 2] = static_cast<uint16_t>(c[2]);
-    if (cnt > 3) out[w + 3] = static_cast<uint16_t>(c[3]);
+    if (cnt > 0) out[w] = static_cast<uint16_t>(c0);
+    if (cnt > 1) out[w + 1] = static_cast<uint16_t>(c1);
+    if (cnt > 2) out[w + 2] = static_cast<uint16_t>(c2);
+    if (cnt > 3) out[w + 3] = static_cast<uint16_t>(c3);
     __syncwarp();
     bool ok = true;
     uint32_t endp = 0;
     for (uint32_t i = l; i < nn; i += 32) {
-        uint32_t ci = out[i];
-        uint32_t nx = ci + 4u + ld16_at(ld, ci + o);
+        const uint32_t ci = out[i];
+        const uint32_t len = ld.u16at(ci + o);
+        const uint32_t nx = ci + 4u + len;
+        if (i == l) { if (lane_pos) *lane_pos = ci; if (lane_len) *lane_len = len; }
         if (i == 0 && ci != 0) ok = false;
         if (i + 1 < nn) { if (out[i + 1] != nx) ok = false; }
         else endp = nx;

@@ -75,33 +75,43 @@ __device__ __forceinline__ bool dfa_run(const DfaDev& D, const uint16_t* trans, 
     return accept[s] != 0;
 }
 
-// Byte-indexed table with PRE-SCALED entries (next state * 256), shared memory only: one add and
-// one ld.shared per byte, text taken from aligned words, absorbing states tested once per word.
+// Byte-indexed table staged in shared memory with ABSOLUTE entries: every entry is the
+// shared-space byte address of the next state's row (row = 256 x u16), so a step is
+// "address = state + 2 * byte; state = ld.shared.u16 [address]".  Text comes from aligned words
+// (one funnel shift per word realigns it), eight bytes per loop trip while the string lasts, the
+// absorbing states are tested once per trip.
+__device__ __forceinline__ uint32_t dfa_step(uint32_t s, uint32_t w, uint32_t k) {
+    uint32_t nxt;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(nxt) : "r"(s + 2u * __byte_perm(w, 0u, 0x4440u + k)));
+    return nxt;
+}
 template <class LD>
-__device__ __forceinline__ bool dfa_run_scaled(const DfaDev& D, uint32_t trans_s, const uint8_t* accept, const LD& ld, uint32_t apos,
-                                               uint32_t len) {
-    uint32_t s = D.start << 8;
-    const uint32_t dead = D.dead << 8; // D.dead == 0xffffffff (none) never equals a scaled state
+__device__ __forceinline__ uint32_t dfa_run_abs(uint32_t s, uint32_t acc_s, uint32_t dead_s, const LD& ld, uint32_t apos, uint32_t len) {
     uint32_t wi = apos >> 2;
-    uint32_t skip = apos & 3u;
-    uint32_t w = ld(wi) >> (skip * 8u);
-    uint32_t n = min(4u - skip, len), i = 0;
-    for (;;) {
-#pragma unroll
-        for (uint32_t b = 0; b < 4; b++) {
-            if (b < n) {
-                uint32_t nxt;
-                asm volatile("ld.shared.u16 %0, [%1];" : "=r"(nxt) : "r"(trans_s + 2u * (s + (w & 0xffu))));
-                s = nxt;
-                w >>= 8;
-            }
-        }
-        i += n;
-        if (i >= len || s == 0u || s == dead) break;
-        w = ld(++wi);
-        n = min(4u, len - i);
+    const uint32_t sh = (apos & 3u) * 8u;
+    uint32_t w0 = ld(wi);
+    uint32_t left = len;
+    while (left >= 8u && s != acc_s && s != dead_s) {
+        const uint32_t w1 = ld(wi + 1), w2 = ld(wi + 2);
+        const uint32_t a = __funnelshift_r(w0, w1, sh), b = __funnelshift_r(w1, w2, sh);
+        s = dfa_step(s, a, 0); s = dfa_step(s, a, 1); s = dfa_step(s, a, 2); s = dfa_step(s, a, 3);
+        s = dfa_step(s, b, 0); s = dfa_step(s, b, 1); s = dfa_step(s, b, 2); s = dfa_step(s, b, 3);
+        w0 = w2; wi += 2; left -= 8u;
     }
-    return accept[s >> 8] != 0;
+    if (left >= 8u) return s; // absorbed
+    if (left >= 4u) {
+        const uint32_t w1 = ld(wi + 1);
+        const uint32_t a = __funnelshift_r(w0, w1, sh);
+        s = dfa_step(s, a, 0); s = dfa_step(s, a, 1); s = dfa_step(s, a, 2); s = dfa_step(s, a, 3);
+        w0 = w1; wi++; left -= 4u;
+    }
+    if (left) {
+        const uint32_t a = __funnelshift_r(w0, ld(wi + 1), sh);
+        s = dfa_step(s, a, 0);
+        if (left > 1u) s = dfa_step(s, a, 1);
+        if (left > 2u) s = dfa_step(s, a, 2);
+    }
+    return s;
 }
 
 struct RegexParams {
@@ -180,16 +190,24 @@ __device__ __forceinline__ bool regex_page(const RegexParams& R, const uint16_t*
     return __any_sync(0xffffffffu, hit);
 }
 
-// stage [trans][cls 256][accept] into shared memory when they fit
+// stage [trans][cls 256][accept] into shared memory when they fit.  `absolute`: byte-indexed
+// entries (next state * 256, u16 units) become shared-space byte addresses of the next row
+// (entry * 2 + address of the table); two entries per 32-bit word, no carry between the halves
+// because every address stays below 64 KiB (checked by the launcher).
 __device__ __forceinline__ void stage_tables(const RegexParams& R, uint8_t* stab, const uint16_t*& trans, const uint8_t*& cls,
-                                             const uint8_t*& accept) {
+                                             const uint8_t*& accept, bool absolute = false) {
     trans = R.D.trans; cls = R.D.cls; accept = R.D.accept;
     if (R.D.in_smem) {
         const uint32_t total = R.D.table_bytes + 256u + R.D.n_states;
         const uint8_t* src = reinterpret_cast<const uint8_t*>(R.D.trans); // the three tables are contiguous on the device
+        const uint32_t rebase = static_cast<uint32_t>(__cvta_generic_to_shared(stab)) * 0x10001u;
+        const uint32_t n_trans16 = absolute ? R.D.table_bytes / 16u : 0u;
         // 16-byte vectors (both sides are 16-byte aligned; the device blob is padded)
-        for (uint32_t i = threadIdx.x; i < (total + 15u) / 16u; i += blockDim.x)
-            reinterpret_cast<uint4*>(stab)[i] = reinterpret_cast<const uint4*>(src)[i];
+        for (uint32_t i = threadIdx.x; i < (total + 15u) / 16u; i += blockDim.x) {
+            uint4 v = reinterpret_cast<const uint4*>(src)[i];
+            if (i < n_trans16) { v.x = (v.x << 1) + rebase; v.y = (v.y << 1) + rebase; v.z = (v.z << 1) + rebase; v.w = (v.w << 1) + rebase; }
+            reinterpret_cast<uint4*>(stab)[i] = v;
+        }
         __syncthreads();
         trans = reinterpret_cast<const uint16_t*>(stab);
         cls = stab + R.D.table_bytes;
@@ -232,19 +250,26 @@ __device__ __forceinline__ void rx_to_slow(const DecodeParams& P, uint32_t q) {
 
 constexpr uint32_t kRxCand = 1024; // length-prefix candidates per page (u16 positions)
 
+// shared memory: [tables, padded to 128 bytes][tile pipeline][candidates per warp]
+__host__ __device__ inline uint32_t rx_table_pad(uint32_t table_bytes, uint32_t n_states, bool in_smem) {
+    return in_smem ? ((table_bytes + 256u + n_states + 127u) & ~127u) : 0u;
+}
+
 __global__ void __launch_bounds__(kThreadsPerCta, 4) k_regex_tiles(RegexParams R) {
     extern __shared__ __align__(128) uint8_t smem[];
-    uint16_t* cand = reinterpret_cast<uint16_t*>(smem + kTilePipeBytes) + warp_id() * kRxCand;
+    uint8_t* pipe = smem + rx_table_pad(R.D.table_bytes, R.D.n_states, R.D.in_smem != 0);
+    uint16_t* cand = reinterpret_cast<uint16_t*>(pipe + kTilePipeBytes) + warp_id() * kRxCand;
     const uint16_t* trans; const uint8_t* cls; const uint8_t* accept;
-    stage_tables(R, smem + kTilePipeBytes + kWarpsPerCta * kRxCand * 2, trans, cls, accept);
+    stage_tables(R, smem, trans, cls, accept, R.D.scaled != 0);
     const DecodeParams& P = R.P;
     const uint32_t l = lane_id();
     const uint32_t trans_s = smem_u32(trans); // meaningful when the tables are staged (R.D.scaled implies it)
+    const uint32_t start_s = trans_s + R.D.start * 512u, dead_s = trans_s + R.D.dead * 512u; // dead == ~0: never equal
     int max_def = 0;
     bool has_dict = false;
     uint32_t dict_n = 0;
     const uint8_t* dmatch = nullptr;
-    tile_pipeline(P, smem,
+    tile_pipeline(P, pipe,
         [&](uint32_t chunk, uint64_t*, uint32_t&) {
             const DevChunk& ck = P.chunks[chunk];
             max_def = ck.max_def; has_dict = ck.has_dict; dict_n = ck.dict_ok_n;
@@ -297,17 +322,20 @@ __global__ void __launch_bounds__(kThreadsPerCta, 4) k_regex_tiles(RegexParams R
                     const uint32_t va = smem_u32(vals);
                     const SmemWords ld{va & ~3u};
                     const uint32_t o = va & 3u;
-                    uint32_t endp = 0;
-                    if (!find_headers_w(ld, o, size - pos, nn, cand, kRxCand, &endp)) slow = true;
+                    uint32_t endp = 0, c1 = 0, len1 = 0;
+                    if (!find_headers_w(ld, o, size - pos, nn, cand, kRxCand, &endp, &c1, &len1)) slow = true;
                     else {
                         for (uint32_t k0 = 0; k0 < nn && !hit; k0 += 32) {
                             uint32_t k = k0 + l;
                             bool h = false;
                             if (k < nn) {
-                                uint32_t c = cand[k];
-                                uint32_t len = ld16_at(ld, c + o);
-                                bool m = R.D.scaled ? dfa_run_scaled(R.D, trans_s, accept, ld, c + o + 4u, len)
-                                                    : dfa_run(R.D, trans, cls, accept, vals + c + 4, len);
+                                const uint32_t c = k0 ? cand[k] : c1;
+                                const uint32_t len = k0 ? ld.u16at(c + o) : len1;
+                                bool m;
+                                if (R.D.scaled) {
+                                    const uint32_t s = dfa_run_abs(start_s, trans_s, dead_s, ld, c + o + 4u, len);
+                                    m = accept[(s - trans_s) >> 9] != 0;
+                                } else m = dfa_run(R.D, trans, cls, accept, vals + c + 4, len);
                                 h = R.neg ? !m : m;
                             }
                             hit = __any_sync(0xffffffffu, h);
@@ -718,7 +746,7 @@ int pqg_regex_scan(pqg_ctx* ctx, pqg_plan* plan, const pqg_dfa* dfa, int neg, ui
         launches += 2;
     }
     const size_t tab_pad = R.D.in_smem ? ((tab_smem + 15) & ~size_t(15)) : 0;
-    const size_t smem_fast = static_cast<size_t>(kTilePipeBytes) + kWarpsPerCta * kRxCand * 2 + tab_pad;
+    const size_t smem_fast = static_cast<size_t>(kTilePipeBytes) + kWarpsPerCta * kRxCand * 2 + rx_table_pad(table_bytes, d.n_states, R.D.in_smem != 0);
     const size_t smem_slow = decode_smem_bytes(false) + tab_pad;
     CUF(ctx, cudaFuncSetAttribute(k_regex_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_fast)));
     CUF(ctx, cudaFuncSetAttribute(k_regex_pages, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_slow)));
