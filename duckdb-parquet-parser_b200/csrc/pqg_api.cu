@@ -544,6 +544,7 @@ static DecodeParams make_params(const pqg_plan* p) {
     P.cluster_size = p->cluster_size; P.part_shift = p->part_shift; P.tile_bytes = p->tile_bytes;
     P.identity_dict = p->identity ? 1u : 0u;
     { static const uint32_t gm = [] { const char* e = std::getenv("PQG_GATHER"); return e ? static_cast<uint32_t>(std::atoi(e)) : 1u; }(); P.gather_mode = gm; } // ld.global.cg measured 2-3 % ahead
+    { static const uint32_t ts = [] { const char* e = std::getenv("PQG_TILE_SYNC"); return e ? static_cast<uint32_t>(std::atoi(e)) : 0u; }(); P.tile_sync = ts; }
     return P;
 }
 

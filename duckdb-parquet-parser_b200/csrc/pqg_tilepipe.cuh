@@ -2,10 +2,12 @@
 //
 // The plan's host side cuts every chunk into tiles (TileDesc): <= kTilePages consecutive pages
 // whose bytes (page headers in between included) fit kTileBytes.  A CTA owns a contiguous run
-// of tiles.  One elected thread stages tile bytes + the tile's page descriptors into a
-// kTileStages-deep shared-memory ring with cp.async.bulk (1-D TMA, SASS UBLKCP) completing on
-// an mbarrier per stage; the CTA's warps take one page each out of shared memory; a
-// __syncthreads frees the stage and the elected thread refills it kTileStages tiles ahead.
+// of tiles.  Tile bytes + the tile's page descriptors are staged into a kTileStages-deep
+// shared-memory ring with cp.async.bulk (1-D TMA, SASS UBLKCP) completing on an mbarrier per
+// stage; the CTA's warps take one page each out of shared memory.  There is no CTA-wide barrier
+// per tile: a warp that is done with a stage bumps the stage's counter, and the LAST warp to do so
+// refills the stage kTileStages tiles ahead -- so warps run up to one tile apart and a slow page
+// does not idle the other seven warps.
 // No register staging, no per-warp global latency chain (descriptor -> chunk -> payload).
 #pragma once
 #include "pqg_page.cuh"
@@ -40,7 +42,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 
 // TB = image bytes per tile (kTileBytes, or kTileBytesLarge for plans whose pages are fat)
 __host__ __device__ constexpr int tile_stage_bytes(int TB) { return TB + 16 + kTilePages * static_cast<int>(sizeof(pqg_page_desc)); }
-constexpr int kBarBytes = 64 + kTileStages * 32; // kTileStages + 1 mbarriers, then per-stage tile meta
+constexpr int kBarBytes = (64 + kTileStages * 64 + 127) & ~127; // kTileStages + 1 mbarriers, stage counters, per-stage tile meta, prefetched descriptors
 __host__ __device__ constexpr int tile_pipe_bytes(int TB) { return kBarBytes + kTileStages * tile_stage_bytes(TB); } // shared memory of the pipeline itself
 constexpr int kTilePipeBytes = tile_pipe_bytes(kTileBytes);
 
@@ -53,19 +55,22 @@ struct TileMeta { uint64_t byte_lo; uint32_t first_page; uint32_t n_pages; uint3
 template <int TB = kTileBytes, class OnChunk, class OnPage>
 __device__ __forceinline__ void tile_pipeline(const DecodeParams& P, uint8_t* smem, OnChunk&& on_chunk, OnPage&& on_page) {
     constexpr int kStageBytes = tile_stage_bytes(TB);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem);          // [kTileStages] tiles, [kTileStages] per-chunk staging
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);          // [kTileStages] tiles, then one for per-chunk staging
+    uint32_t* done = reinterpret_cast<uint32_t*>(smem + 32);     // [kTileStages] warps finished with the stage
     TileMeta* meta = reinterpret_cast<TileMeta*>(smem + 64);     // [kTileStages]
+    TileDesc* ahead = reinterpret_cast<TileDesc*>(smem + 64 + kTileStages * 32); // [kTileStages] descriptor of the tile that refills the stage
     uint8_t* ring = smem + kBarBytes;
     const uint32_t t0 = P.tile_lo + blockIdx.x * P.tiles_per_cta;
     const uint32_t t1 = min(P.tile_hi, t0 + P.tiles_per_cta);
     const uint32_t tid = threadIdx.x;
     if (tid == 0) {
         for (int i = 0; i <= kTileStages; i++) mbar_init(&full[i], 1);
+        for (int i = 0; i < kTileStages; i++) done[i] = 0;
         fence_mbar_init();
     }
     __syncthreads();
     if (t0 >= t1) return;
-    auto issue = [&](uint32_t t, const TileDesc& td) { // thread 0
+    auto issue = [&](uint32_t t, const TileDesc& td) { // one thread
         const uint32_t st = (t - t0) % kTileStages;
         uint8_t* dst = ring + st * kStageBytes;
         meta[st] = TileMeta{td.byte_lo, td.first_page, td.n_pages, td.chunk_idx, 0};
@@ -76,12 +81,10 @@ __device__ __forceinline__ void tile_pipeline(const DecodeParams& P, uint8_t* sm
     };
     if (tid == 0) {
         for (uint32_t t = t0; t < min(t1, t0 + kTileStages); t++) issue(t, P.tiles[t]);
+        for (uint32_t t = t0 + kTileStages; t < min(t1, t0 + 2 * kTileStages); t++) ahead[(t - t0) % kTileStages] = P.tiles[t];
     }
     uint32_t cur_chunk = 0xffffffffu, extra_phase = 0;
     for (uint32_t t = t0; t < t1; t++) {
-        TileDesc nxt{};
-        const bool refill = tid == 0 && t + kTileStages < t1;
-        if (refill) nxt = P.tiles[t + kTileStages]; // in flight while the pages are decoded
         const uint32_t st = (t - t0) % kTileStages;
         mbar_wait(&full[st], ((t - t0) / kTileStages) & 1u);
         const uint8_t* tile = ring + st * kStageBytes;
@@ -95,8 +98,28 @@ __device__ __forceinline__ void tile_pipeline(const DecodeParams& P, uint8_t* sm
             const pqg_page_desc pd = pds[j];
             on_page(tm.first_page + j, pd, tile + (pd.payload_off - tm.byte_lo));
         }
-        __syncthreads(); // stage st is free again
-        if (refill) issue(t + kTileStages, nxt);
+        if (P.tile_sync) { // A/B: the classic CTA-wide barrier, refill by thread 0
+            __syncthreads();
+            if (tid == 0 && t + kTileStages < t1) issue(t + kTileStages, P.tiles[t + kTileStages]);
+            continue;
+        }
+        __syncwarp();
+        if (lane_id() == 0) {
+            // release the stage: my warp's reads are done; the last warp re-arms and refills it
+            uint32_t old;
+            asm volatile("atom.acq_rel.cta.shared.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(&done[st])) : "memory");
+            if (old == kWarpsPerCta - 1u) {
+                done[st] = 0;
+                if (t + kTileStages < t1) {
+                    // the descriptor was fetched one round ago (by the thread that refilled this stage last
+                    // time; its store is ordered before this point by the counter's release/acquire chain)
+                    const TileDesc td = ahead[st];
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic reads of the stage before the bulk write
+                    issue(t + kTileStages, td);
+                    if (t + 2 * kTileStages < t1) ahead[st] = P.tiles[t + 2 * kTileStages];
+                }
+            }
+        }
     }
 }
 
