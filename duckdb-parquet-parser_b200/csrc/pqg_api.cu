@@ -60,6 +60,7 @@ struct pqg_plan {
     bool any_dict = false, any_def = false, is_str = false, is_bool = false;
     int phys = 0, width = 0;
     uint64_t n_slots = 0;
+    mutable uint32_t max_page_values = 0xffffffffu; // most num_values of one page (computed on first use)
     uint8_t* d_values = nullptr;
     uint32_t* d_validity = nullptr;
     uint32_t* d_offsets = nullptr;
@@ -340,6 +341,10 @@ static int plan_create_impl(pqg_ctx* ctx, const pqg_buf* image, const pqg_chunk_
                 d.dict_arena_off = arena;
                 size_t ent = p->is_str ? 8 : static_cast<size_t>(p->width);
                 arena += (static_cast<size_t>(s.dict_num_values) * ent + 31) & ~size_t(15);
+                if (p->is_str) { // 16-byte padded entries for short-string dictionaries (filled by the prepare kernel)
+                    d.dict_pad_off = arena;
+                    arena += static_cast<size_t>(s.dict_num_values) * 16 + 16;
+                }
             }
         }
         if (s.max_def > 0) p->any_def = true;
@@ -883,4 +888,12 @@ size_t plan_dict_arena_bytes(const pqg_plan* p) { return p->dict_bytes; }
 uint64_t plan_slots(const pqg_plan* p) { return p->n_slots; }
 const std::vector<pqg_chunk_desc>& plan_chunks(const pqg_plan* p) { return p->chunks; }
 const std::vector<pqg_page_desc>& plan_pages(const pqg_plan* p) { return p->pages; }
+uint32_t plan_max_page_values(const pqg_plan* p) {
+    if (p->max_page_values == 0xffffffffu) {
+        uint32_t m = 0;
+        for (const pqg_page_desc& pd : p->pages) m = std::max(m, pd.num_values);
+        p->max_page_values = m;
+    }
+    return p->max_page_values;
+}
 } // namespace pqg

@@ -77,8 +77,9 @@ __global__ void __launch_bounds__(1024) k_dict_prepare(DecodeParams P) {
         uint2* ent = reinterpret_cast<uint2*>(dst);
         constexpr uint32_t kNone = 0xffffffffu;
         __shared__ uint32_t s_start[1024], s_end[1024], s_cnt[1024], s_base[1024];
-        __shared__ uint32_t s_ok;
+        __shared__ uint32_t s_ok, s_nok, s_minlen, s_maxlen;
         const uint32_t tid = threadIdx.x, nthr = blockDim.x;
+        if (tid == 0) { s_nok = 0; s_minlen = 0xffffffffu; s_maxlen = 0; }
         auto next_of = [&](uint32_t p) -> uint32_t { // position after the string whose prefix is at p, kNone if it does not fit
             if (static_cast<uint64_t>(p) + 4u > size) return kNone;
             uint32_t len = ld32u(src + p);
@@ -128,7 +129,7 @@ __global__ void __launch_bounds__(1024) k_dict_prepare(DecodeParams P) {
                 uint32_t p = s_start[tid], k = s_base[tid];
                 while (p < hi && k < n) { uint32_t q = next_of(p); if (q == kNone) break; ent[k++] = make_uint2(p + 4u, q - p - 4u); p = q; }
             }
-            if (first) ck.dict_ok_n = n;
+            if (first) { ck.dict_ok_n = n; s_nok = n; }
         } else if (first) {
             uint32_t pos = 0, k = 0;
             for (; k < n; k++) {
@@ -139,7 +140,35 @@ __global__ void __launch_bounds__(1024) k_dict_prepare(DecodeParams P) {
                 pos += 4 + len;
             }
             ck.dict_ok_n = k;
+            s_nok = k;
         }
+        // short-string dictionaries: the padded 16-byte table (one vector load per value instead of
+        // {start, len} + 4-8 unaligned word loads), and the common entry length if there is one
+        __syncthreads();
+        const uint32_t nok = s_nok;
+        uint32_t mn = 0xffffffffu, mx = 0;
+        for (uint32_t i = tid; i < nok; i += nthr) { const uint32_t len = ent[i].y; mn = min(mn, len); mx = max(mx, len); }
+        mn = __reduce_min_sync(0xffffffffu, mn); mx = __reduce_max_sync(0xffffffffu, mx);
+        if ((tid & 31u) == 0) { atomicMin(&s_minlen, mn); atomicMax(&s_maxlen, mx); }
+        __syncthreads();
+        const bool is_short = nok > 0 && s_maxlen <= 15u;
+        if (is_short) {
+            uint4* pad = reinterpret_cast<uint4*>(P.dict_arena + ck.dict_pad_off);
+            for (uint32_t i = tid; i < nok; i += nthr) {
+                const uint2 e = ent[i];
+                const uint8_t* sp = src + e.x;
+                uint32_t w[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    uint32_t v = 4u * k < e.y ? ld32u(sp + 4 * k) : 0u;
+                    const uint32_t rem = e.y > 4u * k ? e.y - 4u * k : 0u;      // bytes of this word that belong to the string
+                    if (rem < 4u) v &= (1u << (8u * rem)) - 1u;
+                    w[k] = v;
+                }
+                pad[i] = make_uint4(w[0], w[1], w[2], w[3] | (e.y << 24));
+            }
+        }
+        if (tid == 0) { ck.dict_short = is_short ? 1u : 0u; ck.dict_len = (nok > 0 && s_minlen == s_maxlen) ? s_maxlen : 0xffffffffu; }
     }
 }
 
@@ -331,6 +360,19 @@ __device__ __forceinline__ void stage_string(uint8_t* dst, const uint8_t* sp, ui
     }
 }
 
+// the same from a padded dictionary entry held in registers (len <= 15)
+__device__ __forceinline__ void stage_words(uint8_t* dst, const uint4& v, uint32_t len) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const uint32_t b = 4u * i;
+        if (b < len) dst[b] = static_cast<uint8_t>(w[i]);
+        if (b + 1u < len) dst[b + 1u] = static_cast<uint8_t>(w[i] >> 8);
+        if (b + 2u < len) dst[b + 2u] = static_cast<uint8_t>(w[i] >> 16);
+        if (b + 3u < len) dst[b + 3u] = static_cast<uint8_t>(w[i] >> 24);
+    }
+}
+
 template <bool COPY>
 __device__ __forceinline__ void decode_str_page(const DecodeParams& P, uint32_t q, const DevChunk& ck, WarpScratch& ws) {
     const uint32_t l = lane_id();
@@ -348,6 +390,8 @@ __device__ __forceinline__ void decode_str_page(const DecodeParams& P, uint32_t 
     const uint2* dent = reinterpret_cast<const uint2*>(P.dict_arena + ck.dict_arena_off);
     const uint8_t* dchars = P.image + ck.dict_off;
     const uint32_t dict_n = ck.dict_ok_n;
+    const bool dshort = c.dict && ck.dict_short != 0;
+    const uint4* dpad = reinterpret_cast<const uint4*>(P.dict_arena + ck.dict_pad_off);
     uint32_t* offs = COPY ? P.offsets + ck.out_row_base + (&ck - P.chunks) : nullptr; // chunk c owns [row_base + c, ...]
     uint8_t* chars = COPY ? P.chars + ck.char_base : nullptr;
     uint64_t page_bytes = 0;                       // running string bytes of this page
@@ -385,9 +429,10 @@ __device__ __forceinline__ void decode_str_page(const DecodeParams& P, uint32_t 
         if (!COPY) {
             if (c.dict) { // sum the lengths of the referenced dictionary entries
                 uint32_t sum = 0;
+                const uint32_t ulen = ck.dict_len; // every entry has this length (~0u: lengths differ)
                 for (uint32_t k = l; k < nn; k += 32) {
                     uint32_t ix = regular ? regular_index2(rs, nn_before + k) : idx_load(ws.idx, k, c.wide);
-                    if (ix < dict_n) sum += dent[ix].y;
+                    if (ix < dict_n) sum += ulen != 0xffffffffu ? ulen : dent[ix].y;
                 }
                 for (int d = 16; d; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
                 page_bytes += sum;
@@ -412,11 +457,13 @@ __device__ __forceinline__ void decode_str_page(const DecodeParams& P, uint32_t 
             }
             uint32_t len = 0;
             const uint8_t* sp = nullptr; // source bytes of this lane's string
+            uint4 pv = make_uint4(0, 0, 0, 0);   // short-string dictionaries: the padded entry itself
             if (valid) {
                 if (c.dict) {
                     uint32_t ix = regular ? regular_index2(rs, nn_before + k) : idx_load(ws.idx, k, c.wide);
-                    if (ix < dict_n) { uint2 e = dent[ix]; sp = dchars + e.x; len = e.y; }
-                    else valid = false;
+                    if (ix >= dict_n) valid = false;
+                    else if (dshort) { pv = ldg_nc16(reinterpret_cast<const uint8_t*>(dpad + ix)); len = pv.w >> 24; }
+                    else { uint2 e = dent[ix]; sp = dchars + e.x; len = e.y; }
                 } else {
                     uint32_t pp = idx_load(ws.idx, k, wide);
                     len = ld32u(vals + pp);
@@ -451,7 +498,8 @@ __device__ __forceinline__ void decode_str_page(const DecodeParams& P, uint32_t 
                     // all loads first (the compiler cannot prove that the staging stores do not
                     // alias the source, and would otherwise serialise one L2 round trip per byte);
                     // unrolled for the warp's longest string: 4, 8 or 12 words
-                    if (maxlen <= 16u) stage_string<4>(st + myoff, sp, len);
+                    if (dshort) stage_words(st + myoff, pv, len);
+                    else if (maxlen <= 16u) stage_string<4>(st + myoff, sp, len);
                     else if (maxlen <= 32u) stage_string<8>(st + myoff, sp, len);
                     else stage_string<kStageMaxLen / 4>(st + myoff, sp, len);
                     __syncwarp();

@@ -44,6 +44,11 @@ struct DevChunk {
     uint8_t def_bw;
     uint8_t rep_bw;
     uint32_t dict_ok_n;      // dictionary entries that parsed (written by the prepare kernel)
+    // BYTE_ARRAY dictionaries whose entries are all <= 15 bytes also get a 16-byte-per-entry table
+    // (15 zero-padded bytes + the length) behind the {start, len} entries: one 16-byte load per value
+    uint32_t dict_short;     // written by the prepare kernel: 1 = the padded table is valid
+    uint32_t dict_len;       // written by the prepare kernel: common length of all entries, ~0u if they differ
+    uint64_t dict_pad_off;   // arena offset of the padded table
 };
 
 // First failing page (lowest page-table index) of a run, plus the per-run work counters

@@ -42,6 +42,7 @@ bool plan_any_dict(const pqg_plan* p);
 uint64_t plan_slots(const pqg_plan* p);
 const std::vector<pqg_chunk_desc>& plan_chunks(const pqg_plan* p);
 const std::vector<pqg_page_desc>& plan_pages(const pqg_plan* p);
+uint32_t plan_max_page_values(const pqg_plan* p);
 size_t plan_dict_arena_bytes(const pqg_plan* p);
 
 namespace {
@@ -120,6 +121,7 @@ struct RegexParams {
     uint8_t* dict_match;  // per dictionary entry (arena entry index): predicate (neg applied)
     uint32_t* page_bits;  // bit per page-table entry
     int neg;
+    uint32_t cand_cap;    // tile scan: length-prefix candidates per page (u16 positions in shared memory)
 };
 
 __global__ void __launch_bounds__(256) k_regex_dict(RegexParams R) {
@@ -248,7 +250,7 @@ __device__ __forceinline__ void rx_to_slow(const DecodeParams& P, uint32_t q) {
     P.slow_pages[P.n_slow_host + k] = q;
 }
 
-constexpr uint32_t kRxCand = 1024; // length-prefix candidates per page (u16 positions)
+constexpr uint32_t kRxCand = 1024; // most length-prefix candidates per page the tile scan keeps (u16 positions); 512 when no page needs more
 
 // shared memory: [tables, padded to 128 bytes][tile pipeline][candidates per warp]
 __host__ __device__ inline uint32_t rx_table_pad(uint32_t table_bytes, uint32_t n_states, bool in_smem) {
@@ -258,7 +260,7 @@ __host__ __device__ inline uint32_t rx_table_pad(uint32_t table_bytes, uint32_t 
 __global__ void __launch_bounds__(kThreadsPerCta, 4) k_regex_tiles(RegexParams R) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* pipe = smem + rx_table_pad(R.D.table_bytes, R.D.n_states, R.D.in_smem != 0);
-    uint16_t* cand = reinterpret_cast<uint16_t*>(pipe + kTilePipeBytes) + warp_id() * kRxCand;
+    uint16_t* cand = reinterpret_cast<uint16_t*>(pipe + kTilePipeBytes) + warp_id() * R.cand_cap;
     const uint16_t* trans; const uint8_t* cls; const uint8_t* accept;
     stage_tables(R, smem, trans, cls, accept, R.D.scaled != 0);
     const DecodeParams& P = R.P;
@@ -323,7 +325,7 @@ __global__ void __launch_bounds__(kThreadsPerCta, 4) k_regex_tiles(RegexParams R
                     const SmemWords ld{va & ~3u};
                     const uint32_t o = va & 3u;
                     uint32_t endp = 0, c1 = 0, len1 = 0;
-                    if (!find_headers_w(ld, o, size - pos, nn, cand, kRxCand, &endp, &c1, &len1)) slow = true;
+                    if (!find_headers_w(ld, o, size - pos, nn, cand, R.cand_cap, &endp, &c1, &len1)) slow = true;
                     else {
                         for (uint32_t k0 = 0; k0 < nn && !hit; k0 += 32) {
                             uint32_t k = k0 + l;
@@ -749,9 +751,11 @@ int pqg_regex_scan(pqg_ctx* ctx, pqg_plan* plan, const pqg_dfa* dfa, int neg, ui
         launches += 2;
     }
     const size_t tab_pad = R.D.in_smem ? ((tab_smem + 15) & ~size_t(15)) : 0;
-    const size_t smem_fast = static_cast<size_t>(kTilePipeBytes) + kWarpsPerCta * kRxCand * 2 + rx_table_pad(table_bytes, d.n_states, R.D.in_smem != 0);
+    R.cand_cap = plan_max_page_values(plan) <= kRxCand / 2 ? kRxCand / 2 : kRxCand;
+    const size_t smem_fast = static_cast<size_t>(kTilePipeBytes) + kWarpsPerCta * R.cand_cap * 2 + rx_table_pad(table_bytes, d.n_states, R.D.in_smem != 0);
     const size_t smem_slow = decode_smem_bytes(false) + tab_pad;
     CUF(ctx, cudaFuncSetAttribute(k_regex_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_fast)));
+    CUF(ctx, cudaFuncSetAttribute(k_regex_tiles, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CUF(ctx, cudaFuncSetAttribute(k_regex_pages, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_slow)));
     if (R.P.tile_hi > R.P.tile_lo) {
         int resident = 1;

@@ -3,7 +3,7 @@
 ncu's CSV export of the source page carries metrics only for the SASS view; the line table comes
 from nvdisasm over the cubin inside libpqg.so (same build as the capture, or the instruction
 counts will not line up and the script says so).
-usage: python scripts/ncu_lines.py <report.ncu-rep> <kernel-substring> <cubin-stem e.g. pqg_scan> [units]
+usage: python scripts/ncu_lines.py <report.ncu-rep> <mangled-kernel-substring> <cubin-stem e.g. pqg_scan> [units] [launch index in the report]
 `units` divides the executed-instruction counts (e.g. pages in the launch) to print per-unit costs."""
 import collections
 import csv
@@ -16,6 +16,7 @@ import tempfile
 
 rep, kern, stem = sys.argv[1], sys.argv[2], sys.argv[3]
 units = float(sys.argv[4]) if len(sys.argv) > 4 else 1.0
+skip = sys.argv[5] if len(sys.argv) > 5 else None
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 so = os.path.join(root, "duckdb-parquet-parser_b200", "libpqg.so")
 tmp = tempfile.mkdtemp()
@@ -34,14 +35,14 @@ for l in sass[start + 1:]:
     m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(.*?);", l)
     if m:
         seq.append((cur, m.group(2)))
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass", "-k", "regex:" + kern],
-                     capture_output=True, text=True).stdout
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
-h = [i for i, r in enumerate(rows) if "Instructions Executed" in r][0]
-hdr, data = rows[h], [r for r in rows[h + 1:] if len(r) == len(rows[h])]
-# several launches may be concatenated: keep the first
-if len(data) > len(seq) and len(data) % len(seq) == 0:
-    data = data[:len(seq)]
+# one section per profiled launch: a "Kernel Name" row, a header row, then one row per instruction
+heads = [i for i, r in enumerate(rows) if "Instructions Executed" in r]
+pick = int(skip) if skip is not None else 0
+h = heads[pick]
+end = heads[pick + 1] - 1 if pick + 1 < len(heads) else len(rows)
+hdr, data = rows[h], [r for r in rows[h + 1:end] if len(r) == len(rows[h])]
 if len(data) != len(seq):
     sys.exit(f"instruction count mismatch: report {len(data)} vs cubin {len(seq)} (different build?)")
 ie, iss = hdr.index("Instructions Executed"), hdr.index("# Samples")
