@@ -117,6 +117,18 @@ def col_str_varlen(rng, n, null_frac=0.1, maxlen=300):
     return strings_to_col(out, nulls(rng, n, null_frac))
 
 
+def col_str_tiny(rng, n, null_frac=0.0):
+    """PLAIN strings of 0..6 bytes over {NUL, 0x01, 'a', 'b'}: runs of empty strings, strings that
+    start with NUL, prefixes that look like each other's shadows -- every heuristic of the parallel
+    length-prefix discovery must fail safely into the sequential walk.  Keep n small: the writer
+    stays PLAIN only while distinct > non_null / 5."""
+    alphabet = np.frombuffer(b"\x00\x01ab", dtype=np.uint8)
+    lens = rng.integers(0, 7, size=n)
+    lens[rng.random(n) < 0.25] = 0
+    out = [alphabet[rng.integers(0, 4, size=int(L))].tobytes() for L in lens]
+    return strings_to_col(out, nulls(rng, n, null_frac))
+
+
 def pad_col(n):
     return fixed_col(np.arange(n, dtype=np.int64) * 1000003 + 17)
 
@@ -180,6 +192,9 @@ def standard_files():
         lambda rng: [[col_city(rng, n), col_str_dict(rng, n, 3000), col_email(rng, n), col_email(rng, n, 0.3),
                       col_str_varlen(rng, n), strings_to_col([b""] * n, np.ones(n, dtype=np.uint8)), col_str_short_dict(rng, n)]
                      for n in (30000, 4321)])
+    add("tiny_plain",
+        [("tiny", BYTE_ARRAY, REQUIRED, -1), ("tinyn", BYTE_ARRAY, OPTIONAL, -1)],
+        lambda rng: [[col_str_tiny(rng, n), col_str_tiny(rng, n, 0.3)] for n in (1500, 700)])
     add("bools",
         [("b", BOOLEAN, REQUIRED, -1), ("bn", BOOLEAN, OPTIONAL, -1)],
         lambda rng: [[col_bool(rng, n), col_bool(rng, n, 0.3)] for n in (5000, 100)])
