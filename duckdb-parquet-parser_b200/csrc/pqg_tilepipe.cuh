@@ -28,16 +28,18 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// the suspend-time hint parks the warp in hardware instead of spinning through issue slots
+constexpr uint32_t kMbarSuspendNs = 20000;
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
         "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
         "@p bra LAB_DONE;\n"
         "bra LAB_WAIT;\n"
         "LAB_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(kMbarSuspendNs) : "memory");
 }
 
 // TB = image bytes per tile (kTileBytes, or kTileBytesLarge for plans whose pages are fat)
