@@ -53,7 +53,8 @@ class PageError(C.Structure):
 
 class Timings(C.Structure):
     _fields_ = [("dict_ms", C.c_float), ("fixed_ms", C.c_float), ("str_size_ms", C.c_float),
-                ("str_copy_ms", C.c_float), ("total_ms", C.c_float), ("launches", C.c_uint32), ("general_ms", C.c_float)]
+                ("str_copy_ms", C.c_float), ("total_ms", C.c_float), ("launches", C.c_uint32), ("general_ms", C.c_float),
+                ("tile_launches", C.c_uint32)]
 
 
 class ValDump(C.Structure):
@@ -131,7 +132,7 @@ PQR_SYMBOLS = [
     "pqr_schema_string", "pqr_page_scan_seconds", "pqr_file_size", "pqr_page_index", "pqr_read_page_data",
     "pqr_read_pages_chunk", "pqr_read_column_by_idx", "pqr_read_column", "pqr_read_column_rg", "pqr_read_pages",
     "pqr_string_iterator_dump", "pqr_valdump_free", "pqr_pagedump_free", "pqr_strdump_free", "pqr_read_columnar",
-    "pqr_columnar_free", "pqr_read_columns_into", "pqr_read_dictionary_indices_into", "pqr_chunk_dictionary", "pqr_release_plans", "pqr_column_tables", "pqr_tables_free", "pqr_chunk_index", "pqr_regex_prune",
+    "pqr_columnar_free", "pqr_read_columns_into", "pqr_read_dictionary_indices_into", "pqr_chunk_dictionary", "pqr_release_plans", "pqr_column_tables", "pqr_columns_tables", "pqr_tables_free", "pqr_chunk_index", "pqr_regex_prune",
     "pqr_page_chunk_index", "pqr_shard_row_groups", "pqr_regex_prune_rgs", "pqr_chunk_index_rgs", "pqr_read_columns_into_rgs",
 ]
 
@@ -243,6 +244,7 @@ def _declare(L):
     d("pqr_chunk_index_rgs", i64, vp, cp, i64, i64, u64, u64, u32, vp, i64, C.POINTER(u64))
     d("pqr_read_columns_into_rgs", i32, vp, C.POINTER(C.c_int32), i32, i64, i64, C.POINTER(Dst), C.POINTER(ReadStats))
     d("pqr_column_tables", i32, vp, i32, i32, C.POINTER(Tables))
+    d("pqr_columns_tables", i32, vp, C.POINTER(C.c_int), i32, i32, C.POINTER(Tables))
     d("pqr_tables_free", None, C.POINTER(Tables))
     d("pqr_chunk_index", i64, vp, cp, u64, vp, i64)
     d("pqr_regex_prune", i64, vp, i32, cp, i32, vp, i64, C.POINTER(C.c_float))
@@ -488,6 +490,20 @@ class Reader:
         lib().pqr_tables_free(C.byref(t))
         return out
 
+    def columns_tables(self, cols, rg=-1):
+        """one table set for several fixed-width columns of the same value width: column k of
+        `cols` owns the output slots [k * S, (k + 1) * S), S = total_slots / len(cols)"""
+        t = Tables()
+        arr = (C.c_int * len(cols))(*cols)
+        self._check(lib().pqr_columns_tables(self.h, arr, len(cols), rg, C.byref(t)))
+        chunks = (ChunkDesc * max(t.n_chunks, 1))()
+        pages = (PageDesc * max(t.n_pages, 1))()
+        C.memmove(chunks, t.chunks, C.sizeof(ChunkDesc) * t.n_chunks)
+        C.memmove(pages, t.pages, C.sizeof(PageDesc) * t.n_pages)
+        out = (chunks, t.n_chunks, pages, t.n_pages, t.total_slots)
+        lib().pqr_tables_free(C.byref(t))
+        return out
+
     def chunk_index(self, name, chunk_size=4096):
         nrows = self.num_rows
         t2c = np.zeros(max(nrows, 1), dtype=np.uint64)
@@ -585,13 +601,13 @@ class Plan:
         t = Timings()
         lib().pqg_plan_timings(self.h, C.byref(t))
         return dict(dict_ms=t.dict_ms, fixed_ms=t.fixed_ms, str_size_ms=t.str_size_ms, str_copy_ms=t.str_copy_ms,
-                    total_ms=t.total_ms, launches=t.launches, general_ms=t.general_ms)
+                    total_ms=t.total_ms, launches=t.launches, general_ms=t.general_ms, tile_launches=t.tile_launches)
 
     def timings_avg(self, last_n=0):
         t, n = Timings(), C.c_uint32(0)
         lib().pqg_plan_timings_avg(self.h, last_n, C.byref(t), C.byref(n))
         return dict(dict_ms=t.dict_ms, fixed_ms=t.fixed_ms, str_size_ms=t.str_size_ms, str_copy_ms=t.str_copy_ms,
-                    total_ms=t.total_ms, launches=t.launches, general_ms=t.general_ms, runs=n.value)
+                    total_ms=t.total_ms, launches=t.launches, general_ms=t.general_ms, tile_launches=t.tile_launches, runs=n.value)
 
     num_slots = property(lambda s: lib().pqg_plan_num_slots(s.h))
     width = property(lambda s: lib().pqg_plan_value_width(s.h))

@@ -60,9 +60,12 @@ struct pqg_plan {
     bool any_dict = false, any_def = false, is_str = false, is_bool = false;
     int phys = 0, width = 0;
     uint64_t n_slots = 0;
+    uint32_t tile_launches = 0;              // tile-kernel launches of the current run
     mutable uint32_t max_page_values = 0xffffffffu; // most num_values of one page (computed on first use)
     uint8_t* d_values = nullptr;
     uint32_t* d_validity = nullptr;
+    uint64_t* d_required_ranges = nullptr;   // plans with validity: slot ranges of the REQUIRED chunks
+    uint32_t n_required_ranges = 0;
     uint32_t* d_offsets = nullptr;
     uint8_t* d_chars = nullptr;
     uint64_t chars_cap = 0, chars_size = 0;
@@ -260,7 +263,7 @@ void pqg_plan_destroy(pqg_ctx* ctx, pqg_plan* p) {
     if (!p) return;
     if (ctx) cudaSetDevice(ctx->device);
     cudaFree(p->d_chunks); cudaFree(p->d_pages); cudaFree(p->d_dict); cudaFree(p->d_values);
-    cudaFree(p->d_validity); cudaFree(p->d_offsets); cudaFree(p->d_chars); cudaFree(p->d_page_chars);
+    cudaFree(p->d_validity); cudaFree(p->d_required_ranges); cudaFree(p->d_offsets); cudaFree(p->d_chars); cudaFree(p->d_page_chars);
     cudaFree(p->d_page_char_base); cudaFree(p->d_bases); cudaFree(p->d_err); cudaFree(p->d_tiles); cudaFree(p->d_slow_pages);
     if (p->h_bases) cudaFreeHost(p->h_bases);
     if (p->h_err) cudaFreeHost(p->h_err);
@@ -269,6 +272,22 @@ void pqg_plan_destroy(pqg_ctx* ctx, pqg_plan* p) {
     if (p->ev_idle) cudaEventDestroy(p->ev_idle);
     delete p;
 }
+
+// Plans that mix REQUIRED and OPTIONAL chunks (several columns in one plan): the slots of the
+// REQUIRED chunks read "valid" in the plan's validity bitmap.  ranges: [2 * i] = first slot,
+// [2 * i + 1] = one past the last slot; one CTA per range.
+__global__ void k_validity_ranges(uint32_t* validity, const uint64_t* ranges) {
+    const uint64_t a0 = ranges[2 * blockIdx.x], a1 = ranges[2 * blockIdx.x + 1];
+    if (a1 <= a0) return;
+    const uint64_t w0 = a0 >> 5, w1 = (a1 - 1) >> 5;
+    for (uint64_t w = w0 + threadIdx.x; w <= w1; w += blockDim.x) {
+        uint32_t m = 0xffffffffu;
+        if (w == w0) m &= ~0u << (a0 & 31u);
+        if (w == w1 && (a1 & 31u)) m &= (1u << (a1 & 31u)) - 1u;
+        if (m == 0xffffffffu) validity[w] = m; else atomicOr(&validity[w], m);
+    }
+}
+static cudaError_t reset_validity(pqg_plan* p, cudaStream_t s);
 
 static int plan_create_impl(pqg_ctx* ctx, const pqg_buf* image, const pqg_chunk_desc* chunks, uint32_t n_chunks,
                             const pqg_page_desc* pages, uint32_t n_pages, bool dict_indices, pqg_plan** out);
@@ -323,7 +342,11 @@ static int plan_create_impl(pqg_ctx* ctx, const pqg_buf* image, const pqg_chunk_
     uint64_t slots = 0;
     for (uint32_t c = 0; c < n_chunks; c++) {
         const pqg_chunk_desc& s = chunks[c];
-        if (s.phys_type != p->phys) return bail(PQG_ERR_ARG, "pqg_plan_create: chunks of one plan must share a physical type");
+        // values are moved as raw bits: chunks of several columns may share a plan when their value width
+        // is the same (INT32/FLOAT, INT64/DOUBLE); BYTE_ARRAY, BOOLEAN and INT96 plans stay single-type
+        if (s.phys_type != p->phys && (p->is_str || p->is_bool || p->width == 12 || type_width(s.phys_type) != p->width ||
+                                       s.phys_type == PQG_BOOLEAN || s.phys_type == PQG_INT96))
+            return bail(PQG_ERR_ARG, "pqg_plan_create: chunks of one plan must share a physical type (or a 4- / 8-byte value width)");
         if (static_cast<uint64_t>(s.first_page) + s.n_pages > n_pages) return bail(PQG_ERR_ARG, "pqg_plan_create: chunk page range out of bounds");
         DevChunk& d = dc[c];
         std::memset(&d, 0, sizeof(d));
@@ -480,6 +503,16 @@ static int plan_create_impl(pqg_ctx* ctx, const pqg_buf* image, const pqg_chunk_
     PA(p->d_slow_pages, sizeof(uint32_t) * (static_cast<size_t>(n_pages) + p->virt_pages.size() + 1));
     PA(p->d_tiles, sizeof(TileDesc) * std::max<size_t>(tiles.size(), 1));
     if (p->any_def) PA(p->d_validity, ((slots + 31) / 32 + 1) * 4);
+    if (p->any_def && !p->is_str) {
+        std::vector<uint64_t> rr;
+        for (uint32_t c = 0; c < n_chunks; c++)
+            if (chunks[c].max_def == 0 && chunks[c].num_values) { rr.push_back(chunks[c].out_row_base); rr.push_back(chunks[c].out_row_base + chunks[c].num_values); }
+        if (!rr.empty()) {
+            PA(p->d_required_ranges, rr.size() * 8);
+            p->n_required_ranges = static_cast<uint32_t>(rr.size() / 2);
+            if ((e = cudaMemcpy(p->d_required_ranges, rr.data(), rr.size() * 8, cudaMemcpyHostToDevice)) != cudaSuccess) { pqg_plan_destroy(ctx, p); return cuda_fail(ctx, e, "cudaMemcpy(ranges)"); }
+        }
+    }
     if (p->is_str) {
         PA(p->d_offsets, (slots + n_chunks + 1) * 4);
         PA(p->d_page_chars, static_cast<size_t>(n_pages + 1) * 4);
@@ -561,6 +594,16 @@ static cudaError_t reset_err(pqg_plan* p, cudaStream_t s) {
 }
 
 // decode of chunks [c0, c1) of a fixed-width plan on stream s; returns kernels launched or -1
+static cudaError_t reset_validity(pqg_plan* p, cudaStream_t s) {
+    if (!p->d_validity) return cudaSuccess;
+    cudaError_t e = cudaMemsetAsync(p->d_validity, 0, ((p->n_slots + 31) / 32 + 1) * 4, s);
+    if (e == cudaSuccess && p->n_required_ranges) {
+        k_validity_ranges<<<p->n_required_ranges, 256, 0, s>>>(p->d_validity, p->d_required_ranges);
+        e = cudaGetLastError();
+    }
+    return e;
+}
+
 static int fixed_subrun(pqg_ctx* ctx, pqg_plan* p, uint32_t c0, uint32_t c1, bool reset_counters, cudaStream_t s, cudaError_t* err,
                         cudaEvent_t ev_tiles_begin = nullptr, cudaEvent_t ev_tiles_end = nullptr) {
     DecodeParams P = make_params(p);
@@ -580,28 +623,43 @@ static int fixed_subrun(pqg_ctx* ctx, pqg_plan* p, uint32_t c0, uint32_t c1, boo
                 DecodeParams Pc = P;
                 Pc.chunk_lo = c;
                 Pc.tile_lo = p->chunk_tile_begin[c]; Pc.tile_hi = p->chunk_tile_begin[c + 1];
-                if (Pc.tile_hi > Pc.tile_lo) { e = launch_fixed_tiles_cluster(Pc, p->width, ctx->sm_count, s); launches++; }
+                if (Pc.tile_hi > Pc.tile_lo) { e = launch_fixed_tiles_cluster(Pc, p->width, ctx->sm_count, s); launches++; p->tile_launches++; }
             }
         } else {
             // Dictionaries too large for shared memory are gathered from L2: keep the dictionaries of
             // the chunks that are in flight together within ~48 MB (a 1 M-entry INT64 dictionary is
             // 8 MB per chunk; with every chunk of a 320 M-row column in one launch the 126 MB L2
             // thrashed and the gather fell from 2.2 to 1.1 TB/s) -- one launch per chunk group.
+            // Plans over several columns: a launch also ends where the KIND of work changes (PLAIN copy /
+            // shared-memory dictionary / L2 gather) -- streaming PLAIN pages next to a gather evicts the
+            // dictionaries (measured: everything in one launch ran 2.4x slower than one launch per column).
+            auto kind_of = [&](const pqg_chunk_desc& ck) {
+                const uint64_t db = ck.has_dict ? static_cast<uint64_t>(ck.dict_num_values) * p->width : 0;
+                return !ck.has_dict ? 0 : (db <= static_cast<uint64_t>(kMaxSmemDictBytes) ? 1 : 2);
+            };
             uint32_t g0 = c0;
             while (g0 < c1 && e == cudaSuccess) {
                 uint64_t dict_bytes = 0;
                 uint32_t g1 = g0;
+                const int kind = kind_of(p->chunks[g0]);
                 while (g1 < c1) {
                     const pqg_chunk_desc& ck = p->chunks[g1];
                     const uint64_t db = ck.has_dict ? static_cast<uint64_t>(ck.dict_num_values) * p->width : 0;
                     const bool in_smem = db <= static_cast<uint64_t>(kMaxSmemDictBytes);
-                    if (g1 > g0 && !in_smem && dict_bytes + db > (48ull << 20)) break;
+                    if (g1 > g0 && (kind_of(ck) != kind || (!in_smem && dict_bytes + db > (48ull << 20)))) break;
                     if (!in_smem) dict_bytes += db;
                     g1++;
                 }
                 DecodeParams Pg = P;
                 Pg.tile_lo = p->chunk_tile_begin[g0]; Pg.tile_hi = p->chunk_tile_begin[g1];
-                if (Pg.tile_hi > Pg.tile_lo) { e = launch_fixed_tiles(Pg, p->width, ctx->sm_count, s); launches++; }
+                // shared memory for the largest staged dictionary of THIS launch only (the carve-out eats L1)
+                Pg.dict_smem = 0;
+                for (uint32_t c = g0; c < g1; c++) {
+                    const pqg_chunk_desc& ck = p->chunks[c];
+                    const uint64_t db = ck.has_dict ? (static_cast<uint64_t>(ck.dict_num_values) * p->width + 15u) & ~15ull : 0;
+                    if (db && db <= p->dict_smem) Pg.dict_smem = std::max<uint32_t>(Pg.dict_smem, static_cast<uint32_t>(db));
+                }
+                if (Pg.tile_hi > Pg.tile_lo) { e = launch_fixed_tiles(Pg, p->width, ctx->sm_count, s); launches++; p->tile_launches++; }
                 g0 = g1;
             }
         }
@@ -633,10 +691,11 @@ int pqg_plan_run(pqg_ctx* ctx, pqg_plan* p) {
     const bool prof = ctx->profiling;
     uint32_t launches = 0;
     p->timed = prof;
+    p->tile_launches = 0;
     if (prof) { p->ev = p->evr[p->runs_timed % pqg_plan::kTimingSlots]; p->runs_timed++; }
     if (prof) CU(ctx, cudaEventRecord(p->ev[0], s));
     CU(ctx, reset_err(p, s));
-    if (p->d_validity) CU(ctx, cudaMemsetAsync(p->d_validity, 0, ((p->n_slots + 31) / 32 + 1) * 4, s));
+    CU(ctx, reset_validity(p, s));
     DecodeParams P = make_params(p);
     if (!p->is_str) {
         // ev0 .. ev1 dictionary preparation, ev1 .. ev2 the tile kernel, ev2 .. ev3 the general kernel
@@ -680,6 +739,7 @@ int pqg_plan_run(pqg_ctx* ctx, pqg_plan* p) {
     }
     if (prof) CU(ctx, cudaEventRecord(p->ev[4], s));
     p->tm.launches = launches;
+    p->tm.tile_launches = p->tile_launches;
     p->last_launches = launches;
     ctx->launches += launches;
     p->ran = true;
@@ -776,9 +836,10 @@ int pqg_plan_run_pipelined(pqg_ctx* ctx, pqg_plan* p, pqg_buf* image, const pqg_
     cudaStream_t s = ctx->stream;
     const bool prof = ctx->profiling;
     p->timed = prof;
+    p->tile_launches = 0;
     if (prof) { p->ev = p->evr[p->runs_timed % pqg_plan::kTimingSlots]; p->runs_timed++; CU(ctx, cudaEventRecord(p->ev[0], s)); CU(ctx, cudaEventRecord(p->ev[1], s)); }
     CU(ctx, reset_err(p, s));
-    if (p->d_validity) CU(ctx, cudaMemsetAsync(p->d_validity, 0, ((p->n_slots + 31) / 32 + 1) * 4, s));
+    CU(ctx, reset_validity(p, s));
     // the image buffer is overwritten: wait for the kernels of the previous run of this plan
     CU(ctx, cudaStreamWaitEvent(ctx->h2d, p->ev_idle, 0));
     uint32_t launches = 0, r = 0;
@@ -806,6 +867,7 @@ int pqg_plan_run_pipelined(pqg_ctx* ctx, pqg_plan* p, pqg_buf* image, const pqg_
     CU(ctx, cudaEventRecord(p->ev_idle, s));
     if (prof) { CU(ctx, cudaEventRecord(p->ev[2], s)); CU(ctx, cudaEventRecord(p->ev[3], s)); CU(ctx, cudaEventRecord(p->ev[4], s)); }
     p->tm.launches = launches;
+    p->tm.tile_launches = p->tile_launches;
     p->last_launches = launches;
     ctx->launches += launches;
     p->ran = true;
@@ -837,6 +899,7 @@ int pqg_plan_timings_avg(const pqg_plan* plan, uint32_t last_n, pqg_timings* out
     }
     if (n) { acc.dict_ms /= n; acc.fixed_ms /= n; acc.str_size_ms /= n; acc.str_copy_ms /= n; acc.total_ms /= n; acc.general_ms /= n; }
     acc.launches = plan->last_launches;
+    acc.tile_launches = plan->tile_launches;
     *out = acc;
     if (n_used) *n_used = n;
     return PQG_OK;

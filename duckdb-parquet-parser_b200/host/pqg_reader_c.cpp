@@ -1,5 +1,6 @@
 // pqg_reader_c.cpp -- extern "C" surface of the host reader (include/pqg_reader.h).
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <string>
 
@@ -346,6 +347,61 @@ int pqr_column_tables(const pqr_reader* r, int col, int rg, pqr_tables* out) {
         out->pages = static_cast<pqg_page_desc*>(std::malloc(sizeof(pqg_page_desc) * (t.pages.size() + 1)));
         std::memcpy(out->chunks, t.chunks.data(), sizeof(pqg_chunk_desc) * t.chunks.size());
         std::memcpy(out->pages, t.pages.data(), sizeof(pqg_page_desc) * t.pages.size());
+        return 0;
+    }, -1);
+}
+int pqr_columns_tables(const pqr_reader* r, const int* cols, int n_cols, int rg, pqr_tables* out) {
+    return guarded([&]() -> int {
+        if (!cols || n_cols <= 0) throw std::runtime_error("pqr_columns_tables: no columns");
+        if (rg >= static_cast<int>(r->r.num_row_groups())) throw std::runtime_error("Invalid row group index");
+        auto width_of = [](int phys) { return phys == PQG_INT32 || phys == PQG_FLOAT ? 4 : (phys == PQG_INT64 || phys == PQG_DOUBLE ? 8 : 0); };
+        std::vector<ColumnTables> ts;
+        int width = 0;
+        uint64_t slots = 0;
+        for (int k = 0; k < n_cols; k++) {
+            if (cols[k] < 0 || cols[k] >= static_cast<int>(r->r.num_columns())) throw std::runtime_error("Invalid column index");
+            ts.push_back(r->r.column_tables(cols[k], rg));
+            const ColumnTables& t = ts.back();
+            for (const pqg_chunk_desc& c : t.chunks) {
+                const int w = width_of(c.phys_type);
+                if (w == 0 || (width && w != width)) throw std::runtime_error("pqr_columns_tables: the columns of one plan must share a 4- or 8-byte value width");
+                width = w;
+            }
+            if (k && t.total_slots != slots) throw std::runtime_error("pqr_columns_tables: the columns must have the same number of slots");
+            slots = t.total_slots;
+        }
+        struct Item { int k; uint32_t c; uint64_t dict_bytes; };
+        std::vector<Item> items;
+        size_t n_pages = 0;
+        for (int k = 0; k < n_cols; k++) {
+            for (uint32_t c = 0; c < ts[k].chunks.size(); c++) {
+                const pqg_chunk_desc& d = ts[k].chunks[c];
+                items.push_back({k, c, d.has_dict ? static_cast<uint64_t>(d.dict_num_values) * width : 0});
+            }
+            n_pages += ts[k].pages.size();
+        }
+        std::stable_sort(items.begin(), items.end(), [](const Item& a, const Item& b) { return a.dict_bytes > b.dict_bytes; });
+        out->n_chunks = static_cast<uint32_t>(items.size());
+        out->n_pages = static_cast<uint32_t>(n_pages);
+        out->total_slots = slots * static_cast<uint64_t>(n_cols);
+        out->chunks = static_cast<pqg_chunk_desc*>(std::malloc(sizeof(pqg_chunk_desc) * (items.size() + 1)));
+        out->pages = static_cast<pqg_page_desc*>(std::malloc(sizeof(pqg_page_desc) * (n_pages + 1)));
+        uint32_t pg = 0;
+        for (uint32_t i = 0; i < items.size(); i++) {
+            const ColumnTables& t = ts[items[i].k];
+            const uint64_t base = slots * static_cast<uint64_t>(items[i].k);
+            pqg_chunk_desc d = t.chunks[items[i].c];
+            const uint32_t first = d.first_page;
+            d.first_page = pg;
+            d.out_row_base += base;
+            out->chunks[i] = d;
+            for (uint32_t q = 0; q < d.n_pages; q++) {
+                pqg_page_desc pd = t.pages[first + q];
+                pd.chunk_idx = i;
+                pd.out_row_base += base;
+                out->pages[pg++] = pd;
+            }
+        }
         return 0;
     }, -1);
 }

@@ -121,6 +121,7 @@ typedef struct pqg_timings {
     float total_ms;
     uint32_t launches;/* kernels launched by the run */
     float general_ms; /* fixed-width plans: the general kernel (levels, RLE runs, big pages) */
+    uint32_t tile_launches; /* fixed-width plans: launches of the tile kernel inside fixed_ms */
 } pqg_timings;
 
 /* ---- context ------------------------------------------------------------------------- */

@@ -138,6 +138,13 @@ PQG_API void pqr_strdump_free(pqr_strdump* d);
 PQG_API int pqr_read_columnar(pqr_reader* r, int col, int rg, pqr_columnar* out);
 PQG_API void pqr_columnar_free(pqr_columnar* c);
 PQG_API int pqr_column_tables(const pqr_reader* r, int col, int rg, pqr_tables* out);
+/* Descriptor tables of SEVERAL fixed-width columns of the same value width (INT32/FLOAT or
+ * INT64/DOUBLE) for ONE plan: column k of the call owns the output slots [k * S, (k + 1) * S) of
+ * the plan's value / validity buffers (S = slots of one column in the selected row groups =
+ * total_slots / n_cols).  Chunks are listed largest dictionary first, so that the long-running
+ * CTAs of a launch start first.  What read_column does for one column (src/reader/
+ * parquet_reader.cpp:133-165), several columns per launch. */
+PQG_API int pqr_columns_tables(const pqr_reader* r, const int* cols, int n_cols, int rg, pqr_tables* out);
 PQG_API void pqr_tables_free(pqr_tables* t);
 
 /* Streaming read of fixed-width columns (the fast path of ParquetReader::read_column for callers

@@ -297,3 +297,56 @@ def test_large_string_dictionary(pq, oracle, tmp_path):
     finally:
         oracle.close(h)
         r.close()
+
+
+def test_multi_column_plan_matches_the_per_column_plans(pq, files):
+    """pqr_columns_tables: several columns of one value width in ONE plan (column k owns the
+    slots [k * S, (k + 1) * S)), chunks listed largest dictionary first -- the decoded bits and
+    the validity must equal what one plan per column produces"""
+    for name in ("fixed_plain", "fixed_dict"):
+        if name not in files:
+            continue
+        path = files[name]
+        img = np.fromfile(path, dtype=np.uint8)
+        r = pq.Reader(path)
+        for types, dt in (((pq.INT64, pq.DOUBLE), np.uint64), ((pq.INT32, pq.FLOAT), np.uint32)):
+            cols = [c for c in range(r.num_columns) if r.column_info(c)["type"] in types]
+            if len(cols) < 2:
+                continue
+            ctx = pq.Context(0)
+            buf = ctx.upload(img.ctypes.data, img.size)
+            t = r.columns_tables(cols, -1)
+            S = t[4] // len(cols)
+            plan = ctx.plan(buf, t)
+            plan.run()
+            plan.finish()
+            vals = np.zeros(S * len(cols), dtype=dt)
+            valid = np.zeros((S * len(cols) + 31) // 32 + 1, dtype=np.uint32)
+            has_validity = plan.validity_ptr is not None and plan.validity_ptr != 0
+            plan.download(values=vals.ctypes.data, validity=valid.ctypes.data if has_validity else None)
+            ctx.sync()
+            slot = np.arange(S * len(cols))
+            vbits = ((valid[slot >> 5] >> (slot & 31).astype(np.uint32)) & 1).astype(bool) if has_validity else np.ones(S * len(cols), dtype=bool)
+            for k, c in enumerate(cols):
+                one = ctx.plan(buf, r.column_tables(c, -1))
+                one.run()
+                one.finish()
+                v1 = np.zeros(S, dtype=dt)
+                m1 = np.zeros((S + 31) // 32 + 1, dtype=np.uint32)
+                hv = one.validity_ptr is not None and one.validity_ptr != 0
+                one.download(values=v1.ctypes.data, validity=m1.ctypes.data if hv else None)
+                ctx.sync()
+                b1 = ((m1[np.arange(S) >> 5] >> (np.arange(S) & 31).astype(np.uint32)) & 1).astype(bool) if hv else np.ones(S, dtype=bool)
+                assert np.array_equal(vals[k * S:(k + 1) * S], v1), (name, r.column_info(c)["name"])
+                assert np.array_equal(vbits[k * S:(k + 1) * S], b1), (name, r.column_info(c)["name"])
+                one.destroy()
+            plan.destroy()
+            ctx.buf_free(buf)
+            ctx.close()
+        # widths cannot be mixed
+        c4 = [c for c in range(r.num_columns) if r.column_info(c)["type"] == pq.INT32]
+        c8 = [c for c in range(r.num_columns) if r.column_info(c)["type"] == pq.INT64]
+        if c4 and c8:
+            with pytest.raises(pq.PqgError, match="value width"):
+                r.columns_tables([c4[0], c8[0]], -1)
+        r.close()
