@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(1024) k_dict_prepare(DecodeParams P) {
         mn = __reduce_min_sync(0xffffffffu, mn); mx = __reduce_max_sync(0xffffffffu, mx);
         if ((tid & 31u) == 0) { atomicMin(&s_minlen, mn); atomicMax(&s_maxlen, mx); }
         __syncthreads();
-        const bool is_short = nok > 0 && s_maxlen <= 15u;
+        const bool is_short = nok > 0 && s_maxlen <= 15u && !P.skip_dict_pad;
         if (is_short) {
             uint4* pad = reinterpret_cast<uint4*>(P.dict_arena + ck.dict_pad_off);
             for (uint32_t i = tid; i < nok; i += nthr) {

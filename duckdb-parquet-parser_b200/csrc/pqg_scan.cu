@@ -746,6 +746,7 @@ int pqg_regex_scan(pqg_ctx* ctx, pqg_plan* plan, const pqg_dfa* dfa, int neg, ui
     uint32_t launches = 0;
     CUF(ctx, cudaEventRecord(e0, s));
     if (plan_any_dict(plan)) {
+        P.skip_dict_pad = 1; // entries {start, len} only: the scan reads the dictionary chars in place
         CUF(ctx, launch_dict_prepare(P, P.n_chunks, 0, 1, s));
         k_regex_dict<<<dim3(64, P.n_chunks), 256, 0, s>>>(R);
         launches += 2;
