@@ -8,7 +8,8 @@ Workload (BASELINE.json configs[1], SURVEY.md section 8 d "Config 2"): a 100 M-r
 10 row groups x 10 M rows with 7 columns -- INT64 PLAIN, DOUBLE PLAIN, INT64 dictionary with
 2^8 / 2^12 / 2^16 / 2^20 distinct keys (index bit widths 8 / 12 / 16 / 20) and DOUBLE
 dictionary with 2^16 keys -- produced by the workload generator, which is byte-identical to the
-reference's ParquetWriter (tests/test_gen_cpu.py).  One step = one decode of all 7 columns.
+reference's ParquetWriter (tests/test_gen_cpu.py).  One step = one decode of all 7 columns
+through ONE plan (pqr_columns_tables; PQG_BENCH_PER_COLUMN=1 runs one plan per column instead).
 
   value      Sigma page payload bytes (data + dictionary pages) / device time, image resident in
              HBM, K steps timed with CUDA events on the decoder's stream, max over ranks.
