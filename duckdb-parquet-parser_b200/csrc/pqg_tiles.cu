@@ -116,6 +116,62 @@ __device__ __forceinline__ void with_dict_mode(int mode, F&& f) {
     }
 }
 
+// RleDecoder::get_batch (include/reader/rle_decoder.hpp:17-95) for a whole page of dictionary
+// indices, run by run: every lane decodes the (warp-uniform) run header; a literal run of g groups
+// is 8 g consecutive bw-bit values -- lane k takes values k, k + 32, ...; an RLE run is one
+// dictionary value stored count times.  Returns false on anything the reference handles by
+// zero-filling, throwing or producing nulls (stream exhausted early, zero-length RLE run, value
+// bytes cut off, index >= dictionary size): the general kernel redoes those pages.
+template <int W, int MODE>
+__device__ __noinline__ bool hybrid_runs_page(const DecodeParams& P, const uint8_t* s, uint32_t len, uint32_t bw, uint32_t n,
+                                             const DictRef& dref, uint32_t dict_n, typename FElem<W>::T* out) {
+    using T = typename FElem<W>::T;
+    const uint32_t l = lane_id();
+    const uint32_t sa = smem_u32(s);
+    const SmemWords ldw{sa & ~3u};
+    const uint32_t bit0 = (sa & 3u) * 8u;
+    const uint32_t nb = (bw + 7u) >> 3, imask = bw >= 32u ? 0xffffffffu : ((1u << bw) - 1u);
+    uint32_t pos = 0, v = 0;
+    bool bad = false;
+    while (v < n) {
+        uint32_t hdr = 0, shift = 0;
+        for (;;) { // varint32 (rle_decoder.hpp:76-86)
+            if (pos >= len || shift > 28u) return false;
+            const uint32_t b = s[pos++];
+            hdr |= (b & 0x7fu) << shift;
+            if (!(b & 0x80u)) break;
+            shift += 7u;
+        }
+        if (hdr & 1u) {
+            const uint32_t groups = hdr >> 1;
+            const uint64_t bytes = static_cast<uint64_t>(groups) * bw;
+            if (pos + bytes > len) return false;
+            const uint32_t take = static_cast<uint32_t>(min(static_cast<uint64_t>(groups) * 8u, static_cast<uint64_t>(n - v)));
+            const uint32_t base = bit0 + pos * 8u;
+            for (uint32_t k = l; k < take; k += 32) {
+                const uint32_t bit = base + k * bw;
+                const uint32_t ix = __funnelshift_r(ldw(bit >> 5), ldw((bit >> 5) + 1u), bit & 31u) & imask;
+                bad = bad || ix >= dict_n;
+                st_stream<T>(out + v + k, dict_get<T, W, MODE>(dref, ix < dict_n ? ix : 0u));
+            }
+            pos += static_cast<uint32_t>(bytes);
+            v += take;
+        } else {
+            const uint32_t cnt = hdr >> 1;
+            if (cnt == 0 || pos + nb > len) return false;
+            uint32_t ix = 0;
+            for (uint32_t i = 0; i < nb; i++) ix |= static_cast<uint32_t>(s[pos + i]) << (8u * i); // not masked, like the reference (:88-95)
+            if (ix >= dict_n) return false;
+            const T x = dict_get<T, W, MODE>(dref, ix);
+            const uint32_t take = min(cnt, n - v);
+            for (uint32_t k = l; k < take; k += 32) st_stream<T>(out + v + k, x);
+            pos += nb;
+            v += take;
+        }
+    }
+    return !__any_sync(0xffffffffu, bad);
+}
+
 // One warp decodes one page out of the staged tile.  `pg` = first payload byte (shared).
 template <int W, bool CLUSTER = false>
 __device__ __forceinline__ bool fast_page(const DecodeParams& P, uint32_t q, const pqg_page_desc& pd, const uint8_t* pg,
@@ -146,9 +202,17 @@ __device__ __forceinline__ bool fast_page(const DecodeParams& P, uint32_t q, con
     const uint32_t bw = pg[0];
     const uint8_t* s = pg + 1;
     RegStream rs;
-    if (bw > 32 || !check_regular2(s, size - 1, bw, n, &rs)) { if (l == 0) to_slow(P, q); return false; }
+    if (bw > 32) { if (l == 0) to_slow(P, q); return false; }
     const DictRef dref{dictp, dict_in_smem ? smem_u32(dictp) : 0u, cd};
     const int mode = CLUSTER ? kDictCluster : (P.identity_dict ? kDictIdent : (dict_in_smem ? kDictSmem : kDictGlobal));
+    if (!check_regular2(s, size - 1, bw, n, &rs)) {
+        // any other well-formed hybrid stream (RLE runs between the groups, literal runs of several
+        // groups as foreign writers emit them): runs in sequence, the warp expands each one together
+        bool ok = false;
+        with_dict_mode(mode, [&](auto tag) { ok = hybrid_runs_page<W, decltype(tag)::value>(P, s, size - 1u, bw, n, dref, dict_n, out); });
+        if (!ok && l == 0) to_slow(P, q); // malformed / truncated / out-of-range index: the general kernel reports like the reference
+        return ok;
+    }
     // index bits straight from aligned shared-memory words; value v sits in group v >> 3 at
     // bit ((v >> 3) * (1 + bw) + 1) * 8 + (v & 7) * bw of the stream: +32 values = +4 groups
     const uint32_t sa = smem_u32(s);
