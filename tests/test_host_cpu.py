@@ -122,3 +122,51 @@ def test_descriptor_tables(pq, oracle):
             assert ck.num_values == row - ck.out_row_base
         assert total == row == r.num_rows
     r.close()
+
+
+def test_multi_column_descriptor_tables(pq, files):
+    """pqr_columns_tables: column k of the call owns the slots [k * S, (k + 1) * S); every chunk and
+    page of the per-column tables shows up exactly once, pages contiguous per chunk, chunks with the
+    largest dictionaries first; columns of different value widths are refused"""
+    name = "fixed_dict" if "fixed_dict" in files else None
+    if name is None:
+        pytest.skip("needs the reference-written fixture files")
+    r = pq.Reader(files[name])
+    cols = [c for c in range(r.num_columns) if r.column_info(c)["type"] in (pq.INT64, pq.DOUBLE)]
+    assert len(cols) >= 3
+    chunks, nc, pages, npg, total = r.columns_tables(cols, -1)
+    S = r.num_rows
+    assert total == S * len(cols)
+    singles = [r.column_tables(c, -1) for c in cols]
+    assert nc == sum(t[1] for t in singles) and npg == sum(t[3] for t in singles)
+    seen = set()
+    pg = 0
+    last_dict = None
+    for i in range(nc):
+        ck = chunks[i]
+        k = cols.index(ck.column)
+        base = k * S
+        one = [singles[k][0][j] for j in range(singles[k][1]) if singles[k][0][j].row_group == ck.row_group][0]
+        assert ck.out_row_base == base + one.out_row_base and ck.num_values == one.num_values
+        assert (ck.dict_off, ck.dict_size, ck.dict_num_values, ck.has_dict, ck.n_pages) == \
+               (one.dict_off, one.dict_size, one.dict_num_values, one.has_dict, one.n_pages)
+        assert ck.first_page == pg
+        row = ck.out_row_base
+        for q in range(ck.n_pages):
+            a, b = pages[pg + q], singles[k][2][one.first_page + q]
+            assert a.chunk_idx == i and a.out_row_base == row
+            assert (a.payload_off, a.payload_size, a.num_values, a.flags) == (b.payload_off, b.payload_size, b.num_values, b.flags)
+            row += a.num_values
+        pg += ck.n_pages
+        d = ck.dict_num_values * 8 if ck.has_dict else 0
+        assert last_dict is None or d <= last_dict  # heaviest gathers start first
+        last_dict = d
+        seen.add((ck.column, ck.row_group))
+    assert len(seen) == nc
+    c4 = [c for c in range(r.num_columns) if r.column_info(c)["type"] in (pq.INT32, pq.FLOAT)]
+    if c4:
+        with pytest.raises(pq.PqgError, match="value width"):
+            r.columns_tables([cols[0], c4[0]], -1)
+    with pytest.raises(pq.PqgError):
+        r.columns_tables([], -1)
+    r.close()
