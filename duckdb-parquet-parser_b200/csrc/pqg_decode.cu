@@ -39,6 +39,20 @@ template <> __device__ __forceinline__ U96 load_plain<12>(const uint8_t* p) {
     return U96{ld32u(p), ld32u(p + 4), ld32u(p + 8)};
 }
 
+__device__ __forceinline__ uint4 shift_bytes(uint4 a, uint4 b, uint32_t sh) {
+    // bytes sh..sh+15 of the 32-byte pair (a,b); sh is warp-uniform
+    uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint32_t bs = (sh & 3u) * 8u;
+    uint4 r;
+    switch (sh >> 2) {
+        case 0: r.x = __funnelshift_r(w[0], w[1], bs); r.y = __funnelshift_r(w[1], w[2], bs); r.z = __funnelshift_r(w[2], w[3], bs); r.w = __funnelshift_r(w[3], w[4], bs); break;
+        case 1: r.x = __funnelshift_r(w[1], w[2], bs); r.y = __funnelshift_r(w[2], w[3], bs); r.z = __funnelshift_r(w[3], w[4], bs); r.w = __funnelshift_r(w[4], w[5], bs); break;
+        case 2: r.x = __funnelshift_r(w[2], w[3], bs); r.y = __funnelshift_r(w[3], w[4], bs); r.z = __funnelshift_r(w[4], w[5], bs); r.w = __funnelshift_r(w[5], w[6], bs); break;
+        default: r.x = __funnelshift_r(w[3], w[4], bs); r.y = __funnelshift_r(w[4], w[5], bs); r.z = __funnelshift_r(w[5], w[6], bs); r.w = __funnelshift_r(w[6], w[7], bs); break;
+    }
+    return r;
+}
+
 // ---------------------------------------------------------------------------------------------
 // dictionary preparation
 // ---------------------------------------------------------------------------------------------
@@ -60,8 +74,20 @@ __global__ void __launch_bounds__(1024) k_dict_prepare(DecodeParams P) {
             if (ok < n) report_error(P.err, ck.first_page, PQG_PAGE_DICT_TRUNCATED, ok * W, W, size);
         }
         typename Elem<W>::T* out = reinterpret_cast<typename Elem<W>::T*>(dst);
-        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < ok; i += gridDim.x * blockDim.x)
-            out[i] = load_plain<W>(src + static_cast<size_t>(i) * W);
+        const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gstride = gridDim.x * blockDim.x;
+        if constexpr (W == 4 || W == 8) {
+            // raw bits: a byte-shifted copy in 16-byte vectors (dst is 16-byte aligned in the arena)
+            const uint32_t m = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(src) & 15u);
+            const uint8_t* a = src - m;
+            const uint32_t nvec = static_cast<uint32_t>((static_cast<uint64_t>(ok) * W) >> 4);
+            for (uint32_t j = gtid; j < nvec; j += gstride) {
+                const uint4 v0 = ldg_nc16(a + 16ull * j);
+                reinterpret_cast<uint4*>(dst)[j] = m ? shift_bytes(v0, ldg_nc16(a + 16ull * j + 16), m) : v0;
+            }
+            for (uint32_t i = nvec * (16u / W) + gtid; i < ok; i += gstride) out[i] = load_plain<W>(src + static_cast<size_t>(i) * W);
+        } else {
+            for (uint32_t i = gtid; i < ok; i += gstride) out[i] = load_plain<W>(src + static_cast<size_t>(i) * W);
+        }
     } else {
         // BYTE_ARRAY: u32 length prefix + bytes (column_reader.cpp:249-253).  Entry table:
         // {start (byte offset of the chars inside the dictionary payload), len}.
@@ -176,20 +202,6 @@ __global__ void __launch_bounds__(1024) k_dict_prepare(DecodeParams P) {
 // PLAIN, REQUIRED, 4/8-byte values: the page payload IS the value array (shifted by the
 // payload's misalignment).  Straight global->global copy, 16-byte vectors.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint4 shift_bytes(uint4 a, uint4 b, uint32_t sh) {
-    // bytes sh..sh+15 of the 32-byte pair (a,b); sh is warp-uniform
-    uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-    uint32_t bs = (sh & 3u) * 8u;
-    uint4 r;
-    switch (sh >> 2) {
-        case 0: r.x = __funnelshift_r(w[0], w[1], bs); r.y = __funnelshift_r(w[1], w[2], bs); r.z = __funnelshift_r(w[2], w[3], bs); r.w = __funnelshift_r(w[3], w[4], bs); break;
-        case 1: r.x = __funnelshift_r(w[1], w[2], bs); r.y = __funnelshift_r(w[2], w[3], bs); r.z = __funnelshift_r(w[3], w[4], bs); r.w = __funnelshift_r(w[4], w[5], bs); break;
-        case 2: r.x = __funnelshift_r(w[2], w[3], bs); r.y = __funnelshift_r(w[3], w[4], bs); r.z = __funnelshift_r(w[4], w[5], bs); r.w = __funnelshift_r(w[5], w[6], bs); break;
-        default: r.x = __funnelshift_r(w[3], w[4], bs); r.y = __funnelshift_r(w[4], w[5], bs); r.z = __funnelshift_r(w[5], w[6], bs); r.w = __funnelshift_r(w[6], w[7], bs); break;
-    }
-    return r;
-}
-
 template <int W>
 __device__ __forceinline__ void plain_copy(const DecodeParams& P, uint32_t q, const pqg_page_desc& pd) {
     const uint32_t l = lane_id();
