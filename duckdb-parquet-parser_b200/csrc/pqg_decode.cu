@@ -1,15 +1,17 @@
 // pqg_decode.cu -- sm_100a page-decode kernels (HBM-bound integer/byte work, no tensor cores).
 //
-//   k_dict_prepare   one CTA per column chunk: dictionary page -> aligned value table
-//                    (fixed width) or {start,len} entry table (BYTE_ARRAY).
+//   k_dict_prepare   per column chunk: dictionary page -> aligned value table (fixed width:
+//                    byte-shifted vector copy) or {start,len} entry table + 16-byte padded
+//                    entries for short-string dictionaries (BYTE_ARRAY, one CTA per dictionary).
 //                    Replaces ColumnReader::read_dictionary_page (column_reader.cpp:128-138).
-//   k_decode_fixed   one warp per data page: levels + PLAIN / dictionary values ->
-//                    values[] + validity bits.  Replaces read_data_page
+//   k_decode_fixed   the GENERAL fixed-width kernel, one warp per data page from the slow list
+//                    (what the tile kernel of pqg_tiles.cu does not take): levels + PLAIN /
+//                    dictionary values -> values[] + validity bits.  Replaces read_data_page
 //                    (column_reader.cpp:140-225) and read_plain_value (:227-268) for
 //                    BOOLEAN / INT32 / INT64 / INT96 / FLOAT / DOUBLE.
-//   k_str_sizes      BYTE_ARRAY pass 1: string bytes per page.
+//   k_str_pages<0>   BYTE_ARRAY pass 1: string bytes per page.
 //   k_str_scan_*     exclusive scans: page bases inside a chunk, chunk bases in the column.
-//   k_str_copy       BYTE_ARRAY pass 2: Arrow-style offsets + chars.
+//   k_str_pages<1>   BYTE_ARRAY pass 2: Arrow-style offsets + chars.
 //
 // Grid sizing: CTAs take contiguous spans of the page table (so a CTA stages a chunk's
 // dictionary once); the grid is a multiple of the SM count when there is enough work.

@@ -1,12 +1,14 @@
 // pqg_scan.cu -- regex page-pruning scan and the greedy chunk indexes.
 //
 //   k_regex_dict     one lane per dictionary entry: predicate of the entry
-//   k_regex_pages    one warp per data page: OR over the page's non-null values of
-//                    (neg ? !match : match); PLAIN pages run the DFA over the page bytes staged
-//                    in shared memory (one lane per string), dictionary pages look the
-//                    predicate of their indices up.  Replaces the parser's
-//                    --regex-column/--regex/--neg-regex mode (reference README.md:54-64; source
-//                    absent, frozen spec SURVEY.md 8 a-19).
+//   k_regex_tiles    the fast scan on the TMA tile pipeline, one warp per data page: OR over
+//                    the page's non-null values of (neg ? !match : match); PLAIN pages: parallel
+//                    length-prefix discovery, then the DFA (absolute-address table in shared
+//                    memory) with one lane per string; dictionary pages look the predicate of
+//                    their indices up.
+//   k_regex_pages    the same for every other page shape (slow list, work stealing).
+//                    Together they replace the parser's --regex-column/--regex/--neg-regex mode
+//                    (reference README.md:54-64; source absent, frozen spec SURVEY.md 8 a-19).
 //   chain engine     greedy ">= chunk_size closes the chunk" chunking over a weight sequence
 //                    (src/main.cpp:21-32 tuple level; README.md:66-72 page level): device-wide
 //                    exclusive scan of the weights, then the cut chain c' = first prefix value

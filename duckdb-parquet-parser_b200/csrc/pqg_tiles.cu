@@ -1,23 +1,28 @@
 // pqg_tiles.cu -- the fast fixed-width decode kernel: TMA-staged page tiles.
 //
-// Covers what the reference's writer emits for REQUIRED INT32/INT64/FLOAT/DOUBLE chunks
-// (src/writer/parquet_writer.cpp:376-460):
+// Covers flat INT32/INT64/FLOAT/DOUBLE chunks, REQUIRED or OPTIONAL (max_def <= 1), as the
+// reference's writer emits them (src/writer/parquet_writer.cpp:376-460) and as foreign writers do
+// while their pages fit a tile:
 //   PLAIN pages          payload = the value array        (reader: column_reader.cpp:213-222,227-248)
-//   dictionary pages     u8 bit width + single bit-packed groups "03 <bw bytes>"
-//                        (reader: column_reader.cpp:174-196 over rle_decoder.hpp:55-65)
-// Anything else found in a tile (RLE runs inside the index stream, out-of-range indices,
-// truncated pages, bit width > 32) is NOT decoded here: the page is appended to the slow
-// list and the general kernel (pqg_decode.cu) handles it right after, with full error
-// reporting.  OPTIONAL / BOOLEAN / INT96 chunks and pages larger than a tile never enter a
-// tile (the host lists them for the general kernel directly).
+//   dictionary pages     u8 bit width + the RLE / bit-packed hybrid stream: single bit-packed
+//                        groups "03 <bw bytes>" with positional index extraction (the writer's
+//                        shape), any other well-formed stream run by run (hybrid_runs_page)
+//                        (reader: column_reader.cpp:174-196 over rle_decoder.hpp:17-95)
+//   definition levels    RLE runs <varint < 128><level> (the writer's shape) -> validity image by
+//                        toggle bits + prefix XOR; one run covering the page -> REQUIRED path
+// Anything else found in a tile (bit-packed levels, out-of-range indices, truncated or malformed
+// pages, bit width > 32) is NOT decoded here: the page is appended to the slow list and the
+// general kernel (pqg_decode.cu) handles it right after, with the reference's error reporting.
+// BOOLEAN / INT96 / nested chunks and pages larger than a tile never enter a tile (the host lists
+// them for the big-page and general kernels).
 //
 // Data movement (HBM-bound, no tensor cores):
 //   * the plan's host side cuts every chunk into tiles: <= 8 consecutive pages whose bytes
 //     (page headers in between included -- pages of a chunk are contiguous in the file) fit
-//     8 KB.  One elected thread stages tile bytes + the tile's 8 page descriptors into a
-//     kTileStages-deep shared-memory ring with cp.async.bulk (1-D TMA, UBLKCP) completing on an
-//     mbarrier; 8 warps decode one page each out of shared memory.  No register staging,
-//     loads stay 3 tiles ahead of the math.
+//     8 KB (16 KB for plans with OPTIONAL chunks).  Tile bytes + the tile's page descriptors are
+//     staged into a kTileStages-deep shared-memory ring with cp.async.bulk (1-D TMA, UBLKCP)
+//     completing on an mbarrier; 8 warps decode one page each out of shared memory; the last warp
+//     to finish a stage refills it (pqg_tilepipe.cuh).  No register staging.
 //   * a dictionary that fits (<= 32 KB of values) is staged once per chunk with the same
 //     bulk copy; larger ones are gathered from L2 (the 126 MB L2 holds even the 8 MB
 //     dictionary of a 2^20-key chunk; outputs are written with streaming stores so they do
