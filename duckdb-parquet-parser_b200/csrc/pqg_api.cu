@@ -708,7 +708,7 @@ int pqg_plan_run(pqg_ctx* ctx, pqg_plan* p) {
         // byte counts, page bases and chunk bases are known from the page headers: copy pass only
         if (prof) { CU(ctx, cudaEventRecord(p->ev[1], s)); CU(ctx, cudaEventRecord(p->ev[2], s)); }
         P.check_layout = 1;
-        if (P.page_end) { CU(ctx, launch_str_copy(P, ctx->sm_count, s)); launches++; }
+        if (P.page_end) { CU(ctx, launch_str_copy(P, p->any_dict, ctx->sm_count, s)); launches++; }
         if (prof) CU(ctx, cudaEventRecord(p->ev[3], s));
     } else {
         if (p->any_dict) {
@@ -734,7 +734,7 @@ int pqg_plan_run(pqg_ctx* ctx, pqg_plan* p) {
             p->chars_size = total;
             P.chars = p->d_chars;
         }
-        if (P.page_end) { CU(ctx, launch_str_copy(P, ctx->sm_count, s)); launches++; }
+        if (P.page_end) { CU(ctx, launch_str_copy(P, p->any_dict, ctx->sm_count, s)); launches++; }
         if (prof) CU(ctx, cudaEventRecord(p->ev[3], s));
     }
     if (prof) CU(ctx, cudaEventRecord(p->ev[4], s));

@@ -387,7 +387,140 @@ __device__ __forceinline__ void stage_words(uint8_t* dst, const uint4& v, uint32
     }
 }
 
-template <bool COPY>
+// ---- copy pass, short-string dictionaries ----------------------------------------------------
+// One tile (t <= 1024 slots) of a dictionary page whose index stream is regular and staged in shared
+// memory, against a dictionary with the 16-byte padded table (all entries <= 15 bytes): the lean
+// form of the loop in decode_str_page -- two groups of 32 slots per trip (both gathers in flight
+// together), 32-bit shared-memory addressing, positional index extraction, ONE 16-byte load per
+// value, chars packed into the zeroed staging buffer with word-wise red.shared.or (5 per string
+// instead of 15 byte stores) and flushed as full aligned 16-byte vectors: the partial vector at
+// the end of a trip stays in the buffer for the next one, only the first and last bytes of the
+// tile are stored byte-wise.  Validity comes from the tile's image afterwards (words, atomics
+// only where a word is shared with a neighbouring page).  Returns the string bytes of the tile.
+__device__ __forceinline__ uint32_t copy_short_dict_tile(const DecodeParams& P, WarpScratch& ws, const RegStream& rs, uint32_t nn_before,
+                                                         uint32_t t, const uint4* dpad, uint32_t dict_n, uint32_t* offs_tile, uint8_t* dst,
+                                                         uint32_t off0, uint64_t abs_slot0) {
+    const uint32_t l = lane_id();
+    const uint32_t sa = static_cast<uint32_t>(__cvta_generic_to_shared(rs.s));
+    const SmemWords ldw{sa & ~3u};
+    const uint32_t bit0 = (sa & 3u) * 8u, bw = rs.bw, gs = 1u + bw;
+    const uint32_t imask = bw >= 32u ? 0xffffffffu : ((1u << bw) - 1u);
+    const uint32_t stw = static_cast<uint32_t>(__cvta_generic_to_shared(ws.stage)); // 16-byte aligned
+    for (uint32_t i = l; i < static_cast<uint32_t>(kStageBytes32) / 16u; i += 32) reinterpret_cast<uint4*>(ws.stage)[i] = make_uint4(0, 0, 0, 0);
+    __syncwarp();
+    const uint32_t mis0 = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(dst) & 15u);
+    uint8_t* const abase = dst - mis0;      // aligned-space origin: byte p of the tile's chars sits at abase[mis0 + p]
+    uint32_t outp = 0;                      // chars produced so far
+    uint32_t sbase = 0;                     // aligned-space position of stage byte 0 (multiple of 16)
+    auto fetch = [&](uint32_t s, uint32_t* wv_out, bool* bad) -> uint4 {
+        uint4 pv = make_uint4(0, 0, 0, 0);
+        if (s < t) {
+            const uint32_t wv = ws.valid[s >> 5];
+            *wv_out = wv;
+            if ((wv >> (s & 31u)) & 1u) {
+                const uint32_t k = nn_before + ws.rankbase[s >> 5] + __popc(wv & ((1u << (s & 31u)) - 1u));
+                const uint32_t bit = bit0 + (((k >> 3) * gs + 1u) << 3) + (k & 7u) * bw;
+                uint32_t ix = __funnelshift_r(ldw(bit >> 5), ldw((bit >> 5) + 1u), bit & 31u) & imask;
+                ix = k >= rs.tail_start ? rs.tail_val : ix;
+                if (ix < dict_n) pv = ldg_nc16(reinterpret_cast<const uint8_t*>(dpad + ix));
+                else *bad = true;   // no value: NULL in the reference (column_reader.cpp:190-194)
+            }
+        }
+        return pv;
+    };
+    auto put = [&](const uint4& pv, uint32_t apos) { // OR the (zero-padded) string into the stage at aligned-space position apos
+        const uint32_t o = apos - sbase, sh = (o & 3u) * 8u, a = stw + (o & ~3u);
+        const uint32_t w3 = pv.w & 0x00ffffffu;
+        const uint32_t x0 = pv.x << sh, x1 = __funnelshift_l(pv.x, pv.y, sh), x2 = __funnelshift_l(pv.y, pv.z, sh);
+        const uint32_t x3 = __funnelshift_l(pv.z, w3, sh), x4 = __funnelshift_l(w3, 0u, sh);
+        if (x0) asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(a), "r"(x0) : "memory");
+        if (x1) asm volatile("red.shared.or.b32 [%0+4], %1;" ::"r"(a), "r"(x1) : "memory");
+        if (x2) asm volatile("red.shared.or.b32 [%0+8], %1;" ::"r"(a), "r"(x2) : "memory");
+        if (x3) asm volatile("red.shared.or.b32 [%0+12], %1;" ::"r"(a), "r"(x3) : "memory");
+        if (x4) asm volatile("red.shared.or.b32 [%0+16], %1;" ::"r"(a), "r"(x4) : "memory");
+    };
+    for (uint32_t g = 0; g < t; g += 64) {
+        const uint32_t s0 = g + l, s1 = g + 32u + l;
+        bool bad0 = false, bad1 = false;
+        uint32_t wv0 = 0, wv1 = 0;
+        const uint4 p0 = fetch(s0, &wv0, &bad0);
+        const uint4 p1 = fetch(s1, &wv1, &bad1);
+        const uint32_t len0 = p0.w >> 24, len1 = p1.w >> 24;
+        const uint32_t incl0 = warp_incl_scan(len0), incl1 = warp_incl_scan(len1);
+        const uint32_t tot0 = __shfl_sync(0xffffffffu, incl0, 31), tot1 = __shfl_sync(0xffffffffu, incl1, 31);
+        const uint32_t my0 = outp + incl0 - len0, my1 = outp + tot0 + incl1 - len1;
+        if (s0 < t) offs_tile[s0] = off0 + my0;
+        if (s1 < t) offs_tile[s1] = off0 + my1;
+        // out-of-range indices: the slot turns NULL (after every lane has read its validity word)
+        const uint32_t b0 = __ballot_sync(0xffffffffu, bad0), b1 = __ballot_sync(0xffffffffu, bad1);
+        if (b0 | b1) {
+            __syncwarp();
+            if (l == 0) { if (b0) ws.valid[g >> 5] &= ~b0; if (b1) ws.valid[(g >> 5) + 1u] &= ~b1; }
+        }
+        const uint32_t total = tot0 + tot1;
+        if (total) {
+            if (len0) put(p0, mis0 + my0);
+            if (len1) put(p1, mis0 + my1);
+            __syncwarp();
+            outp += total;
+            const uint32_t end = mis0 + outp;                   // aligned-space end of the staged bytes
+            const uint32_t nfull = (end >> 4) - (sbase >> 4);   // complete vectors in the stage
+            if (nfull) {
+                if (sbase == 0 && mis0) { // first vector: the bytes in front belong to another page
+                    if (l >= mis0 && l < 16u) abase[l] = ws.stage[l];
+                    __syncwarp();
+                }
+                for (uint32_t j = l; j < nfull; j += 32) {
+                    const uint4 v = *reinterpret_cast<const uint4*>(ws.stage + 16u * j);
+                    *reinterpret_cast<uint4*>(ws.stage + 16u * j) = make_uint4(0, 0, 0, 0);
+                    if (sbase + j || !mis0) *reinterpret_cast<uint4*>(abase + sbase + 16u * j) = v;
+                }
+                __syncwarp();
+                if (l == 0) { // the partial vector moves to the front
+                    const uint4 v = *reinterpret_cast<const uint4*>(ws.stage + 16u * nfull);
+                    *reinterpret_cast<uint4*>(ws.stage + 16u * nfull) = make_uint4(0, 0, 0, 0);
+                    *reinterpret_cast<uint4*>(ws.stage) = v;
+                }
+                sbase += 16u * nfull;
+                __syncwarp();
+            }
+        } else {
+            __syncwarp();
+        }
+    }
+    // the bytes behind the last complete vector (and a first vector that never filled up)
+    {
+        const uint32_t end = mis0 + outp;
+        const uint32_t from = sbase == 0 ? mis0 : sbase;
+        if (from + l < end) abase[from + l] = ws.stage[from - sbase + l]; // < 16 bytes
+        __syncwarp();
+        if (l == 0) *reinterpret_cast<uint4*>(ws.stage) = make_uint4(0, 0, 0, 0);
+    }
+    // validity: the tile's image shifted to its position in the column's bitmap, one word per lane
+    if (P.validity) {
+        __syncwarp();
+        const uint32_t head = static_cast<uint32_t>(abs_slot0 & 31u), nwords = (t + 31u) >> 5;
+        uint32_t* vp = P.validity + (abs_slot0 >> 5);
+        const uint32_t cur = l < nwords ? ws.valid[l] : 0u;
+        const uint32_t prev = (l > 0 && l <= nwords) ? ws.valid[l - 1] : 0u;
+        const uint32_t gw = head ? ((cur << head) | (prev >> (32u - head))) : cur;
+        const uint32_t totb = head + t, gwords = (totb + 31u) >> 5;
+        if (l < gwords) {
+            const bool full = (l > 0 || head == 0) && (l + 1u) * 32u <= totb;
+            if (full) vp[l] = gw; else if (gw) atomicOr(&vp[l], gw);
+        }
+        if (l == 0 && gwords > 32u) { // head pushes the last bits into a 33rd word
+            const uint32_t last = ws.valid[31] >> (32u - head);
+            if (last) atomicOr(&vp[32], last);
+        }
+    }
+    __syncwarp();
+    return outp;
+}
+
+// LEAN: the plan has dictionary chunks -- compile the short-string-dictionary copy path in (kept out of the
+// instantiation that PLAIN-only plans run: its registers cost the PLAIN path 7 %)
+template <bool COPY, bool LEAN>
 __device__ __forceinline__ void decode_str_page(const DecodeParams& P, uint32_t q, const DevChunk& ck, WarpScratch& ws) {
     const uint32_t l = lane_id();
     const pqg_page_desc pd = P.pages[q];
@@ -459,6 +592,13 @@ __device__ __forceinline__ void decode_str_page(const DecodeParams& P, uint32_t 
         }
         // ---- COPY: offsets, then chars, 32 slots per step ----
         const uint64_t slot0 = (pd.out_row_base - ck.out_row_base) + ts; // chunk-relative slot
+        if constexpr (LEAN) if (dshort && regular && c.size <= static_cast<uint32_t>(kSlotBytes)) { // (the page is in the shared slot)
+            page_bytes += copy_short_dict_tile(P, ws, rs, nn_before, t, dpad, dict_n, offs + slot0, chars + page_base + page_bytes,
+                                               static_cast<uint32_t>(page_base + page_bytes), pd.out_row_base + ts);
+            nn_before += nn;
+            __syncwarp();
+            continue;
+        }
         for (uint32_t g = 0; g < t; g += 32) {
             const uint32_t s = g + l;
             const bool in = s < t;
@@ -557,7 +697,7 @@ __device__ __forceinline__ void decode_str_page(const DecodeParams& P, uint32_t 
     }
 }
 
-template <bool COPY>
+template <bool COPY, bool LEAN>
 __global__ void __launch_bounds__(kThreadsPerCta, 3) k_str_pages(DecodeParams P) {
     extern __shared__ __align__(16) uint8_t smem[];
     WarpScratch& ws = reinterpret_cast<WarpScratch*>(smem)[warp_id()];
@@ -565,7 +705,7 @@ __global__ void __launch_bounds__(kThreadsPerCta, 3) k_str_pages(DecodeParams P)
     const uint32_t p1 = min(P.page_end, p + P.pages_per_cta);
     for (uint32_t q = p + warp_id(); q < p1; q += kWarpsPerCta) {
         const DevChunk& ck = P.chunks[P.pages[q].chunk_idx];
-        decode_str_page<COPY>(P, q, ck, ws);
+        decode_str_page<COPY, LEAN>(P, q, ck, ws);
     }
 }
 
@@ -671,19 +811,21 @@ cudaError_t launch_decode_fixed(const DecodeParams& p, int width, bool boolean_p
     }
 }
 
-template <bool COPY>
+template <bool COPY, bool LEAN>
 static cudaError_t launch_str_t(DecodeParams p, int sm_count, cudaStream_t s) {
     const size_t smem = decode_smem_bytes(false);
     uint32_t n = p.page_end - p.page_begin;
     if (n == 0) return cudaSuccess;
-    cudaError_t e = cudaFuncSetAttribute(k_str_pages<COPY>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    cudaError_t e = cudaFuncSetAttribute(k_str_pages<COPY, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
     uint32_t grid = grid_for(n, sm_count, &p.pages_per_cta, 5);
-    k_str_pages<COPY><<<grid, kThreadsPerCta, smem, s>>>(p);
+    k_str_pages<COPY, LEAN><<<grid, kThreadsPerCta, smem, s>>>(p);
     return cudaGetLastError();
 }
-cudaError_t launch_str_sizes(const DecodeParams& p, int sm_count, cudaStream_t s) { return launch_str_t<false>(p, sm_count, s); }
-cudaError_t launch_str_copy(const DecodeParams& p, int sm_count, cudaStream_t s) { return launch_str_t<true>(p, sm_count, s); }
+cudaError_t launch_str_sizes(const DecodeParams& p, int sm_count, cudaStream_t s) { return launch_str_t<false, false>(p, sm_count, s); }
+cudaError_t launch_str_copy(const DecodeParams& p, bool any_dict, int sm_count, cudaStream_t s) {
+    return any_dict ? launch_str_t<true, true>(p, sm_count, s) : launch_str_t<true, false>(p, sm_count, s);
+}
 
 // total_chars: device pointer to [n_chunks + 1 chunk bases][grand total]
 cudaError_t launch_str_scan(const DecodeParams& p, uint64_t* bases_and_total, cudaStream_t s) {

@@ -121,7 +121,7 @@ bool chunk_is_tileable(int phys_type, int max_def, int max_rep);
 cudaError_t launch_big_pages(const DecodeParams& p, int width, int sm_count, cudaStream_t s);
 cudaError_t launch_str_sizes(const DecodeParams& p, int sm_count, cudaStream_t s);
 cudaError_t launch_str_scan(const DecodeParams& p, uint64_t* total_chars, cudaStream_t s);
-cudaError_t launch_str_copy(const DecodeParams& p, int sm_count, cudaStream_t s);
+cudaError_t launch_str_copy(const DecodeParams& p, bool any_dict, int sm_count, cudaStream_t s);
 size_t decode_smem_bytes(bool with_dict);
 
 // regex / chunk index (pqg_scan.cu)
