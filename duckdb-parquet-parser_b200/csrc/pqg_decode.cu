@@ -15,6 +15,8 @@
 //
 // Grid sizing: CTAs take contiguous spans of the page table (so a CTA stages a chunk's
 // dictionary once); the grid is a multiple of the SM count when there is enough work.
+#include <algorithm>
+
 #include "pqg_page.cuh"
 
 namespace pqg {
@@ -697,15 +699,28 @@ __device__ __forceinline__ void decode_str_page(const DecodeParams& P, uint32_t 
     }
 }
 
+// Persistent CTAs; every warp takes the next batch of pages_per_cta consecutive pages from a device
+// counter (the size pass counts in DevErr::slow_count, the copy pass in DevErr::slow_cursor; both
+// are zeroed at the start of a run): all resident warps stay busy until the pages run out, whatever
+// the spread of the per-page work (a fixed page per warp left 40 % of the warp slots idle).
 template <bool COPY, bool LEAN>
 __global__ void __launch_bounds__(kThreadsPerCta, 3) k_str_pages(DecodeParams P) {
     extern __shared__ __align__(16) uint8_t smem[];
     WarpScratch& ws = reinterpret_cast<WarpScratch*>(smem)[warp_id()];
-    uint32_t p = P.page_begin + blockIdx.x * P.pages_per_cta;
-    const uint32_t p1 = min(P.page_end, p + P.pages_per_cta);
-    for (uint32_t q = p + warp_id(); q < p1; q += kWarpsPerCta) {
-        const DevChunk& ck = P.chunks[P.pages[q].chunk_idx];
-        decode_str_page<COPY, LEAN>(P, q, ck, ws);
+    uint32_t* cursor = COPY ? &P.err->slow_cursor : &P.err->slow_count;
+    const uint32_t n = P.page_end - P.page_begin, batch = P.pages_per_cta;
+    for (;;) {
+        uint32_t i = 0;
+        if (lane_id() == 0) i = atomicAdd(cursor, batch);
+        i = __shfl_sync(0xffffffffu, i, 0);
+        if (i >= n) break;
+        const uint32_t i1 = min(n, i + batch);
+        for (; i < i1; i++) {
+            const uint32_t q = P.page_begin + i;
+            const DevChunk& ck = P.chunks[P.pages[q].chunk_idx];
+            decode_str_page<COPY, LEAN>(P, q, ck, ws);
+            __syncwarp();
+        }
     }
 }
 
@@ -757,14 +772,6 @@ __global__ void k_str_scan_chunks(DecodeParams P, uint64_t* chunk_bases, uint64_
     }
 }
 
-uint32_t grid_for(uint32_t n_pages, int sm_count, uint32_t* pages_per_cta, int ctas_per_sm) {
-    // contiguous spans; aim for ctas_per_sm * SMs CTAs, at least one page per warp and step
-    uint32_t target = static_cast<uint32_t>(sm_count) * ctas_per_sm * 4u;
-    uint32_t per = (n_pages + target - 1) / target;
-    if (per < kWarpsPerCta) per = kWarpsPerCta;
-    *pages_per_cta = per;
-    return (n_pages + per - 1) / per;
-}
 
 } // namespace
 
@@ -818,7 +825,13 @@ static cudaError_t launch_str_t(DecodeParams p, int sm_count, cudaStream_t s) {
     if (n == 0) return cudaSuccess;
     cudaError_t e = cudaFuncSetAttribute(k_str_pages<COPY, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
-    uint32_t grid = grid_for(n, sm_count, &p.pages_per_cta, 5);
+    int resident = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k_str_pages<COPY, LEAN>, kThreadsPerCta, smem);
+    if (resident < 1) resident = 1;
+    const uint32_t warps = static_cast<uint32_t>(sm_count) * static_cast<uint32_t>(resident) * kWarpsPerCta;
+    // ~16 grabs per warp: few enough atomics on the one counter, fine enough for the tail
+    p.pages_per_cta = std::min<uint32_t>(16u, std::max<uint32_t>(1u, n / (warps * 16u)));
+    const uint32_t grid = std::min<uint32_t>((n + kWarpsPerCta - 1) / kWarpsPerCta, static_cast<uint32_t>(sm_count) * static_cast<uint32_t>(resident));
     k_str_pages<COPY, LEAN><<<grid, kThreadsPerCta, smem, s>>>(p);
     return cudaGetLastError();
 }
