@@ -305,19 +305,17 @@ __device__ __forceinline__ void fast_page_opt(const DecodeParams& P, uint32_t q,
     __syncwarp();
     bool ok = true;
     uint32_t carry = 0, last_lv = 0;
+    const uint32_t sdef = smem_u32(s);
     for (uint32_t base = 0; base < nr && carry < n; base += 32) {
         const uint32_t r = base + l;
         uint32_t cnt = 0, lv = 0;
-        if (r < nr) { const uint32_t b = s[2 * r]; ok = ok && ((b & 0x81u) == 0u) && b != 0u; cnt = b >> 1; lv = s[2 * r + 1] >= 1u ? 1u : 0u; }
+        if (r < nr) { const uint32_t bl = SmemWords{sdef}.u16at(2u * r), b = bl & 0xffu; ok = ok && ((b & 0x81u) == 0u) && b != 0u; cnt = b >> 1; lv = (bl >> 8) >= 1u ? 1u : 0u; }
         const uint32_t incl = warp_incl_scan(cnt);
         const uint32_t start = carry + incl - cnt;
         uint32_t prev = __shfl_up_sync(0xffffffffu, lv, 1);
         if (l == 0) prev = last_lv;
         const bool tog = r < nr && start < n && lv != prev;
-        const uint32_t key = tog ? (start >> 5) : 0xffffu; // few distinct keys: match.any costs one round per distinct value
-        const uint32_t grp = __match_any_sync(0xffffffffu, key);
-        const uint32_t orv = __reduce_or_sync(grp, tog ? (1u << (start & 31u)) : 0u);
-        if (tog && l == static_cast<uint32_t>(__ffs(grp) - 1)) vwords[start >> 5] ^= orv;
+        if (tog) atomicXor(&vwords[start >> 5], 1u << (start & 31u));
         const uint32_t last_lane = min(31u, nr - 1u - base);
         last_lv = __shfl_sync(0xffffffffu, lv, last_lane);
         carry += __shfl_sync(0xffffffffu, incl, 31);
