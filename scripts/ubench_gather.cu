@@ -56,6 +56,55 @@ __global__ void __launch_bounds__(kThreads, 4) k_gather(const uint64_t* __restri
     if (acc == 0x1234567) out[0] = acc;
 }
 
+// pipelined split: per warp two mbarriers and two slot buffers; the bulk copies of round r + 1 are in flight
+// while the lanes do the ld.global gathers of round r.  n_tma of the kBatch values per lane go through the TMA unit.
+__global__ void __launch_bounds__(kThreads, 4) k_gather_split(const uint64_t* __restrict__ table, uint32_t mask, int rounds, int n_tma, uint64_t* out) {
+    __shared__ __align__(16) uint8_t slots[2][kThreads * kBatch * 16];
+    __shared__ __align__(8) uint64_t bars[kThreads / 32][2];
+    const uint32_t tid = threadIdx.x, l = tid & 31u, w = tid >> 5;
+    if (l == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bars[w][0])), "r"(1) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bars[w][1])), "r"(1) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    uint32_t x = (blockIdx.x * kThreads + tid) * 2654435761u + 12345u;
+    uint64_t acc = 0;
+    uint32_t ixn[kBatch], ixc[kBatch];
+    auto draw = [&](uint32_t* ix) {
+#pragma unroll
+        for (int b = 0; b < kBatch; b++) { x = x * 1664525u + 1013904223u; ix[b] = (x >> 8) & mask; }
+    };
+    auto issue = [&](const uint32_t* ix, int buf) {
+        if (l == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bars[w][buf])), "r"(32 * n_tma * 16) : "memory");
+        __syncwarp();
+        for (int b = 0; b < n_tma; b++)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 16, [%2];"
+                         ::"r"(smem_u32(slots[buf] + (tid * kBatch + b) * 16)), "l"(table + (ix[b] & ~1u)), "r"(smem_u32(&bars[w][buf])) : "memory");
+    };
+    draw(ixc);
+    issue(ixc, 0);
+    uint32_t ph0 = 0, ph1 = 0;
+    for (int r = 0; r < rounds; r++) {
+        const int buf = r & 1;
+        draw(ixn);
+        if (r + 1 < rounds) issue(ixn, buf ^ 1);
+        for (int b = n_tma; b < kBatch; b++) {
+            uint64_t v;
+            asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(v) : "l"(table + ixc[b]));
+            acc += v;
+        }
+        const uint32_t ph = buf ? ph1 : ph0;
+        asm volatile("{\n.reg .pred p;\nW: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra D;\nbra W;\nD:\n}\n" ::"r"(smem_u32(&bars[w][buf])), "r"(ph) : "memory");
+        if (buf) ph1 ^= 1; else ph0 ^= 1;
+        for (int b = 0; b < n_tma; b++) acc += *reinterpret_cast<const uint64_t*>(slots[buf] + (tid * kBatch + b) * 16 + (ixc[b] & 1u) * 8);
+        __syncwarp();
+#pragma unroll
+        for (int b = 0; b < kBatch; b++) ixc[b] = ixn[b];
+    }
+    if (acc == 0x1234567) out[0] = acc;
+}
+
 int main(int argc, char** argv) {
     const uint32_t entries = argc > 1 ? static_cast<uint32_t>(std::atoi(argv[1])) : 65536u; // power of two
     const int rounds = 2000;
@@ -79,6 +128,18 @@ int main(int argc, char** argv) {
         const double gathers = static_cast<double>(grid) * kThreads * kBatch * rounds;
         std::printf("mode %d entries %u: %.3f ms, %.1f G gathers/s, %.3f gathers/clk/SM (at %d MHz nominal)  [%s]\n", mode, entries, ms,
                     gathers / ms / 1e6, gathers / (ms * 1e-3) / (clk_khz * 1e3) / prop.multiProcessorCount, clk_khz / 1000, cudaGetErrorString(e));
+    }
+    for (int n_tma = 1; n_tma <= 2; n_tma++) {
+        cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+        k_gather_split<<<grid, kThreads>>>(d_table, entries - 1, 50, n_tma, d_out);
+        cudaEventRecord(e0);
+        k_gather_split<<<grid, kThreads>>>(d_table, entries - 1, rounds, n_tma, d_out);
+        cudaEventRecord(e1);
+        cudaError_t e = cudaDeviceSynchronize();
+        float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+        const double gathers = static_cast<double>(grid) * kThreads * kBatch * rounds;
+        std::printf("pipelined split %d of %d through the TMA unit, entries %u: %.3f ms, %.1f G gathers/s, %.3f gathers/clk/SM  [%s]\n", n_tma, kBatch, entries, ms,
+                    gathers / ms / 1e6, gathers / (ms * 1e-3) / (clk_khz * 1e3) / prop.multiProcessorCount, cudaGetErrorString(e));
     }
     return 0;
 }
