@@ -105,6 +105,24 @@ __global__ void __launch_bounds__(kThreads, 4) k_gather_split(const uint64_t* __
     if (acc == 0x1234567) out[0] = acc;
 }
 
+// texture path: tex1Dfetch<int2> over the same table; n_tex of the kBatch values per lane through the TEX pipe
+__global__ void __launch_bounds__(kThreads, 4) k_gather_tex(const uint64_t* __restrict__ table, cudaTextureObject_t tex, uint32_t mask, int rounds, int n_tex, uint64_t* out) {
+    const uint32_t tid = threadIdx.x;
+    uint32_t x = (blockIdx.x * kThreads + tid) * 2654435761u + 12345u;
+    uint64_t acc = 0;
+    for (int r = 0; r < rounds; r++) {
+        uint32_t ix[kBatch];
+#pragma unroll
+        for (int b = 0; b < kBatch; b++) { x = x * 1664525u + 1013904223u; ix[b] = (x >> 8) & mask; }
+#pragma unroll
+        for (int b = 0; b < kBatch; b++) {
+            if (b < n_tex) { const int2 v = tex1Dfetch<int2>(tex, static_cast<int>(ix[b])); acc += static_cast<uint32_t>(v.x) + (static_cast<uint64_t>(static_cast<uint32_t>(v.y)) << 32); }
+            else { uint64_t v; asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(v) : "l"(table + ix[b])); acc += v; }
+        }
+    }
+    if (acc == 0x1234567) out[0] = acc;
+}
+
 int main(int argc, char** argv) {
     const uint32_t entries = argc > 1 ? static_cast<uint32_t>(std::atoi(argv[1])) : 65536u; // power of two
     const int rounds = 2000;
@@ -128,6 +146,26 @@ int main(int argc, char** argv) {
         const double gathers = static_cast<double>(grid) * kThreads * kBatch * rounds;
         std::printf("mode %d entries %u: %.3f ms, %.1f G gathers/s, %.3f gathers/clk/SM (at %d MHz nominal)  [%s]\n", mode, entries, ms,
                     gathers / ms / 1e6, gathers / (ms * 1e-3) / (clk_khz * 1e3) / prop.multiProcessorCount, clk_khz / 1000, cudaGetErrorString(e));
+    }
+    {
+        cudaResourceDesc rd{}; rd.resType = cudaResourceTypeLinear; rd.res.linear.devPtr = d_table;
+        rd.res.linear.desc = cudaCreateChannelDesc<int2>(); rd.res.linear.sizeInBytes = static_cast<size_t>(entries) * 8;
+        cudaTextureDesc td{}; td.readMode = cudaReadModeElementType;
+        cudaTextureObject_t tex = 0;
+        cudaError_t ce = cudaCreateTextureObject(&tex, &rd, &td, nullptr);
+        for (int n_tex = 1; n_tex <= 4 && ce == cudaSuccess; n_tex++) {
+            cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+            k_gather_tex<<<grid, kThreads>>>(d_table, tex, entries - 1, 50, n_tex, d_out);
+            cudaEventRecord(e0);
+            k_gather_tex<<<grid, kThreads>>>(d_table, tex, entries - 1, rounds, n_tex, d_out);
+            cudaEventRecord(e1);
+            cudaError_t e = cudaDeviceSynchronize();
+            float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+            const double gathers = static_cast<double>(grid) * kThreads * kBatch * rounds;
+            std::printf("%d of %d through tex1Dfetch<int2>, entries %u: %.3f ms, %.1f G gathers/s, %.3f gathers/clk/SM  [%s]\n", n_tex, kBatch, entries, ms,
+                        gathers / ms / 1e6, gathers / (ms * 1e-3) / (clk_khz * 1e3) / prop.multiProcessorCount, cudaGetErrorString(e));
+        }
+        if (ce != cudaSuccess) std::printf("texture object: %s\n", cudaGetErrorString(ce));
     }
     for (int n_tma = 1; n_tma <= 2; n_tma++) {
         cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
