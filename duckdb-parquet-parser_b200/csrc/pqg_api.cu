@@ -61,6 +61,7 @@ struct pqg_plan {
     int phys = 0, width = 0;
     uint64_t n_slots = 0;
     uint32_t tile_launches = 0;              // tile-kernel launches of the current run
+    uint32_t handover_seen = 0xffffffffu;    // pages handed to the general kernel in the last finished run (~0u: none finished yet)
     mutable uint32_t max_page_values = 0xffffffffu; // most num_values of one page (computed on first use)
     uint8_t* d_values = nullptr;
     uint32_t* d_validity = nullptr;
@@ -573,7 +574,7 @@ static DecodeParams make_params(const pqg_plan* p) {
     P.chunks = p->d_chunks; P.pages = p->d_pages;
     P.page_begin = 0; P.page_end = static_cast<uint32_t>(p->pages.size());
     P.n_chunks = static_cast<uint32_t>(p->chunks.size());
-    P.dict_arena = p->d_dict; P.values = p->d_values; P.validity = p->d_validity;
+    P.dict_arena = p->d_dict; P.values = p->d_values; P.validity = p->d_validity; P.handover_hint = p->handover_seen;
     P.offsets = p->d_offsets; P.chars = p->d_chars;
     P.page_chars = p->d_page_chars; P.page_char_base = p->d_page_char_base; P.err = p->d_err;
     P.tiles = p->d_tiles; P.tile_lo = 0; P.tile_hi = p->n_tiles; P.dict_smem = p->dict_smem;
@@ -777,6 +778,7 @@ int pqg_plan_finish(pqg_ctx* ctx, pqg_plan* p, pqg_page_error* err) {
     }
     pqg_page_error pe{};
     const DevErr& d = *p->h_err;
+    p->handover_seen = d.slow_count;
     if (std::getenv("PQG_DEBUG"))
         std::fprintf(stderr, "[pqg] plan: %zu pages, %u tiles, %u host-listed slow pages, %u handed over by the tile kernel (last sub-run), bad_index %u\n",
                      p->pages.size(), p->n_tiles, p->n_slow_host, d.slow_count, d.bad_index);

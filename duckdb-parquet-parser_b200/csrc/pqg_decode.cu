@@ -798,11 +798,16 @@ static cudaError_t launch_fixed_t(DecodeParams p, int sm_count, uint32_t slow_hi
     const size_t smem = decode_smem_bytes(false);
     cudaError_t e = cudaFuncSetAttribute(k_decode_fixed<W, BOOLP>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
-    // persistent CTAs over the work-stealing list; the list length is only known on the
-    // device (the tile kernel appends to it), so size the grid for the host-known part
-    uint32_t want = (slow_hint + kWarpsPerCta - 1) / kWarpsPerCta;
-    uint32_t cap = static_cast<uint32_t>(sm_count) * 4u;
-    uint32_t grid = want < static_cast<uint32_t>(sm_count) ? static_cast<uint32_t>(sm_count) : (want > cap ? cap : want);
+    // persistent CTAs over the work-stealing list; the list length is only known on the device
+    // (the tile kernel appends to it): size the grid for the host-known part plus what the tile
+    // kernel handed over in the previous run of the plan; nothing known yet -> every resident slot
+    // (one CTA per SM left 3/4 of the warp slots of this latency-bound kernel empty)
+    const uint32_t cap = static_cast<uint32_t>(sm_count) * 3u;
+    uint32_t grid = cap;
+    if (p.handover_hint != 0xffffffffu) {
+        const uint32_t want = (slow_hint + p.handover_hint + kWarpsPerCta - 1) / kWarpsPerCta;
+        grid = want < static_cast<uint32_t>(sm_count) ? static_cast<uint32_t>(sm_count) : (want > cap ? cap : want);
+    }
     k_decode_fixed<W, BOOLP><<<grid, kThreadsPerCta, smem, s>>>(p);
     return cudaGetLastError();
 }

@@ -104,6 +104,7 @@ struct DecodeParams {
     uint32_t part_shift;     // log2 of the dictionary entries per CTA of the cluster
     uint32_t gather_mode;    // cache operator of the global dictionary gather (A/B switch)
     uint32_t tile_sync;      // 1: CTA-wide barrier per tile instead of the last-warp refill (A/B switch)
+    uint32_t handover_hint;  // pages the tile kernel handed to the general kernel in the previous run of the plan (~0u: unknown)
     uint32_t skip_dict_pad;  // 1: the run does not materialise strings (regex scan): no padded short-string table
     uint32_t tile_bytes;     // tile size the plan's tiles were cut for (kTileBytes / kTileBytesLarge)
     uint32_t identity_dict;  // dictionary-form output: emit the dictionary INDEX of every slot instead of the entry
