@@ -564,6 +564,10 @@ __device__ __forceinline__ bool page_begin(const DecodeParams& P, uint32_t q, co
         __syncwarp();
         c.pg = ws.slot + shift;
     } else {
+        // read in place: bring the first 64 KB of the page towards the SM first (every lane a line),
+        // otherwise each dependent bit-field load of the decode below waits for DRAM on its own
+        const uint32_t pre = min(c.size, 65536u);
+        for (uint32_t off = l * 128u; off < pre; off += 32u * 128u) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + off));
         c.pg = src;
     }
     uint32_t pos = 0;
