@@ -579,9 +579,17 @@ __device__ __forceinline__ void decode_str_page(const DecodeParams& P, uint32_t 
             if (c.dict) { // sum the lengths of the referenced dictionary entries
                 uint32_t sum = 0;
                 const uint32_t ulen = ck.dict_len; // every entry has this length (~0u: lengths differ)
-                for (uint32_t k = l; k < nn; k += 32) {
-                    uint32_t ix = regular ? regular_index2(rs, nn_before + k) : idx_load(ws.idx, k, c.wide);
-                    if (ix < dict_n) sum += ulen != 0xffffffffu ? ulen : dent[ix].y;
+                // one common length and no index can be out of range (2^bw <= entries; the unmasked value
+                // of a trailing RLE run checked apart): the page's bytes follow from the count alone
+                const bool all_in_range = regular && c.bw < 32u && dict_n >= (1u << c.bw) &&
+                                          (rs.tail_start >= nn_before + nn || rs.tail_val < dict_n);
+                if (ulen != 0xffffffffu && all_in_range) {
+                    if (l == 0) sum = ulen * nn;
+                } else {
+                    for (uint32_t k = l; k < nn; k += 32) {
+                        uint32_t ix = regular ? regular_index2(rs, nn_before + k) : idx_load(ws.idx, k, c.wide);
+                        if (ix < dict_n) sum += ulen != 0xffffffffu ? ulen : dent[ix].y;
+                    }
                 }
                 for (int d = 16; d; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
                 page_bytes += sum;
