@@ -334,6 +334,31 @@ def cpu_reference_run(pq, cols, rows, rg_rows, sample_rgs, steps, warmup, thread
                                         f"one reader per thread, page cache warm")
 
 
+class _DevView:
+    """a raw device pointer as a CUDA-array-interface object (torch.as_tensor wraps it without a copy)"""
+
+    def __init__(self, ptr, n, typestr="<i8"):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+def device_parity_check(plans, cols, rows, fused):
+    import torch
+    checked = 0
+    for k, col in enumerate(cols):
+        exp = torch.from_numpy(np.ascontiguousarray(col["fixed"]).view(np.int64)).cuda()
+        p = plans[0] if fused else plans[k]
+        base = p.values_ptr + (k * rows * 8 if fused else 0)
+        got = torch.as_tensor(_DevView(base, rows), device="cuda")
+        if not torch.equal(got, exp):
+            bad = int((got != exp).nonzero()[0].item())
+            raise AssertionError(f"bench parity (timed arm, device): column {k} differs first at row {bad}")
+        checked += rows
+        del exp, got
+    torch.cuda.empty_cache()
+    return {"checked_values": checked, "how": "device output of the timed plan == the generator's input columns (torch.equal on the device, "
+            "all rows, every column), before the timed steps; page errors checked after them"}
+
+
 # ── GPU arm ─────────────────────────────────────────────────────────────────────────────
 def main():
     claim_stdout()
@@ -448,6 +473,10 @@ def main():
     for p in plans:
         p.finish()
     bytes_out = sum(p.bytes_out for p in plans)
+    # parity of the TIMED arm at full size, before timing: the plan's device output against the generator's
+    # input columns (the generator is byte-identical to the reference's writer, tests/test_gen_cpu.py, so these
+    # ARE the values the reference's reader returns for this file), compared on the device, column by column
+    value_parity = device_parity_check(plans, cols, a.rows, fused)
     launches0 = ctx.launches
     sampler = ClockSampler(local)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -489,7 +518,7 @@ def main():
                 "frac": achieved / peak, "traffic": None,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)",
                 "algorithmic_bytes_per_step": k_bytes, "kernel_ms_per_step": k_ms, "launches_per_step": tile_launches,
-                "plan": "one plan over all columns" if fused else "one plan per column",
+                "plan": "one plan over all columns" if fused else "one plan per column", "parity": value_parity,
                 "kernel_share_of_step": k_ms / ms_per_step if ms_per_step else None,
                 "general_kernel_ms_per_step": sum(t["general_ms"] for t in tm), "dict_prepare_ms_per_step": sum(t["dict_ms"] for t in tm),
                 "per_column": [{"column": s[0], "ms": t["fixed_ms"], "dict_ms": t["dict_ms"], "general_ms": t["general_ms"],

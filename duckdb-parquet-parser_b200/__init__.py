@@ -22,6 +22,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libpqg.so")
 # Parquet physical types / repetition (values fixed by the format)
 BOOLEAN, INT32, INT64, INT96, FLOAT, DOUBLE, BYTE_ARRAY, FIXED_LEN_BYTE_ARRAY = range(8)
 PQG_OK, PQG_ERR_CUDA, PQG_ERR_ARG, PQG_ERR_UNSUPPORTED, PQG_ERR_PAGE, PQG_ERR_REGEX, PQG_ERR_NOMEM = range(7)
+PQG_PAGE_FLAG_DICT, PQG_PAGE_FLAG_V2 = 1, 2  # pqg_page_desc.flags; bits 8..15 = DataPageHeader.encoding
 
 
 def build(verbose=False):
@@ -169,7 +170,7 @@ def _declare(L):
     d("pqg_device_count", i32)
     d("pqg_kernel_launches", u64, vp)
     d("pqg_upload", i32, vp, vp, u64, C.POINTER(vp))
-    d("pqg_wrap_device", i32, vp, vp, u64, C.POINTER(vp))
+    d("pqg_wrap_device", i32, vp, vp, u64, u64, C.POINTER(vp))
     d("pqg_buf_alloc", i32, vp, u64, C.POINTER(vp))
     d("pqg_buf_write", i32, vp, vp, u64, vp, u64)
     d("pqg_buf_size", u64, vp)
@@ -563,9 +564,12 @@ class Context:
         self.check(lib().pqg_upload(self.h, host_ptr, size, C.byref(b)))
         return b
 
-    def wrap_device(self, dev_ptr, size):
+    def wrap_device(self, dev_ptr, size, capacity=None):
+        """capacity = bytes readable behind dev_ptr (>= size + 64; defaults to exactly that: the caller vouches for the tail)"""
+        if capacity is None:
+            capacity = size + 64
         b = C.c_void_p()
-        self.check(lib().pqg_wrap_device(self.h, dev_ptr, size, C.byref(b)))
+        self.check(lib().pqg_wrap_device(self.h, dev_ptr, size, capacity, C.byref(b)))
         return b
 
     def buf_free(self, b):

@@ -26,6 +26,7 @@ struct pqg_ctx {
 struct pqg_buf {
     uint8_t* d = nullptr;
     uint64_t size = 0;
+    uint64_t capacity = 0; // readable bytes behind d (>= size + kImagePad)
     bool owned = false;
 };
 
@@ -45,7 +46,6 @@ struct pqg_plan {
     uint32_t n_slow_host = 0;
     uint32_t dict_smem = 0;
     uint32_t max_dict_blocks = 1;
-    uint32_t cluster_size = 0, part_shift = 0; // DSMEM dictionary mode (0 = off)
     uint32_t tile_bytes = kTileBytes;
     // BYTE_ARRAY plans whose pages are all PLAIN REQUIRED: byte counts from the page headers
     // (payload - 4 * values), scans on the host, no size pass and no mid-run synchronisation;
@@ -58,6 +58,8 @@ struct pqg_plan {
     cudaEvent_t ev_idle = nullptr;           // last decode of the previous run (guards the image buffer)
     bool pipelined_in_flight = false;
     bool any_dict = false, any_def = false, is_str = false, is_bool = false;
+    bool forced_validity = false; // a REQUIRED chunk held an out-of-range dictionary index (null in the reference): validity added, plan re-run
+    bool run_pending = false;     // pqg_plan_run / run_pipelined enqueued, pqg_plan_finish not called yet
     int phys = 0, width = 0;
     uint64_t n_slots = 0;
     uint32_t tile_launches = 0;              // tile-kernel launches of the current run
@@ -188,6 +190,7 @@ int pqg_upload(pqg_ctx* ctx, const void* host_bytes, uint64_t size, pqg_buf** ou
     cudaError_t e = cudaMalloc(&b->d, size + kImagePad);
     if (e != cudaSuccess) { delete b; return cuda_fail(ctx, e, "cudaMalloc(image)"); }
     b->size = size;
+    b->capacity = size + kImagePad;
     b->owned = true;
     e = cudaMemsetAsync(b->d + size, 0, kImagePad, ctx->stream);
     if (e == cudaSuccess && size) e = cudaMemcpyAsync(b->d, host_bytes, size, cudaMemcpyHostToDevice, ctx->stream);
@@ -204,6 +207,7 @@ int pqg_buf_alloc(pqg_ctx* ctx, uint64_t size, pqg_buf** out) {
     cudaError_t e = cudaMalloc(&b->d, size + kImagePad);
     if (e != cudaSuccess) { delete b; return cuda_fail(ctx, e, "cudaMalloc(image)"); }
     b->size = size;
+    b->capacity = size + kImagePad;
     b->owned = true;
     e = cudaMemsetAsync(b->d + size, 0, kImagePad, ctx->stream);
     if (e != cudaSuccess) { cudaFree(b->d); delete b; return cuda_fail(ctx, e, "cudaMemsetAsync(image pad)"); }
@@ -221,13 +225,16 @@ int pqg_buf_write(pqg_ctx* ctx, pqg_buf* buf, uint64_t dst_off, const void* host
 
 uint64_t pqg_buf_size(const pqg_buf* buf) { return buf ? buf->size : 0; }
 
-int pqg_wrap_device(pqg_ctx* ctx, const void* dev_ptr, uint64_t size, pqg_buf** out) {
+int pqg_wrap_device(pqg_ctx* ctx, const void* dev_ptr, uint64_t size, uint64_t capacity, pqg_buf** out) {
     if (!ctx || !out || !dev_ptr) return fail(ctx, PQG_ERR_ARG, "pqg_wrap_device: bad argument");
     if (reinterpret_cast<uintptr_t>(dev_ptr) & 15u) return fail(ctx, PQG_ERR_ARG, "pqg_wrap_device: pointer must be 16-byte aligned");
+    // the kernels read 16-byte vectors / whole tiles: up to kImagePad bytes behind the image must be readable
+    if (capacity < size + kImagePad) return fail(ctx, PQG_ERR_ARG, "pqg_wrap_device: the allocation must be readable for 64 bytes past `size` (capacity >= size + 64)");
     pqg_buf* b = new (std::nothrow) pqg_buf();
     if (!b) return fail(ctx, PQG_ERR_NOMEM, "out of memory");
     b->d = const_cast<uint8_t*>(static_cast<const uint8_t*>(dev_ptr));
     b->size = size;
+    b->capacity = capacity;
     b->owned = false;
     *out = b;
     return PQG_OK;
@@ -374,6 +381,15 @@ static int plan_create_impl(pqg_ctx* ctx, const pqg_buf* image, const pqg_chunk_
         if (s.max_def > 0) p->any_def = true;
         for (uint32_t q = s.first_page; q < s.first_page + s.n_pages; q++) {
             if (pages[q].chunk_idx != c) return bail(PQG_ERR_ARG, "pqg_plan_create: pages of a chunk must be contiguous");
+            if (pages[q].flags & PQG_PAGE_FLAG_V2)
+                return bail(PQG_ERR_UNSUPPORTED, "DATA_PAGE_V2 pages are not supported (row group " + std::to_string(s.row_group) + ", column " + std::to_string(s.column) + ")");
+            const uint32_t enc = PQG_PAGE_ENCODING(pages[q].flags);
+            if (enc != 0u && enc != 2u && enc != 8u) {
+                static const char* names[] = {"PLAIN", "GROUP_VAR_INT", "PLAIN_DICTIONARY", "RLE", "BIT_PACKED", "DELTA_BINARY_PACKED",
+                                              "DELTA_LENGTH_BYTE_ARRAY", "DELTA_BYTE_ARRAY", "RLE_DICTIONARY", "BYTE_STREAM_SPLIT"};
+                return bail(PQG_ERR_UNSUPPORTED, std::string("data page encoding ") + (enc < 10u ? names[enc] : std::to_string(enc).c_str()) +
+                                                     " is not supported (row group " + std::to_string(s.row_group) + ", column " + std::to_string(s.column) + ")");
+            }
             if (pages[q].payload_off + pages[q].payload_size > image->size) return bail(PQG_ERR_ARG, "pqg_plan_create: page outside the image");
             p->bytes_in += pages[q].payload_size;
         }
@@ -452,25 +468,10 @@ static int plan_create_impl(pqg_ctx* ctx, const pqg_buf* image, const pqg_chunk_
         p->n_tiles = static_cast<uint32_t>(tiles.size());
         p->n_slow_host = static_cast<uint32_t>(slow.size());
         p->max_dict_blocks = std::max<uint32_t>(1, std::min<uint32_t>(64, (max_dict_n + 2047) / 2048));
-        // dictionaries beyond one CTA's shared memory but within a cluster's: DSMEM mode.
-        // MEASURED SLOWER on B200 (100 M random 8-byte gathers: 1.68 ms through
-        // ld.shared::cluster with 8-CTA clusters vs 0.50 ms through L1TEX/L2, profiles/README.md),
-        // so it is opt-in (PQG_CLUSTER_DICT=1) and kept for A/B measurements only.
-        if (!p->is_str && !p->any_def && (p->width == 4 || p->width == 8) && std::getenv("PQG_CLUSTER_DICT")) {
-            const uint64_t dict_bytes = static_cast<uint64_t>(max_dict_n) * p->width;
-            if (dict_bytes > static_cast<uint64_t>(kMaxSmemDictBytes) && dict_bytes <= 8ull * 64 * 1024) {
-                uint32_t cs = 2;
-                while (cs < 8 && dict_bytes > static_cast<uint64_t>(cs) * 64 * 1024) cs <<= 1;
-                uint32_t per = (max_dict_n + cs - 1) / cs, sh = 0;
-                while ((1u << sh) < per) sh++;
-                p->cluster_size = cs;
-                p->part_shift = sh;
-            }
-        }
     }
 
     std::vector<uint32_t> h_page_chars, h_page_base;
-    if (p->is_str && n_pages && !std::getenv("PQG_EXACT_SIZES")) {
+    if (p->is_str && n_pages) {
         bool all = true;
         h_page_chars.assign(n_pages + 1, 0);
         h_page_base.assign(n_pages + 1, 0);
@@ -501,7 +502,8 @@ static int plan_create_impl(pqg_ctx* ctx, const pqg_buf* image, const pqg_chunk_
     PA(p->d_pages, sizeof(pqg_page_desc) * std::max<size_t>(static_cast<size_t>(n_pages) + p->virt_pages.size(), 1));
     PA(p->d_err, sizeof(DevErr));
     if (p->any_dict) PA(p->d_dict, arena + 64);
-    PA(p->d_slow_pages, sizeof(uint32_t) * (static_cast<size_t>(n_pages) + p->virt_pages.size() + 1));
+    // host-listed pages, then room for EVERY page to be handed over on the device (the big-page kernel re-lists host-listed pages)
+    PA(p->d_slow_pages, sizeof(uint32_t) * (slow.size() + static_cast<size_t>(n_pages) + p->virt_pages.size() + 2));
     PA(p->d_tiles, sizeof(TileDesc) * std::max<size_t>(tiles.size(), 1));
     if (p->any_def) PA(p->d_validity, ((slots + 31) / 32 + 1) * 4);
     if (p->any_def && !p->is_str) {
@@ -578,12 +580,10 @@ static DecodeParams make_params(const pqg_plan* p) {
     P.offsets = p->d_offsets; P.chars = p->d_chars;
     P.page_chars = p->d_page_chars; P.page_char_base = p->d_page_char_base; P.err = p->d_err;
     P.tiles = p->d_tiles; P.tile_lo = 0; P.tile_hi = p->n_tiles; P.dict_smem = p->dict_smem;
-    P.slow_lo = 0; P.slow_hi = p->n_slow_host; P.n_slow_host = p->n_slow_host; P.slow_pages = p->d_slow_pages;
+    P.slow_lo = 0; P.slow_hi = p->n_slow_host; P.slow_pages = p->d_slow_pages; P.slow_append = p->d_slow_pages + p->n_slow_host;
     P.chunk_lo = 0;
-    P.cluster_size = p->cluster_size; P.part_shift = p->part_shift; P.tile_bytes = p->tile_bytes;
+    P.tile_bytes = p->tile_bytes;
     P.identity_dict = p->identity ? 1u : 0u;
-    { static const uint32_t gm = [] { const char* e = std::getenv("PQG_GATHER"); return e ? static_cast<uint32_t>(std::atoi(e)) : 1u; }(); P.gather_mode = gm; } // ld.global.cg measured 2-3 % ahead
-    { static const uint32_t ts = [] { const char* e = std::getenv("PQG_TILE_SYNC"); return e ? static_cast<uint32_t>(std::atoi(e)) : 0u; }(); P.tile_sync = ts; }
     return P;
 }
 
@@ -619,14 +619,7 @@ static int fixed_subrun(pqg_ctx* ctx, pqg_plan* p, uint32_t c0, uint32_t c1, boo
     if (e == cudaSuccess && any_dict) { e = launch_dict_prepare(P, c1 - c0, p->width, p->max_dict_blocks, s); launches++; }
     if (e == cudaSuccess && ev_tiles_begin) e = cudaEventRecord(ev_tiles_begin, s);
     if (e == cudaSuccess && P.tile_hi > P.tile_lo) {
-        if (p->cluster_size) { // one launch per chunk: a cluster holds one dictionary
-            for (uint32_t c = c0; c < c1 && e == cudaSuccess; c++) {
-                DecodeParams Pc = P;
-                Pc.chunk_lo = c;
-                Pc.tile_lo = p->chunk_tile_begin[c]; Pc.tile_hi = p->chunk_tile_begin[c + 1];
-                if (Pc.tile_hi > Pc.tile_lo) { e = launch_fixed_tiles_cluster(Pc, p->width, ctx->sm_count, s); launches++; p->tile_launches++; }
-            }
-        } else {
+        {
             // Dictionaries too large for shared memory are gathered from L2: keep the dictionaries of
             // the chunks that are in flight together within ~48 MB (a 1 M-entry INT64 dictionary is
             // 8 MB per chunk; with every chunk of a 320 M-row column in one launch the 126 MB L2
@@ -669,7 +662,10 @@ static int fixed_subrun(pqg_ctx* ctx, pqg_plan* p, uint32_t c0, uint32_t c1, boo
     // host-listed pages (oversized, or of chunks the tile kernel does not take) of 4/8-byte plans:
     // one CTA per page first; what that kernel cannot take joins the slow list
     bool host_list_taken = false;
-    if (e == cudaSuccess && P.slow_hi > P.slow_lo && !p->is_bool && (p->width == 4 || p->width == 8)) {
+    bool big_useful = false; // nested chunks (max_def > 1 / max_rep > 0) are always handed on: skip the launch when nothing else is listed
+    for (uint32_t c = c0; c < c1 && !big_useful; c++)
+        big_useful = p->chunk_slow_begin[c + 1] > p->chunk_slow_begin[c] && p->chunks[c].max_def <= 1 && p->chunks[c].max_rep <= 0;
+    if (e == cudaSuccess && big_useful && !p->is_bool && (p->width == 4 || p->width == 8)) {
         e = launch_big_pages(P, p->width, ctx->sm_count, s);
         launches++;
         host_list_taken = true;
@@ -744,6 +740,7 @@ int pqg_plan_run(pqg_ctx* ctx, pqg_plan* p) {
     p->last_launches = launches;
     ctx->launches += launches;
     p->ran = true;
+    p->run_pending = true;
     return PQG_OK;
 }
 
@@ -767,10 +764,12 @@ int pqg_plan_finish(pqg_ctx* ctx, pqg_plan* p, pqg_page_error* err) {
     CU(ctx, cudaSetDevice(ctx->device));
     CU(ctx, cudaMemcpyAsync(p->h_err, p->d_err, sizeof(DevErr), cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
+    const bool was_pipelined = p->pipelined_in_flight;
     if (p->pipelined_in_flight) { // the copy-out stream carries this plan's last D2H
         if (ctx->d2h) CU(ctx, cudaStreamSynchronize(ctx->d2h));
         p->pipelined_in_flight = false;
     }
+    p->run_pending = false;
     if (p->timed) elapsed_of(p, p->ev, &p->tm);
     if (p->is_str) {
         uint64_t slots = p->n_slots;
@@ -792,6 +791,30 @@ int pqg_plan_finish(pqg_ctx* ctx, pqg_plan* p, pqg_page_error* err) {
         if (d.d_page == raw_page) { pe.pos = d.d_pos; pe.need = d.d_need; pe.size = d.d_size; }
     }
     if (err) *err = pe;
+    if (!pe.count && d.bad_index && !p->d_validity) {
+        // an out-of-range dictionary index in a REQUIRED chunk: NULL in the reference whatever the repetition
+        // (column_reader.cpp:190-194).  The plan has no validity bitmap: add one and decode again.
+        if (was_pipelined)
+            return fail(ctx, PQG_ERR_PAGE, "out-of-range dictionary index in a REQUIRED column chunk (a null in the reference): "
+                                           "decode this column through pqg_plan_run, which adds a validity bitmap");
+        const uint64_t slots = p->n_slots;
+        CU(ctx, cudaMalloc(reinterpret_cast<void**>(&p->d_validity), ((slots + 31) / 32 + 1) * 4));
+        if (!p->is_str) { // every chunk is REQUIRED: all slots start valid, the general kernel clears the bad ones
+            std::vector<uint64_t> rr;
+            for (const pqg_chunk_desc& ck : p->chunks) if (ck.num_values) { rr.push_back(ck.out_row_base); rr.push_back(ck.out_row_base + ck.num_values); }
+            if (!rr.empty()) {
+                CU(ctx, cudaMalloc(reinterpret_cast<void**>(&p->d_required_ranges), rr.size() * 8));
+                CU(ctx, cudaMemcpy(p->d_required_ranges, rr.data(), rr.size() * 8, cudaMemcpyHostToDevice));
+                p->n_required_ranges = static_cast<uint32_t>(rr.size() / 2);
+            }
+            p->bytes_out += (slots + 7) / 8;
+        }
+        p->any_def = true;
+        p->forced_validity = true;
+        int rc = pqg_plan_run(ctx, p);
+        if (rc != PQG_OK) return rc;
+        return pqg_plan_finish(ctx, p, err);
+    }
     if (pe.count && pe.code == PQG_PAGE_LAYOUT && p->host_sizes && !p->force_exact) {
         // a PLAIN page carries bytes beyond its values: redo the column with the size pass
         p->force_exact = true;
@@ -873,6 +896,7 @@ int pqg_plan_run_pipelined(pqg_ctx* ctx, pqg_plan* p, pqg_buf* image, const pqg_
     p->last_launches = launches;
     ctx->launches += launches;
     p->ran = true;
+    p->run_pending = true;
     p->pipelined_in_flight = true;
     return PQG_OK;
 }
@@ -948,6 +972,7 @@ void ctx_add_launches(pqg_ctx* c, uint32_t n) { c->launches += n; }
 int ctx_fail(pqg_ctx* c, int code, const std::string& m) { return fail(c, code, m); }
 bool plan_is_str(const pqg_plan* p) { return p->is_str; }
 bool plan_ran(const pqg_plan* p) { return p->ran; }
+bool plan_run_pending(const pqg_plan* p) { return p->run_pending; }
 bool plan_any_dict(const pqg_plan* p) { return p->any_dict; }
 size_t plan_dict_arena_bytes(const pqg_plan* p) { return p->dict_bytes; }
 uint64_t plan_slots(const pqg_plan* p) { return p->n_slots; }

@@ -47,7 +47,7 @@ struct BigSmem {
 
 __device__ __forceinline__ void hand_over(const DecodeParams& P, uint32_t q) {
     uint32_t k = atomicAdd(&P.err->slow_count, 1u);
-    P.slow_pages[P.n_slow_host + k] = q;
+    P.slow_append[k] = q;
 }
 
 // stage `take` bytes of a stream slice into S.chunk keeping the source's 16-byte phase; returns the phase

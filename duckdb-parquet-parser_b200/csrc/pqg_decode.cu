@@ -314,7 +314,10 @@ __device__ __forceinline__ void decode_fixed_page(const DecodeParams& P, uint32_
                 if (dict_page) {
                     uint32_t ix = regular ? regular_index2(rs, nn_before + k) : idx_load(ws.idx, k, c.wide);
                     if (ix < dict_n) v = dict_value<T>(P, dictp, ix);
-                    else valid = false; // out-of-range index -> null (column_reader.cpp:190-194)
+                    else { // out-of-range index -> null (column_reader.cpp:190-194)
+                        valid = false;
+                        if (!P.validity) atomicAdd(&P.err->bad_index, 1u); // REQUIRED-only plan: pqg_plan_finish adds a validity bitmap and re-runs
+                    }
                 } else if (BOOLP) {
                     uint32_t kk = nn_before + k;
                     if constexpr (W == 1) v = (vals[kk >> 3] >> (kk & 7u)) & 1u;
@@ -324,9 +327,10 @@ __device__ __forceinline__ void decode_fixed_page(const DecodeParams& P, uint32_
             }
             if (in) out[g + l] = v;
             if (P.validity) {
-                uint32_t m = __ballot_sync(0xffffffffu, valid);
+                const uint32_t m = __ballot_sync(0xffffffffu, valid), inm = __ballot_sync(0xffffffffu, in);
                 if (l == 0) {
                     if (g >= abs0 && g + 32 <= gend) P.validity[g >> 5] = m;
+                    else if (ck.max_def <= 0) { if (inm & ~m) atomicAnd(&P.validity[g >> 5], ~(inm & ~m)); } // REQUIRED chunks start all-valid (k_validity_ranges)
                     else if (m) atomicOr(&P.validity[g >> 5], m);
                 }
             }
@@ -350,7 +354,7 @@ __global__ void __launch_bounds__(kThreadsPerCta) k_decode_fixed(DecodeParams P)
         if (lane_id() == 0) i = atomicAdd(&P.err->slow_cursor, 1u);
         i = __shfl_sync(0xffffffffu, i, 0);
         if (i >= total) break;
-        const uint32_t q = i < n_host ? P.slow_pages[P.slow_lo + i] : P.slow_pages[P.n_slow_host + (i - n_host)];
+        const uint32_t q = i < n_host ? P.slow_pages[P.slow_lo + i] : P.slow_append[i - n_host];
         const DevChunk& ck = P.chunks[P.pages[q].chunk_idx];
         decode_fixed_page<W, BOOLP>(P, q, ck, P.dict_arena + ck.dict_arena_off, ws);
         __syncwarp();
@@ -457,7 +461,11 @@ __device__ __forceinline__ uint32_t copy_short_dict_tile(const DecodeParams& P, 
         const uint32_t b0 = __ballot_sync(0xffffffffu, bad0), b1 = __ballot_sync(0xffffffffu, bad1);
         if (b0 | b1) {
             __syncwarp();
-            if (l == 0) { if (b0) ws.valid[g >> 5] &= ~b0; if (b1) ws.valid[(g >> 5) + 1u] &= ~b1; }
+            if (l == 0) {
+                if (b0) ws.valid[g >> 5] &= ~b0;
+                if (b1) ws.valid[(g >> 5) + 1u] &= ~b1;
+                if (!P.validity) atomicAdd(&P.err->bad_index, __popc(b0) + __popc(b1)); // REQUIRED column: finish re-runs with a validity bitmap
+            }
         }
         const uint32_t total = tot0 + tot1;
         if (total) {
@@ -625,7 +633,7 @@ __device__ __forceinline__ void decode_str_page(const DecodeParams& P, uint32_t 
             if (valid) {
                 if (c.dict) {
                     uint32_t ix = regular ? regular_index2(rs, nn_before + k) : idx_load(ws.idx, k, c.wide);
-                    if (ix >= dict_n) valid = false;
+                    if (ix >= dict_n) { valid = false; if (!P.validity) atomicAdd(&P.err->bad_index, 1u); } // null in the reference
                     else if (dshort) { pv = ldg_nc16(reinterpret_cast<const uint8_t*>(dpad + ix)); len = pv.w >> 24; }
                     else { uint2 e = dent[ix]; sp = dchars + e.x; len = e.y; }
                 } else {

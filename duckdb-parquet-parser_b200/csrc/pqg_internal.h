@@ -97,13 +97,10 @@ struct DecodeParams {
     uint32_t tiles_per_cta;
     uint32_t dict_smem;      // bytes of shared memory reserved for a staged dictionary
     uint32_t slow_lo, slow_hi; // host-listed slow pages of this launch: slow_pages[slow_lo, slow_hi)
-    uint32_t n_slow_host;    // device-appended slow pages start at slow_pages[n_slow_host]
-    uint32_t* slow_pages;    // capacity: every page of the plan
+    uint32_t* slow_pages;    // host-listed slow pages (n_slow_host entries)
+    uint32_t* slow_append;   // pages handed over on the device: slow_append[0 .. err->slow_count); capacity: every page of the plan
     uint32_t chunk_lo;       // first chunk of this launch (dictionary preparation)
-    uint32_t cluster_size;   // > 0: large dictionaries are spread over a cluster's shared memories
-    uint32_t part_shift;     // log2 of the dictionary entries per CTA of the cluster
-    uint32_t gather_mode;    // cache operator of the global dictionary gather (A/B switch)
-    uint32_t tile_sync;      // 1: CTA-wide barrier per tile instead of the last-warp refill (A/B switch)
+    uint32_t tile_sync;      // 1: CTA-wide barrier per tile instead of the last-warp refill (the regex scan: issue bound)
     uint32_t handover_hint;  // pages the tile kernel handed to the general kernel in the previous run of the plan (~0u: unknown)
     uint32_t skip_dict_pad;  // 1: the run does not materialise strings (regex scan): no padded short-string table
     uint32_t tile_bytes;     // tile size the plan's tiles were cut for (kTileBytes / kTileBytesLarge)
@@ -116,7 +113,6 @@ cudaError_t launch_dict_prepare(const DecodeParams& p, uint32_t n_chunks, int wi
 cudaError_t launch_decode_fixed(const DecodeParams& p, int width, bool boolean_plain, int sm_count, cudaStream_t s);
 // fast path (pqg_tiles.cu): PLAIN / regular-dictionary pages of REQUIRED 4- and 8-byte chunks
 cudaError_t launch_fixed_tiles(const DecodeParams& p, int width, int sm_count, cudaStream_t s);
-cudaError_t launch_fixed_tiles_cluster(const DecodeParams& p, int width, int sm_count, cudaStream_t s); // one chunk per launch
 bool chunk_is_tileable(int phys_type, int max_def, int max_rep);
 // oversized pages of 4/8-byte plans: one CTA per page (pqg_bigpage.cu); what it cannot take goes to the slow list
 cudaError_t launch_big_pages(const DecodeParams& p, int width, int sm_count, cudaStream_t s);

@@ -40,6 +40,7 @@ void ctx_add_launches(pqg_ctx* c, uint32_t n);
 int ctx_fail(pqg_ctx* c, int code, const std::string& m);
 bool plan_is_str(const pqg_plan* p);
 bool plan_ran(const pqg_plan* p);
+bool plan_run_pending(const pqg_plan* p);
 bool plan_any_dict(const pqg_plan* p);
 uint64_t plan_slots(const pqg_plan* p);
 const std::vector<pqg_chunk_desc>& plan_chunks(const pqg_plan* p);
@@ -234,7 +235,7 @@ __global__ void __launch_bounds__(kThreadsPerCta) k_regex_pages(RegexParams R) {
         if (lane_id() == 0) i = atomicAdd(&P.err->slow_cursor, 1u);
         i = __shfl_sync(0xffffffffu, i, 0);
         if (i >= total) break;
-        const uint32_t q = i < n_host ? P.slow_pages[P.slow_lo + i] : P.slow_pages[P.n_slow_host + (i - n_host)];
+        const uint32_t q = i < n_host ? P.slow_pages[P.slow_lo + i] : P.slow_append[i - n_host];
         const DevChunk& ck = P.chunks[P.pages[q].chunk_idx];
         bool hit = regex_page(R, trans, cls, accept, q, ck, ws);
         if (hit && lane_id() == 0) atomicOr(&R.page_bits[q >> 5], 1u << (q & 31u));
@@ -249,7 +250,7 @@ __global__ void __launch_bounds__(kThreadsPerCta) k_regex_pages(RegexParams R) {
 // the slow list.
 __device__ __forceinline__ void rx_to_slow(const DecodeParams& P, uint32_t q) {
     uint32_t k = atomicAdd(&P.err->slow_count, 1u);
-    P.slow_pages[P.n_slow_host + k] = q;
+    P.slow_append[k] = q;
 }
 
 constexpr uint32_t kRxCand = 1024; // most length-prefix candidates per page the tile scan keeps (u16 positions); 512 when no page needs more
@@ -582,6 +583,12 @@ struct DevMem { // stream-ordered scratch (the device's memory pool keeps freed 
     }
 };
 
+struct EventPair { // RAII: the timing events of one call
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaError_t create() { cudaError_t e = cudaEventCreate(&e0); return e != cudaSuccess ? e : cudaEventCreate(&e1); }
+    ~EventPair() { if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); }
+};
+
 struct ChainOut {
     uint64_t n_cuts = 0, total = 0, last_cut_P = 0;
     uint64_t* d_P = nullptr;     // n + 1
@@ -696,6 +703,8 @@ extern "C" {
 int pqg_regex_scan(pqg_ctx* ctx, pqg_plan* plan, const pqg_dfa* dfa, int neg, uint32_t* page_bits, float* kernel_ms) {
     if (!ctx || !plan || !dfa || !page_bits) return ctx_fail(ctx, PQG_ERR_ARG, "pqg_regex_scan: bad argument");
     if (!plan_is_str(plan)) return ctx_fail(ctx, PQG_ERR_ARG, "pqg_regex_scan: the plan must describe a BYTE_ARRAY column");
+    // the scan prepares the chunks' dictionaries in its own way (no padded table): not between a run and its finish
+    if (plan_run_pending(plan)) return ctx_fail(ctx, PQG_ERR_ARG, "pqg_regex_scan: the plan has an unfinished decode (call pqg_plan_finish first)");
     CUF(ctx, cudaSetDevice(ctx_device(ctx)));
     cudaStream_t s = ctx_stream(ctx);
     const CompiledDfa& d = dfa_tables(dfa);
@@ -721,6 +730,11 @@ int pqg_regex_scan(pqg_ctx* ctx, pqg_plan* plan, const pqg_dfa* dfa, int neg, ui
     std::memcpy(blob.data() + table_bytes + 256, d.accept.data(), d.n_states);
     DevMem mem(s);
     uint8_t* d_blob = nullptr; uint8_t* d_dmatch = nullptr; uint32_t* d_bits = nullptr;
+    // the scan's own error record / work counters and hand-over list: the plan's decode state stays untouched
+    DevErr* d_err = nullptr; uint32_t* d_append = nullptr;
+    CUF(ctx, mem.alloc(&d_err, 1));
+    CUF(ctx, mem.alloc(&d_append, static_cast<size_t>(n_pages) + 1));
+    P.err = d_err; P.slow_append = d_append;
     CUF(ctx, mem.alloc(&d_blob, blob.size() + 16));
     CUF(ctx, mem.alloc(&d_dmatch, plan_dict_arena_bytes(plan) / 8 + 16));
     CUF(ctx, mem.alloc(&d_bits, words + 1));
@@ -732,7 +746,7 @@ int pqg_regex_scan(pqg_ctx* ctx, pqg_plan* plan, const pqg_dfa* dfa, int neg, ui
     R.P = P;
     // ~660 warp instructions per page: the scan is issue bound, and warps spinning on the next
     // stage's mbarrier cost more than idling at a barrier (measured 0.618 vs 0.650 ms per 20 M strings)
-    if (!std::getenv("PQG_TILE_SYNC")) R.P.tile_sync = 1;
+    R.P.tile_sync = 1;
     R.D.trans = reinterpret_cast<const uint16_t*>(d_blob);
     R.D.cls = d_blob + table_bytes;
     R.D.accept = d_blob + table_bytes + 256;
@@ -742,9 +756,9 @@ int pqg_regex_scan(pqg_ctx* ctx, pqg_plan* plan, const pqg_dfa* dfa, int neg, ui
     R.D.in_smem = tab_smem <= 48 * 1024;
     R.D.scaled = wide && R.D.in_smem;
     R.dict_match = d_dmatch; R.page_bits = d_bits; R.neg = neg ? 1 : 0;
-    cudaEvent_t e0, e1;
-    CUF(ctx, cudaEventCreate(&e0));
-    CUF(ctx, cudaEventCreate(&e1));
+    EventPair ev;
+    CUF(ctx, ev.create());
+    const cudaEvent_t e0 = ev.e0, e1 = ev.e1;
     uint32_t launches = 0;
     CUF(ctx, cudaEventRecord(e0, s));
     if (plan_any_dict(plan)) {
@@ -778,7 +792,6 @@ int pqg_regex_scan(pqg_ctx* ctx, pqg_plan* plan, const pqg_dfa* dfa, int neg, ui
     CUF(ctx, cudaStreamSynchronize(s));
     float ms = 0;
     cudaEventElapsedTime(&ms, e0, e1);
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
     if (kernel_ms) *kernel_ms = ms;
     ctx_add_launches(ctx, launches);
     if (std::getenv("PQG_DEBUG")) std::fprintf(stderr, "[pqg] regex scan: %u pages, %u through the general kernel, %.3f ms\n", n_pages, herr.slow_count, ms);

@@ -60,63 +60,39 @@ template <> __device__ __forceinline__ void st_stream<uint64_t>(uint64_t* p, uin
 __device__ __forceinline__ void to_slow(const DecodeParams& P, uint32_t q) {
     // one lane
     uint32_t k = atomicAdd(&P.err->slow_count, 1u);
-    P.slow_pages[P.n_slow_host + k] = q;
+    P.slow_append[k] = q;
 }
 
-// A dictionary spread over the shared memories of a thread-block cluster: entry ix lives in
-// CTA (ix >> shift) at byte (ix & mask) * W of that CTA's part.
-struct ClusterDict { uint32_t base, shift, mask; };
-
-template <typename T> __device__ __forceinline__ T dsmem_ld(uint32_t local_addr, uint32_t rank);
-template <> __device__ __forceinline__ uint64_t dsmem_ld<uint64_t>(uint32_t local_addr, uint32_t rank) {
-    uint32_t ra; uint64_t v;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_addr), "r"(rank));
-    asm volatile("ld.shared::cluster.u64 %0, [%1];" : "=l"(v) : "r"(ra));
-    return v;
-}
-template <> __device__ __forceinline__ uint32_t dsmem_ld<uint32_t>(uint32_t local_addr, uint32_t rank) {
-    uint32_t ra, v;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_addr), "r"(rank));
-    asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(ra));
-    return v;
-}
-
-// random dictionary gather from global memory; the cache operator is selectable for A/B runs
-// (PQG_GATHER=0 ld.global.nc, 1 ld.global.cg = L2 only, 2 ld.global.nc.L1::no_allocate)
-template <typename T> __device__ __forceinline__ T ldg_gather(const T* p, uint32_t mode);
-template <> __device__ __forceinline__ uint64_t ldg_gather<uint64_t>(const uint64_t* p, uint32_t mode) {
+// random dictionary gather from global memory: L2 only (ld.global.cg; measured 2-3 % ahead of
+// ld.global.nc and ld.global.nc.L1::no_allocate, scripts/ubench_gather.cu)
+template <typename T> __device__ __forceinline__ T ldg_gather(const T* p);
+template <> __device__ __forceinline__ uint64_t ldg_gather<uint64_t>(const uint64_t* p) {
     uint64_t v;
-    if (mode == 1) asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(v) : "l"(p));
-    else if (mode == 2) asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(p));
-    else v = __ldg(reinterpret_cast<const unsigned long long*>(p));
+    asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(v) : "l"(p));
     return v;
 }
-template <> __device__ __forceinline__ uint32_t ldg_gather<uint32_t>(const uint32_t* p, uint32_t mode) {
+template <> __device__ __forceinline__ uint32_t ldg_gather<uint32_t>(const uint32_t* p) {
     uint32_t v;
-    if (mode == 1) asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p));
-    else if (mode == 2) asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
-    else v = __ldg(p);
+    asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p));
     return v;
 }
 
 // How a dictionary index turns into a value -- resolved ONCE per page and compiled into the
 // inner loops (a run-time choice per value cost ~18 instructions and divergent branches):
-enum { kDictIdent = 0, kDictSmem = 1, kDictGlobal = 2, kDictCluster = 3 };
+enum { kDictIdent = 0, kDictSmem = 1, kDictGlobal = 2 };
 template <int M> struct ModeTag { static constexpr int value = M; };
-struct DictRef { const void* gptr; uint32_t saddr; ClusterDict cd; };
+struct DictRef { const void* gptr; uint32_t saddr; };
 template <typename T, int W, int MODE>
 __device__ __forceinline__ T dict_get(const DictRef& d, uint32_t ix) {
     if constexpr (MODE == kDictIdent) return static_cast<T>(ix);
     else if constexpr (MODE == kDictSmem) return lds_elem<T>(d.saddr + ix * W);
-    else if constexpr (MODE == kDictCluster) return dsmem_ld<T>(d.cd.base + (ix & d.cd.mask) * W, ix >> d.cd.shift);
-    else return ldg_gather<T>(static_cast<const T*>(d.gptr) + ix, 1u); // ld.global.cg
+    else return ldg_gather<T>(static_cast<const T*>(d.gptr) + ix);
 }
 template <class F>
 __device__ __forceinline__ void with_dict_mode(int mode, F&& f) {
     switch (mode) {
         case kDictIdent: f(ModeTag<kDictIdent>{}); break;
         case kDictSmem: f(ModeTag<kDictSmem>{}); break;
-        case kDictCluster: f(ModeTag<kDictCluster>{}); break;
         default: f(ModeTag<kDictGlobal>{}); break;
     }
 }
@@ -178,10 +154,9 @@ __device__ __noinline__ bool hybrid_runs_page(const DecodeParams& P, const uint8
 }
 
 // One warp decodes one page out of the staged tile.  `pg` = first payload byte (shared).
-template <int W, bool CLUSTER = false>
+template <int W>
 __device__ __forceinline__ bool fast_page(const DecodeParams& P, uint32_t q, const pqg_page_desc& pd, const uint8_t* pg,
-                                          bool chunk_has_dict, const uint8_t* dictp, uint32_t dict_n, bool dict_in_smem,
-                                          ClusterDict cd = ClusterDict{0, 0, 0}) {
+                                          bool chunk_has_dict, const uint8_t* dictp, uint32_t dict_n, bool dict_in_smem) {
     using T = typename FElem<W>::T;
     const uint32_t l = lane_id();
     const uint32_t n = pd.num_values, size = pd.payload_size;
@@ -208,8 +183,8 @@ __device__ __forceinline__ bool fast_page(const DecodeParams& P, uint32_t q, con
     const uint8_t* s = pg + 1;
     RegStream rs;
     if (bw > 32) { if (l == 0) to_slow(P, q); return false; }
-    const DictRef dref{dictp, dict_in_smem ? smem_u32(dictp) : 0u, cd};
-    const int mode = CLUSTER ? kDictCluster : (P.identity_dict ? kDictIdent : (dict_in_smem ? kDictSmem : kDictGlobal));
+    const DictRef dref{dictp, dict_in_smem ? smem_u32(dictp) : 0u};
+    const int mode = P.identity_dict ? kDictIdent : (dict_in_smem ? kDictSmem : kDictGlobal);
     if (!check_regular2(s, size - 1, bw, n, &rs)) {
         // any other well-formed hybrid stream (RLE runs between the groups, literal runs of several
         // groups as foreign writers emit them): runs in sequence, the warp expands each one together
@@ -364,7 +339,7 @@ __device__ __forceinline__ void fast_page_opt(const DecodeParams& P, uint32_t q,
     const uint32_t bit0 = (va & 3u) * 8u;
     const uint32_t gs = 1u + bw, imask = bw >= 32u ? 0xffffffffu : ((1u << bw) - 1u);
     const uint32_t kmax = nn ? nn - 1u : 0u;
-    const DictRef dref{dictp, dict_in_smem ? smem_u32(dictp) : 0u, ClusterDict{0, 0, 0}};
+    const DictRef dref{dictp, dict_in_smem ? smem_u32(dictp) : 0u};
     const int mode = !dict_page ? -1 : (P.identity_dict ? kDictIdent : (dict_in_smem ? kDictSmem : kDictGlobal));
     auto emit = [&](auto tag) {
         constexpr int MODE = decltype(tag)::value; // -1: PLAIN
@@ -462,50 +437,6 @@ __global__ void __launch_bounds__(kThreadsPerCta, OPT ? 3 : 4) k_fixed_tiles(con
         });
 }
 
-__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-
-// Same pipeline, for ONE chunk whose dictionary is too large for one CTA's shared memory but
-// fits the cluster's: every CTA of the cluster keeps 1/CS of the dictionary (bulk copy) and
-// gathers through distributed shared memory (mapa + ld.shared::cluster) instead of L1TEX/L2 --
-// a random 8-byte global gather costs one L1TEX wavefront and one 32-byte L2 sector per value
-// and tops out near 2 TB/s of decoded output; DSMEM serves it next to the SMs.
-template <int W>
-__global__ void __launch_bounds__(kThreadsPerCta, 2) k_fixed_tiles_cluster(const DecodeParams P) {
-    extern __shared__ __align__(128) uint8_t smem[];
-    uint64_t* dbar = reinterpret_cast<uint64_t*>(smem + kTilePipeBytes);
-    uint8_t* sdict = smem + kTilePipeBytes + 16;
-    const uint32_t rank = cluster_ctarank();
-    const DevChunk& ck = P.chunks[P.chunk_lo];
-    const bool has_dict = ck.has_dict;
-    const uint32_t dict_n = ck.dict_ok_n;
-    const uint32_t part = 1u << P.part_shift;
-    const uint32_t first = rank * part;
-    const uint32_t cnt = (has_dict && first < dict_n) ? min(part, dict_n - first) : 0u;
-    const uint32_t dbytes = (cnt * W + 15u) & ~15u;
-    if (threadIdx.x == 0) {
-        mbar_init(dbar, 1);
-        fence_mbar_init();
-        if (dbytes) {
-            mbar_expect_tx(dbar, dbytes);
-            bulk_g2s(sdict, P.dict_arena + ck.dict_arena_off + static_cast<size_t>(first) * W, dbytes, dbar);
-        }
-    }
-    __syncthreads();
-    if (dbytes) mbar_wait(dbar, 0);
-    cluster_sync_all(); // every part of the dictionary is in place
-    const ClusterDict cd{smem_u32(sdict), P.part_shift, part - 1u};
-    tile_pipeline(P, smem,
-        [&](uint32_t, uint64_t*, uint32_t&) {},
-        [&](uint32_t q, const pqg_page_desc& pd, const uint8_t* pg) {
-            fast_page<W, true>(P, q, pd, pg, has_dict, nullptr, dict_n, false, cd);
-        });
-    cluster_sync_all(); // nobody may leave while a peer can still read its part
-}
-
 } // namespace
 
 bool chunk_is_tileable(int phys_type, int max_def, int max_rep) {
@@ -525,42 +456,6 @@ static cudaError_t launch_tiles_t(DecodeParams p, int sm_count, cudaStream_t s) 
     const uint32_t grid = tile_grid(p.tile_hi - p.tile_lo, sm_count, resident, &p.tiles_per_cta);
     k_fixed_tiles<W, TB, OPT><<<grid, kThreadsPerCta, smem, s>>>(p);
     return cudaGetLastError();
-}
-
-template <int W>
-static cudaError_t launch_cluster_t(DecodeParams p, int sm_count, cudaStream_t s) {
-    const uint32_t cs = p.cluster_size;
-    const size_t smem = static_cast<size_t>(kTilePipeBytes) + 16 + (static_cast<size_t>(W) << p.part_shift);
-    cudaError_t e = cudaFuncSetAttribute(k_fixed_tiles_cluster<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    if (e != cudaSuccess) return e;
-    const uint32_t n_tiles = p.tile_hi - p.tile_lo;
-    // resident CTAs: 2 per SM by shared memory at most; one wave of clusters, spans of >= 4 tiles
-    uint32_t ctas = static_cast<uint32_t>(sm_count) * (smem <= 100 * 1024 ? 2u : 1u);
-    ctas = (ctas / cs) * cs;
-    uint32_t per = (n_tiles + ctas - 1) / ctas;
-    if (per < 4) per = 4;
-    uint32_t grid = (n_tiles + per - 1) / per;
-    grid = ((grid + cs - 1) / cs) * cs;
-    p.tiles_per_cta = per;
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(kThreadsPerCta);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, k_fixed_tiles_cluster<W>, p);
-}
-
-// one launch per chunk: the cluster holds exactly one dictionary
-cudaError_t launch_fixed_tiles_cluster(const DecodeParams& p, int width, int sm_count, cudaStream_t s) {
-    if (p.tile_hi <= p.tile_lo) return cudaSuccess;
-    if (width == 4) return launch_cluster_t<4>(p, sm_count, s);
-    if (width == 8) return launch_cluster_t<8>(p, sm_count, s);
-    return cudaErrorInvalidValue;
 }
 
 cudaError_t launch_fixed_tiles(const DecodeParams& p, int width, int sm_count, cudaStream_t s) {

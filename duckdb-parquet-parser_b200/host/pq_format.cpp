@@ -82,7 +82,10 @@ public:
     void list(uint8_t& elem_type, int32_t& count) {
         uint8_t b = byte();
         elem_type = b & 0x0F;
-        count = (b >> 4) == 0x0F ? static_cast<int32_t>(varint()) : (b >> 4);
+        const uint64_t n = (b >> 4) == 0x0F ? varint() : (b >> 4);
+        // every element takes at least one byte on the wire: a larger count is a corrupt header
+        if (n > static_cast<uint64_t>(end_ - p_)) throw FormatError("thrift list longer than its buffer");
+        count = static_cast<int32_t>(n);
     }
     void skip(uint8_t type, int depth = 0) {
         if (depth > 64) throw FormatError("thrift nesting too deep");
@@ -95,14 +98,17 @@ public:
             case T_LIST: case T_SET: {
                 uint8_t et; int32_t n;
                 list(et, n);
-                for (int32_t i = 0; i < n; i++) skip(et, depth + 1);
+                if (et == T_TRUE || et == T_FALSE) skip_bytes(static_cast<size_t>(n)); // bool elements are one byte each inside a list
+                else for (int32_t i = 0; i < n; i++) skip(et, depth + 1);
                 break;
             }
             case T_MAP: {
-                int32_t n = static_cast<int32_t>(varint());
+                const uint64_t n = varint();
+                if (n > static_cast<uint64_t>(end_ - p_)) throw FormatError("thrift map longer than its buffer");
                 if (n > 0) {
                     uint8_t kv = byte();
-                    for (int32_t i = 0; i < n; i++) { skip(kv >> 4, depth + 1); skip(kv & 0x0F, depth + 1); }
+                    auto elem = [&](uint8_t t) { if (t == T_TRUE || t == T_FALSE) skip_bytes(1); else skip(t, depth + 1); };
+                    for (uint64_t i = 0; i < n; i++) { elem(kv >> 4); elem(kv & 0x0F); }
                 }
                 break;
             }
@@ -268,7 +274,20 @@ size_t parse_page_header(const uint8_t* data, size_t avail, PageHeader& ph) {
                 ph.dictionary_page_header = d;
                 break;
             }
-            case 8: ph.is_v2 = true; c.skip(t); break;
+            case 8: { // DataPageHeaderV2 {1 num_values, 2 num_nulls, 3 num_rows, 4 encoding, ...}: never decoded, only stepped over
+                ph.is_v2 = true;
+                DataPageHeader d;
+                int16_t l2 = 0, id2; uint8_t t2;
+                while (c.field(l2, id2, t2)) {
+                    switch (id2) {
+                        case 1: d.num_values = c.i32(); break;
+                        case 4: d.encoding = static_cast<Encoding>(c.i32()); break;
+                        default: c.skip(t2);
+                    }
+                }
+                ph.v2_header = d;
+                break;
+            }
             default: c.skip(t);
         }
     }
@@ -359,7 +378,16 @@ void walk_chunk_pages(const uint8_t* image, uint64_t image_file_off, uint64_t im
                 throw FormatError("bad_optional_access: data page without its header");
             }
         } else if (ph.type == PageType::DATA_PAGE_V2) {
-            r.counted = true; // gets a global id in the reference's page index, never decoded
+            // gets a global id in the reference's page index and is never decoded there (column_reader.cpp:66-67: the
+            // reference's loop does not even advance past it).  Here the page's values are counted so that the walk ends,
+            // and every decode of the chunk is refused with an explicit error (pqg_plan_create: PQG_PAGE_FLAG_V2).
+            r.counted = true;
+            if (ph.v2_header) {
+                r.num_values = ph.v2_header->num_values;
+                r.encoding = ph.v2_header->encoding;
+                if (r.num_values < 0) throw FormatError("negative num_values");
+                values_read += r.num_values;
+            }
         }
         pages.push_back(r);
         cur = r.payload_off + r.payload_size;
@@ -402,14 +430,28 @@ void append_chunk_tables(ColumnTables& t, const std::vector<PageRecord>& pages, 
             p.payload_size = r.payload_size;
             p.num_values = static_cast<uint32_t>(r.num_values);
             p.chunk_idx = static_cast<uint32_t>(t.chunks.size() - 1);
-            p.flags = (r.encoding == Encoding::PLAIN_DICTIONARY || r.encoding == Encoding::RLE_DICTIONARY) ? PQG_PAGE_FLAG_DICT : 0;
+            p.flags = PQG_PAGE_FLAGS(r.encoding == Encoding::PLAIN_DICTIONARY || r.encoding == Encoding::RLE_DICTIONARY, static_cast<int32_t>(r.encoding));
             t.pages.push_back(p);
             t.page_row_group.push_back(rg);
             c.n_pages++;
             c.num_values += p.num_values;
             t.total_slots += p.num_values;
         }
-        // INDEX_PAGE / DATA_PAGE_V2 / unknown: skipped like the reference (column_reader.cpp:66-67)
+        else if (r.type == PageType::DATA_PAGE_V2) {
+            // listed so that pqg_plan_create refuses the chunk (PQG_ERR_UNSUPPORTED); it contributes no slots
+            if (!opened) { open_chunk(nullptr); opened = true; }
+            pqg_page_desc p;
+            std::memset(&p, 0, sizeof(p));
+            p.payload_off = r.payload_off - image_file_off;
+            p.out_row_base = t.total_slots;
+            p.payload_size = r.payload_size;
+            p.chunk_idx = static_cast<uint32_t>(t.chunks.size() - 1);
+            p.flags = PQG_PAGE_FLAG_V2 | PQG_PAGE_FLAGS(false, static_cast<int32_t>(r.encoding));
+            t.pages.push_back(p);
+            t.page_row_group.push_back(rg);
+            t.chunks.back().n_pages++;
+        }
+        // INDEX_PAGE / unknown: skipped like the reference (column_reader.cpp:66-67)
     }
     if (opened && t.chunks.back().n_pages == 0) t.chunks.pop_back();
 }

@@ -104,6 +104,7 @@ struct PageHeader {
     std::optional<DataPageHeader> data_page_header;
     std::optional<DictionaryPageHeader> dictionary_page_header;
     bool is_v2 = false;
+    std::optional<DataPageHeader> v2_header; // DATA_PAGE_V2: num_values + encoding only (stepped over, never decoded)
 };
 
 // Leaf column description (reference include/reader/column_info.hpp).

@@ -86,6 +86,14 @@ typedef struct pqg_chunk_desc {
 } pqg_chunk_desc;
 
 #define PQG_PAGE_FLAG_DICT 1u /* DataPageHeader.encoding is PLAIN_DICTIONARY / RLE_DICTIONARY */
+#define PQG_PAGE_FLAG_V2 2u   /* the page is a DATA_PAGE_V2: pqg_plan_create rejects the plan (PQG_ERR_UNSUPPORTED) */
+/* bits 8..15 of pqg_page_desc.flags: the Encoding enum value of DataPageHeader.encoding (0 PLAIN,
+ * 2 PLAIN_DICTIONARY, 8 RLE_DICTIONARY are decoded; DELTA_BINARY_PACKED 5, DELTA_LENGTH_BYTE_ARRAY 6,
+ * DELTA_BYTE_ARRAY 7, BYTE_STREAM_SPLIT 9 and anything else make pqg_plan_create fail with
+ * PQG_ERR_UNSUPPORTED -- the reference decodes such pages as PLAIN and returns garbage,
+ * src/reader/column_reader.cpp:173-222) */
+#define PQG_PAGE_ENCODING(flags) (((flags) >> 8) & 0xffu)
+#define PQG_PAGE_FLAGS(dict, encoding) (((dict) ? PQG_PAGE_FLAG_DICT : 0u) | (((uint32_t)(encoding) & 0xffu) << 8))
 
 /* One DATA_PAGE.  Replaces PageHeader + the per-page cursor of read_all
  * (src/reader/column_reader.cpp:32-64) and PageIndexEntry
@@ -96,7 +104,7 @@ typedef struct pqg_page_desc {
     uint32_t payload_size; /* compressed_page_size */
     uint32_t num_values;   /* DataPageHeader.num_values */
     uint32_t chunk_idx;    /* index into the chunk table */
-    uint32_t flags;        /* PQG_PAGE_FLAG_* */
+    uint32_t flags;        /* PQG_PAGE_FLAG_* | encoding << 8 */
 } pqg_page_desc;
 
 typedef struct pqg_page_error {
@@ -136,7 +144,10 @@ PQG_API uint64_t pqg_kernel_launches(const pqg_ctx* ctx); /* total kernels launc
 
 /* ---- file image: replaces ParquetReader::read_range (parquet_reader.cpp:173-178) ------ */
 PQG_API int pqg_upload(pqg_ctx* ctx, const void* host_bytes, uint64_t size, pqg_buf** out);
-PQG_API int pqg_wrap_device(pqg_ctx* ctx, const void* dev_ptr, uint64_t size, pqg_buf** out);
+/* wrap caller-owned device memory (16-byte aligned).  `capacity` = bytes readable behind dev_ptr:
+ * the kernels read whole 16-byte vectors and TMA tiles, so capacity must be >= size + 64
+ * (PQG_ERR_ARG otherwise); the bytes past `size` are never interpreted. */
+PQG_API int pqg_wrap_device(pqg_ctx* ctx, const void* dev_ptr, uint64_t size, uint64_t capacity, pqg_buf** out);
 /* an empty device image to be filled range by range (a column's chunks packed together):
  * asynchronous H2D of `n` host bytes to image offset `dst_off` on the context's stream */
 PQG_API int pqg_buf_alloc(pqg_ctx* ctx, uint64_t size, pqg_buf** out);
@@ -188,7 +199,12 @@ typedef struct pqg_h2d_range {
 } pqg_h2d_range;
 PQG_API int pqg_plan_run_pipelined(pqg_ctx* ctx, pqg_plan* plan, pqg_buf* image, const pqg_h2d_range* ranges,
                                    uint32_t n_ranges, void* host_values, uint32_t* host_validity);
-/* wait for the run and report page errors; PQG_ERR_PAGE when err->count > 0 */
+/* wait for the run and report page errors; PQG_ERR_PAGE when err->count > 0.
+ * An out-of-range dictionary index is a NULL in the reference whatever the column's repetition
+ * (src/reader/column_reader.cpp:190-194).  A plan whose chunks are all REQUIRED carries no validity
+ * bitmap; when such an index shows up, pqg_plan_finish adds the bitmap and decodes the plan again
+ * (pqg_plan_validity is non-NULL afterwards).  After pqg_plan_run_pipelined that is not possible
+ * (the host buffers are the caller's): PQG_ERR_PAGE "... out-of-range dictionary index ...". */
 PQG_API int pqg_plan_finish(pqg_ctx* ctx, pqg_plan* plan, pqg_page_error* err);
 PQG_API int pqg_plan_timings(const pqg_plan* plan, pqg_timings* out);
 /* mean over the last `last_n` (0 = all kept, at most 8) profiled runs whose events have

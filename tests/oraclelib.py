@@ -423,3 +423,25 @@ def fixed_col(arr, is_null=None):
     else:
         fx = a.astype(np.uint64)
     return dict(is_null=is_null, fixed=fx)
+
+
+def re2_page_bits(src, h, col, pattern, neg):
+    """the frozen spec of a-19 evaluated with RE2 itself (pyarrow's match_substring_regex) over the per-page
+    values of ColumnReader::read_pages as `src` (oracle or compiled reference) returns them"""
+    import pyarrow as pa
+    import pyarrow.compute as pc
+    nrg = src.num_row_groups(h)
+    bits = []
+    for rg in range(nrg):
+        pages = src.read_pages(h, rg, col)
+        v = pages.values
+        strs = [None if v.is_null[i] else v.chars[int(v.str_off[i]):int(v.str_off[i + 1])].tobytes().decode() for i in range(v.n)]
+        m = np.array(pc.match_substring_regex(pa.array(strs, type=pa.string()), pattern).fill_null(False).to_pylist(), dtype=bool)
+        isn = v.is_null.astype(bool)
+        pred = (~m if neg else m) & ~isn
+        for k in range(len(pages.page_num)):
+            if pages.page_type[k] != 0:
+                continue
+            a, b = int(pages.first_value[k]), int(pages.first_value[k + 1])
+            bits.append(1 if pred[a:b].any() else 0)
+    return np.array(bits, dtype=np.uint8)

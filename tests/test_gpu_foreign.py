@@ -114,3 +114,145 @@ def test_pyarrow_files_match_oracle_and_reference(pq, oracle, tmp_path, variant)
         if hr is not None:
             ref.close(hr)
         r.close()
+
+
+def _compare_all(pq, oracle, path, expect_ref=True):
+    """every column chunk of the file: GPU path vs oracle and (where it opens the file) the compiled reference"""
+    import oraclelib
+    ref = oraclelib.Ref() if oraclelib.Ref.available() else None
+    r = pq.Reader(path)
+    ho = oracle.open(path)
+    hr = None
+    if ref:
+        try:
+            hr = ref.open(path)
+        except Exception:
+            hr = None
+    checked_ref = 0
+    try:
+        for c in range(r.num_columns):
+            for rg in range(r.num_row_groups):
+                got = to_values(r.read_column_by_idx(rg, c))
+                d = got.diff(oracle.read_column_by_idx(ho, rg, c))
+                assert d is None, (r.column_info(c)["name"], rg, d)
+                if hr is not None:
+                    d = got.diff(ref.read_column_by_idx(hr, rg, c))
+                    assert d is None, ("vs reference", r.column_info(c)["name"], rg, d)
+                    checked_ref += 1
+        return r.num_columns, checked_ref
+    finally:
+        oracle.close(ho)
+        if hr is not None:
+            ref.close(hr)
+        r.close()
+
+
+def test_optional_struct_leaf_max_def_2_many_pages(pq, oracle, tmp_path):
+    """optional struct -> optional leaf: max_def = 2, no repetition.  Deterministic in the reference
+    (levels: src/reader/column_reader.cpp:146-170; schema walk: src/reader/parquet_reader.cpp:484-543):
+    a slot is a value iff its level is 2.  Several hundred small pages per chunk: every page of such a
+    chunk is host-listed for the general kernel (the hand-over list must hold them all)."""
+    rng = np.random.default_rng(21)
+    n = 150_000
+    leaf_null = rng.random(n) < 0.2
+    struct_null = rng.random(n) < 0.1
+    i64 = rng.integers(-2**50, 2**50, size=n)
+    f64 = rng.random(n)
+    small = rng.integers(0, 50, size=n)
+    strs = np.array([f"k{v:04d}" for v in rng.integers(0, 300, size=n)], dtype=object)
+    st = pa.StructArray.from_arrays(
+        [pa.array(i64, mask=leaf_null, type=pa.int64()), pa.array(f64, mask=leaf_null, type=pa.float64()),
+         pa.array(small.astype(np.int32), mask=leaf_null, type=pa.int32()), pa.array(strs, mask=leaf_null, type=pa.string())],
+        names=["x", "y", "z", "s"], mask=pa.array(struct_null))
+    t = pa.table({"st": st, "plain": pa.array(i64, type=pa.int64())})
+    for name, kw in (("small", dict(data_page_size=1500, row_group_size=75_000)),
+                     ("small_plain", dict(data_page_size=1500, row_group_size=75_000, use_dictionary=False)),
+                     ("big", dict(data_page_size=1 << 20, row_group_size=n))):
+        path = write(str(tmp_path / f"nested_{name}.parquet"), t, **kw)
+        r = pq.Reader(path)
+        infos = [r.column_info(c) for c in range(r.num_columns)]
+        r.close()
+        assert [i["max_def_level"] for i in infos] == [2, 2, 2, 2, 0] and all(i["max_rep_level"] == 0 for i in infos)
+        ncols, _ = _compare_all(pq, oracle, path)
+        assert ncols == 5
+        # and pyarrow's reading: null iff struct or leaf is null
+        r = pq.Reader(path)
+        got = r.read_column("st.x") if r.find_column("st.x") >= 0 else r.read_column(infos[0]["name"])
+        assert np.array_equal(got["is_null"].astype(bool), leaf_null | struct_null)
+        valid = ~(leaf_null | struct_null)
+        assert np.array_equal(got["fixed"].astype(np.uint64).view(np.int64)[valid], i64[valid])
+        r.close()
+
+
+def test_oversized_pages_with_nulls_beyond_the_big_page_kernel(pq, oracle, tmp_path):
+    """one page of > 131072 slots with nulls: the one-CTA-per-page kernel hands it on to the general kernel"""
+    rng = np.random.default_rng(22)
+    n = 300_000
+    nulls = rng.random(n) < 0.3
+    t = pa.table({"a": pa.array(rng.integers(-2**40, 2**40, size=n), mask=nulls, type=pa.int64()),
+                  "d": pa.array(rng.integers(0, 1000, size=n), mask=nulls, type=pa.int64())})
+    path = write(str(tmp_path / "huge_pages.parquet"), t, data_page_size=8 << 20, row_group_size=n, dictionary_pagesize_limit=8 << 20)
+    _compare_all(pq, oracle, path)
+
+
+def test_int96_renders_like_the_reference(pq, oracle, tmp_path):
+    """INT96 values come back as the STRING "INT96(high:low)" (reference src/reader/column_reader.cpp:257-264)"""
+    import datetime
+    rng = np.random.default_rng(23)
+    n = 20_000
+    base = datetime.datetime(2001, 1, 1)
+    ts = [None if rng.random() < 0.1 else base + datetime.timedelta(seconds=int(s), microseconds=int(u))
+          for s, u in zip(rng.integers(0, 10**9, size=n), rng.integers(0, 10**6, size=n))]
+    t = pa.table({"ts": pa.array(ts, type=pa.timestamp("us")), "ts_req": pa.array([v or base for v in ts], type=pa.timestamp("ns"))})
+    for name, kw in (("dict", {}), ("plain", dict(use_dictionary=False))):
+        path = write(str(tmp_path / f"int96_{name}.parquet"), t, use_deprecated_int96_timestamps=True, data_page_size=2000, **kw)
+        r = pq.Reader(path)
+        assert r.column_info(0)["type"] == pq.INT96
+        got = r.read_column("ts")
+        r.close()
+        assert int(got["vidx"][~got["is_null"].astype(bool)][0]) == 5  # the string alternative of Value
+        s0 = got["chars"].tobytes()[int(got["str_off"][0]):int(got["str_off"][1])] if not got["is_null"][0] else b"INT96("
+        assert s0.startswith(b"INT96(")
+        _compare_all(pq, oracle, path)
+
+
+def test_unsupported_files_fail_with_explicit_errors(pq, tmp_path):
+    """compressed chunks: the reference's message (src/reader/column_reader.cpp:13-15); DATA_PAGE_V2 and
+    DELTA_* / BYTE_STREAM_SPLIT pages: explicit errors instead of the reference's skipped / garbage decode
+    (column_reader.cpp:66-67,173-222)"""
+    rng = np.random.default_rng(24)
+    n = 5000
+    t = pa.table({"i": pa.array(rng.integers(0, 1 << 40, size=n), type=pa.int64()),
+                  "f": pa.array(rng.random(n), type=pa.float64()),
+                  "s": pa.array([f"s{v}" for v in rng.integers(0, 100, size=n)], type=pa.string())})
+    cases = [
+        ("snappy", dict(compression="SNAPPY"), "Only uncompressed parquet files are supported", ["i", "f", "s"]),
+        ("zstd", dict(compression="ZSTD"), "Only uncompressed parquet files are supported", ["i"]),
+        ("v2", dict(data_page_version="2.0"), "DATA_PAGE_V2", ["i", "f", "s"]),
+        ("delta", dict(use_dictionary=False, column_encoding={"i": "DELTA_BINARY_PACKED"}), "DELTA_BINARY_PACKED", ["i"]),
+        ("bss", dict(use_dictionary=False, column_encoding={"f": "BYTE_STREAM_SPLIT"}), "BYTE_STREAM_SPLIT", ["f"]),
+        ("dlba", dict(use_dictionary=False, column_encoding={"s": "DELTA_LENGTH_BYTE_ARRAY"}), "DELTA_LENGTH_BYTE_ARRAY", ["s"]),
+        ("dba", dict(use_dictionary=False, column_encoding={"s": "DELTA_BYTE_ARRAY"}), "DELTA_BYTE_ARRAY", ["s"]),
+    ]
+    for name, kw, msg, cols in cases:
+        path = write(str(tmp_path / f"unsupported_{name}.parquet"), t, **kw)
+        r = pq.Reader(path)
+        try:
+            assert r.num_rows == n  # the file opens: footer and page walk are fine
+            for c in cols:
+                with pytest.raises(pq.PqgError, match=msg):
+                    r.read_column(c)
+                with pytest.raises(pq.PqgError, match=msg):
+                    r.read_columnar(r.find_column(c))
+                if c == "s":
+                    with pytest.raises(pq.PqgError, match=msg):
+                        r.regex_prune(r.find_column(c), "s1")
+                    with pytest.raises(pq.PqgError, match=msg):
+                        r.string_iterator(c)
+            # columns the option did not touch still decode
+            for c in ("i", "f", "s"):
+                if c not in cols:
+                    got = r.read_column(c)
+                    assert len(got["is_null"]) == n
+        finally:
+            r.close()

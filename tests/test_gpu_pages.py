@@ -67,9 +67,9 @@ class Builder:
         self.pages = []
         self.rows = 0
 
-    def add_page(self, payload, num_values, dict_page=True, misalign=0):
+    def add_page(self, payload, num_values, dict_page=True, misalign=0, flags=None):
         self.img += b"\xEE" * misalign
-        self.pages.append((len(self.img), len(payload), num_values, dict_page, self.rows))
+        self.pages.append((len(self.img), len(payload), num_values, (1 if dict_page else 0) if flags is None else flags, self.rows))
         self.img += payload
         self.rows += num_values
 
@@ -83,7 +83,13 @@ class Builder:
                              1 if self.dict_n else 0, (C.c_uint8 * 2)(0, 0))
         pg = (pq.PageDesc * max(len(self.pages), 1))()
         for i, (off, size, nv, dp, row) in enumerate(self.pages):
-            pg[i] = pq.PageDesc(off, row, size, nv, 0, 1 if dp else 0)
+            pg[i] = pq.PageDesc(off, row, size, nv, 0, dp)
+        if expect_error is not None and expect_error[0] == "create":
+            with pytest.raises(pq.PqgError, match=expect_error[1]):
+                ctx.plan(buf, (ck, 1, pg, len(self.pages), self.rows))
+            ctx.buf_free(buf)
+            ctx.close()
+            return None, None, None
         plan = ctx.plan(buf, (ck, 1, pg, len(self.pages), self.rows))
         plan.run()
         try:
@@ -96,10 +102,12 @@ class Builder:
             plan.finish()
             vals = np.zeros(self.rows, dtype=np.int64)
             valid = np.zeros((self.rows + 31) // 32 + 1, dtype=np.uint32)
-            plan.download(values=vals.ctypes.data, validity=valid.ctypes.data if self.max_def else None)
+            has_validity = bool(plan.validity_ptr)
+            assert has_validity or not self.max_def
+            plan.download(values=vals.ctypes.data, validity=valid.ctypes.data if has_validity else None)
             ctx.sync()
             v = None
-            if self.max_def:
+            if has_validity:
                 v = ((valid[np.arange(self.rows) >> 5] >> (np.arange(self.rows) & 31).astype(np.uint32)) & 1).astype(bool)
             return vals, v, None
         finally:
@@ -287,3 +295,71 @@ def test_plain_string_pages_with_trailing_bytes_fall_back_to_the_size_pass(pq):
         exp = a + b + a
         assert chars == b"".join(exp)
         assert offs.tolist() == np.concatenate([[0], np.cumsum([len(s) for s in exp])]).tolist()
+
+
+def test_required_chunk_out_of_range_indices_become_nulls(pq, oracle):
+    """Value::null() for an out-of-range dictionary index whatever max_def is (reference
+    src/reader/column_reader.cpp:190-194): a REQUIRED-only plan has no validity bitmap, so
+    pqg_plan_finish adds one and decodes again.  Writer-shaped streams (tile kernel), foreign
+    streams (run-by-run path) and a page that only the general kernel takes."""
+    rng = np.random.default_rng(17)
+    dict_vals = np.arange(100, dtype=np.int64) * 13 + 5
+    b = Builder(pq, dict_vals, max_def=0)
+    exp_vals, exp_valid = [], []
+    for page, n in enumerate((40, 1024, 777, 64, 1500)):
+        idx = rng.integers(0, 100, size=n).astype(np.uint32)
+        if page != 3:  # page 3 stays clean
+            idx[n // 3] = 100
+            idx[n - 1] = 126
+        stream = foreign_stream(idx, 7, rng) if page % 2 else bytes(_enc(idx, 7))
+        dec = oracle.rle_decode_i32(np.frombuffer(stream, dtype=np.uint8), 7, n).astype(np.uint32)
+        b.add_page(bytes([7]) + stream, n, misalign=page)
+        good = dec < 100
+        v = np.zeros(n, dtype=np.int64)
+        v[good] = dict_vals[dec[good]]
+        exp_vals.append(v)
+        exp_valid.append(good)
+    vals, valid, _ = b.run()
+    assert valid is not None, "the plan must grow a validity bitmap"
+    assert np.array_equal(valid, np.concatenate(exp_valid))
+    assert np.array_equal(vals, np.concatenate(exp_vals))
+    # a clean REQUIRED plan still carries none
+    b = Builder(pq, dict_vals, max_def=0)
+    b.add_page(bytes([7]) + bytes(_enc(np.arange(64, dtype=np.uint32), 7)), 64)
+    vals, valid, _ = b.run()
+    assert valid is None and np.array_equal(vals, dict_vals[:64])
+
+
+def test_unsupported_pages_are_rejected_at_plan_creation(pq):
+    """SURVEY 8(b) "Unsupported inputs": DATA_PAGE_V2 and DELTA_* / BYTE_STREAM_SPLIT data pages fail with
+    PQG_ERR_UNSUPPORTED and a message instead of being decoded as PLAIN (what the reference does,
+    src/reader/column_reader.cpp:66-67,173-222)"""
+    vals = np.arange(8, dtype=np.int64).tobytes()
+    for enc, name in ((5, "DELTA_BINARY_PACKED"), (6, "DELTA_LENGTH_BYTE_ARRAY"), (7, "DELTA_BYTE_ARRAY"), (9, "BYTE_STREAM_SPLIT"), (4, "BIT_PACKED")):
+        b = Builder(pq, None)
+        b.add_page(vals, 8, flags=0)
+        b.add_page(vals, 8, flags=enc << 8)
+        b.run(expect_error=("create", name))
+    b = Builder(pq, None)
+    b.add_page(vals, 8, flags=pq.PQG_PAGE_FLAG_V2)
+    b.run(expect_error=("create", "DATA_PAGE_V2"))
+    # the encodings that ARE decoded, spelled out in the flags
+    b = Builder(pq, np.arange(16, dtype=np.int64))
+    b.add_page(vals, 8, flags=0 << 8)
+    b.add_page(bytes([4]) + _enc(np.arange(8, dtype=np.uint32), 4), 8, flags=1 | (8 << 8))
+    b.add_page(bytes([4]) + _enc(np.arange(8, dtype=np.uint32), 4), 8, flags=1 | (2 << 8))
+    out, _, _ = b.run()
+    assert out.tolist() == list(range(8)) * 3
+
+
+def test_wrap_device_requires_a_readable_tail(pq):
+    ctx = pq.Context(0)
+    img = np.zeros(4096, dtype=np.uint8)
+    buf = ctx.upload(img.ctypes.data, 1024)
+    ptr = pq.lib().pqg_buf_device_ptr(buf)
+    with pytest.raises(pq.PqgError, match="capacity"):
+        ctx.wrap_device(ptr, 1024, capacity=1024)
+    w = ctx.wrap_device(ptr, 1024 - 64, capacity=1024)
+    ctx.buf_free(w)
+    ctx.buf_free(buf)
+    ctx.close()

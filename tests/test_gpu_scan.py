@@ -5,7 +5,7 @@ values; the loop of src/main.cpp restated in oracle/pq_oracle.c)."""
 import numpy as np
 import pytest
 
-from oraclelib import BYTE_ARRAY
+from oraclelib import BYTE_ARRAY, re2_page_bits
 
 pytestmark = pytest.mark.gpu
 
@@ -43,6 +43,29 @@ def test_regex_prune_matches_oracle(pq, oracle, files):
         finally:
             oracle.close(ho)
             r.close()
+
+
+def test_regex_prune_matches_re2(pq, oracle, files):
+    """page-match sets identical to RE2's PartialMatch over the reference reader's values (ASCII / valid UTF-8 columns)"""
+    pytest.importorskip("pyarrow")
+    import oraclelib
+    ref = oraclelib.Ref() if oraclelib.Ref.available() else None
+    path = files["golden_mixed"]
+    r = pq.Reader(path)
+    src = ref or oracle
+    h = src.open(path)
+    try:
+        for c in string_columns(r):
+            if r.column_info(c)["name"] == "wild":
+                continue  # arbitrary bytes: not valid UTF-8
+            for pat in PATTERNS:
+                for neg in (False, True):
+                    got, _ = r.regex_prune(c, pat, neg)
+                    exp = re2_page_bits(src, h, c, pat, neg)
+                    assert np.array_equal(got, exp), (r.column_info(c)["name"], pat, neg)
+    finally:
+        src.close(h)
+        r.close()
 
 
 def test_regex_rejects_unsupported_and_non_string(pq, files):

@@ -170,3 +170,80 @@ def test_multi_column_descriptor_tables(pq, files):
     with pytest.raises(pq.PqgError):
         r.columns_tables([], -1)
     r.close()
+
+
+def test_page_descriptors_carry_encoding_and_page_type(pq, tmp_path):
+    """DataPageHeader.encoding travels in pqg_page_desc.flags bits 8..15 and DATA_PAGE_V2 pages are listed with
+    PQG_PAGE_FLAG_V2, so that pqg_plan_create can refuse what the kernels do not decode (SURVEY 8 b)"""
+    pa = pytest.importorskip("pyarrow")
+    pqa = pytest.importorskip("pyarrow.parquet")
+    rng = np.random.default_rng(1)
+    n = 4000
+    t = pa.table({"i": pa.array(rng.integers(0, 1 << 40, size=n), type=pa.int64()),
+                  "d": pa.array(rng.integers(0, 10, size=n), type=pa.int64()),
+                  "f": pa.array(rng.random(n), type=pa.float64())})
+    base = dict(compression="NONE", data_page_version="1.0", write_statistics=False)
+
+    def flags(path, col):
+        r = pq.Reader(path)
+        try:
+            assert r.num_rows == n
+            _, _, pages, npg, _ = r.column_tables(col, -1)
+            return [pages[k].flags for k in range(npg)]
+        finally:
+            r.close()
+
+    p = str(tmp_path / "v1.parquet")
+    pqa.write_table(t, p, use_dictionary=["d"], **base)
+    assert set(flags(p, 0)) == {0}                                   # PLAIN
+    assert all(f & 1 and (f >> 8) in (2, 8) for f in flags(p, 1))    # dictionary
+    p = str(tmp_path / "delta.parquet")
+    pqa.write_table(t, p, use_dictionary=False, column_encoding={"i": "DELTA_BINARY_PACKED", "f": "BYTE_STREAM_SPLIT"}, **base)
+    assert {f >> 8 for f in flags(p, 0)} == {5} and {f >> 8 for f in flags(p, 2)} == {9}
+    p = str(tmp_path / "v2.parquet")
+    pqa.write_table(t, p, use_dictionary=False, **dict(base, data_page_version="2.0"))
+    assert all(f & pq.PQG_PAGE_FLAG_V2 for f in flags(p, 0))
+    p = str(tmp_path / "snappy.parquet")
+    pqa.write_table(t, p, **dict(base, compression="SNAPPY"))
+    r = pq.Reader(p)
+    with pytest.raises(pq.PqgError, match="Only uncompressed parquet files are supported"):
+        r.column_tables(0, -1)
+    r.close()
+
+
+def _thrift_file(bool_list_len, declared_len=None):
+    """a minimal file whose FileMetaData carries an unknown field (id 100) of type list<bool> in front of
+    num_rows: bool elements are one byte each inside a list (compact protocol)"""
+    def varint(x):
+        out = bytearray()
+        while x >= 0x80:
+            out.append((x & 0x7F) | 0x80)
+            x >>= 7
+        out.append(x)
+        return bytes(out)
+
+    def zz(x):
+        return varint((x << 1) ^ (x >> 63))
+    md = bytearray()
+    md += b"\x15" + zz(2)                      # 1: version i32
+    md += b"\x19\x1c"                          # 2: schema list<struct>, 1 element
+    md += b"\x48" + varint(6) + b"schema" + b"\x15" + zz(0) + b"\x00"   # name (4), num_children (5) = 0
+    k = bool_list_len if declared_len is None else declared_len
+    md += b"\x09" + zz(100)                    # id 100 (long form): list
+    md += (bytes([(k << 4) | 1]) if k < 15 else b"\xf1" + varint(k)) + bytes([1, 2] * (bool_list_len // 2) + [1] * (bool_list_len % 2))
+    md += b"\x06" + zz(3) + zz(123)            # 3: num_rows i64 (long form: the id goes backwards)
+    md += b"\x19\x0c"                          # 4: row_groups, empty
+    md += b"\x00"
+    return b"PAR1" + bytes(md) + len(md).to_bytes(4, "little") + b"PAR1"
+
+
+def test_thrift_skip_of_bool_lists_and_hostile_counts(pq):
+    r = pq.Reader(data=np.frombuffer(_thrift_file(5), dtype=np.uint8))
+    assert r.num_rows == 123 and r.num_row_groups == 0
+    r.close()
+    r = pq.Reader(data=np.frombuffer(_thrift_file(40), dtype=np.uint8))
+    assert r.num_rows == 123
+    r.close()
+    # a count far beyond the buffer is a corrupt footer, not a 2^31-iteration loop
+    with pytest.raises(pq.PqgError):
+        pq.Reader(data=np.frombuffer(_thrift_file(4, declared_len=(1 << 31) - 1), dtype=np.uint8))

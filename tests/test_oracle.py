@@ -119,3 +119,25 @@ def test_page_chunk_index_spec(oracle):
             assert list(pc) == exp_c and list(po) == exp_o and list(cf) == first
     finally:
         oracle.close(h)
+
+
+def test_oracle_regex_prune_is_pinned_to_re2(oracle, ref):
+    """a-19: the oracle's page bitmaps == RE2 (pyarrow's match_substring_regex) applied to the values the
+    REFERENCE's ColumnReader::read_pages returns for every page of the golden file"""
+    pytest.importorskip("pyarrow")
+    from oraclelib import BYTE_ARRAY, re2_page_bits
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mixed.parquet")
+    ho = oracle.open(path)
+    src, hs = (ref, ref.open(path)) if ref is not None else (oracle, ho)
+    try:
+        for c in range(oracle.num_columns(ho)):
+            ci = oracle.column_info(ho, c)
+            if ci["type"] != BYTE_ARRAY or ci["name"] == "wild":
+                continue
+            for pat in (r"^[a-z0-9._]+@[a-z0-9.]+\.com$", r"@mail7", r"Berlin|Dublin", r"^$", r"[^a-z]", r"\d{9}", r"example\.com!!$"):
+                for neg in (False, True):
+                    assert np.array_equal(oracle.regex_prune(ho, c, pat, neg), re2_page_bits(src, hs, c, pat, neg)), (ci["name"], pat, neg)
+    finally:
+        if src is not oracle:
+            src.close(hs)
+        oracle.close(ho)

@@ -1,7 +1,8 @@
 """CPU tests of the host regex -> DFA compiler (product, host/pq_regex.cpp) against two
-independent checkers: the oracle's backtracking matcher (oracle/regex_oracle.c) and Python's
-`re` on the common subset.  Parity for the regex mode is UNPINNED (no reference source,
-README.md:54-64 only): the contract is the frozen spec in SURVEY.md section 8 (a-19)."""
+checkers: RE2 itself (pyarrow.compute.match_substring_regex -- the library the reference's regex
+mode links, README.md:7-29,54-64; its call sites are absent from the tree, so RE2's PartialMatch on
+the column values IS the pin for a-19), the oracle's backtracking matcher (oracle/regex_oracle.c,
+pinned to RE2 by the same tests) and Python's `re` on the common subset."""
 import re
 
 import numpy as np
@@ -114,3 +115,78 @@ def test_dfa_random_corpus(pq, oracle):
 def test_dfa_size_limit(pq):
     with pytest.raises(ValueError, match="too large"):
         pq.regex_compile(r"(a|b)*a(a|b){14}")
+
+
+# ---- a-19 pinned to RE2 -----------------------------------------------------------------------
+# The reference's regex mode links RE2 (README.md:7-29); its source is absent, but pyarrow's
+# `match_substring_regex` IS RE2 (UTF-8 mode on string arrays, unanchored = PartialMatch).  The host
+# DFA compiler must agree with it on every supported pattern; whatever RE2 accepts and the DFA
+# compiler does not support must be REJECTED explicitly, never matched differently.
+RE2_ACCEPTS_WE_REJECT = [r"\b", r"(?i)a", r"(?P<n>a)", r"[[:alpha:]]", r"[é]", r"\pL", r"\Qa\E", r"\xff", r"\Ba", r"(?s).", r"(?m)^a$",
+                         r"\A", r"\z", r"\C", r"[^é]", r"\x{10FFFF}"]
+
+
+def _re2():
+    pa = pytest.importorskip("pyarrow")
+    pc = pytest.importorskip("pyarrow.compute")
+    return pa, pc
+
+
+def _valid_utf8(b):
+    try:
+        b.decode()
+        return True
+    except UnicodeDecodeError:
+        return False
+
+
+def test_dfa_agrees_with_re2_on_the_pattern_list(pq, oracle):
+    pa, pc = _re2()
+    texts = [t for t in TEXTS if _valid_utf8(t)]
+    arr = pa.array([t.decode() for t in texts], type=pa.string())
+    for pattern in PATTERNS:
+        dfa = pq.regex_compile(pattern)
+        exp = pc.match_substring_regex(arr, pattern).to_pylist()  # raises if RE2 rejects what we accept
+        got = [bool(pq.dfa_match_host(dfa, t)) for t in texts]
+        pq.lib().pqg_dfa_free(dfa)
+        assert got == exp, (pattern, [t for t, g, e in zip(texts, got, exp) if g != e])
+        assert [bool(oracle.regex_search(pattern, t)) for t in texts] == exp, ("oracle vs RE2", pattern)
+
+
+def test_dfa_agrees_with_re2_on_a_random_corpus(pq):
+    pa, pc = _re2()
+    rng = np.random.default_rng(11)
+    alphabet = ["a", "b", "c", ".", "@", "0", "7", "\n", " ", "_", "é", "日", "z", "-", "Z"]
+    strs = ["".join(rng.choice(alphabet, size=rng.integers(0, 16))) for _ in range(3000)]
+    strs += [f"user{rng.integers(0, 10**6)}@mail{rng.integers(0, 999)}.example.com" for _ in range(300)]
+    strs += [f"user{rng.integers(0, 10**6)}.mail.example.co!" for _ in range(100)]
+    arr = pa.array(strs, type=pa.string())
+    enc = [s.encode() for s in strs]
+    patterns = [r"^[a-z0-9._]+@[a-z0-9.]+\.com$", r"a+b", r"^[ab]*@", r"(a|b)*c$", r"\.\d", r"^a.b$", r"[^ab]{2}", r"(ab|ba)+0?$",
+                r"^.{0,3}$", r"é.", r"[a-c]+[^a-c]", r"\w+@\w+", r"^\S+$", r"\s\S\s", r"(a|é|日)+z", r"^(?:[a-z]|\d){4,}$", r"[-_.]\D",
+                r"^$", r"\W$", r"^[^@\n]*$", r"a{2,3}b{0,1}c", r"0|7|Z", r"[0-9][a-z]|[a-z][0-9]", r"\n.", r".\n", r"^\n",
+                r"a*?b", r"^a+?$", r"ab??c"]  # lazy quantifiers: same language, so the same match / no-match answer
+    for pattern in patterns:
+        dfa = pq.regex_compile(pattern)
+        exp = np.array(pc.match_substring_regex(arr, pattern).to_pylist())
+        got = np.array([bool(pq.dfa_match_host(dfa, t)) for t in enc])
+        pq.lib().pqg_dfa_free(dfa)
+        bad = np.nonzero(got != exp)[0]
+        assert len(bad) == 0, (pattern, [strs[i] for i in bad[:5]])
+
+
+def test_divergences_from_re2_are_rejections(pq):
+    """every construct RE2 takes and the DFA compiler does not: an explicit error, never a different answer"""
+    pa, pc = _re2()
+    arr = pa.array(["abc"], type=pa.string())
+    for pattern in RE2_ACCEPTS_WE_REJECT:
+        pc.match_substring_regex(arr, pattern)  # RE2 accepts it
+        with pytest.raises(ValueError, match="^regex: "):
+            pq.regex_compile(pattern)
+    for pattern in REJECTED:
+        re2_ok = True
+        try:
+            pc.match_substring_regex(arr, pattern)
+        except Exception:
+            re2_ok = False
+        assert re2_ok == (pattern in RE2_ACCEPTS_WE_REJECT), pattern
