@@ -90,119 +90,6 @@ def cfg2_columns(rows, seed):
     return cols
 
 
-EMAIL_PATTERN = r"^[a-z0-9._]+@[a-z0-9.]+\.com$"
-
-
-def cfg4_email_column(rows, seed):
-    """BASELINE.json configs[3] (scaled): PLAIN BYTE_ARRAY 'user<9 digits>@mail<3 digits>.example.com'
-    (33 bytes), 20 % noise in runs of 2000 rows so that whole pages are noise: half of the noise
-    rows have no '@', half end in '.co!' -- both polarities of the predicate prune pages."""
-    rng = np.random.default_rng(seed)
-    tmpl = np.frombuffer(b"user000000000@mail000.example.com", dtype=np.uint8)
-    m = np.tile(tmpl, (rows, 1))
-    u = rng.integers(10**8, 10**9, size=rows, dtype=np.int64)
-    for d in range(9):
-        m[:, 4 + 8 - d] = 48 + (u % 10)
-        u //= 10
-    k = rng.integers(0, 1000, size=rows, dtype=np.int64)
-    for d in range(3):
-        m[:, 18 + 2 - d] = 48 + (k % 10)
-        k //= 10
-    blk = np.arange(rows) // 2000
-    noise = (blk % 5) == 3
-    kind = (blk // 5) % 2
-    m[noise & (kind == 0), 13] = ord(".")
-    m[noise & (kind == 1), 32] = ord("!")
-    off = np.arange(rows + 1, dtype=np.uint64) * 33
-    return dict(str_off=off, chars=m.reshape(-1))
-
-
-def regex_bench(pq, ctx_device, stream, steps, warmup, peak, rows, rg_rows):
-    """regex-pruned pages/s on a device-resident PLAIN BYTE_ARRAY column (BASELINE configs[3] shape)"""
-    import torch
-    t0 = time.time()
-    col = cfg4_email_column(rows, 99)
-    specs = [("email", 6, 0, 0)]
-    g = pq.generate(specs, [col], rg_split(rows, rg_rows))
-    size = g.size
-    host = torch.empty(size + 64, dtype=torch.uint8, pin_memory=True)
-    g.emit(host.data_ptr(), size)
-    g.free()
-    log(f"[bench] regex workload: {rows} rows, file {size / 1e9:.3f} GB, built in {time.time() - t0:.1f}s")
-    reader = pq.Reader.from_pointer(host.data_ptr(), size, device=ctx_device)
-    ctx = pq.Context(ctx_device, stream.cuda_stream)
-    dev_img = torch.empty(size + 64, dtype=torch.uint8, device="cuda")
-    with torch.cuda.stream(stream):
-        dev_img[:size].copy_(host[:size], non_blocking=True)
-        dev_img[size:].zero_()
-    stream.synchronize()
-    image = ctx.wrap_device(dev_img.data_ptr(), size)
-    tables = reader.column_tables(0, -1)
-    plan = ctx.plan(image, tables)
-    n_pages = tables[3]
-    out = {}
-    import ctypes
-    L = pq.lib()
-    for neg in (0, 1):
-        dfa = pq.regex_compile(EMAIL_PATTERN)
-        bits = np.zeros((n_pages + 31) // 32 + 1, dtype=np.uint32)
-        ms = ctypes.c_float(0)
-        times = []
-        for it in range(warmup + steps):
-            rc = L.pqg_regex_scan(ctx.h, plan.h, dfa, neg, bits.ctypes.data, ctypes.byref(ms))
-            if rc != 0:
-                raise RuntimeError(ctx.err())
-            if it >= warmup:
-                times.append(ms.value)
-        L.pqg_dfa_free(dfa)
-        t = sum(times) / len(times)
-        unpacked = ((bits[np.arange(n_pages) >> 5] >> (np.arange(n_pages) & 31).astype(np.uint32)) & 1).astype(np.uint8)
-        out["neg" if neg else "pos"] = dict(ms=t, bits=unpacked)
-    bytes_in = plan.bytes_in
-    # parity + CPU baseline on a bounded sample: the first row group through the oracle
-    # (reference-order decode + backtracking matcher; kind "port" -- the reference's regex mode has no source)
-    cpu = None
-    try:
-        import oraclelib
-        oraclelib.build_oracle()
-        orc = oraclelib.Oracle()
-        take = min(rows, rg_rows)
-        sub = dict(str_off=col["str_off"][:take + 1], chars=col["chars"][:take * 33])
-        path = os.path.join(scratch_dir(1 << 30), f"pqg_bench_regex_{os.getpid()}.parquet")
-        gg = pq.generate(specs, [sub], [take])
-        gg.write(path)
-        gg.free()
-        try:
-            h = orc.open(path)
-            t1 = time.perf_counter()
-            exp = orc.regex_prune(h, 0, EMAIL_PATTERN, False)
-            cpu_s = time.perf_counter() - t1
-            expn = orc.regex_prune(h, 0, EMAIL_PATTERN, True)
-            orc.close(h)
-        finally:
-            os.unlink(path)
-        if not (np.array_equal(exp, out["pos"]["bits"][:len(exp)]) and np.array_equal(expn, out["neg"]["bits"][:len(expn)])):
-            raise AssertionError("regex page bitmap differs from the oracle on the sample row group")
-        cpu = {"value": len(exp) / cpu_s, "unit": "pages/s", "cores": 1, "kind": "port",
-               "sample": f"first row group ({take} values, {len(exp)} pages): oracle/regex_oracle.c over the reference-order decode"}
-    except AssertionError:
-        raise
-    except Exception as e:
-        cpu = {"value": None, "unit": "pages/s", "cores": 1, "kind": "port", "sample": f"unavailable: {e}"}
-    ms = out["pos"]["ms"]
-    res = {"metric": "regex_pruned_pages_per_s", "value": n_pages / (ms * 1e-3), "unit": "pages/s", "pattern": EMAIL_PATTERN,
-           "workload": f"cfg4 (scaled): {rows} PLAIN BYTE_ARRAY email-like values, {n_pages} pages, {bytes_in / 1e9:.2f} GB payload, device resident",
-           "kernel_ms": ms, "payload_GBps": bytes_in / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": bytes_in / (ms * 1e-3) / 1e9 / peak,
-           "pages_pruned": int((out["pos"]["bits"] == 0).sum()),
-           "neg_regex": {"value": n_pages / (out["neg"]["ms"] * 1e-3), "kernel_ms": out["neg"]["ms"], "pages_pruned": int((out["neg"]["bits"] == 0).sum())},
-           "cpu_baseline": cpu, "parity": "page bitmaps (both polarities) identical to the oracle on the sample row group"}
-    plan.destroy()
-    ctx.buf_free(image)
-    reader.close()
-    del dev_img
-    return res
-
-
 def scratch_dir(need_bytes):
     """RAM-backed scratch for the CPU arm's sample file when it has room (page cache warm either way)"""
     import shutil
@@ -372,7 +259,11 @@ def main():
     ap.add_argument("--cpu-sample-rgs", type=int, default=4)
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--regex-rows", type=int, default=20_000_000, help="0 = skip the regex-pruning measurement")
+    ap.add_argument("--no-scans", action="store_true", help="skip the strings / regex / chunk-index measurements (BASELINE configs[2..4])")
+    ap.add_argument("--strings-rows", type=int, default=100_000_000, help="cfg3 shape: rows per GPU (0 = skip)")
+    ap.add_argument("--regex-rows", type=int, default=270_000_000, help="cfg4: values of the ONE ~10 GB file (37 bytes of payload each; 0 = skip)")
+    ap.add_argument("--chunk-rgs", type=int, default=64, help="cfg5 shape: alternating PLAIN / dictionary row groups of 5 M rows per GPU (64 = 6.4 GB; 0 = skip)")
+    ap.add_argument("--scan-steps", type=int, default=5)
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -590,9 +481,30 @@ def main():
                       "values_per_step": a.rows * ncols},
             "ingest": {"host_open_page_scan_s": open_s, "h2d_ms": h2d_ms, "h2d_GBps": size / (h2d_ms * 1e-3) / 1e9 if h2d_ms else None},
             "frac_of_hbm_peak_in_plus_out": (bytes_in + bytes_out) * world / (ms_per_step * 1e-3) / 1e9 / (peak * world)}
-    if rank == 0 and world == 1 and a.regex_rows > 0:
-        torch.cuda.empty_cache()
-        line["regex"] = regex_bench(pq, local, stream, a.steps, warmup, peak, a.regex_rows, 1_250_000)
+    # BASELINE configs[2..4] next to the headline, at every N (bench_scans.py)
+    del outs, host
+    torch.cuda.empty_cache()
+    if not a.no_scans:
+        import bench_scans as bs
+        dd = bs.Dist(rank, world)
+        psrc = roofline["peak_source"]
+        want_cpu = world == 1 and not a.no_cpu_baseline
+        scan_steps = max(1, min(a.scan_steps, a.steps))
+        if a.strings_rows > 0:
+            t0 = time.time()
+            line_strings = bs.strings_bench(pq, local, stream, dd, scan_steps, warmup, peak, psrc, a.strings_rows, min(a.rg_rows, a.strings_rows), want_cpu)
+            line_strings["wall_s"] = time.time() - t0
+            line["strings"] = line_strings
+        if a.regex_rows > 0:
+            t0 = time.time()
+            line_regex = bs.regex_bench(pq, local, stream, dd, scan_steps, warmup, peak, psrc, a.regex_rows, min(1_250_000, a.regex_rows), want_cpu)
+            line_regex["wall_s"] = time.time() - t0
+            line["regex"] = line_regex
+        if a.chunk_rgs > 0:
+            t0 = time.time()
+            line_ci = bs.chunk_index_bench(pq, local, stream, dd, min(scan_steps, 3), 1, peak, psrc, a.chunk_rgs, 5_000_000 if a.rows >= 50_000_000 else 500_000, want_cpu)
+            line_ci["wall_s"] = time.time() - t0
+            line["chunk_index"] = line_ci
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         try:
             r = cpu_reference_run(pq, cols, a.rows, a.rg_rows, a.cpu_sample_rgs, 1, 0, cores)

@@ -125,7 +125,8 @@ PQG_SYMBOLS = [
     "pqg_plan_value_width", "pqg_plan_values", "pqg_plan_validity", "pqg_plan_offsets", "pqg_plan_chars",
     "pqg_plan_chars_size", "pqg_plan_char_bases", "pqg_plan_bytes_in", "pqg_plan_bytes_out", "pqg_plan_download",
     "pqg_regex_compile", "pqg_dfa_free", "pqg_dfa_num_states", "pqg_dfa_match_host", "pqg_regex_scan",
-    "pqg_chunk_index", "pqg_page_chunk_index",
+    "pqg_chunk_index", "pqg_page_chunk_index", "pqg_chunk_index_prepare", "pqg_chunk_index_stitch", "pqg_chunk_index_emit",
+    "pqg_chunk_job_ids", "pqg_chunk_job_total_weight", "pqg_chunk_job_free",
 ]
 PQR_SYMBOLS = [
     "pqr_last_error", "pqr_open", "pqr_open_memory", "pqr_close", "pqr_num_rows", "pqr_num_row_groups",
@@ -135,9 +136,11 @@ PQR_SYMBOLS = [
     "pqr_string_iterator_dump", "pqr_valdump_free", "pqr_pagedump_free", "pqr_strdump_free", "pqr_read_columnar",
     "pqr_columnar_free", "pqr_read_columns_into", "pqr_read_dictionary_indices_into", "pqr_chunk_dictionary", "pqr_release_plans", "pqr_column_tables", "pqr_columns_tables", "pqr_tables_free", "pqr_chunk_index", "pqr_regex_prune",
     "pqr_page_chunk_index", "pqr_shard_row_groups", "pqr_regex_prune_rgs", "pqr_chunk_index_rgs", "pqr_read_columns_into_rgs",
+    "pqr_chunk_index_prepare_rgs", "pqr_chunk_index_stitch", "pqr_chunk_index_emit", "pqr_chunk_job_free", "pqr_column_tables_rgs",
 ]
 
-PQGEN_SYMBOLS = ["pqgen_last_error", "pqgen_encode", "pqgen_size", "pqgen_emit", "pqgen_write_file", "pqgen_free"]
+PQGEN_SYMBOLS = ["pqgen_last_error", "pqgen_encode", "pqgen_size", "pqgen_emit", "pqgen_write_file", "pqgen_free", "pqgen_string_len", "pqgen_fill_strings"]
+PQGEN_EMAILS, PQGEN_CITY64K = 0, 1
 
 _lib = None
 
@@ -203,6 +206,12 @@ def _declare(L):
     d("pqg_regex_scan", i32, vp, vp, vp, i32, vp, C.POINTER(C.c_float))
     d("pqg_chunk_index", i32, vp, vp, u64, u64, u32, vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(C.c_float))
     d("pqg_page_chunk_index", i32, vp, vp, u32, u64, vp, vp, vp, u32, C.POINTER(u32))
+    d("pqg_chunk_index_prepare", i32, vp, vp, u64, C.POINTER(vp), C.POINTER(C.c_float))
+    d("pqg_chunk_index_stitch", i32, vp, vp, u64, C.POINTER(u64), C.POINTER(u64))
+    d("pqg_chunk_index_emit", i32, vp, vp, u32, vp, C.POINTER(C.c_float))
+    d("pqg_chunk_job_ids", vp, vp)
+    d("pqg_chunk_job_total_weight", u64, vp)
+    d("pqg_chunk_job_free", None, vp, vp)
 
     d("pqgen_last_error", cp)
     d("pqgen_encode", vp, C.POINTER(GenCol), i32, vp, i32, i32)
@@ -210,6 +219,8 @@ def _declare(L):
     d("pqgen_emit", i32, vp, vp, u64)
     d("pqgen_write_file", i32, vp, cp)
     d("pqgen_free", None, vp)
+    d("pqgen_string_len", u32, i32)
+    d("pqgen_fill_strings", i32, i32, u64, u64, u64, vp, vp, u64, vp, u32, i32)
 
     d("pqr_last_error", cp)
     d("pqr_open", vp, cp, i32)
@@ -244,6 +255,11 @@ def _declare(L):
     d("pqr_regex_prune_rgs", i64, vp, i32, i64, i64, cp, i32, vp, i64, C.POINTER(C.c_float))
     d("pqr_chunk_index_rgs", i64, vp, cp, i64, i64, u64, u64, u32, vp, i64, C.POINTER(u64))
     d("pqr_read_columns_into_rgs", i32, vp, C.POINTER(C.c_int32), i32, i64, i64, C.POINTER(Dst), C.POINTER(ReadStats))
+    d("pqr_chunk_index_prepare_rgs", vp, vp, cp, i64, i64, u64, C.POINTER(u64), C.POINTER(C.c_float), C.POINTER(C.c_float))
+    d("pqr_chunk_index_stitch", i64, vp, u64, C.POINTER(u64))
+    d("pqr_chunk_index_emit", i32, vp, u32, vp, i64, C.POINTER(C.c_float))
+    d("pqr_chunk_job_free", None, vp)
+    d("pqr_column_tables_rgs", i32, vp, i32, i64, i64, C.POINTER(Tables))
     d("pqr_column_tables", i32, vp, i32, i32, C.POINTER(Tables))
     d("pqr_columns_tables", i32, vp, C.POINTER(C.c_int), i32, i32, C.POINTER(Tables))
     d("pqr_tables_free", None, C.POINTER(Tables))
@@ -441,6 +457,45 @@ class Reader:
         n = self._check(lib().pqr_chunk_index_rgs(self.h, name.encode(), rg_begin, rg_end, chunk_size, carry_in, id_base,
                                                   ids.ctypes.data, ids.size, C.byref(carry)))
         return ids[:rows], n, carry.value
+
+    # chunk index of a shard in phases (multi-GPU: prepare everywhere, stitch in shard order, emit everywhere)
+    def chunk_index_prepare_rgs(self, name, rg_begin, rg_end, chunk_size=4096):
+        """-> job dict(h, num_slots, decode_ms, prepare_ms): upload + decode + everything that needs no carry"""
+        slots, dms, pms = C.c_uint64(0), C.c_float(0), C.c_float(0)
+        h = lib().pqr_chunk_index_prepare_rgs(self.h, name.encode(), rg_begin, rg_end, chunk_size, C.byref(slots), C.byref(dms), C.byref(pms))
+        if not h:
+            raise PqgError(lib().pqr_last_error().decode())
+        return dict(h=h, num_slots=slots.value, decode_ms=dms.value, prepare_ms=pms.value)
+
+    def chunk_index_stitch(self, job, carry_in):
+        """-> (shard chunk count, carry_out); the only step ordered between shards"""
+        carry = C.c_uint64(0)
+        n = self._check(lib().pqr_chunk_index_stitch(job["h"], carry_in, C.byref(carry)))
+        return n, carry.value
+
+    def chunk_index_emit(self, job, id_base):
+        """-> chunk ids of the shard's rows (id_base + local id, nulls 0); frees the job"""
+        ids = np.zeros(job["num_slots"] + 1, dtype=np.uint32)
+        ms = C.c_float(0)
+        try:
+            self._check(lib().pqr_chunk_index_emit(job["h"], id_base, ids.ctypes.data, ids.size, C.byref(ms)))
+        finally:
+            lib().pqr_chunk_job_free(job["h"])
+            job["h"] = None
+        job["emit_ms"] = ms.value
+        return ids[:job["num_slots"]]
+
+    def column_tables_rgs(self, col, rg_begin, rg_end):
+        """descriptor tables of the row groups [rg_begin, rg_end) (file offsets)"""
+        t = Tables()
+        self._check(lib().pqr_column_tables_rgs(self.h, col, rg_begin, rg_end, C.byref(t)))
+        chunks = (ChunkDesc * max(t.n_chunks, 1))()
+        pages = (PageDesc * max(t.n_pages, 1))()
+        C.memmove(chunks, t.chunks, C.sizeof(ChunkDesc) * t.n_chunks)
+        C.memmove(pages, t.pages, C.sizeof(PageDesc) * t.n_pages)
+        out = (chunks, t.n_chunks, pages, t.n_pages, t.total_slots)
+        lib().pqr_tables_free(C.byref(t))
+        return out
 
     def read_columns_into_rgs(self, cols, dsts, rg_begin, rg_end):
         n = len(cols)
@@ -729,3 +784,22 @@ def generate(specs, columns, rg_rows, threads=0):
     if not job:
         raise PqgError(lib().pqgen_last_error().decode())
     return Generated(job)
+
+
+def synth_strings(kind, rows, seed, first_row=0, null_permille=0, threads=0, off_base=0, chars=None, str_off=None, is_null=None):
+    """native filler of the BASELINE string workloads (include/pqg_gen.h: pqgen_fill_strings) -> column dict for generate().
+    Buffers may be passed in (slices of larger arrays: mixed columns are filled row group by row group)."""
+    L = lib().pqgen_string_len(kind)
+    if chars is None:
+        chars = np.empty(max(rows * L, 1), dtype=np.uint8)
+    if str_off is None:
+        str_off = np.empty(rows + 1, dtype=np.uint64)
+    if is_null is None and null_permille:
+        is_null = np.empty(max(rows, 1), dtype=np.uint8)
+    if lib().pqgen_fill_strings(kind, first_row, rows, seed, chars.ctypes.data, str_off.ctypes.data, off_base,
+                                is_null.ctypes.data if is_null is not None else None, null_permille, threads) != 0:
+        raise PqgError(lib().pqgen_last_error().decode())
+    col = dict(str_off=str_off, chars=chars)
+    if is_null is not None:
+        col["is_null"] = is_null
+    return col

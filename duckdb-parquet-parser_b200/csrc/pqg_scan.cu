@@ -483,36 +483,40 @@ __global__ void k_chain_tiles(const uint64_t* P, uint64_t n, uint64_t S, uint64_
     ncand[t] = static_cast<uint32_t>(cnt);
 }
 
-// every candidate of every tile walks its tile: number of cuts inside, first cut after it
+// every candidate of every tile walks its tile: number of cuts inside, first cut after it, prefix value of the last cut inside
 __global__ void __launch_bounds__(128) k_chain_walk(const uint64_t* P, uint64_t n, uint64_t S, uint64_t L, const uint64_t* klo,
-                                                     const uint32_t* ncand, const uint64_t* cand_base, uint64_t* res_exit, uint32_t* res_cnt) {
+                                                     const uint32_t* ncand, const uint64_t* cand_base, uint64_t* res_exit, uint32_t* res_cnt,
+                                                     uint64_t* res_last) {
     const uint64_t t = blockIdx.x;
     const uint64_t end = (t + 1) * L;
     for (uint32_t j = threadIdx.x; j < ncand[t]; j += blockDim.x) {
-        uint64_t k = klo[t] + j;
+        uint64_t k = klo[t] + j, last = 0;
         uint32_t cnt = 0;
         while (k < n) {
             uint64_t pk = P[k];
             if (pk >= end) break;
             cnt++;
+            last = pk;
             k = lower_bound_from(P, n, k, pk + S);
         }
         res_exit[cand_base[t] + j] = k;
         res_cnt[cand_base[t] + j] = cnt;
+        res_last[cand_base[t] + j] = last;
     }
 }
 
-// first cut of the sequence: first slot with carry_in + P >= S
-// out[2] = number of slots that can still start a chunk: with zero-weight (null) slots masked,
-// the slots behind the last weighted one never do (the reference only cuts when a value follows)
-__global__ void k_chain_entry(const uint64_t* P, uint64_t n, uint64_t x0, bool mask_zero, uint64_t* out) {
+// out[0] = total weight, out[1] = number of slots that can still start a chunk: with zero-weight (null) slots
+// masked, the slots behind the last weighted one never do (the reference only cuts when a value follows)
+__global__ void k_chain_totals(const uint64_t* P, uint64_t n, bool mask_zero, uint64_t* out) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         const uint64_t total = P[n];
-        const uint64_t n_eff = mask_zero ? lower_bound_P(P, n, total) : n;
-        out[0] = lower_bound_P(P, n_eff, x0);
-        out[1] = total;
-        out[2] = n_eff;
+        out[0] = total;
+        out[1] = mask_zero ? lower_bound_P(P, n, total) : n;
     }
+}
+// first cut of the sequence: first slot with carry_in + P >= S, i.e. P >= x0
+__global__ void k_chain_entry(const uint64_t* P, uint64_t n_eff, uint64_t x0, uint64_t* out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) out[0] = lower_bound_P(P, n_eff, x0);
 }
 
 // materialise the cuts: tile t walks from its true entry
@@ -589,105 +593,138 @@ struct EventPair { // RAII: the timing events of one call
     ~EventPair() { if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); }
 };
 
-struct ChainOut {
-    uint64_t n_cuts = 0, total = 0, last_cut_P = 0;
-    uint64_t* d_P = nullptr;     // n + 1
-    uint64_t* d_cuts = nullptr;  // n_cuts
-    uint32_t launches = 0;
-};
-
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return e_; } while (0)
 
-// Greedy chunking of the weight sequence src(0..n): d_ids[i] = chunk id (shard local, the
-// open chunk carried in is id 0).  Synchronises the stream (the stitch runs on the host).
+// Greedy chunking of a weight sequence src(0..n), in three phases so that shards of one column (one per GPU)
+// overlap everything but a host loop:
+//   prepare  weights -> exclusive prefix sums P -> per weight-space tile the candidate first cuts -> every candidate
+//            walks its tile (cuts inside, exit, prefix value of its last cut).  Needs no carry: runs on all shards at once.
+//   stitch   the carry of the previous shard fixes the first cut (one lower bound on the device, 8 bytes back), then one
+//            table lookup per tile on the host -> number of cuts, carry for the next shard.  The only serial step.
+//   emit     cuts and chunk ids materialised on the device (runs on all shards at once again).
+struct ChainJob {
+    DevMem mem;
+    cudaStream_t s;
+    uint64_t n_all = 0, n = 0, S = 0, L = 0, T = 0, total = 0;
+    bool mask_zero = false;
+    uint64_t* d_P = nullptr;
+    uint64_t* d_entry = nullptr;
+    std::vector<uint64_t> klo, cand_base, r_exit, r_last, tile_entry, tile_base;
+    std::vector<uint32_t> ncand, r_cnt;
+    uint64_t n_cuts = 0, last_cut_P = 0, carry_in = 0;
+    bool stitched = false;
+    uint64_t* d_cuts = nullptr;
+    uint32_t* d_ids = nullptr; // n_all entries (after emit)
+    uint32_t launches = 0;
+    explicit ChainJob(cudaStream_t st) : mem(st), s(st) {}
+};
+
 template <class Src>
-cudaError_t run_chain(Src src, uint64_t n, uint64_t S, uint64_t carry_in, bool mask_zero, uint32_t id_base, uint32_t* d_ids, DevMem& mem,
-                      ChainOut& out, cudaStream_t s) {
+cudaError_t chain_prepare(ChainJob& J, Src src, uint64_t n, uint64_t S, bool mask_zero) {
+    cudaStream_t s = J.s;
+    J.n_all = n; J.S = S; J.mask_zero = mask_zero;
     const uint64_t nb = (n + kScanTile - 1) / kScanTile;
     uint64_t* d_sums = nullptr;
-    CK(mem.alloc(&d_sums, nb + 2));
-    CK(mem.alloc(&out.d_P, n + 1));
+    CK(J.mem.alloc(&d_sums, nb + 2));
+    CK(J.mem.alloc(&J.d_P, n + 1));
     if (nb) {
         k_scan_reduce<Src><<<static_cast<unsigned>(nb), kScanThreads, 0, s>>>(src, n, d_sums);
         k_scan_sums<<<1, kScanThreads, 0, s>>>(d_sums, nb);
-        k_scan_write<Src><<<static_cast<unsigned>(nb), kScanThreads, 0, s>>>(src, n, d_sums, out.d_P);
-        out.launches += 3;
+        k_scan_write<Src><<<static_cast<unsigned>(nb), kScanThreads, 0, s>>>(src, n, d_sums, J.d_P);
+        J.launches += 3;
     } else {
-        CK(cudaMemsetAsync(out.d_P, 0, 8, s));
+        CK(cudaMemsetAsync(J.d_P, 0, 8, s));
     }
-    const uint64_t x0 = carry_in >= S ? 0 : S - carry_in;
-    uint64_t* d_entry = nullptr;
-    CK(mem.alloc(&d_entry, 3));
-    k_chain_entry<<<1, 32, 0, s>>>(out.d_P, n, x0, mask_zero, d_entry);
-    out.launches++;
-    uint64_t h_entry[3];
-    CK(cudaMemcpyAsync(h_entry, d_entry, 24, cudaMemcpyDeviceToHost, s));
+    CK(J.mem.alloc(&J.d_entry, 2));
+    k_chain_totals<<<1, 32, 0, s>>>(J.d_P, n, mask_zero, J.d_entry);
+    J.launches++;
+    uint64_t h_tot[2];
+    CK(cudaMemcpyAsync(h_tot, J.d_entry, 16, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
-    out.total = h_entry[1];
-    const uint64_t n_all = n;
-    n = h_entry[2]; // the chain only sees slots that can start a chunk
-    const uint64_t L = S * kChainTileChunks;
-    const uint64_t T = out.total / L + 1;
+    J.total = h_tot[0];
+    J.n = h_tot[1]; // the chain only sees slots that can start a chunk
+    J.L = S * kChainTileChunks;
+    J.T = J.total / J.L + 1;
+    const uint64_t T = J.T;
     uint64_t* d_klo = nullptr; uint32_t* d_ncand = nullptr;
-    CK(mem.alloc(&d_klo, T + 1));
-    CK(mem.alloc(&d_ncand, T + 1));
-    k_chain_tiles<<<static_cast<unsigned>((T + 1 + 127) / 128), 128, 0, s>>>(out.d_P, n, S, L, T, d_klo, d_ncand);
-    out.launches++;
-    std::vector<uint64_t> klo(T + 1);
-    std::vector<uint32_t> ncand(T);
-    CK(cudaMemcpyAsync(klo.data(), d_klo, (T + 1) * 8, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(ncand.data(), d_ncand, T * 4, cudaMemcpyDeviceToHost, s));
+    CK(J.mem.alloc(&d_klo, T + 1));
+    CK(J.mem.alloc(&d_ncand, T + 1));
+    k_chain_tiles<<<static_cast<unsigned>((T + 1 + 127) / 128), 128, 0, s>>>(J.d_P, J.n, S, J.L, T, d_klo, d_ncand);
+    J.launches++;
+    J.klo.resize(T + 1);
+    J.ncand.resize(T);
+    CK(cudaMemcpyAsync(J.klo.data(), d_klo, (T + 1) * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(J.ncand.data(), d_ncand, T * 4, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
-    std::vector<uint64_t> cand_base(T + 1, 0);
-    for (uint64_t t = 0; t < T; t++) cand_base[t + 1] = cand_base[t] + ncand[t];
-    const uint64_t n_cand = cand_base[T];
-    uint64_t* d_cand_base = nullptr; uint64_t* d_exit = nullptr; uint32_t* d_cnt = nullptr;
-    CK(mem.alloc(&d_cand_base, T + 1));
-    CK(mem.alloc(&d_exit, n_cand));
-    CK(mem.alloc(&d_cnt, n_cand));
-    CK(cudaMemcpyAsync(d_cand_base, cand_base.data(), (T + 1) * 8, cudaMemcpyHostToDevice, s));
-    k_chain_walk<<<static_cast<unsigned>(T), 128, 0, s>>>(out.d_P, n, S, L, d_klo, d_ncand, d_cand_base, d_exit, d_cnt);
-    out.launches++;
-    std::vector<uint64_t> r_exit(n_cand);
-    std::vector<uint32_t> r_cnt(n_cand);
+    J.cand_base.assign(T + 1, 0);
+    for (uint64_t t = 0; t < T; t++) J.cand_base[t + 1] = J.cand_base[t] + J.ncand[t];
+    const uint64_t n_cand = J.cand_base[T];
+    uint64_t* d_cand_base = nullptr; uint64_t* d_exit = nullptr; uint32_t* d_cnt = nullptr; uint64_t* d_last = nullptr;
+    CK(J.mem.alloc(&d_cand_base, T + 1));
+    CK(J.mem.alloc(&d_exit, n_cand));
+    CK(J.mem.alloc(&d_cnt, n_cand));
+    CK(J.mem.alloc(&d_last, n_cand));
+    CK(cudaMemcpyAsync(d_cand_base, J.cand_base.data(), (T + 1) * 8, cudaMemcpyHostToDevice, s));
+    k_chain_walk<<<static_cast<unsigned>(T), 128, 0, s>>>(J.d_P, J.n, S, J.L, d_klo, d_ncand, d_cand_base, d_exit, d_cnt, d_last);
+    J.launches++;
+    J.r_exit.resize(n_cand); J.r_cnt.resize(n_cand); J.r_last.resize(n_cand);
     if (n_cand) {
-        CK(cudaMemcpyAsync(r_exit.data(), d_exit, n_cand * 8, cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(r_cnt.data(), d_cnt, n_cand * 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(J.r_exit.data(), d_exit, n_cand * 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(J.r_cnt.data(), d_cnt, n_cand * 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(J.r_last.data(), d_last, n_cand * 8, cudaMemcpyDeviceToHost, s));
     }
     CK(cudaStreamSynchronize(s));
-    // stitch: one lookup per tile
-    std::vector<uint64_t> tile_entry(T), tile_base(T + 1, 0);
-    uint64_t e = h_entry[0];
-    for (uint64_t t = 0; t < T; t++) {
-        tile_entry[t] = e;
-        tile_base[t + 1] = tile_base[t];
-        if (e < n && e >= klo[t] && e < klo[t + 1]) {
-            uint64_t j = e - klo[t];
-            if (j >= ncand[t]) return cudaErrorAssert; // cannot happen: an entry is always a candidate
-            tile_base[t + 1] += r_cnt[cand_base[t] + j];
-            e = r_exit[cand_base[t] + j];
+    return cudaGetLastError();
+}
+
+inline cudaError_t chain_stitch(ChainJob& J, uint64_t carry_in) {
+    cudaStream_t s = J.s;
+    const uint64_t x0 = carry_in >= J.S ? 0 : J.S - carry_in;
+    k_chain_entry<<<1, 32, 0, s>>>(J.d_P, J.n, x0, J.d_entry);
+    J.launches++;
+    uint64_t e = 0;
+    CK(cudaMemcpyAsync(&e, J.d_entry, 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const uint64_t T = J.T, n = J.n;
+    J.tile_entry.assign(T, 0);
+    J.tile_base.assign(T + 1, 0);
+    J.last_cut_P = 0;
+    for (uint64_t t = 0; t < T; t++) { // one lookup per tile
+        J.tile_entry[t] = e;
+        J.tile_base[t + 1] = J.tile_base[t];
+        if (e < n && e >= J.klo[t] && e < J.klo[t + 1]) {
+            const uint64_t j = e - J.klo[t];
+            if (j >= J.ncand[t]) return cudaErrorAssert; // cannot happen: an entry is always a candidate
+            const uint64_t ci = J.cand_base[t] + j;
+            if (J.r_cnt[ci]) J.last_cut_P = J.r_last[ci];
+            J.tile_base[t + 1] += J.r_cnt[ci];
+            e = J.r_exit[ci];
         }
     }
-    out.n_cuts = tile_base[T];
+    J.n_cuts = J.tile_base[T];
+    J.carry_in = carry_in;
+    J.stitched = true;
+    return cudaSuccess;
+}
+inline uint64_t chain_carry_out(const ChainJob& J) { return J.n_cuts ? J.total - J.last_cut_P : J.carry_in + J.total; }
+
+template <class Src>
+cudaError_t chain_emit(ChainJob& J, Src src, uint32_t id_base) {
+    cudaStream_t s = J.s;
+    const uint64_t T = J.T;
     uint64_t* d_tile_entry = nullptr; uint64_t* d_tile_base = nullptr;
-    CK(mem.alloc(&d_tile_entry, T));
-    CK(mem.alloc(&d_tile_base, T + 1));
-    CK(mem.alloc(&out.d_cuts, out.n_cuts));
-    CK(cudaMemcpyAsync(d_tile_entry, tile_entry.data(), T * 8, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(d_tile_base, tile_base.data(), (T + 1) * 8, cudaMemcpyHostToDevice, s));
-    k_chain_emit<<<static_cast<unsigned>((T + 127) / 128), 128, 0, s>>>(out.d_P, n, S, L, T, d_tile_entry, d_tile_base, out.d_cuts);
-    out.launches++;
-    if (n_all && d_ids) {
-        k_chain_ids<Src><<<static_cast<unsigned>((n_all + 2047) / 2048), 256, 0, s>>>(src, n_all, out.d_cuts, out.n_cuts, mask_zero, id_base, d_ids);
-        out.launches++;
+    CK(J.mem.alloc(&d_tile_entry, T));
+    CK(J.mem.alloc(&d_tile_base, T + 1));
+    CK(J.mem.alloc(&J.d_cuts, J.n_cuts));
+    CK(J.mem.alloc(&J.d_ids, J.n_all + 1));
+    CK(cudaMemcpyAsync(d_tile_entry, J.tile_entry.data(), T * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_tile_base, J.tile_base.data(), (T + 1) * 8, cudaMemcpyHostToDevice, s));
+    k_chain_emit<<<static_cast<unsigned>((T + 127) / 128), 128, 0, s>>>(J.d_P, J.n, J.S, J.L, T, d_tile_entry, d_tile_base, J.d_cuts);
+    J.launches++;
+    if (J.n_all) {
+        k_chain_ids<Src><<<static_cast<unsigned>((J.n_all + 2047) / 2048), 256, 0, s>>>(src, J.n_all, J.d_cuts, J.n_cuts, J.mask_zero, id_base, J.d_ids);
+        J.launches++;
     }
-    if (out.n_cuts) {
-        uint64_t last_slot = 0;
-        CK(cudaMemcpyAsync(&last_slot, out.d_cuts + out.n_cuts - 1, 8, cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));
-        CK(cudaMemcpyAsync(&out.last_cut_P, out.d_P + last_slot, 8, cudaMemcpyDeviceToHost, s));
-    }
-    CK(cudaStreamSynchronize(s));
     return cudaGetLastError();
 }
 
@@ -804,39 +841,96 @@ int pqg_regex_scan(pqg_ctx* ctx, pqg_plan* plan, const pqg_dfa* dfa, int neg, ui
     return PQG_OK;
 }
 
-int pqg_chunk_index(pqg_ctx* ctx, pqg_plan* plan, uint64_t chunk_size, uint64_t carry_in, uint32_t id_base, uint32_t* tuple_to_chunk,
-                    uint64_t* n_chunks, uint64_t* carry_out, float* kernel_ms) {
-    if (!ctx || !plan) return ctx_fail(ctx, PQG_ERR_ARG, "pqg_chunk_index: bad argument");
+// ---- tuple-level chunk index in phases (multi-GPU: prepare on every shard at once, stitch in shard order, emit at once) ----
+struct pqg_chunk_job {
+    ChainJob J;
+    StrWeights src{};
+    float prepare_ms = 0;
+    explicit pqg_chunk_job(cudaStream_t s) : J(s) {}
+};
+
+int pqg_chunk_index_prepare(pqg_ctx* ctx, pqg_plan* plan, uint64_t chunk_size, pqg_chunk_job** out, float* kernel_ms) {
+    if (!ctx || !plan || !out) return ctx_fail(ctx, PQG_ERR_ARG, "pqg_chunk_index_prepare: bad argument");
+    *out = nullptr;
     if (chunk_size == 0) return ctx_fail(ctx, PQG_ERR_ARG, "pqg_chunk_index: chunk_size must be > 0");
-    if (!plan_is_str(plan) || !plan_ran(plan)) return ctx_fail(ctx, PQG_ERR_ARG, "pqg_chunk_index: needs a decoded BYTE_ARRAY plan (pqg_plan_run + pqg_plan_finish first)");
+    if (!plan_is_str(plan) || !plan_ran(plan) || plan_run_pending(plan))
+        return ctx_fail(ctx, PQG_ERR_ARG, "pqg_chunk_index: needs a decoded BYTE_ARRAY plan (pqg_plan_run + pqg_plan_finish first)");
     CUF(ctx, cudaSetDevice(ctx_device(ctx)));
     cudaStream_t s = ctx_stream(ctx);
     DecodeParams P = plan_params(plan);
     const uint64_t n = plan_slots(plan);
-    DevMem mem(s);
-    uint64_t* d_rb = nullptr; uint32_t* d_ids = nullptr;
-    CUF(ctx, mem.alloc(&d_rb, P.n_chunks + 2));
-    CUF(ctx, mem.alloc(&d_ids, n + 1));
-    cudaEvent_t e0, e1;
-    CUF(ctx, cudaEventCreate(&e0));
-    CUF(ctx, cudaEventCreate(&e1));
-    CUF(ctx, cudaEventRecord(e0, s));
+    pqg_chunk_job* job = new (std::nothrow) pqg_chunk_job(s);
+    if (!job) return ctx_fail(ctx, PQG_ERR_NOMEM, "out of memory");
+    struct Guard { pqg_chunk_job* j; ~Guard() { delete j; } } g{job};
+    uint64_t* d_rb = nullptr;
+    CUF(ctx, job->J.mem.alloc(&d_rb, P.n_chunks + 2));
+    EventPair ev;
+    CUF(ctx, ev.create());
+    CUF(ctx, cudaEventRecord(ev.e0, s));
     k_chunk_row_bases<<<(P.n_chunks + 1 + 127) / 128, 128, 0, s>>>(P.chunks, P.n_chunks, n, d_rb);
-    StrWeights src{P.offsets, P.validity, d_rb, P.n_chunks};
-    ChainOut out;
-    cudaError_t ce = run_chain(src, n, chunk_size, carry_in, true, id_base, d_ids, mem, out, s);
+    job->src = StrWeights{P.offsets, P.validity, d_rb, P.n_chunks};
+    cudaError_t ce = chain_prepare(job->J, job->src, n, chunk_size, true);
     if (ce != cudaSuccess) return ctx_fail(ctx, PQG_ERR_CUDA, std::string("chunk index: ") + cudaGetErrorString(ce));
-    CUF(ctx, cudaEventRecord(e1, s));
-    if (tuple_to_chunk && n) CUF(ctx, cudaMemcpyAsync(tuple_to_chunk, d_ids, n * 4, cudaMemcpyDeviceToHost, s));
+    CUF(ctx, cudaEventRecord(ev.e1, s));
+    CUF(ctx, cudaStreamSynchronize(s));
+    cudaEventElapsedTime(&job->prepare_ms, ev.e0, ev.e1);
+    if (kernel_ms) *kernel_ms = job->prepare_ms;
+    g.j = nullptr;
+    *out = job;
+    return PQG_OK;
+}
+
+int pqg_chunk_index_stitch(pqg_ctx* ctx, pqg_chunk_job* job, uint64_t carry_in, uint64_t* n_chunks, uint64_t* carry_out) {
+    if (!ctx || !job) return ctx_fail(ctx, PQG_ERR_ARG, "pqg_chunk_index_stitch: bad argument");
+    CUF(ctx, cudaSetDevice(ctx_device(ctx)));
+    cudaError_t ce = chain_stitch(job->J, carry_in);
+    if (ce != cudaSuccess) return ctx_fail(ctx, PQG_ERR_CUDA, std::string("chunk index stitch: ") + cudaGetErrorString(ce));
+    if (n_chunks) *n_chunks = job->J.n_cuts + 1;
+    if (carry_out) *carry_out = chain_carry_out(job->J);
+    return PQG_OK;
+}
+
+int pqg_chunk_index_emit(pqg_ctx* ctx, pqg_chunk_job* job, uint32_t id_base, uint32_t* tuple_to_chunk, float* kernel_ms) {
+    if (!ctx || !job) return ctx_fail(ctx, PQG_ERR_ARG, "pqg_chunk_index_emit: bad argument");
+    if (!job->J.stitched) return ctx_fail(ctx, PQG_ERR_ARG, "pqg_chunk_index_emit: call pqg_chunk_index_stitch first");
+    CUF(ctx, cudaSetDevice(ctx_device(ctx)));
+    cudaStream_t s = job->J.s;
+    EventPair ev;
+    CUF(ctx, ev.create());
+    CUF(ctx, cudaEventRecord(ev.e0, s));
+    cudaError_t ce = chain_emit(job->J, job->src, id_base);
+    if (ce != cudaSuccess) return ctx_fail(ctx, PQG_ERR_CUDA, std::string("chunk index emit: ") + cudaGetErrorString(ce));
+    CUF(ctx, cudaEventRecord(ev.e1, s));
+    if (tuple_to_chunk && job->J.n_all) CUF(ctx, cudaMemcpyAsync(tuple_to_chunk, job->J.d_ids, job->J.n_all * 4, cudaMemcpyDeviceToHost, s));
     CUF(ctx, cudaStreamSynchronize(s));
     float ms = 0;
-    cudaEventElapsedTime(&ms, e0, e1);
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaEventElapsedTime(&ms, ev.e0, ev.e1);
     if (kernel_ms) *kernel_ms = ms;
-    if (n_chunks) *n_chunks = out.n_cuts + 1;
-    if (carry_out) *carry_out = out.n_cuts ? out.total - out.last_cut_P : carry_in + out.total;
-    ctx_add_launches(ctx, out.launches + 1);
+    ctx_add_launches(ctx, job->J.launches + 1);
+    job->J.launches = 0;
     return PQG_OK;
+}
+
+const uint32_t* pqg_chunk_job_ids(const pqg_chunk_job* job) { return job ? job->J.d_ids : nullptr; }
+uint64_t pqg_chunk_job_total_weight(const pqg_chunk_job* job) { return job ? job->J.total : 0; }
+
+void pqg_chunk_job_free(pqg_ctx* ctx, pqg_chunk_job* job) {
+    if (!job) return;
+    if (ctx) cudaSetDevice(ctx_device(ctx));
+    delete job;
+}
+
+int pqg_chunk_index(pqg_ctx* ctx, pqg_plan* plan, uint64_t chunk_size, uint64_t carry_in, uint32_t id_base, uint32_t* tuple_to_chunk,
+                    uint64_t* n_chunks, uint64_t* carry_out, float* kernel_ms) {
+    pqg_chunk_job* job = nullptr;
+    float ms0 = 0, ms1 = 0;
+    int rc = pqg_chunk_index_prepare(ctx, plan, chunk_size, &job, &ms0);
+    if (rc != PQG_OK) return rc;
+    rc = pqg_chunk_index_stitch(ctx, job, carry_in, n_chunks, carry_out);
+    if (rc == PQG_OK) rc = pqg_chunk_index_emit(ctx, job, id_base, tuple_to_chunk, &ms1);
+    pqg_chunk_job_free(ctx, job);
+    if (kernel_ms) *kernel_ms = ms0 + ms1;
+    return rc;
 }
 
 int pqg_page_chunk_index(pqg_ctx* ctx, const uint32_t* page_sizes, uint32_t n_pages, uint64_t chunk_size, uint32_t* page_chunk,
@@ -847,32 +941,32 @@ int pqg_page_chunk_index(pqg_ctx* ctx, const uint32_t* page_sizes, uint32_t n_pa
     if (n_pages == 0) return PQG_OK;
     CUF(ctx, cudaSetDevice(ctx_device(ctx)));
     cudaStream_t s = ctx_stream(ctx);
-    DevMem mem(s);
-    uint32_t* d_w = nullptr; uint32_t* d_ids = nullptr; uint32_t* d_off = nullptr; uint32_t* d_first = nullptr;
-    CUF(ctx, mem.alloc(&d_w, n_pages));
-    CUF(ctx, mem.alloc(&d_ids, n_pages));
-    CUF(ctx, mem.alloc(&d_off, n_pages));
+    ChainJob J(s);
+    uint32_t* d_w = nullptr; uint32_t* d_off = nullptr; uint32_t* d_first = nullptr;
+    CUF(ctx, J.mem.alloc(&d_w, n_pages));
+    CUF(ctx, J.mem.alloc(&d_off, n_pages));
     CUF(ctx, cudaMemcpyAsync(d_w, page_sizes, static_cast<size_t>(n_pages) * 4, cudaMemcpyHostToDevice, s));
     ArrWeights src{d_w};
-    ChainOut out;
     // the first page never closes a chunk (there is nothing to close): carry_in = 0
-    cudaError_t ce = run_chain(src, n_pages, chunk_size, 0, false, 0, d_ids, mem, out, s);
+    cudaError_t ce = chain_prepare(J, src, n_pages, chunk_size, false);
+    if (ce == cudaSuccess) ce = chain_stitch(J, 0);
+    if (ce == cudaSuccess) ce = chain_emit(J, src, 0);
     if (ce != cudaSuccess) return ctx_fail(ctx, PQG_ERR_CUDA, std::string("page chunk index: ") + cudaGetErrorString(ce));
-    k_page_offsets<<<(n_pages + 255) / 256, 256, 0, s>>>(out.d_P, n_pages, d_ids, out.d_cuts, d_off);
-    if (page_chunk) CUF(ctx, cudaMemcpyAsync(page_chunk, d_ids, static_cast<size_t>(n_pages) * 4, cudaMemcpyDeviceToHost, s));
+    k_page_offsets<<<(n_pages + 255) / 256, 256, 0, s>>>(J.d_P, n_pages, J.d_ids, J.d_cuts, d_off);
+    if (page_chunk) CUF(ctx, cudaMemcpyAsync(page_chunk, J.d_ids, static_cast<size_t>(n_pages) * 4, cudaMemcpyDeviceToHost, s));
     if (page_off) CUF(ctx, cudaMemcpyAsync(page_off, d_off, static_cast<size_t>(n_pages) * 4, cudaMemcpyDeviceToHost, s));
     if (chunk_first_page && cap) {
         chunk_first_page[0] = 0;
-        uint64_t take = std::min<uint64_t>(out.n_cuts, cap - 1);
+        uint64_t take = std::min<uint64_t>(J.n_cuts, cap - 1);
         if (take) {
-            CUF(ctx, mem.alloc(&d_first, take));
-            k_narrow<<<static_cast<unsigned>((take + 255) / 256), 256, 0, s>>>(out.d_cuts, take, d_first);
+            CUF(ctx, J.mem.alloc(&d_first, take));
+            k_narrow<<<static_cast<unsigned>((take + 255) / 256), 256, 0, s>>>(J.d_cuts, take, d_first);
             CUF(ctx, cudaMemcpyAsync(chunk_first_page + 1, d_first, take * 4, cudaMemcpyDeviceToHost, s));
         }
     }
     CUF(ctx, cudaStreamSynchronize(s));
-    if (n_chunks) *n_chunks = static_cast<uint32_t>(out.n_cuts + 1);
-    ctx_add_launches(ctx, out.launches + 2);
+    if (n_chunks) *n_chunks = static_cast<uint32_t>(J.n_cuts + 1);
+    ctx_add_launches(ctx, J.launches + 2);
     return PQG_OK;
 }
 

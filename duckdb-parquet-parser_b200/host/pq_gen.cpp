@@ -457,4 +457,53 @@ int pqgen_write_file(const pqgen_job* job, const char* path) {
 
 void pqgen_free(pqgen_job* job) { delete job; }
 
+static inline uint64_t splitmix64(uint64_t x) {
+    x += 0x9e3779b97f4a7c15ULL;
+    x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ULL;
+    x = (x ^ (x >> 27)) * 0x94d049bb133111ebULL;
+    return x ^ (x >> 31);
+}
+
+uint32_t pqgen_string_len(int32_t kind) { return kind == PQGEN_EMAILS ? 33u : (kind == PQGEN_CITY64K ? 13u : 0u); }
+
+int pqgen_fill_strings(int32_t kind, uint64_t first_row, uint64_t rows, uint64_t seed, uint8_t* chars, uint64_t* str_off,
+                       uint64_t off_base, uint8_t* is_null, uint32_t null_permille, int32_t threads) {
+    const uint32_t L = pqgen_string_len(kind);
+    if (!L || (!chars && rows)) { g_err = "pqgen_fill_strings: bad argument"; return -1; }
+    int nt = threads > 0 ? threads : static_cast<int>(std::thread::hardware_concurrency());
+    if (nt < 1) nt = 1;
+    const uint64_t per = (rows + static_cast<uint64_t>(nt) - 1) / static_cast<uint64_t>(nt);
+    auto work = [&](uint64_t a, uint64_t b) {
+        for (uint64_t i = a; i < b; i++) {
+            const uint64_t row = first_row + i;
+            const uint64_t r = splitmix64(seed * 0x100000001b3ULL + row);
+            uint8_t* d = chars + i * L;
+            if (kind == PQGEN_EMAILS) {
+                std::memcpy(d, "user000000000@mail000.example.com", 33);
+                uint64_t u = 100000000ULL + (r % 900000000ULL);
+                for (int k = 12; k >= 4; k--) { d[k] = static_cast<uint8_t>('0' + u % 10); u /= 10; }
+                uint32_t m = static_cast<uint32_t>((r >> 40) % 1000u);
+                for (int k = 20; k >= 18; k--) { d[k] = static_cast<uint8_t>('0' + m % 10); m /= 10; }
+                const uint64_t blk = row / 2000;
+                if (blk % 5 == 3) { if ((blk / 5) % 2 == 0) d[13] = '.'; else d[32] = '!'; }
+            } else {
+                std::memcpy(d, "city_000000_x", 13);
+                uint32_t c = static_cast<uint32_t>(r & 0xffffu);
+                for (int k = 10; k >= 5; k--) { d[k] = static_cast<uint8_t>('0' + c % 10); c /= 10; }
+            }
+            if (str_off) str_off[i] = off_base + i * L;
+            if (is_null) is_null[i] = (splitmix64(r ^ 0x5bd1e995ULL) % 1000u) < null_permille ? 1 : 0;
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nt; t++) {
+        const uint64_t a = std::min(rows, per * static_cast<uint64_t>(t)), b = std::min(rows, a + per);
+        if (a < b) pool.emplace_back(work, a, b);
+    }
+    work(0, std::min(rows, per));
+    for (auto& th : pool) th.join();
+    if (str_off) str_off[rows] = off_base + rows * L;
+    return 0;
+}
+
 } // extern "C"

@@ -4,6 +4,7 @@
 #include "pq_scan.hpp"
 
 #include <cstring>
+#include <memory>
 #include <stdexcept>
 #include <vector>
 
@@ -50,22 +51,49 @@ int64_t regex_prune_rgs(ParquetReader& r, int col, size_t rg_begin, size_t rg_en
     return static_cast<int64_t>(dp.n_pages);
 }
 
-int64_t chunk_index_rgs(ParquetReader& r, const std::string& col_name, size_t rg_begin, size_t rg_end, uint64_t chunk_size,
-                        uint64_t carry_in, uint32_t id_base, uint32_t* ids, int64_t cap, uint64_t* carry_out) {
+ChunkIndexJob::~ChunkIndexJob() { if (job) pqg_chunk_job_free(ctx, job); }
+
+ChunkIndexJob* chunk_index_prepare_rgs(ParquetReader& r, const std::string& col_name, size_t rg_begin, size_t rg_end, uint64_t chunk_size) {
     int col = string_column(r, col_name);
-    if (carry_out) *carry_out = carry_in;
     ParquetReader::DevicePlan dp = r.device_plan_range(col, rg_begin, rg_end, true);
-    if (!dp.plan) return 1; // no values: the open chunk only
+    auto j = std::make_unique<ChunkIndexJob>();
+    j->ctx = dp.ctx;
+    if (!dp.plan) return j.release(); // no values: the open chunk only
+    pqg_ctx_set_profiling(dp.ctx, 1);
     if (pqg_plan_run(dp.ctx, dp.plan) != PQG_OK) throw std::runtime_error(pqg_last_error(dp.ctx));
     pqg_page_error pe;
     if (pqg_plan_finish(dp.ctx, dp.plan, &pe) != PQG_OK) throw std::runtime_error(pqg_last_error(dp.ctx));
-    const uint64_t n = pqg_plan_num_slots(dp.plan);
-    if (static_cast<uint64_t>(cap) < n) throw std::runtime_error("chunk_index: output buffer too small");
-    uint64_t n_chunks = 0, carry = 0;
-    if (pqg_chunk_index(dp.ctx, dp.plan, chunk_size, carry_in, id_base, ids, &n_chunks, &carry, nullptr) != PQG_OK)
+    pqg_timings tm;
+    if (pqg_plan_timings(dp.plan, &tm) == PQG_OK) j->decode_ms = tm.total_ms;
+    j->num_slots = pqg_plan_num_slots(dp.plan);
+    if (pqg_chunk_index_prepare(dp.ctx, dp.plan, chunk_size, &j->job, &j->prepare_ms) != PQG_OK)
         throw std::runtime_error(pqg_last_error(dp.ctx));
+    return j.release();
+}
+
+int64_t chunk_index_stitch(ChunkIndexJob& j, uint64_t carry_in, uint64_t* carry_out) {
+    if (carry_out) *carry_out = carry_in;
+    if (!j.job) return 1;
+    uint64_t n_chunks = 0, carry = 0;
+    if (pqg_chunk_index_stitch(j.ctx, j.job, carry_in, &n_chunks, &carry) != PQG_OK) throw std::runtime_error(pqg_last_error(j.ctx));
     if (carry_out) *carry_out = carry;
     return static_cast<int64_t>(n_chunks);
+}
+
+void chunk_index_emit(ChunkIndexJob& j, uint32_t id_base, uint32_t* ids, int64_t cap, float* kernel_ms) {
+    if (kernel_ms) *kernel_ms = 0;
+    if (!j.job) return;
+    if (ids && static_cast<uint64_t>(cap) < j.num_slots) throw std::runtime_error("chunk_index: output buffer too small");
+    if (pqg_chunk_index_emit(j.ctx, j.job, id_base, ids, kernel_ms) != PQG_OK) throw std::runtime_error(pqg_last_error(j.ctx));
+}
+
+int64_t chunk_index_rgs(ParquetReader& r, const std::string& col_name, size_t rg_begin, size_t rg_end, uint64_t chunk_size,
+                        uint64_t carry_in, uint32_t id_base, uint32_t* ids, int64_t cap, uint64_t* carry_out) {
+    std::unique_ptr<ChunkIndexJob> j(chunk_index_prepare_rgs(r, col_name, rg_begin, rg_end, chunk_size));
+    if (j->job && static_cast<uint64_t>(cap) < j->num_slots) throw std::runtime_error("chunk_index: output buffer too small");
+    const int64_t n_chunks = chunk_index_stitch(*j, carry_in, carry_out);
+    chunk_index_emit(*j, id_base, ids, cap, nullptr);
+    return n_chunks;
 }
 
 int64_t chunk_index(ParquetReader& r, const std::string& col_name, uint64_t chunk_size, uint64_t* tuple_to_chunk, int64_t num_rows) {

@@ -32,6 +32,20 @@ int64_t regex_prune_rgs(ParquetReader& r, int col, size_t rg_begin, size_t rg_en
 int64_t chunk_index_rgs(ParquetReader& r, const std::string& col_name, size_t rg_begin, size_t rg_end, uint64_t chunk_size,
                         uint64_t carry_in, uint32_t id_base, uint32_t* tuple_to_chunk_local, int64_t cap, uint64_t* carry_out);
 
+// The same in phases (include/pqg.h: pqg_chunk_index_prepare / _stitch / _emit): `prepare` uploads and decodes the
+// shard and runs everything that does not need the previous shard's carry; only `stitch` is ordered between shards.
+struct ChunkIndexJob {
+    pqg_ctx* ctx = nullptr;
+    pqg_chunk_job* job = nullptr;   // null: the shard has no values
+    uint64_t num_slots = 0;
+    float decode_ms = 0, prepare_ms = 0;
+    ~ChunkIndexJob();
+};
+ChunkIndexJob* chunk_index_prepare_rgs(ParquetReader& r, const std::string& col_name, size_t rg_begin, size_t rg_end, uint64_t chunk_size);
+// returns the shard's chunk count (local ids 0 .. count-1)
+int64_t chunk_index_stitch(ChunkIndexJob& j, uint64_t carry_in, uint64_t* carry_out);
+void chunk_index_emit(ChunkIndexJob& j, uint32_t id_base, uint32_t* ids, int64_t cap, float* kernel_ms);
+
 int64_t page_chunk_index(ParquetReader& r, int col, uint64_t chunk_size, uint32_t* page_chunk,
                          uint32_t* page_off, uint32_t* chunk_first_page, int64_t cap,
                          int64_t* first_global_page, int64_t* n_col_pages);

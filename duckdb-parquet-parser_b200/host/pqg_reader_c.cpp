@@ -330,6 +330,32 @@ int64_t pqr_chunk_index_rgs(pqr_reader* r, const char* name, int64_t rg_begin, i
     }, -1);
 }
 
+pqr_chunk_job* pqr_chunk_index_prepare_rgs(pqr_reader* r, const char* name, int64_t rg_begin, int64_t rg_end, uint64_t chunk_size,
+                                           uint64_t* num_slots, float* decode_ms, float* prepare_ms) {
+    return guarded([&]() -> pqr_chunk_job* {
+        if (rg_begin < 0 || rg_end < rg_begin) throw std::runtime_error("Invalid row group index");
+        ChunkIndexJob* j = chunk_index_prepare_rgs(r->r, name, static_cast<size_t>(rg_begin), static_cast<size_t>(rg_end), chunk_size);
+        if (num_slots) *num_slots = j->num_slots;
+        if (decode_ms) *decode_ms = j->decode_ms;
+        if (prepare_ms) *prepare_ms = j->prepare_ms;
+        return reinterpret_cast<pqr_chunk_job*>(j);
+    }, static_cast<pqr_chunk_job*>(nullptr));
+}
+int64_t pqr_chunk_index_stitch(pqr_chunk_job* job, uint64_t carry_in, uint64_t* carry_out) {
+    return guarded([&]() -> int64_t {
+        if (!job) throw std::runtime_error("pqr_chunk_index_stitch: no job");
+        return chunk_index_stitch(*reinterpret_cast<ChunkIndexJob*>(job), carry_in, carry_out);
+    }, static_cast<int64_t>(-1));
+}
+int pqr_chunk_index_emit(pqr_chunk_job* job, uint32_t id_base, uint32_t* ids, int64_t cap, float* kernel_ms) {
+    return guarded([&]() -> int {
+        if (!job) throw std::runtime_error("pqr_chunk_index_emit: no job");
+        chunk_index_emit(*reinterpret_cast<ChunkIndexJob*>(job), id_base, ids, cap, kernel_ms);
+        return 0;
+    }, -1);
+}
+void pqr_chunk_job_free(pqr_chunk_job* job) { delete reinterpret_cast<ChunkIndexJob*>(job); }
+
 void pqr_columnar_free(pqr_columnar* c) {
     if (c && c->owner) delete static_cast<ColumnarOwner*>(c->owner);
     if (c) std::memset(c, 0, sizeof(*c));
@@ -340,6 +366,21 @@ int pqr_column_tables(const pqr_reader* r, int col, int rg, pqr_tables* out) {
         if (col < 0 || col >= static_cast<int>(r->r.num_columns())) throw std::runtime_error("Invalid column index");
         if (rg >= static_cast<int>(r->r.num_row_groups())) throw std::runtime_error("Invalid row group index");
         ColumnTables t = r->r.column_tables(col, rg);
+        out->n_chunks = static_cast<uint32_t>(t.chunks.size());
+        out->n_pages = static_cast<uint32_t>(t.pages.size());
+        out->total_slots = t.total_slots;
+        out->chunks = static_cast<pqg_chunk_desc*>(std::malloc(sizeof(pqg_chunk_desc) * (t.chunks.size() + 1)));
+        out->pages = static_cast<pqg_page_desc*>(std::malloc(sizeof(pqg_page_desc) * (t.pages.size() + 1)));
+        std::memcpy(out->chunks, t.chunks.data(), sizeof(pqg_chunk_desc) * t.chunks.size());
+        std::memcpy(out->pages, t.pages.data(), sizeof(pqg_page_desc) * t.pages.size());
+        return 0;
+    }, -1);
+}
+int pqr_column_tables_rgs(const pqr_reader* r, int col, int64_t rg_begin, int64_t rg_end, pqr_tables* out) {
+    return guarded([&]() -> int {
+        if (col < 0 || col >= static_cast<int>(r->r.num_columns())) throw std::runtime_error("Invalid column index");
+        if (rg_begin < 0 || rg_end < rg_begin || rg_end > static_cast<int64_t>(r->r.num_row_groups())) throw std::runtime_error("Invalid row group index");
+        ColumnTables t = r->r.column_tables_range(col, static_cast<size_t>(rg_begin), static_cast<size_t>(rg_end));
         out->n_chunks = static_cast<uint32_t>(t.chunks.size());
         out->n_pages = static_cast<uint32_t>(t.pages.size());
         out->total_slots = t.total_slots;

@@ -261,6 +261,21 @@ PQG_API int pqg_regex_scan(pqg_ctx* ctx, pqg_plan* plan, const pqg_dfa* dfa, int
 PQG_API int pqg_chunk_index(pqg_ctx* ctx, pqg_plan* plan, uint64_t chunk_size, uint64_t carry_in,
                             uint32_t id_base, uint32_t* tuple_to_chunk, uint64_t* n_chunks,
                             uint64_t* carry_out, float* kernel_ms);
+/* The same in three phases, for shards of ONE column decoded on several GPUs (SURVEY.md section 8 e): everything that
+ * is heavy -- weights, prefix sums, the speculative walks (prepare) and the materialisation of cuts and ids (emit) --
+ * needs no knowledge of the other shards and runs on all GPUs at once; only `stitch` (one 8-byte device lookup + one
+ * table lookup per 256 KB of weight on the host) runs in shard order, handing carry_out / chunk counts to the next shard:
+ *     prepare(shard r) on every r   ->   for r = 0..: stitch(r, carry_in = carry_out(r-1))   ->   emit(r, id_base_r) on every r
+ * with id_base_r = sum over earlier shards of (n_chunks - 1).  pqg_chunk_index == prepare + stitch + emit. */
+typedef struct pqg_chunk_job pqg_chunk_job;
+PQG_API int pqg_chunk_index_prepare(pqg_ctx* ctx, pqg_plan* plan, uint64_t chunk_size, pqg_chunk_job** out, float* kernel_ms);
+PQG_API int pqg_chunk_index_stitch(pqg_ctx* ctx, pqg_chunk_job* job, uint64_t carry_in, uint64_t* n_chunks, uint64_t* carry_out);
+/* tuple_to_chunk: HOST array of num_slots uint32, or NULL to keep the ids on the device (pqg_chunk_job_ids) */
+PQG_API int pqg_chunk_index_emit(pqg_ctx* ctx, pqg_chunk_job* job, uint32_t id_base, uint32_t* tuple_to_chunk, float* kernel_ms);
+PQG_API const uint32_t* pqg_chunk_job_ids(const pqg_chunk_job* job);       /* device pointer, valid after emit */
+PQG_API uint64_t pqg_chunk_job_total_weight(const pqg_chunk_job* job);     /* sum of the shard's weights */
+PQG_API void pqg_chunk_job_free(pqg_ctx* ctx, pqg_chunk_job* job);
+
 /* Page-level map (index_test): pages packed greedily by payload size in page-table order.
  * HOST outputs: page_chunk[n_pages], page_off[n_pages], chunk_first_page[cap]. */
 PQG_API int pqg_page_chunk_index(pqg_ctx* ctx, const uint32_t* page_sizes, uint32_t n_pages,

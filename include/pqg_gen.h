@@ -56,6 +56,19 @@ PQG_API int pqgen_emit(const pqgen_job* job, uint8_t* dst, uint64_t cap); /* 0 =
 PQG_API int pqgen_write_file(const pqgen_job* job, const char* path);
 PQG_API void pqgen_free(pqgen_job* job);
 
+/* Synthetic BYTE_ARRAY columns of the BASELINE.json configurations, filled natively (multi-threaded; row i of the
+ * file depends on (kind, seed, first_row + i) only, so shards generated apart agree with the whole):
+ *   PQGEN_EMAILS   configs[3]: "user<9 digits>@mail<3 digits>.example.com" (33 bytes); rows in blocks of 2000, every
+ *                  fifth block is noise -- alternately without '@' ('.' instead) and ending in ".co!" -- so that whole
+ *                  pages fail the anchored e-mail pattern and both polarities of the predicate prune pages
+ *   PQGEN_CITY64K  configs[2]: "city_<6 digits>_x" (13 bytes), 65 536 distinct values, uniform
+ * All strings of a kind have one length (pqgen_string_len): chars receives rows * len bytes, str_off (may be NULL)
+ * rows + 1 offsets starting at off_base; is_null (may be NULL) gets 1 with probability null_permille / 1000. */
+enum { PQGEN_EMAILS = 0, PQGEN_CITY64K = 1 };
+PQG_API uint32_t pqgen_string_len(int32_t kind);
+PQG_API int pqgen_fill_strings(int32_t kind, uint64_t first_row, uint64_t rows, uint64_t seed, uint8_t* chars, uint64_t* str_off,
+                               uint64_t off_base, uint8_t* is_null, uint32_t null_permille, int32_t threads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -200,6 +200,16 @@ PQG_API int64_t pqr_regex_prune_rgs(pqr_reader* r, int col, int64_t rg_begin, in
  * id_base + n - 1, carry_in = carry_out), <0 on error */
 PQG_API int64_t pqr_chunk_index_rgs(pqr_reader* r, const char* name, int64_t rg_begin, int64_t rg_end, uint64_t chunk_size,
                                     uint64_t carry_in, uint32_t id_base, uint32_t* ids, int64_t cap, uint64_t* carry_out);
+/* chunk index of a shard in phases (pqg.h: pqg_chunk_index_prepare / _stitch / _emit): prepare on every shard at once,
+ * stitch in shard order (microseconds, host), emit on every shard at once */
+typedef struct pqr_chunk_job pqr_chunk_job;
+PQG_API pqr_chunk_job* pqr_chunk_index_prepare_rgs(pqr_reader* r, const char* name, int64_t rg_begin, int64_t rg_end, uint64_t chunk_size,
+                                                   uint64_t* num_slots, float* decode_ms, float* prepare_ms);
+PQG_API int64_t pqr_chunk_index_stitch(pqr_chunk_job* job, uint64_t carry_in, uint64_t* carry_out); /* the shard's chunk count, <0 on error */
+PQG_API int pqr_chunk_index_emit(pqr_chunk_job* job, uint32_t id_base, uint32_t* ids, int64_t cap, float* kernel_ms);
+PQG_API void pqr_chunk_job_free(pqr_chunk_job* job);
+/* descriptor tables of the row groups [rg_begin, rg_end) of a column (file offsets) */
+PQG_API int pqr_column_tables_rgs(const pqr_reader* r, int col, int64_t rg_begin, int64_t rg_end, pqr_tables* out);
 PQG_API int pqr_read_columns_into_rgs(pqr_reader* r, const int32_t* cols, int32_t n_cols, int64_t rg_begin, int64_t rg_end,
                                       const pqr_dst* dsts, pqr_read_stats* stats);
 

@@ -53,21 +53,30 @@ class OracleOps:
         a, b = sum(per[:rg0]), sum(per[:rg1])
         return bits[a:b], 0.0
 
-    def chunk_index_rgs(self, name, rg0, rg1, chunk_size=4096, carry_in=0, id_base=0):
+    # the phased chunk index (multi_gpu.chunk_index_sharded): prepare / stitch / emit
+    def chunk_index_prepare_rgs(self, name, rg0, rg1, chunk_size=4096):
         pos, off, _ = self.o.string_iterator(self.h, name)
         rows = [self.o.row_group_num_rows(self.h, rg) for rg in range(self.o.num_row_groups(self.h))]
         r0, r1 = sum(rows[:rg0]), sum(rows[:rg1])
-        ids = np.zeros(r1 - r0, dtype=np.uint32)
         lens = np.diff(off.astype(np.int64))
+        keep = (pos >= r0) & (pos < r1)
+        return dict(pos=pos[keep] - r0, lens=lens[keep], rows=r1 - r0, chunk_size=chunk_size)
+
+    def chunk_index_stitch(self, job, carry_in):
+        local = np.zeros(len(job["pos"]), dtype=np.uint32)
         bytes_, cid = carry_in, 0
-        for p, ln in zip(pos, lens):  # the loop of reference src/main.cpp:21-32 on the shard's values
-            if p < r0 or p >= r1:
-                continue
-            if bytes_ >= chunk_size:
+        for k, ln in enumerate(job["lens"]):  # the loop of reference src/main.cpp:21-32 on the shard's values
+            if bytes_ >= job["chunk_size"]:
                 bytes_, cid = 0, cid + 1
             bytes_ += len(str(int(ln))) + int(ln)
-            ids[p - r0] = id_base + cid
-        return ids, cid + 1, bytes_
+            local[k] = cid
+        job["local"] = local
+        return cid + 1, bytes_
+
+    def chunk_index_emit(self, job, id_base):
+        ids = np.zeros(job["rows"], dtype=np.uint32)
+        ids[job["pos"]] = id_base + job["local"]
+        return ids
 
 
 def _free_port():
