@@ -39,6 +39,8 @@ struct pqg_plan {
     DevChunk* d_chunks = nullptr;
     pqg_page_desc* d_pages = nullptr;
     uint8_t* d_dict = nullptr;
+    DictSeg* d_dict_segs = nullptr;  // BYTE_ARRAY plans: segment records of the dictionary preparation
+    uint32_t str_dict_blocks = 1;    // ... and its blocks of 256 threads per dictionary
     size_t dict_bytes = 0;
     TileDesc* d_tiles = nullptr;      // fast path: TMA-staged page tiles (fixed-width plans)
     uint32_t n_tiles = 0;
@@ -51,6 +53,7 @@ struct pqg_plan {
     // (payload - 4 * values), scans on the host, no size pass and no mid-run synchronisation;
     // the copy pass verifies every page and the plan falls back to the size pass on a mismatch
     bool host_sizes = false, force_exact = false;
+    bool chars_sized = false; // a finished run sized d_chars: later runs launch the copy pass without waiting for the size pass
     bool identity = false; // dictionary-form output of a BYTE_ARRAY column: uint32 dictionary indices per slot
     std::vector<uint32_t> chunk_tile_begin;  // n_chunks + 1: tiles of chunk c = [begin[c], begin[c+1])
     std::vector<uint32_t> chunk_slow_begin;  // n_chunks + 1: host-listed slow pages of chunk c
@@ -270,7 +273,7 @@ static uint8_t level_bw(int16_t m) { // ColumnReader::bit_width (column_reader.c
 void pqg_plan_destroy(pqg_ctx* ctx, pqg_plan* p) {
     if (!p) return;
     if (ctx) cudaSetDevice(ctx->device);
-    cudaFree(p->d_chunks); cudaFree(p->d_pages); cudaFree(p->d_dict); cudaFree(p->d_values);
+    cudaFree(p->d_chunks); cudaFree(p->d_pages); cudaFree(p->d_dict); cudaFree(p->d_dict_segs); cudaFree(p->d_values);
     cudaFree(p->d_validity); cudaFree(p->d_required_ranges); cudaFree(p->d_offsets); cudaFree(p->d_chars); cudaFree(p->d_page_chars);
     cudaFree(p->d_page_char_base); cudaFree(p->d_bases); cudaFree(p->d_err); cudaFree(p->d_tiles); cudaFree(p->d_slow_pages);
     if (p->h_bases) cudaFreeHost(p->h_bases);
@@ -346,7 +349,8 @@ static int plan_create_impl(pqg_ctx* ctx, const pqg_buf* image, const pqg_chunk_
     }
 
     std::vector<DevChunk> dc(n_chunks);
-    size_t arena = 0;
+    size_t arena = 0, n_segs = 0;
+    uint32_t max_segs = 0;
     uint64_t slots = 0;
     for (uint32_t c = 0; c < n_chunks; c++) {
         const pqg_chunk_desc& s = chunks[c];
@@ -375,6 +379,11 @@ static int plan_create_impl(pqg_ctx* ctx, const pqg_buf* image, const pqg_chunk_
                 if (p->is_str) { // 16-byte padded entries for short-string dictionaries (filled by the prepare kernel)
                     d.dict_pad_off = arena;
                     arena += static_cast<size_t>(s.dict_num_values) * 16 + 16;
+                    const uint32_t segs = (s.dict_size + kDictSeg - 1) / kDictSeg + 1;
+                    if (n_segs + segs > 0xffffffffull) return bail(PQG_ERR_UNSUPPORTED, "pqg_plan_create: more than 512 GB of dictionary pages in one plan");
+                    d.dict_seg_first = static_cast<uint32_t>(n_segs);
+                    n_segs += segs;
+                    max_segs = std::max(max_segs, segs);
                 }
             }
         }
@@ -502,6 +511,7 @@ static int plan_create_impl(pqg_ctx* ctx, const pqg_buf* image, const pqg_chunk_
     PA(p->d_pages, sizeof(pqg_page_desc) * std::max<size_t>(static_cast<size_t>(n_pages) + p->virt_pages.size(), 1));
     PA(p->d_err, sizeof(DevErr));
     if (p->any_dict) PA(p->d_dict, arena + 64);
+    if (p->any_dict && p->is_str) { PA(p->d_dict_segs, n_segs * sizeof(DictSeg)); p->str_dict_blocks = std::max<uint32_t>(1, std::min<uint32_t>(64, (max_segs + 255) / 256)); }
     // host-listed pages, then room for EVERY page to be handed over on the device (the big-page kernel re-lists host-listed pages)
     PA(p->d_slow_pages, sizeof(uint32_t) * (slow.size() + static_cast<size_t>(n_pages) + p->virt_pages.size() + 2));
     PA(p->d_tiles, sizeof(TileDesc) * std::max<size_t>(tiles.size(), 1));
@@ -576,7 +586,7 @@ static DecodeParams make_params(const pqg_plan* p) {
     P.chunks = p->d_chunks; P.pages = p->d_pages;
     P.page_begin = 0; P.page_end = static_cast<uint32_t>(p->pages.size());
     P.n_chunks = static_cast<uint32_t>(p->chunks.size());
-    P.dict_arena = p->d_dict; P.values = p->d_values; P.validity = p->d_validity; P.handover_hint = p->handover_seen;
+    P.dict_arena = p->d_dict; P.dict_segs = p->d_dict_segs; P.values = p->d_values; P.validity = p->d_validity; P.handover_hint = p->handover_seen;
     P.offsets = p->d_offsets; P.chars = p->d_chars;
     P.page_chars = p->d_page_chars; P.page_char_base = p->d_page_char_base; P.err = p->d_err;
     P.tiles = p->d_tiles; P.tile_lo = 0; P.tile_hi = p->n_tiles; P.dict_smem = p->dict_smem;
@@ -584,6 +594,7 @@ static DecodeParams make_params(const pqg_plan* p) {
     P.chunk_lo = 0;
     P.tile_bytes = p->tile_bytes;
     P.identity_dict = p->identity ? 1u : 0u;
+    P.exact_sizes = p->force_exact ? 1u : 0u;
     return P;
 }
 
@@ -616,7 +627,7 @@ static int fixed_subrun(pqg_ctx* ctx, pqg_plan* p, uint32_t c0, uint32_t c1, boo
     P.slow_lo = p->chunk_slow_begin[c0]; P.slow_hi = p->chunk_slow_begin[c1];
     bool any_dict = false;
     for (uint32_t c = c0; c < c1 && !p->identity; c++) any_dict = any_dict || p->chunks[c].has_dict; // dictionary-form plans keep no device dictionary
-    if (e == cudaSuccess && any_dict) { e = launch_dict_prepare(P, c1 - c0, p->width, p->max_dict_blocks, s); launches++; }
+    if (e == cudaSuccess && any_dict) { e = launch_dict_prepare(P, c1 - c0, p->width, p->max_dict_blocks, s); launches += static_cast<int>(dict_prepare_launches(p->width)); }
     if (e == cudaSuccess && ev_tiles_begin) e = cudaEventRecord(ev_tiles_begin, s);
     if (e == cudaSuccess && P.tile_hi > P.tile_lo) {
         {
@@ -709,8 +720,8 @@ int pqg_plan_run(pqg_ctx* ctx, pqg_plan* p) {
         if (prof) CU(ctx, cudaEventRecord(p->ev[3], s));
     } else {
         if (p->any_dict) {
-            CU(ctx, launch_dict_prepare(P, P.n_chunks, 0, 1, s));
-            launches++;
+            CU(ctx, launch_dict_prepare(P, P.n_chunks, 0, p->str_dict_blocks, s));
+            launches += dict_prepare_launches(0);
         }
         if (prof) CU(ctx, cudaEventRecord(p->ev[1], s));
         if (P.page_end) { CU(ctx, launch_str_sizes(P, ctx->sm_count, s)); launches++; }
@@ -718,7 +729,13 @@ int pqg_plan_run(pqg_ctx* ctx, pqg_plan* p) {
         launches += 2;
         CU(ctx, cudaMemcpyAsync(p->h_bases, p->d_bases, (P.n_chunks + 2) * 8, cudaMemcpyDeviceToHost, s));
         if (prof) CU(ctx, cudaEventRecord(p->ev[2], s));
-        {
+        if (p->chars_sized && p->d_chars) {
+            // the same plan ran before: reuse its chars buffer and do not wait for the size pass -- the copy kernel
+            // checks the grand total against the capacity on the device (PQG_PAGE_CHARS_CAP -> finish re-sizes and re-runs)
+            P.chars = p->d_chars;
+            P.chars_cap = p->chars_cap;
+            P.total_chars = p->d_bases + P.n_chunks + 1;
+        } else {
             // the output size is data dependent: wait for the size pass, (re)allocate if needed
             CU(ctx, cudaStreamSynchronize(s));
             uint64_t total = p->h_bases[P.n_chunks + 1];
@@ -771,6 +788,7 @@ int pqg_plan_finish(pqg_ctx* ctx, pqg_plan* p, pqg_page_error* err) {
     }
     p->run_pending = false;
     if (p->timed) elapsed_of(p, p->ev, &p->tm);
+    if (p->is_str && !(p->host_sizes && !p->force_exact) && p->ran) p->chars_size = p->h_bases[p->chunks.size() + 1]; // of the run that just finished
     if (p->is_str) {
         uint64_t slots = p->n_slots;
         p->bytes_out = p->chars_size + 4 * (slots + p->chunks.size()) + (p->any_def ? (slots + 7) / 8 : 0);
@@ -815,13 +833,23 @@ int pqg_plan_finish(pqg_ctx* ctx, pqg_plan* p, pqg_page_error* err) {
         if (rc != PQG_OK) return rc;
         return pqg_plan_finish(ctx, p, err);
     }
-    if (pe.count && pe.code == PQG_PAGE_LAYOUT && p->host_sizes && !p->force_exact) {
-        // a PLAIN page carries bytes beyond its values: redo the column with the size pass
-        p->force_exact = true;
+    if (pe.count && pe.code == PQG_PAGE_CHARS_CAP && p->is_str && p->chars_sized) {
+        // the chars buffer kept from the previous run is too small for this one: size it by the host again
+        p->chars_sized = false;
         int rc = pqg_plan_run(ctx, p);
         if (rc != PQG_OK) return rc;
         return pqg_plan_finish(ctx, p, err);
     }
+    if (pe.count && pe.code == PQG_PAGE_LAYOUT && p->is_str && !p->force_exact) {
+        // a page broke the byte count a fast path assumed (a PLAIN page carrying bytes beyond its values / an out-of-range
+        // index inside an RLE run of a dictionary page): redo the column with the exact size pass
+        p->force_exact = true;
+        p->chars_sized = false;
+        int rc = pqg_plan_run(ctx, p);
+        if (rc != PQG_OK) return rc;
+        return pqg_plan_finish(ctx, p, err);
+    }
+    if (p->is_str && !pe.count) p->chars_sized = true;
     if (pe.count) {
         char msg[256];
         if (pe.code == PQG_PAGE_TRUNCATED || pe.code == PQG_PAGE_DICT_TRUNCATED)
@@ -975,6 +1003,7 @@ bool plan_ran(const pqg_plan* p) { return p->ran; }
 bool plan_run_pending(const pqg_plan* p) { return p->run_pending; }
 bool plan_any_dict(const pqg_plan* p) { return p->any_dict; }
 size_t plan_dict_arena_bytes(const pqg_plan* p) { return p->dict_bytes; }
+uint32_t plan_str_dict_blocks(const pqg_plan* p) { return p->str_dict_blocks; }
 uint64_t plan_slots(const pqg_plan* p) { return p->n_slots; }
 const std::vector<pqg_chunk_desc>& plan_chunks(const pqg_plan* p) { return p->chunks; }
 const std::vector<pqg_page_desc>& plan_pages(const pqg_plan* p) { return p->pages; }

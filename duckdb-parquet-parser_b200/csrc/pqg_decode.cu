@@ -61,7 +61,7 @@ __device__ __forceinline__ uint4 shift_bytes(uint4 a, uint4 b, uint32_t sh) {
 // dictionary preparation
 // ---------------------------------------------------------------------------------------------
 template <int W>
-__global__ void __launch_bounds__(1024) k_dict_prepare(DecodeParams P) {
+__global__ void __launch_bounds__(256) k_dict_prepare(DecodeParams P) {
     // grid: (blocks per chunk, chunks)
     DevChunk& ck = P.chunks[P.chunk_lo + blockIdx.y];
     const bool first = blockIdx.x == 0 && threadIdx.x == 0;
@@ -92,114 +92,179 @@ __global__ void __launch_bounds__(1024) k_dict_prepare(DecodeParams P) {
         } else {
             for (uint32_t i = gtid; i < ok; i += gstride) out[i] = load_plain<W>(src + static_cast<size_t>(i) * W);
         }
-    } else {
-        // BYTE_ARRAY: u32 length prefix + bytes (column_reader.cpp:249-253).  Entry table:
-        // {start (byte offset of the chars inside the dictionary payload), len}.
-        // The prefix chain is sequential by format; it is cut into one segment per thread:
-        //   1. every thread picks the first position of its segment that LOOKS like a prefix
-        //      eight links deep (string inside the payload, and so for its 8 successors), and
-        //      walks the chain from there to the end of its segment (count, end position);
-        //   2. one thread links the segments: a segment's start must be exactly where the
-        //      previous walk ended, otherwise the speculation failed (exactness check);
-        //   3. every thread walks its segment again and writes its entries at its base index.
-        // On any failed link (or a truncated dictionary) one thread walks the whole page like
-        // the reference does, with the reference's error reporting.
-        uint2* ent = reinterpret_cast<uint2*>(dst);
-        constexpr uint32_t kNone = 0xffffffffu;
-        __shared__ uint32_t s_start[1024], s_end[1024], s_cnt[1024], s_base[1024];
-        __shared__ uint32_t s_ok, s_nok, s_minlen, s_maxlen;
-        const uint32_t tid = threadIdx.x, nthr = blockDim.x;
-        if (tid == 0) { s_nok = 0; s_minlen = 0xffffffffu; s_maxlen = 0; }
-        auto next_of = [&](uint32_t p) -> uint32_t { // position after the string whose prefix is at p, kNone if it does not fit
-            if (static_cast<uint64_t>(p) + 4u > size) return kNone;
-            uint32_t len = ld32u(src + p);
-            uint64_t e = static_cast<uint64_t>(p) + 4u + len;
-            return e <= size ? static_cast<uint32_t>(e) : kNone;
-        };
-        const uint32_t seg = max(64u, (size + nthr - 1) / nthr);
-        const uint32_t lo = tid * seg, hi = min(size, lo + seg);
-        uint32_t start = kNone, endp = kNone, cnt = 0;
-        if (lo < size && n > 0) {
-            if (tid == 0) start = 0;
-            else {
-                for (uint32_t p = lo; p < hi && start == kNone; p++) {
-                    uint32_t q = p;
-                    int depth = 0;
-                    for (; depth < 8; depth++) { q = next_of(q); if (q == kNone) break; if (q == size) { depth = 8; break; } }
-                    if (depth >= 8) start = p;
+    }
+}
+
+// ---- BYTE_ARRAY dictionaries: u32 length prefix + bytes (column_reader.cpp:249-253) -----------------------------
+// Entry table {start (byte offset of the chars inside the dictionary payload), len} + a 16-byte padded copy of every
+// entry (15 bytes + the length; meaningful when all entries are <= 15 bytes: one vector load per value).
+// The prefix chain is sequential by format; it is cut into kDictSeg-byte segments, one THREAD each, over as many CTAs
+// as the dictionary needs (a 1.1 MB dictionary: 8.6 K threads; one 1024-thread CTA took 0.31 ms of a 0.56 ms decode):
+//   k_dict_seg   every thread picks the first position of its segment that LOOKS like a prefix eight links deep
+//                (string inside the payload, and so for its 8 successors) and walks the chain from there to the end of
+//                its segment: (start, end, entries);
+//   k_dict_link  one warp per dictionary links the segments in order: a segment's start must be exactly where the
+//                previous walk ended, else the speculation failed (exactness check); 32 segments per step when the
+//                chain runs straight through them, one by one where a long string jumps over segments; on a failed
+//                link or a truncated page one lane walks the whole page like the reference does, with its error;
+//   k_dict_emit  every thread walks its segment again and writes its entries at its base index.
+constexpr uint32_t kSegNone = 0xffffffffu;
+
+__device__ __forceinline__ uint32_t dict_next_of(const uint8_t* src, uint32_t size, uint32_t p) {
+    // position after the string whose prefix is at p, kSegNone if it does not fit
+    if (static_cast<uint64_t>(p) + 4u > size) return kSegNone;
+    const uint32_t len = ld32u(src + p);
+    const uint64_t e = static_cast<uint64_t>(p) + 4u + len;
+    return e <= size ? static_cast<uint32_t>(e) : kSegNone;
+}
+
+__global__ void __launch_bounds__(256) k_dict_seg(DecodeParams P) {
+    DevChunk& ck = P.chunks[P.chunk_lo + blockIdx.y];
+    if (!ck.has_dict || ck.dict_n == 0) return;
+    const uint8_t* src = P.image + ck.dict_off;
+    const uint32_t size = ck.dict_size;
+    const uint32_t nseg = (size + kDictSeg - 1) / kDictSeg;
+    DictSeg* segs = P.dict_segs + ck.dict_seg_first;
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nseg; t += gridDim.x * blockDim.x) {
+        const uint32_t lo = t * kDictSeg, hi = min(size, lo + kDictSeg);
+        uint32_t start = kSegNone, endp = kSegNone, cnt = 0;
+        if (t == 0) start = 0;
+        else {
+            for (uint32_t p = lo; p < hi && start == kSegNone; p++) {
+                uint32_t q = p;
+                int depth = 0;
+                for (; depth < 8; depth++) { q = dict_next_of(src, size, q); if (q == kSegNone) break; if (q == size) { depth = 8; break; } }
+                if (depth >= 8) start = p;
+            }
+        }
+        if (start != kSegNone) {
+            uint32_t p = start;
+            while (p < hi) { const uint32_t q = dict_next_of(src, size, p); if (q == kSegNone) break; cnt++; p = q; }
+            endp = p; // first chain position >= hi, or the position where the chain broke
+        }
+        segs[t] = DictSeg{start, endp, cnt, kSegNone};
+    }
+}
+
+__global__ void __launch_bounds__(32) k_dict_link(DecodeParams P) {
+    DevChunk& ck = P.chunks[P.chunk_lo + blockIdx.x];
+    const uint32_t l = threadIdx.x;
+    if (!ck.has_dict) { if (l == 0) { ck.dict_ok_n = 0; ck.dict_minlen = 0xffffffffu; ck.dict_maxlen = 0; } return; }
+    const uint8_t* src = P.image + ck.dict_off;
+    const uint32_t n = ck.dict_n, size = ck.dict_size;
+    const uint32_t nseg = (size + kDictSeg - 1) / kDictSeg;
+    DictSeg* segs = P.dict_segs + ck.dict_seg_first;
+    __shared__ DictSeg sb[32];
+    uint32_t cur = 0, base = 0, ok = n > 0 ? 1u : 0u;
+    for (uint32_t b0 = 0; b0 < nseg && ok && base < n; b0 += 32) {
+        const uint32_t t = b0 + l;
+        const bool live = t < nseg;
+        DictSeg sg = live ? segs[t] : DictSeg{kSegNone, kSegNone, 0, kSegNone};
+        const uint32_t thi = min(size, (t + 1) * kDictSeg);
+        // straight run: every segment starts where its predecessor ended, and ends inside (or at the start of) the next one
+        const uint32_t prev_end = __shfl_up_sync(0xffffffffu, sg.end, 1);
+        const uint32_t want = l == 0 ? cur : prev_end;
+        const uint32_t next_hi = min(size, (t + 2) * kDictSeg);
+        const bool fine = !live || (sg.start == want && sg.start != kSegNone && sg.end >= thi && (sg.end < next_hi || sg.end == size));
+        const uint32_t incl = warp_incl_scan(live ? sg.cnt : 0u);
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        if (__all_sync(0xffffffffu, fine) && base + total <= n) {
+            if (live) segs[t].base = base + incl - sg.cnt;
+            base += total;
+            const uint32_t last = min(31u, nseg - 1u - b0);
+            cur = __shfl_sync(0xffffffffu, sg.end, last);
+            continue;
+        }
+        // one by one (a string longer than a segment, the end of the entries, or a failed speculation)
+        sb[l] = sg;
+        __syncwarp();
+        if (l == 0) {
+            for (uint32_t i = 0; i < 32u && b0 + i < nseg; i++) {
+                const uint32_t tt = b0 + i, tlo = tt * kDictSeg, hh = min(size, tlo + kDictSeg);
+                uint32_t bse = kSegNone;
+                if (ok && base < n && cur < hh) {             // (cur >= hh: a string spans the whole segment)
+                    if (sb[i].start != cur) ok = 0;            // speculation failed
+                    else {
+                        bse = base;
+                        base += sb[i].cnt;
+                        cur = sb[i].end;
+                        if (cur < hh && base < n) ok = 0;      // the chain broke before n entries: truncated page
+                    }
                 }
-            }
-            if (start != kNone) {
-                uint32_t p = start;
-                while (p < hi) { uint32_t q = next_of(p); if (q == kNone) break; cnt++; p = q; }
-                endp = p; // first chain position >= hi, or the position where the chain broke
+                segs[tt].base = bse;
             }
         }
-        s_start[tid] = start; s_end[tid] = endp; s_cnt[tid] = cnt;
-        __syncthreads();
-        if (tid == 0) {
-            uint32_t cur = 0, base = 0, ok = n > 0 ? 1u : 0u;
-            for (uint32_t t = 0; t < nthr; t++) {
-                s_base[t] = kNone; // kNone: the segment writes nothing
-                const uint32_t tlo = t * seg, thi = min(size, tlo + seg);
-                if (!ok || base >= n || tlo >= size) continue;
-                if (cur >= thi) continue;                       // a string spans the whole segment
-                if (s_start[t] != cur) { ok = 0; continue; }    // speculation failed
-                s_base[t] = base;
-                base += s_cnt[t];
-                cur = s_end[t];
-                if (cur < thi && base < n) ok = 0;              // the chain broke before n entries: truncated page
-            }
-            if (base < n) ok = 0;
-            s_ok = ok;
+        cur = __shfl_sync(0xffffffffu, cur, 0);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        ok = __shfl_sync(0xffffffffu, ok, 0);
+        __syncwarp();
+    }
+    if (base < n) ok = 0;
+    // (segments behind the last entry keep base == kSegNone from k_dict_seg; a segment that would run past n entries is
+    //  cut by k_dict_emit's k < n)
+    if (ok) {
+        if (l == 0) { ck.dict_ok_n = n; ck.dict_minlen = 0xffffffffu; ck.dict_maxlen = 0; }
+        return;
+    }
+    // fallback: nothing from the segments; one lane walks the page like the reference (and reports like it)
+    for (uint32_t t = l; t < nseg; t += 32) segs[t].base = kSegNone;
+    if (l == 0) {
+        uint2* ent = reinterpret_cast<uint2*>(P.dict_arena + ck.dict_arena_off);
+        uint32_t pos = 0, k = 0, mn = 0xffffffffu;
+        for (; k < n; k++) {
+            if (static_cast<uint64_t>(pos) + 4 > size) { report_error(P.err, ck.first_page, PQG_PAGE_DICT_TRUNCATED, pos, 4, size); break; }
+            const uint32_t len = ld32u(src + pos);
+            if (static_cast<uint64_t>(pos) + 4 + len > size) { report_error(P.err, ck.first_page, PQG_PAGE_DICT_TRUNCATED, pos + 4, len, size); break; }
+            ent[k] = make_uint2(pos + 4, len);
+            mn = min(mn, len);
+            pos += 4 + len;
         }
-        __syncthreads();
-        if (s_ok) {
-            if (s_base[tid] != kNone) {
-                uint32_t p = s_start[tid], k = s_base[tid];
-                while (p < hi && k < n) { uint32_t q = next_of(p); if (q == kNone) break; ent[k++] = make_uint2(p + 4u, q - p - 4u); p = q; }
-            }
-            if (first) { ck.dict_ok_n = n; s_nok = n; }
-        } else if (first) {
-            uint32_t pos = 0, k = 0;
-            for (; k < n; k++) {
-                if (static_cast<uint64_t>(pos) + 4 > size) { report_error(P.err, ck.first_page, PQG_PAGE_DICT_TRUNCATED, pos, 4, size); break; }
-                uint32_t len = ld32u(src + pos);
-                if (static_cast<uint64_t>(pos) + 4 + len > size) { report_error(P.err, ck.first_page, PQG_PAGE_DICT_TRUNCATED, pos + 4, len, size); break; }
-                ent[k] = make_uint2(pos + 4, len);
-                pos += 4 + len;
-            }
-            ck.dict_ok_n = k;
-            s_nok = k;
-        }
-        // short-string dictionaries: the padded 16-byte table (one vector load per value instead of
-        // {start, len} + 4-8 unaligned word loads), and the common entry length if there is one
-        __syncthreads();
-        const uint32_t nok = s_nok;
-        uint32_t mn = 0xffffffffu, mx = 0;
-        for (uint32_t i = tid; i < nok; i += nthr) { const uint32_t len = ent[i].y; mn = min(mn, len); mx = max(mx, len); }
-        mn = __reduce_min_sync(0xffffffffu, mn); mx = __reduce_max_sync(0xffffffffu, mx);
-        if ((tid & 31u) == 0) { atomicMin(&s_minlen, mn); atomicMax(&s_maxlen, mx); }
-        __syncthreads();
-        const bool is_short = nok > 0 && s_maxlen <= 15u && !P.skip_dict_pad;
-        if (is_short) {
-            uint4* pad = reinterpret_cast<uint4*>(P.dict_arena + ck.dict_pad_off);
-            for (uint32_t i = tid; i < nok; i += nthr) {
-                const uint2 e = ent[i];
-                const uint8_t* sp = src + e.x;
+        ck.dict_ok_n = k;
+        ck.dict_minlen = mn;
+        ck.dict_maxlen = 0xfffffffeu; // no padded table, no common length: the general paths only
+    }
+}
+
+__global__ void __launch_bounds__(256) k_dict_emit(DecodeParams P) {
+    DevChunk& ck = P.chunks[P.chunk_lo + blockIdx.y];
+    if (!ck.has_dict || ck.dict_n == 0) return;
+    const uint8_t* src = P.image + ck.dict_off;
+    const uint32_t n = ck.dict_n, size = ck.dict_size;
+    const uint32_t nseg = (size + kDictSeg - 1) / kDictSeg;
+    const DictSeg* segs = P.dict_segs + ck.dict_seg_first;
+    uint2* ent = reinterpret_cast<uint2*>(P.dict_arena + ck.dict_arena_off);
+    uint4* pad = reinterpret_cast<uint4*>(P.dict_arena + ck.dict_pad_off);
+    const bool want_pad = !P.skip_dict_pad;
+    uint32_t mn = 0xffffffffu, mx = 0;
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nseg; t += gridDim.x * blockDim.x) {
+        const DictSeg sg = segs[t];
+        if (sg.base == kSegNone) continue;
+        const uint32_t hi = min(size, (t + 1) * kDictSeg);
+        uint32_t p = sg.start, k = sg.base;
+        while (p < hi && k < n) {
+            const uint32_t q = dict_next_of(src, size, p);
+            if (q == kSegNone) break;
+            const uint32_t len = q - p - 4u;
+            ent[k] = make_uint2(p + 4u, len);
+            mn = min(mn, len); mx = max(mx, len);
+            if (want_pad) { // zero-padded first 15 bytes + the length in the top byte (used only if every entry is <= 15 bytes)
+                const uint8_t* sp = src + p + 4u;
                 uint32_t w[4];
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    uint32_t v = 4u * k < e.y ? ld32u(sp + 4 * k) : 0u;
-                    const uint32_t rem = e.y > 4u * k ? e.y - 4u * k : 0u;      // bytes of this word that belong to the string
+                for (int i = 0; i < 4; i++) {
+                    uint32_t v = 4u * i < len ? ld32u(sp + 4 * i) : 0u;
+                    const uint32_t rem = len > 4u * i ? len - 4u * i : 0u;
                     if (rem < 4u) v &= (1u << (8u * rem)) - 1u;
-                    w[k] = v;
+                    w[i] = v;
                 }
-                pad[i] = make_uint4(w[0], w[1], w[2], w[3] | (e.y << 24));
+                pad[k] = make_uint4(w[0], w[1], w[2], (w[3] & 0x00ffffffu) | (min(len, 255u) << 24));
             }
+            k++;
+            p = q;
         }
-        if (tid == 0) { ck.dict_short = is_short ? 1u : 0u; ck.dict_len = (nok > 0 && s_minlen == s_maxlen) ? s_maxlen : 0xffffffffu; }
     }
+    mn = __reduce_min_sync(0xffffffffu, mn); mx = __reduce_max_sync(0xffffffffu, mx);
+    if ((threadIdx.x & 31u) == 0 && mx >= mn) { atomicMin(&ck.dict_minlen, mn); atomicMax(&ck.dict_maxlen, mx); }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -528,6 +593,148 @@ __device__ __forceinline__ uint32_t copy_short_dict_tile(const DecodeParams& P, 
     return outp;
 }
 
+// ---- copy pass, short-string dictionaries, lanes by RANK -----------------------------------------
+// The same job as copy_short_dict_tile for tiles in which EVERY index is known to be in range (2^bw <= dictionary
+// entries, the unmasked value of a trailing RLE run checked by the caller), so that the k-th non-null slot of the tile
+// is the k-th string of its chars: the chars loop runs over ranks -- no validity / rank lookups, and for dictionaries
+// with one common entry length (UNIFORM) no prefix sums either: string k starts at k * ulen.  Two groups of 32
+// strings per trip (two gathers in flight); the strings are OR-ed into the zeroed staging buffer word-wise and
+// leave as full aligned 16-byte vectors.  Offsets are written by SLOT afterwards, four per lane: the offset of a
+// slot is the start of the string of its rank (for a null: of the next string).  Returns the string bytes of the tile.
+template <bool UNIFORM>
+__device__ __forceinline__ uint32_t copy_ranked_dict_tile(const DecodeParams& P, WarpScratch& ws, const RegStream& rs, uint32_t nn_before,
+                                                          uint32_t t, uint32_t nn, const uint4* dpad, uint32_t ulen, uint32_t* offs_tile,
+                                                          uint8_t* dst, uint32_t off0, uint64_t abs_slot0) {
+    const uint32_t l = lane_id();
+    const uint32_t sa = static_cast<uint32_t>(__cvta_generic_to_shared(rs.s));
+    const SmemWords ldw{sa & ~3u};
+    const uint32_t bit0 = (sa & 3u) * 8u, bw = rs.bw, gs = 1u + bw;
+    const uint32_t imask = bw >= 32u ? 0xffffffffu : ((1u << bw) - 1u);
+    const uint32_t stw = static_cast<uint32_t>(__cvta_generic_to_shared(ws.stage)); // 16-byte aligned
+    constexpr uint32_t kZeroVecs = (64u * 15u + 48u + 15u) / 16u; // 64 strings of <= 15 bytes + phase + the carried vector
+    for (uint32_t i = l; i < kZeroVecs; i += 32) reinterpret_cast<uint4*>(ws.stage)[i] = make_uint4(0, 0, 0, 0);
+    uint16_t* pos16 = reinterpret_cast<uint16_t*>(ws.idx); // start of string k inside the tile's chars (variable lengths only)
+    __syncwarp();
+    const uint32_t mis0 = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(dst) & 15u);
+    uint8_t* const abase = dst - mis0;
+    uint32_t outp = 0, sbase = 0;
+    auto fetch = [&](uint32_t k) -> uint4 {
+        uint4 pv = make_uint4(0, 0, 0, 0);
+        if (k < nn) {
+            const uint32_t kk = nn_before + k;
+            const uint32_t bit = bit0 + (((kk >> 3) * gs + 1u) << 3) + (kk & 7u) * bw;
+            uint32_t ix = __funnelshift_r(ldw(bit >> 5), ldw((bit >> 5) + 1u), bit & 31u) & imask;
+            ix = kk >= rs.tail_start ? rs.tail_val : ix;
+            pv = ldg_nc16(reinterpret_cast<const uint8_t*>(dpad + ix));
+        }
+        return pv;
+    };
+    auto put = [&](const uint4& pv, uint32_t apos) {
+        const uint32_t o = apos - sbase, sh = (o & 3u) * 8u, a = stw + (o & ~3u);
+        const uint32_t w3 = pv.w & 0x00ffffffu;
+        const uint32_t x0 = pv.x << sh, x1 = __funnelshift_l(pv.x, pv.y, sh), x2 = __funnelshift_l(pv.y, pv.z, sh);
+        const uint32_t x3 = __funnelshift_l(pv.z, w3, sh), x4 = __funnelshift_l(w3, 0u, sh);
+        if (x0) asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(a), "r"(x0) : "memory");
+        if (x1) asm volatile("red.shared.or.b32 [%0+4], %1;" ::"r"(a), "r"(x1) : "memory");
+        if (x2) asm volatile("red.shared.or.b32 [%0+8], %1;" ::"r"(a), "r"(x2) : "memory");
+        if (x3) asm volatile("red.shared.or.b32 [%0+12], %1;" ::"r"(a), "r"(x3) : "memory");
+        if (x4) asm volatile("red.shared.or.b32 [%0+16], %1;" ::"r"(a), "r"(x4) : "memory");
+    };
+    for (uint32_t g = 0; g < nn; g += 64) {
+        const uint32_t k0 = g + l, k1 = g + 32u + l;
+        const uint4 p0 = fetch(k0), p1 = fetch(k1);
+        uint32_t my0, my1, total;
+        if constexpr (UNIFORM) {
+            const uint32_t n0 = min(32u, nn - g), n1 = nn - g > 32u ? min(32u, nn - g - 32u) : 0u;
+            my0 = outp + l * ulen;
+            my1 = outp + (n0 + l) * ulen;
+            total = (n0 + n1) * ulen;
+        } else {
+            const uint32_t len0 = p0.w >> 24, len1 = p1.w >> 24;
+            const uint32_t incl0 = warp_incl_scan(len0), incl1 = warp_incl_scan(len1);
+            const uint32_t tot0 = __shfl_sync(0xffffffffu, incl0, 31), tot1 = __shfl_sync(0xffffffffu, incl1, 31);
+            my0 = outp + incl0 - len0;
+            my1 = outp + tot0 + incl1 - len1;
+            total = tot0 + tot1;
+            if (k0 < nn) pos16[k0] = static_cast<uint16_t>(my0);
+            if (k1 < nn) pos16[k1] = static_cast<uint16_t>(my1);
+        }
+        if (total) {
+            if (k0 < nn) put(p0, mis0 + my0);
+            if (k1 < nn) put(p1, mis0 + my1);
+            __syncwarp();
+            outp += total;
+            const uint32_t end = mis0 + outp;
+            const uint32_t nfull = (end >> 4) - (sbase >> 4);
+            if (nfull) {
+                if (sbase == 0 && mis0) { // first vector: the bytes in front belong to another page
+                    if (l >= mis0 && l < 16u) abase[l] = ws.stage[l];
+                    __syncwarp();
+                }
+                for (uint32_t j = l; j < nfull; j += 32) {
+                    const uint4 v = *reinterpret_cast<const uint4*>(ws.stage + 16u * j);
+                    *reinterpret_cast<uint4*>(ws.stage + 16u * j) = make_uint4(0, 0, 0, 0);
+                    if (sbase + j || !mis0) *reinterpret_cast<uint4*>(abase + sbase + 16u * j) = v;
+                }
+                __syncwarp();
+                if (l == 0) { // the partial vector moves to the front
+                    const uint4 v = *reinterpret_cast<const uint4*>(ws.stage + 16u * nfull);
+                    *reinterpret_cast<uint4*>(ws.stage + 16u * nfull) = make_uint4(0, 0, 0, 0);
+                    *reinterpret_cast<uint4*>(ws.stage) = v;
+                }
+                sbase += 16u * nfull;
+                __syncwarp();
+            }
+        } else {
+            __syncwarp();
+        }
+    }
+    { // the bytes behind the last complete vector (and a first vector that never filled up)
+        const uint32_t end = mis0 + outp;
+        const uint32_t from = sbase == 0 ? mis0 : sbase;
+        if (from + l < end) abase[from + l] = ws.stage[from - sbase + l]; // < 16 bytes
+        __syncwarp();
+        if (l == 0) *reinterpret_cast<uint4*>(ws.stage) = make_uint4(0, 0, 0, 0);
+    }
+    // offsets by slot, four consecutive slots per lane (they share a validity word)
+    for (uint32_t s0 = 4u * l; s0 < t; s0 += 128u) {
+        const uint32_t wv = ws.valid[s0 >> 5], b = s0 & 31u;
+        uint32_t r = ws.rankbase[s0 >> 5] + __popc(wv & ((1u << b) - 1u));
+        uint32_t o[4];
+#pragma unroll
+        for (uint32_t j = 0; j < 4u; j++) {
+            if constexpr (UNIFORM) o[j] = off0 + r * ulen;
+            else o[j] = off0 + (r < nn ? static_cast<uint32_t>(pos16[r]) : outp);
+            r += (wv >> (b + j)) & 1u;
+        }
+        uint32_t* op = offs_tile + s0;
+        if (s0 + 3u < t && (reinterpret_cast<uintptr_t>(op) & 15u) == 0) *reinterpret_cast<uint4*>(op) = make_uint4(o[0], o[1], o[2], o[3]);
+        else {
+#pragma unroll
+            for (uint32_t j = 0; j < 4u; j++) if (s0 + j < t) op[j] = o[j];
+        }
+    }
+    // validity: the tile's image shifted to its position in the column's bitmap, one word per lane
+    if (P.validity) {
+        const uint32_t head = static_cast<uint32_t>(abs_slot0 & 31u), nwords = (t + 31u) >> 5;
+        uint32_t* vp = P.validity + (abs_slot0 >> 5);
+        const uint32_t cur = l < nwords ? ws.valid[l] : 0u;
+        const uint32_t prev = (l > 0 && l <= nwords) ? ws.valid[l - 1] : 0u;
+        const uint32_t gw = head ? ((cur << head) | (prev >> (32u - head))) : cur;
+        const uint32_t totb = head + t, gwords = (totb + 31u) >> 5;
+        if (l < gwords) {
+            const bool full = (l > 0 || head == 0) && (l + 1u) * 32u <= totb;
+            if (full) vp[l] = gw; else if (gw) atomicOr(&vp[l], gw);
+        }
+        if (l == 0 && gwords > 32u) { // head pushes the last bits into a 33rd word
+            const uint32_t last = ws.valid[31] >> (32u - head);
+            if (last) atomicOr(&vp[32], last);
+        }
+    }
+    __syncwarp();
+    return outp;
+}
+
 // LEAN: the plan has dictionary chunks -- compile the short-string-dictionary copy path in (kept out of the
 // instantiation that PLAIN-only plans run: its registers cost the PLAIN path 7 %)
 template <bool COPY, bool LEAN>
@@ -535,6 +742,48 @@ __device__ __forceinline__ void decode_str_page(const DecodeParams& P, uint32_t 
     const uint32_t l = lane_id();
     const pqg_page_desc pd = P.pages[q];
     if (pd.num_values == 0) { if (!COPY && l == 0) P.page_chars[q] = 0; return; }
+    if constexpr (!COPY) {
+        // Size pass, dictionaries whose entries all have one length (ck.dict_len) and whose size covers every bw-bit
+        // index: the page's bytes are that length times its present slots -- counted from the definition-level runs
+        // right where they lie in global memory (the writer's <varint < 128><level> layout), nothing staged, no index
+        // decoded.  Optimistic in one point: an RLE run INSIDE the index stream carries an unmasked value that may be
+        // out of range (a null in the reference, so fewer bytes); the copy pass compares every page's bytes with this
+        // count and the plan falls back to the exact size pass (P.exact_sizes) on a mismatch.
+        const bool dict_page = (pd.flags & PQG_PAGE_FLAG_DICT) && ck.has_dict;
+        if (dict_page && !P.exact_sizes && ck.dict_len() != 0xffffffffu && ck.max_rep <= 0 && ck.max_def <= 1) {
+            const uint8_t* src = P.image + pd.payload_off;
+            const uint32_t size = pd.payload_size, n = pd.num_values;
+            uint32_t pos = 0, nn = n;
+            bool ok = true;
+            if (ck.max_def == 1) {
+                ok = size >= 4u;
+                const uint32_t def_len = ok ? ld32u(src) : 0u;
+                ok = ok && def_len <= size - 4u && !(def_len & 1u);
+                if (ok) {
+                    const uint8_t* s = src + 4;
+                    const uint32_t nr = def_len >> 1;
+                    uint32_t total = 0, present = 0;
+                    for (uint32_t r = l; r < nr; r += 32) {
+                        const uint32_t b = s[2 * r], v = s[2 * r + 1];
+                        ok = ok && ((b & 0x81u) == 0u) && b != 0u;
+                        total += b >> 1;
+                        if (v >= 1u) present += b >> 1;
+                    }
+                    total = __reduce_add_sync(0xffffffffu, total);
+                    nn = __reduce_add_sync(0xffffffffu, present);
+                    ok = __all_sync(0xffffffffu, ok) && total <= n; // (runs reaching past the page: exact path)
+                    pos = 4u + def_len;
+                }
+            }
+            if (ok) {
+                const uint32_t bw = pos < size ? src[pos] : 99u;
+                if (bw < 32u && ck.dict_ok_n >= (1u << bw)) {
+                    if (l == 0) P.page_chars[q] = ck.dict_len() * nn;
+                    return;
+                }
+            }
+        }
+    }
     PageCtx c;
     if (!page_begin(P, q, pd, ck, ws, c)) { if (!COPY && l == 0) P.page_chars[q] = 0; return; }
     const uint8_t* vals = c.pg + c.vals_pos;
@@ -547,7 +796,7 @@ __device__ __forceinline__ void decode_str_page(const DecodeParams& P, uint32_t 
     const uint2* dent = reinterpret_cast<const uint2*>(P.dict_arena + ck.dict_arena_off);
     const uint8_t* dchars = P.image + ck.dict_off;
     const uint32_t dict_n = ck.dict_ok_n;
-    const bool dshort = c.dict && ck.dict_short != 0;
+    const bool dshort = c.dict && ck.dict_short();
     const uint4* dpad = reinterpret_cast<const uint4*>(P.dict_arena + ck.dict_pad_off);
     uint32_t* offs = COPY ? P.offsets + ck.out_row_base + (&ck - P.chunks) : nullptr; // chunk c owns [row_base + c, ...]
     uint8_t* chars = COPY ? P.chars + ck.char_base : nullptr;
@@ -586,7 +835,7 @@ __device__ __forceinline__ void decode_str_page(const DecodeParams& P, uint32_t 
         if (!COPY) {
             if (c.dict) { // sum the lengths of the referenced dictionary entries
                 uint32_t sum = 0;
-                const uint32_t ulen = ck.dict_len; // every entry has this length (~0u: lengths differ)
+                const uint32_t ulen = ck.dict_len(); // every entry has this length (~0u: lengths differ)
                 // one common length and no index can be out of range (2^bw <= entries; the unmasked value
                 // of a trailing RLE run checked apart): the page's bytes follow from the count alone
                 const bool all_in_range = regular && c.bw < 32u && dict_n >= (1u << c.bw) &&
@@ -611,6 +860,19 @@ __device__ __forceinline__ void decode_str_page(const DecodeParams& P, uint32_t 
         // ---- COPY: offsets, then chars, 32 slots per step ----
         const uint64_t slot0 = (pd.out_row_base - ck.out_row_base) + ts; // chunk-relative slot
         if constexpr (LEAN) if (dshort && regular && c.size <= static_cast<uint32_t>(kSlotBytes)) { // (the page is in the shared slot)
+            // every index in range (the trailing RLE run's unmasked value included): the k-th present slot is the k-th string
+            const bool all_in_range = c.bw < 32u && dict_n >= (1u << c.bw) && (rs.tail_start >= nn_before + nn || rs.tail_val < dict_n);
+            if (all_in_range) {
+                const uint32_t ulen = ck.dict_len();
+                uint8_t* dstp = chars + page_base + page_bytes;
+                const uint32_t o0 = static_cast<uint32_t>(page_base + page_bytes);
+                page_bytes += ulen != 0xffffffffu
+                    ? copy_ranked_dict_tile<true>(P, ws, rs, nn_before, t, nn, dpad, ulen, offs + slot0, dstp, o0, pd.out_row_base + ts)
+                    : copy_ranked_dict_tile<false>(P, ws, rs, nn_before, t, nn, dpad, 0u, offs + slot0, dstp, o0, pd.out_row_base + ts);
+                nn_before += nn;
+                __syncwarp();
+                continue;
+            }
             page_bytes += copy_short_dict_tile(P, ws, rs, nn_before, t, dpad, dict_n, offs + slot0, chars + page_base + page_bytes,
                                                static_cast<uint32_t>(page_base + page_bytes), pd.out_row_base + ts);
             nn_before += nn;
@@ -709,6 +971,8 @@ __device__ __forceinline__ void decode_str_page(const DecodeParams& P, uint32_t 
         // byte counts taken from the page headers (no size pass) hold only if the page is exactly its values
         if (P.check_layout && !c.dict && l == 0 && page_bytes != static_cast<uint64_t>(vavail) - 4ull * nn_before)
             report_error(P.err, q, PQG_PAGE_LAYOUT);
+        // the size pass counted this dictionary page optimistically (see there): hold it to its word
+        if (c.dict && !P.exact_sizes && l == 0 && page_bytes != P.page_chars[q]) report_error(P.err, q, PQG_PAGE_LAYOUT);
         // the last page of the chunk closes the Arrow offsets array
         if (l == 0 && q + 1 == ck.first_page + ck.n_pages)
             offs[(pd.out_row_base - ck.out_row_base) + c.n] = static_cast<uint32_t>(page_base + page_bytes);
@@ -725,6 +989,14 @@ __global__ void __launch_bounds__(kThreadsPerCta, 3) k_str_pages(DecodeParams P)
     WarpScratch& ws = reinterpret_cast<WarpScratch*>(smem)[warp_id()];
     uint32_t* cursor = COPY ? &P.err->slow_cursor : &P.err->slow_count;
     const uint32_t n = P.page_end - P.page_begin, batch = P.pages_per_cta;
+    if constexpr (COPY) {
+        // launched without waiting for the size pass (the chars buffer of the previous run is reused): the grand total
+        // must fit, otherwise nothing is written and pqg_plan_finish sizes the buffer and runs again
+        if (P.total_chars && *P.total_chars > P.chars_cap) {
+            if (blockIdx.x == 0 && threadIdx.x == 0) report_error(P.err, 0, PQG_PAGE_CHARS_CAP);
+            return;
+        }
+    }
     for (;;) {
         uint32_t i = 0;
         if (lane_id() == 0) i = atomicAdd(cursor, batch);
@@ -797,9 +1069,15 @@ size_t decode_smem_bytes(bool with_dict) {
 
 cudaError_t launch_dict_prepare(const DecodeParams& p, uint32_t n_chunks, int width, uint32_t max_dict_blocks, cudaStream_t s) {
     if (n_chunks == 0) return cudaSuccess;
-    dim3 grid(width == 0 ? 1u : max_dict_blocks, n_chunks);
+    if (width == 0) { // strings: segments over many CTAs, one warp per dictionary to link them, entries over many CTAs
+        dim3 grid(max_dict_blocks ? max_dict_blocks : 1u, n_chunks);
+        k_dict_seg<<<grid, 256, 0, s>>>(p);
+        k_dict_link<<<n_chunks, 32, 0, s>>>(p);
+        k_dict_emit<<<grid, 256, 0, s>>>(p);
+        return cudaGetLastError();
+    }
+    dim3 grid(max_dict_blocks, n_chunks);
     switch (width) {
-        case 0: k_dict_prepare<0><<<grid, 1024, 0, s>>>(p); break; // strings: one 1024-thread CTA per dictionary
         case 1: k_dict_prepare<1><<<grid, 256, 0, s>>>(p); break;
         case 4: k_dict_prepare<4><<<grid, 256, 0, s>>>(p); break;
         case 8: k_dict_prepare<8><<<grid, 256, 0, s>>>(p); break;

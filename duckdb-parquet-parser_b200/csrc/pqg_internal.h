@@ -46,10 +46,19 @@ struct DevChunk {
     uint32_t dict_ok_n;      // dictionary entries that parsed (written by the prepare kernel)
     // BYTE_ARRAY dictionaries whose entries are all <= 15 bytes also get a 16-byte-per-entry table
     // (15 zero-padded bytes + the length) behind the {start, len} entries: one 16-byte load per value
-    uint32_t dict_short;     // written by the prepare kernel: 1 = the padded table is valid
-    uint32_t dict_len;       // written by the prepare kernel: common length of all entries, ~0u if they differ
+    uint32_t dict_minlen;    // BYTE_ARRAY, written by the prepare kernels: shortest / longest dictionary entry
+    uint32_t dict_maxlen;    //   (all <= 15 bytes: the padded table is valid; equal: one common length)
     uint64_t dict_pad_off;   // arena offset of the padded table
+    uint32_t dict_seg_first; // BYTE_ARRAY: first record of this chunk in the plan's dictionary-segment scratch
+    uint32_t pad_;
+#ifdef __CUDACC__
+    __device__ __forceinline__ bool dict_short() const { return dict_ok_n > 0 && dict_maxlen <= 15u; }
+    // common length of all entries, ~0u if they differ
+    __device__ __forceinline__ uint32_t dict_len() const { return (dict_ok_n > 0 && dict_minlen == dict_maxlen) ? dict_maxlen : 0xffffffffu; }
+#endif
 };
+struct DictSeg { uint32_t start, end, cnt, base; }; // one segment of a BYTE_ARRAY dictionary page (k_dict_seg / _link / _emit)
+constexpr uint32_t kDictSeg = 128;                  // bytes per segment
 
 // First failing page (lowest page-table index) of a run, plus the per-run work counters
 // (one memset resets everything).
@@ -84,6 +93,7 @@ struct DecodeParams {
     uint32_t pages_per_cta;
     uint32_t n_chunks;
     uint8_t* dict_arena;
+    DictSeg* dict_segs;      // BYTE_ARRAY plans: scratch of the dictionary preparation
     uint8_t* values;
     uint32_t* validity;
     uint32_t* offsets;
@@ -106,10 +116,15 @@ struct DecodeParams {
     uint32_t tile_bytes;     // tile size the plan's tiles were cut for (kTileBytes / kTileBytesLarge)
     uint32_t identity_dict;  // dictionary-form output: emit the dictionary INDEX of every slot instead of the entry
     uint32_t check_layout;   // BYTE_ARRAY copy pass: page byte counts came from the page headers -- verify them
+    uint32_t exact_sizes;    // BYTE_ARRAY size pass: no optimistic per-page byte counts (a page broke its count in an earlier run)
+    uint64_t chars_cap;      // BYTE_ARRAY copy pass launched without a host sync: capacity of `chars` ...
+    const uint64_t* total_chars; // ... and the device-side grand total it must hold (null: the host already checked)
 };
 
 // launchers (pqg_decode.cu)
+// width 0 = BYTE_ARRAY: three launches (segments, link, emit), max_dict_blocks = blocks of 256 threads per dictionary
 cudaError_t launch_dict_prepare(const DecodeParams& p, uint32_t n_chunks, int width, uint32_t max_dict_blocks, cudaStream_t s);
+inline uint32_t dict_prepare_launches(int width) { return width == 0 ? 3u : 1u; }
 cudaError_t launch_decode_fixed(const DecodeParams& p, int width, bool boolean_plain, int sm_count, cudaStream_t s);
 // fast path (pqg_tiles.cu): PLAIN / regular-dictionary pages of REQUIRED 4- and 8-byte chunks
 cudaError_t launch_fixed_tiles(const DecodeParams& p, int width, int sm_count, cudaStream_t s);

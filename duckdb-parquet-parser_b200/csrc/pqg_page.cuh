@@ -206,17 +206,37 @@ __device__ __forceinline__ uint32_t levels_tile(Walker& w, WarpScratch& ws, uint
         bool ok = true;
         for (uint32_t r = l; r < nr; r += 32) { uint32_t b = s[2 * r]; ok = ok && ((b & 0x81u) == 0u) && b != 0u; }
         if (__all_sync(0xffffffffu, ok)) {
-            uint32_t carry = 0;
+            // no bit ranges, no loops over words: every run whose level class (present / null) differs from its
+            // predecessor's sets ONE toggle bit at its first slot; the validity image is the prefix XOR of the toggles
+            uint32_t carry = 0, last_present = 0;
             for (uint32_t base = 0; base < nr && carry < t; base += 32) {
-                uint32_t r = base + l;
-                uint32_t cnt = 0, val = 0;
-                if (r < nr) { cnt = s[2 * r] >> 1; val = s[2 * r + 1]; }
-                uint32_t incl = warp_incl_scan(cnt);
-                uint32_t start = carry + incl - cnt;
-                if (cnt && start < t && level_present(val, max_def)) set_bits_range(ws.valid, start, min(cnt, t - start));
+                const uint32_t r = base + l;
+                uint32_t cnt = 0, pres = 0;
+                if (r < nr) { cnt = s[2 * r] >> 1; pres = level_present(s[2 * r + 1], max_def) ? 1u : 0u; }
+                const uint32_t incl = warp_incl_scan(cnt);
+                const uint32_t start = carry + incl - cnt;
+                uint32_t prev = __shfl_up_sync(0xffffffffu, pres, 1);
+                if (l == 0) prev = last_present;
+                if (r < nr && start < t && pres != prev) atomicXor(&ws.valid[start >> 5], 1u << (start & 31u));
+                last_present = __shfl_sync(0xffffffffu, pres, min(31u, nr - 1u - base));
                 carry += __shfl_sync(0xffffffffu, incl, 31);
             }
-            w.pos = w.len; // consumed (a short stream leaves the remaining slots null)
+            __syncwarp();
+            // a short stream leaves the remaining slots null (rle_decoder.hpp:21-24)
+            if (l == 0 && last_present && carry < t) ws.valid[carry >> 5] ^= 1u << (carry & 31u);
+            __syncwarp();
+            uint32_t x = ws.valid[l];
+            const uint32_t par = __popc(x) & 1u;
+            x ^= x << 1; x ^= x << 2; x ^= x << 4; x ^= x << 8; x ^= x << 16;
+            uint32_t px = par; // inclusive xor-scan of the word parities
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, px, d); if (l >= static_cast<uint32_t>(d)) px ^= o; }
+            if ((px ^ par) & 1u) x = ~x; // an odd number of toggles in front of this word
+            const uint32_t lo = l * 32u;
+            x &= lo >= t ? 0u : (t - lo >= 32u ? 0xffffffffu : ((1u << (t - lo)) - 1u));
+            __syncwarp();
+            ws.valid[l] = x;
+            w.pos = w.len; // consumed
             done = true;
         }
     }

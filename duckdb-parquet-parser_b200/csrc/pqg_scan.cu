@@ -47,6 +47,7 @@ const std::vector<pqg_chunk_desc>& plan_chunks(const pqg_plan* p);
 const std::vector<pqg_page_desc>& plan_pages(const pqg_plan* p);
 uint32_t plan_max_page_values(const pqg_plan* p);
 size_t plan_dict_arena_bytes(const pqg_plan* p);
+uint32_t plan_str_dict_blocks(const pqg_plan* p);
 
 namespace {
 
@@ -369,17 +370,25 @@ struct StrWeights {
     const uint32_t* validity;  // may be null
     const uint64_t* chunk_row_base; // n_chunks + 1 (device)
     uint32_t n_chunks;
-    __device__ uint32_t operator()(uint64_t i) const {
-        if (validity && !((validity[i >> 5] >> (i & 31)) & 1u)) return 0;
-        uint32_t lo = 0, hi = n_chunks; // chunk of slot i
+    __device__ uint32_t chunk_of(uint64_t i) const {
+        uint32_t lo = 0, hi = n_chunks;
         while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (chunk_row_base[mid] <= i) lo = mid; else hi = mid; }
-        const uint32_t* off = offsets + i + lo;
+        return lo;
+    }
+    // weight of slot i; c = chunk of some slot <= i (a cursor: threads walk consecutive slots)
+    __device__ uint32_t at(uint64_t i, uint32_t& c) const {
+        if (validity && !((validity[i >> 5] >> (i & 31)) & 1u)) return 0;
+        while (c + 1 < n_chunks && chunk_row_base[c + 1] <= i) c++;
+        const uint32_t* off = offsets + i + c;
         uint32_t len = off[1] - off[0];
         return dec_digits(len) + len;
     }
+    __device__ uint32_t operator()(uint64_t i) const { uint32_t c = chunk_of(i); return at(i, c); }
 };
 struct ArrWeights {
     const uint32_t* w;
+    __device__ uint32_t chunk_of(uint64_t) const { return 0; }
+    __device__ uint32_t at(uint64_t i, uint32_t&) const { return w[i]; }
     __device__ uint32_t operator()(uint64_t i) const { return w[i]; }
 };
 
@@ -405,11 +414,13 @@ __device__ __forceinline__ uint64_t block_excl_scan(uint64_t v, uint64_t* total_
 
 template <class Src>
 __global__ void __launch_bounds__(kScanThreads) k_scan_reduce(Src src, uint64_t n, uint64_t* block_sums) {
-    const uint64_t base = static_cast<uint64_t>(blockIdx.x) * kScanTile;
+    // every thread takes kScanItems consecutive slots (the same split as k_scan_write): one chunk lookup per thread
+    const uint64_t base = static_cast<uint64_t>(blockIdx.x) * kScanTile + static_cast<uint64_t>(threadIdx.x) * kScanItems;
     uint64_t sum = 0;
-    for (int j = 0; j < kScanItems; j++) {
-        uint64_t i = base + static_cast<uint64_t>(j) * kScanThreads + threadIdx.x;
-        if (i < n) sum += src(i);
+    if (base < n) {
+        uint32_t c = src.chunk_of(base);
+#pragma unroll
+        for (int j = 0; j < kScanItems; j++) { uint64_t i = base + j; if (i < n) sum += src.at(i, c); }
     }
     uint64_t total;
     block_excl_scan(sum, &total);
@@ -439,8 +450,9 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_write(Src src, uint64_t n
     const uint64_t base = static_cast<uint64_t>(blockIdx.x) * kScanTile + static_cast<uint64_t>(threadIdx.x) * kScanItems;
     uint32_t w[kScanItems];
     uint64_t sum = 0;
+    uint32_t c = base < n ? src.chunk_of(base) : 0u;
 #pragma unroll
-    for (int j = 0; j < kScanItems; j++) { uint64_t i = base + j; w[j] = i < n ? src(i) : 0; sum += w[j]; }
+    for (int j = 0; j < kScanItems; j++) { uint64_t i = base + j; w[j] = i < n ? src.at(i, c) : 0; sum += w[j]; }
     uint64_t total;
     uint64_t ex = block_sums[blockIdx.x] + block_excl_scan(sum, &total);
 #pragma unroll
@@ -465,7 +477,10 @@ __device__ __forceinline__ uint64_t lower_bound_from(const uint64_t* P, uint64_t
     return hi;
 }
 
-constexpr uint32_t kChainTileChunks = 64; // a weight-space tile spans this many chunk sizes
+// a weight-space tile spans this many chunk sizes: at least kChainTileChunks, more for long columns so that the
+// tile count stays near kChainTilesTarget (every tile has ~(slots per chunk) candidates whose walk results go to the
+// host for the stitch: fewer, longer tiles = fewer candidates to copy; the total walking work does not change)
+constexpr uint32_t kChainTileChunks = 64, kChainTileChunksMax = 4096, kChainTilesTarget = 2048;
 
 // per weight-space tile t: klo[t] = first slot with P >= t*L, ncand[t] = candidate first cuts
 __global__ void k_chain_tiles(const uint64_t* P, uint64_t n, uint64_t S, uint64_t L, uint64_t T, uint64_t* klo, uint32_t* ncand) {
@@ -483,25 +498,44 @@ __global__ void k_chain_tiles(const uint64_t* P, uint64_t n, uint64_t S, uint64_
     ncand[t] = static_cast<uint32_t>(cnt);
 }
 
-// every candidate of every tile walks its tile: number of cuts inside, first cut after it, prefix value of the last cut inside
-__global__ void __launch_bounds__(128) k_chain_walk(const uint64_t* P, uint64_t n, uint64_t S, uint64_t L, const uint64_t* klo,
+// first index >= lo with P[index] >= x (n if none), galloping from lo
+__device__ __forceinline__ uint64_t lower_bound_ge(const uint64_t* P, uint64_t n, uint64_t lo, uint64_t x) {
+    if (lo >= n) return n;
+    if (P[lo] >= x) return lo;
+    return lower_bound_from(P, n, lo, x);
+}
+
+// next[k] = the cut that follows a cut at slot k: first slot with P >= P[k] + S.  Every thread takes kNextItems
+// consecutive slots: next is monotone, so each search starts where the previous one ended (a step or two).
+constexpr int kNextItems = 8;
+__global__ void __launch_bounds__(256) k_chain_next(const uint64_t* P, uint64_t n, uint64_t S, uint32_t* next) {
+    const uint64_t k0 = (static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * kNextItems;
+    if (k0 >= n) return;
+    uint64_t r = lower_bound_from(P, n, k0, P[k0] + S);
+    next[k0] = static_cast<uint32_t>(r);
+#pragma unroll
+    for (int j = 1; j < kNextItems; j++) {
+        const uint64_t k = k0 + j;
+        if (k >= n) break;
+        r = lower_bound_ge(P, n, max(r, k + 1), P[k] + S);
+        next[k] = static_cast<uint32_t>(r);
+    }
+}
+
+// every candidate of every tile walks its tile along next[]: number of cuts inside, first cut after it, prefix value of
+// the last cut inside.  (Candidates x cuts per tile = slots per chunk x cuts in all: about one step per slot of the column.)
+__global__ void __launch_bounds__(128) k_chain_walk(const uint64_t* P, const uint32_t* next, const uint64_t* klo,
                                                      const uint32_t* ncand, const uint64_t* cand_base, uint64_t* res_exit, uint32_t* res_cnt,
                                                      uint64_t* res_last) {
     const uint64_t t = blockIdx.x;
-    const uint64_t end = (t + 1) * L;
+    const uint64_t end_slot = klo[t + 1]; // first slot of the next tile: P >= (t + 1) * L from there on
     for (uint32_t j = threadIdx.x; j < ncand[t]; j += blockDim.x) {
         uint64_t k = klo[t] + j, last = 0;
         uint32_t cnt = 0;
-        while (k < n) {
-            uint64_t pk = P[k];
-            if (pk >= end) break;
-            cnt++;
-            last = pk;
-            k = lower_bound_from(P, n, k, pk + S);
-        }
+        while (k < end_slot) { cnt++; last = k; k = next[k]; }
         res_exit[cand_base[t] + j] = k;
         res_cnt[cand_base[t] + j] = cnt;
-        res_last[cand_base[t] + j] = last;
+        res_last[cand_base[t] + j] = cnt ? P[last] : 0;
     }
 }
 
@@ -520,19 +554,14 @@ __global__ void k_chain_entry(const uint64_t* P, uint64_t n_eff, uint64_t x0, ui
 }
 
 // materialise the cuts: tile t walks from its true entry
-__global__ void k_chain_emit(const uint64_t* P, uint64_t n, uint64_t S, uint64_t L, uint64_t T, const uint64_t* tile_entry,
+__global__ void k_chain_emit(const uint32_t* next, uint64_t n, uint64_t T, const uint64_t* klo, const uint64_t* tile_entry,
                              const uint64_t* tile_base, uint64_t* cuts) {
     uint64_t t = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (t >= T) return;
     uint64_t k = tile_entry[t], o = tile_base[t];
-    const uint64_t end = (t + 1) * L;
-    if (k >= n || P[k] < t * L) return; // no cut starts in this tile
-    while (k < n) {
-        uint64_t pk = P[k];
-        if (pk >= end) break;
-        cuts[o++] = k;
-        k = lower_bound_from(P, n, k, pk + S);
-    }
+    if (k >= n || k < klo[t]) return; // no cut starts in this tile
+    const uint64_t end_slot = klo[t + 1];
+    while (k < end_slot) { cuts[o++] = k; k = next[k]; }
 }
 
 // ids[i] = number of cuts at slots <= i (0 for zero-weight slots when mask_zero)
@@ -609,6 +638,8 @@ struct ChainJob {
     bool mask_zero = false;
     uint64_t* d_P = nullptr;
     uint64_t* d_entry = nullptr;
+    uint64_t* d_klo = nullptr;   // T + 1 tile starts (slots)
+    uint32_t* d_next = nullptr;  // n: the cut that follows a cut at each slot
     std::vector<uint64_t> klo, cand_base, r_exit, r_last, tile_entry, tile_base;
     std::vector<uint32_t> ncand, r_cnt;
     uint64_t n_cuts = 0, last_cut_P = 0, carry_in = 0;
@@ -643,14 +674,23 @@ cudaError_t chain_prepare(ChainJob& J, Src src, uint64_t n, uint64_t S, bool mas
     CK(cudaStreamSynchronize(s));
     J.total = h_tot[0];
     J.n = h_tot[1]; // the chain only sees slots that can start a chunk
-    J.L = S * kChainTileChunks;
+    {
+        const uint64_t chunks = J.total / S + 1;
+        uint64_t m = (chunks + kChainTilesTarget - 1) / kChainTilesTarget;
+        m = m < kChainTileChunks ? kChainTileChunks : (m > kChainTileChunksMax ? kChainTileChunksMax : m);
+        J.L = S * m;
+    }
     J.T = J.total / J.L + 1;
     const uint64_t T = J.T;
+    if (J.n >= 0xffffffffull) return cudaErrorInvalidValue; // next[] holds 32-bit slots (a plan of >= 4 G slots is split by the host)
     uint64_t* d_klo = nullptr; uint32_t* d_ncand = nullptr;
     CK(J.mem.alloc(&d_klo, T + 1));
     CK(J.mem.alloc(&d_ncand, T + 1));
+    CK(J.mem.alloc(&J.d_next, J.n + 1));
+    J.d_klo = d_klo;
     k_chain_tiles<<<static_cast<unsigned>((T + 1 + 127) / 128), 128, 0, s>>>(J.d_P, J.n, S, J.L, T, d_klo, d_ncand);
-    J.launches++;
+    if (J.n) k_chain_next<<<static_cast<unsigned>((J.n + 256ull * kNextItems - 1) / (256ull * kNextItems)), 256, 0, s>>>(J.d_P, J.n, S, J.d_next);
+    J.launches += 2;
     J.klo.resize(T + 1);
     J.ncand.resize(T);
     CK(cudaMemcpyAsync(J.klo.data(), d_klo, (T + 1) * 8, cudaMemcpyDeviceToHost, s));
@@ -665,7 +705,7 @@ cudaError_t chain_prepare(ChainJob& J, Src src, uint64_t n, uint64_t S, bool mas
     CK(J.mem.alloc(&d_cnt, n_cand));
     CK(J.mem.alloc(&d_last, n_cand));
     CK(cudaMemcpyAsync(d_cand_base, J.cand_base.data(), (T + 1) * 8, cudaMemcpyHostToDevice, s));
-    k_chain_walk<<<static_cast<unsigned>(T), 128, 0, s>>>(J.d_P, J.n, S, J.L, d_klo, d_ncand, d_cand_base, d_exit, d_cnt, d_last);
+    k_chain_walk<<<static_cast<unsigned>(T), 128, 0, s>>>(J.d_P, J.d_next, d_klo, d_ncand, d_cand_base, d_exit, d_cnt, d_last);
     J.launches++;
     J.r_exit.resize(n_cand); J.r_cnt.resize(n_cand); J.r_last.resize(n_cand);
     if (n_cand) {
@@ -719,7 +759,7 @@ cudaError_t chain_emit(ChainJob& J, Src src, uint32_t id_base) {
     CK(J.mem.alloc(&J.d_ids, J.n_all + 1));
     CK(cudaMemcpyAsync(d_tile_entry, J.tile_entry.data(), T * 8, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(d_tile_base, J.tile_base.data(), (T + 1) * 8, cudaMemcpyHostToDevice, s));
-    k_chain_emit<<<static_cast<unsigned>((T + 127) / 128), 128, 0, s>>>(J.d_P, J.n, J.S, J.L, T, d_tile_entry, d_tile_base, J.d_cuts);
+    k_chain_emit<<<static_cast<unsigned>((T + 127) / 128), 128, 0, s>>>(J.d_next, J.n, T, J.d_klo, d_tile_entry, d_tile_base, J.d_cuts);
     J.launches++;
     if (J.n_all) {
         k_chain_ids<Src><<<static_cast<unsigned>((J.n_all + 2047) / 2048), 256, 0, s>>>(src, J.n_all, J.d_cuts, J.n_cuts, J.mask_zero, id_base, J.d_ids);
@@ -800,9 +840,9 @@ int pqg_regex_scan(pqg_ctx* ctx, pqg_plan* plan, const pqg_dfa* dfa, int neg, ui
     CUF(ctx, cudaEventRecord(e0, s));
     if (plan_any_dict(plan)) {
         P.skip_dict_pad = 1; // entries {start, len} only: the scan reads the dictionary chars in place
-        CUF(ctx, launch_dict_prepare(P, P.n_chunks, 0, 1, s));
+        CUF(ctx, launch_dict_prepare(P, P.n_chunks, 0, plan_str_dict_blocks(plan), s));
         k_regex_dict<<<dim3(64, P.n_chunks), 256, 0, s>>>(R);
-        launches += 2;
+        launches += 1 + dict_prepare_launches(0);
     }
     const size_t tab_pad = R.D.in_smem ? ((tab_smem + 15) & ~size_t(15)) : 0;
     R.cand_cap = plan_max_page_values(plan) <= kRxCand / 2 ? kRxCand / 2 : kRxCand;

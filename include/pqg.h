@@ -57,7 +57,8 @@ enum {
     PQG_PAGE_BAD_RUN = 3,       /* zero-length RLE run / empty literal run: reference UB */
     PQG_PAGE_DICT_TRUNCATED = 4,/* dictionary page shorter than its entries */
     PQG_PAGE_CHARS_OVERFLOW = 5,/* a column chunk decodes to >= 4 GiB of string bytes */
-    PQG_PAGE_LAYOUT = 6         /* internal: a PLAIN string page is not exactly its values (the plan re-runs with the size pass) */
+    PQG_PAGE_LAYOUT = 6,        /* internal: a string page broke the byte count the fast path assumed (the plan re-runs with the exact size pass) */
+    PQG_PAGE_CHARS_CAP = 7      /* internal: the chars buffer of the previous run is too small (the plan re-sizes it and re-runs) */
 };
 
 /* Physical types: reference enum ParquetType (include/common.hpp:16-25). */

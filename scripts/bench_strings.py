@@ -13,10 +13,11 @@ import time
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import bench
+import bench_scans as bench
 import pqb200 as pq
 
 rows = int(sys.argv[1]) if len(sys.argv) > 1 else 10_000_000
+only = sys.argv[2] if len(sys.argv) > 2 else ""  # cfg1 | cfg3 | cfg4: one workload only (ncu captures)
 rg_rows = 2_500_000
 rng = np.random.default_rng(7)
 L = pq.lib()
@@ -98,7 +99,23 @@ def run(name, col, rep):
     return out
 
 
-res = [run("cfg1 city: 8-entry dictionary, 30% nulls", dict_strings(rows, 8, b"City%03d", 7), 1),
-       run("cfg3 shape: 64K-entry dictionary 'city_%06u_x', 30% nulls", dict_strings(rows, 65536, b"city_%06d_x", 13), 1),
-       run("cfg4 shape: PLAIN email-like strings", bench.cfg4_email_column(rows, 5), 0)]
+def cfg1_city():
+    names = [b"Berlin", b"Dublin", b"Paris", b"Rome", b"Vienna", b"Amsterdam", b"Lisbon", b"Copenhagen"]
+    idx = rng.integers(0, 8, size=rows)
+    lens = np.array([len(x) for x in names], dtype=np.uint64)[idx]
+    off = np.zeros(rows + 1, dtype=np.uint64)
+    np.cumsum(lens, out=off[1:])
+    chars = np.frombuffer(b"".join(names[i] for i in idx[:0]), dtype=np.uint8)
+    table = np.zeros((8, 10), dtype=np.uint8)
+    for i, x in enumerate(names):
+        table[i, :len(x)] = np.frombuffer(x, dtype=np.uint8)
+    mask = np.arange(10)[None, :] < np.array([len(x) for x in names])[idx][:, None]
+    chars = table[idx][mask]
+    return dict(str_off=off, chars=chars, is_null=(rng.random(rows) < 0.3).astype(np.uint8))
+
+
+work = {"cfg1": lambda: run("cfg1 city: 8 city names (variable length), 30% nulls", cfg1_city(), 1),
+        "cfg3": lambda: run("cfg3 shape: 64K-entry dictionary 'city_%06u_x', 30% nulls", pq.synth_strings(pq.PQGEN_CITY64K, rows, 333, null_permille=300), 1),
+        "cfg4": lambda: run("cfg4 shape: PLAIN email-like strings", pq.synth_strings(pq.PQGEN_EMAILS, rows, 99), 0)}
+res = [f() for k, f in work.items() if not only or k == only]
 print(json.dumps({"hbm_peak_GBps": peak, "results": res}, indent=1))
