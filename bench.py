@@ -263,6 +263,7 @@ def main():
     ap.add_argument("--strings-rows", type=int, default=100_000_000, help="cfg3 shape: rows per GPU (0 = skip)")
     ap.add_argument("--regex-rows", type=int, default=270_000_000, help="cfg4: values of the ONE ~10 GB file (37 bytes of payload each; 0 = skip)")
     ap.add_argument("--chunk-rgs", type=int, default=64, help="cfg5 shape: alternating PLAIN / dictionary row groups of 5 M rows per GPU (64 = 6.4 GB; 0 = skip)")
+    ap.add_argument("--chunk-rg-rows", type=int, default=5_000_000)
     ap.add_argument("--scan-steps", type=int, default=5)
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -502,7 +503,7 @@ def main():
             line["regex"] = line_regex
         if a.chunk_rgs > 0:
             t0 = time.time()
-            line_ci = bs.chunk_index_bench(pq, local, stream, dd, min(scan_steps, 3), 1, peak, psrc, a.chunk_rgs, 5_000_000 if a.rows >= 50_000_000 else 500_000, want_cpu)
+            line_ci = bs.chunk_index_bench(pq, local, stream, dd, min(scan_steps, 3), 1, peak, psrc, a.chunk_rgs, a.chunk_rg_rows, want_cpu)
             line_ci["wall_s"] = time.time() - t0
             line["chunk_index"] = line_ci
     if rank == 0 and world == 1 and not a.no_cpu_baseline:

@@ -100,14 +100,17 @@ __global__ void __launch_bounds__(256) k_dict_prepare(DecodeParams P) {
 // entry (15 bytes + the length; meaningful when all entries are <= 15 bytes: one vector load per value).
 // The prefix chain is sequential by format; it is cut into kDictSeg-byte segments, one THREAD each, over as many CTAs
 // as the dictionary needs (a 1.1 MB dictionary: 8.6 K threads; one 1024-thread CTA took 0.31 ms of a 0.56 ms decode):
-//   k_dict_seg   every thread picks the first position of its segment that LOOKS like a prefix eight links deep
-//                (string inside the payload, and so for its 8 successors) and walks the chain from there to the end of
-//                its segment: (start, end, entries);
-//   k_dict_link  one warp per dictionary links the segments in order: a segment's start must be exactly where the
-//                previous walk ended, else the speculation failed (exactness check); 32 segments per step when the
-//                chain runs straight through them, one by one where a long string jumps over segments; on a failed
-//                link or a truncated page one lane walks the whole page like the reference does, with its error;
-//   k_dict_emit  every thread walks its segment again and writes its entries at its base index.
+//   k_dict_seg   every thread collects the first kDictCand positions of its segment that LOOK like a prefix eight links
+//                deep (string inside the payload, and so for its 8 successors) and walks the chain from each of them to
+//                the end of its segment: (start, end, entries).  More than one candidate, because the bytes in front of
+//                a prefix often pass the test too: "x" + the next prefix <0d 00 00> reads as a length whose string ends
+//                exactly on a later prefix whenever the entries have one size;
+//   k_dict_link  one warp per dictionary links the segments in order: a segment is entered exactly where the previous
+//                walk ended -- the candidate that starts there is the true one, no candidate there means the speculation
+//                failed (exactness check); 32 segments per step when the chain runs straight through them, one by one
+//                where a long string jumps over segments; on a failed link or a truncated page one lane walks the whole
+//                page like the reference does, with its error;
+//   k_dict_emit  every thread walks its segment again from the picked candidate and writes its entries at its base index.
 constexpr uint32_t kSegNone = 0xffffffffu;
 
 __device__ __forceinline__ uint32_t dict_next_of(const uint8_t* src, uint32_t size, uint32_t p) {
@@ -127,71 +130,198 @@ __global__ void __launch_bounds__(256) k_dict_seg(DecodeParams P) {
     DictSeg* segs = P.dict_segs + ck.dict_seg_first;
     for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nseg; t += gridDim.x * blockDim.x) {
         const uint32_t lo = t * kDictSeg, hi = min(size, lo + kDictSeg);
-        uint32_t start = kSegNone, endp = kSegNone, cnt = 0;
-        if (t == 0) start = 0;
+        DictSeg sg;
+#pragma unroll
+        for (int c = 0; c < kDictCand; c++) { sg.start[c] = kSegNone; sg.end[c] = kSegNone; sg.cnt[c] = 0; }
+        sg.base = kSegNone; sg.pick = 0;
+        int nc = 0;
+        if (t == 0) { sg.start[0] = 0; nc = 1; }
         else {
-            for (uint32_t p = lo; p < hi && start == kSegNone; p++) {
-                uint32_t q = p;
-                int depth = 0;
-                for (; depth < 8; depth++) { q = dict_next_of(src, size, q); if (q == kSegNone) break; if (q == size) { depth = 8; break; } }
-                if (depth >= 8) start = p;
+            // first link for every position of the segment (independent loads: they overlap), survivors in a bit mask
+            uint32_t m[kDictSeg / 32] = {};
+#pragma unroll 8
+            for (uint32_t i = 0; i < kDictSeg; i++) {
+                const uint32_t p = lo + i;
+                const bool okp = p < hi && dict_next_of(src, size, p) != kSegNone;
+                if (okp) m[i >> 5] |= 1u << (i & 31u);
+            }
+#pragma unroll
+            for (uint32_t wi = 0; wi < kDictSeg / 32; wi++) {
+                uint32_t bits = m[wi];
+                while (bits && nc < kDictCand) {
+                    const uint32_t p = lo + wi * 32u + static_cast<uint32_t>(__ffs(static_cast<int>(bits)) - 1);
+                    bits &= bits - 1;
+                    uint32_t q = p;
+                    int depth = 0;
+                    for (; depth < 8; depth++) { q = dict_next_of(src, size, q); if (q == kSegNone) break; if (q == size) { depth = 8; break; } }
+                    if (depth >= 8) {
+#pragma unroll
+                        for (int c = 0; c < kDictCand; c++) if (c == nc) sg.start[c] = p;
+                        nc++;
+                    }
+                }
             }
         }
-        if (start != kSegNone) {
-            uint32_t p = start;
-            while (p < hi) { const uint32_t q = dict_next_of(src, size, p); if (q == kSegNone) break; cnt++; p = q; }
-            endp = p; // first chain position >= hi, or the position where the chain broke
+        { // the candidates' walks, in lockstep (independent chains: their loads overlap)
+            uint32_t p[kDictCand], cnt[kDictCand];
+            bool go[kDictCand];
+#pragma unroll
+            for (int c = 0; c < kDictCand; c++) { p[c] = sg.start[c]; cnt[c] = 0; go[c] = sg.start[c] != kSegNone && p[c] < hi; }
+            while (go[0] || go[1] || go[2] || go[3]) {
+#pragma unroll
+                for (int c = 0; c < kDictCand; c++) {
+                    if (!go[c]) continue;
+                    const uint32_t q = dict_next_of(src, size, p[c]);
+                    if (q == kSegNone) { go[c] = false; continue; }
+                    cnt[c]++; p[c] = q;
+                    go[c] = q < hi;
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < kDictCand; c++) if (sg.start[c] != kSegNone) { sg.end[c] = p[c]; sg.cnt[c] = static_cast<uint16_t>(cnt[c]); }
         }
-        segs[t] = DictSeg{start, endp, cnt, kSegNone};
+        segs[t] = sg;
     }
 }
 
-__global__ void __launch_bounds__(32) k_dict_link(DecodeParams P) {
+static_assert(kDictCand == 4, "k_dict_seg / k_dict_link unroll four candidates");
+constexpr int kLinkThreads = 256;
+__global__ void __launch_bounds__(kLinkThreads) k_dict_link(DecodeParams P) {
     DevChunk& ck = P.chunks[P.chunk_lo + blockIdx.x];
-    const uint32_t l = threadIdx.x;
-    if (!ck.has_dict) { if (l == 0) { ck.dict_ok_n = 0; ck.dict_minlen = 0xffffffffu; ck.dict_maxlen = 0; } return; }
+    const uint32_t tid = threadIdx.x, l = tid & 31u;
+    if (!ck.has_dict) { if (tid == 0) { ck.dict_ok_n = 0; ck.dict_minlen = 0xffffffffu; ck.dict_maxlen = 0; } return; }
     const uint8_t* src = P.image + ck.dict_off;
     const uint32_t n = ck.dict_n, size = ck.dict_size;
     const uint32_t nseg = (size + kDictSeg - 1) / kDictSeg;
     DictSeg* segs = P.dict_segs + ck.dict_seg_first;
+    // ---- the straight case, kLinkThreads segments per step: every walk ends inside the next segment, exactly one candidate
+    //      of every segment starts where a candidate of its left neighbour ends, and those picks form an exact chain from 0
+    {
+        __shared__ uint32_t s_pe[kLinkThreads], s_w[kLinkThreads / 32], s_bad;
+        uint32_t carry_base = 0, carry_cur = 0;
+        bool straight = n > 0;
+        if (tid == 0) s_bad = 0;
+        __syncthreads();
+        for (uint32_t c0 = 0; c0 < nseg && straight; c0 += kLinkThreads) {
+            const uint32_t t = c0 + tid;
+            const bool live = t < nseg;
+            uint32_t pstart = kSegNone, pe = kSegNone, pcnt = 0;
+            int pick = -1, npick = 0;
+            if (live) {
+                const DictSeg sg = segs[t];
+                uint32_t lend[kDictCand] = {kSegNone, kSegNone, kSegNone, kSegNone};
+                if (t > 0) {
+#pragma unroll
+                    for (int d = 0; d < kDictCand; d++) lend[d] = segs[t - 1].end[d];
+                }
+#pragma unroll
+                for (int c = 0; c < kDictCand; c++) {
+                    bool sup = false;
+                    if (sg.start[c] != kSegNone) {
+                        if (t == 0) sup = sg.start[c] == 0u;
+                        else {
+#pragma unroll
+                            for (int d = 0; d < kDictCand; d++) sup = sup || lend[d] == sg.start[c];
+                        }
+                    }
+                    if (sup) { if (pick < 0) { pick = c; pstart = sg.start[c]; pe = sg.end[c]; pcnt = sg.cnt[c]; } npick++; }
+                }
+            }
+            s_pe[tid] = pe;
+            __syncthreads();
+            const uint32_t thi = min(size, (t + 1) * kDictSeg), next_hi = min(size, (t + 2) * kDictSeg);
+            const uint32_t want = tid == 0 ? carry_cur : s_pe[tid - 1];
+            const bool fine = !live || (npick == 1 && pstart == want && pe >= thi && (pe < next_hi || pe == size));
+            // block-wide exclusive scan of the entry counts
+            const uint32_t incl = warp_incl_scan(pcnt);
+            if (l == 31) s_w[tid >> 5] = incl;
+            if (!fine) s_bad = 1;
+            __syncthreads();
+            uint32_t wbase = 0, total = 0;
+#pragma unroll
+            for (int i = 0; i < kLinkThreads / 32; i++) { const uint32_t x = s_w[i]; if (i < static_cast<int>(tid >> 5)) wbase += x; total += x; }
+            if (s_bad || carry_base + total > n) { straight = false; break; }
+            if (live) { segs[t].base = carry_base + wbase + incl - pcnt; segs[t].pick = static_cast<uint32_t>(pick); }
+            carry_base += total;
+            carry_cur = s_pe[min(static_cast<uint32_t>(kLinkThreads) - 1u, nseg - 1u - c0)];
+            __syncthreads();
+        }
+        if (straight && carry_base == n) {
+            if (tid == 0) { ck.dict_ok_n = n; ck.dict_minlen = 0xffffffffu; ck.dict_maxlen = 0; }
+            return;
+        }
+    }
+    // ---- anything else (a string longer than a segment, trailing bytes behind the entries, ambiguous candidates): one warp,
+    //      segment by segment where needed
+    __syncthreads();
+    for (uint32_t t = tid; t < nseg; t += kLinkThreads) segs[t].base = kSegNone;
+    __syncthreads();
+    if (tid >= 32) return;
     __shared__ DictSeg sb[32];
     uint32_t cur = 0, base = 0, ok = n > 0 ? 1u : 0u;
     for (uint32_t b0 = 0; b0 < nseg && ok && base < n; b0 += 32) {
         const uint32_t t = b0 + l;
         const bool live = t < nseg;
-        DictSeg sg = live ? segs[t] : DictSeg{kSegNone, kSegNone, 0, kSegNone};
-        const uint32_t thi = min(size, (t + 1) * kDictSeg);
-        // straight run: every segment starts where its predecessor ended, and ends inside (or at the start of) the next one
-        const uint32_t prev_end = __shfl_up_sync(0xffffffffu, sg.end, 1);
-        const uint32_t want = l == 0 ? cur : prev_end;
-        const uint32_t next_hi = min(size, (t + 2) * kDictSeg);
-        const bool fine = !live || (sg.start == want && sg.start != kSegNone && sg.end >= thi && (sg.end < next_hi || sg.end == size));
-        const uint32_t incl = warp_incl_scan(live ? sg.cnt : 0u);
+        DictSeg sg;
+        if (live) sg = segs[t];
+        else {
+#pragma unroll
+            for (int c = 0; c < kDictCand; c++) { sg.start[c] = kSegNone; sg.end[c] = kSegNone; sg.cnt[c] = 0; }
+        }
+        const uint32_t thi = min(size, (t + 1) * kDictSeg), next_hi = min(size, (t + 2) * kDictSeg);
+        // straight run: the walk of every segment ends inside the next one (or at the page end).  Then the candidate a
+        // segment is entered at is the one some candidate of its left neighbour ends on; picked that way in parallel,
+        // then verified as an exact chain from `cur`.
+        uint32_t pend[kDictCand];
+#pragma unroll
+        for (int c = 0; c < kDictCand; c++) pend[c] = __shfl_up_sync(0xffffffffu, sg.end[c], 1);
+        int pick = -1, npick = 0;
+#pragma unroll
+        for (int c = 0; c < kDictCand; c++) {
+            bool sup = false;
+            if (sg.start[c] != kSegNone) {
+                if (l == 0) sup = sg.start[c] == cur;
+                else {
+#pragma unroll
+                    for (int d = 0; d < kDictCand; d++) sup = sup || pend[d] == sg.start[c];
+                }
+            }
+            if (sup) { if (pick < 0) pick = c; npick++; }
+        }
+        uint32_t pstart = kSegNone, pe = kSegNone, pcnt = 0;
+#pragma unroll
+        for (int c = 0; c < kDictCand; c++) if (c == pick) { pstart = sg.start[c]; pe = sg.end[c]; pcnt = sg.cnt[c]; }
+        const uint32_t left_end = __shfl_up_sync(0xffffffffu, pe, 1);
+        const uint32_t want = l == 0 ? cur : left_end;
+        const bool fine = !live || (npick == 1 && pstart == want && pe >= thi && (pe < next_hi || pe == size));
+        const uint32_t incl = warp_incl_scan(live ? pcnt : 0u);
         const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
         if (__all_sync(0xffffffffu, fine) && base + total <= n) {
-            if (live) segs[t].base = base + incl - sg.cnt;
+            if (live) { segs[t].base = base + incl - pcnt; segs[t].pick = static_cast<uint32_t>(pick); }
             base += total;
-            const uint32_t last = min(31u, nseg - 1u - b0);
-            cur = __shfl_sync(0xffffffffu, sg.end, last);
+            cur = __shfl_sync(0xffffffffu, pe, min(31u, nseg - 1u - b0));
             continue;
         }
-        // one by one (a string longer than a segment, the end of the entries, or a failed speculation)
+        // one by one (a string longer than a segment, the end of the entries, ambiguous candidates, a failed speculation)
         sb[l] = sg;
         __syncwarp();
         if (l == 0) {
             for (uint32_t i = 0; i < 32u && b0 + i < nseg; i++) {
                 const uint32_t tt = b0 + i, tlo = tt * kDictSeg, hh = min(size, tlo + kDictSeg);
-                uint32_t bse = kSegNone;
-                if (ok && base < n && cur < hh) {             // (cur >= hh: a string spans the whole segment)
-                    if (sb[i].start != cur) ok = 0;            // speculation failed
+                uint32_t bse = kSegNone, pk = 0;
+                if (ok && base < n && cur < hh) {              // (cur >= hh: a string spans the whole segment)
+                    int c = 0;
+                    while (c < kDictCand && sb[i].start[c] != cur) c++;
+                    if (c == kDictCand) ok = 0;                 // nobody starts where the chain enters: speculation failed
                     else {
-                        bse = base;
-                        base += sb[i].cnt;
-                        cur = sb[i].end;
+                        bse = base; pk = static_cast<uint32_t>(c);
+                        base += sb[i].cnt[c];
+                        cur = sb[i].end[c];
                         if (cur < hh && base < n) ok = 0;      // the chain broke before n entries: truncated page
                     }
                 }
                 segs[tt].base = bse;
+                segs[tt].pick = pk;
             }
         }
         cur = __shfl_sync(0xffffffffu, cur, 0);
@@ -240,7 +370,9 @@ __global__ void __launch_bounds__(256) k_dict_emit(DecodeParams P) {
         const DictSeg sg = segs[t];
         if (sg.base == kSegNone) continue;
         const uint32_t hi = min(size, (t + 1) * kDictSeg);
-        uint32_t p = sg.start, k = sg.base;
+        uint32_t p = sg.start[0], k = sg.base;
+#pragma unroll
+        for (int c = 1; c < kDictCand; c++) if (static_cast<uint32_t>(c) == sg.pick) p = sg.start[c];
         while (p < hi && k < n) {
             const uint32_t q = dict_next_of(src, size, p);
             if (q == kSegNone) break;
@@ -735,6 +867,131 @@ __device__ __forceinline__ uint32_t copy_ranked_dict_tile(const DecodeParams& P,
     return outp;
 }
 
+// ---- copy pass, PLAIN pages, lanes by RANK ------------------------------------------------------
+// One tile (= the whole page, staged in the shared slot) whose length prefixes were found (ws.idx holds the u16 position
+// of every prefix inside the value section, in order) and whose strings are all <= kStageMaxLen bytes.  The chars of
+// the page are the value section minus the prefixes: string k starts at pos[k] - 4 k.  Every lane ORs its string into
+// the zeroed staging buffer WORD-wise -- aligned words of the slot, one funnel shift for the phase difference between
+// source and destination, first / last word masked -- instead of byte by byte (33 byte stores per e-mail address
+// before), and the buffer leaves as full aligned 16-byte vectors.  Offsets by slot afterwards (nulls: next string).
+template <int NW>
+__device__ __forceinline__ void stage_or_words(uint32_t stage_s, uint32_t o, uint32_t sp, uint32_t len) {
+    // `len` bytes at shared address `sp` -> stage byte offset `o`
+    const uint32_t d = o & 3u, src0 = sp - d, sa = src0 & ~3u, sh = (src0 & 3u) * 8u;
+    const uint32_t nw = (d + len + 3u) >> 2, da = stage_s + (o & ~3u), tail = (d + len) & 3u;
+    uint32_t wp;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wp) : "r"(sa));
+#pragma unroll
+    for (int j = 0; j < NW; j++) {
+        if (static_cast<uint32_t>(j) < nw) {
+            uint32_t wn;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wn) : "r"(sa + 4u * (j + 1)));
+            uint32_t x = __funnelshift_r(wp, wn, sh);
+            if (j == 0) x &= 0xffffffffu << (8u * d);
+            if (static_cast<uint32_t>(j) == nw - 1u && tail) x &= (1u << (8u * tail)) - 1u;
+            if (x) asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(da + 4u * j), "r"(x) : "memory");
+            wp = wn;
+        }
+    }
+}
+
+__device__ __forceinline__ uint32_t copy_ranked_plain_tile(const DecodeParams& P, WarpScratch& ws, const uint8_t* vals, uint32_t t, uint32_t nn,
+                                                           uint32_t maxlen, uint32_t* offs_tile, uint8_t* dst, uint32_t off0, uint64_t abs_slot0) {
+    const uint32_t l = lane_id();
+    const uint16_t* pos16 = reinterpret_cast<const uint16_t*>(ws.idx);
+    const uint32_t stw = static_cast<uint32_t>(__cvta_generic_to_shared(ws.stage));
+    const uint32_t vs = static_cast<uint32_t>(__cvta_generic_to_shared(vals));
+    for (uint32_t i = l; i < static_cast<uint32_t>(kStageBytes32) / 16u; i += 32) reinterpret_cast<uint4*>(ws.stage)[i] = make_uint4(0, 0, 0, 0);
+    __syncwarp();
+    const uint32_t mis0 = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(dst) & 15u);
+    uint8_t* const abase = dst - mis0;
+    uint32_t outp = 0, sbase = 0;
+    for (uint32_t g = 0; g < nn; g += 32) {
+        const uint32_t k = g + l;
+        uint32_t len = 0, pp = 0;
+        if (k < nn) { pp = pos16[k]; len = SmemWords{vs & ~3u}.u16at((vs & 3u) + pp) | (SmemWords{vs & ~3u}.u16at((vs & 3u) + pp + 2u) << 16); }
+        const uint32_t my = pp - 4u * k;                       // start of string k in the page's chars
+        const uint32_t last = min(nn, g + 32u) - 1u;           // the group ends where its last string ends
+        const uint32_t lend = __shfl_sync(0xffffffffu, my + len, last - g);
+        const uint32_t total = lend - outp;
+        if (total) {
+            if (len) {
+                const uint32_t o = mis0 + my - sbase;
+                if (maxlen <= 16u) stage_or_words<5>(stw, o, vs + pp + 4u, len);
+                else if (maxlen <= 32u) stage_or_words<9>(stw, o, vs + pp + 4u, len);
+                else stage_or_words<13>(stw, o, vs + pp + 4u, len);
+            }
+            __syncwarp();
+            outp += total;
+            const uint32_t end = mis0 + outp;
+            const uint32_t nfull = (end >> 4) - (sbase >> 4);
+            if (nfull) {
+                if (sbase == 0 && mis0) { // first vector: the bytes in front belong to another page
+                    if (l >= mis0 && l < 16u) abase[l] = ws.stage[l];
+                    __syncwarp();
+                }
+                for (uint32_t j = l; j < nfull; j += 32) {
+                    const uint4 v = *reinterpret_cast<const uint4*>(ws.stage + 16u * j);
+                    *reinterpret_cast<uint4*>(ws.stage + 16u * j) = make_uint4(0, 0, 0, 0);
+                    if (sbase + j || !mis0) *reinterpret_cast<uint4*>(abase + sbase + 16u * j) = v;
+                }
+                __syncwarp();
+                if (l == 0) { // the partial vector moves to the front
+                    const uint4 v = *reinterpret_cast<const uint4*>(ws.stage + 16u * nfull);
+                    *reinterpret_cast<uint4*>(ws.stage + 16u * nfull) = make_uint4(0, 0, 0, 0);
+                    *reinterpret_cast<uint4*>(ws.stage) = v;
+                }
+                sbase += 16u * nfull;
+                __syncwarp();
+            }
+        } else {
+            __syncwarp();
+        }
+    }
+    { // the bytes behind the last complete vector (and a first vector that never filled up)
+        const uint32_t end = mis0 + outp;
+        const uint32_t from = sbase == 0 ? mis0 : sbase;
+        if (from + l < end) abase[from + l] = ws.stage[from - sbase + l]; // < 16 bytes
+        __syncwarp();
+        if (l == 0) *reinterpret_cast<uint4*>(ws.stage) = make_uint4(0, 0, 0, 0);
+    }
+    // offsets by slot, four consecutive slots per lane (they share a validity word)
+    for (uint32_t s0 = 4u * l; s0 < t; s0 += 128u) {
+        const uint32_t wv = ws.valid[s0 >> 5], b = s0 & 31u;
+        uint32_t r = ws.rankbase[s0 >> 5] + __popc(wv & ((1u << b) - 1u));
+        uint32_t o[4];
+#pragma unroll
+        for (uint32_t j = 0; j < 4u; j++) {
+            o[j] = off0 + (r < nn ? static_cast<uint32_t>(pos16[r]) - 4u * r : outp);
+            r += (wv >> (b + j)) & 1u;
+        }
+        uint32_t* op = offs_tile + s0;
+        if (s0 + 3u < t && (reinterpret_cast<uintptr_t>(op) & 15u) == 0) *reinterpret_cast<uint4*>(op) = make_uint4(o[0], o[1], o[2], o[3]);
+        else {
+#pragma unroll
+            for (uint32_t j = 0; j < 4u; j++) if (s0 + j < t) op[j] = o[j];
+        }
+    }
+    if (P.validity) {
+        const uint32_t head = static_cast<uint32_t>(abs_slot0 & 31u), nwords = (t + 31u) >> 5;
+        uint32_t* vp = P.validity + (abs_slot0 >> 5);
+        const uint32_t cur = l < nwords ? ws.valid[l] : 0u;
+        const uint32_t prev = (l > 0 && l <= nwords) ? ws.valid[l - 1] : 0u;
+        const uint32_t gw = head ? ((cur << head) | (prev >> (32u - head))) : cur;
+        const uint32_t totb = head + t, gwords = (totb + 31u) >> 5;
+        if (l < gwords) {
+            const bool full = (l > 0 || head == 0) && (l + 1u) * 32u <= totb;
+            if (full) vp[l] = gw; else if (gw) atomicOr(&vp[l], gw);
+        }
+        if (l == 0 && gwords > 32u) {
+            const uint32_t last = ws.valid[31] >> (32u - head);
+            if (last) atomicOr(&vp[32], last);
+        }
+    }
+    __syncwarp();
+    return outp;
+}
+
 // LEAN: the plan has dictionary chunks -- compile the short-string-dictionary copy path in (kept out of the
 // instantiation that PLAIN-only plans run: its registers cost the PLAIN path 7 %)
 template <bool COPY, bool LEAN>
@@ -749,8 +1006,10 @@ __device__ __forceinline__ void decode_str_page(const DecodeParams& P, uint32_t 
         // decoded.  Optimistic in one point: an RLE run INSIDE the index stream carries an unmasked value that may be
         // out of range (a null in the reference, so fewer bytes); the copy pass compares every page's bytes with this
         // count and the plan falls back to the exact size pass (P.exact_sizes) on a mismatch.
+        // PLAIN pages the same way: the value section is exactly its present values (4-byte prefix + bytes each), so the
+        // page's bytes are the section minus 4 per present slot -- header arithmetic, verified by the copy pass as well.
         const bool dict_page = (pd.flags & PQG_PAGE_FLAG_DICT) && ck.has_dict;
-        if (dict_page && !P.exact_sizes && ck.dict_len() != 0xffffffffu && ck.max_rep <= 0 && ck.max_def <= 1) {
+        if (!P.exact_sizes && (!dict_page || ck.dict_len() != 0xffffffffu) && ck.max_rep <= 0 && ck.max_def <= 1) {
             const uint8_t* src = P.image + pd.payload_off;
             const uint32_t size = pd.payload_size, n = pd.num_values;
             uint32_t pos = 0, nn = n;
@@ -775,12 +1034,15 @@ __device__ __forceinline__ void decode_str_page(const DecodeParams& P, uint32_t 
                     pos = 4u + def_len;
                 }
             }
-            if (ok) {
+            if (ok && dict_page) {
                 const uint32_t bw = pos < size ? src[pos] : 99u;
                 if (bw < 32u && ck.dict_ok_n >= (1u << bw)) {
                     if (l == 0) P.page_chars[q] = ck.dict_len() * nn;
                     return;
                 }
+            } else if (ok && static_cast<uint64_t>(pos) + 4ull * nn <= size) {
+                if (l == 0) P.page_chars[q] = size - pos - 4u * nn;
+                return;
             }
         }
     }
@@ -802,9 +1064,9 @@ __device__ __forceinline__ void decode_str_page(const DecodeParams& P, uint32_t 
     uint8_t* chars = COPY ? P.chars + ck.char_base : nullptr;
     uint64_t page_bytes = 0;                       // running string bytes of this page
     const uint32_t page_base = COPY ? P.page_char_base[q] : 0;
-    bool regular = false;
+    bool regular = false, plain_found = false;
     RegStream rs{};
-    uint32_t nn_before = 0, wpos = 0;
+    uint32_t nn_before = 0, wpos = 0, plain_maxlen = 0xffffffffu;
     for (uint32_t ts = 0; ts < c.n; ts += T_) {
         const uint32_t t = min(T_, c.n - ts);
         uint32_t bad = 0;
@@ -822,9 +1084,33 @@ __device__ __forceinline__ void decode_str_page(const DecodeParams& P, uint32_t 
             // parallel length-prefix discovery first (text pages); sequential walk otherwise
             bool found = false;
             if (single && !wide) {
-                uint32_t endp = 0;
-                found = find_headers(vals, vavail, nn, reinterpret_cast<uint16_t*>(ws.idx), static_cast<uint32_t>(kIdxWords) * 2u, &endp);
-                if (found) wpos = endp;
+                // values of ONE length: the section is nn x (4 + len) bytes and string k sits at k * stride -- verified exactly
+                // (every prefix reads len: by induction those are the prefixes of the chain); no candidate search
+                const uint32_t stride = nn ? vavail / nn : 0u;
+                if (nn && stride >= 4u && stride * nn == vavail && vavail <= 65535u && nn <= static_cast<uint32_t>(kIdxWords) * 2u) {
+                    bool same = true;
+                    for (uint32_t k = l; k < nn; k += 32) same = same && ld32u(vals + k * stride) == stride - 4u;
+                    if (__all_sync(0xffffffffu, same)) {
+                        for (uint32_t k = l; k < nn; k += 32) reinterpret_cast<uint16_t*>(ws.idx)[k] = static_cast<uint16_t>(k * stride);
+                        __syncwarp();
+                        found = true;
+                        wpos = vavail;
+                        plain_maxlen = stride - 4u;
+                    }
+                }
+                if (!found) {
+                    uint32_t endp = 0;
+                    found = find_headers(vals, vavail, nn, reinterpret_cast<uint16_t*>(ws.idx), static_cast<uint32_t>(kIdxWords) * 2u, &endp);
+                    if (found) {
+                        wpos = endp;
+                        if (COPY) { // longest string of the page (the word-wise staging takes <= kStageMaxLen bytes per string)
+                            uint32_t mx = 0;
+                            for (uint32_t k = l; k < nn; k += 32) mx = max(mx, ld32u(vals + reinterpret_cast<const uint16_t*>(ws.idx)[k]));
+                            plain_maxlen = __reduce_max_sync(0xffffffffu, mx);
+                        }
+                    }
+                }
+                plain_found = found;
             }
             uint32_t epos = 0, eneed = 0;
             if (!found && !walk_strings(vals, vavail, &wpos, nn, ws, wide, COPY, &epos, &eneed)) {
@@ -875,6 +1161,14 @@ __device__ __forceinline__ void decode_str_page(const DecodeParams& P, uint32_t 
             }
             page_bytes += copy_short_dict_tile(P, ws, rs, nn_before, t, dpad, dict_n, offs + slot0, chars + page_base + page_bytes,
                                                static_cast<uint32_t>(page_base + page_bytes), pd.out_row_base + ts);
+            nn_before += nn;
+            __syncwarp();
+            continue;
+        }
+        if (!c.dict && plain_found && plain_maxlen <= static_cast<uint32_t>(kStageMaxLen) && c.size <= static_cast<uint32_t>(kSlotBytes)) {
+            // PLAIN page in the shared slot, prefixes known, short strings: lanes by rank, word-wise staging
+            page_bytes += copy_ranked_plain_tile(P, ws, vals, t, nn, plain_maxlen, offs + slot0, chars + page_base + page_bytes,
+                                                 static_cast<uint32_t>(page_base + page_bytes), pd.out_row_base + ts);
             nn_before += nn;
             __syncwarp();
             continue;
@@ -971,8 +1265,8 @@ __device__ __forceinline__ void decode_str_page(const DecodeParams& P, uint32_t 
         // byte counts taken from the page headers (no size pass) hold only if the page is exactly its values
         if (P.check_layout && !c.dict && l == 0 && page_bytes != static_cast<uint64_t>(vavail) - 4ull * nn_before)
             report_error(P.err, q, PQG_PAGE_LAYOUT);
-        // the size pass counted this dictionary page optimistically (see there): hold it to its word
-        if (c.dict && !P.exact_sizes && l == 0 && page_bytes != P.page_chars[q]) report_error(P.err, q, PQG_PAGE_LAYOUT);
+        // the size pass counted this page optimistically (see there): hold it to its word
+        if (!P.check_layout && !P.exact_sizes && l == 0 && page_bytes != P.page_chars[q]) report_error(P.err, q, PQG_PAGE_LAYOUT);
         // the last page of the chunk closes the Arrow offsets array
         if (l == 0 && q + 1 == ck.first_page + ck.n_pages)
             offs[(pd.out_row_base - ck.out_row_base) + c.n] = static_cast<uint32_t>(page_base + page_bytes);
@@ -1072,7 +1366,7 @@ cudaError_t launch_dict_prepare(const DecodeParams& p, uint32_t n_chunks, int wi
     if (width == 0) { // strings: segments over many CTAs, one warp per dictionary to link them, entries over many CTAs
         dim3 grid(max_dict_blocks ? max_dict_blocks : 1u, n_chunks);
         k_dict_seg<<<grid, 256, 0, s>>>(p);
-        k_dict_link<<<n_chunks, 32, 0, s>>>(p);
+        k_dict_link<<<n_chunks, kLinkThreads, 0, s>>>(p);
         k_dict_emit<<<grid, 256, 0, s>>>(p);
         return cudaGetLastError();
     }

@@ -57,7 +57,10 @@ struct DevChunk {
     __device__ __forceinline__ uint32_t dict_len() const { return (dict_ok_n > 0 && dict_minlen == dict_maxlen) ? dict_maxlen : 0xffffffffu; }
 #endif
 };
-struct DictSeg { uint32_t start, end, cnt, base; }; // one segment of a BYTE_ARRAY dictionary page (k_dict_seg / _link / _emit)
+// one segment of a BYTE_ARRAY dictionary page (k_dict_seg / _link / _emit): up to kDictCand speculative entry positions,
+// each with the end of its walk and its entry count; the link picks the one the chain from the left really enters at
+constexpr int kDictCand = 4;
+struct DictSeg { uint32_t start[kDictCand], end[kDictCand]; uint16_t cnt[kDictCand]; uint32_t base, pick; };
 constexpr uint32_t kDictSeg = 128;                  // bytes per segment
 
 // First failing page (lowest page-table index) of a run, plus the per-run work counters

@@ -329,7 +329,38 @@ __global__ void __launch_bounds__(kThreadsPerCta, 4) k_regex_tiles(RegexParams R
                     const SmemWords ld{va & ~3u};
                     const uint32_t o = va & 3u;
                     uint32_t endp = 0, c1 = 0, len1 = 0;
-                    if (!find_headers_w(ld, o, size - pos, nn, cand, R.cand_cap, &endp, &c1, &len1)) slow = true;
+                    // Values of ONE length (header arithmetic): the section is nn x (4 + len) bytes, so string k sits at
+                    // k * stride -- verified exactly (every prefix must read len; by induction those ARE the prefixes of
+                    // the chain), and no candidate search is needed.
+                    const uint32_t vsec = size - pos;
+                    const uint32_t stride = nn ? vsec / nn : 0u;
+                    bool uniform = nn > 0 && stride >= 4u && stride * nn == vsec && vsec <= 65535u && nn <= R.cand_cap;
+                    if (uniform) {
+                        const uint32_t ulen = stride - 4u;
+                        bool same = true;
+                        for (uint32_t k = l; k < nn; k += 32) {
+                            const uint32_t a = k * stride + o;
+                            same = same && __funnelshift_r(ld(a >> 2), ld((a >> 2) + 1u), (a & 3u) * 8u) == ulen;
+                        }
+                        uniform = __all_sync(0xffffffffu, same);
+                        if (uniform) {
+                            for (uint32_t k0 = 0; k0 < nn && !hit; k0 += 32) {
+                                const uint32_t k = k0 + l;
+                                bool h = false;
+                                if (k < nn) {
+                                    bool m;
+                                    if (R.D.scaled) {
+                                        const uint32_t st = dfa_run_abs(start_s, trans_s, dead_s, ld, k * stride + o + 4u, ulen);
+                                        m = accept[(st - trans_s) >> 9] != 0;
+                                    } else m = dfa_run(R.D, trans, cls, accept, vals + k * stride + 4, ulen);
+                                    h = R.neg ? !m : m;
+                                }
+                                hit = __any_sync(0xffffffffu, h);
+                            }
+                        }
+                    }
+                    if (uniform) { /* done */ }
+                    else if (!find_headers_w(ld, o, size - pos, nn, cand, R.cand_cap, &endp, &c1, &len1)) slow = true;
                     else {
                         for (uint32_t k0 = 0; k0 < nn && !hit; k0 += 32) {
                             uint32_t k = k0 + l;
@@ -383,13 +414,14 @@ struct StrWeights {
         uint32_t len = off[1] - off[0];
         return dec_digits(len) + len;
     }
-    __device__ uint32_t operator()(uint64_t i) const { uint32_t c = chunk_of(i); return at(i, c); }
+    // zero weight <=> null (a non-null string weighs at least the one digit of its length)
+    __device__ bool is_zero(uint64_t i) const { return validity && !((validity[i >> 5] >> (i & 31)) & 1u); }
 };
 struct ArrWeights {
     const uint32_t* w;
     __device__ uint32_t chunk_of(uint64_t) const { return 0; }
     __device__ uint32_t at(uint64_t i, uint32_t&) const { return w[i]; }
-    __device__ uint32_t operator()(uint64_t i) const { return w[i]; }
+    __device__ bool is_zero(uint64_t i) const { return w[i] == 0; }
 };
 
 constexpr int kScanThreads = 256;
@@ -427,21 +459,29 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_reduce(Src src, uint64_t 
     if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
 }
 
-// single block: exclusive scan of the block sums in place; grand total -> sums[nb]
-__global__ void __launch_bounds__(kScanThreads) k_scan_sums(uint64_t* sums, uint64_t nb) {
-    __shared__ uint64_t carry;
-    if (threadIdx.x == 0) carry = 0;
+// single block of 1024 threads: exclusive scan of the block sums in place; grand total -> sums[nb].
+// Every thread owns a contiguous run of the sums (sequential inside the run, one block-wide scan of the run totals).
+__global__ void __launch_bounds__(1024) k_scan_sums(uint64_t* sums, uint64_t nb) {
+    __shared__ uint64_t wsum[32];
+    const uint32_t tid = threadIdx.x, l = tid & 31u, w = tid >> 5;
+    const uint64_t per = (nb + 1023) / 1024, a = min(nb, tid * per), b = min(nb, a + per);
+    uint64_t run = 0;
+    for (uint64_t i = a; i < b; i++) run += sums[i];
+    uint64_t incl = run;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint64_t t = __shfl_up_sync(0xffffffffu, incl, d); if (l >= static_cast<uint32_t>(d)) incl += t; }
+    if (l == 31) wsum[w] = incl;
     __syncthreads();
-    for (uint64_t b0 = 0; b0 < nb; b0 += kScanThreads) {
-        uint64_t i = b0 + threadIdx.x;
-        uint64_t v = i < nb ? sums[i] : 0, total;
-        uint64_t ex = block_excl_scan(v, &total);
-        if (i < nb) sums[i] = carry + ex;
-        __syncthreads();
-        if (threadIdx.x == 0) carry += total;
-        __syncthreads();
+    if (w == 0) {
+        uint64_t x = wsum[l], xi = x;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { uint64_t t = __shfl_up_sync(0xffffffffu, xi, d); if (l >= static_cast<uint32_t>(d)) xi += t; }
+        wsum[l] = xi - x;
     }
-    if (threadIdx.x == 0) sums[nb] = carry;
+    __syncthreads();
+    uint64_t ex = wsum[w] + incl - run;
+    for (uint64_t i = a; i < b; i++) { const uint64_t v = sums[i]; sums[i] = ex; ex += v; }
+    if (tid == 1023) sums[nb] = ex;
 }
 
 // P[i] = exclusive prefix of the weights, P[n] = total
@@ -564,25 +604,40 @@ __global__ void k_chain_emit(const uint32_t* next, uint64_t n, uint64_t T, const
     while (k < end_slot) { cuts[o++] = k; k = next[k]; }
 }
 
-// ids[i] = number of cuts at slots <= i (0 for zero-weight slots when mask_zero)
+// ids[i] = number of cuts at slots <= i (0 for zero-weight slots when mask_zero).  A block takes kIdsBlock consecutive slots;
+// the cuts that fall into them (a handful: one per chunk size of weight) are staged in shared memory and every slot counts
+// the ones at or before it there.
+constexpr uint32_t kIdsBlock = 4096, kIdsCuts = 1024;
 template <class Src>
 __global__ void __launch_bounds__(256) k_chain_ids(Src src, uint64_t n, const uint64_t* cuts, uint64_t n_cuts, bool mask_zero, uint32_t id_base, uint32_t* ids) {
-    __shared__ uint64_t first;
-    const uint64_t b0 = static_cast<uint64_t>(blockIdx.x) * 2048u;
-    if (threadIdx.x == 0) { // cuts <= b0
+    __shared__ uint64_t first_s, last_s;
+    __shared__ uint32_t cs[kIdsCuts]; // block-relative slots of the cuts inside the block
+    const uint64_t b0 = static_cast<uint64_t>(blockIdx.x) * kIdsBlock, b1 = min(n, b0 + kIdsBlock);
+    if (threadIdx.x < 2) { // cuts < b0 (thread 0), cuts < b1 (thread 1)
+        const uint64_t x = threadIdx.x ? b1 : b0;
         uint64_t lo = 0, hi = n_cuts;
-        while (lo < hi) { uint64_t mid = (lo + hi) >> 1; if (cuts[mid] <= b0) lo = mid + 1; else hi = mid; }
-        first = lo;
+        while (lo < hi) { uint64_t mid = (lo + hi) >> 1; if (cuts[mid] < x) lo = mid + 1; else hi = mid; }
+        if (threadIdx.x) last_s = lo; else first_s = lo;
     }
     __syncthreads();
-    for (uint32_t j = threadIdx.x; j < 2048u; j += blockDim.x) {
-        uint64_t i = b0 + j;
-        if (i >= n) break;
-        // cuts are distinct slots: at most j + 1 of them lie in (b0, i]
-        uint64_t lo = first, hi = min(n_cuts, first + j + 1);
-        while (lo < hi) { uint64_t mid = (lo + hi) >> 1; if (cuts[mid] <= i) lo = mid + 1; else hi = mid; }
-        const uint64_t c = lo;
-        ids[i] = (mask_zero && src(i) == 0) ? 0u : id_base + static_cast<uint32_t>(c);
+    const uint64_t first = first_s;
+    const uint32_t nc = static_cast<uint32_t>(last_s - first);
+    const bool staged = nc <= kIdsCuts;
+    if (staged) for (uint32_t j = threadIdx.x; j < nc; j += blockDim.x) cs[j] = static_cast<uint32_t>(cuts[first + j] - b0);
+    __syncthreads();
+    for (uint32_t j = threadIdx.x; b0 + j < b1; j += blockDim.x) {
+        const uint64_t i = b0 + j;
+        uint64_t c;
+        if (staged) { // cuts at block-relative slots <= j
+            uint32_t lo = 0, hi = nc;
+            while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (cs[mid] <= j) lo = mid + 1; else hi = mid; }
+            c = first + lo;
+        } else {
+            uint64_t lo = first, hi = first + nc;
+            while (lo < hi) { uint64_t mid = (lo + hi) >> 1; if (cuts[mid] <= i) lo = mid + 1; else hi = mid; }
+            c = lo;
+        }
+        ids[i] = (mask_zero && src.is_zero(i)) ? 0u : id_base + static_cast<uint32_t>(c);
     }
 }
 
@@ -660,7 +715,7 @@ cudaError_t chain_prepare(ChainJob& J, Src src, uint64_t n, uint64_t S, bool mas
     CK(J.mem.alloc(&J.d_P, n + 1));
     if (nb) {
         k_scan_reduce<Src><<<static_cast<unsigned>(nb), kScanThreads, 0, s>>>(src, n, d_sums);
-        k_scan_sums<<<1, kScanThreads, 0, s>>>(d_sums, nb);
+        k_scan_sums<<<1, 1024, 0, s>>>(d_sums, nb);
         k_scan_write<Src><<<static_cast<unsigned>(nb), kScanThreads, 0, s>>>(src, n, d_sums, J.d_P);
         J.launches += 3;
     } else {
@@ -762,7 +817,7 @@ cudaError_t chain_emit(ChainJob& J, Src src, uint32_t id_base) {
     k_chain_emit<<<static_cast<unsigned>((T + 127) / 128), 128, 0, s>>>(J.d_next, J.n, T, J.d_klo, d_tile_entry, d_tile_base, J.d_cuts);
     J.launches++;
     if (J.n_all) {
-        k_chain_ids<Src><<<static_cast<unsigned>((J.n_all + 2047) / 2048), 256, 0, s>>>(src, J.n_all, J.d_cuts, J.n_cuts, J.mask_zero, id_base, J.d_ids);
+        k_chain_ids<Src><<<static_cast<unsigned>((J.n_all + kIdsBlock - 1) / kIdsBlock), 256, 0, s>>>(src, J.n_all, J.d_cuts, J.n_cuts, J.mask_zero, id_base, J.d_ids);
         J.launches++;
     }
     return cudaGetLastError();
