@@ -298,6 +298,16 @@ def main():
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py: no CUDA device; this framework has no CPU fallback")
     torch.cuda.set_device(local)
+    affinity = None
+    if world > 1 and hasattr(os, "sched_setaffinity"):
+        # every rank keeps to its own cores (page-header scan, staging copies): the ranks share one host
+        try:
+            cores_all = sorted(os.sched_getaffinity(0))
+            mine = cores_all[local::world] if len(cores_all) >= world else cores_all
+            os.sched_setaffinity(0, mine)
+            affinity = {"cores": len(mine), "of": len(cores_all)}
+        except OSError:
+            affinity = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -472,6 +482,72 @@ def main():
                   "H2D/decode/D2H pipelined per row group)",
            "parity": "decoded columns bit-identical to the generator's input arrays (full check after warm-up, tail check after the timed steps)",
            "pcie_GBps": {"h2d": h2d_bytes / e2e_s / 1e9, "d2h": d2h_bytes / e2e_s / 1e9}}
+    # ---- what the platform gives: the same bytes as plain copies, nothing else (pinned host <-> device, both directions at
+    #      once, every rank at the same time) -- the ceiling of ANY host-to-host path on this box
+    probe = None
+    try:
+        d_in = torch.empty(int(h2d_bytes), dtype=torch.uint8, device="cuda")
+        d_out = torch.empty(int(d2h_bytes), dtype=torch.uint8, device="cuda")
+        s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+        flat_out = [o.view(torch.uint8) for o in outs]
+        times = []
+        for it in range(3):
+            barrier()
+            t0 = time.perf_counter()
+            with torch.cuda.stream(s_in):
+                d_in.copy_(host[:int(h2d_bytes)], non_blocking=True)
+            with torch.cuda.stream(s_out):
+                off = 0
+                for fo in flat_out:
+                    fo.copy_(d_out[off:off + fo.numel()], non_blocking=True)
+                    off += fo.numel()
+            s_in.synchronize()
+            s_out.synchronize()
+            times.append(time.perf_counter() - t0)
+        probe_s = min(times[1:])
+        if world > 1:
+            t = torch.tensor([probe_s], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            probe_s = float(t.item())
+        probe = {"value": bytes_in * world / probe_s / 1e9, "unit": UNIT, "ms": probe_s * 1e3,
+                 "h2d_GBps": h2d_bytes * world / probe_s / 1e9, "d2h_GBps": d2h_bytes * world / probe_s / 1e9,
+                 "what": "the step's H2D and D2H bytes as bare cudaMemcpyAsync from / to pinned memory on two streams, all ranks at once, no kernels: "
+                         "the same metric if decoding were free"}
+        del d_in, d_out
+    except Exception as ex:  # never lose the headline to the probe
+        probe = {"error": str(ex)}
+    e2e["platform_ceiling"] = probe
+    if probe and probe.get("value"):
+        e2e["frac_of_platform_ceiling"] = e2e["value"] / probe["value"]
+    # ---- cold: a fresh reader (footer + page-header scan on the host threads, descriptor tables, plan and device buffers
+    #      built) and its first read -- what the reference's arm pays inside every read_column_by_idx
+    try:
+        for o in outs:
+            o.zero_()
+        barrier()
+        t0 = time.perf_counter()
+        r2 = pq.Reader.from_pointer(host.data_ptr(), size, device=local)
+        r2.read_columns_into(list(range(ncols)), dsts, -1)
+        torch.cuda.synchronize()
+        cold_s = time.perf_counter() - t0
+        open_s2 = r2.page_scan_seconds if hasattr(r2, "page_scan_seconds") else None
+        r2.close()
+        for c in range(ncols):
+            if not np.array_equal(outs[c].numpy().view(np.uint64)[::4099], np.ascontiguousarray(cols[c]["fixed"]).view(np.uint64)[::4099]):
+                raise AssertionError(f"bench parity check (cold read) failed on column {c}")
+        if world > 1:
+            t = torch.tensor([cold_s], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            cold_s = float(t.item())
+        e2e["cold"] = {"value": bytes_in * world / cold_s / 1e9, "unit": UNIT, "ms": cold_s * 1e3, "page_scan_ms": None if open_s2 is None else open_s2 * 1e3,
+                       "includes": "pqr_open_memory (footer parse + page-header scan of every column chunk on the host threads) + descriptor tables + "
+                                   "plan / device-buffer creation + the first pipelined read of all columns"}
+    except AssertionError:
+        raise
+    except Exception as ex:
+        e2e["cold"] = {"error": str(ex)}
+    if affinity:
+        e2e["rank_affinity"] = affinity
     reader.close()
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": warmup,

@@ -137,20 +137,18 @@ __global__ void __launch_bounds__(256) k_dict_seg(DecodeParams P) {
         int nc = 0;
         if (t == 0) { sg.start[0] = 0; nc = 1; }
         else {
-            // first link for every position of the segment (independent loads: they overlap), survivors in a bit mask
-            uint32_t m[kDictSeg / 32] = {};
-#pragma unroll 8
-            for (uint32_t i = 0; i < kDictSeg; i++) {
-                const uint32_t p = lo + i;
-                const bool okp = p < hi && dict_next_of(src, size, p) != kSegNone;
-                if (okp) m[i >> 5] |= 1u << (i & 31u);
-            }
+            // positions in groups of 8: their first links are independent loads (they overlap); the survivors get the
+            // deep test one by one; the scan stops at kDictCand accepted candidates (usually within two entries)
+            for (uint32_t g = lo; g < hi && nc < kDictCand; g += 8u) {
+                uint32_t m = 0;
 #pragma unroll
-            for (uint32_t wi = 0; wi < kDictSeg / 32; wi++) {
-                uint32_t bits = m[wi];
-                while (bits && nc < kDictCand) {
-                    const uint32_t p = lo + wi * 32u + static_cast<uint32_t>(__ffs(static_cast<int>(bits)) - 1);
-                    bits &= bits - 1;
+                for (uint32_t i = 0; i < 8u; i++) {
+                    const uint32_t p = g + i;
+                    if (p < hi && dict_next_of(src, size, p) != kSegNone) m |= 1u << i;
+                }
+                while (m && nc < kDictCand) {
+                    const uint32_t p = g + static_cast<uint32_t>(__ffs(static_cast<int>(m)) - 1);
+                    m &= m - 1;
                     uint32_t q = p;
                     int depth = 0;
                     for (; depth < 8; depth++) { q = dict_next_of(src, size, q); if (q == kSegNone) break; if (q == size) { depth = 8; break; } }
@@ -602,14 +600,17 @@ __device__ __forceinline__ void stage_words(uint8_t* dst, const uint4& v, uint32
 // only where a word is shared with a neighbouring page).  Returns the string bytes of the tile.
 __device__ __forceinline__ uint32_t copy_short_dict_tile(const DecodeParams& P, WarpScratch& ws, const RegStream& rs, uint32_t nn_before,
                                                          uint32_t t, const uint4* dpad, uint32_t dict_n, uint32_t* offs_tile, uint8_t* dst,
-                                                         uint32_t off0, uint64_t abs_slot0) {
+                                                         uint32_t off0, uint64_t abs_slot0, bool& stage_dirty) {
     const uint32_t l = lane_id();
     const uint32_t sa = static_cast<uint32_t>(__cvta_generic_to_shared(rs.s));
     const SmemWords ldw{sa & ~3u};
     const uint32_t bit0 = (sa & 3u) * 8u, bw = rs.bw, gs = 1u + bw;
     const uint32_t imask = bw >= 32u ? 0xffffffffu : ((1u << bw) - 1u);
     const uint32_t stw = static_cast<uint32_t>(__cvta_generic_to_shared(ws.stage)); // 16-byte aligned
-    for (uint32_t i = l; i < static_cast<uint32_t>(kStageBytes32) / 16u; i += 32) reinterpret_cast<uint4*>(ws.stage)[i] = make_uint4(0, 0, 0, 0);
+    if (stage_dirty) {
+        for (uint32_t i = l; i < static_cast<uint32_t>(kStageBytes32) / 16u; i += 32) reinterpret_cast<uint4*>(ws.stage)[i] = make_uint4(0, 0, 0, 0);
+        stage_dirty = false;
+    }
     __syncwarp();
     const uint32_t mis0 = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(dst) & 15u);
     uint8_t* const abase = dst - mis0;      // aligned-space origin: byte p of the tile's chars sits at abase[mis0 + p]
@@ -736,15 +737,17 @@ __device__ __forceinline__ uint32_t copy_short_dict_tile(const DecodeParams& P, 
 template <bool UNIFORM>
 __device__ __forceinline__ uint32_t copy_ranked_dict_tile(const DecodeParams& P, WarpScratch& ws, const RegStream& rs, uint32_t nn_before,
                                                           uint32_t t, uint32_t nn, const uint4* dpad, uint32_t ulen, uint32_t* offs_tile,
-                                                          uint8_t* dst, uint32_t off0, uint64_t abs_slot0) {
+                                                          uint8_t* dst, uint32_t off0, uint64_t abs_slot0, bool& stage_dirty) {
     const uint32_t l = lane_id();
     const uint32_t sa = static_cast<uint32_t>(__cvta_generic_to_shared(rs.s));
     const SmemWords ldw{sa & ~3u};
     const uint32_t bit0 = (sa & 3u) * 8u, bw = rs.bw, gs = 1u + bw;
     const uint32_t imask = bw >= 32u ? 0xffffffffu : ((1u << bw) - 1u);
     const uint32_t stw = static_cast<uint32_t>(__cvta_generic_to_shared(ws.stage)); // 16-byte aligned
-    constexpr uint32_t kZeroVecs = (64u * 15u + 48u + 15u) / 16u; // 64 strings of <= 15 bytes + phase + the carried vector
-    for (uint32_t i = l; i < kZeroVecs; i += 32) reinterpret_cast<uint4*>(ws.stage)[i] = make_uint4(0, 0, 0, 0);
+    if (stage_dirty) { // (the OR-based copies leave the buffer zeroed: only a byte-staging pass dirties it)
+        for (uint32_t i = l; i < static_cast<uint32_t>(kStageBytes32) / 16u; i += 32) reinterpret_cast<uint4*>(ws.stage)[i] = make_uint4(0, 0, 0, 0);
+        stage_dirty = false;
+    }
     uint16_t* pos16 = reinterpret_cast<uint16_t*>(ws.idx); // start of string k inside the tile's chars (variable lengths only)
     __syncwarp();
     const uint32_t mis0 = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(dst) & 15u);
@@ -896,12 +899,16 @@ __device__ __forceinline__ void stage_or_words(uint32_t stage_s, uint32_t o, uin
 }
 
 __device__ __forceinline__ uint32_t copy_ranked_plain_tile(const DecodeParams& P, WarpScratch& ws, const uint8_t* vals, uint32_t t, uint32_t nn,
-                                                           uint32_t maxlen, uint32_t* offs_tile, uint8_t* dst, uint32_t off0, uint64_t abs_slot0) {
+                                                           uint32_t maxlen, uint32_t* offs_tile, uint8_t* dst, uint32_t off0, uint64_t abs_slot0,
+                                                           bool& stage_dirty) {
     const uint32_t l = lane_id();
     const uint16_t* pos16 = reinterpret_cast<const uint16_t*>(ws.idx);
     const uint32_t stw = static_cast<uint32_t>(__cvta_generic_to_shared(ws.stage));
     const uint32_t vs = static_cast<uint32_t>(__cvta_generic_to_shared(vals));
-    for (uint32_t i = l; i < static_cast<uint32_t>(kStageBytes32) / 16u; i += 32) reinterpret_cast<uint4*>(ws.stage)[i] = make_uint4(0, 0, 0, 0);
+    if (stage_dirty) {
+        for (uint32_t i = l; i < static_cast<uint32_t>(kStageBytes32) / 16u; i += 32) reinterpret_cast<uint4*>(ws.stage)[i] = make_uint4(0, 0, 0, 0);
+        stage_dirty = false;
+    }
     __syncwarp();
     const uint32_t mis0 = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(dst) & 15u);
     uint8_t* const abase = dst - mis0;
@@ -995,9 +1002,9 @@ __device__ __forceinline__ uint32_t copy_ranked_plain_tile(const DecodeParams& P
 // LEAN: the plan has dictionary chunks -- compile the short-string-dictionary copy path in (kept out of the
 // instantiation that PLAIN-only plans run: its registers cost the PLAIN path 7 %)
 template <bool COPY, bool LEAN>
-__device__ __forceinline__ void decode_str_page(const DecodeParams& P, uint32_t q, const DevChunk& ck, WarpScratch& ws) {
+__device__ __forceinline__ void decode_str_page(const DecodeParams& P, uint32_t q, const pqg_page_desc& pd, const DevChunk& ck, WarpScratch& ws,
+                                                const uint8_t* prestaged, bool& stage_dirty) {
     const uint32_t l = lane_id();
-    const pqg_page_desc pd = P.pages[q];
     if (pd.num_values == 0) { if (!COPY && l == 0) P.page_chars[q] = 0; return; }
     if constexpr (!COPY) {
         // Size pass, dictionaries whose entries all have one length (ck.dict_len) and whose size covers every bw-bit
@@ -1047,7 +1054,7 @@ __device__ __forceinline__ void decode_str_page(const DecodeParams& P, uint32_t 
         }
     }
     PageCtx c;
-    if (!page_begin(P, q, pd, ck, ws, c)) { if (!COPY && l == 0) P.page_chars[q] = 0; return; }
+    if (!page_begin(P, q, pd, ck, ws, c, prestaged)) { if (!COPY && l == 0) P.page_chars[q] = 0; return; }
     const uint8_t* vals = c.pg + c.vals_pos;
     const uint32_t vavail = c.size - c.vals_pos;
     // plain pages keep prefix positions in ws.idx: u16 unless the page is large
@@ -1153,14 +1160,14 @@ __device__ __forceinline__ void decode_str_page(const DecodeParams& P, uint32_t 
                 uint8_t* dstp = chars + page_base + page_bytes;
                 const uint32_t o0 = static_cast<uint32_t>(page_base + page_bytes);
                 page_bytes += ulen != 0xffffffffu
-                    ? copy_ranked_dict_tile<true>(P, ws, rs, nn_before, t, nn, dpad, ulen, offs + slot0, dstp, o0, pd.out_row_base + ts)
-                    : copy_ranked_dict_tile<false>(P, ws, rs, nn_before, t, nn, dpad, 0u, offs + slot0, dstp, o0, pd.out_row_base + ts);
+                    ? copy_ranked_dict_tile<true>(P, ws, rs, nn_before, t, nn, dpad, ulen, offs + slot0, dstp, o0, pd.out_row_base + ts, stage_dirty)
+                    : copy_ranked_dict_tile<false>(P, ws, rs, nn_before, t, nn, dpad, 0u, offs + slot0, dstp, o0, pd.out_row_base + ts, stage_dirty);
                 nn_before += nn;
                 __syncwarp();
                 continue;
             }
             page_bytes += copy_short_dict_tile(P, ws, rs, nn_before, t, dpad, dict_n, offs + slot0, chars + page_base + page_bytes,
-                                               static_cast<uint32_t>(page_base + page_bytes), pd.out_row_base + ts);
+                                               static_cast<uint32_t>(page_base + page_bytes), pd.out_row_base + ts, stage_dirty);
             nn_before += nn;
             __syncwarp();
             continue;
@@ -1168,11 +1175,12 @@ __device__ __forceinline__ void decode_str_page(const DecodeParams& P, uint32_t 
         if (!c.dict && plain_found && plain_maxlen <= static_cast<uint32_t>(kStageMaxLen) && c.size <= static_cast<uint32_t>(kSlotBytes)) {
             // PLAIN page in the shared slot, prefixes known, short strings: lanes by rank, word-wise staging
             page_bytes += copy_ranked_plain_tile(P, ws, vals, t, nn, plain_maxlen, offs + slot0, chars + page_base + page_bytes,
-                                                 static_cast<uint32_t>(page_base + page_bytes), pd.out_row_base + ts);
+                                                 static_cast<uint32_t>(page_base + page_bytes), pd.out_row_base + ts, stage_dirty);
             nn_before += nn;
             __syncwarp();
             continue;
         }
+        stage_dirty = true; // the byte-staging path below writes the buffer without clearing it
         for (uint32_t g = 0; g < t; g += 32) {
             const uint32_t s = g + l;
             const bool in = s < t;
@@ -1277,8 +1285,16 @@ __device__ __forceinline__ void decode_str_page(const DecodeParams& P, uint32_t 
 // counter (the size pass counts in DevErr::slow_count, the copy pass in DevErr::slow_cursor; both
 // are zeroed at the start of a run): all resident warps stay busy until the pages run out, whatever
 // the spread of the per-page work (a fixed page per warp left 40 % of the warp slots idle).
+// Measured on 40 M-row columns (scripts/gpu_variants.sh, profiles/README.md): the copy pass runs best with 2 CTAs per SM
+// (128 registers: no spills; 136 KB of shared memory leaves the L1 its share for the dictionary gathers) and the next
+// page staged ahead with cp.async -- cfg4 PLAIN 2.43 -> 2.17 ms, cfg3 dictionary 0.47 -> 0.46 ms against 3 CTAs without
+// prefetch; 3 CTAs WITH the second buffer lose (2.81 / 0.63 ms: 204 KB of shared memory starve the L1).  The size pass
+// stages nothing and keeps 3 CTAs.
+#ifndef PQG_STR_PREFETCH
+#define PQG_STR_PREFETCH 1
+#endif
 template <bool COPY, bool LEAN>
-__global__ void __launch_bounds__(kThreadsPerCta, 3) k_str_pages(DecodeParams P) {
+__global__ void __launch_bounds__(kThreadsPerCta, COPY ? 2 : 3) k_str_pages(DecodeParams P) {
     extern __shared__ __align__(16) uint8_t smem[];
     WarpScratch& ws = reinterpret_cast<WarpScratch*>(smem)[warp_id()];
     uint32_t* cursor = COPY ? &P.err->slow_cursor : &P.err->slow_count;
@@ -1291,17 +1307,44 @@ __global__ void __launch_bounds__(kThreadsPerCta, 3) k_str_pages(DecodeParams P)
             return;
         }
     }
+    // Copy pass: pages are staged one ahead -- while a page is decoded out of one shared buffer, the next page of the
+    // batch streams into the other (cp.async), so its global latency (descriptor -> payload) hides behind the decode.
+    uint8_t* alt = smem + sizeof(WarpScratch) * kWarpsPerCta + warp_id() * kSlotAlloc;
+    bool stage_dirty = true;
     for (;;) {
         uint32_t i = 0;
         if (lane_id() == 0) i = atomicAdd(cursor, batch);
         i = __shfl_sync(0xffffffffu, i, 0);
         if (i >= n) break;
         const uint32_t i1 = min(n, i + batch);
-        for (; i < i1; i++) {
-            const uint32_t q = P.page_begin + i;
-            const DevChunk& ck = P.chunks[P.pages[q].chunk_idx];
-            decode_str_page<COPY, LEAN>(P, q, ck, ws);
-            __syncwarp();
+        if constexpr (COPY && PQG_STR_PREFETCH) {
+            uint32_t cur = 0;
+            pqg_page_desc pd = P.pages[P.page_begin + i];
+            page_stage_async(P, pd, ws.slot);
+            page_stage_commit();
+            for (; i < i1; i++) {
+                const uint32_t q = P.page_begin + i;
+                pqg_page_desc pn = pd;
+                if (i + 1 < i1) {
+                    pn = P.pages[q + 1];
+                    page_stage_async(P, pn, cur ? ws.slot : alt);
+                    page_stage_commit();
+                    page_stage_wait<1>();
+                } else page_stage_wait<0>();
+                const DevChunk& ck = P.chunks[pd.chunk_idx];
+                decode_str_page<COPY, LEAN>(P, q, pd, ck, ws, cur ? alt : ws.slot, stage_dirty);
+                __syncwarp();
+                pd = pn;
+                cur ^= 1u;
+            }
+        } else {
+            for (; i < i1; i++) {
+                const uint32_t q = P.page_begin + i;
+                const pqg_page_desc pd = P.pages[q];
+                const DevChunk& ck = P.chunks[pd.chunk_idx];
+                decode_str_page<COPY, LEAN>(P, q, pd, ck, ws, nullptr, stage_dirty);
+                __syncwarp();
+            }
         }
     }
 }
@@ -1413,7 +1456,7 @@ cudaError_t launch_decode_fixed(const DecodeParams& p, int width, bool boolean_p
 
 template <bool COPY, bool LEAN>
 static cudaError_t launch_str_t(DecodeParams p, int sm_count, cudaStream_t s) {
-    const size_t smem = decode_smem_bytes(false);
+    const size_t smem = decode_smem_bytes(false) + (COPY && PQG_STR_PREFETCH ? static_cast<size_t>(kWarpsPerCta) * kSlotAlloc : 0); // + the second staging buffer per warp
     uint32_t n = p.page_end - p.page_begin;
     if (n == 0) return cudaSuccess;
     cudaError_t e = cudaFuncSetAttribute(k_str_pages<COPY, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));

@@ -204,15 +204,19 @@ __device__ __forceinline__ uint32_t levels_tile(Walker& w, WarpScratch& ws, uint
         const uint8_t* s = w.s;
         uint32_t nr = w.len >> 1;
         bool ok = true;
-        for (uint32_t r = l; r < nr; r += 32) { uint32_t b = s[2 * r]; ok = ok && ((b & 0x81u) == 0u) && b != 0u; }
-        if (__all_sync(0xffffffffu, ok)) {
+        {
             // no bit ranges, no loops over words: every run whose level class (present / null) differs from its
-            // predecessor's sets ONE toggle bit at its first slot; the validity image is the prefix XOR of the toggles
+            // predecessor's sets ONE toggle bit at its first slot; the validity image is the prefix XOR of the toggles.
+            // The layout is verified on the way (a header byte that is not <even, 2..126> voids the image: general walk).
             uint32_t carry = 0, last_present = 0;
             for (uint32_t base = 0; base < nr && carry < t; base += 32) {
                 const uint32_t r = base + l;
                 uint32_t cnt = 0, pres = 0;
-                if (r < nr) { cnt = s[2 * r] >> 1; pres = level_present(s[2 * r + 1], max_def) ? 1u : 0u; }
+                if (r < nr) {
+                    const uint32_t b = s[2 * r];
+                    ok = ok && ((b & 0x81u) == 0u) && b != 0u;
+                    cnt = b >> 1; pres = level_present(s[2 * r + 1], max_def) ? 1u : 0u;
+                }
                 const uint32_t incl = warp_incl_scan(cnt);
                 const uint32_t start = carry + incl - cnt;
                 uint32_t prev = __shfl_up_sync(0xffffffffu, pres, 1);
@@ -235,9 +239,14 @@ __device__ __forceinline__ uint32_t levels_tile(Walker& w, WarpScratch& ws, uint
             const uint32_t lo = l * 32u;
             x &= lo >= t ? 0u : (t - lo >= 32u ? 0xffffffffu : ((1u << (t - lo)) - 1u));
             __syncwarp();
-            ws.valid[l] = x;
-            w.pos = w.len; // consumed
-            done = true;
+            if (__all_sync(0xffffffffu, ok)) {
+                ws.valid[l] = x;
+                w.pos = w.len; // consumed
+                done = true;
+            } else {
+                ws.valid[l] = 0; // not the writer's layout after all
+                __syncwarp();
+            }
         }
     }
     uint32_t produced = 0;
@@ -567,15 +576,35 @@ struct PageCtx {
 
 // Stage the payload and parse [def levels][rep levels][bit width] like read_data_page
 // (column_reader.cpp:143-182).  Returns false (after reporting) when the page is unusable.
+// asynchronous staging of a page into a slot-sized shared buffer (cp.async, 16 bytes per copy; the page then starts
+// `payload_off & 15` bytes into the buffer, exactly as page_begin lays it out).  Pages beyond kSlotBytes are not staged.
+__device__ __forceinline__ void page_stage_async(const DecodeParams& P, const pqg_page_desc& pd, uint8_t* buf) {
+    if (pd.payload_size > static_cast<uint32_t>(kSlotBytes) || pd.num_values == 0) return;
+    const uint32_t shift = static_cast<uint32_t>(pd.payload_off & 15u);
+    const uint8_t* a = P.image + pd.payload_off - shift;
+    const uint32_t nvec = (shift + pd.payload_size + 15u) >> 4;
+    const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(buf));
+    for (uint32_t j = lane_id(); j < nvec; j += 32)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 16u * j), "l"(a + 16u * j) : "memory");
+}
+__device__ __forceinline__ void page_stage_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int PENDING> __device__ __forceinline__ void page_stage_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory");
+    __syncwarp();
+}
+
+// `prestaged`: the page already sits in that buffer (page_stage_async + wait); null: staged here into ws.slot
 __device__ __forceinline__ bool page_begin(const DecodeParams& P, uint32_t q, const pqg_page_desc& pd,
-                                           const DevChunk& ck, WarpScratch& ws, PageCtx& c) {
+                                           const DevChunk& ck, WarpScratch& ws, PageCtx& c, const uint8_t* prestaged = nullptr) {
     const uint32_t l = lane_id();
     c.size = pd.payload_size;
     c.n = pd.num_values;
     c.dict = (pd.flags & PQG_PAGE_FLAG_DICT) && ck.has_dict;
     c.has_def = ck.max_def > 0;
     const uint8_t* src = P.image + pd.payload_off;
-    if (c.size <= static_cast<uint32_t>(kSlotBytes)) {
+    if (prestaged && c.size <= static_cast<uint32_t>(kSlotBytes)) {
+        c.pg = prestaged + static_cast<uint32_t>(pd.payload_off & 15u);
+    } else if (c.size <= static_cast<uint32_t>(kSlotBytes)) {
         uint32_t shift = static_cast<uint32_t>(pd.payload_off & 15u);
         const uint8_t* a = src - shift;
         uint32_t nvec = (shift + c.size + 15u) >> 4;
