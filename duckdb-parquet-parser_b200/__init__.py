@@ -22,6 +22,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libpqg.so")
 # Parquet physical types / repetition (values fixed by the format)
 BOOLEAN, INT32, INT64, INT96, FLOAT, DOUBLE, BYTE_ARRAY, FIXED_LEN_BYTE_ARRAY = range(8)
 PQG_OK, PQG_ERR_CUDA, PQG_ERR_ARG, PQG_ERR_UNSUPPORTED, PQG_ERR_PAGE, PQG_ERR_REGEX, PQG_ERR_NOMEM = range(7)
+PQG_OPT_PARTITIONED_DICT = 1
 PQG_PAGE_FLAG_DICT, PQG_PAGE_FLAG_V2 = 1, 2  # pqg_page_desc.flags; bits 8..15 = DataPageHeader.encoding
 
 
@@ -121,7 +122,7 @@ PQG_SYMBOLS = [
     "pqg_ctx_create", "pqg_ctx_destroy", "pqg_last_error", "pqg_ctx_sync", "pqg_ctx_set_profiling", "pqg_device_count",
     "pqg_kernel_launches", "pqg_upload", "pqg_wrap_device", "pqg_buf_alloc", "pqg_buf_write", "pqg_buf_size",
     "pqg_buf_free", "pqg_buf_device_ptr", "pqg_host_alloc", "pqg_host_free", "pqg_plan_create", "pqg_plan_create_dict_indices", "pqg_plan_destroy",
-    "pqg_plan_set_image", "pqg_plan_run", "pqg_plan_run_pipelined", "pqg_plan_finish", "pqg_plan_timings", "pqg_plan_timings_avg", "pqg_plan_num_slots",
+    "pqg_plan_set_image", "pqg_plan_set_option", "pqg_plan_run", "pqg_plan_run_pipelined", "pqg_plan_finish", "pqg_plan_timings", "pqg_plan_timings_avg", "pqg_plan_num_slots",
     "pqg_plan_value_width", "pqg_plan_values", "pqg_plan_validity", "pqg_plan_offsets", "pqg_plan_chars",
     "pqg_plan_chars_size", "pqg_plan_char_bases", "pqg_plan_bytes_in", "pqg_plan_bytes_out", "pqg_plan_download",
     "pqg_regex_compile", "pqg_dfa_free", "pqg_dfa_num_states", "pqg_dfa_match_host", "pqg_regex_scan",
@@ -185,6 +186,7 @@ def _declare(L):
     d("pqg_plan_create_dict_indices", i32, vp, vp, C.POINTER(ChunkDesc), u32, C.POINTER(PageDesc), u32, C.POINTER(vp))
     d("pqg_plan_destroy", None, vp, vp)
     d("pqg_plan_set_image", i32, vp, vp, vp)
+    d("pqg_plan_set_option", i32, vp, i32, i32)
     d("pqg_plan_run", i32, vp, vp)
     d("pqg_plan_run_pipelined", i32, vp, vp, vp, C.POINTER(H2dRange), u32, vp, vp)
     d("pqg_plan_finish", i32, vp, vp, C.POINTER(PageError))
@@ -677,6 +679,9 @@ class Plan:
     validity_ptr = property(lambda s: lib().pqg_plan_validity(s.h))
     offsets_ptr = property(lambda s: lib().pqg_plan_offsets(s.h))
     chars_ptr = property(lambda s: lib().pqg_plan_chars(s.h))
+
+    def set_option(self, option, value):
+        self.ctx.check(lib().pqg_plan_set_option(self.h, option, value))
 
     def set_image(self, image):
         self.ctx.check(lib().pqg_plan_set_image(self.ctx.h, self.h, image))

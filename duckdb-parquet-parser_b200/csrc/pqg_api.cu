@@ -63,6 +63,7 @@ struct pqg_plan {
     bool any_dict = false, any_def = false, is_str = false, is_bool = false;
     bool forced_validity = false; // a REQUIRED chunk held an out-of-range dictionary index (null in the reference): validity added, plan re-run
     bool run_pending = false;     // pqg_plan_run / run_pipelined enqueued, pqg_plan_finish not called yet
+    bool no_part = false;         // A/B: partitioned-dictionary mode off (pqg_plan_set_option)
     int phys = 0, width = 0;
     uint64_t n_slots = 0;
     uint32_t tile_launches = 0;              // tile-kernel launches of the current run
@@ -572,6 +573,12 @@ static int plan_create_impl(pqg_ctx* ctx, const pqg_buf* image, const pqg_chunk_
     return PQG_OK;
 }
 
+int pqg_plan_set_option(pqg_plan* plan, int option, int value) {
+    if (!plan) return PQG_ERR_ARG;
+    if (option == PQG_OPT_PARTITIONED_DICT) { plan->no_part = value == 0; return PQG_OK; }
+    return PQG_ERR_ARG;
+}
+
 int pqg_plan_set_image(pqg_ctx* ctx, pqg_plan* plan, const pqg_buf* image) {
     if (!ctx || !plan || !image) return fail(ctx, PQG_ERR_ARG, "pqg_plan_set_image: bad argument");
     if (image->size < plan->image->size) return fail(ctx, PQG_ERR_ARG, "pqg_plan_set_image: image is smaller than the planned one");
@@ -638,9 +645,13 @@ static int fixed_subrun(pqg_ctx* ctx, pqg_plan* p, uint32_t c0, uint32_t c1, boo
             // Plans over several columns: a launch also ends where the KIND of work changes (PLAIN copy /
             // shared-memory dictionary / L2 gather) -- streaming PLAIN pages next to a gather evicts the
             // dictionaries (measured: everything in one launch ran 2.4x slower than one launch per column).
+            // kind 3: dictionaries of 32 KB .. 512 KB in REQUIRED-only plans -- partitioned over 2^k sibling CTAs' shared memories
+            const bool part_ok = !p->any_def && !p->identity && (p->width == 4 || p->width == 8) && !p->no_part;
             auto kind_of = [&](const pqg_chunk_desc& ck) {
                 const uint64_t db = ck.has_dict ? static_cast<uint64_t>(ck.dict_num_values) * p->width : 0;
-                return !ck.has_dict ? 0 : (db <= static_cast<uint64_t>(kMaxSmemDictBytes) ? 1 : 2);
+                if (!ck.has_dict) return 0;
+                if (db <= static_cast<uint64_t>(kMaxSmemDictBytes)) return 1;
+                return (part_ok && db <= static_cast<uint64_t>(kPartDictBytes) * kPartMaxParts) ? 3 : 2;
             };
             uint32_t g0 = c0;
             while (g0 < c1 && e == cudaSuccess) {
@@ -663,6 +674,15 @@ static int fixed_subrun(pqg_ctx* ctx, pqg_plan* p, uint32_t c0, uint32_t c1, boo
                     const pqg_chunk_desc& ck = p->chunks[c];
                     const uint64_t db = ck.has_dict ? (static_cast<uint64_t>(ck.dict_num_values) * p->width + 15u) & ~15ull : 0;
                     if (db && db <= p->dict_smem) Pg.dict_smem = std::max<uint32_t>(Pg.dict_smem, static_cast<uint32_t>(db));
+                }
+                if (kind == 3) {
+                    uint64_t max_db = 0;
+                    for (uint32_t c = g0; c < g1; c++) max_db = std::max<uint64_t>(max_db, static_cast<uint64_t>(p->chunks[c].dict_num_values) * p->width);
+                    uint32_t bits = 0;
+                    while ((static_cast<uint64_t>(kPartDictBytes) << bits) < max_db) bits++;
+                    Pg.part_bits = bits;
+                    Pg.part_entries = static_cast<uint32_t>(kPartDictBytes / p->width);
+                    Pg.dict_smem = static_cast<uint32_t>(std::min<uint64_t>(kPartDictBytes, (max_db + 15u) & ~15ull));
                 }
                 if (Pg.tile_hi > Pg.tile_lo) { e = launch_fixed_tiles(Pg, p->width, ctx->sm_count, s); launches++; p->tile_launches++; }
                 g0 = g1;

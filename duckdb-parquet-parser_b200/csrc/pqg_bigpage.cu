@@ -23,7 +23,10 @@ namespace pqg {
 namespace {
 
 constexpr int kBigThreads = 256;
-constexpr int kBigChunk = 48 * 1024;   // staged stream bytes per step
+constexpr int kBigChunk = 40 * 1024;   // staged stream bytes per step
+constexpr int kScanWin = 4096;         // bytes of the staged slice the parallel run-boundary scan looks at per step (16 per thread)
+constexpr int kSeqRunBudget = 48;      // runs the one-thread scan may walk before the stream counts as dense (-> parallel scan)
+constexpr uint32_t kNxtInvalid = 0xffffu, kNxtBad = 0xfffeu; // header / data reach beyond the staged slice; zero-length run
 constexpr int kBigRuns = 1024;         // run-table entries per step
 constexpr int kBigSlots = 131072;      // slots per page the null-aware path can hold (validity image + ranks in shared memory)
 
@@ -40,6 +43,11 @@ struct BigSmem {
     uint8_t run_lit[kBigRuns];
     uint32_t n_runs, next_pos, next_val, status; // status: 0 ok, 1 hand the page over
     uint32_t flag, all_valid, nn, lo_slot, hi_slot;
+    uint16_t jmp[kScanWin];           // run-boundary scan: position after the run whose header would start at byte i, doubled per round
+    uint16_t endp[kBigRuns + 2];      // ... position after run r
+    uint32_t reach[kScanWin / 32];    // ... byte i IS a run header (on the chain from byte 0)
+    uint32_t changed, n_true, inv_seen, dense;
+    unsigned long long vtotal;
     uint32_t pv[kBigSlots / 32];      // page-relative validity words (pages with nulls)
     uint32_t rb[kBigSlots / 32 + 1];  // rank of the first slot of every word (exclusive popcount prefix)
     __align__(16) uint8_t chunk[kBigChunk + 32];
@@ -63,10 +71,10 @@ __device__ __forceinline__ const uint8_t* stage_slice(BigSmem& S, const uint8_t*
 // rle_decoder.hpp:37-53): fills the run table for values [v0, ...) until the table or the slice
 // is full.  spos = stream position of cb[0], slen = stream length.
 __device__ __forceinline__ void scan_runs(BigSmem& S, const uint8_t* cb, uint32_t take, uint32_t bw, uint32_t n, uint32_t v0,
-                                          uint32_t spos, uint32_t slen) {
+                                          uint32_t spos, uint32_t slen, uint32_t max_runs = kBigRuns) {
     const uint32_t nb = (bw + 7u) >> 3;
     uint32_t p = 0, v = v0, r = 0, st = 0;
-    while (r < static_cast<uint32_t>(kBigRuns) && v < n) {
+    while (r < max_runs && v < n) {
         if (spos + p >= slen) { // stream exhausted: the remaining values read as 0 (:21-24)
             S.run_first[r] = v; S.run_data[r] = 0; S.run_lit[r] = 0; r++; v = n; break;
         }
@@ -96,6 +104,159 @@ __device__ __forceinline__ void scan_runs(BigSmem& S, const uint8_t* cb, uint32_
     if (r == 0 && st == 0) st = 1; // no progress: the general kernel decides
     S.run_first[r] = v;
     S.n_runs = r; S.next_pos = spos + p; S.next_val = v; S.status = st;
+}
+
+// ---- the run-boundary scan, in parallel (all kBigThreads threads) -----------------------------------------------
+// RleDecoder::next_counts (rle_decoder.hpp:37-53) walks the run headers one after the other: header -> size of its
+// payload -> next header.  Streams of many short runs (definition levels of columns with scattered nulls as foreign
+// writers emit them: literal groups and RLE runs of 8+ in turns; run-heavy dictionary indices) make that walk the whole
+// cost of a page.  Here EVERY byte of a window is taken for a header: jmp[i] = the position the run starting at i would end
+// at.  The true headers are the chain 0 -> jmp[0] -> ...; it is marked by pointer doubling -- round r marks the successors
+// of everything marked so far (reaching chain distance 2^(r+1)) and squares the jump table -- in log2(runs) rounds, then
+// the marked headers are compacted in order (block scans of their number and of their value counts) into the same run
+// table scan_runs fills.  Same contract as scan_runs: runs for values [v0, ...) until the table, the window or the values
+// end; S.status = 1 hands the page over.
+struct RunHdr { uint32_t next, cnt, lit, data; };
+__device__ __forceinline__ RunHdr parse_run_header(const uint8_t* cb, uint32_t take, uint32_t i, uint32_t bw, uint32_t nb) {
+    RunHdr h{kNxtInvalid, 0, 0, 0};
+    uint32_t ind = 0, shift = 0, hp = i;
+    bool complete = false;
+    while (hp < take && hp < i + 10u) { const uint32_t b = cb[hp++]; if (shift < 32) ind |= (b & 0x7Fu) << shift; if (!(b & 0x80u)) { complete = true; break; } shift += 7; }
+    if (!complete) return h; // the header continues in the next slice (or is no varint at all)
+    if (ind & 1u) {
+        const uint64_t cnt = static_cast<uint64_t>(ind >> 1) * 8u, dbytes = (cnt * bw + 7u) >> 3;
+        if (cnt == 0) { h.next = kNxtBad; return h; }
+        if (hp + dbytes > take) return h;
+        h.next = hp + static_cast<uint32_t>(dbytes); h.cnt = static_cast<uint32_t>(cnt); h.lit = 1; h.data = hp * 8u;
+    } else {
+        const uint32_t cnt = ind >> 1;
+        if (cnt == 0) { h.next = kNxtBad; return h; }
+        if (hp + nb > take) return h;
+        uint32_t val = 0;
+        for (uint32_t k = 0; k < nb && k < 4u; k++) val |= static_cast<uint32_t>(cb[hp + k]) << (8u * k);
+        h.next = hp + nb; h.cnt = cnt; h.lit = 0; h.data = val;
+    }
+    return h;
+}
+
+__device__ __forceinline__ unsigned long long block_excl_scan_u64(unsigned long long v, unsigned long long* total) {
+    __shared__ unsigned long long wsum[kBigThreads / 32];
+    const uint32_t l = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    unsigned long long incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { unsigned long long t = __shfl_up_sync(0xffffffffu, incl, d); if (l >= static_cast<uint32_t>(d)) incl += t; }
+    if (l == 31) wsum[w] = incl;
+    __syncthreads();
+    unsigned long long base = 0, tot = 0;
+#pragma unroll
+    for (int i = 0; i < kBigThreads / 32; i++) { const unsigned long long x = wsum[i]; if (i < static_cast<int>(w)) base += x; tot += x; }
+    __syncthreads();
+    *total = tot;
+    return base + incl - v;
+}
+
+__device__ __noinline__ void scan_runs_parallel(BigSmem& S, const uint8_t* cb, uint32_t take, uint32_t bw, uint32_t n, uint32_t v0,
+                                               uint32_t spos, uint32_t slen) {
+    const uint32_t tid = threadIdx.x;
+    const uint32_t nb = (bw + 7u) >> 3;
+    const uint32_t W = min(take, static_cast<uint32_t>(kScanWin));
+    constexpr uint32_t kPer = kScanWin / kBigThreads; // positions per thread (contiguous)
+    // A: the jump table
+    for (uint32_t k = 0; k < kPer; k++) {
+        const uint32_t i = tid * kPer + k;
+        if (i < W) S.jmp[i] = static_cast<uint16_t>(parse_run_header(cb, take, i, bw, nb).next);
+    }
+    if (tid < kScanWin / 32) S.reach[tid] = tid == 0 ? 1u : 0u;
+    if (tid == 0) { S.status = 0; S.inv_seen = 0; }
+    __syncthreads();
+    // B: mark the chain by pointer doubling
+    for (int round = 0; round < 13; round++) {
+        if (tid == 0) S.changed = 0;
+        __syncthreads();
+        const uint32_t mine = (S.reach[(tid * kPer) >> 5] >> ((tid * kPer) & 31u)) & ((1u << kPer) - 1u);
+        uint32_t m = mine;
+        while (m) {
+            const uint32_t k = static_cast<uint32_t>(__ffs(static_cast<int>(m)) - 1);
+            m &= m - 1;
+            const uint32_t j = S.jmp[tid * kPer + k];
+            if (j < W) {
+                const uint32_t bit = 1u << (j & 31u);
+                if (!(atomicOr(&S.reach[j >> 5], bit) & bit)) S.changed = 1;
+            }
+        }
+        __syncthreads();
+        if (!S.changed) break;
+        uint16_t nj[kPer];
+#pragma unroll
+        for (uint32_t k = 0; k < kPer; k++) {
+            const uint32_t i = tid * kPer + k;
+            uint32_t j = i < W ? S.jmp[i] : kNxtInvalid;
+            if (j < W) j = S.jmp[j];
+            nj[k] = static_cast<uint16_t>(j);
+        }
+        __syncthreads();
+#pragma unroll
+        for (uint32_t k = 0; k < kPer; k++) { const uint32_t i = tid * kPer + k; if (i < W) S.jmp[i] = nj[k]; }
+        __syncthreads();
+    }
+    // C: the marked headers, in order: thread t takes the 16 positions it owns
+    const uint32_t mine = (S.reach[(tid * kPer) >> 5] >> ((tid * kPer) & 31u)) & ((1u << kPer) - 1u);
+    unsigned long long vsum = 0;
+    uint32_t usable = 0; // headers with a complete run inside the slice
+    {
+        uint32_t m = mine;
+        while (m) {
+            const uint32_t k = static_cast<uint32_t>(__ffs(static_cast<int>(m)) - 1);
+            m &= m - 1;
+            const RunHdr h = parse_run_header(cb, take, tid * kPer + k, bw, nb);
+            if (h.next == kNxtBad) S.status = 1;           // zero-length run: the general kernel reports it
+            else if (h.next == kNxtInvalid) S.inv_seen = 1; // the chain ends here: restage from this header
+            else { usable++; vsum += h.cnt; }
+        }
+    }
+    unsigned long long vtot = 0, rtot = 0;
+    const unsigned long long vbase = block_excl_scan_u64(vsum, &vtot);
+    const uint32_t rbase = static_cast<uint32_t>(block_excl_scan_u64(usable, &rtot));
+    {
+        uint32_t m = mine, r = rbase;
+        unsigned long long v = vbase;
+        while (m) {
+            const uint32_t k = static_cast<uint32_t>(__ffs(static_cast<int>(m)) - 1);
+            m &= m - 1;
+            const RunHdr h = parse_run_header(cb, take, tid * kPer + k, bw, nb);
+            if (h.next >= kNxtBad) continue;
+            if (r <= static_cast<uint32_t>(kBigRuns)) { // (entry kBigRuns: only the first value, the sentinel behind a full table)
+                const unsigned long long vs = static_cast<unsigned long long>(v0) + v;
+                S.run_first[r] = vs < n ? static_cast<uint32_t>(vs) : n;
+            }
+            if (r < static_cast<uint32_t>(kBigRuns)) {
+                S.run_data[r] = h.data;
+                S.run_lit[r] = static_cast<uint8_t>(h.lit);
+                S.endp[r] = static_cast<uint16_t>(h.next);
+            }
+            r++;
+            v += h.cnt;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const uint32_t R = static_cast<uint32_t>(min(rtot, static_cast<unsigned long long>(kBigRuns)));
+        const unsigned long long vend = static_cast<unsigned long long>(v0) + vtot;
+        if (rtot <= static_cast<unsigned long long>(kBigRuns)) S.run_first[R] = vend < n ? static_cast<uint32_t>(vend) : n;
+        uint32_t lo = 0, hi = R; // runs whose first value lies inside the page
+        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (S.run_first[mid] < n) lo = mid + 1; else hi = mid; }
+        uint32_t nr = lo;
+        uint32_t next_val = nr ? S.run_first[nr] : v0, next_pos = nr ? S.endp[nr - 1] : 0u;
+        if (nr == 0 && !S.status && spos < slen) S.status = 1; // no progress inside the slice: the general kernel decides
+        if (!S.status && spos + next_pos >= slen && next_val < n && nr < static_cast<uint32_t>(kBigRuns)) {
+            // stream exhausted: the remaining values read as 0 (rle_decoder.hpp:21-24)
+            S.run_first[nr] = next_val; S.run_data[nr] = 0; S.run_lit[nr] = 0; nr++;
+            next_val = n;
+            S.run_first[nr] = n;
+        }
+        S.n_runs = nr; S.next_pos = spos + next_pos; S.next_val = next_val;
+    }
+    __syncthreads();
 }
 
 __device__ __forceinline__ uint32_t find_run(const BigSmem& S, uint32_t nr, uint32_t v) {
@@ -153,9 +314,15 @@ __global__ void __launch_bounds__(kBigThreads) k_big_pages(const DecodeParams P)
             for (uint32_t w = tid; w < nwords; w += kBigThreads) S.pv[w] = 0;
             const uint8_t* cb = stage_slice(S, pg + 4, def_len);
             uint32_t spos = 0, vdone = 0;
+            bool dense = false; // many short runs: the one-thread header walk would be the whole cost -> parallel run-boundary scan
             while (vdone < n && ok) {
-                if (tid == 0) scan_runs(S, cb + spos, def_len - spos, 1u, n, vdone, spos, def_len);
-                __syncthreads();
+                if (!dense) {
+                    if (tid == 0) scan_runs(S, cb + spos, def_len - spos, 1u, n, vdone, spos, def_len, kSeqRunBudget);
+                    __syncthreads();
+                    dense = !S.status && S.n_runs == static_cast<uint32_t>(kSeqRunBudget) && S.next_val < n;
+                    __syncthreads();
+                }
+                if (dense) scan_runs_parallel(S, cb + spos, def_len - spos, 1u, n, vdone, spos, def_len);
                 if (S.status) { ok = false; break; }
                 const uint32_t nr = S.n_runs, vend = S.next_val;
                 const uint8_t* rb_base = cb + spos; // literal bit offsets are relative to the scanned slice
@@ -254,11 +421,19 @@ __global__ void __launch_bounds__(kBigThreads) k_big_pages(const DecodeParams P)
             const uint32_t imask = bw >= 32u ? 0xffffffffu : ((1u << bw) - 1u);
             uint32_t spos = 0, vdone = 0, slot_lo = 0; // next run header, values decoded, slots emitted
             if (nn == 0) { for (uint32_t sl = tid; sl < n; sl += kBigThreads) __stcs(out + sl, T(0)); }
+            bool dense = false;
             while (vdone < nn && ok) {
-                const uint32_t take = min(static_cast<uint32_t>(kBigChunk), slen - min(slen, spos));
+                // (dense streams are consumed a scan window at a time: stage less)
+                const uint32_t take = min(dense ? 2u * static_cast<uint32_t>(kScanWin) : static_cast<uint32_t>(kBigChunk), slen - min(slen, spos));
                 const uint8_t* cb = stage_slice(S, stream + spos, take);
-                if (tid == 0) {
-                    scan_runs(S, cb, take, bw, nn, vdone, spos, slen);
+                if (!dense) {
+                    if (tid == 0) scan_runs(S, cb, take, bw, nn, vdone, spos, slen, kSeqRunBudget);
+                    __syncthreads();
+                    dense = !S.status && S.n_runs == static_cast<uint32_t>(kSeqRunBudget) && S.next_val < nn && S.next_pos < spos + take;
+                    __syncthreads();
+                }
+                if (dense) scan_runs_parallel(S, cb, take, bw, nn, vdone, spos, slen);
+                if (tid == 0 && !S.status) {
                     // slots of this batch: up to (excluding) the slot of value next_val; the last batch takes the rest
                     uint32_t hi_slot = n;
                     if (!all_valid && S.next_val < nn) {

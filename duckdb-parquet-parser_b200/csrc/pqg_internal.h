@@ -16,6 +16,11 @@ constexpr int kIdxWords = 512;            // per-warp index scratch: 1024 x u16 
 constexpr int kTileNarrow = 1024;         // slots per tile when indices fit 16 bits
 constexpr int kTileWide = 512;
 constexpr int kMaxSmemDictBytes = 32 * 1024; // dictionaries up to this size are staged per CTA
+// Dictionaries beyond that and up to kPartMaxParts x kPartDictBytes: PARTITIONED mode of the tile kernel -- 2^k CTAs read
+// the same tiles, each keeps 1 / 2^k of the dictionary in its shared memory and emits only the values whose index falls
+// into its part (local ld.shared instead of one L1TEX wavefront + one 32-byte L2 sector per gathered value)
+constexpr int kPartDictBytes = 128 * 1024;
+constexpr int kPartMaxParts = 4;
 constexpr int kStageMaxLen = 48;          // strings up to this length go through the per-warp staging buffer
 constexpr int kStageBytes32 = 32 * kStageMaxLen + 32; // 32 strings + alignment phase (multiple of 16)
 constexpr int kImagePad = 64;             // readable bytes required past the image end
@@ -114,6 +119,8 @@ struct DecodeParams {
     uint32_t* slow_append;   // pages handed over on the device: slow_append[0 .. err->slow_count); capacity: every page of the plan
     uint32_t chunk_lo;       // first chunk of this launch (dictionary preparation)
     uint32_t tile_sync;      // 1: CTA-wide barrier per tile instead of the last-warp refill (the regex scan: issue bound)
+    uint32_t part_bits;      // partitioned-dictionary launch: log2 of the CTAs that share a tile span (0: off)
+    uint32_t part_entries;   // ... dictionary entries per part (a power of two)
     uint32_t handover_hint;  // pages the tile kernel handed to the general kernel in the previous run of the plan (~0u: unknown)
     uint32_t skip_dict_pad;  // 1: the run does not materialise strings (regex scan): no padded short-string table
     uint32_t tile_bytes;     // tile size the plan's tiles were cut for (kTileBytes / kTileBytesLarge)

@@ -62,7 +62,7 @@ __device__ __forceinline__ void tile_pipeline(const DecodeParams& P, uint8_t* sm
     TileMeta* meta = reinterpret_cast<TileMeta*>(smem + 64);     // [kTileStages]
     TileDesc* ahead = reinterpret_cast<TileDesc*>(smem + 64 + kTileStages * 32); // [kTileStages] descriptor of the tile that refills the stage
     uint8_t* ring = smem + kBarBytes;
-    const uint32_t t0 = P.tile_lo + blockIdx.x * P.tiles_per_cta;
+    const uint32_t t0 = P.tile_lo + (blockIdx.x >> P.part_bits) * P.tiles_per_cta; // (partitioned dictionaries: 2^part_bits CTAs per span)
     const uint32_t t1 = min(P.tile_hi, t0 + P.tiles_per_cta);
     const uint32_t tid = threadIdx.x;
     if (tid == 0) {

@@ -28,6 +28,8 @@
 //     dictionary of a 2^20-key chunk; outputs are written with streaming stores so they do
 //     not evict it).
 //   * outputs: 8 or 4 bytes per lane, consecutive lanes -> consecutive slots (coalesced).
+#include <algorithm>
+
 #include "pqg_tilepipe.cuh"
 
 namespace pqg {
@@ -154,9 +156,11 @@ __device__ __noinline__ bool hybrid_runs_page(const DecodeParams& P, const uint8
 }
 
 // One warp decodes one page out of the staged tile.  `pg` = first payload byte (shared).
-template <int W>
+// PART: partitioned-dictionary launch -- this CTA holds entries [part_lo, part_lo + P.part_entries) of the dictionary in shared
+// memory (dictp) and stores only the values whose index lies there; its sibling CTAs emit the rest of the same page.
+template <int W, bool PART = false>
 __device__ __forceinline__ bool fast_page(const DecodeParams& P, uint32_t q, const pqg_page_desc& pd, const uint8_t* pg,
-                                          bool chunk_has_dict, const uint8_t* dictp, uint32_t dict_n, bool dict_in_smem) {
+                                          bool chunk_has_dict, const uint8_t* dictp, uint32_t dict_n, bool dict_in_smem, uint32_t part_lo = 0) {
     using T = typename FElem<W>::T;
     const uint32_t l = lane_id();
     const uint32_t n = pd.num_values, size = pd.payload_size;
@@ -164,6 +168,7 @@ __device__ __forceinline__ bool fast_page(const DecodeParams& P, uint32_t q, con
     T* out = reinterpret_cast<T*>(P.values) + pd.out_row_base;
     if (!((pd.flags & PQG_PAGE_FLAG_DICT) && chunk_has_dict)) {
         // PLAIN: read_plain_value per slot == a shifted copy
+        if constexpr (PART) { if (part_lo != 0) return true; } // (a PLAIN fallback page inside a dictionary chunk: one sibling copies it)
         if (static_cast<uint64_t>(n) * W > size) { if (l == 0) to_slow(P, q); return false; }
         uint32_t e = l;
         for (; e + 96 < n; e += 128) {
@@ -185,6 +190,39 @@ __device__ __forceinline__ bool fast_page(const DecodeParams& P, uint32_t q, con
     if (bw > 32) { if (l == 0) to_slow(P, q); return false; }
     const DictRef dref{dictp, dict_in_smem ? smem_u32(dictp) : 0u};
     const int mode = P.identity_dict ? kDictIdent : (dict_in_smem ? kDictSmem : kDictGlobal);
+    if constexpr (PART) {
+        // the writer's stream shape only; anything else goes to the general kernel (handed over by ONE sibling)
+        if (bw > 32 || !check_regular2(s, size - 1, bw, n, &rs)) { if (l == 0 && part_lo == 0) to_slow(P, q); return false; }
+        const uint32_t sa = smem_u32(s);
+        const SmemWords ldw{sa & ~3u};
+        const uint32_t gs = 1u + bw, imask = bw >= 32u ? 0xffffffffu : ((1u << bw) - 1u);
+        const uint32_t bit_l = (sa & 3u) * 8u + (((l >> 3) * gs + 1u) << 3) + (l & 7u) * bw;
+        const uint32_t step32 = 32u * gs, dsa = smem_u32(dictp), pn = P.part_entries;
+        bool bad = false;
+        auto index_at = [&](uint32_t bitpos, uint32_t k) -> uint32_t {
+            const uint32_t ix = __funnelshift_r(ldw(bitpos >> 5), ldw((bitpos >> 5) + 1u), bitpos & 31u) & imask;
+            return k >= rs.tail_start ? rs.tail_val : ix;
+        };
+        uint32_t bit = bit_l, v = l;
+        for (; v + 96 < n; v += 128, bit += 4u * step32) {
+            const uint32_t i0 = index_at(bit, v), i1 = index_at(bit + step32, v + 32);
+            const uint32_t i2 = index_at(bit + 2u * step32, v + 64), i3 = index_at(bit + 3u * step32, v + 96);
+            bad = bad || i0 >= dict_n || i1 >= dict_n || i2 >= dict_n || i3 >= dict_n;
+            const uint32_t r0 = i0 - part_lo, r1 = i1 - part_lo, r2 = i2 - part_lo, r3 = i3 - part_lo; // wraps below the part
+            if (r0 < pn && i0 < dict_n) st_stream<T>(out + v, lds_elem<T>(dsa + r0 * W));
+            if (r1 < pn && i1 < dict_n) st_stream<T>(out + v + 32, lds_elem<T>(dsa + r1 * W));
+            if (r2 < pn && i2 < dict_n) st_stream<T>(out + v + 64, lds_elem<T>(dsa + r2 * W));
+            if (r3 < pn && i3 < dict_n) st_stream<T>(out + v + 96, lds_elem<T>(dsa + r3 * W));
+        }
+        for (; v < n; v += 32, bit += step32) {
+            const uint32_t i0 = index_at(bit, v), r0 = i0 - part_lo;
+            bad = bad || i0 >= dict_n;
+            if (r0 < pn && i0 < dict_n) st_stream<T>(out + v, lds_elem<T>(dsa + r0 * W));
+        }
+        const bool any_bad = __any_sync(0xffffffffu, bad);
+        if (any_bad && l == 0 && part_lo == 0) { to_slow(P, q); atomicAdd(&P.err->bad_index, 1u); }
+        return !any_bad;
+    }
     if (!check_regular2(s, size - 1, bw, n, &rs)) {
         // any other well-formed hybrid stream (RLE runs between the groups, literal runs of several
         // groups as foreign writers emit them): runs in sequence, the warp expands each one together
@@ -402,8 +440,8 @@ __device__ __forceinline__ void fast_page_opt(const DecodeParams& P, uint32_t q,
 // OPT = the plan has OPTIONAL chunks.  The REQUIRED-only instantiation stays at <= 64 registers
 // (4 CTAs/SM); carrying the level code costs 8 more and a whole CTA per SM (measured: PLAIN
 // 0.262 -> 0.284 ms, dictionary bw 8 0.177 -> 0.203 ms per 100 M values).
-template <int W, int TB, bool OPT>
-__global__ void __launch_bounds__(kThreadsPerCta, OPT ? 3 : 4) k_fixed_tiles(const DecodeParams P) {
+template <int W, int TB, bool OPT, bool PART = false>
+__global__ void __launch_bounds__(kThreadsPerCta, PART ? 1 : (OPT ? 3 : 4)) k_fixed_tiles(const DecodeParams P) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint32_t* vwords = reinterpret_cast<uint32_t*>(smem + tile_pipe_bytes(TB)) + warp_id() * 64; // per warp: 32 validity words + 32 rank bases
     uint8_t* sdict = smem + tile_pipe_bytes(TB) + kLevelScratchBytes;
@@ -411,6 +449,7 @@ __global__ void __launch_bounds__(kThreadsPerCta, OPT ? 3 : 4) k_fixed_tiles(con
     const uint8_t* dictp = nullptr;
     bool has_dict = false, dict_in_smem = false;
     int max_def = 0;
+    uint32_t part_lo = 0;
     tile_pipeline<TB>(P, smem,
         [&](uint32_t chunk, uint64_t* bar, uint32_t& phase) {
             const DevChunk& ck = P.chunks[chunk];
@@ -419,6 +458,21 @@ __global__ void __launch_bounds__(kThreadsPerCta, OPT ? 3 : 4) k_fixed_tiles(con
             dict_n = ck.dict_ok_n;
             dictp = P.dict_arena + ck.dict_arena_off;
             dict_in_smem = false;
+            if constexpr (PART) {
+                // this CTA's part of the dictionary: entries [part_lo, part_lo + part_entries)
+                part_lo = (blockIdx.x & ((1u << P.part_bits) - 1u)) * P.part_entries;
+                const uint32_t cnt = (has_dict && part_lo < dict_n) ? min(P.part_entries, dict_n - part_lo) : 0u;
+                const uint32_t pbytes = (cnt * W + 15u) & ~15u;
+                __syncthreads(); // nobody reads the previous dictionary any more
+                if (pbytes) {
+                    if (threadIdx.x == 0) { mbar_expect_tx(bar, pbytes); bulk_g2s(sdict, dictp + static_cast<size_t>(part_lo) * W, pbytes, bar); }
+                    mbar_wait(bar, phase);
+                    phase ^= 1;
+                }
+                dictp = sdict;
+                dict_in_smem = true;
+                return;
+            }
             const uint32_t dbytes = (dict_n * W + 15u) & ~15u;
             if (has_dict && dbytes && dbytes <= P.dict_smem) {
                 __syncthreads(); // nobody reads the previous dictionary any more
@@ -433,7 +487,8 @@ __global__ void __launch_bounds__(kThreadsPerCta, OPT ? 3 : 4) k_fixed_tiles(con
             if constexpr (OPT) {
                 if (max_def > 0) { fast_page_opt<W>(P, q, pd, pg, has_dict, dictp, dict_n, dict_in_smem, vwords, vwords + 32); return; }
             }
-            fast_page<W>(P, q, pd, pg, has_dict, dictp, dict_n, dict_in_smem);
+            if constexpr (PART) fast_page<W, true>(P, q, pd, pg, has_dict, dictp, dict_n, true, part_lo);
+            else fast_page<W>(P, q, pd, pg, has_dict, dictp, dict_n, dict_in_smem);
         });
 }
 
@@ -444,17 +499,28 @@ bool chunk_is_tileable(int phys_type, int max_def, int max_rep) {
     return w48 && max_def <= 1 && max_rep <= 0;
 }
 
-template <int W, int TB, bool OPT>
+template <int W, int TB, bool OPT, bool PART = false>
 static cudaError_t launch_tiles_t(DecodeParams p, int sm_count, cudaStream_t s) {
     const size_t smem = static_cast<size_t>(tile_pipe_bytes(TB)) + kLevelScratchBytes + p.dict_smem;
     // (attributes are per device: set on every launch, it is cheap)
-    cudaError_t e = cudaFuncSetAttribute(k_fixed_tiles<W, TB, OPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    cudaError_t e = cudaFuncSetAttribute(k_fixed_tiles<W, TB, OPT, PART>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
     // contiguous tile spans per CTA (a CTA stages a chunk's dictionary once)
     int resident = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k_fixed_tiles<W, TB, OPT>, kThreadsPerCta, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k_fixed_tiles<W, TB, OPT, PART>, kThreadsPerCta, smem);
+    if (PART) {
+        // 2^part_bits sibling CTAs per tile span: spans sized so that the siblings of all spans are resident together
+        const uint32_t parts = 1u << p.part_bits, n_tiles = p.tile_hi - p.tile_lo;
+        uint32_t spans = std::max<uint32_t>(1u, static_cast<uint32_t>(sm_count) * static_cast<uint32_t>(std::max(resident, 1)) * 2u / parts);
+        uint32_t per = (n_tiles + spans - 1) / spans;
+        if (per < 4) per = 4;
+        p.tiles_per_cta = per;
+        const uint32_t grid = ((n_tiles + per - 1) / per) * parts;
+        k_fixed_tiles<W, TB, OPT, PART><<<grid, kThreadsPerCta, smem, s>>>(p);
+        return cudaGetLastError();
+    }
     const uint32_t grid = tile_grid(p.tile_hi - p.tile_lo, sm_count, resident, &p.tiles_per_cta);
-    k_fixed_tiles<W, TB, OPT><<<grid, kThreadsPerCta, smem, s>>>(p);
+    k_fixed_tiles<W, TB, OPT, PART><<<grid, kThreadsPerCta, smem, s>>>(p);
     return cudaGetLastError();
 }
 
@@ -462,6 +528,11 @@ cudaError_t launch_fixed_tiles(const DecodeParams& p, int width, int sm_count, c
     if (p.tile_hi <= p.tile_lo) return cudaSuccess;
     // plans with OPTIONAL chunks: 16 KB tiles + the level code; REQUIRED-only plans: the lean kernel
     const bool opt = p.tile_bytes == static_cast<uint32_t>(kTileBytesLarge);
+    if (p.part_entries && !opt) { // partitioned dictionary (REQUIRED-only plans)
+        if (width == 4) return launch_tiles_t<4, kTileBytes, false, true>(p, sm_count, s);
+        if (width == 8) return launch_tiles_t<8, kTileBytes, false, true>(p, sm_count, s);
+        return cudaErrorInvalidValue;
+    }
     if (width == 4) return opt ? launch_tiles_t<4, kTileBytesLarge, true>(p, sm_count, s) : launch_tiles_t<4, kTileBytes, false>(p, sm_count, s);
     if (width == 8) return opt ? launch_tiles_t<8, kTileBytesLarge, true>(p, sm_count, s) : launch_tiles_t<8, kTileBytes, false>(p, sm_count, s);
     return cudaErrorInvalidValue;

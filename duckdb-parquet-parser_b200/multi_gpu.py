@@ -27,8 +27,8 @@ def gather_page_bits(local_bits, world):
     if world == 1:
         return local, [len(local)]
     parts = [None] * world
-    _dist().all_gather_object(parts, local)
-    return np.concatenate(parts), [len(p) for p in parts]
+    _dist().all_gather_object(parts, (np.packbits(local), len(local)))  # one bit per page on the wire
+    return np.concatenate([np.unpackbits(b)[:n] for b, n in parts]), [n for _, n in parts]
 
 
 def regex_prune_sharded(ops, col, pattern, neg=False, rank=0, world=1):

@@ -176,6 +176,11 @@ PQG_API int pqg_plan_create_dict_indices(pqg_ctx* ctx, const pqg_buf* image, con
                                          uint32_t n_chunks, const pqg_page_desc* pages, uint32_t n_pages,
                                          pqg_plan** out);
 PQG_API void pqg_plan_destroy(pqg_ctx* ctx, pqg_plan* plan);
+/* tuning switches of a plan (A/B measurements; the defaults are the measured best).  PQG_OPT_PARTITIONED_DICT (default 1):
+ * dictionaries of 32 KB .. 512 KB of values in REQUIRED-only 4/8-byte plans are split over the shared memories of 2..4
+ * sibling CTAs that read the same page tiles (0: gathered from L2 like the larger ones). */
+enum { PQG_OPT_PARTITIONED_DICT = 1 };
+PQG_API int pqg_plan_set_option(pqg_plan* plan, int option, int value);
 /* re-point a plan at another resident image with the same layout (pipelined ingest) */
 PQG_API int pqg_plan_set_image(pqg_ctx* ctx, pqg_plan* plan, const pqg_buf* image);
 /* enqueue the decode on the context's stream.  Asynchronous, except that the first run of
