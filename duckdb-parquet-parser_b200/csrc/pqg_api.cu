@@ -63,7 +63,7 @@ struct pqg_plan {
     bool any_dict = false, any_def = false, is_str = false, is_bool = false;
     bool forced_validity = false; // a REQUIRED chunk held an out-of-range dictionary index (null in the reference): validity added, plan re-run
     bool run_pending = false;     // pqg_plan_run / run_pipelined enqueued, pqg_plan_finish not called yet
-    bool no_part = false;         // A/B: partitioned-dictionary mode off (pqg_plan_set_option)
+    bool no_part = true;          // partitioned-dictionary mode: measured slower than the L2 gather (0.60 vs 0.49 ms per 100 M values): opt-in (pqg_plan_set_option)
     int phys = 0, width = 0;
     uint64_t n_slots = 0;
     uint32_t tile_launches = 0;              // tile-kernel launches of the current run
@@ -675,14 +675,21 @@ static int fixed_subrun(pqg_ctx* ctx, pqg_plan* p, uint32_t c0, uint32_t c1, boo
                     const uint64_t db = ck.has_dict ? (static_cast<uint64_t>(ck.dict_num_values) * p->width + 15u) & ~15ull : 0;
                     if (db && db <= p->dict_smem) Pg.dict_smem = std::max<uint32_t>(Pg.dict_smem, static_cast<uint32_t>(db));
                 }
-                if (kind == 3) {
-                    uint64_t max_db = 0;
-                    for (uint32_t c = g0; c < g1; c++) max_db = std::max<uint64_t>(max_db, static_cast<uint64_t>(p->chunks[c].dict_num_values) * p->width);
-                    uint32_t bits = 0;
-                    while ((static_cast<uint64_t>(kPartDictBytes) << bits) < max_db) bits++;
-                    Pg.part_bits = bits;
-                    Pg.part_entries = static_cast<uint32_t>(kPartDictBytes / p->width);
-                    Pg.dict_smem = static_cast<uint32_t>(std::min<uint64_t>(kPartDictBytes, (max_db + 15u) & ~15ull));
+                if (kind == 3) { // partitioned dictionaries: one launch per chunk (a CTA keeps one dictionary part for the whole launch)
+                    for (uint32_t c = g0; c < g1 && e == cudaSuccess; c++) {
+                        const uint64_t db = static_cast<uint64_t>(p->chunks[c].dict_num_values) * p->width;
+                        DecodeParams Pc = P;
+                        Pc.chunk_lo = c;
+                        Pc.tile_lo = p->chunk_tile_begin[c]; Pc.tile_hi = p->chunk_tile_begin[c + 1];
+                        uint32_t bits = 0;
+                        while ((static_cast<uint64_t>(kPartDictBytes) << bits) < db) bits++;
+                        Pc.part_bits = bits;
+                        Pc.part_entries = static_cast<uint32_t>(kPartDictBytes / p->width);
+                        Pc.dict_smem = static_cast<uint32_t>(std::min<uint64_t>(kPartDictBytes, (db + 15u) & ~15ull));
+                        if (Pc.tile_hi > Pc.tile_lo) { e = launch_fixed_tiles_part(Pc, p->width, ctx->sm_count, s); launches++; p->tile_launches++; }
+                    }
+                    g0 = g1;
+                    continue;
                 }
                 if (Pg.tile_hi > Pg.tile_lo) { e = launch_fixed_tiles(Pg, p->width, ctx->sm_count, s); launches++; p->tile_launches++; }
                 g0 = g1;

@@ -138,6 +138,7 @@ inline uint32_t dict_prepare_launches(int width) { return width == 0 ? 3u : 1u; 
 cudaError_t launch_decode_fixed(const DecodeParams& p, int width, bool boolean_plain, int sm_count, cudaStream_t s);
 // fast path (pqg_tiles.cu): PLAIN / regular-dictionary pages of REQUIRED 4- and 8-byte chunks
 cudaError_t launch_fixed_tiles(const DecodeParams& p, int width, int sm_count, cudaStream_t s);
+cudaError_t launch_fixed_tiles_part(const DecodeParams& p, int width, int sm_count, cudaStream_t s); // partitioned dictionary: ONE chunk per launch
 bool chunk_is_tileable(int phys_type, int max_def, int max_rep);
 // oversized pages of 4/8-byte plans: one CTA per page (pqg_bigpage.cu); what it cannot take goes to the slow list
 cudaError_t launch_big_pages(const DecodeParams& p, int width, int sm_count, cudaStream_t s);

@@ -54,23 +54,31 @@ struct TileMeta { uint64_t byte_lo; uint32_t first_page; uint32_t n_pages; uint3
 // memory.  on_chunk(chunk_idx, extra_bar, phase&) is called by all threads (CTA-uniform) when
 // the chunk changes -- it may __syncthreads and stage per-chunk data with a bulk copy on
 // extra_bar.  on_page(q, pd, payload) is called by one warp per page.
+// A CTA of several 256-thread GROUPS runs one pipeline per group (its own ring, barriers and tile span): `grp` names the
+// group's barrier (0 = the whole CTA: __syncthreads), its thread / warp ids and its tile span.
+struct PipeGroup { uint32_t bar_id, tid, warp, t0, t1; };
+__device__ __forceinline__ void pipe_sync(uint32_t bar_id) {
+    if (bar_id == 0) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(kThreadsPerCta) : "memory");
+}
+
 template <int TB = kTileBytes, class OnChunk, class OnPage>
-__device__ __forceinline__ void tile_pipeline(const DecodeParams& P, uint8_t* smem, OnChunk&& on_chunk, OnPage&& on_page) {
+__device__ __forceinline__ void tile_pipeline(const DecodeParams& P, uint8_t* smem, OnChunk&& on_chunk, OnPage&& on_page, const PipeGroup* grp = nullptr) {
     constexpr int kStageBytes = tile_stage_bytes(TB);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);          // [kTileStages] tiles, then one for per-chunk staging
     uint32_t* done = reinterpret_cast<uint32_t*>(smem + 32);     // [kTileStages] warps finished with the stage
     TileMeta* meta = reinterpret_cast<TileMeta*>(smem + 64);     // [kTileStages]
     TileDesc* ahead = reinterpret_cast<TileDesc*>(smem + 64 + kTileStages * 32); // [kTileStages] descriptor of the tile that refills the stage
     uint8_t* ring = smem + kBarBytes;
-    const uint32_t t0 = P.tile_lo + (blockIdx.x >> P.part_bits) * P.tiles_per_cta; // (partitioned dictionaries: 2^part_bits CTAs per span)
-    const uint32_t t1 = min(P.tile_hi, t0 + P.tiles_per_cta);
-    const uint32_t tid = threadIdx.x;
+    const uint32_t t0 = grp ? grp->t0 : P.tile_lo + blockIdx.x * P.tiles_per_cta;
+    const uint32_t t1 = grp ? grp->t1 : min(P.tile_hi, t0 + P.tiles_per_cta);
+    const uint32_t tid = grp ? grp->tid : threadIdx.x, wid = grp ? grp->warp : warp_id(), bar_id = grp ? grp->bar_id : 0u;
     if (tid == 0) {
         for (int i = 0; i <= kTileStages; i++) mbar_init(&full[i], 1);
         for (int i = 0; i < kTileStages; i++) done[i] = 0;
         fence_mbar_init();
     }
-    __syncthreads();
+    pipe_sync(bar_id);
     if (t0 >= t1) return;
     auto issue = [&](uint32_t t, const TileDesc& td) { // one thread
         const uint32_t st = (t - t0) % kTileStages;
@@ -96,12 +104,12 @@ __device__ __forceinline__ void tile_pipeline(const DecodeParams& P, uint8_t* sm
             on_chunk(cur_chunk, &full[kTileStages], extra_phase);
         }
         const pqg_page_desc* pds = reinterpret_cast<const pqg_page_desc*>(tile + TB + 16);
-        for (uint32_t j = warp_id(); j < tm.n_pages; j += kWarpsPerCta) {
+        for (uint32_t j = wid; j < tm.n_pages; j += kWarpsPerCta) {
             const pqg_page_desc pd = pds[j];
             on_page(tm.first_page + j, pd, tile + (pd.payload_off - tm.byte_lo));
         }
-        if (P.tile_sync) { // A/B: the classic CTA-wide barrier, refill by thread 0
-            __syncthreads();
+        if (P.tile_sync) { // the classic barrier per tile, refill by thread 0
+            pipe_sync(bar_id);
             if (tid == 0 && t + kTileStages < t1) issue(t + kTileStages, P.tiles[t + kTileStages]);
             continue;
         }

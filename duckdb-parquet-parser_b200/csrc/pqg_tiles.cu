@@ -440,8 +440,8 @@ __device__ __forceinline__ void fast_page_opt(const DecodeParams& P, uint32_t q,
 // OPT = the plan has OPTIONAL chunks.  The REQUIRED-only instantiation stays at <= 64 registers
 // (4 CTAs/SM); carrying the level code costs 8 more and a whole CTA per SM (measured: PLAIN
 // 0.262 -> 0.284 ms, dictionary bw 8 0.177 -> 0.203 ms per 100 M values).
-template <int W, int TB, bool OPT, bool PART = false>
-__global__ void __launch_bounds__(kThreadsPerCta, PART ? 1 : (OPT ? 3 : 4)) k_fixed_tiles(const DecodeParams P) {
+template <int W, int TB, bool OPT>
+__global__ void __launch_bounds__(kThreadsPerCta, OPT ? 3 : 4) k_fixed_tiles(const DecodeParams P) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint32_t* vwords = reinterpret_cast<uint32_t*>(smem + tile_pipe_bytes(TB)) + warp_id() * 64; // per warp: 32 validity words + 32 rank bases
     uint8_t* sdict = smem + tile_pipe_bytes(TB) + kLevelScratchBytes;
@@ -449,7 +449,6 @@ __global__ void __launch_bounds__(kThreadsPerCta, PART ? 1 : (OPT ? 3 : 4)) k_fi
     const uint8_t* dictp = nullptr;
     bool has_dict = false, dict_in_smem = false;
     int max_def = 0;
-    uint32_t part_lo = 0;
     tile_pipeline<TB>(P, smem,
         [&](uint32_t chunk, uint64_t* bar, uint32_t& phase) {
             const DevChunk& ck = P.chunks[chunk];
@@ -458,21 +457,6 @@ __global__ void __launch_bounds__(kThreadsPerCta, PART ? 1 : (OPT ? 3 : 4)) k_fi
             dict_n = ck.dict_ok_n;
             dictp = P.dict_arena + ck.dict_arena_off;
             dict_in_smem = false;
-            if constexpr (PART) {
-                // this CTA's part of the dictionary: entries [part_lo, part_lo + part_entries)
-                part_lo = (blockIdx.x & ((1u << P.part_bits) - 1u)) * P.part_entries;
-                const uint32_t cnt = (has_dict && part_lo < dict_n) ? min(P.part_entries, dict_n - part_lo) : 0u;
-                const uint32_t pbytes = (cnt * W + 15u) & ~15u;
-                __syncthreads(); // nobody reads the previous dictionary any more
-                if (pbytes) {
-                    if (threadIdx.x == 0) { mbar_expect_tx(bar, pbytes); bulk_g2s(sdict, dictp + static_cast<size_t>(part_lo) * W, pbytes, bar); }
-                    mbar_wait(bar, phase);
-                    phase ^= 1;
-                }
-                dictp = sdict;
-                dict_in_smem = true;
-                return;
-            }
             const uint32_t dbytes = (dict_n * W + 15u) & ~15u;
             if (has_dict && dbytes && dbytes <= P.dict_smem) {
                 __syncthreads(); // nobody reads the previous dictionary any more
@@ -487,9 +471,48 @@ __global__ void __launch_bounds__(kThreadsPerCta, PART ? 1 : (OPT ? 3 : 4)) k_fi
             if constexpr (OPT) {
                 if (max_def > 0) { fast_page_opt<W>(P, q, pd, pg, has_dict, dictp, dict_n, dict_in_smem, vwords, vwords + 32); return; }
             }
-            if constexpr (PART) fast_page<W, true>(P, q, pd, pg, has_dict, dictp, dict_n, true, part_lo);
-            else fast_page<W>(P, q, pd, pg, has_dict, dictp, dict_n, dict_in_smem);
+            fast_page<W>(P, q, pd, pg, has_dict, dictp, dict_n, dict_in_smem);
         });
+}
+
+// Partitioned dictionary: ONE chunk per launch (P.chunk_lo), 1024-thread CTAs = kPartGroups groups of 8 warps.  The CTA keeps
+// entries [part_lo, part_lo + P.part_entries) of the chunk's dictionary in shared memory (staged once, with one bulk copy);
+// its 2^part_bits - 1 siblings (neighbouring block ids) keep the other parts and read the same tiles.  Every group runs its
+// own tile pipeline over its own span of tiles and stores only the values whose index falls into the CTA's part.
+// Why 1024 threads: with the dictionary part taking 128 KB only one CTA fits an SM, and 8 warps cannot hide the latency of the
+// index -> ld.shared -> store chain (measured with 256-thread CTAs: 1.21 ms per 100 M values against 0.49 ms through L2).
+constexpr int kPartGroups = 4;
+template <int W>
+__global__ void __launch_bounds__(kThreadsPerCta * kPartGroups, 1) k_fixed_tiles_part(const DecodeParams P) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t* dbar = reinterpret_cast<uint64_t*>(smem);
+    uint8_t* sdict = smem + 128;
+    uint8_t* pipes = sdict + P.dict_smem;
+    const DevChunk& ck = P.chunks[P.chunk_lo];
+    const uint32_t dict_n = ck.dict_ok_n;
+    const uint32_t part_lo = (blockIdx.x & ((1u << P.part_bits) - 1u)) * P.part_entries;
+    const uint32_t cnt = (ck.has_dict && part_lo < dict_n) ? min(P.part_entries, dict_n - part_lo) : 0u;
+    const uint32_t pbytes = (cnt * W + 15u) & ~15u;
+    if (threadIdx.x == 0) {
+        mbar_init(dbar, 1);
+        fence_mbar_init();
+        if (pbytes) { mbar_expect_tx(dbar, pbytes); bulk_g2s(sdict, P.dict_arena + ck.dict_arena_off + static_cast<size_t>(part_lo) * W, pbytes, dbar); }
+    }
+    __syncthreads();
+    if (pbytes) mbar_wait(dbar, 0);
+    const uint32_t group = threadIdx.x / kThreadsPerCta;
+    const uint32_t sub = (blockIdx.x >> P.part_bits) * kPartGroups + group; // this group's span of the chunk's tiles
+    PipeGroup g;
+    g.bar_id = 1u + group;
+    g.tid = threadIdx.x % kThreadsPerCta;
+    g.warp = g.tid >> 5;
+    g.t0 = min(P.tile_hi, P.tile_lo + sub * P.tiles_per_cta);
+    g.t1 = min(P.tile_hi, g.t0 + P.tiles_per_cta);
+    const bool has_dict = ck.has_dict;
+    tile_pipeline<kTileBytes>(P, pipes + group * tile_pipe_bytes(kTileBytes),
+        [&](uint32_t, uint64_t*, uint32_t&) {},
+        [&](uint32_t q, const pqg_page_desc& pd, const uint8_t* pg) { fast_page<W, true>(P, q, pd, pg, has_dict, sdict, dict_n, true, part_lo); },
+        &g);
 }
 
 } // namespace
@@ -499,40 +522,48 @@ bool chunk_is_tileable(int phys_type, int max_def, int max_rep) {
     return w48 && max_def <= 1 && max_rep <= 0;
 }
 
-template <int W, int TB, bool OPT, bool PART = false>
+template <int W, int TB, bool OPT>
 static cudaError_t launch_tiles_t(DecodeParams p, int sm_count, cudaStream_t s) {
     const size_t smem = static_cast<size_t>(tile_pipe_bytes(TB)) + kLevelScratchBytes + p.dict_smem;
     // (attributes are per device: set on every launch, it is cheap)
-    cudaError_t e = cudaFuncSetAttribute(k_fixed_tiles<W, TB, OPT, PART>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    cudaError_t e = cudaFuncSetAttribute(k_fixed_tiles<W, TB, OPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
     // contiguous tile spans per CTA (a CTA stages a chunk's dictionary once)
     int resident = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k_fixed_tiles<W, TB, OPT, PART>, kThreadsPerCta, smem);
-    if (PART) {
-        // 2^part_bits sibling CTAs per tile span: spans sized so that the siblings of all spans are resident together
-        const uint32_t parts = 1u << p.part_bits, n_tiles = p.tile_hi - p.tile_lo;
-        uint32_t spans = std::max<uint32_t>(1u, static_cast<uint32_t>(sm_count) * static_cast<uint32_t>(std::max(resident, 1)) * 2u / parts);
-        uint32_t per = (n_tiles + spans - 1) / spans;
-        if (per < 4) per = 4;
-        p.tiles_per_cta = per;
-        const uint32_t grid = ((n_tiles + per - 1) / per) * parts;
-        k_fixed_tiles<W, TB, OPT, PART><<<grid, kThreadsPerCta, smem, s>>>(p);
-        return cudaGetLastError();
-    }
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k_fixed_tiles<W, TB, OPT>, kThreadsPerCta, smem);
     const uint32_t grid = tile_grid(p.tile_hi - p.tile_lo, sm_count, resident, &p.tiles_per_cta);
-    k_fixed_tiles<W, TB, OPT, PART><<<grid, kThreadsPerCta, smem, s>>>(p);
+    k_fixed_tiles<W, TB, OPT><<<grid, kThreadsPerCta, smem, s>>>(p);
     return cudaGetLastError();
+}
+
+// one chunk (p.chunk_lo, tiles [tile_lo, tile_hi)); p.part_bits / part_entries / dict_smem set by the caller
+template <int W>
+static cudaError_t launch_part_t(DecodeParams p, int sm_count, cudaStream_t s) {
+    const size_t smem = 128 + p.dict_smem + static_cast<size_t>(kPartGroups) * tile_pipe_bytes(kTileBytes);
+    cudaError_t e = cudaFuncSetAttribute(k_fixed_tiles_part<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    const uint32_t parts = 1u << p.part_bits, n_tiles = p.tile_hi - p.tile_lo;
+    // one wave: sm_count CTAs = sm_count / parts spans x parts; every span is cut into kPartGroups sub-spans
+    uint32_t spans = std::max<uint32_t>(1u, static_cast<uint32_t>(sm_count) / parts);
+    uint32_t per = (n_tiles + spans * kPartGroups - 1) / (spans * kPartGroups);
+    if (per < 2) per = 2;
+    p.tiles_per_cta = per;
+    spans = (n_tiles + per * kPartGroups - 1) / (per * kPartGroups);
+    k_fixed_tiles_part<W><<<spans * parts, kThreadsPerCta * kPartGroups, smem, s>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fixed_tiles_part(const DecodeParams& p, int width, int sm_count, cudaStream_t s) {
+    if (p.tile_hi <= p.tile_lo) return cudaSuccess;
+    if (width == 4) return launch_part_t<4>(p, sm_count, s);
+    if (width == 8) return launch_part_t<8>(p, sm_count, s);
+    return cudaErrorInvalidValue;
 }
 
 cudaError_t launch_fixed_tiles(const DecodeParams& p, int width, int sm_count, cudaStream_t s) {
     if (p.tile_hi <= p.tile_lo) return cudaSuccess;
     // plans with OPTIONAL chunks: 16 KB tiles + the level code; REQUIRED-only plans: the lean kernel
     const bool opt = p.tile_bytes == static_cast<uint32_t>(kTileBytesLarge);
-    if (p.part_entries && !opt) { // partitioned dictionary (REQUIRED-only plans)
-        if (width == 4) return launch_tiles_t<4, kTileBytes, false, true>(p, sm_count, s);
-        if (width == 8) return launch_tiles_t<8, kTileBytes, false, true>(p, sm_count, s);
-        return cudaErrorInvalidValue;
-    }
     if (width == 4) return opt ? launch_tiles_t<4, kTileBytesLarge, true>(p, sm_count, s) : launch_tiles_t<4, kTileBytes, false>(p, sm_count, s);
     if (width == 8) return opt ? launch_tiles_t<8, kTileBytesLarge, true>(p, sm_count, s) : launch_tiles_t<8, kTileBytes, false>(p, sm_count, s);
     return cudaErrorInvalidValue;

@@ -176,9 +176,11 @@ PQG_API int pqg_plan_create_dict_indices(pqg_ctx* ctx, const pqg_buf* image, con
                                          uint32_t n_chunks, const pqg_page_desc* pages, uint32_t n_pages,
                                          pqg_plan** out);
 PQG_API void pqg_plan_destroy(pqg_ctx* ctx, pqg_plan* plan);
-/* tuning switches of a plan (A/B measurements; the defaults are the measured best).  PQG_OPT_PARTITIONED_DICT (default 1):
- * dictionaries of 32 KB .. 512 KB of values in REQUIRED-only 4/8-byte plans are split over the shared memories of 2..4
- * sibling CTAs that read the same page tiles (0: gathered from L2 like the larger ones). */
+/* tuning switches of a plan (A/B measurements; the defaults are the measured best).  PQG_OPT_PARTITIONED_DICT (default 0):
+ * dictionaries of 32 KB .. 512 KB of values in REQUIRED-only 4/8-byte plans are split over the shared memories of 1..4
+ * sibling 1024-thread CTAs that read the same page tiles and emit only the values of their part, instead of being gathered
+ * from L2.  Measured on B200 (bench.py, cfg2 i64_d16 / f64_d16, 100 M values): 0.60 ms against 0.49 ms for the L2 gather
+ * (256-thread CTAs: 1.21 ms), so it stays off; kept for A/B runs. */
 enum { PQG_OPT_PARTITIONED_DICT = 1 };
 PQG_API int pqg_plan_set_option(pqg_plan* plan, int option, int value);
 /* re-point a plan at another resident image with the same layout (pipelined ingest) */
