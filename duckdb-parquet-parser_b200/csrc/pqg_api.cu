@@ -63,6 +63,7 @@ struct pqg_plan {
     bool any_dict = false, any_def = false, is_str = false, is_bool = false;
     bool forced_validity = false; // a REQUIRED chunk held an out-of-range dictionary index (null in the reference): validity added, plan re-run
     bool run_pending = false;     // pqg_plan_run / run_pipelined enqueued, pqg_plan_finish not called yet
+    bool opt_idx = false;         // OPTIONAL fixed-width plan with foreign-looking pages (see DecodeParams::opt_idx)
     bool no_part = true;          // partitioned-dictionary mode: measured slower than the L2 gather (0.60 vs 0.49 ms per 100 M values): opt-in (pqg_plan_set_option)
     int phys = 0, width = 0;
     uint64_t n_slots = 0;
@@ -469,6 +470,8 @@ static int plan_create_impl(pqg_ctx* ctx, const pqg_buf* image, const pqg_chunk_
                     continue;
                 }
                 if (!tileable || too_big) { flush(); slow.push_back(q); continue; }
+                // OPTIONAL pages beyond the writer's shapes: the tile kernel decodes the small ones itself and needs its index buffer
+                if (!p->is_str && s.max_def == 1 && (pg.num_values > 1024u || pg.payload_size > 2048u)) p->opt_idx = true;
                 place(q, pg);
             }
             flush();
@@ -598,9 +601,11 @@ static DecodeParams make_params(const pqg_plan* p) {
     P.page_chars = p->d_page_chars; P.page_char_base = p->d_page_char_base; P.err = p->d_err;
     P.tiles = p->d_tiles; P.tile_lo = 0; P.tile_hi = p->n_tiles; P.dict_smem = p->dict_smem;
     P.slow_lo = 0; P.slow_hi = p->n_slow_host; P.slow_pages = p->d_slow_pages; P.slow_append = p->d_slow_pages + p->n_slow_host;
+    P.slow_cap = static_cast<uint32_t>(p->pages.size() + p->virt_pages.size() + 1); P.n_slots = p->n_slots;
     P.chunk_lo = 0;
     P.tile_bytes = p->tile_bytes;
     P.identity_dict = p->identity ? 1u : 0u;
+    P.opt_idx = p->opt_idx ? 1u : 0u;
     P.exact_sizes = p->force_exact ? 1u : 0u;
     return P;
 }

@@ -55,6 +55,7 @@ struct BigSmem {
 
 __device__ __forceinline__ void hand_over(const DecodeParams& P, uint32_t q) {
     uint32_t k = atomicAdd(&P.err->slow_count, 1u);
+    PQG_ASSERT(k < P.slow_cap);
     P.slow_append[k] = q;
 }
 
@@ -164,6 +165,7 @@ __device__ __noinline__ void scan_runs_parallel(BigSmem& S, const uint8_t* cb, u
     // A: the jump table
     for (uint32_t k = 0; k < kPer; k++) {
         const uint32_t i = tid * kPer + k;
+        PQG_ASSERT(take <= static_cast<uint32_t>(kBigChunk) + 32u);
         if (i < W) S.jmp[i] = static_cast<uint16_t>(parse_run_header(cb, take, i, bw, nb).next);
     }
     if (tid < kScanWin / 32) S.reach[tid] = tid == 0 ? 1u : 0u;
@@ -180,6 +182,7 @@ __device__ __noinline__ void scan_runs_parallel(BigSmem& S, const uint8_t* cb, u
             m &= m - 1;
             const uint32_t j = S.jmp[tid * kPer + k];
             if (j < W) {
+                PQG_ASSERT((j >> 5) < static_cast<uint32_t>(kScanWin) / 32u);
                 const uint32_t bit = 1u << (j & 31u);
                 if (!(atomicOr(&S.reach[j >> 5], bit) & bit)) S.changed = 1;
             }
@@ -278,6 +281,7 @@ __global__ void __launch_bounds__(kBigThreads) k_big_pages(const DecodeParams P)
         const DevChunk& ck = P.chunks[pd.chunk_idx];
         const uint32_t n = pd.num_values, size = pd.payload_size;
         if (n == 0) continue;
+        PQG_ASSERT(pd.out_row_base + n <= P.n_slots);
         const uint8_t* pg = P.image + pd.payload_off;
         __syncthreads();
         // ---- levels ----
@@ -340,6 +344,7 @@ __global__ void __launch_bounds__(kBigThreads) k_big_pages(const DecodeParams P)
                         sl += cnt;
                         r++;
                     }
+                    PQG_ASSERT(w < static_cast<uint32_t>(kBigSlots) / 32u);
                     if (bits) atomicOr(&S.pv[w], bits);
                 }
                 __syncthreads();

@@ -550,6 +550,7 @@ __global__ void __launch_bounds__(kThreadsPerCta) k_decode_fixed(DecodeParams P)
         i = __shfl_sync(0xffffffffu, i, 0);
         if (i >= total) break;
         const uint32_t q = i < n_host ? P.slow_pages[P.slow_lo + i] : P.slow_append[i - n_host];
+        PQG_ASSERT(i < n_host || i - n_host < P.slow_cap);
         const DevChunk& ck = P.chunks[P.pages[q].chunk_idx];
         decode_fixed_page<W, BOOLP>(P, q, ck, P.dict_arena + ck.dict_arena_off, ws);
         __syncwarp();
@@ -766,6 +767,7 @@ __device__ __forceinline__ uint32_t copy_ranked_dict_tile(const DecodeParams& P,
     };
     auto put = [&](const uint4& pv, uint32_t apos) {
         const uint32_t o = apos - sbase, sh = (o & 3u) * 8u, a = stw + (o & ~3u);
+        PQG_ASSERT((o & ~3u) + 20u <= static_cast<uint32_t>(kStageBytes32));
         const uint32_t w3 = pv.w & 0x00ffffffu;
         const uint32_t x0 = pv.x << sh, x1 = __funnelshift_l(pv.x, pv.y, sh), x2 = __funnelshift_l(pv.y, pv.z, sh);
         const uint32_t x3 = __funnelshift_l(pv.z, w3, sh), x4 = __funnelshift_l(w3, 0u, sh);
@@ -882,6 +884,7 @@ __device__ __forceinline__ void stage_or_words(uint32_t stage_s, uint32_t o, uin
     // `len` bytes at shared address `sp` -> stage byte offset `o`
     const uint32_t d = o & 3u, src0 = sp - d, sa = src0 & ~3u, sh = (src0 & 3u) * 8u;
     const uint32_t nw = (d + len + 3u) >> 2, da = stage_s + (o & ~3u), tail = (d + len) & 3u;
+    PQG_ASSERT(nw <= static_cast<uint32_t>(NW) && (o & ~3u) + 4u * nw <= static_cast<uint32_t>(kStageBytes32));
     uint32_t wp;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wp) : "r"(sa));
 #pragma unroll

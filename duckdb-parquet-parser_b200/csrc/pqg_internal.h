@@ -6,6 +6,15 @@
 
 #include "pqg.h"
 
+// Debug build (make EXTRA=-DPQG_DEBUG_ASSERTS): device-side checks of the shared / global indices the kernels compute
+// (compute-sanitizer is not available on the GPU pool; the GPU suite is run once under this build, see profiles/README.md)
+#if defined(PQG_DEBUG_ASSERTS) && defined(__CUDACC__)
+#include <cstdio>
+#define PQG_ASSERT(c) do { if (!(c)) { printf("PQG_ASSERT failed: %s  (%s:%d, block %d thread %d)\n", #c, __FILE__, __LINE__, blockIdx.x, threadIdx.x); __trap(); } } while (0)
+#else
+#define PQG_ASSERT(c) ((void)0)
+#endif
+
 namespace pqg {
 
 constexpr int kWarpsPerCta = 8;
@@ -117,8 +126,11 @@ struct DecodeParams {
     uint32_t slow_lo, slow_hi; // host-listed slow pages of this launch: slow_pages[slow_lo, slow_hi)
     uint32_t* slow_pages;    // host-listed slow pages (n_slow_host entries)
     uint32_t* slow_append;   // pages handed over on the device: slow_append[0 .. err->slow_count); capacity: every page of the plan
+    uint32_t slow_cap;       // ... that capacity (debug asserts)
+    uint64_t n_slots;        // output slots of the plan (debug asserts)
     uint32_t chunk_lo;       // first chunk of this launch (dictionary preparation)
     uint32_t tile_sync;      // 1: CTA-wide barrier per tile instead of the last-warp refill (the regex scan: issue bound)
+    uint32_t opt_idx;        // OPTIONAL plans with foreign-looking pages (> 1024 slots / > 4 KB): the tile kernel carries a per-warp index buffer
     uint32_t part_bits;      // partitioned-dictionary launch: log2 of the CTAs that share a tile span (0: off)
     uint32_t part_entries;   // ... dictionary entries per part (a power of two)
     uint32_t handover_hint;  // pages the tile kernel handed to the general kernel in the previous run of the plan (~0u: unknown)

@@ -8,9 +8,10 @@
 // Replaces, per page: read_data_page's level / index decoding
 // (reference src/reader/column_reader.cpp:143-182) and RleDecoder::get_batch
 // (reference include/reader/rle_decoder.hpp:17-95), restated as
-//   run discovery  -> a table of runs (lane 0 walks headers; two regular layouts are
-//                     recognised in parallel and need no walk at all),
-//   run expansion  -> one lane per run (long RLE runs: whole warp),
+//   run discovery  -> two regular layouts (the reference writer's) are recognised and expanded fully in parallel;
+//                     any other stream is taken run by run with warp-uniform header parsing (every lane reads the
+//                     same header bytes), so that
+//   run expansion  -> is done by the whole warp on every run (lanes by validity word / by value),
 //   slot emission  -> one lane per output slot, 32 slots per step, coalesced stores.
 #pragma once
 #include "pqg_internal.h"
@@ -89,16 +90,10 @@ struct __align__(16) WarpScratch {
     uint32_t idx[kIdxWords];
     uint32_t valid[32];
     uint32_t rankbase[32];
-    uint32_t run_start[32];
-    uint32_t run_count[32]; // bit 31: literal (bit-packed) piece
-    uint32_t run_val[32];   // RLE value, or bit offset of the literal piece
-    uint32_t nruns;
-    uint32_t batch_total;
-    uint32_t pad[2];
     uint8_t stage[kStageBytes32]; // BYTE_ARRAY copy pass: the chars of 32 short strings, flushed with aligned vectors
 };
 
-// ---- run discovery: the sequential header walk (lane 0) ------------------------------------
+// ---- run discovery ---------------------------------------------------------------------------
 struct Walker {
     const uint8_t* s;  // stream bytes
     uint32_t len;      // header parsing bound (RleDecoder::size_)
@@ -113,49 +108,45 @@ __device__ __forceinline__ void walker_init(Walker& w, const uint8_t* s, uint32_
     w.rem = 0; w.lit = 0; w.val = 0; w.bit = 0; w.next_pos = 0; w.bad = 0;
 }
 
-// Lane 0: append up to 32 run pieces covering `want` values to the scratch table.
-// Literal pieces are capped at 32 values so that one lane expands one piece.
-__device__ __forceinline__ void walker_fill(Walker& w, WarpScratch& ws, uint32_t want) {
-    uint32_t n = 0, produced = 0;
+// ---- run discovery, warp-uniform: EVERY lane parses the next run header (the same bytes: a broadcast load), so the warp
+// can expand the run together -- no lane-0 walk, no 32-value pieces, no run table.  RleDecoder::next_counts
+// (rle_decoder.hpp:37-53): returns false when the stream is exhausted (remaining outputs read as 0, :21-24); w.bad is set
+// for a zero-length run (undefined behaviour in the reference).
+__device__ __forceinline__ bool walker_next_run(Walker& w) {
+    if (w.pos >= w.len) return false;
     const uint8_t* s = w.s;
-    while (n < 32 && produced < want) {
-        if (w.rem == 0) {
-            if (w.pos >= w.len) { // stream exhausted: remaining outputs are 0 (rle_decoder.hpp:21-24)
-                ws.run_start[n] = produced; ws.run_count[n] = want - produced; ws.run_val[n] = 0;
-                n++; produced = want;
-                break;
-            }
-            uint32_t ind = 0, shift = 0;
-            while (w.pos < w.len) { // read_varint32 (rle_decoder.hpp:76-86)
-                uint32_t b = s[w.pos++];
-                if (shift < 32) ind |= (b & 0x7Fu) << shift;
-                if (!(b & 0x80u)) break;
-                shift += 7;
-            }
-            if (ind & 1u) {
-                w.rem = (ind >> 1) * 8u; w.lit = 1; w.bit = w.pos * 8u;
-                w.next_pos = w.pos + static_cast<uint32_t>((static_cast<uint64_t>(w.rem) * w.bw + 7) >> 3);
-            } else {
-                w.rem = ind >> 1; w.lit = 0;
-                uint32_t nb = (w.bw + 7) >> 3, v = 0;
-                for (uint32_t i = 0; i < nb && w.pos < w.len; i++) { // value bytes are not masked (:88-95)
-                    if (i < 4) v |= static_cast<uint32_t>(s[w.pos]) << (8 * i);
-                    w.pos++;
-                }
-                w.val = v;
-            }
-            if (w.rem == 0) { w.bad = PQG_PAGE_BAD_RUN; break; } // reference: undefined behaviour
-        }
-        uint32_t take = min(w.rem, want - produced);
-        if (w.lit) take = min(take, 32u);
-        ws.run_start[n] = produced;
-        ws.run_count[n] = take | (w.lit << 31);
-        ws.run_val[n] = w.lit ? w.bit : w.val;
-        n++; produced += take; w.rem -= take;
-        if (w.lit) { w.bit += take * w.bw; if (w.rem == 0) w.pos = w.next_pos; }
+    uint32_t ind = 0, shift = 0;
+    while (w.pos < w.len) { // read_varint32 (rle_decoder.hpp:76-86)
+        const uint32_t b = s[w.pos++];
+        if (shift < 32) ind |= (b & 0x7Fu) << shift;
+        if (!(b & 0x80u)) break;
+        shift += 7;
     }
-    ws.nruns = n;
-    ws.batch_total = produced;
+    if (ind & 1u) {
+        w.rem = (ind >> 1) * 8u; w.lit = 1; w.bit = w.pos * 8u;
+        w.next_pos = w.pos + static_cast<uint32_t>((static_cast<uint64_t>(w.rem) * w.bw + 7) >> 3);
+    } else {
+        w.rem = ind >> 1; w.lit = 0;
+        const uint32_t nb = (w.bw + 7) >> 3;
+        uint32_t v = 0;
+        for (uint32_t i = 0; i < nb && w.pos < w.len; i++) { // value bytes are not masked (:88-95)
+            if (i < 4) v |= static_cast<uint32_t>(s[w.pos]) << (8 * i);
+            w.pos++;
+        }
+        w.val = v;
+    }
+    if (w.rem == 0) w.bad = PQG_PAGE_BAD_RUN;
+    return true;
+}
+// OR `cnt` bits (all ones, or the stream bits from `srcbit` on when src != null) into words[] from bit `start` on; lanes by word
+__device__ __forceinline__ void or_bits_warp(uint32_t* words, uint32_t start, uint32_t cnt, const uint8_t* src, uint32_t srcbit) {
+    const uint32_t w0 = start >> 5, w1 = (start + cnt - 1u) >> 5;
+    for (uint32_t w = w0 + lane_id(); w <= w1; w += 32) {
+        const uint32_t lo = max(w * 32u, start), hi = min(w * 32u + 32u, start + cnt), c = hi - lo;
+        uint32_t bits = c >= 32u ? 0xffffffffu : ((1u << c) - 1u);
+        if (src) bits &= ldbits(src, srcbit + (lo - start), c);
+        if (bits) atomicOr(&words[w], bits << (lo & 31u));
+    }
 }
 
 __device__ __forceinline__ void set_bits_range(uint32_t* words, uint32_t start, uint32_t cnt) {
@@ -249,38 +240,41 @@ __device__ __forceinline__ uint32_t levels_tile(Walker& w, WarpScratch& ws, uint
             }
         }
     }
-    uint32_t produced = 0;
-    uint32_t bw = __shfl_sync(0xffffffffu, w.bw, 0);
-    uint32_t avail = __shfl_sync(0xffffffffu, w.avail, 0);
-    unsigned long long sp = __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(w.s), 0);
-    const uint8_t* s = reinterpret_cast<const uint8_t*>(sp);
-    while (!done && produced < t) {
-        if (l == 0) walker_fill(w, ws, t - produced);
-        __syncwarp();
-        uint32_t nruns = ws.nruns, total = ws.batch_total;
-        uint32_t wbad = __shfl_sync(0xffffffffu, w.bad, 0);
-        if (wbad) { *bad = wbad; return 0; }
-        if (l < nruns) {
-            uint32_t rc = ws.run_count[l], start = produced + ws.run_start[l], v = ws.run_val[l];
-            uint32_t cnt = rc & 0x7fffffffu;
-            if (!(rc >> 31)) {
-                if (cnt && level_present(v, max_def)) set_bits_range(ws.valid, start, cnt);
-            } else if (cnt) {
-                uint32_t m = 0;
-                bool inb = ((static_cast<uint64_t>(v) + static_cast<uint64_t>(cnt) * bw + 7) >> 3) <= avail;
+    // any other stream: run by run, the whole warp on each run (the Walker state is the same in every lane)
+    {
+        const uint32_t bw = w.bw, avail = w.avail;
+        const uint8_t* s = w.s;
+        uint32_t produced = 0;
+        while (!done && produced < t) {
+            if (w.rem == 0) {
+                if (!walker_next_run(w)) break;            // exhausted: the remaining slots read level 0 = null (max_def > 0 here)
+                if (w.bad) { *bad = w.bad; return 0; }
+            }
+            const uint32_t take = min(w.rem, t - produced);
+            if (!w.lit) {
+                if (level_present(w.val, max_def)) or_bits_warp(ws.valid, produced, take, nullptr, 0);
+            } else {
+                const bool inb = ((static_cast<uint64_t>(w.bit) + static_cast<uint64_t>(take) * bw + 7) >> 3) <= avail;
                 if (inb && bw == 1 && max_def == 1) {
-                    m = ldbits(s, v, cnt); // the packed bits ARE the validity bits
+                    or_bits_warp(ws.valid, produced, take, s, w.bit); // the packed bits ARE the validity bits
                 } else {
-                    for (uint32_t j = 0; j < cnt; j++) {
-                        uint32_t lv = inb ? ldbits(s, v + j * bw, bw) : ldbits_bounded(s, v + j * bw, bw, avail);
-                        if (level_present(lv, max_def)) m |= 1u << j;
+                    for (uint32_t j0 = 0; j0 < take; j0 += 32) {
+                        const uint32_t j = j0 + l;
+                        bool pres = false;
+                        if (j < take) {
+                            const uint32_t lv = inb ? ldbits(s, w.bit + j * bw, bw) : ldbits_bounded(s, w.bit + j * bw, bw, avail);
+                            pres = level_present(lv, max_def);
+                        }
+                        const uint32_t m = __ballot_sync(0xffffffffu, pres);
+                        if (l == 0) set_bits_word(ws.valid, produced + j0, m);
                     }
                 }
-                set_bits_word(ws.valid, start, m);
+                w.bit += take * bw;
             }
+            w.rem -= take;
+            if (w.lit && w.rem == 0) w.pos = w.next_pos;
+            produced += take;
         }
-        produced += total;
-        __syncwarp();
     }
     __syncwarp();
     uint32_t c = __popc(ws.valid[l]);
@@ -302,43 +296,31 @@ __device__ __forceinline__ uint32_t idx_load(const uint32_t* buf, uint32_t k, bo
 // `wide` = indices may need more than 16 bits (bw > 16): cnt <= 512, else cnt <= 1024.
 __device__ __forceinline__ void indices_tile(Walker& w, WarpScratch& ws, uint32_t cnt_total, bool wide, uint32_t* bad) {
     const uint32_t l = lane_id();
+    const uint32_t bw = w.bw, avail = w.avail;
+    const uint8_t* s = w.s;
     uint32_t produced = 0;
-    uint32_t bw = __shfl_sync(0xffffffffu, w.bw, 0);
-    uint32_t avail = __shfl_sync(0xffffffffu, w.avail, 0);
-    unsigned long long sp = __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(w.s), 0);
-    const uint8_t* s = reinterpret_cast<const uint8_t*>(sp);
-    while (produced < cnt_total) {
-        if (l == 0) walker_fill(w, ws, cnt_total - produced);
-        __syncwarp();
-        uint32_t nruns = ws.nruns, total = ws.batch_total;
-        uint32_t wbad = __shfl_sync(0xffffffffu, w.bad, 0);
-        if (wbad) { *bad = wbad; return; }
-        uint32_t rc = 0, start = 0, v = 0;
-        if (l < nruns) { rc = ws.run_count[l]; start = produced + ws.run_start[l]; v = ws.run_val[l]; }
-        uint32_t cnt = rc & 0x7fffffffu;
-        bool lit = rc >> 31;
-        if (cnt && lit) {
-            bool inb = ((static_cast<uint64_t>(v) + static_cast<uint64_t>(cnt) * bw + 7) >> 3) <= avail;
-            for (uint32_t j = 0; j < cnt; j++) {
-                uint32_t x = inb ? ldbits(s, v + j * bw, bw) : ldbits_bounded(s, v + j * bw, bw, avail);
-                idx_store(ws.idx, start + j, x, wide);
+    while (produced < cnt_total) { // run by run, the whole warp on each run (uniform Walker state)
+        if (w.rem == 0) {
+            if (!walker_next_run(w)) { // exhausted: the remaining indices read as 0 (rle_decoder.hpp:21-24)
+                for (uint32_t k = produced + l; k < cnt_total; k += 32) idx_store(ws.idx, k, 0u, wide);
+                break;
             }
-        } else if (cnt && cnt <= 32) {
-            for (uint32_t j = 0; j < cnt; j++) idx_store(ws.idx, start + j, v, wide);
+            if (w.bad) { *bad = w.bad; return; }
         }
-        // long RLE runs: the whole warp fills them
-        uint32_t longm = __ballot_sync(0xffffffffu, cnt > 32 && !lit);
-        while (longm) {
-            int r = __ffs(longm) - 1;
-            longm &= longm - 1;
-            uint32_t rs = __shfl_sync(0xffffffffu, start, r);
-            uint32_t rn = __shfl_sync(0xffffffffu, cnt, r);
-            uint32_t rv = __shfl_sync(0xffffffffu, v, r);
-            for (uint32_t j = l; j < rn; j += 32) idx_store(ws.idx, rs + j, rv, wide);
+        const uint32_t take = min(w.rem, cnt_total - produced);
+        if (w.lit) {
+            const bool inb = ((static_cast<uint64_t>(w.bit) + static_cast<uint64_t>(take) * bw + 7) >> 3) <= avail;
+            for (uint32_t j = l; j < take; j += 32)
+                idx_store(ws.idx, produced + j, inb ? ldbits(s, w.bit + j * bw, bw) : ldbits_bounded(s, w.bit + j * bw, bw, avail), wide);
+            w.bit += take * bw;
+        } else {
+            for (uint32_t j = l; j < take; j += 32) idx_store(ws.idx, produced + j, w.val, wide);
         }
-        produced += total;
-        __syncwarp();
+        w.rem -= take;
+        if (w.lit && w.rem == 0) w.pos = w.next_pos;
+        produced += take;
     }
+    __syncwarp();
 }
 
 // All runs are single bit-packed groups "03 <bw bytes>" (what RleBpEncoder emits for data

@@ -251,6 +251,7 @@ __global__ void __launch_bounds__(kThreadsPerCta) k_regex_pages(RegexParams R) {
 // the slow list.
 __device__ __forceinline__ void rx_to_slow(const DecodeParams& P, uint32_t q) {
     uint32_t k = atomicAdd(&P.err->slow_count, 1u);
+    PQG_ASSERT(k < P.slow_cap);
     P.slow_append[k] = q;
 }
 
@@ -866,7 +867,7 @@ int pqg_regex_scan(pqg_ctx* ctx, pqg_plan* plan, const pqg_dfa* dfa, int neg, ui
     DevErr* d_err = nullptr; uint32_t* d_append = nullptr;
     CUF(ctx, mem.alloc(&d_err, 1));
     CUF(ctx, mem.alloc(&d_append, static_cast<size_t>(n_pages) + 1));
-    P.err = d_err; P.slow_append = d_append;
+    P.err = d_err; P.slow_append = d_append; P.slow_cap = n_pages + 1;
     CUF(ctx, mem.alloc(&d_blob, blob.size() + 16));
     CUF(ctx, mem.alloc(&d_dmatch, plan_dict_arena_bytes(plan) / 8 + 16));
     CUF(ctx, mem.alloc(&d_bits, words + 1));

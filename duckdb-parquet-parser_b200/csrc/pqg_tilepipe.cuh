@@ -106,6 +106,7 @@ __device__ __forceinline__ void tile_pipeline(const DecodeParams& P, uint8_t* sm
         const pqg_page_desc* pds = reinterpret_cast<const pqg_page_desc*>(tile + TB + 16);
         for (uint32_t j = wid; j < tm.n_pages; j += kWarpsPerCta) {
             const pqg_page_desc pd = pds[j];
+            PQG_ASSERT(pd.payload_off >= tm.byte_lo && pd.payload_off - tm.byte_lo + pd.payload_size <= static_cast<uint64_t>(TB) + 16u);
             on_page(tm.first_page + j, pd, tile + (pd.payload_off - tm.byte_lo));
         }
         if (P.tile_sync) { // the classic barrier per tile, refill by thread 0

@@ -36,6 +36,7 @@ namespace pqg {
 namespace {
 
 constexpr int kLevelScratchBytes = kWarpsPerCta * 64 * 4; // validity image + rank bases per warp
+constexpr int kOptIdxBytes = kWarpsPerCta * 1024 * 2;   // u16 dictionary indices of a 1024-slot sub-tile per warp (opt_page_runs)
 
 template <int W> struct FElem;
 template <> struct FElem<4> { using T = uint32_t; };
@@ -62,6 +63,7 @@ template <> __device__ __forceinline__ void st_stream<uint64_t>(uint64_t* p, uin
 __device__ __forceinline__ void to_slow(const DecodeParams& P, uint32_t q) {
     // one lane
     uint32_t k = atomicAdd(&P.err->slow_count, 1u);
+    PQG_ASSERT(k < P.slow_cap);
     P.slow_append[k] = q;
 }
 
@@ -87,7 +89,7 @@ struct DictRef { const void* gptr; uint32_t saddr; };
 template <typename T, int W, int MODE>
 __device__ __forceinline__ T dict_get(const DictRef& d, uint32_t ix) {
     if constexpr (MODE == kDictIdent) return static_cast<T>(ix);
-    else if constexpr (MODE == kDictSmem) return lds_elem<T>(d.saddr + ix * W);
+    else if constexpr (MODE == kDictSmem) { PQG_ASSERT(ix * W < static_cast<uint32_t>(kMaxSmemDictBytes)); return lds_elem<T>(d.saddr + ix * W); }
     else return ldg_gather<T>(static_cast<const T*>(d.gptr) + ix);
 }
 template <class F>
@@ -165,6 +167,7 @@ __device__ __forceinline__ bool fast_page(const DecodeParams& P, uint32_t q, con
     const uint32_t l = lane_id();
     const uint32_t n = pd.num_values, size = pd.payload_size;
     if (n == 0) return true;
+    PQG_ASSERT(pd.out_row_base + n <= P.n_slots);
     T* out = reinterpret_cast<T*>(P.values) + pd.out_row_base;
     if (!((pd.flags & PQG_PAGE_FLAG_DICT) && chunk_has_dict)) {
         // PLAIN: read_plain_value per slot == a shifted copy
@@ -269,6 +272,178 @@ __device__ __forceinline__ bool fast_page(const DecodeParams& P, uint32_t q, con
     return !any_bad;
 }
 
+// ---- OPTIONAL pages, any well-formed streams (foreign writers) ---------------------------------------------------
+// What fast_page_opt does not take -- definition levels in literal (bit-packed) runs or RLE runs longer than 63, index
+// streams with RLE runs / literal runs of several groups, pages of more than 1024 slots -- decoded by the same warp out
+// of the staged tile instead of being handed to the general kernel (which walks run headers with one lane and reads the
+// page in place from global memory).  RleDecoder::get_batch (include/reader/rle_decoder.hpp:17-95) restated run by run:
+// every lane parses the (warp-uniform) run header; the warp expands the run together -- a literal level run IS validity
+// bits (copied word-wise into the image), an RLE run a bit range; index runs go to a per-warp u16 buffer addressed by
+// rank.  The page is taken in sub-tiles of 1024 slots; the run state carries over.  Returns false for what the general
+// kernel must do (bit width > 16, truncated / zero-length runs: the reference's error paths).
+struct RunCursor {
+    const uint8_t* s;   // stream bytes (shared)
+    uint32_t len;       // bytes
+    uint32_t pos;       // next header
+    uint32_t rem;       // values left in the current run
+    uint32_t lit;       // literal run
+    uint32_t val;       // RLE value (unmasked)
+    uint32_t bit;       // bit offset of the next literal value
+};
+// parse the next run header (warp-uniform); false: zero-length run or data beyond the stream
+__device__ __forceinline__ bool run_next(RunCursor& c, uint32_t bw) {
+    uint32_t ind = 0, shift = 0;
+    for (;;) {
+        if (c.pos >= c.len || shift > 28u) return false;
+        const uint32_t b = c.s[c.pos++];
+        ind |= (b & 0x7fu) << shift;
+        if (!(b & 0x80u)) break;
+        shift += 7u;
+    }
+    if (ind & 1u) {
+        const uint64_t cnt = static_cast<uint64_t>(ind >> 1) * 8u, bytes = (cnt * bw + 7u) >> 3;
+        if (cnt == 0 || cnt > 0x7fffffffull || c.pos + bytes > c.len) return false;
+        c.rem = static_cast<uint32_t>(cnt); c.lit = 1; c.bit = c.pos * 8u;
+        c.pos += static_cast<uint32_t>(bytes);
+    } else {
+        const uint32_t nb = (bw + 7u) >> 3;
+        if ((ind >> 1) == 0 || c.pos + nb > c.len) return false;
+        uint32_t v = 0;
+        for (uint32_t i = 0; i < nb && i < 4u; i++) v |= static_cast<uint32_t>(c.s[c.pos + i]) << (8u * i);
+        c.rem = ind >> 1; c.lit = 0; c.val = v;
+        c.pos += nb;
+    }
+    return true;
+}
+
+constexpr uint32_t kOptMaxSlots = 8192; // pages beyond that (in a <= 16 KB tile: bit width <= 8 or mostly nulls) go to the general kernel
+
+template <int W>
+__device__ __noinline__ bool opt_page_runs(const DecodeParams& P, const pqg_page_desc& pd, const uint8_t* pg, bool dict_page,
+                                           const uint8_t* dictp, uint32_t dict_n, bool dict_in_smem, uint32_t* vwords, uint32_t* rankbase,
+                                           uint16_t* idx16) {
+    using T = typename FElem<W>::T;
+    const uint32_t l = lane_id();
+    const uint32_t n = pd.num_values, size = pd.payload_size;
+    const uint32_t def_len = ld32u(pg); // (validated by the caller)
+    RunCursor lv{pg + 4, def_len, 0, 0, 0, 0, 0}, ix{nullptr, 0, 0, 0, 0, 0, 0};
+    uint32_t vpos = 4u + def_len, bw = 0;
+    if (dict_page) {
+        if (vpos >= size) return false;
+        bw = pg[vpos];
+        if (bw > 16u) return false;
+        ix.s = pg + vpos + 1u; ix.len = size - vpos - 1u;
+    }
+    const uint8_t* vals = pg + vpos;
+    const DictRef dref{dictp, dict_in_smem ? smem_u32(dictp) : 0u};
+    const int mode = !dict_page ? -1 : (P.identity_dict ? kDictIdent : (dict_in_smem ? kDictSmem : kDictGlobal));
+    uint32_t nn_before = 0;
+    bool lv_done = false; // level stream exhausted: the remaining slots are null (rle_decoder.hpp:21-24)
+    for (uint32_t ts = 0; ts < n; ts += 1024u) {
+        const uint32_t t = min(1024u, n - ts);
+        // ---- validity image of the sub-tile
+        vwords[l] = 0;
+        __syncwarp();
+        for (uint32_t produced = 0; produced < t && !lv_done;) {
+            if (lv.rem == 0) {
+                if (lv.pos >= lv.len) { lv_done = true; break; }
+                if (!run_next(lv, 1u)) return false;
+            }
+            const uint32_t take = min(lv.rem, t - produced);
+            if (lv.lit || (lv.val & 0xffu) >= 1u) { // (an RLE run of level 0 leaves zeros)
+                const uint32_t w0 = produced >> 5, w1 = (produced + take - 1u) >> 5;
+                for (uint32_t w = w0 + l; w <= w1; w += 32) {
+                    const uint32_t lo = max(w * 32u, produced), hi = min(w * 32u + 32u, produced + take), cnt = hi - lo;
+                    uint32_t bits = cnt >= 32u ? 0xffffffffu : ((1u << cnt) - 1u);
+                    if (lv.lit) bits &= ldbits(lv.s, lv.bit + (lo - produced), cnt);
+                    if (bits) atomicOr(&vwords[w], bits << (lo & 31u));
+                }
+            }
+            if (lv.lit) lv.bit += take;
+            lv.rem -= take;
+            produced += take;
+        }
+        __syncwarp();
+        const uint32_t c = __popc(vwords[l]);
+        const uint32_t incl = warp_incl_scan(c);
+        rankbase[l] = incl - c;
+        const uint32_t nn = __shfl_sync(0xffffffffu, incl, 31);
+        __syncwarp();
+        // ---- the sub-tile's values: dictionary indices by rank, or the PLAIN bounds
+        if (dict_page) {
+            for (uint32_t produced = 0; produced < nn;) {
+                if (ix.rem == 0) {
+                    if (ix.pos >= ix.len) { // exhausted: the remaining indices read as 0
+                        for (uint32_t k = produced + l; k < nn; k += 32) idx16[k] = 0;
+                        break;
+                    }
+                    if (!run_next(ix, bw)) return false;
+                    if (!ix.lit && ix.val > 0xffffu) return false; // (cannot be held in the u16 buffer: out of range anyway, the general kernel nulls it)
+                }
+                const uint32_t take = min(ix.rem, nn - produced);
+                if (ix.lit) {
+                    for (uint32_t k = l; k < take; k += 32) idx16[produced + k] = static_cast<uint16_t>(ldbits(ix.s, ix.bit + k * bw, bw));
+                    ix.bit += take * bw;
+                } else {
+                    for (uint32_t k = l; k < take; k += 32) idx16[produced + k] = static_cast<uint16_t>(ix.val);
+                }
+                ix.rem -= take;
+                produced += take;
+            }
+            __syncwarp();
+        } else if (static_cast<uint64_t>(nn_before + nn) * W > size - vpos) return false;
+        // ---- emission: one slot per lane, 32 per step (the validity word of a step is warp-uniform)
+        T* outp = reinterpret_cast<T*>(P.values) + pd.out_row_base + ts;
+        auto emit = [&](auto tag) {
+            constexpr int MODE = decltype(tag)::value; // -1: PLAIN
+            for (uint32_t j = 0; j < t; j += 32) {
+                const uint32_t wv = vwords[j >> 5];
+                const bool valid = (wv >> l) & 1u;
+                const uint32_t k = rankbase[j >> 5] + __popc(wv & ((1u << l) - 1u));
+                T x = T(0);
+                bool bad = false;
+                if constexpr (MODE < 0) {
+                    if (valid) x = ld_elem<W>(vals + static_cast<size_t>(nn_before + k) * W);
+                } else {
+                    const uint32_t i = valid ? static_cast<uint32_t>(idx16[k]) : 0u;
+                    const bool in_range = i < dict_n;
+                    bad = valid && !in_range; // NULL in the reference (column_reader.cpp:190-194)
+                    const T v = dict_get<T, W, MODE>(dref, in_range ? i : 0u);
+                    x = (valid && in_range) ? v : T(0);
+                }
+                if (j + l < t) st_stream<T>(outp + j + l, x);
+                if constexpr (MODE >= 0) {
+                    const uint32_t b = __ballot_sync(0xffffffffu, bad);
+                    if (b && l == 0) vwords[j >> 5] = wv & ~b;
+                }
+            }
+        };
+        if (mode < 0) emit(ModeTag<-1>{});
+        else with_dict_mode(mode, emit);
+        __syncwarp();
+        { // validity: the image shifted to its position in the column's bitmap, one word per lane
+            const uint64_t a0 = pd.out_row_base + ts;
+            const uint32_t head = static_cast<uint32_t>(a0 & 31u), nwords = (t + 31u) >> 5;
+            uint32_t* vp = P.validity + (a0 >> 5);
+            const uint32_t cur = l < nwords ? vwords[l] : 0u;
+            const uint32_t prev = (l > 0 && l <= nwords) ? vwords[l - 1] : 0u;
+            const uint32_t gw = head ? ((cur << head) | (prev >> (32u - head))) : cur;
+            const uint32_t total = head + t, gwords = (total + 31u) >> 5;
+            if (l < gwords) {
+                const bool full = (l > 0 || head == 0) && (l + 1u) * 32u <= total;
+                if (full) vp[l] = gw; else if (gw) atomicOr(&vp[l], gw);
+            }
+            if (l == 0 && gwords > 32u) {
+                const uint32_t last = vwords[31] >> (32u - head);
+                if (last) atomicOr(&vp[32], last);
+            }
+        }
+        nn_before += nn;
+        __syncwarp();
+    }
+    return true;
+}
+
 // OPTIONAL (max_def == 1) pages: definition levels as the writer emits them -- RLE runs
 // <varint < 128><level byte> only (src/writer/parquet_writer.cpp:103-135) -- are verified and
 // expanded in parallel (one lane per run, warp prefix sum of the run lengths, bit ranges OR-ed
@@ -279,11 +454,12 @@ __device__ __forceinline__ bool fast_page(const DecodeParams& P, uint32_t q, con
 template <int W>
 __device__ __forceinline__ void fast_page_opt(const DecodeParams& P, uint32_t q, const pqg_page_desc& pd, const uint8_t* pg,
                                               bool chunk_has_dict, const uint8_t* dictp, uint32_t dict_n, bool dict_in_smem,
-                                              uint32_t* vwords, uint32_t* rankbase) {
+                                              uint32_t* vwords, uint32_t* rankbase, uint16_t* idx16) {
     using T = typename FElem<W>::T;
     const uint32_t l = lane_id();
     const uint32_t n = pd.num_values, size = pd.payload_size;
     if (n == 0) return;
+    PQG_ASSERT(pd.out_row_base + n <= P.n_slots);
     if (size < 4u) { if (l == 0) to_slow(P, q); return; }
     const uint32_t def_len = ld32u(pg);
     if (def_len > size - 4u) { if (l == 0) to_slow(P, q); return; }
@@ -307,7 +483,14 @@ __device__ __forceinline__ void fast_page_opt(const DecodeParams& P, uint32_t q,
             return;
         }
     }
-    if (n > 1024u || (def_len & 1u)) { if (l == 0) to_slow(P, q); return; }
+    // anything that is not the writer's shape: the run-by-run decode (plans with the index buffer), else the general kernel
+    auto general = [&]() {
+        const bool dp = (pd.flags & PQG_PAGE_FLAG_DICT) && chunk_has_dict;
+        // (pages beyond 4 KB: one or two of them fill a 16 KB tile, i.e. one or two busy warps per CTA -- the general kernel, a
+        //  warp per page over all resident warps, is the better shape: measured 0.13 vs 0.26 ms per 4884 8-KB pyarrow pages)
+        if (!(idx16 && size <= 4096u && n <= kOptMaxSlots && opt_page_runs<W>(P, pd, pg, dp, dictp, dict_n, dict_in_smem, vwords, rankbase, idx16)) && l == 0) to_slow(P, q);
+    };
+    if (n > 1024u || (def_len & 1u)) { general(); return; }
     const uint8_t* s = pg + 4;
     const uint32_t nr = def_len >> 1;
     // Validity image without shared-memory atomics: every run boundary where the level flips
@@ -349,7 +532,7 @@ __device__ __forceinline__ void fast_page_opt(const DecodeParams& P, uint32_t q,
         t &= lo >= n ? 0u : (n - lo >= 32u ? 0xffffffffu : ((1u << (n - lo)) - 1u));
         vwords[l] = t;
     }
-    if (!__all_sync(0xffffffffu, ok)) { if (l == 0) to_slow(P, q); return; }
+    if (!__all_sync(0xffffffffu, ok)) { general(); return; }
     __syncwarp();
     const uint32_t c = __popc(vwords[l]);
     const uint32_t incl = warp_incl_scan(c);
@@ -365,7 +548,7 @@ __device__ __forceinline__ void fast_page_opt(const DecodeParams& P, uint32_t q,
         if (pos >= size) { if (l == 0) to_slow(P, q); return; }
         bw = pg[pos];
         vals = pg + pos + 1;
-        if (bw > 32u || !check_regular2(vals, size - pos - 1u, bw, nn, &rs)) { if (l == 0) to_slow(P, q); return; }
+        if (bw > 32u || !check_regular2(vals, size - pos - 1u, bw, nn, &rs)) { general(); return; }
     } else if (static_cast<uint64_t>(nn) * W > size - pos) { if (l == 0) to_slow(P, q); return; }
     // emission: 64 page-relative slots per step, two adjacent slots per lane (one 16-byte store
     // for 8-byte values); the validity image is written to global memory afterwards in one step.
@@ -444,7 +627,9 @@ template <int W, int TB, bool OPT>
 __global__ void __launch_bounds__(kThreadsPerCta, OPT ? 3 : 4) k_fixed_tiles(const DecodeParams P) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint32_t* vwords = reinterpret_cast<uint32_t*>(smem + tile_pipe_bytes(TB)) + warp_id() * 64; // per warp: 32 validity words + 32 rank bases
-    uint8_t* sdict = smem + tile_pipe_bytes(TB) + kLevelScratchBytes;
+    // plans with foreign-looking OPTIONAL pages: + 1024 u16 dictionary indices per warp (opt_page_runs)
+    uint16_t* idx16 = (OPT && P.opt_idx) ? reinterpret_cast<uint16_t*>(smem + tile_pipe_bytes(TB) + kLevelScratchBytes) + warp_id() * 1024 : nullptr;
+    uint8_t* sdict = smem + tile_pipe_bytes(TB) + kLevelScratchBytes + ((OPT && P.opt_idx) ? kOptIdxBytes : 0);
     uint32_t dict_n = 0;
     const uint8_t* dictp = nullptr;
     bool has_dict = false, dict_in_smem = false;
@@ -469,7 +654,7 @@ __global__ void __launch_bounds__(kThreadsPerCta, OPT ? 3 : 4) k_fixed_tiles(con
         },
         [&](uint32_t q, const pqg_page_desc& pd, const uint8_t* pg) {
             if constexpr (OPT) {
-                if (max_def > 0) { fast_page_opt<W>(P, q, pd, pg, has_dict, dictp, dict_n, dict_in_smem, vwords, vwords + 32); return; }
+                if (max_def > 0) { fast_page_opt<W>(P, q, pd, pg, has_dict, dictp, dict_n, dict_in_smem, vwords, vwords + 32, idx16); return; }
             }
             fast_page<W>(P, q, pd, pg, has_dict, dictp, dict_n, dict_in_smem);
         });
@@ -524,7 +709,7 @@ bool chunk_is_tileable(int phys_type, int max_def, int max_rep) {
 
 template <int W, int TB, bool OPT>
 static cudaError_t launch_tiles_t(DecodeParams p, int sm_count, cudaStream_t s) {
-    const size_t smem = static_cast<size_t>(tile_pipe_bytes(TB)) + kLevelScratchBytes + p.dict_smem;
+    const size_t smem = static_cast<size_t>(tile_pipe_bytes(TB)) + kLevelScratchBytes + ((OPT && p.opt_idx) ? kOptIdxBytes : 0) + p.dict_smem;
     // (attributes are per device: set on every launch, it is cheap)
     cudaError_t e = cudaFuncSetAttribute(k_fixed_tiles<W, TB, OPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;

@@ -8,7 +8,7 @@ import sys
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import bench
+import bench_scans as bench
 import pqb200 as pq
 
 rows = int(sys.argv[1]) if len(sys.argv) > 1 else 20_000_000
