@@ -370,7 +370,7 @@ def main():
     # measured slower) against the default L2 gather, on the columns it applies to
     col_l2 = {}
     for i, (spec, p) in enumerate(zip(cfg2_specs(), col_plans)):
-        if spec[0].endswith("_d16"):
+        if spec[0].endswith("_d16") and os.environ.get("PQG_BENCH_NO_AB", "0") != "1":  # (profiling runs skip the A/B: fewer launches to step over)
             p.set_option(pq.PQG_OPT_PARTITIONED_DICT, 1)
             for _ in range(4):
                 p.run()

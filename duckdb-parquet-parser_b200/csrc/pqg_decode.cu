@@ -1284,6 +1284,90 @@ __device__ __forceinline__ void decode_str_page(const DecodeParams& P, uint32_t 
     }
 }
 
+// ---- copy pass, the dominant page shape of PLAIN string columns, without the generic page context -----------------
+// REQUIRED PLAIN page staged in shared memory whose values all have ONE length <= kStageMaxLen (header arithmetic: the
+// section is n x (4 + len) bytes; every prefix is checked, so the positions are exact).  No levels, no validity, no
+// candidate search, no position table: string k sits at k * stride + 4, its chars go to k * len, its offset is base +
+// k * len.  Same word-wise staging and vector flush as copy_ranked_plain_tile.  Returns false when the page is not of
+// that shape (the caller takes the general path).
+__device__ __forceinline__ bool lean_plain_page(const DecodeParams& P, uint32_t q, const pqg_page_desc& pd, const DevChunk& ck, WarpScratch& ws,
+                                                const uint8_t* buf, bool& stage_dirty) {
+    const uint32_t l = lane_id();
+    const uint32_t n = pd.num_values, size = pd.payload_size;
+    if (n == 0 || n > 1024u || size > static_cast<uint32_t>(kSlotBytes)) return false;
+    const uint32_t stride = size / n;
+    if (stride < 4u || stride * n != size || stride - 4u > static_cast<uint32_t>(kStageMaxLen)) return false;
+    const uint32_t ulen = stride - 4u;
+    const uint32_t vs = static_cast<uint32_t>(__cvta_generic_to_shared(buf)) + static_cast<uint32_t>(pd.payload_off & 15u);
+    const SmemWords ldw{vs & ~3u};
+    bool same = true;
+    for (uint32_t k = l; k < n; k += 32) {
+        const uint32_t a = (vs & 3u) + k * stride;
+        same = same && __funnelshift_r(ldw(a >> 2), ldw((a >> 2) + 1u), (a & 3u) * 8u) == ulen;
+    }
+    if (!__all_sync(0xffffffffu, same)) return false;
+    const uint32_t page_base = P.page_char_base[q];
+    uint32_t* offs = P.offsets + ck.out_row_base + (&ck - P.chunks) + (pd.out_row_base - ck.out_row_base);
+    for (uint32_t k = l; k < n; k += 32) offs[k] = page_base + k * ulen;
+    const uint32_t total = n * ulen;
+    if (ulen) {
+        uint8_t* dst = P.chars + ck.char_base + page_base;
+        const uint32_t stw = static_cast<uint32_t>(__cvta_generic_to_shared(ws.stage));
+        if (stage_dirty) {
+            for (uint32_t i = l; i < static_cast<uint32_t>(kStageBytes32) / 16u; i += 32) reinterpret_cast<uint4*>(ws.stage)[i] = make_uint4(0, 0, 0, 0);
+            stage_dirty = false;
+        }
+        __syncwarp();
+        const uint32_t mis0 = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(dst) & 15u);
+        uint8_t* const abase = dst - mis0;
+        uint32_t outp = 0, sbase = 0;
+        for (uint32_t g = 0; g < n; g += 32) {
+            const uint32_t k = g + l, cnt = min(32u, n - g);
+            if (k < n) {
+                const uint32_t o = mis0 + k * ulen - sbase, sp = vs + k * stride + 4u;
+                if (ulen <= 16u) stage_or_words<5>(stw, o, sp, ulen);
+                else if (ulen <= 32u) stage_or_words<9>(stw, o, sp, ulen);
+                else stage_or_words<13>(stw, o, sp, ulen);
+            }
+            __syncwarp();
+            outp += cnt * ulen;
+            const uint32_t end = mis0 + outp;
+            const uint32_t nfull = (end >> 4) - (sbase >> 4);
+            if (nfull) {
+                if (sbase == 0 && mis0) { // first vector: the bytes in front belong to another page
+                    if (l >= mis0 && l < 16u) abase[l] = ws.stage[l];
+                    __syncwarp();
+                }
+                for (uint32_t j = l; j < nfull; j += 32) {
+                    const uint4 v = *reinterpret_cast<const uint4*>(ws.stage + 16u * j);
+                    *reinterpret_cast<uint4*>(ws.stage + 16u * j) = make_uint4(0, 0, 0, 0);
+                    if (sbase + j || !mis0) *reinterpret_cast<uint4*>(abase + sbase + 16u * j) = v;
+                }
+                __syncwarp();
+                if (l == 0) { // the partial vector moves to the front
+                    const uint4 v = *reinterpret_cast<const uint4*>(ws.stage + 16u * nfull);
+                    *reinterpret_cast<uint4*>(ws.stage + 16u * nfull) = make_uint4(0, 0, 0, 0);
+                    *reinterpret_cast<uint4*>(ws.stage) = v;
+                }
+                sbase += 16u * nfull;
+                __syncwarp();
+            }
+        }
+        const uint32_t end = mis0 + outp;
+        const uint32_t from = sbase == 0 ? mis0 : sbase;
+        if (from + l < end) abase[from + l] = ws.stage[from - sbase + l]; // < 16 bytes
+        __syncwarp();
+        if (l == 0) *reinterpret_cast<uint4*>(ws.stage) = make_uint4(0, 0, 0, 0);
+        __syncwarp();
+    }
+    // the page's bytes against what the size pass / the page headers said; the last page closes the offsets array
+    if (l == 0) {
+        if (!P.exact_sizes && total != P.page_chars[q]) report_error(P.err, q, PQG_PAGE_LAYOUT);
+        if (q + 1 == ck.first_page + ck.n_pages) offs[n] = page_base + total;
+    }
+    return true;
+}
+
 // Persistent CTAs; every warp takes the next batch of pages_per_cta consecutive pages from a device
 // counter (the size pass counts in DevErr::slow_count, the copy pass in DevErr::slow_cursor; both
 // are zeroed at the start of a run): all resident warps stay busy until the pages run out, whatever
@@ -1335,7 +1419,10 @@ __global__ void __launch_bounds__(kThreadsPerCta, COPY ? 2 : 3) k_str_pages(Deco
                     page_stage_wait<1>();
                 } else page_stage_wait<0>();
                 const DevChunk& ck = P.chunks[pd.chunk_idx];
-                decode_str_page<COPY, LEAN>(P, q, pd, ck, ws, cur ? alt : ws.slot, stage_dirty);
+                const uint8_t* buf = cur ? alt : ws.slot;
+                const bool plain_req = !((pd.flags & PQG_PAGE_FLAG_DICT) && ck.has_dict) && ck.max_def <= 0 && ck.max_rep <= 0 && !P.validity;
+                if (!(plain_req && lean_plain_page(P, q, pd, ck, ws, buf, stage_dirty)))
+                    decode_str_page<COPY, LEAN>(P, q, pd, ck, ws, buf, stage_dirty);
                 __syncwarp();
                 pd = pn;
                 cur ^= 1u;
