@@ -63,6 +63,7 @@ struct pqg_plan {
     bool any_dict = false, any_def = false, is_str = false, is_bool = false;
     bool forced_validity = false; // a REQUIRED chunk held an out-of-range dictionary index (null in the reference): validity added, plan re-run
     bool run_pending = false;     // pqg_plan_run / run_pipelined enqueued, pqg_plan_finish not called yet
+    bool regex_tile_sync = true;  // regex scan: CTA barrier per tile (pqg_plan_set_option)
     bool opt_idx = false;         // OPTIONAL fixed-width plan with foreign-looking pages (see DecodeParams::opt_idx)
     bool no_part = true;          // partitioned-dictionary mode: measured slower than the L2 gather (0.60 vs 0.49 ms per 100 M values): opt-in (pqg_plan_set_option)
     int phys = 0, width = 0;
@@ -579,6 +580,7 @@ static int plan_create_impl(pqg_ctx* ctx, const pqg_buf* image, const pqg_chunk_
 int pqg_plan_set_option(pqg_plan* plan, int option, int value) {
     if (!plan) return PQG_ERR_ARG;
     if (option == PQG_OPT_PARTITIONED_DICT) { plan->no_part = value == 0; return PQG_OK; }
+    if (option == PQG_OPT_REGEX_TILE_BARRIER) { plan->regex_tile_sync = value != 0; return PQG_OK; }
     return PQG_ERR_ARG;
 }
 
@@ -1033,6 +1035,7 @@ int ctx_fail(pqg_ctx* c, int code, const std::string& m) { return fail(c, code, 
 bool plan_is_str(const pqg_plan* p) { return p->is_str; }
 bool plan_ran(const pqg_plan* p) { return p->ran; }
 bool plan_run_pending(const pqg_plan* p) { return p->run_pending; }
+bool plan_regex_tile_sync(const pqg_plan* p) { return p->regex_tile_sync; }
 bool plan_any_dict(const pqg_plan* p) { return p->any_dict; }
 size_t plan_dict_arena_bytes(const pqg_plan* p) { return p->dict_bytes; }
 uint32_t plan_str_dict_blocks(const pqg_plan* p) { return p->str_dict_blocks; }

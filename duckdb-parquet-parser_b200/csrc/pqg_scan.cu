@@ -41,6 +41,7 @@ int ctx_fail(pqg_ctx* c, int code, const std::string& m);
 bool plan_is_str(const pqg_plan* p);
 bool plan_ran(const pqg_plan* p);
 bool plan_run_pending(const pqg_plan* p);
+bool plan_regex_tile_sync(const pqg_plan* p);
 bool plan_any_dict(const pqg_plan* p);
 uint64_t plan_slots(const pqg_plan* p);
 const std::vector<pqg_chunk_desc>& plan_chunks(const pqg_plan* p);
@@ -334,8 +335,9 @@ __global__ void __launch_bounds__(kThreadsPerCta, 4) k_regex_tiles(RegexParams R
                     // k * stride -- verified exactly (every prefix must read len; by induction those ARE the prefixes of
                     // the chain), and no candidate search is needed.
                     const uint32_t vsec = size - pos;
-                    const uint32_t stride = nn ? vsec / nn : 0u;
-                    bool uniform = nn > 0 && stride >= 4u && stride * nn == vsec && vsec <= 65535u && nn <= R.cand_cap;
+                    // (no division: the first prefix names the only possible common length)
+                    const uint32_t stride = (nn && vsec >= 4u) ? __funnelshift_r(ld(o >> 2), ld((o >> 2) + 1u), (o & 3u) * 8u) + 4u : 0u;
+                    bool uniform = nn > 0 && stride >= 4u && stride <= 65535u && stride * nn == vsec && vsec <= 65535u && nn <= R.cand_cap;
                     if (uniform) {
                         const uint32_t ulen = stride - 4u;
                         bool same = true;
@@ -879,7 +881,7 @@ int pqg_regex_scan(pqg_ctx* ctx, pqg_plan* plan, const pqg_dfa* dfa, int neg, ui
     R.P = P;
     // ~660 warp instructions per page: the scan is issue bound, and warps spinning on the next
     // stage's mbarrier cost more than idling at a barrier (measured 0.618 vs 0.650 ms per 20 M strings)
-    R.P.tile_sync = 1;
+    R.P.tile_sync = plan_regex_tile_sync(plan) ? 1u : 0u;
     R.D.trans = reinterpret_cast<const uint16_t*>(d_blob);
     R.D.cls = d_blob + table_bytes;
     R.D.accept = d_blob + table_bytes + 256;

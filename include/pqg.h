@@ -181,7 +181,8 @@ PQG_API void pqg_plan_destroy(pqg_ctx* ctx, pqg_plan* plan);
  * sibling 1024-thread CTAs that read the same page tiles and emit only the values of their part, instead of being gathered
  * from L2.  Measured on B200 (bench.py, cfg2 i64_d16 / f64_d16, 100 M values): 0.60 ms against 0.49 ms for the L2 gather
  * (256-thread CTAs: 1.21 ms), so it stays off; kept for A/B runs. */
-enum { PQG_OPT_PARTITIONED_DICT = 1 };
+enum { PQG_OPT_PARTITIONED_DICT = 1,
+       PQG_OPT_REGEX_TILE_BARRIER = 2 /* regex scan: CTA-wide barrier per page tile (default 1) instead of the last-warp refill */ };
 PQG_API int pqg_plan_set_option(pqg_plan* plan, int option, int value);
 /* re-point a plan at another resident image with the same layout (pipelined ingest) */
 PQG_API int pqg_plan_set_image(pqg_ctx* ctx, pqg_plan* plan, const pqg_buf* image);

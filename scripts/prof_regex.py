@@ -31,4 +31,15 @@ for neg in (0, 1):
         assert L.pqg_regex_scan(ctx.h, plan.h, dfa, neg, bits.ctypes.data, ctypes.byref(ms)) == 0, ctx.err()
     L.pqg_dfa_free(dfa)
     out["neg" if neg else "pos"] = {"ms": ms.value, "Gpages_per_s": t[3] / ms.value / 1e6, "payload_GBps": plan.bytes_in / ms.value / 1e6}
+for ts in (0, 1):  # A/B: tile barrier off / on
+    plan.set_option(2, ts)
+    dfa = pq.regex_compile(bs.EMAIL_PATTERN)
+    bits = np.zeros((t[3] + 31) // 32 + 1, dtype=np.uint32)
+    ms = ctypes.c_float(0)
+    best = 1e9
+    for _ in range(6):
+        assert L.pqg_regex_scan(ctx.h, plan.h, dfa, 0, bits.ctypes.data, ctypes.byref(ms)) == 0, ctx.err()
+        best = min(best, ms.value)
+    L.pqg_dfa_free(dfa)
+    out["tile_barrier_%d_ms" % ts] = best
 print(json.dumps({"rows": rows, "pages": t[3], "pattern": bs.EMAIL_PATTERN, **out}))
