@@ -4,7 +4,7 @@
     python bench.py --gpus N --steps K --warmup W          # this repo's CUDA path
     python bench.py --impl reference --steps K --warmup W  # the reference's CPU ColumnReader
 
-Workload (BASELINE.json configs[1], SURVEY.md section 8 d "Config 2"): a 100 M-row file as
+Headline workload (BASELINE.json configs[1], SURVEY.md section 8 d "Config 2"): a 100 M-row file as
 10 row groups x 10 M rows with 7 columns -- INT64 PLAIN, DOUBLE PLAIN, INT64 dictionary with
 2^8 / 2^12 / 2^16 / 2^20 distinct keys (index bit widths 8 / 12 / 16 / 20) and DOUBLE
 dictionary with 2^16 keys -- produced by the workload generator, which is byte-identical to the
@@ -12,16 +12,25 @@ reference's ParquetWriter (tests/test_gen_cpu.py).  One step = one decode of all
 through ONE plan (pqr_columns_tables; PQG_BENCH_PER_COLUMN=1 runs one plan per column instead).
 
   value      Sigma page payload bytes (data + dictionary pages) / device time, image resident in
-             HBM, K steps timed with CUDA events on the decoder's stream, max over ranks.
+             HBM, K steps timed with CUDA events on the decoder's stream, max over ranks.  Before the
+             timed steps the plan's device output is compared with the generator's input columns on
+             the device, all rows of every column (roofline.parity).
   e2e        same metric through the reference-facing reader API (pqr_* C-ABI) with HOST buffers:
              every step uploads the column chunks from pinned host memory and reads the
-             decoded columns back to the host.
+             decoded columns back to the host.  e2e.platform_ceiling: the same bytes as bare copies
+             (what the box allows); e2e.cold: a fresh reader + its first read.
   roofline   dominant kernel (k_fixed_tiles): (bytes_in + bytes_out) of its launches / their
              CUDA-event durations inside the timed steps, against MEASURED_PEAKS.json hbm_gbs.
   cpu_baseline / --impl reference
              the UNMODIFIED reference (oracle/_ref/libpqref.so, compiled from /root/reference
              sources) reading a bounded sample (the first row groups of the same data, written
              as its own file) with one ParquetReader per host thread.
+  strings / regex / chunk_index  (bench_scans.py; --no-scans skips them)
+             BASELINE.json configs[2..4] next to the headline, at every N, each with its own roofline,
+             cpu_baseline (N = 1) and parity statement: the cfg3 dictionary-string shape (100 M rows per
+             GPU), the regex page-pruning scan over ONE ~10 GB file whose row groups are split over the
+             ranks (bitmaps gathered on the host), and the 4 KB chunk index over a mixed PLAIN /
+             dictionary column of 6.4 GB per GPU with the carry chain across the ranks.
 
 N > 1 (torchrun): every rank decodes its own 100 M-row shard (row groups are independent; no
 data-path collective), "scaling": "weak"; value = total bytes / max-over-ranks time.

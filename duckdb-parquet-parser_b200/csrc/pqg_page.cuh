@@ -199,21 +199,32 @@ __device__ __forceinline__ uint32_t levels_tile(Walker& w, WarpScratch& ws, uint
             // no bit ranges, no loops over words: every run whose level class (present / null) differs from its
             // predecessor's sets ONE toggle bit at its first slot; the validity image is the prefix XOR of the toggles.
             // The layout is verified on the way (a header byte that is not <even, 2..126> voids the image: general walk).
+            // two runs per lane and step (64 runs per warp prefix sum)
             uint32_t carry = 0, last_present = 0;
-            for (uint32_t base = 0; base < nr && carry < t; base += 32) {
-                const uint32_t r = base + l;
-                uint32_t cnt = 0, pres = 0;
-                if (r < nr) {
-                    const uint32_t b = s[2 * r];
+            for (uint32_t base = 0; base < nr && carry < t; base += 64) {
+                const uint32_t r0 = base + 2u * l, r1 = r0 + 1u;
+                uint32_t cnt0 = 0, cnt1 = 0, pres0 = 0, pres1 = 0;
+                if (r0 < nr) {
+                    const uint32_t b = s[2 * r0];
                     ok = ok && ((b & 0x81u) == 0u) && b != 0u;
-                    cnt = b >> 1; pres = level_present(s[2 * r + 1], max_def) ? 1u : 0u;
+                    cnt0 = b >> 1; pres0 = level_present(s[2 * r0 + 1], max_def) ? 1u : 0u;
                 }
-                const uint32_t incl = warp_incl_scan(cnt);
-                const uint32_t start = carry + incl - cnt;
-                uint32_t prev = __shfl_up_sync(0xffffffffu, pres, 1);
+                if (r1 < nr) {
+                    const uint32_t b = s[2 * r1];
+                    ok = ok && ((b & 0x81u) == 0u) && b != 0u;
+                    cnt1 = b >> 1; pres1 = level_present(s[2 * r1 + 1], max_def) ? 1u : 0u;
+                }
+                const uint32_t both = cnt0 + cnt1;
+                const uint32_t incl = warp_incl_scan(both);
+                const uint32_t start0 = carry + incl - both, start1 = start0 + cnt0;
+                // class of the run in front of this lane's first run: the second run of the lane below (its last one in range)
+                uint32_t prev = __shfl_up_sync(0xffffffffu, pres1, 1);
                 if (l == 0) prev = last_present;
-                if (r < nr && start < t && pres != prev) atomicXor(&ws.valid[start >> 5], 1u << (start & 31u));
-                last_present = __shfl_sync(0xffffffffu, pres, min(31u, nr - 1u - base));
+                if (r0 < nr && start0 < t && pres0 != prev) atomicXor(&ws.valid[start0 >> 5], 1u << (start0 & 31u));
+                if (r1 < nr && start1 < t && pres1 != pres0) atomicXor(&ws.valid[start1 >> 5], 1u << (start1 & 31u));
+                const uint32_t last_run = min(63u, nr - 1u - base);            // last run of this step, 0..63
+                const uint32_t lp0 = __shfl_sync(0xffffffffu, pres0, last_run >> 1), lp1 = __shfl_sync(0xffffffffu, pres1, last_run >> 1);
+                last_present = (last_run & 1u) ? lp1 : lp0;
                 carry += __shfl_sync(0xffffffffu, incl, 31);
             }
             __syncwarp();

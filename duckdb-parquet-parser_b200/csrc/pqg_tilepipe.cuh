@@ -44,8 +44,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 
 // TB = image bytes per tile (kTileBytes, or kTileBytesLarge for plans whose pages are fat)
 __host__ __device__ constexpr int tile_stage_bytes(int TB) { return TB + 16 + kTilePages * static_cast<int>(sizeof(pqg_page_desc)); }
-constexpr int kBarBytes = (64 + kTileStages * 64 + 127) & ~127; // kTileStages + 1 mbarriers, stage counters, per-stage tile meta, prefetched descriptors
-__host__ __device__ constexpr int tile_pipe_bytes(int TB) { return kBarBytes + kTileStages * tile_stage_bytes(TB); } // shared memory of the pipeline itself
+// ST + 1 mbarriers (<= 32 bytes), stage counters (<= 32 bytes), per-stage tile meta (32 B) and prefetched descriptors (32 B)
+__host__ __device__ constexpr int tile_bar_bytes(int ST = kTileStages) { return (64 + ST * 64 + 127) & ~127; }
+constexpr int kBarBytes = tile_bar_bytes();
+__host__ __device__ constexpr int tile_pipe_bytes(int TB, int ST = kTileStages) { return tile_bar_bytes(ST) + ST * tile_stage_bytes(TB); } // shared memory of the pipeline itself
 constexpr int kTilePipeBytes = tile_pipe_bytes(kTileBytes);
 
 struct TileMeta { uint64_t byte_lo; uint32_t first_page; uint32_t n_pages; uint32_t chunk_idx; uint32_t pad; };
@@ -62,8 +64,11 @@ __device__ __forceinline__ void pipe_sync(uint32_t bar_id) {
     else asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(kThreadsPerCta) : "memory");
 }
 
-template <int TB = kTileBytes, class OnChunk, class OnPage>
+template <int TB = kTileBytes, int ST = kTileStages, class OnChunk, class OnPage>
 __device__ __forceinline__ void tile_pipeline(const DecodeParams& P, uint8_t* smem, OnChunk&& on_chunk, OnPage&& on_page, const PipeGroup* grp = nullptr) {
+    static_assert(ST >= 2 && ST <= 3, "barrier block layout: 4 mbarriers and 4 counters at most");
+    constexpr int kTileStages = ST; // (shadows the global default inside the pipeline)
+    constexpr int kBarBytes = tile_bar_bytes(ST);
     constexpr int kStageBytes = tile_stage_bytes(TB);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);          // [kTileStages] tiles, then one for per-chunk staging
     uint32_t* done = reinterpret_cast<uint32_t*>(smem + 32);     // [kTileStages] warps finished with the stage

@@ -626,15 +626,17 @@ __device__ __forceinline__ void fast_page_opt(const DecodeParams& P, uint32_t q,
 template <int W, int TB, bool OPT>
 __global__ void __launch_bounds__(kThreadsPerCta, OPT ? 3 : 4) k_fixed_tiles(const DecodeParams P) {
     extern __shared__ __align__(128) uint8_t smem[];
-    uint32_t* vwords = reinterpret_cast<uint32_t*>(smem + tile_pipe_bytes(TB)) + warp_id() * 64; // per warp: 32 validity words + 32 rank bases
+    // (a third stage for OPTIONAL plans changed nothing: 0.285 vs 0.282 ms per 40 M slots, profiles/README.md)
+    constexpr int ST = kTileStages;
+    uint32_t* vwords = reinterpret_cast<uint32_t*>(smem + tile_pipe_bytes(TB, ST)) + warp_id() * 64; // per warp: 32 validity words + 32 rank bases
     // plans with foreign-looking OPTIONAL pages: + 1024 u16 dictionary indices per warp (opt_page_runs)
-    uint16_t* idx16 = (OPT && P.opt_idx) ? reinterpret_cast<uint16_t*>(smem + tile_pipe_bytes(TB) + kLevelScratchBytes) + warp_id() * 1024 : nullptr;
-    uint8_t* sdict = smem + tile_pipe_bytes(TB) + kLevelScratchBytes + ((OPT && P.opt_idx) ? kOptIdxBytes : 0);
+    uint16_t* idx16 = (OPT && P.opt_idx) ? reinterpret_cast<uint16_t*>(smem + tile_pipe_bytes(TB, ST) + kLevelScratchBytes) + warp_id() * 1024 : nullptr;
+    uint8_t* sdict = smem + tile_pipe_bytes(TB, ST) + kLevelScratchBytes + ((OPT && P.opt_idx) ? kOptIdxBytes : 0);
     uint32_t dict_n = 0;
     const uint8_t* dictp = nullptr;
     bool has_dict = false, dict_in_smem = false;
     int max_def = 0;
-    tile_pipeline<TB>(P, smem,
+    tile_pipeline<TB, ST>(P, smem,
         [&](uint32_t chunk, uint64_t* bar, uint32_t& phase) {
             const DevChunk& ck = P.chunks[chunk];
             has_dict = ck.has_dict;
@@ -709,7 +711,7 @@ bool chunk_is_tileable(int phys_type, int max_def, int max_rep) {
 
 template <int W, int TB, bool OPT>
 static cudaError_t launch_tiles_t(DecodeParams p, int sm_count, cudaStream_t s) {
-    const size_t smem = static_cast<size_t>(tile_pipe_bytes(TB)) + kLevelScratchBytes + ((OPT && p.opt_idx) ? kOptIdxBytes : 0) + p.dict_smem;
+    const size_t smem = static_cast<size_t>(tile_pipe_bytes(TB, kTileStages)) + kLevelScratchBytes + ((OPT && p.opt_idx) ? kOptIdxBytes : 0) + p.dict_smem;
     // (attributes are per device: set on every launch, it is cheap)
     cudaError_t e = cudaFuncSetAttribute(k_fixed_tiles<W, TB, OPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
