@@ -416,7 +416,18 @@ static int plan_create_impl(pqg_ctx* ctx, const pqg_buf* image, const pqg_chunk_
     std::vector<uint32_t> slow;
     {
         // OPTIONAL fixed-width pages carry ~0.9 level bytes per slot: larger tiles keep 8 pages (= 8 warps) per tile
-        p->tile_bytes = (!p->is_str && p->any_def) ? kTileBytesLarge : kTileBytes;
+        // (strings: the tiles feed the regex scan, one page per warp -- pages whose stride in the file is past 1 KB
+        // would fill an 8 KB tile with seven or fewer, so their plans get the 10 KB or 16 KB tiles)
+        uint64_t str_span = 0, str_pages = 0;
+        if (p->is_str) for (uint32_t c = 0; c < n_chunks; c++) {
+            const pqg_chunk_desc& s = chunks[c];
+            if (s.n_pages == 0) continue;
+            const pqg_page_desc& a = pages[s.first_page]; const pqg_page_desc& b = pages[s.first_page + s.n_pages - 1];
+            if (b.payload_off + b.payload_size > a.payload_off) { str_span += b.payload_off + b.payload_size - a.payload_off; str_pages += s.n_pages; }
+        }
+        const uint64_t str_need = str_pages ? str_span * kTilePages / str_pages + 64 : 0; // eight average pages
+        p->tile_bytes = p->is_str ? (str_need <= kTileBytes ? kTileBytes : str_need <= kTileBytesMid ? kTileBytesMid : kTileBytesLarge)
+                                  : (p->any_def ? kTileBytesLarge : kTileBytes);
         const uint64_t tile_cap = p->tile_bytes;
         uint32_t max_dict_n = 0;
         for (uint32_t c = 0; c < n_chunks; c++) {

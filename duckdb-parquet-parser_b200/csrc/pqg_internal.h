@@ -36,6 +36,7 @@ constexpr int kImagePad = 64;             // readable bytes required past the im
 // TMA-staged tile pipeline of the fast fixed-width kernel (pqg_tiles.cu)
 constexpr int kTileBytes = 8192;          // image bytes per tile (16-byte aligned range covering whole pages)
 constexpr int kTileBytesLarge = 16384;     // tiles of OPTIONAL fixed-width plans (level bytes make their pages ~1.8 KB: 8 pages per tile)
+constexpr int kTileBytesMid = 10240;       // string plans whose pages run just past 1 KB (eight of them per tile for the regex scan)
 constexpr int kTilePages = 8;             // pages per tile (one per warp)
 constexpr int kTileStages = 2;            // ring depth per CTA (measured: 2 x 8 KB beats 3-4 stages and 16 KB tiles: the shared-memory
                                           // carve-out eats L1, which the large-dictionary gathers and the PLAIN copy both feel)

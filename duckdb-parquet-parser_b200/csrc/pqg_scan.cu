@@ -263,10 +263,11 @@ __host__ __device__ inline uint32_t rx_table_pad(uint32_t table_bytes, uint32_t 
     return in_smem ? ((table_bytes + 256u + n_states + 127u) & ~127u) : 0u;
 }
 
-__global__ void __launch_bounds__(kThreadsPerCta, 4) k_regex_tiles(RegexParams R) {
+template <int TB>
+__global__ void __launch_bounds__(kThreadsPerCta, 5) k_regex_tiles(RegexParams R) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* pipe = smem + rx_table_pad(R.D.table_bytes, R.D.n_states, R.D.in_smem != 0);
-    uint16_t* cand = reinterpret_cast<uint16_t*>(pipe + kTilePipeBytes) + warp_id() * R.cand_cap;
+    uint16_t* cand = reinterpret_cast<uint16_t*>(pipe + tile_pipe_bytes(TB)) + warp_id() * R.cand_cap;
     const uint16_t* trans; const uint8_t* cls; const uint8_t* accept;
     stage_tables(R, smem, trans, cls, accept, R.D.scaled != 0);
     const DecodeParams& P = R.P;
@@ -277,7 +278,7 @@ __global__ void __launch_bounds__(kThreadsPerCta, 4) k_regex_tiles(RegexParams R
     bool has_dict = false;
     uint32_t dict_n = 0;
     const uint8_t* dmatch = nullptr;
-    tile_pipeline(P, pipe,
+    tile_pipeline<TB>(P, pipe,
         [&](uint32_t chunk, uint64_t*, uint32_t&) {
             const DevChunk& ck = P.chunks[chunk];
             max_def = ck.max_def; has_dict = ck.has_dict; dict_n = ck.dict_ok_n;
@@ -904,16 +905,19 @@ int pqg_regex_scan(pqg_ctx* ctx, pqg_plan* plan, const pqg_dfa* dfa, int neg, ui
     }
     const size_t tab_pad = R.D.in_smem ? ((tab_smem + 15) & ~size_t(15)) : 0;
     R.cand_cap = plan_max_page_values(plan) <= kRxCand / 2 ? kRxCand / 2 : kRxCand;
-    const size_t smem_fast = static_cast<size_t>(kTilePipeBytes) + kWarpsPerCta * R.cand_cap * 2 + rx_table_pad(table_bytes, d.n_states, R.D.in_smem != 0);
+    // the plan cut its tiles for 8 KB or (pages of ~1 KB and more: eight of them per tile, one per warp) 10 / 16 KB
+    const int tb = static_cast<int>(R.P.tile_bytes);
+    const size_t smem_fast = static_cast<size_t>(tile_pipe_bytes(tb)) + kWarpsPerCta * R.cand_cap * 2 + rx_table_pad(table_bytes, d.n_states, R.D.in_smem != 0);
     const size_t smem_slow = decode_smem_bytes(false) + tab_pad;
-    CUF(ctx, cudaFuncSetAttribute(k_regex_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_fast)));
-    CUF(ctx, cudaFuncSetAttribute(k_regex_tiles, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    auto* fast = tb == kTileBytesLarge ? k_regex_tiles<kTileBytesLarge> : tb == kTileBytesMid ? k_regex_tiles<kTileBytesMid> : k_regex_tiles<kTileBytes>;
+    CUF(ctx, cudaFuncSetAttribute(fast, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_fast)));
+    CUF(ctx, cudaFuncSetAttribute(fast, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CUF(ctx, cudaFuncSetAttribute(k_regex_pages, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_slow)));
     if (R.P.tile_hi > R.P.tile_lo) {
         int resident = 1;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k_regex_tiles, kThreadsPerCta, smem_fast);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, fast, kThreadsPerCta, smem_fast);
         const uint32_t grid = tile_grid(R.P.tile_hi - R.P.tile_lo, ctx_sm_count(ctx), resident, &R.P.tiles_per_cta);
-        k_regex_tiles<<<grid, kThreadsPerCta, smem_fast, s>>>(R);
+        fast<<<grid, kThreadsPerCta, smem_fast, s>>>(R);
         launches++;
     }
     // host-listed (oversized) pages + whatever the tile kernel handed over
