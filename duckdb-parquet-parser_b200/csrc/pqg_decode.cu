@@ -1295,7 +1295,7 @@ __device__ __forceinline__ bool lean_plain_page(const DecodeParams& P, uint32_t 
     const uint32_t n = pd.num_values, size = pd.payload_size;
     if (n == 0 || n > 1024u || size > static_cast<uint32_t>(kSlotBytes)) return false;
     const uint32_t stride = size / n;
-    if (stride < 4u || stride * n != size || stride - 4u > static_cast<uint32_t>(kStageMaxLen)) return false;
+    if (stride < 4u || stride * n != size) return false;
     const uint32_t ulen = stride - 4u;
     const uint32_t vs = static_cast<uint32_t>(__cvta_generic_to_shared(buf)) + static_cast<uint32_t>(pd.payload_off & 15u);
     const SmemWords ldw{vs & ~3u};
@@ -1309,7 +1309,41 @@ __device__ __forceinline__ bool lean_plain_page(const DecodeParams& P, uint32_t 
     uint32_t* offs = P.offsets + ck.out_row_base + (&ck - P.chunks) + (pd.out_row_base - ck.out_row_base);
     for (uint32_t k = l; k < n; k += 32) offs[k] = page_base + k * ulen;
     const uint32_t total = n * ulen;
-    if (ulen) {
+    if (ulen >= 4u) {
+        // Strings of four bytes and more: no staging at all.  Output byte j is source byte j + 4 * (j / ulen + 1), so a
+        // lane builds one aligned 16-byte vector of the chars out of the page in shared memory -- per output word two
+        // unaligned source words (the one at the byte, the one past the next prefix) and one byte permute that takes the
+        // first `left in this string` bytes from the first and the rest from the second.  j / ulen: multiply-high by
+        // ceil(2^32 / ulen), exact below 2^16.
+        uint8_t* dst = P.chars + ck.char_base + page_base;
+        const uint32_t vo = vs & 3u;
+        const uint32_t magic = 0xffffffffu / ulen + 1u;
+        const uint32_t head = min(total, (16u - static_cast<uint32_t>(reinterpret_cast<uintptr_t>(dst) & 15u)) & 15u);
+        const uint32_t nvec = (total - head) >> 4;
+        for (uint32_t v = l; v < nvec; v += 32) {
+            uint32_t j = head + 16u * v;
+            uint32_t k = __umulhi(j, magic), r = j - k * ulen;
+            uint32_t w[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const uint32_t a = vo + j + 4u * k + 4u, sh = (a & 3u) * 8u;
+                const uint32_t x0 = ldw(a >> 2), x1 = ldw((a >> 2) + 1u), x2 = ldw((a >> 2) + 2u);
+                const uint32_t c = min(ulen - r, 4u); // bytes of this word that string k still has
+                w[i] = __byte_perm(__funnelshift_r(x0, x1, sh), __funnelshift_r(x1, x2, sh), 0x3210u + ((0x4444u << (4u * c)) & 0xffffu));
+                j += 4u; r += 4u;
+                if (r >= ulen) { r -= ulen; k++; }
+            }
+            *reinterpret_cast<uint4*>(dst + head + 16u * v) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        // the bytes in front of the first and behind the last aligned vector (< 16 each): lanes 0..15 / 16..31
+        const uint32_t jb = l < 16u ? l : head + 16u * nvec + (l - 16u);
+        if (l < 16u ? l < head : jb < total) {
+            const uint32_t a = vs + jb + 4u * __umulhi(jb, magic) + 4u;
+            uint32_t b;
+            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(b) : "r"(a));
+            dst[jb] = static_cast<uint8_t>(b);
+        }
+    } else if (ulen) {
         uint8_t* dst = P.chars + ck.char_base + page_base;
         const uint32_t stw = static_cast<uint32_t>(__cvta_generic_to_shared(ws.stage));
         if (stage_dirty) {

@@ -297,6 +297,29 @@ def test_plain_string_pages_with_trailing_bytes_fall_back_to_the_size_pass(pq):
         assert offs.tolist() == np.concatenate([[0], np.cumsum([len(s) for s in exp])]).tolist()
 
 
+@pytest.mark.parametrize("ulen", [0, 1, 3, 4, 5, 7, 8, 13, 16, 17, 31, 33, 48, 49, 64, 100, 500])
+def test_plain_string_pages_of_one_length(pq, ulen):
+    """REQUIRED PLAIN pages whose values all have one length take the copy pass without staging (chars assembled straight
+    into aligned vectors): every length class, page sizes from one value to the 2 KB staging limit, so that the pages'
+    char ranges start at every alignment; a page whose LAST prefix differs has the same section size only by accident
+    and must take the general path"""
+    rng = np.random.default_rng(ulen)
+    def page(strs):
+        return b"".join(len(s).to_bytes(4, "little") + s for s in strs)
+    pages, counts, exp = [], [], []
+    cap = max(1, min(40, 2040 // (ulen + 4)))
+    for i in range(60):
+        n = int(rng.integers(1, cap + 1))
+        strs = [bytes(rng.integers(33, 127, ulen, dtype=np.uint8)) for _ in range(n)]
+        if i % 7 == 3 and n >= 2 and ulen >= 1:  # same section size, two lengths
+            strs[-2] = strs[-2] + b"+"
+            strs[-1] = strs[-1][:-1]
+        pages.append(page(strs)); counts.append(n); exp += strs
+    offs, chars = _string_plan(pq, pages, counts)
+    assert chars == b"".join(exp)
+    assert offs.tolist() == np.concatenate([[0], np.cumsum([len(s) for s in exp])]).tolist()
+
+
 def test_required_chunk_out_of_range_indices_become_nulls(pq, oracle):
     """Value::null() for an out-of-range dictionary index whatever max_def is (reference
     src/reader/column_reader.cpp:190-194): a REQUIRED-only plan has no validity bitmap, so
