@@ -46,6 +46,15 @@ struct pqg_plan {
     uint32_t n_tiles = 0;
     uint32_t* d_slow_pages = nullptr; // pages for the general kernel: host-listed, then device-appended
     uint32_t n_slow_host = 0;
+    // flat decode of the slow list (pqg_flat.cu): fixed-width 4/8-byte plans with OPTIONAL chunks or host-listed pages
+    bool flat_on = false;
+    FlatPage* d_flat_pages = nullptr;
+    FlatBlk* d_flat_blk = nullptr;
+    uint2* d_flat_ckpt = nullptr;
+    uint32_t* d_flat_append = nullptr;
+    uint32_t flat_blk_cap = 0;
+    bool flat_ran = false;                   // the current run launched the flat kernels
+    uint32_t tile_handover_seen = 0xffffffffu; // pages the tile kernel handed over in the last finished run (~0u: none finished yet)
     uint32_t dict_smem = 0;
     uint32_t max_dict_blocks = 1;
     uint32_t tile_bytes = kTileBytes;
@@ -279,6 +288,7 @@ void pqg_plan_destroy(pqg_ctx* ctx, pqg_plan* p) {
     cudaFree(p->d_chunks); cudaFree(p->d_pages); cudaFree(p->d_dict); cudaFree(p->d_dict_segs); cudaFree(p->d_values);
     cudaFree(p->d_validity); cudaFree(p->d_required_ranges); cudaFree(p->d_offsets); cudaFree(p->d_chars); cudaFree(p->d_page_chars);
     cudaFree(p->d_page_char_base); cudaFree(p->d_bases); cudaFree(p->d_err); cudaFree(p->d_tiles); cudaFree(p->d_slow_pages);
+    cudaFree(p->d_flat_pages); cudaFree(p->d_flat_blk); cudaFree(p->d_flat_ckpt); cudaFree(p->d_flat_append);
     if (p->h_bases) cudaFreeHost(p->h_bases);
     if (p->h_err) cudaFreeHost(p->h_err);
     for (auto& slot : p->evr) for (auto& e : slot) if (e) cudaEventDestroy(e);
@@ -531,6 +541,22 @@ static int plan_create_impl(pqg_ctx* ctx, const pqg_buf* image, const pqg_chunk_
     // host-listed pages, then room for EVERY page to be handed over on the device (the big-page kernel re-lists host-listed pages)
     PA(p->d_slow_pages, sizeof(uint32_t) * (slow.size() + static_cast<size_t>(n_pages) + p->virt_pages.size() + 2));
     PA(p->d_tiles, sizeof(TileDesc) * std::max<size_t>(tiles.size(), 1));
+    p->flat_on = !p->is_str && !p->is_bool && (p->width == 4 || p->width == 8) && (p->any_def || !slow.empty());
+    if (p->flat_on) {
+        // every page may end up on the work list (the tile kernel hands over on the device): one entry per page, one block per 1024 slots
+        uint64_t blocks = 1;
+        for (uint32_t q = 0; q < n_pages; q++) blocks += (static_cast<uint64_t>(pages[q].num_values) + 1023u) >> 10;
+        for (const pqg_page_desc& v : p->virt_pages) blocks += (static_cast<uint64_t>(v.num_values) + 1023u) >> 10;
+        if (blocks > 0x7fffffffull) p->flat_on = false;
+        else {
+            const size_t cap = static_cast<size_t>(n_pages) + p->virt_pages.size() + 2;
+            p->flat_blk_cap = static_cast<uint32_t>(blocks);
+            PA(p->d_flat_pages, sizeof(FlatPage) * cap);
+            PA(p->d_flat_append, sizeof(uint32_t) * cap);
+            PA(p->d_flat_blk, sizeof(FlatBlk) * blocks);
+            PA(p->d_flat_ckpt, sizeof(uint2) * blocks);
+        }
+    }
     if (p->any_def) PA(p->d_validity, ((slots + 31) / 32 + 1) * 4);
     if (p->any_def && !p->is_str) {
         std::vector<uint64_t> rr;
@@ -620,6 +646,10 @@ static DecodeParams make_params(const pqg_plan* p) {
     P.identity_dict = p->identity ? 1u : 0u;
     P.opt_idx = p->opt_idx ? 1u : 0u;
     P.exact_sizes = p->force_exact ? 1u : 0u;
+    if (p->flat_on) {
+        P.flat = &p->d_err->flat; P.flat_pages = p->d_flat_pages; P.flat_blk = p->d_flat_blk;
+        P.flat_ckpt = p->d_flat_ckpt; P.flat_blk_cap = p->flat_blk_cap; P.flat_append = p->d_flat_append;
+    }
     return P;
 }
 
@@ -646,7 +676,7 @@ static int fixed_subrun(pqg_ctx* ctx, pqg_plan* p, uint32_t c0, uint32_t c1, boo
     DecodeParams P = make_params(p);
     int launches = 0;
     cudaError_t e = cudaSuccess;
-    if (reset_counters) e = cudaMemsetAsync(&p->d_err->slow_count, 0, 8, s);
+    if (reset_counters) e = cudaMemsetAsync(&p->d_err->slow_count, 0, kWorkCounterBytes, s);
     P.chunk_lo = c0;
     P.tile_lo = p->chunk_tile_begin[c0]; P.tile_hi = p->chunk_tile_begin[c1];
     P.slow_lo = p->chunk_slow_begin[c0]; P.slow_hi = p->chunk_slow_begin[c1];
@@ -715,21 +745,22 @@ static int fixed_subrun(pqg_ctx* ctx, pqg_plan* p, uint32_t c0, uint32_t c1, boo
         }
     }
     if (e == cudaSuccess && ev_tiles_end) e = cudaEventRecord(ev_tiles_end, s);
-    // host-listed pages (oversized, or of chunks the tile kernel does not take) of 4/8-byte plans:
-    // one CTA per page first; what that kernel cannot take joins the slow list
-    bool host_list_taken = false;
-    bool big_useful = false; // nested chunks (max_def > 1 / max_rep > 0) are always handed on: skip the launch when nothing else is listed
-    for (uint32_t c = c0; c < c1 && !big_useful; c++)
-        big_useful = p->chunk_slow_begin[c + 1] > p->chunk_slow_begin[c] && p->chunks[c].max_def <= 1 && p->chunks[c].max_rep <= 0;
-    if (e == cudaSuccess && big_useful && !p->is_bool && (p->width == 4 || p->width == 8)) {
-        e = launch_big_pages(P, p->width, ctx->sm_count, s);
-        launches++;
-        host_list_taken = true;
+    // plans with OPTIONAL chunks or host-listed pages (oversized, or of chunks the tile kernel does not take), 4/8-byte values:
+    // the slow list -- host-listed pages and what the tile kernel handed over -- is decoded as a flat list of 1024-slot blocks;
+    // what those kernels cannot take is listed again for the general kernel
+    DecodeParams Pg = P;
+    // (no host-listed pages and the tile kernel handed nothing over in the previous run: the general kernel alone -- it takes
+    //  whatever shows up -- instead of three launches over an empty list)
+    if (e == cudaSuccess && p->flat_on && (P.slow_hi > P.slow_lo || (P.tile_hi > P.tile_lo && p->tile_handover_seen != 0))) {
+        p->flat_ran = true;
+        e = launch_flat_pages(P, p->width, ctx->sm_count, any_dict, s);
+        launches += static_cast<int>(flat_launches());
+        Pg.slow_hi = Pg.slow_lo;
+        Pg.slow_append = P.flat_append;
+        Pg.append_count = &p->d_err->flat.handed;
     }
-    // the general kernel takes what is left of the host list plus whatever the other kernels handed over
+    // the general kernel: every page shape, one warp per page
     if (e == cudaSuccess && (P.slow_hi > P.slow_lo || P.tile_hi > P.tile_lo)) {
-        DecodeParams Pg = P;
-        if (host_list_taken) Pg.slow_hi = Pg.slow_lo;
         e = launch_decode_fixed(Pg, p->width, p->is_bool, ctx->sm_count, s);
         launches++;
     }
@@ -840,7 +871,9 @@ int pqg_plan_finish(pqg_ctx* ctx, pqg_plan* p, pqg_page_error* err) {
     }
     pqg_page_error pe{};
     const DevErr& d = *p->h_err;
-    p->handover_seen = d.slow_count;
+    p->tile_handover_seen = d.slow_count;
+    p->handover_seen = p->flat_ran ? d.flat.handed : d.slow_count; // what the general kernel had to take
+    p->flat_ran = false;
     if (std::getenv("PQG_DEBUG"))
         std::fprintf(stderr, "[pqg] plan: %zu pages, %u tiles, %u host-listed slow pages, %u handed over by the tile kernel (last sub-run), bad_index %u\n",
                      p->pages.size(), p->n_tiles, p->n_slow_host, d.slow_count, d.bad_index);

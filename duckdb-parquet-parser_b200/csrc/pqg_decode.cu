@@ -543,7 +543,7 @@ __global__ void __launch_bounds__(kThreadsPerCta) k_decode_fixed(DecodeParams P)
     extern __shared__ __align__(16) uint8_t smem[];
     WarpScratch& ws = reinterpret_cast<WarpScratch*>(smem)[warp_id()];
     const uint32_t n_host = P.slow_hi - P.slow_lo;
-    const uint32_t total = n_host + P.err->slow_count;
+    const uint32_t total = n_host + (P.append_count ? *P.append_count : P.err->slow_count);
     for (;;) {
         uint32_t i = 0;
         if (lane_id() == 0) i = atomicAdd(&P.err->slow_cursor, 1u);

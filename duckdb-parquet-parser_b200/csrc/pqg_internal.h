@@ -78,6 +78,8 @@ constexpr int kDictCand = 4;
 struct DictSeg { uint32_t start[kDictCand], end[kDictCand]; uint16_t cnt[kDictCand]; uint32_t base, pick; };
 constexpr uint32_t kDictSeg = 128;                  // bytes per segment
 
+struct FlatCtl { uint32_t scan_cursor, rank_cursor, emit_cursor, nblk, handed, pad; }; // (pqg_flat.cu) cursors of the flat kernels, blocks handed out, pages handed on
+
 // First failing page (lowest page-table index) of a run, plus the per-run work counters
 // (one memset resets everything).
 struct DevErr {
@@ -89,6 +91,23 @@ struct DevErr {
     // work counters, reset before every (sub-)run: keep them last and together
     uint32_t slow_count;     // pages the tile kernel handed to the general kernel
     uint32_t slow_cursor;    // work-stealing cursor of the general kernel
+    FlatCtl flat;
+};
+constexpr size_t kWorkCounterBytes = 8 + sizeof(FlatCtl); // slow_count .. the end
+
+// Flat decode of oversized / OPTIONAL pages (pqg_flat.cu): per work-list entry, and the cursors of its three kernels
+// (reset with the other work counters of a (sub-)run).
+struct FlatPage { uint32_t status, nn, vpos, bw, blk0, page; }; // status 0: decode; vpos: values / first index-run header inside the payload
+struct __align__(16) FlatBlk { // one 1024-slot block, everything its warp needs in one read (written by k_flat_ranks)
+    uint64_t src;      // image offset: PLAIN -- the block's first value; dictionary page -- the index stream (behind the bit-width byte)
+    uint64_t row;      // output slot of the block's first slot
+    uint32_t nslots;   // 1 .. 1024; 0: nothing to do (the page went to the general kernel)
+    uint32_t rank0;    // values of the page in front of the block
+    uint32_t cp_pos, cp_first; // dictionary page: the checkpoint in front of value rank0 {run header position, first value of that run}
+    uint32_t slen;     // dictionary page: length of the index stream
+    uint32_t info;     // bits 0..5: index bit width; bit 8: dictionary page; bit 9: no validity to read (REQUIRED chunk)
+    uint32_t chunk;
+    uint32_t pad;
 };
 
 // A run of consecutive pages of one chunk whose bytes are staged with one bulk copy.
@@ -140,6 +159,14 @@ struct DecodeParams {
     uint32_t identity_dict;  // dictionary-form output: emit the dictionary INDEX of every slot instead of the entry
     uint32_t check_layout;   // BYTE_ARRAY copy pass: page byte counts came from the page headers -- verify them
     uint32_t exact_sizes;    // BYTE_ARRAY size pass: no optimistic per-page byte counts (a page broke its count in an earlier run)
+    // flat decode of the slow list (plans with OPTIONAL chunks or host-listed pages, 4/8-byte values): null when off
+    FlatCtl* flat;
+    FlatPage* flat_pages;    // per work-list entry (capacity slow_cap)
+    FlatBlk* flat_blk;       // per 1024-slot block of a listed page
+    uint2* flat_ckpt;        // per 1024 VALUES of a listed dictionary page: {run header position, first value of that run}
+    uint32_t flat_blk_cap;
+    uint32_t* flat_append;   // pages the flat kernels hand to the general kernel: flat_append[0 .. flat->handed)
+    const uint32_t* append_count; // general kernel: number of device-appended pages behind slow_append (null: err->slow_count)
     uint64_t chars_cap;      // BYTE_ARRAY copy pass launched without a host sync: capacity of `chars` ...
     const uint64_t* total_chars; // ... and the device-side grand total it must hold (null: the host already checked)
 };
@@ -153,6 +180,9 @@ cudaError_t launch_decode_fixed(const DecodeParams& p, int width, bool boolean_p
 cudaError_t launch_fixed_tiles(const DecodeParams& p, int width, int sm_count, cudaStream_t s);
 cudaError_t launch_fixed_tiles_part(const DecodeParams& p, int width, int sm_count, cudaStream_t s); // partitioned dictionary: ONE chunk per launch
 bool chunk_is_tileable(int phys_type, int max_def, int max_rep);
+// the slow list of 4/8-byte plans as a flat list of 1024-slot blocks (pqg_flat.cu); what it cannot take goes to flat_append
+cudaError_t launch_flat_pages(const DecodeParams& p, int width, int sm_count, bool any_dict, cudaStream_t s);
+uint32_t flat_launches();
 // oversized pages of 4/8-byte plans: one CTA per page (pqg_bigpage.cu); what it cannot take goes to the slow list
 cudaError_t launch_big_pages(const DecodeParams& p, int width, int sm_count, cudaStream_t s);
 cudaError_t launch_str_sizes(const DecodeParams& p, int sm_count, cudaStream_t s);

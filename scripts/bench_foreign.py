@@ -1,6 +1,7 @@
 """Decode throughput on pyarrow-written files (uncompressed, data page v1): INT64 PLAIN and
 dictionary columns with 64 KB and 1 MB pages -- the pages exceed the 8 KB tiles, so they run
-through the general kernel (one warp per page).  usage: python scripts/bench_foreign.py [rows]"""
+through the general kernel (one warp per page).  usage: python scripts/bench_foreign.py [rows] [page_bytes] [column]
+(page_bytes / column restrict the run to one page size / one of plain, dict, plain_nulls, dict_nulls: ncu captures)"""
 import json
 import os
 import sys
@@ -14,6 +15,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import pqb200 as pq
 
 rows = int(sys.argv[1]) if len(sys.argv) > 1 else 10_000_000
+only_page = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+only_col = sys.argv[3] if len(sys.argv) > 3 else None
 rng = np.random.default_rng(2)
 nulls = rng.random(rows) < 0.25
 t = pa.table({"plain": pa.array(rng.integers(-2**60, 2**60, size=rows), type=pa.int64()),
@@ -22,6 +25,8 @@ t = pa.table({"plain": pa.array(rng.integers(-2**60, 2**60, size=rows), type=pa.
               "dict_nulls": pa.array(rng.integers(0, 4096, size=rows) * 977, mask=nulls, type=pa.int64())})
 out = []
 for page in (8 * 1024, 64 * 1024, 1 << 20):
+    if only_page and page != only_page:
+        continue
     with tempfile.TemporaryDirectory() as d:
         p = os.path.join(d, "f.parquet")
         pqa.write_table(t, p, compression="NONE", data_page_version="1.0", write_statistics=False, data_page_size=page,
@@ -32,6 +37,8 @@ for page in (8 * 1024, 64 * 1024, 1 << 20):
     buf = ctx.upload(img.ctypes.data, img.size)
     ctx.set_profiling(True)
     for c in range(4):
+        if only_col and t.column_names[c] != only_col:
+            continue
         plan = ctx.plan(buf, r.column_tables(c, -1))
         for _ in range(4):
             plan.run()
