@@ -35,6 +35,13 @@ template <int W> __device__ __forceinline__ typename FlatElem<W>::T flat_ld(cons
 template <> __device__ __forceinline__ uint32_t flat_ld<4>(const uint8_t* p) { return ld32u(p); }
 template <> __device__ __forceinline__ uint64_t flat_ld<8>(const uint8_t* p) { return ld64u(p); }
 
+// shared-state-space accesses by address (the generic forms cost an address conversion per access)
+__device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+template <int W> __device__ __forceinline__ typename FlatElem<W>::T lds_elem(uint32_t a);
+template <> __device__ __forceinline__ uint32_t lds_elem<4>(uint32_t a) { return lds32(a); }
+template <> __device__ __forceinline__ uint64_t lds_elem<8>(uint32_t a) { uint64_t v; asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a)); return v; }
+
 __device__ __forceinline__ void prefetch_l1(const uint8_t* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 // lanes prefetch the 128-byte lines of [p + from, p + to)
 __device__ __forceinline__ void prefetch_range(const uint8_t* p, uint32_t from, uint32_t to) {
@@ -407,6 +414,7 @@ __device__ __forceinline__ void flat_emit_block(const DecodeParams& P, uint32_t 
     }
     // ---- dictionary block: indices of values [rank0, rank0 + cntb) -> shared memory ----
     const uint32_t bw = d.info & 63u;
+    const uint32_t idx_s = static_cast<uint32_t>(__cvta_generic_to_shared(idx));
     const uint8_t* stream = P.image + d.src;
     const uint32_t slen = d.slen;
     const DevChunk& ck = P.chunks[d.chunk];
@@ -426,19 +434,26 @@ __device__ __forceinline__ void flat_emit_block(const DecodeParams& P, uint32_t 
             const uint32_t cnt = w.rem; // (validated by k_flat_scan: no bad runs, literal data inside the page)
             const uint32_t lo = max(v, rank0), hi = min(v + min(cnt, vend - v), vend);
             if (w.lit) {
-                for (uint32_t t = lo + l; t < hi; t += 32) idx[t - rank0] = ldbits(stream, w.bit + (t - v) * bw, bw) & imask;
+                for (uint32_t t = lo + l; t < hi; t += 32u * kFlatUnroll) { // four loads in flight per lane, then the stores
+                    uint32_t x[kFlatUnroll];
+#pragma unroll
+                    for (uint32_t u = 0; u < kFlatUnroll; u++) x[u] = ldbits(stream, w.bit + (min(t + 32u * u, hi - 1u) - v) * bw, bw) & imask;
+#pragma unroll
+                    for (uint32_t u = 0; u < kFlatUnroll; u++) if (t + 32u * u < hi) sts32(idx_s + 4u * (t + 32u * u - rank0), x[u]);
+                }
                 w.pos = w.next_pos;
             } else {
-                for (uint32_t t = lo + l; t < hi; t += 32) idx[t - rank0] = w.val;
+                for (uint32_t t = lo + l; t < hi; t += 32) sts32(idx_s + 4u * (t - rank0), w.val);
             }
             v += min(cnt, vend - v);
         }
-        for (uint32_t t = max(v, rank0) + l; t < vend; t += 32) idx[t - rank0] = 0; // exhausted stream: zeros
+        for (uint32_t t = max(v, rank0) + l; t < vend; t += 32) sts32(idx_s + 4u * (t - rank0), 0u); // exhausted stream: zeros
     }
     __syncwarp();
     const T* dict = reinterpret_cast<const T*>(P.dict_arena + ck.dict_arena_off);
     const uint32_t dict_n = ck.dict_ok_n;
     const bool staged = d.chunk == sdict_chunk; // the CTA holds this chunk's dictionary in shared memory
+    const uint32_t sdict_s = static_cast<uint32_t>(__cvta_generic_to_shared(sdict));
     uint32_t* gv = P.validity;
     uint32_t nbad = 0;
     for (uint32_t st = 0; st < nsteps; st += kFlatUnroll) {
@@ -449,7 +464,7 @@ __device__ __forceinline__ void flat_emit_block(const DecodeParams& P, uint32_t 
             const uint32_t sw = min(st + u, 31u);
             const uint32_t word = __shfl_sync(0xffffffffu, vw, sw), base = __shfl_sync(0xffffffffu, excl, sw);
             const bool valid = st + u < nsteps && ((word >> l) & 1u);
-            ix[u] = valid ? idx[base + __popc(word & ((1u << l) - 1u))] : 0u;
+            ix[u] = lds32(idx_s + 4u * min(base + __popc(word & ((1u << l) - 1u)), 1023u)); // (null slots read and discard)
             in[u] = valid && ix[u] < dict_n;
             if (valid && !in[u]) { // out-of-range index: NULL (column_reader.cpp:190-194)
                 const uint64_t gs = d.row + 32u * (st + u) + l;
@@ -461,7 +476,7 @@ __device__ __forceinline__ void flat_emit_block(const DecodeParams& P, uint32_t 
 #pragma unroll
         for (uint32_t u = 0; u < kFlatUnroll; u++) {
             x[u] = 0;
-            if (in[u]) x[u] = P.identity_dict ? static_cast<T>(ix[u]) : (staged ? reinterpret_cast<const T*>(sdict)[ix[u]] : __ldg(dict + ix[u]));
+            if (in[u]) x[u] = P.identity_dict ? static_cast<T>(ix[u]) : (staged ? lds_elem<W>(sdict_s + static_cast<uint32_t>(W) * ix[u]) : __ldg(dict + ix[u]));
         }
 #pragma unroll
         for (uint32_t u = 0; u < kFlatUnroll; u++) {
