@@ -23,7 +23,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libpqg.so")
 BOOLEAN, INT32, INT64, INT96, FLOAT, DOUBLE, BYTE_ARRAY, FIXED_LEN_BYTE_ARRAY = range(8)
 PQG_OK, PQG_ERR_CUDA, PQG_ERR_ARG, PQG_ERR_UNSUPPORTED, PQG_ERR_PAGE, PQG_ERR_REGEX, PQG_ERR_NOMEM = range(7)
 PQG_OPT_PARTITIONED_DICT = 1
-PQG_PAGE_FLAG_DICT, PQG_PAGE_FLAG_V2 = 1, 2  # pqg_page_desc.flags; bits 8..15 = DataPageHeader.encoding
+PQG_PAGE_FLAG_DICT, PQG_PAGE_FLAG_V2, PQG_PAGE_FLAG_NO_NULLS, PQG_PAGE_FLAG_LEVELS_SEEN = 1, 2, 4, 8  # pqg_page_desc.flags; bits 8..15 = DataPageHeader.encoding
 
 
 def build(verbose=False):

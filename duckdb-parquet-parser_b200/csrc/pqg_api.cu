@@ -440,6 +440,7 @@ static int plan_create_impl(pqg_ctx* ctx, const pqg_buf* image, const pqg_chunk_
                                   : (p->any_def ? kTileBytesLarge : kTileBytes);
         const uint64_t tile_cap = p->tile_bytes;
         uint32_t max_dict_n = 0;
+        const bool flat_ok = !p->is_str && !p->is_bool && (p->width == 4 || p->width == 8);
         for (uint32_t c = 0; c < n_chunks; c++) {
             const pqg_chunk_desc& s = chunks[c];
             p->chunk_tile_begin.push_back(static_cast<uint32_t>(tiles.size()));
@@ -492,6 +493,10 @@ static int plan_create_impl(pqg_ctx* ctx, const pqg_buf* image, const pqg_chunk_
                     continue;
                 }
                 if (!tileable || too_big) { flush(); slow.push_back(q); continue; }
+                // OPTIONAL pages of more than 1024 slots: the tile kernel takes them only when they hold no nulls (one level run:
+                // a REQUIRED page).  When the table's producer looked at the levels, the others skip the tile kernel (it would stage them and
+                // hand them over) and go to the block decode of the slow list directly; tables without the hint keep the device-side hand-over.
+                if (flat_ok && s.max_def == 1 && pg.num_values > 1024u && (pg.flags & (PQG_PAGE_FLAG_LEVELS_SEEN | PQG_PAGE_FLAG_NO_NULLS)) == PQG_PAGE_FLAG_LEVELS_SEEN) { flush(); slow.push_back(q); continue; }
                 // OPTIONAL pages beyond the writer's shapes: the tile kernel decodes the small ones itself and needs its index buffer
                 if (!p->is_str && s.max_def == 1 && (pg.num_values > 1024u || pg.payload_size > 2048u)) p->opt_idx = true;
                 place(q, pg);

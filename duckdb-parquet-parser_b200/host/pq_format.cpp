@@ -361,6 +361,7 @@ void walk_chunk_pages(const uint8_t* image, uint64_t image_file_off, uint64_t im
         r.encoding = Encoding::PLAIN;
         r.num_values = 0;
         r.counted = false;
+        r.one_level_run = false;
         if (ph.compressed_page_size < 0) throw FormatError("negative page size");
         if (ph.type == PageType::DICTIONARY_PAGE) {
             if (!ph.dictionary_page_header) throw FormatError("bad_optional_access: dictionary page without its header");
@@ -373,6 +374,19 @@ void walk_chunk_pages(const uint8_t* image, uint64_t image_file_off, uint64_t im
                 r.encoding = ph.data_page_header->encoding;
                 if (r.num_values < 0) throw FormatError("negative num_values");
                 values_read += r.num_values;
+                // routing hint for OPTIONAL flat columns: levels = one RLE run of level 1 over the whole page (no nulls)
+                const uint64_t po = r.payload_off - image_file_off;
+                if (r.payload_size >= 6 && po + r.payload_size <= image_size) {
+                    const uint8_t* pl = image + po;
+                    const uint32_t def_len = static_cast<uint32_t>(pl[0]) | static_cast<uint32_t>(pl[1]) << 8 | static_cast<uint32_t>(pl[2]) << 16 | static_cast<uint32_t>(pl[3]) << 24;
+                    if (def_len >= 2 && def_len <= r.payload_size - 4) {
+                        uint64_t ind = 0;
+                        uint32_t shift = 0, hp = 0;
+                        bool complete = false;
+                        while (hp < def_len && hp < 5) { const uint8_t b = pl[4 + hp++]; ind |= static_cast<uint64_t>(b & 0x7f) << shift; shift += 7; if (!(b & 0x80)) { complete = true; break; } }
+                        r.one_level_run = complete && !(ind & 1) && (ind >> 1) >= static_cast<uint64_t>(r.num_values) && hp < def_len && pl[4 + hp] == 1;
+                    }
+                }
             } else {
                 // the reference dereferences an empty optional here (bad_optional_access)
                 throw FormatError("bad_optional_access: data page without its header");
@@ -431,6 +445,7 @@ void append_chunk_tables(ColumnTables& t, const std::vector<PageRecord>& pages, 
             p.num_values = static_cast<uint32_t>(r.num_values);
             p.chunk_idx = static_cast<uint32_t>(t.chunks.size() - 1);
             p.flags = PQG_PAGE_FLAGS(r.encoding == Encoding::PLAIN_DICTIONARY || r.encoding == Encoding::RLE_DICTIONARY, static_cast<int32_t>(r.encoding));
+            if (max_def == 1 && max_rep == 0) p.flags |= PQG_PAGE_FLAG_LEVELS_SEEN | (r.one_level_run ? PQG_PAGE_FLAG_NO_NULLS : 0u);
             t.pages.push_back(p);
             t.page_row_group.push_back(rg);
             c.n_pages++;

@@ -145,6 +145,7 @@ struct PageRecord {
     PageType type;
     Encoding encoding;
     bool counted;          // contributes to the global page index (DATA_PAGE / DATA_PAGE_V2)
+    bool one_level_run;    // data pages: the payload starts like <u32 length><RLE run of value 1 covering num_values> (PQG_PAGE_FLAG_NO_NULLS for max_def 1 columns)
 };
 
 // Walks the pages of a chunk exactly like every reference loop does

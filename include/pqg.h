@@ -88,6 +88,12 @@ typedef struct pqg_chunk_desc {
 
 #define PQG_PAGE_FLAG_DICT 1u /* DataPageHeader.encoding is PLAIN_DICTIONARY / RLE_DICTIONARY */
 #define PQG_PAGE_FLAG_V2 2u   /* the page is a DATA_PAGE_V2: pqg_plan_create rejects the plan (PQG_ERR_UNSUPPORTED) */
+#define PQG_PAGE_FLAG_LEVELS_SEEN 8u /* the producer of the table looked at the page's level bytes: PQG_PAGE_FLAG_NO_NULLS is set where it holds */
+#define PQG_PAGE_FLAG_NO_NULLS 4u /* routing hint (optional; the kernels verify it): the definition levels of this page of an OPTIONAL
+                                   * flat column are ONE RLE run of level 1 covering all its values -- what nullable-by-default writers
+                                   * emit for a page without nulls.  Such pages decode as REQUIRED pages in the tile kernel whatever
+                                   * their size; OPTIONAL pages of more than 1024 values with LEVELS_SEEN and without NO_NULLS go straight to the block
+                                   * decode of oversized pages instead of being looked at and handed over by the tile kernel. */
 /* bits 8..15 of pqg_page_desc.flags: the Encoding enum value of DataPageHeader.encoding (0 PLAIN,
  * 2 PLAIN_DICTIONARY, 8 RLE_DICTIONARY are decoded; DELTA_BINARY_PACKED 5, DELTA_LENGTH_BYTE_ARRAY 6,
  * DELTA_BYTE_ARRAY 7, BYTE_STREAM_SPLIT 9 and anything else make pqg_plan_create fail with

@@ -195,7 +195,12 @@ def test_page_descriptors_carry_encoding_and_page_type(pq, tmp_path):
 
     p = str(tmp_path / "v1.parquet")
     pqa.write_table(t, p, use_dictionary=["d"], **base)
-    assert set(flags(p, 0)) == {0}                                   # PLAIN
+    # PLAIN; the columns are nullable without nulls: the reader saw one level run per page (routing hints)
+    assert set(flags(p, 0)) == {pq.PQG_PAGE_FLAG_LEVELS_SEEN | pq.PQG_PAGE_FLAG_NO_NULLS}
+    tn = pa.table({"i": pa.array(rng.integers(0, 1 << 40, size=n), mask=rng.random(n) < 0.3, type=pa.int64())})
+    pn = str(tmp_path / "nulls.parquet")
+    pqa.write_table(tn, pn, use_dictionary=False, **base)
+    assert set(flags(pn, 0)) == {pq.PQG_PAGE_FLAG_LEVELS_SEEN}       # nulls: seen, no NO_NULLS
     assert all(f & 1 and (f >> 8) in (2, 8) for f in flags(p, 1))    # dictionary
     p = str(tmp_path / "delta.parquet")
     pqa.write_table(t, p, use_dictionary=False, column_encoding={"i": "DELTA_BINARY_PACKED", "f": "BYTE_STREAM_SPLIT"}, **base)
