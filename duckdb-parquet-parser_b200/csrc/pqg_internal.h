@@ -183,8 +183,6 @@ bool chunk_is_tileable(int phys_type, int max_def, int max_rep);
 // the slow list of 4/8-byte plans as a flat list of 1024-slot blocks (pqg_flat.cu); what it cannot take goes to flat_append
 cudaError_t launch_flat_pages(const DecodeParams& p, int width, int sm_count, bool any_dict, cudaStream_t s);
 uint32_t flat_launches();
-// oversized pages of 4/8-byte plans: one CTA per page (pqg_bigpage.cu); what it cannot take goes to the slow list
-cudaError_t launch_big_pages(const DecodeParams& p, int width, int sm_count, cudaStream_t s);
 cudaError_t launch_str_sizes(const DecodeParams& p, int sm_count, cudaStream_t s);
 cudaError_t launch_str_scan(const DecodeParams& p, uint64_t* total_chars, cudaStream_t s);
 cudaError_t launch_str_copy(const DecodeParams& p, bool any_dict, int sm_count, cudaStream_t s);
