@@ -1,5 +1,5 @@
 # Round-2 captures for profiles/: bench lines (both arms), ncu launch list of the bench, ncu --set full of the dominant kernel
-# (the 4 k_fixed_tiles launches of one timed step), of the string kernels and of the regex tile kernel, and the side benches.
+# (the 4 k_fixed_tiles launches of one timed step), of the string kernels, the regex tile kernel and the flat block decode, and the side benches.
 mkdir -p gpurun_out
 T=${TAG:-r02}
 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/${T}_bench_ref.json 2> gpurun_out/${T}_bench_ref.err; echo "reference arm rc=$?"
@@ -12,7 +12,10 @@ for W in cfg3 cfg4; do
   ncu --set full --clock-control none --import-source on -k regex:k_str_pages -s 2 -c 2 -f -o gpurun_out/${T}_prof_str_$W python scripts/bench_strings.py 40000000 $W > gpurun_out/ncu_s_$W.log 2>&1; echo "strings capture $W rc=$?"
 done
 ncu --set full --clock-control none --import-source on -k regex:k_regex_tiles -s 2 -c 1 -f -o gpurun_out/${T}_prof_regex python scripts/prof_regex.py 20000000 > gpurun_out/ncu_r.log 2>&1; echo "regex capture rc=$?"
-python scripts/prof_regex.py 40000000 > gpurun_out/${T}_regex.json 2>> gpurun_out/side.err
+for K in emit scan; do
+  ncu --set full --clock-control none --import-source on -k regex:k_flat_$K -s 2 -c 1 -f -o gpurun_out/${T}_prof_flat_$K python scripts/bench_foreign.py 40000000 65536 dict_nulls > gpurun_out/ncu_f_$K.log 2>&1; echo "flat $K capture rc=$?"
+done
+python scripts/prof_regex.py 100000000 > gpurun_out/${T}_regex.json 2>> gpurun_out/side.err
 python scripts/bench_strings.py 40000000 > gpurun_out/${T}_strings.json 2>> gpurun_out/side.err; echo "strings rc=$?"
 python scripts/bench_optional.py 40000000 > gpurun_out/${T}_optional.json 2>> gpurun_out/side.err; echo "optional rc=$?"
 python scripts/bench_foreign.py 40000000 > gpurun_out/${T}_foreign.json 2>> gpurun_out/side.err; echo "foreign rc=$?"
