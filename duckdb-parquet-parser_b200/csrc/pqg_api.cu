@@ -53,6 +53,7 @@ struct pqg_plan {
     uint2* d_flat_ckpt = nullptr;
     uint32_t* d_flat_append = nullptr;
     uint32_t flat_blk_cap = 0;
+    uint32_t max_dict_n = 0;                 // most entries of one dictionary of the plan
     bool flat_ran = false;                   // the current run launched the flat kernels
     uint32_t tile_handover_seen = 0xffffffffu; // pages the tile kernel handed over in the last finished run (~0u: none finished yet)
     uint32_t dict_smem = 0;
@@ -508,6 +509,7 @@ static int plan_create_impl(pqg_ctx* ctx, const pqg_buf* image, const pqg_chunk_
         p->n_tiles = static_cast<uint32_t>(tiles.size());
         p->n_slow_host = static_cast<uint32_t>(slow.size());
         p->max_dict_blocks = std::max<uint32_t>(1, std::min<uint32_t>(64, (max_dict_n + 2047) / 2048));
+        p->max_dict_n = max_dict_n;
     }
 
     std::vector<uint32_t> h_page_chars, h_page_base;
@@ -758,7 +760,7 @@ static int fixed_subrun(pqg_ctx* ctx, pqg_plan* p, uint32_t c0, uint32_t c1, boo
     //  whatever shows up -- instead of three launches over an empty list)
     if (e == cudaSuccess && p->flat_on && (P.slow_hi > P.slow_lo || (P.tile_hi > P.tile_lo && p->tile_handover_seen != 0))) {
         p->flat_ran = true;
-        e = launch_flat_pages(P, p->width, ctx->sm_count, any_dict, s);
+        e = launch_flat_pages(P, p->width, ctx->sm_count, any_dict, p->max_dict_n <= 0xffffu, s);
         launches += static_cast<int>(flat_launches());
         Pg.slow_hi = Pg.slow_lo;
         Pg.slow_append = P.flat_append;

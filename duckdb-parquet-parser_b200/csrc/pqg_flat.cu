@@ -38,6 +38,16 @@ template <> __device__ __forceinline__ uint64_t flat_ld<8>(const uint8_t* p) { r
 // shared-state-space accesses by address (the generic forms cost an address conversion per access)
 __device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+// the block's index buffer: 32-bit entries, or 16-bit ones when every dictionary of the plan has <= 65535 entries (an index
+// beyond 16 bits is out of range there whatever its value: it is stored as 0xffff and stays out of range)
+template <bool IDX16> __device__ __forceinline__ void sts_idx(uint32_t base, uint32_t i, uint32_t v) {
+    if constexpr (IDX16) asm volatile("st.shared.u16 [%0], %1;" ::"r"(base + 2u * i), "h"(static_cast<uint16_t>(min(v, 0xffffu))) : "memory");
+    else sts32(base + 4u * i, v);
+}
+template <bool IDX16> __device__ __forceinline__ uint32_t lds_idx(uint32_t base, uint32_t i) {
+    if constexpr (IDX16) { uint16_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(base + 2u * i)); return v; }
+    else return lds32(base + 4u * i);
+}
 template <int W> __device__ __forceinline__ typename FlatElem<W>::T lds_elem(uint32_t a);
 template <> __device__ __forceinline__ uint32_t lds_elem<4>(uint32_t a) { return lds32(a); }
 template <> __device__ __forceinline__ uint64_t lds_elem<8>(uint32_t a) { uint64_t v; asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a)); return v; }
@@ -192,6 +202,15 @@ __device__ __forceinline__ void flat_scan_page(const DecodeParams& P, uint32_t e
         while (v < n) {
             keep_ahead(pos + 1u + w.pos, pf);
             if (!seq) {
+                // a run that fills the window by itself (literal runs of foreign writers: 504 values) needs no chain
+                const RunAt head = parse_run_at(stream, slen, w.pos, bw);
+                if (head.cnt && head.end - w.pos >= 32u) {
+                    const uint32_t cnt = min(head.cnt, n - v);
+                    for (uint32_t j = ((v + 1023u) >> 10) + l; (j << 10) < v + cnt; j += 32) ckpt[j] = make_uint2(w.pos, v);
+                    v += cnt;
+                    w.pos = head.end;
+                    continue;
+                }
                 RunAt r;
                 bool cut;
                 const uint32_t used = window_runs(stream, slen, w.pos, bw, r, &cut);
@@ -374,8 +393,8 @@ __global__ void __launch_bounds__(kThreadsPerCta) k_flat_ranks(const DecodeParam
 }
 
 // ---- emission -----------------------------------------------------------------------------------------------------------
-template <int W>
-__device__ __forceinline__ void flat_emit_block(const DecodeParams& P, uint32_t g, uint32_t* idx, const uint8_t* sdict, uint32_t sdict_chunk) {
+template <int W, bool IDX16>
+__device__ __forceinline__ void flat_emit_block(const DecodeParams& P, uint32_t g, uint32_t idx_s, const uint8_t* sdict, uint32_t sdict_chunk) {
     using T = typename FlatElem<W>::T;
     const uint32_t l = lane_id();
     const FlatBlk d = P.flat_blk[g];
@@ -414,7 +433,6 @@ __device__ __forceinline__ void flat_emit_block(const DecodeParams& P, uint32_t 
     }
     // ---- dictionary block: indices of values [rank0, rank0 + cntb) -> shared memory ----
     const uint32_t bw = d.info & 63u;
-    const uint32_t idx_s = static_cast<uint32_t>(__cvta_generic_to_shared(idx));
     const uint8_t* stream = P.image + d.src;
     const uint32_t slen = d.slen;
     const DevChunk& ck = P.chunks[d.chunk];
@@ -439,15 +457,15 @@ __device__ __forceinline__ void flat_emit_block(const DecodeParams& P, uint32_t 
 #pragma unroll
                     for (uint32_t u = 0; u < kFlatUnroll; u++) x[u] = ldbits(stream, w.bit + (min(t + 32u * u, hi - 1u) - v) * bw, bw) & imask;
 #pragma unroll
-                    for (uint32_t u = 0; u < kFlatUnroll; u++) if (t + 32u * u < hi) sts32(idx_s + 4u * (t + 32u * u - rank0), x[u]);
+                    for (uint32_t u = 0; u < kFlatUnroll; u++) if (t + 32u * u < hi) sts_idx<IDX16>(idx_s, t + 32u * u - rank0, x[u]);
                 }
                 w.pos = w.next_pos;
             } else {
-                for (uint32_t t = lo + l; t < hi; t += 32) sts32(idx_s + 4u * (t - rank0), w.val);
+                for (uint32_t t = lo + l; t < hi; t += 32) sts_idx<IDX16>(idx_s, t - rank0, w.val);
             }
             v += min(cnt, vend - v);
         }
-        for (uint32_t t = max(v, rank0) + l; t < vend; t += 32) sts32(idx_s + 4u * (t - rank0), 0u); // exhausted stream: zeros
+        for (uint32_t t = max(v, rank0) + l; t < vend; t += 32) sts_idx<IDX16>(idx_s, t - rank0, 0u); // exhausted stream: zeros
     }
     __syncwarp();
     const T* dict = reinterpret_cast<const T*>(P.dict_arena + ck.dict_arena_off);
@@ -464,7 +482,7 @@ __device__ __forceinline__ void flat_emit_block(const DecodeParams& P, uint32_t 
             const uint32_t sw = min(st + u, 31u);
             const uint32_t word = __shfl_sync(0xffffffffu, vw, sw), base = __shfl_sync(0xffffffffu, excl, sw);
             const bool valid = st + u < nsteps && ((word >> l) & 1u);
-            ix[u] = lds32(idx_s + 4u * min(base + __popc(word & ((1u << l) - 1u)), 1023u)); // (null slots read and discard)
+            ix[u] = lds_idx<IDX16>(idx_s, min(base + __popc(word & ((1u << l) - 1u)), 1023u)); // (null slots read and discard)
             in[u] = valid && ix[u] < dict_n;
             if (valid && !in[u]) { // out-of-range index: NULL (column_reader.cpp:190-194)
                 const uint64_t gs = d.row + 32u * (st + u) + l;
@@ -491,12 +509,13 @@ __device__ __forceinline__ void flat_emit_block(const DecodeParams& P, uint32_t 
 // the dictionary of the batch's chunk in shared memory when it fits (<= kMaxSmemDictBytes, as the tile kernel does): a
 // gather from L1 costs one wavefront per lane, 40 M of them were the whole emission time of a 4096-entry dictionary column.
 constexpr uint32_t kFlatBatch = 32;
-template <int W>
+template <int W, bool IDX16>
 __global__ void __launch_bounds__(kThreadsPerCta) k_flat_emit(const DecodeParams P, uint32_t with_dict) {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ uint32_t s_batch, s_chunk;
-    uint32_t* idx = reinterpret_cast<uint32_t*>(smem) + warp_id() * 1024u; // the block's dictionary indices, by value
-    uint8_t* sdict = smem + kWarpsPerCta * 4096u;
+    constexpr uint32_t kIdxBytes = IDX16 ? 2048u : 4096u;
+    const uint32_t idx_s = static_cast<uint32_t>(__cvta_generic_to_shared(smem)) + warp_id() * kIdxBytes; // the block's dictionary indices, by value
+    uint8_t* sdict = smem + kWarpsPerCta * kIdxBytes;
     const uint32_t total = P.flat->nblk;
     if (blockIdx.x * kFlatBatch >= total) return;
     uint32_t cur_chunk = 0xffffffffu;
@@ -532,7 +551,7 @@ __global__ void __launch_bounds__(kThreadsPerCta) k_flat_emit(const DecodeParams
             }
         }
         for (uint32_t g = g0 + warp_id(); g < g1; g += kWarpsPerCta) {
-            flat_emit_block<W>(P, g, idx, sdict, cur_chunk);
+            flat_emit_block<W, IDX16>(P, g, idx_s, sdict, cur_chunk);
             __syncwarp();
         }
     }
@@ -543,25 +562,23 @@ __global__ void __launch_bounds__(kThreadsPerCta) k_flat_emit(const DecodeParams
 uint32_t flat_launches() { return 3; }
 
 // p.flat (the cursors) must be zero: the caller resets it with the other work counters of the (sub-)run
-cudaError_t launch_flat_pages(const DecodeParams& p, int width, int sm_count, bool any_dict, cudaStream_t s) {
-    if (width != 4 && width != 8) return cudaErrorInvalidValue;
+template <int W, bool IDX16>
+static cudaError_t launch_flat_t(const DecodeParams& p, int sm_count, bool any_dict, cudaStream_t s) {
     const unsigned grid = static_cast<unsigned>(sm_count) * 6u; // 48 warps per SM (<= 48 registers)
-    // emission of plans with dictionaries: per-warp index buffers + the staged dictionary = 64 KB per CTA, 3 CTAs per SM
-    const size_t smem = any_dict ? static_cast<size_t>(kWarpsPerCta) * 4096u + kMaxSmemDictBytes : 0;
-    const unsigned egrid = static_cast<unsigned>(sm_count) * (any_dict ? 3u : 6u);
-    cudaError_t e;
-    if (width == 4) {
-        if ((e = cudaFuncSetAttribute(k_flat_emit<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))) != cudaSuccess) return e;
-        k_flat_scan<4><<<grid, kThreadsPerCta, 0, s>>>(p);
-        k_flat_ranks<4><<<grid, kThreadsPerCta, 0, s>>>(p);
-        k_flat_emit<4><<<egrid, kThreadsPerCta, smem, s>>>(p, any_dict ? 1u : 0u);
-    } else {
-        if ((e = cudaFuncSetAttribute(k_flat_emit<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))) != cudaSuccess) return e;
-        k_flat_scan<8><<<grid, kThreadsPerCta, 0, s>>>(p);
-        k_flat_ranks<8><<<grid, kThreadsPerCta, 0, s>>>(p);
-        k_flat_emit<8><<<egrid, kThreadsPerCta, smem, s>>>(p, any_dict ? 1u : 0u);
-    }
+    // emission of plans with dictionaries: per-warp index buffers + the staged dictionary = 48 / 64 KB per CTA, 4 / 3 CTAs per SM
+    const size_t smem = any_dict ? static_cast<size_t>(kWarpsPerCta) * (IDX16 ? 2048u : 4096u) + kMaxSmemDictBytes : 0;
+    const unsigned egrid = static_cast<unsigned>(sm_count) * (any_dict ? (IDX16 ? 4u : 3u) : 6u);
+    cudaError_t e = cudaFuncSetAttribute(k_flat_emit<W, IDX16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    k_flat_scan<W><<<grid, kThreadsPerCta, 0, s>>>(p);
+    k_flat_ranks<W><<<grid, kThreadsPerCta, 0, s>>>(p);
+    k_flat_emit<W, IDX16><<<egrid, kThreadsPerCta, smem, s>>>(p, any_dict ? 1u : 0u);
     return cudaGetLastError();
+}
+cudaError_t launch_flat_pages(const DecodeParams& p, int width, int sm_count, bool any_dict, bool idx16, cudaStream_t s) {
+    if (width == 4) return idx16 ? launch_flat_t<4, true>(p, sm_count, any_dict, s) : launch_flat_t<4, false>(p, sm_count, any_dict, s);
+    if (width == 8) return idx16 ? launch_flat_t<8, true>(p, sm_count, any_dict, s) : launch_flat_t<8, false>(p, sm_count, any_dict, s);
+    return cudaErrorInvalidValue;
 }
 
 } // namespace pqg

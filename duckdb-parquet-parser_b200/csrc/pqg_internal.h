@@ -181,7 +181,8 @@ cudaError_t launch_fixed_tiles(const DecodeParams& p, int width, int sm_count, c
 cudaError_t launch_fixed_tiles_part(const DecodeParams& p, int width, int sm_count, cudaStream_t s); // partitioned dictionary: ONE chunk per launch
 bool chunk_is_tileable(int phys_type, int max_def, int max_rep);
 // the slow list of 4/8-byte plans as a flat list of 1024-slot blocks (pqg_flat.cu); what it cannot take goes to flat_append
-cudaError_t launch_flat_pages(const DecodeParams& p, int width, int sm_count, bool any_dict, cudaStream_t s);
+// idx16: no dictionary of the plan has more than 65535 entries (the emission keeps 16-bit indices: 4 CTAs per SM instead of 3)
+cudaError_t launch_flat_pages(const DecodeParams& p, int width, int sm_count, bool any_dict, bool idx16, cudaStream_t s);
 uint32_t flat_launches();
 cudaError_t launch_str_sizes(const DecodeParams& p, int sm_count, cudaStream_t s);
 cudaError_t launch_str_scan(const DecodeParams& p, uint64_t* total_chars, cudaStream_t s);
