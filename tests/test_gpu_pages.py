@@ -211,13 +211,13 @@ def _level_stream(present, rng, style):
     return bytes(out)
 
 
-@pytest.mark.parametrize("bw", [0, 1, 5, 12, 16, 20, 32])
+@pytest.mark.parametrize("bw", [0, 1, 5, 12, 16, 17, 20, 32])
 def test_big_optional_dictionary_pages_through_the_block_decode(pq, oracle, bw):
     """pages of more than 1024 slots of an OPTIONAL dictionary column go through k_flat_scan / k_flat_ranks / k_flat_emit:
     every level-stream style, index streams as foreign writers emit them (long literal runs, RLE runs with 1..3-byte
     headers), out-of-range indices -> nulls, short streams -> nulls / index 0, page sizes around the 1024-slot blocks"""
     rng = np.random.default_rng(100 + bw)
-    dict_n = 1 if bw == 0 else min(1 << min(bw, 13), 6000)
+    dict_n = 1 if bw == 0 else (70000 if bw == 17 else min(1 << min(bw, 13), 6000))  # (bw 17: beyond 16-bit index buffers)
     dict_vals = rng.integers(-2**62, 2**62, size=dict_n, dtype=np.int64)
     hi = 1 if bw == 0 else min((1 << bw) if bw < 32 else 1 << 32, dict_n + (dict_n // 50 if bw >= 5 else 0))  # a few out of range
     b = Builder(pq, dict_vals, max_def=1)
