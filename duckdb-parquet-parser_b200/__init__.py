@@ -127,7 +127,7 @@ PQG_SYMBOLS = [
     "pqg_plan_chars_size", "pqg_plan_char_bases", "pqg_plan_bytes_in", "pqg_plan_bytes_out", "pqg_plan_download",
     "pqg_regex_compile", "pqg_dfa_free", "pqg_dfa_num_states", "pqg_dfa_match_host", "pqg_regex_scan",
     "pqg_chunk_index", "pqg_page_chunk_index", "pqg_chunk_index_prepare", "pqg_chunk_index_stitch", "pqg_chunk_index_emit",
-    "pqg_chunk_job_ids", "pqg_chunk_job_total_weight", "pqg_chunk_job_free",
+    "pqg_chunk_job_ids", "pqg_chunk_job_total_weight", "pqg_chunk_job_free", "pqg_plan_create_ext",
 ]
 PQR_SYMBOLS = [
     "pqr_last_error", "pqr_open", "pqr_open_memory", "pqr_close", "pqr_num_rows", "pqr_num_row_groups",
@@ -138,6 +138,7 @@ PQR_SYMBOLS = [
     "pqr_columnar_free", "pqr_read_columns_into", "pqr_read_dictionary_indices_into", "pqr_chunk_dictionary", "pqr_release_plans", "pqr_column_tables", "pqr_columns_tables", "pqr_tables_free", "pqr_chunk_index", "pqr_regex_prune",
     "pqr_page_chunk_index", "pqr_shard_row_groups", "pqr_regex_prune_rgs", "pqr_chunk_index_rgs", "pqr_read_columns_into_rgs",
     "pqr_chunk_index_prepare_rgs", "pqr_chunk_index_stitch", "pqr_chunk_index_emit", "pqr_chunk_job_free", "pqr_column_tables_rgs",
+    "pqr_set_extensions",
 ]
 
 PQGEN_SYMBOLS = ["pqgen_last_error", "pqgen_encode", "pqgen_size", "pqgen_emit", "pqgen_write_file", "pqgen_free", "pqgen_string_len", "pqgen_fill_strings"]
@@ -228,6 +229,7 @@ def _declare(L):
     d("pqr_open", vp, cp, i32)
     d("pqr_open_memory", vp, vp, u64, i32)
     d("pqr_close", None, vp)
+    d("pqr_set_extensions", None, vp, i32)
     for n in ("pqr_num_rows", "pqr_num_row_groups", "pqr_num_columns", "pqr_num_pages"):
         d(n, i64, vp)
     d("pqr_row_group_num_rows", i64, vp, i32)
@@ -292,7 +294,9 @@ def _valdump_to_dict(d):
 class Reader:
     """pqg::ParquetReader through include/pqg_reader.h (reference: ParquetReader)."""
 
-    def __init__(self, path=None, data=None, device=-1):
+    def __init__(self, path=None, data=None, device=-1, extensions=False):
+        """extensions=True: SNAPPY-compressed chunks and DATA_PAGE_V2 pages decode (beyond the reference, which refuses /
+        skips them); the default keeps the reference's behaviour"""
         L = lib()
         self._keep = data
         if path is not None:
@@ -306,6 +310,8 @@ class Reader:
                 raise ValueError("data must be a uint8 array")
         if not self.h:
             raise PqgError(L.pqr_last_error().decode())
+        if extensions:
+            L.pqr_set_extensions(self.h, 1)
 
     @classmethod
     def from_pointer(cls, ptr, size, device=-1):

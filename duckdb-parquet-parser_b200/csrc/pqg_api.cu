@@ -53,6 +53,11 @@ struct pqg_plan {
     uint2* d_flat_ckpt = nullptr;
     uint32_t* d_flat_append = nullptr;
     uint32_t flat_blk_cap = 0;
+    // pqg_plan_create_ext: the plan's own image (`image` points at it) is rebuilt from the caller's at the start of every run
+    const pqg_buf* ext_src = nullptr;
+    pqg_buf* ext_image = nullptr;
+    XformRec* d_xform = nullptr;
+    uint32_t n_xform = 0;
     uint32_t max_dict_n = 0;                 // most entries of one dictionary of the plan
     bool flat_ran = false;                   // the current run launched the flat kernels
     uint32_t tile_handover_seen = 0xffffffffu; // pages the tile kernel handed over in the last finished run (~0u: none finished yet)
@@ -289,6 +294,7 @@ void pqg_plan_destroy(pqg_ctx* ctx, pqg_plan* p) {
     cudaFree(p->d_chunks); cudaFree(p->d_pages); cudaFree(p->d_dict); cudaFree(p->d_dict_segs); cudaFree(p->d_values);
     cudaFree(p->d_validity); cudaFree(p->d_required_ranges); cudaFree(p->d_offsets); cudaFree(p->d_chars); cudaFree(p->d_page_chars);
     cudaFree(p->d_page_char_base); cudaFree(p->d_bases); cudaFree(p->d_err); cudaFree(p->d_tiles); cudaFree(p->d_slow_pages);
+    cudaFree(p->d_xform); if (p->ext_image) { cudaFree(p->ext_image->d); delete p->ext_image; }
     cudaFree(p->d_flat_pages); cudaFree(p->d_flat_blk); cudaFree(p->d_flat_ckpt); cudaFree(p->d_flat_append);
     if (p->h_bases) cudaFreeHost(p->h_bases);
     if (p->h_err) cudaFreeHost(p->h_err);
@@ -325,6 +331,83 @@ int pqg_plan_create(pqg_ctx* ctx, const pqg_buf* image, const pqg_chunk_desc* ch
 int pqg_plan_create_dict_indices(pqg_ctx* ctx, const pqg_buf* image, const pqg_chunk_desc* chunks, uint32_t n_chunks,
                                  const pqg_page_desc* pages, uint32_t n_pages, pqg_plan** out) {
     return plan_create_impl(ctx, image, chunks, n_chunks, pages, n_pages, true, out);
+}
+
+int pqg_plan_create_ext(pqg_ctx* ctx, const pqg_buf* image, const pqg_chunk_desc* chunks, uint32_t n_chunks,
+                        const pqg_page_desc* pages, uint32_t n_pages, const pqg_page_ext* page_ext,
+                        const pqg_chunk_ext* chunk_ext, pqg_plan** out) {
+    if (!ctx || !image || !out || (!chunks && n_chunks) || (!pages && n_pages) || (!page_ext && n_pages) || (!chunk_ext && n_chunks))
+        return fail(ctx, PQG_ERR_ARG, "pqg_plan_create_ext: bad argument");
+    // the layout of the plan's own image: per chunk the dictionary page, then its data pages, each as a DATA_PAGE payload
+    std::vector<pqg_chunk_desc> ck(chunks, chunks + n_chunks);
+    std::vector<pqg_page_desc> pg(pages, pages + n_pages);
+    std::vector<XformRec> recs;
+    recs.reserve(static_cast<size_t>(n_pages) + n_chunks);
+    uint64_t off = 0;
+    auto place = [&](uint64_t bytes) { const uint64_t at = off; off = (off + bytes + 15u) & ~uint64_t(15); return at; };
+    for (uint32_t c = 0; c < n_chunks; c++) {
+        const pqg_chunk_desc& s = chunks[c];
+        if (s.first_page > n_pages || s.n_pages > n_pages - s.first_page) return fail(ctx, PQG_ERR_ARG, "pqg_plan_create_ext: chunk page range outside the page table");
+        if (s.has_dict) {
+            const uint32_t codec = chunk_ext[c].dict_codec;
+            if (codec > PQG_CODEC_SNAPPY) return fail(ctx, PQG_ERR_UNSUPPORTED, "pqg_plan_create_ext: dictionary page codec " + std::to_string(codec) + " is not supported (SNAPPY only)");
+            if (s.dict_off + s.dict_size > image->size) return fail(ctx, PQG_ERR_ARG, "pqg_plan_create_ext: dictionary page outside the image");
+            const uint32_t usz = codec ? chunk_ext[c].dict_uncompressed_size : static_cast<uint32_t>(s.dict_size);
+            XformRec r{};
+            r.src_off = s.dict_off; r.src_size = static_cast<uint32_t>(s.dict_size);
+            r.dst_off = place(usz); r.dst_size = usz;
+            r.kind = codec << 8; r.page = s.first_page;
+            recs.push_back(r);
+            ck[c].dict_off = r.dst_off; ck[c].dict_size = usz;
+        }
+        for (uint32_t q = s.first_page; q < s.first_page + s.n_pages; q++) {
+            const pqg_page_desc& p = pages[q];
+            const pqg_page_ext& e = page_ext[q];
+            const uint32_t codec = (e.kind >> 8) & 0xffu;
+            const bool v2 = e.kind & PQG_PAGE_EXT_V2;
+            if (codec > PQG_CODEC_SNAPPY) return fail(ctx, PQG_ERR_UNSUPPORTED, "pqg_plan_create_ext: page codec " + std::to_string(codec) + " is not supported (SNAPPY only)");
+            if (p.payload_off + p.payload_size > image->size) return fail(ctx, PQG_ERR_ARG, "pqg_plan_create_ext: page outside the image");
+            if (p.flags & PQG_PAGE_FLAG_V2) return fail(ctx, PQG_ERR_ARG, "pqg_plan_create_ext: DATA_PAGE_V2 pages are marked in pqg_page_ext.kind, not in flags");
+            XformRec r{};
+            r.src_off = p.payload_off; r.src_size = p.payload_size;
+            r.kind = codec << 8; r.page = q; r.num_values = p.num_values;
+            uint32_t usz;
+            if (v2) {
+                if (s.max_rep > 0 || e.rep_len) return fail(ctx, PQG_ERR_UNSUPPORTED, "pqg_plan_create_ext: DATA_PAGE_V2 of a nested column (repetition levels) is not supported");
+                if (static_cast<uint64_t>(e.def_len) + e.rep_len > e.uncompressed_size || static_cast<uint64_t>(e.def_len) + e.rep_len > p.payload_size)
+                    return fail(ctx, PQG_ERR_ARG, "pqg_plan_create_ext: level lengths exceed the page");
+                const uint32_t values = e.uncompressed_size - e.def_len - e.rep_len; // uncompressed size of the value section
+                uint32_t lev = 0;
+                r.kind |= kXformV2;
+                if (s.max_def > 0) { r.kind |= kXformPrefix; lev = e.def_len ? 4u + e.def_len : kXformSynthBytes; }
+                else if (e.def_len) return fail(ctx, PQG_ERR_ARG, "pqg_plan_create_ext: definition levels in a page of a REQUIRED column");
+                r.def_len = e.def_len; r.rep_len = e.rep_len;
+                usz = lev + values;
+            } else usz = codec ? e.uncompressed_size : p.payload_size;
+            r.dst_off = place(usz); r.dst_size = usz;
+            recs.push_back(r);
+            pg[q].payload_off = r.dst_off; pg[q].payload_size = usz;
+        }
+    }
+    pqg_buf* own = new pqg_buf();
+    own->size = off; own->capacity = off + kImagePad; own->owned = true;
+    if (cudaSetDevice(ctx->device) != cudaSuccess || cudaMalloc(reinterpret_cast<void**>(&own->d), own->capacity) != cudaSuccess) {
+        delete own;
+        return cuda_fail(ctx, cudaGetLastError(), "cudaMalloc(plan image)");
+    }
+    cudaMemsetAsync(own->d + off, 0, kImagePad, ctx->stream);
+    pqg_plan* p = nullptr;
+    const int rc = plan_create_impl(ctx, own, ck.data(), n_chunks, pg.data(), n_pages, false, &p);
+    if (rc != PQG_OK) { cudaFree(own->d); delete own; return rc; }
+    p->ext_src = image; p->ext_image = own;
+    p->n_xform = static_cast<uint32_t>(recs.size());
+    if (!recs.empty()) {
+        cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&p->d_xform), recs.size() * sizeof(XformRec));
+        if (e == cudaSuccess) e = cudaMemcpy(p->d_xform, recs.data(), recs.size() * sizeof(XformRec), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { pqg_plan_destroy(ctx, p); return cuda_fail(ctx, e, "cudaMalloc(plan transform table)"); }
+    }
+    *out = p;
+    return PQG_OK;
 }
 
 static int plan_create_impl(pqg_ctx* ctx, const pqg_buf* image, const pqg_chunk_desc* chunks, uint32_t n_chunks,
@@ -630,6 +713,7 @@ int pqg_plan_set_option(pqg_plan* plan, int option, int value) {
 
 int pqg_plan_set_image(pqg_ctx* ctx, pqg_plan* plan, const pqg_buf* image) {
     if (!ctx || !plan || !image) return fail(ctx, PQG_ERR_ARG, "pqg_plan_set_image: bad argument");
+    if (plan->ext_image) return fail(ctx, PQG_ERR_UNSUPPORTED, "pqg_plan_set_image: not for plans of pqg_plan_create_ext");
     if (image->size < plan->image->size) return fail(ctx, PQG_ERR_ARG, "pqg_plan_set_image: image is smaller than the planned one");
     plan->image = image;
     return PQG_OK;
@@ -787,6 +871,10 @@ int pqg_plan_run(pqg_ctx* ctx, pqg_plan* p) {
     if (prof) CU(ctx, cudaEventRecord(p->ev[0], s));
     CU(ctx, reset_err(p, s));
     CU(ctx, reset_validity(p, s));
+    if (p->n_xform) { // pqg_plan_create_ext: the plan's image from the caller's (V2 framing, SNAPPY)
+        CU(ctx, launch_xform(p->ext_src->d, p->ext_image->d, p->d_xform, p->n_xform, p->d_err, ctx->sm_count, s));
+        launches++;
+    }
     DecodeParams P = make_params(p);
     if (!p->is_str) {
         // ev0 .. ev1 dictionary preparation, ev1 .. ev2 the tile kernel, ev2 .. ev3 the general kernel
@@ -943,6 +1031,8 @@ int pqg_plan_finish(pqg_ctx* ctx, pqg_plan* p, pqg_page_error* err) {
             std::snprintf(msg, sizeof(msg), "page %u: dictionary index bit width %u > 32 is not supported", pe.page, pe.need);
         else if (pe.code == PQG_PAGE_BAD_RUN)
             std::snprintf(msg, sizeof(msg), "page %u: zero-length RLE/bit-packed run (undefined in the reference decoder)", pe.page);
+        else if (pe.code == PQG_PAGE_DECOMPRESS)
+            std::snprintf(msg, sizeof(msg), "page %u: the page (or its chunk's dictionary page) does not decompress to its uncompressed_page_size", pe.page);
         else if (pe.code == PQG_PAGE_CHARS_OVERFLOW)
             std::snprintf(msg, sizeof(msg), "page %u: column chunk exceeds 4 GiB of string bytes", pe.page);
         else
@@ -956,6 +1046,7 @@ int pqg_plan_run_pipelined(pqg_ctx* ctx, pqg_plan* p, pqg_buf* image, const pqg_
                            void* host_values, uint32_t* host_validity) {
     if (!ctx || !p || !image || (!ranges && n_ranges)) return fail(ctx, PQG_ERR_ARG, "pqg_plan_run_pipelined: bad argument");
     if (p->is_str) return fail(ctx, PQG_ERR_UNSUPPORTED, "pqg_plan_run_pipelined: BYTE_ARRAY plans need the size pass first; use pqg_plan_run");
+    if (p->ext_image) return fail(ctx, PQG_ERR_UNSUPPORTED, "pqg_plan_run_pipelined: not for plans of pqg_plan_create_ext; use pqg_plan_run");
     if (image != p->image || !image->owned) return fail(ctx, PQG_ERR_ARG, "pqg_plan_run_pipelined: image must be the plan's own pqg_buf_alloc buffer");
     CU(ctx, cudaSetDevice(ctx->device));
     if (!ctx->h2d) CU(ctx, cudaStreamCreateWithFlags(&ctx->h2d, cudaStreamNonBlocking));

@@ -171,6 +171,20 @@ struct DecodeParams {
     const uint64_t* total_chars; // ... and the device-side grand total it must hold (null: the host already checked)
 };
 
+// Rewrite of DATA_PAGE_V2 / SNAPPY pages into the layout the decode kernels know (pqg_ext.cu): one record per dictionary
+// page and per data page of a plan created by pqg_plan_create_ext
+constexpr uint32_t kXformV2 = 1u, kXformPrefix = 2u; // XformRec::kind bits (bits 8..15: PQG_CODEC_* of the compressed part)
+constexpr uint32_t kXformSynthBytes = 10u;           // length word + the one RLE run written for a V2 page of an OPTIONAL column without level bytes
+struct XformRec {
+    uint64_t src_off, dst_off; // in the caller's image / in the plan's image
+    uint32_t src_size, dst_size;
+    uint32_t kind, def_len, rep_len, num_values;
+    uint32_t page;             // page-table index for error reports (dictionary pages: their chunk's first page)
+    uint32_t pad;
+};
+struct DevErr;
+cudaError_t launch_xform(const uint8_t* src, uint8_t* dst, const XformRec* recs, uint32_t n, DevErr* err, int sm_count, cudaStream_t s);
+
 // launchers (pqg_decode.cu)
 // width 0 = BYTE_ARRAY: three launches (segments, link, emit), max_dict_blocks = blocks of 256 threads per dictionary
 cudaError_t launch_dict_prepare(const DecodeParams& p, uint32_t n_chunks, int width, uint32_t max_dict_blocks, cudaStream_t s);

@@ -274,7 +274,7 @@ size_t parse_page_header(const uint8_t* data, size_t avail, PageHeader& ph) {
                 ph.dictionary_page_header = d;
                 break;
             }
-            case 8: { // DataPageHeaderV2 {1 num_values, 2 num_nulls, 3 num_rows, 4 encoding, ...}: never decoded, only stepped over
+            case 8: { // DataPageHeaderV2 {1 num_values, 2 num_nulls, 3 num_rows, 4 encoding, 5 / 6 level byte lengths, 7 is_compressed}
                 ph.is_v2 = true;
                 DataPageHeader d;
                 int16_t l2 = 0, id2; uint8_t t2;
@@ -282,6 +282,9 @@ size_t parse_page_header(const uint8_t* data, size_t avail, PageHeader& ph) {
                     switch (id2) {
                         case 1: d.num_values = c.i32(); break;
                         case 4: d.encoding = static_cast<Encoding>(c.i32()); break;
+                        case 5: ph.v2_def_len = c.i32(); break;
+                        case 6: ph.v2_rep_len = c.i32(); break;
+                        case 7: ph.v2_compressed = (t2 == T_TRUE); break;
                         default: c.skip(t2);
                     }
                 }
@@ -362,6 +365,10 @@ void walk_chunk_pages(const uint8_t* image, uint64_t image_file_off, uint64_t im
         r.num_values = 0;
         r.counted = false;
         r.one_level_run = false;
+        r.uncompressed_size = ph.uncompressed_page_size < 0 ? 0u : static_cast<uint32_t>(ph.uncompressed_page_size);
+        r.v2_def_len = ph.v2_def_len < 0 ? 0u : static_cast<uint32_t>(ph.v2_def_len);
+        r.v2_rep_len = ph.v2_rep_len < 0 ? 0u : static_cast<uint32_t>(ph.v2_rep_len);
+        r.v2_compressed = ph.v2_compressed;
         if (ph.compressed_page_size < 0) throw FormatError("negative page size");
         if (ph.type == PageType::DICTIONARY_PAGE) {
             if (!ph.dictionary_page_header) throw FormatError("bad_optional_access: dictionary page without its header");
@@ -409,7 +416,10 @@ void walk_chunk_pages(const uint8_t* image, uint64_t image_file_off, uint64_t im
 }
 
 void append_chunk_tables(ColumnTables& t, const std::vector<PageRecord>& pages, uint64_t image_file_off,
-                         ParquetType type, int16_t max_def, int16_t max_rep, uint32_t rg, uint32_t col) {
+                         ParquetType type, int16_t max_def, int16_t max_rep, uint32_t rg, uint32_t col,
+                         bool extensions, CompressionCodec codec) {
+    const uint32_t pcodec = static_cast<uint32_t>(codec); // PQG_CODEC_* share the format's numbering for 0 / 1
+    if (extensions && codec != CompressionCodec::UNCOMPRESSED) t.ext = true;
     auto open_chunk = [&](const PageRecord* dict) {
         pqg_chunk_desc c;
         std::memset(&c, 0, sizeof(c));
@@ -425,13 +435,14 @@ void append_chunk_tables(ColumnTables& t, const std::vector<PageRecord>& pages, 
             c.dict_num_values = dict->num_values < 0 ? 0u : static_cast<uint32_t>(dict->num_values);
         }
         t.chunks.push_back(c);
+        t.chunk_ext.push_back(pqg_chunk_ext{dict ? dict->uncompressed_size : 0u, dict ? pcodec : 0u});
     };
     bool opened = false;
     for (const PageRecord& r : pages) {
         if (r.type == PageType::DICTIONARY_PAGE) {
             // a new dictionary replaces the previous one for the following data pages
             // (column_reader.cpp:48-54): start a new table chunk
-            if (opened && t.chunks.back().n_pages == 0) t.chunks.pop_back();
+            if (opened && t.chunks.back().n_pages == 0) { t.chunks.pop_back(); t.chunk_ext.pop_back(); }
             open_chunk(&r);
             opened = true;
         } else if (r.type == PageType::DATA_PAGE) {
@@ -447,7 +458,28 @@ void append_chunk_tables(ColumnTables& t, const std::vector<PageRecord>& pages, 
             p.flags = PQG_PAGE_FLAGS(r.encoding == Encoding::PLAIN_DICTIONARY || r.encoding == Encoding::RLE_DICTIONARY, static_cast<int32_t>(r.encoding));
             if (max_def == 1 && max_rep == 0) p.flags |= PQG_PAGE_FLAG_LEVELS_SEEN | (r.one_level_run ? PQG_PAGE_FLAG_NO_NULLS : 0u);
             t.pages.push_back(p);
+            t.page_ext.push_back(pqg_page_ext{r.uncompressed_size, 0u, 0u, pcodec << 8});
             t.page_row_group.push_back(rg);
+            c.n_pages++;
+            c.num_values += p.num_values;
+            t.total_slots += p.num_values;
+        }
+        else if (r.type == PageType::DATA_PAGE_V2 && extensions) {
+            // decodable through pqg_plan_create_ext: a data page like any other + its level lengths
+            if (!opened) { open_chunk(nullptr); opened = true; }
+            pqg_chunk_desc& c = t.chunks.back();
+            pqg_page_desc p;
+            std::memset(&p, 0, sizeof(p));
+            p.payload_off = r.payload_off - image_file_off;
+            p.out_row_base = t.total_slots;
+            p.payload_size = r.payload_size;
+            p.num_values = static_cast<uint32_t>(r.num_values);
+            p.chunk_idx = static_cast<uint32_t>(t.chunks.size() - 1);
+            p.flags = PQG_PAGE_FLAGS(r.encoding == Encoding::PLAIN_DICTIONARY || r.encoding == Encoding::RLE_DICTIONARY, static_cast<int32_t>(r.encoding));
+            t.pages.push_back(p);
+            t.page_ext.push_back(pqg_page_ext{r.uncompressed_size, r.v2_def_len, r.v2_rep_len, PQG_PAGE_EXT_V2 | ((r.v2_compressed ? pcodec : 0u) << 8)});
+            t.page_row_group.push_back(rg);
+            t.ext = true;
             c.n_pages++;
             c.num_values += p.num_values;
             t.total_slots += p.num_values;
@@ -463,12 +495,13 @@ void append_chunk_tables(ColumnTables& t, const std::vector<PageRecord>& pages, 
             p.chunk_idx = static_cast<uint32_t>(t.chunks.size() - 1);
             p.flags = PQG_PAGE_FLAG_V2 | PQG_PAGE_FLAGS(false, static_cast<int32_t>(r.encoding));
             t.pages.push_back(p);
+            t.page_ext.push_back(pqg_page_ext{0u, 0u, 0u, 0u});
             t.page_row_group.push_back(rg);
             t.chunks.back().n_pages++;
         }
         // INDEX_PAGE / unknown: skipped like the reference (column_reader.cpp:66-67)
     }
-    if (opened && t.chunks.back().n_pages == 0) t.chunks.pop_back();
+    if (opened && t.chunks.back().n_pages == 0) { t.chunks.pop_back(); t.chunk_ext.pop_back(); }
 }
 
 } // namespace pqg

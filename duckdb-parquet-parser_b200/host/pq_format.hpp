@@ -104,7 +104,9 @@ struct PageHeader {
     std::optional<DataPageHeader> data_page_header;
     std::optional<DictionaryPageHeader> dictionary_page_header;
     bool is_v2 = false;
-    std::optional<DataPageHeader> v2_header; // DATA_PAGE_V2: num_values + encoding only (stepped over, never decoded)
+    std::optional<DataPageHeader> v2_header; // DATA_PAGE_V2: num_values + encoding (the reference steps over such pages)
+    int32_t v2_def_len = 0, v2_rep_len = 0;  // DATA_PAGE_V2: definition_ / repetition_levels_byte_length
+    bool v2_compressed = true;               // DATA_PAGE_V2: is_compressed (default true)
 };
 
 // Leaf column description (reference include/reader/column_info.hpp).
@@ -145,6 +147,9 @@ struct PageRecord {
     PageType type;
     Encoding encoding;
     bool counted;          // contributes to the global page index (DATA_PAGE / DATA_PAGE_V2)
+    uint32_t uncompressed_size; // PageHeader.uncompressed_page_size
+    uint32_t v2_def_len, v2_rep_len; // DATA_PAGE_V2 level lengths
+    bool v2_compressed;    // DATA_PAGE_V2: the value section is compressed with the chunk's codec
     bool one_level_run;    // data pages: the payload starts like <u32 length><RLE run of value 1 covering num_values> (PQG_PAGE_FLAG_NO_NULLS for max_def 1 columns)
 };
 
@@ -166,12 +171,19 @@ inline uint64_t chunk_start_offset(const ColumnMetaData& m) {
 struct ColumnTables {
     std::vector<pqg_chunk_desc> chunks;
     std::vector<pqg_page_desc> pages;
+    // extension mode (DATA_PAGE_V2 / SNAPPY, pqg_plan_create_ext): parallel to chunks / pages; `ext` = some entry needs it
+    std::vector<pqg_chunk_ext> chunk_ext;
+    std::vector<pqg_page_ext> page_ext;
+    bool ext = false;
     std::vector<uint32_t> page_row_group; // per page: source row group (for views)
     uint64_t total_slots = 0;
 };
 
 // Appends the tables of one column chunk.  image_file_off = file offset of image byte 0.
+// extensions: list DATA_PAGE_V2 pages as decodable pages and record `codec` (pqg_plan_create_ext); otherwise V2 pages are
+// listed with PQG_PAGE_FLAG_V2 (refused at plan creation, like the reference never decodes them)
 void append_chunk_tables(ColumnTables& t, const std::vector<PageRecord>& pages, uint64_t image_file_off,
-                         ParquetType type, int16_t max_def, int16_t max_rep, uint32_t rg, uint32_t col);
+                         ParquetType type, int16_t max_def, int16_t max_rep, uint32_t rg, uint32_t col,
+                         bool extensions = false, CompressionCodec codec = CompressionCodec::UNCOMPRESSED);
 
 } // namespace pqg

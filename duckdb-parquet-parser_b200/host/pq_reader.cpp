@@ -155,8 +155,11 @@ DecodedColumn decode_packed(Device& dev, const uint8_t* src_base, const PackedIm
     } g{ctx, buf};
     for (const Range& r : img.ranges)
         if (pqg_buf_write(ctx, buf, r.dst_off, src_base + r.src_off, r.len) != PQG_OK) throw_ctx(ctx, "upload");
-    if (pqg_plan_create(ctx, buf, t.chunks.data(), static_cast<uint32_t>(t.chunks.size()), t.pages.data(),
-                        static_cast<uint32_t>(t.pages.size()), &g.p) != PQG_OK) {
+    const int crc = t.ext ? pqg_plan_create_ext(ctx, buf, t.chunks.data(), static_cast<uint32_t>(t.chunks.size()), t.pages.data(),
+                                                static_cast<uint32_t>(t.pages.size()), t.page_ext.data(), t.chunk_ext.data(), &g.p)
+                          : pqg_plan_create(ctx, buf, t.chunks.data(), static_cast<uint32_t>(t.chunks.size()), t.pages.data(),
+                                            static_cast<uint32_t>(t.pages.size()), &g.p);
+    if (crc != PQG_OK) {
         // keep the reference's wording for unsupported types
         throw std::runtime_error(pqg_last_error(ctx));
     }
@@ -450,10 +453,13 @@ ColumnTables ParquetReader::column_tables_range(int col_idx, size_t rg0, size_t 
     for (size_t rg = rg0; rg < rg1; rg++) {
         const ColumnChunk& chunk = metadata_.row_groups[rg].columns.at(static_cast<size_t>(ci.column_index));
         if (!chunk.meta_data) throw std::runtime_error("ColumnChunk has no metadata");
-        if (chunk.meta_data->codec != CompressionCodec::UNCOMPRESSED)
-            throw std::runtime_error("Only uncompressed parquet files are supported");
+        const CompressionCodec codec = chunk.meta_data->codec;
+        if (codec != CompressionCodec::UNCOMPRESSED && !(extensions_ && codec == CompressionCodec::SNAPPY))
+            throw std::runtime_error(extensions_ ? std::string("Only uncompressed and SNAPPY-compressed parquet files are supported (codec ") +
+                                                       compression_name(codec) + ")"
+                                                 : std::string("Only uncompressed parquet files are supported"));
         append_chunk_tables(t, chunk_pages_[rg][static_cast<size_t>(ci.column_index)], 0, ci.type,
-                            ci.max_def_level, ci.max_rep_level, static_cast<uint32_t>(rg), static_cast<uint32_t>(col_idx));
+                            ci.max_def_level, ci.max_rep_level, static_cast<uint32_t>(rg), static_cast<uint32_t>(col_idx), extensions_, codec);
     }
     return t;
 }
@@ -523,6 +529,7 @@ CachedPlan& ParquetReader::cached_plan_range(int col_idx, size_t rg0, size_t rg1
     static const uint32_t widths[] = {1, 4, 8, 12, 4, 8, 0, 0};
     cp->width = widths[static_cast<int>(cp->type) & 7];
     cp->t = column_tables_range(col_idx, rg0, rg1);
+    if (cp->t.ext) throw std::runtime_error("compressed / DATA_PAGE_V2 chunks (extensions) decode through read_column / read_column_columnar, not the pipelined reads");
     cp->img = pack_column(cp->t, file_size_);
     cp->ctx = Device::get(device_).ctx();
     if (cp->t.chunks.empty()) { auto& ref = *cp; plans_[key] = std::move(cp); return ref; }

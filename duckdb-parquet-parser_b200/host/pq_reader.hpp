@@ -251,6 +251,11 @@ public:
     size_t first_page_id(size_t rg, size_t col_idx) const;
 
     void set_device(int device) { device_ = device; }
+    // Beyond the reference: with extensions on, SNAPPY-compressed chunks and DATA_PAGE_V2 pages of flat columns
+    // decode (read_column*, read_column_columnar; pqg_plan_create_ext) instead of being refused / skipped like the reference
+    // does (src/reader/column_reader.cpp:13-15,66-67).  Off by default: the reader then behaves exactly like the reference.
+    void set_extensions(bool on) { extensions_ = on; }
+    bool extensions() const { return extensions_; }
     int device() const { return device_; }
 
 private:
@@ -261,6 +266,7 @@ private:
     size_t file_size_ = 0;
     bool mapped_ = false;
     int device_ = -1;
+    bool extensions_ = false;
     std::string open_error_;
     double scan_seconds_ = 0;
     FileMetaData metadata_;

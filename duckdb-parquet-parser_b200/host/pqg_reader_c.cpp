@@ -80,6 +80,7 @@ pqr_reader* pqr_open_memory(const uint8_t* data, uint64_t size, int device) {
 }
 
 void pqr_close(pqr_reader* r) { delete r; }
+void pqr_set_extensions(pqr_reader* r, int on) { if (r) r->r.set_extensions(on != 0); }
 
 int64_t pqr_num_rows(const pqr_reader* r) { return r->r.num_rows(); }
 int64_t pqr_num_row_groups(const pqr_reader* r) { return static_cast<int64_t>(r->r.num_row_groups()); }
@@ -366,6 +367,7 @@ int pqr_column_tables(const pqr_reader* r, int col, int rg, pqr_tables* out) {
         if (col < 0 || col >= static_cast<int>(r->r.num_columns())) throw std::runtime_error("Invalid column index");
         if (rg >= static_cast<int>(r->r.num_row_groups())) throw std::runtime_error("Invalid row group index");
         ColumnTables t = r->r.column_tables(col, rg);
+        if (t.ext) throw std::runtime_error("tables of compressed / DATA_PAGE_V2 chunks are not exported (decode them through pqr_read_column*)");
         out->n_chunks = static_cast<uint32_t>(t.chunks.size());
         out->n_pages = static_cast<uint32_t>(t.pages.size());
         out->total_slots = t.total_slots;
@@ -381,6 +383,7 @@ int pqr_column_tables_rgs(const pqr_reader* r, int col, int64_t rg_begin, int64_
         if (col < 0 || col >= static_cast<int>(r->r.num_columns())) throw std::runtime_error("Invalid column index");
         if (rg_begin < 0 || rg_end < rg_begin || rg_end > static_cast<int64_t>(r->r.num_row_groups())) throw std::runtime_error("Invalid row group index");
         ColumnTables t = r->r.column_tables_range(col, static_cast<size_t>(rg_begin), static_cast<size_t>(rg_end));
+        if (t.ext) throw std::runtime_error("tables of compressed / DATA_PAGE_V2 chunks are not exported (decode them through pqr_read_column*)");
         out->n_chunks = static_cast<uint32_t>(t.chunks.size());
         out->n_pages = static_cast<uint32_t>(t.pages.size());
         out->total_slots = t.total_slots;
@@ -403,6 +406,7 @@ int pqr_columns_tables(const pqr_reader* r, const int* cols, int n_cols, int rg,
             if (cols[k] < 0 || cols[k] >= static_cast<int>(r->r.num_columns())) throw std::runtime_error("Invalid column index");
             ts.push_back(r->r.column_tables(cols[k], rg));
             const ColumnTables& t = ts.back();
+            if (t.ext) throw std::runtime_error("tables of compressed / DATA_PAGE_V2 chunks are not exported (decode them through pqr_read_column*)");
             for (const pqg_chunk_desc& c : t.chunks) {
                 const int w = width_of(c.phys_type);
                 if (w == 0 || (width && w != width)) throw std::runtime_error("pqr_columns_tables: the columns of one plan must share a 4- or 8-byte value width");

@@ -58,7 +58,8 @@ enum {
     PQG_PAGE_DICT_TRUNCATED = 4,/* dictionary page shorter than its entries */
     PQG_PAGE_CHARS_OVERFLOW = 5,/* a column chunk decodes to >= 4 GiB of string bytes */
     PQG_PAGE_LAYOUT = 6,        /* internal: a string page broke the byte count the fast path assumed (the plan re-runs with the exact size pass) */
-    PQG_PAGE_CHARS_CAP = 7      /* internal: the chars buffer of the previous run is too small (the plan re-sizes it and re-runs) */
+    PQG_PAGE_CHARS_CAP = 7,     /* internal: the chars buffer of the previous run is too small (the plan re-sizes it and re-runs) */
+    PQG_PAGE_DECOMPRESS = 8     /* pqg_plan_create_ext plans: a page did not decompress to its uncompressed_page_size (corrupt SNAPPY data / wrong sizes) */
 };
 
 /* Physical types: reference enum ParquetType (include/common.hpp:16-25). */
@@ -181,6 +182,33 @@ PQG_API int pqg_plan_create(pqg_ctx* ctx, const pqg_buf* image, const pqg_chunk_
 PQG_API int pqg_plan_create_dict_indices(pqg_ctx* ctx, const pqg_buf* image, const pqg_chunk_desc* chunks,
                                          uint32_t n_chunks, const pqg_page_desc* pages, uint32_t n_pages,
                                          pqg_plan** out);
+/* ---- beyond the reference: DATA_PAGE_V2 and SNAPPY pages ---------------- */
+/* The reference refuses compressed chunks (src/reader/column_reader.cpp:13-15) and skips DATA_PAGE_V2
+ * (:66-67); pqg_plan_create does the same (PQG_ERR_UNSUPPORTED).  This entry point takes, next to the
+ * usual tables, what those pages need from their headers.  The plan keeps its OWN device image: at the
+ * start of every run one kernel rewrites each dictionary / data page of `image` into the DATA_PAGE
+ * layout the decode kernels know (length word in front of V2 definition levels, SNAPPY blocks decoded),
+ * then the run proceeds as for pqg_plan_create.  In `pages`, payload_off / payload_size describe the
+ * bytes as STORED (compressed size), flags carry no PQG_PAGE_FLAG_V2; in `chunks`, dict_size likewise.
+ * Flat columns only (max_rep == 0: PQG_ERR_UNSUPPORTED otherwise); codecs other than SNAPPY:
+ * PQG_ERR_UNSUPPORTED.  pqg_plan_run_pipelined and pqg_plan_set_image do not apply to such plans. */
+#define PQG_CODEC_UNCOMPRESSED 0u
+#define PQG_CODEC_SNAPPY 1u
+#define PQG_PAGE_EXT_V2 1u
+typedef struct pqg_page_ext {
+    uint32_t uncompressed_size; /* PageHeader.uncompressed_page_size (levels included) */
+    uint32_t def_len;           /* DATA_PAGE_V2: definition_levels_byte_length (DATA_PAGE: 0) */
+    uint32_t rep_len;           /* DATA_PAGE_V2: repetition_levels_byte_length (DATA_PAGE: 0) */
+    uint32_t kind;              /* PQG_PAGE_EXT_V2 | codec << 8 -- codec of the compressed part: the whole payload of a DATA_PAGE, the
+                                 * value section of a DATA_PAGE_V2 (PQG_CODEC_UNCOMPRESSED when its is_compressed is false) */
+} pqg_page_ext;
+typedef struct pqg_chunk_ext {
+    uint32_t dict_uncompressed_size; /* PageHeader.uncompressed_page_size of the dictionary page */
+    uint32_t dict_codec;             /* PQG_CODEC_* of the dictionary page */
+} pqg_chunk_ext;
+PQG_API int pqg_plan_create_ext(pqg_ctx* ctx, const pqg_buf* image, const pqg_chunk_desc* chunks, uint32_t n_chunks,
+                                const pqg_page_desc* pages, uint32_t n_pages, const pqg_page_ext* page_ext,
+                                const pqg_chunk_ext* chunk_ext, pqg_plan** out);
 PQG_API void pqg_plan_destroy(pqg_ctx* ctx, pqg_plan* plan);
 /* tuning switches of a plan (A/B measurements; the defaults are the measured best).  PQG_OPT_PARTITIONED_DICT (default 0):
  * dictionaries of 32 KB .. 512 KB of values in REQUIRED-only 4/8-byte plans are split over the shared memories of 1..4

@@ -107,6 +107,11 @@ PQG_API const char* pqr_last_error(void);
 PQG_API pqr_reader* pqr_open(const char* path, int device);
 PQG_API pqr_reader* pqr_open_memory(const uint8_t* data, uint64_t size, int device);
 PQG_API void pqr_close(pqr_reader* r);
+/* Beyond the reference, off by default: SNAPPY-compressed chunks and DATA_PAGE_V2 pages of flat columns decode
+ * through pqr_read_column* (pqg_plan_create_ext) instead of failing with "Only uncompressed parquet files are supported" /
+ * PQG_ERR_UNSUPPORTED like the reference refuses or skips them (src/reader/column_reader.cpp:13-15,66-67).  The pipelined
+ * reads and the table exports keep refusing such chunks. */
+PQG_API void pqr_set_extensions(pqr_reader* r, int on);
 
 PQG_API int64_t pqr_num_rows(const pqr_reader* r);
 PQG_API int64_t pqr_num_row_groups(const pqr_reader* r);
