@@ -108,6 +108,17 @@ class ReadStats(C.Structure):
                 ("bytes_out", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
 
 
+class StringsDst(C.Structure):
+    _fields_ = [("offsets", C.c_void_p), ("offsets_cap", C.c_uint64), ("chars", C.c_void_p), ("chars_cap", C.c_uint64),
+                ("validity", C.c_void_p), ("validity_cap", C.c_uint64), ("char_bases", C.c_void_p), ("char_bases_cap", C.c_uint64)]
+
+
+class StringsStats(C.Structure):
+    _fields_ = [("num_slots", C.c_uint64), ("n_chunks", C.c_uint64), ("chars_size", C.c_uint64), ("has_validity", C.c_int32),
+                ("reserved", C.c_int32), ("bytes_in", C.c_uint64), ("bytes_out", C.c_uint64), ("h2d_bytes", C.c_uint64),
+                ("d2h_bytes", C.c_uint64)]
+
+
 class H2dRange(C.Structure):
     _fields_ = [("host", C.c_void_p), ("image_off", C.c_uint64), ("len", C.c_uint64), ("chunk", C.c_uint32), ("reserved", C.c_uint32)]
 
@@ -138,7 +149,7 @@ PQR_SYMBOLS = [
     "pqr_columnar_free", "pqr_read_columns_into", "pqr_read_dictionary_indices_into", "pqr_chunk_dictionary", "pqr_release_plans", "pqr_column_tables", "pqr_columns_tables", "pqr_tables_free", "pqr_chunk_index", "pqr_regex_prune",
     "pqr_page_chunk_index", "pqr_shard_row_groups", "pqr_regex_prune_rgs", "pqr_chunk_index_rgs", "pqr_read_columns_into_rgs",
     "pqr_chunk_index_prepare_rgs", "pqr_chunk_index_stitch", "pqr_chunk_index_emit", "pqr_chunk_job_free", "pqr_column_tables_rgs",
-    "pqr_set_extensions",
+    "pqr_set_extensions", "pqr_read_strings_into",
 ]
 
 PQGEN_SYMBOLS = ["pqgen_last_error", "pqgen_encode", "pqgen_size", "pqgen_emit", "pqgen_write_file", "pqgen_free", "pqgen_string_len", "pqgen_fill_strings"]
@@ -253,6 +264,7 @@ def _declare(L):
     d("pqr_columnar_free", None, C.POINTER(Columnar))
     d("pqr_read_columns_into", i32, vp, C.POINTER(C.c_int32), i32, i32, C.POINTER(Dst), C.POINTER(ReadStats))
     d("pqr_read_dictionary_indices_into", i32, vp, i32, i64, i64, C.POINTER(Dst), C.POINTER(ReadStats))
+    d("pqr_read_strings_into", i32, vp, i32, i64, i64, C.POINTER(StringsDst), C.POINTER(StringsStats))
     d("pqr_chunk_dictionary", i32, vp, i32, i64, vp, i64, vp, i64, C.POINTER(i64), C.POINTER(i64))
     d("pqr_release_plans", None, vp)
     d("pqr_shard_row_groups", i32, vp, i32, i32, C.POINTER(C.c_int32))
@@ -515,6 +527,19 @@ class Reader:
         self._check(lib().pqr_read_columns_into_rgs(self.h, ci, n, rg_begin, rg_end, ds, st))
         return [dict(num_slots=s.num_slots, width=s.width, has_validity=bool(s.has_validity), bytes_in=s.bytes_in,
                      bytes_out=s.bytes_out, h2d_bytes=s.h2d_bytes, d2h_bytes=s.d2h_bytes) for s in st]
+
+    def read_strings_into(self, col, rg_begin, rg_end, offsets, chars, char_bases, validity=None):
+        """pipelined BYTE_ARRAY read into caller-owned numpy arrays / (ptr, capacity) pairs: offsets uint32, chars uint8,
+        char_bases uint64, validity uint32 words or None.  Returns the stats dict (chars_size, n_chunks, ...)."""
+        def pc(x, item):
+            return (x[0], x[1]) if isinstance(x, tuple) else (x.ctypes.data, x.nbytes // item)
+        (op, oc), (cp, cc), (bp, bc) = pc(offsets, 4), pc(chars, 1), pc(char_bases, 8)
+        vp_, vc = pc(validity, 4) if validity is not None else (None, 0)
+        ds = StringsDst(op, oc, cp, cc, vp_, vc, bp, bc)
+        st = StringsStats()
+        self._check(lib().pqr_read_strings_into(self.h, col, rg_begin, rg_end, C.byref(ds), C.byref(st)))
+        return dict(num_slots=st.num_slots, n_chunks=st.n_chunks, chars_size=st.chars_size, has_validity=bool(st.has_validity),
+                    bytes_in=st.bytes_in, bytes_out=st.bytes_out, h2d_bytes=st.h2d_bytes, d2h_bytes=st.d2h_bytes)
 
     def read_dictionary_indices(self, col, rg_begin=0, rg_end=None, out=None, validity=None):
         """dictionary-form read: (uint32 indices per slot, validity words | None, stats)"""

@@ -36,7 +36,14 @@ Device::Device(int device) : device_(device) {
     if (pqg_ctx_create(device, nullptr, &ctx_) != PQG_OK)
         throw std::runtime_error(std::string("GPU decoder unavailable: ") + pqg_last_error(nullptr));
 }
-Device::~Device() { pqg_ctx_destroy(ctx_); }
+Device::~Device() { if (ctx2_) pqg_ctx_destroy(ctx2_); pqg_ctx_destroy(ctx_); }
+pqg_ctx* Device::ctx2() {
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    if (!ctx2_ && pqg_ctx_create(device_, nullptr, &ctx2_) != PQG_OK)
+        throw std::runtime_error(std::string("GPU decoder unavailable: ") + pqg_last_error(nullptr));
+    return ctx2_;
+}
 
 Device& Device::get(int device) {
     static std::mutex mu;
@@ -277,7 +284,10 @@ std::vector<PageResult> ColumnReader::read_pages() {
 
 // ── ParquetReader ────────────────────────────────────────────────────────────────────────
 ParquetReader::ParquetReader() = default;
-ParquetReader::~ParquetReader() { close_file(); }
+ParquetReader::~ParquetReader() {
+    close_file();
+    for (int i = 0; i < 2; i++) if (vscratch_[i]) { pqg_host_free(vscratch_[i]); vscratch_[i] = nullptr; vscratch_words_[i] = 0; }
+}
 
 void ParquetReader::close_file() {
     if (mapped_ && data_) munmap(const_cast<uint8_t*>(data_), file_size_);
@@ -518,10 +528,10 @@ CachedPlan& ParquetReader::cached_plan(int col_idx, int row_group_idx) {
     return cached_plan_range(col_idx, rg0, rg1);
 }
 
-CachedPlan& ParquetReader::cached_plan_range(int col_idx, size_t rg0, size_t rg1, bool dict_indices) {
+CachedPlan& ParquetReader::cached_plan_range(int col_idx, size_t rg0, size_t rg1, bool dict_indices, int lane) {
     if (rg1 > metadata_.row_groups.size() || rg0 > rg1) throw std::runtime_error("Invalid row group index");
     if (col_idx < 0 || col_idx >= static_cast<int>(columns_.size())) throw std::runtime_error("Invalid column index");
-    auto key = std::make_tuple(col_idx, rg0, rg1, dict_indices ? 1 : 0);
+    auto key = std::make_tuple(col_idx, rg0, rg1, (dict_indices ? 1 : 0) + 2 * lane);
     auto it = plans_.find(key);
     if (it != plans_.end()) return *it->second;
     auto cp = std::make_unique<CachedPlan>();
@@ -531,7 +541,7 @@ CachedPlan& ParquetReader::cached_plan_range(int col_idx, size_t rg0, size_t rg1
     cp->t = column_tables_range(col_idx, rg0, rg1);
     if (cp->t.ext) throw std::runtime_error("compressed / DATA_PAGE_V2 chunks (extensions) decode through read_column / read_column_columnar, not the pipelined reads");
     cp->img = pack_column(cp->t, file_size_);
-    cp->ctx = Device::get(device_).ctx();
+    cp->ctx = lane ? Device::get(device_).ctx2() : Device::get(device_).ctx();
     if (cp->t.chunks.empty()) { auto& ref = *cp; plans_[key] = std::move(cp); return ref; }
     if (pqg_buf_alloc(cp->ctx, cp->img.size, &cp->buf) != PQG_OK) throw_ctx(cp->ctx, "device image");
     auto create = dict_indices ? pqg_plan_create_dict_indices : pqg_plan_create;
@@ -646,6 +656,105 @@ void ParquetReader::read_dictionary_indices_into(int col_idx, size_t rg0, size_t
     if (dst.values_cap < need || (need && !dst.values)) throw std::runtime_error("read_dictionary_indices_into: indices buffer too small");
     std::vector<CachedPlan*> cps{&cp};
     run_pipelined(cps, &dst, stats);
+}
+
+void ParquetReader::read_strings_into_range(int col_idx, size_t rg0, size_t rg1, const StringsDst& dst, StringsReadStats* stats) {
+    if (col_idx < 0 || col_idx >= static_cast<int>(columns_.size())) throw std::runtime_error("Invalid column index");
+    if (rg1 > metadata_.row_groups.size() || rg0 > rg1) throw std::runtime_error("Invalid row group index");
+    const ColumnInfo& ci = columns_[static_cast<size_t>(col_idx)];
+    if (ci.type != ParquetType::BYTE_ARRAY)
+        throw std::runtime_error("Column '" + ci.name + "' is not BYTE_ARRAY (type: " + parquet_type_name(ci.type) + ")");
+    const size_t K = rg1 - rg0;
+    std::vector<CachedPlan*> cps(K);
+    std::vector<uint64_t> row_base(K + 1, 0), chunk_base(K + 1, 0);
+    for (size_t k = 0; k < K; k++) {
+        cps[k] = &cached_plan_range(col_idx, rg0 + k, rg0 + k + 1, false, static_cast<int>(k & 1));
+        row_base[k + 1] = row_base[k] + cps[k]->t.total_slots;
+        chunk_base[k + 1] = chunk_base[k] + cps[k]->t.chunks.size();
+    }
+    const uint64_t slots = row_base[K], n_chunks = chunk_base[K], vwords = (slots + 31) / 32;
+    if (dst.offsets_cap < slots + n_chunks || ((slots + n_chunks) && !dst.offsets)) throw std::runtime_error("read_strings_into: offsets buffer too small");
+    if (dst.char_bases_cap < n_chunks + 1 || !dst.char_bases) throw std::runtime_error("read_strings_into: char_bases buffer too small");
+    if (dst.validity && dst.validity_cap < vwords) throw std::runtime_error("read_strings_into: validity buffer too small");
+    if (dst.validity) std::memset(dst.validity, 0, vwords * 4);
+    StringsReadStats st;
+    st.num_slots = slots; st.n_chunks = n_chunks;
+    struct Flight { bool on = false; size_t k = 0; uint64_t char_base = 0, chars_size = 0; } fl[2];
+    std::string first_error;
+    auto land = [&](int lane) { // wait for the lane's row group, merge what needs the host
+        Flight& f = fl[lane];
+        if (!f.on) return;
+        f.on = false;
+        CachedPlan& cp = *cps[f.k];
+        pqg_page_error pe;
+        if (pqg_plan_finish(cp.ctx, cp.plan, &pe) != PQG_OK) { if (first_error.empty()) first_error = pqg_last_error(cp.ctx); return; }
+        if (pqg_plan_chars_size(cp.plan) != f.chars_size) { // (a plan that met other data than in its previous run: fetch again)
+            if (first_error.empty()) first_error = "read_strings_into: the string bytes of a row group changed between two reads of the same file";
+            return;
+        }
+        const uint64_t nc = cp.t.chunks.size(), n = cp.t.total_slots;
+        std::vector<uint64_t> local(nc + 1);
+        pqg_plan_char_bases(cp.ctx, cp.plan, local.data(), static_cast<uint32_t>(nc + 1));
+        for (uint64_t c = 0; c < nc; c++) dst.char_bases[chunk_base[f.k] + c] = f.char_base + local[c];
+        const bool has_v = pqg_plan_validity(cp.plan) != nullptr;
+        if (has_v) st.has_validity = 1;
+        if (dst.validity && n) { // the row group's bits at their place in the range's bitmap
+            const uint64_t b0 = row_base[f.k];
+            const uint32_t sh = static_cast<uint32_t>(b0 & 31);
+            uint32_t* out = dst.validity + (b0 >> 5);
+            const uint64_t nw = (n + 31) / 32;
+            for (uint64_t w = 0; w < nw; w++) {
+                uint32_t bits = has_v ? vscratch_[lane][w] : 0xffffffffu;
+                if (w == nw - 1 && (n & 31)) bits &= (1u << (n & 31)) - 1u;
+                out[w] |= bits << sh;
+                if (sh && (bits >> (32 - sh))) out[w + 1] |= bits >> (32 - sh);
+            }
+        }
+        st.bytes_in += pqg_plan_bytes_in(cp.plan);
+        st.bytes_out += pqg_plan_bytes_out(cp.plan);
+        st.h2d_bytes += cp.h2d_bytes;
+        st.d2h_bytes += f.chars_size + 4 * (n + nc) + (has_v && dst.validity ? ((n + 31) / 32) * 4 : 0);
+    };
+    uint64_t char_base = 0;
+    for (size_t k = 0; k < K && first_error.empty(); k++) {
+        const int lane = static_cast<int>(k & 1);
+        land(lane);
+        if (!first_error.empty()) break;
+        CachedPlan& cp = *cps[k];
+        if (!cp.plan) continue; // a row group without pages of this column
+        for (const pqg_h2d_range& r : cp.ranges)
+            if (pqg_buf_write(cp.ctx, cp.buf, r.image_off, r.host, r.len) != PQG_OK) throw_ctx(cp.ctx, "upload");
+        if (pqg_plan_run(cp.ctx, cp.plan) != PQG_OK) { first_error = pqg_last_error(cp.ctx); break; }
+        const uint64_t csize = pqg_plan_chars_size(cp.plan);
+        if (char_base + csize > dst.chars_cap || (csize && !dst.chars)) {
+            first_error = "read_strings_into: chars buffer too small (" + std::to_string(char_base + csize) + " bytes needed up to row group " +
+                          std::to_string(rg0 + k) + ", " + std::to_string(dst.chars_cap) + " given)";
+            pqg_page_error pe;
+            pqg_plan_finish(cp.ctx, cp.plan, &pe);
+            break;
+        }
+        const uint64_t nw = (cp.t.total_slots + 31) / 32;
+        uint32_t* vdst = nullptr;
+        if (dst.validity && pqg_plan_validity(cp.plan)) {
+            if (vscratch_words_[lane] < nw + 1) {
+                if (vscratch_[lane]) pqg_host_free(vscratch_[lane]);
+                vscratch_[lane] = static_cast<uint32_t*>(pqg_host_alloc((nw + 1) * 4));
+                vscratch_words_[lane] = vscratch_[lane] ? nw + 1 : 0;
+                if (!vscratch_[lane]) throw std::runtime_error("read_strings_into: pinned staging allocation failed");
+            }
+            vdst = vscratch_[lane];
+        }
+        if (pqg_plan_download(cp.ctx, cp.plan, nullptr, vdst, dst.offsets + row_base[k] + chunk_base[k], dst.chars + char_base) != PQG_OK)
+            throw_ctx(cp.ctx, "download");
+        fl[lane] = Flight{true, k, char_base, csize};
+        char_base += csize;
+    }
+    land(0);
+    land(1);
+    if (!first_error.empty()) throw std::runtime_error(first_error);
+    dst.char_bases[n_chunks] = char_base;
+    st.chars_size = char_base;
+    if (stats) *stats = st;
 }
 
 void ParquetReader::chunk_dictionary(int col_idx, size_t rg, std::vector<uint32_t>& offsets, std::vector<uint8_t>& chars) const {

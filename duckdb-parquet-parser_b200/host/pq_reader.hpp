@@ -66,11 +66,13 @@ class Device {
 public:
     static Device& get(int device = -1);
     pqg_ctx* ctx() const { return ctx_; }
+    pqg_ctx* ctx2();              // a second context (own streams) on the same device: the pipelined string reads alternate between the two
     int index() const { return device_; }
     ~Device();
 private:
     explicit Device(int device);
     pqg_ctx* ctx_ = nullptr;
+    pqg_ctx* ctx2_ = nullptr;
     int device_ = 0;
 };
 
@@ -133,6 +135,21 @@ struct ColumnDst {
     uint64_t values_cap = 0;         // bytes available behind `values`
     uint32_t* validity = nullptr;    // ceil(num_slots / 32) words, or nullptr
     uint64_t validity_cap = 0;       // words available behind `validity`
+};
+// Destination of a pipelined BYTE_ARRAY read (read_strings_into_range): the caller's (ideally pinned) buffers.
+//   offsets    total_slots + n_chunks entries: chunk c owns [chunk_row_base[c] + c, chunk_row_base[c + 1] + c], offsets relative to the chunk's chars
+//   chars      all string bytes, chunk after chunk; char_bases[c] = where chunk c's bytes start (n_chunks + 1 entries)
+//   validity   ceil(total_slots / 32) words over the whole range (may be null)
+struct StringsDst {
+    uint32_t* offsets = nullptr; uint64_t offsets_cap = 0;   // entries
+    uint8_t* chars = nullptr; uint64_t chars_cap = 0;        // bytes
+    uint32_t* validity = nullptr; uint64_t validity_cap = 0; // words
+    uint64_t* char_bases = nullptr; uint64_t char_bases_cap = 0;
+};
+struct StringsReadStats {
+    uint64_t num_slots = 0, n_chunks = 0, chars_size = 0;
+    int32_t has_validity = 0;
+    uint64_t bytes_in = 0, bytes_out = 0, h2d_bytes = 0, d2h_bytes = 0;
 };
 struct ColumnReadStats {
     uint64_t num_slots = 0;
@@ -216,6 +233,11 @@ public:
     // read_columns_into.  Throws "... not dictionary-encoded throughout" otherwise.  The strings
     // of slot i are entry indices[i] of chunk_dictionary(row group of i).
     void read_dictionary_indices_into(int col_idx, size_t rg_begin, size_t rg_end, const ColumnDst& dst, ColumnReadStats* stats);
+    // Pipelined read of a BYTE_ARRAY column (the reference has no counterpart: its read_column materialises Values one by
+    // one, src/reader/parquet_reader.cpp:125-165): one cached plan per row group, alternating between two contexts of the
+    // device, so that the upload and size pass of row group k + 1 overlap the copy pass and the D2H of row group k.
+    // The output sizes are data dependent: `chars_cap` too small fails with the bytes needed so far in the message.
+    void read_strings_into_range(int col_idx, size_t rg_begin, size_t rg_end, const StringsDst& dst, StringsReadStats* stats);
     // the dictionary page of one column chunk, parsed on the host: n + 1 offsets into chars
     void chunk_dictionary(int col_idx, size_t rg, std::vector<uint32_t>& offsets, std::vector<uint8_t>& chars) const;
     void release_plans();
@@ -275,9 +297,11 @@ private:
     std::vector<PageIndexEntry> page_index_;
     std::vector<std::vector<std::vector<PageRecord>>> chunk_pages_; // [rg][chunk column]
     std::vector<std::vector<size_t>> chunk_first_page_;              // [rg][chunk column] -> global id
-    std::map<std::tuple<int, size_t, size_t, int>, std::unique_ptr<CachedPlan>> plans_; // (column, row groups [begin, end), dictionary form)
+    std::map<std::tuple<int, size_t, size_t, int>, std::unique_ptr<CachedPlan>> plans_; // (column, row groups [begin, end), dictionary form + 2 * context lane)
+    uint32_t* vscratch_[2] = {nullptr, nullptr}; // pinned validity staging of the pipelined string reads, one per lane
+    uint64_t vscratch_words_[2] = {0, 0};
     CachedPlan& cached_plan(int col_idx, int row_group_idx);
-    CachedPlan& cached_plan_range(int col_idx, size_t rg_begin, size_t rg_end, bool dict_indices = false);
+    CachedPlan& cached_plan_range(int col_idx, size_t rg_begin, size_t rg_end, bool dict_indices = false, int lane = 0);
     void run_pipelined(const std::vector<CachedPlan*>& cps, const ColumnDst* dsts, ColumnReadStats* stats);
 };
 

@@ -287,6 +287,17 @@ int pqr_read_dictionary_indices_into(pqr_reader* r, int32_t col, int64_t rg_begi
         return 0;
     }, -1);
 }
+int pqr_read_strings_into(pqr_reader* r, int32_t col, int64_t rg_begin, int64_t rg_end, const pqr_strings_dst* dst, pqr_strings_stats* stats) {
+    return guarded([&]() -> int {
+        if (rg_begin < 0 || rg_end < rg_begin || !dst) throw std::runtime_error("Invalid row group index");
+        StringsReadStats st;
+        r->r.read_strings_into_range(col, static_cast<size_t>(rg_begin), static_cast<size_t>(rg_end),
+                                     StringsDst{dst->offsets, dst->offsets_cap, dst->chars, dst->chars_cap, dst->validity, dst->validity_cap,
+                                                dst->char_bases, dst->char_bases_cap}, &st);
+        if (stats) *stats = pqr_strings_stats{st.num_slots, st.n_chunks, st.chars_size, st.has_validity, 0, st.bytes_in, st.bytes_out, st.h2d_bytes, st.d2h_bytes};
+        return 0;
+    }, -1);
+}
 int pqr_chunk_dictionary(const pqr_reader* r, int32_t col, int64_t rg, uint32_t* offsets, int64_t offsets_cap, uint8_t* chars,
                          int64_t chars_cap, int64_t* n_entries, int64_t* n_bytes) {
     return guarded([&]() -> int {

@@ -173,6 +173,27 @@ PQG_API int pqr_read_columns_into(pqr_reader* r, const int32_t* cols, int32_t n_
  * "... not dictionary-encoded throughout" for columns with PLAIN pages. */
 PQG_API int pqr_read_dictionary_indices_into(pqr_reader* r, int32_t col, int64_t rg_begin, int64_t rg_end,
                                              const pqr_dst* dst, pqr_read_stats* stats);
+/* Pipelined read of a BYTE_ARRAY column into the caller's (ideally pinned) buffers -- no counterpart in the reference, whose
+ * read_column materialises one Value per slot (src/reader/parquet_reader.cpp:125-165).  One cached plan per row group,
+ * alternating between two contexts of the device: the upload and size pass of row group k + 1 overlap the copy pass and the
+ * D2H of row group k.  Layout as pqr_read_columnar: `offsets` holds total_slots + n_chunks entries (chunk c owns
+ * [row_base(c) + c, row_base(c + 1) + c], relative to the chunk's chars), chunk c's bytes start at chars[char_bases[c]]
+ * (n_chunks + 1 entries), `validity` covers the whole range (may be NULL).  A chars buffer that is too small fails with the
+ * number of bytes needed so far in the message; the uncompressed size of the column's pages is always enough for PLAIN
+ * columns, rows x longest dictionary entry for dictionary columns. */
+typedef struct pqr_strings_dst {
+    uint32_t* offsets; uint64_t offsets_cap;    /* entries */
+    uint8_t* chars; uint64_t chars_cap;         /* bytes */
+    uint32_t* validity; uint64_t validity_cap;  /* words */
+    uint64_t* char_bases; uint64_t char_bases_cap;
+} pqr_strings_dst;
+typedef struct pqr_strings_stats {
+    uint64_t num_slots, n_chunks, chars_size;
+    int32_t has_validity, reserved;
+    uint64_t bytes_in, bytes_out, h2d_bytes, d2h_bytes;
+} pqr_strings_stats;
+PQG_API int pqr_read_strings_into(pqr_reader* r, int32_t col, int64_t rg_begin, int64_t rg_end, const pqr_strings_dst* dst,
+                                  pqr_strings_stats* stats);
 /* offsets: n_entries + 1 uint32 into chars; pass NULL buffers to query the sizes first */
 PQG_API int pqr_chunk_dictionary(const pqr_reader* r, int32_t col, int64_t rg, uint32_t* offsets, int64_t offsets_cap,
                                  uint8_t* chars, int64_t chars_cap, int64_t* n_entries, int64_t* n_bytes);
