@@ -183,6 +183,47 @@ def strings_bench(pq, device, stream, dist, steps, warmup, peak, peak_source, ro
            "kernel_ms": {"dict_prepare": tm["dict_ms"], "size_pass": tm["str_size_ms"], "copy_pass": tm["str_copy_ms"]},
            "roofline": roofline("k_dict_prepare<0> + k_str_pages<sizes> + k_str_pages<copy>", bytes_in, bytes_out, k_ms, peak, peak_source),
            "parity": "full size, on the device: chars == the input strings of the non-null rows, offsets == 13 x rank, validity == !is_null"}
+    # end to end through the reader: pinned host file image in, pinned host offsets / chars / validity out, row group by row
+    # group on two alternating contexts (pqr_read_strings_into) -- against the same column uploaded, decoded and downloaded
+    # as ONE plan (pqr_read_columnar's way: nothing overlaps)
+    chars_size = int(plan.chars_size)
+    pin_img = torch.empty(size + 64, dtype=torch.uint8, pin_memory=True)
+    pin_img.numpy()[:size] = host[:size]
+    r2 = pq.Reader.from_pointer(pin_img.data_ptr(), size, device=device)
+    n_rg = r2.num_row_groups
+    o_off = torch.empty(rows + n_chunks + 8, dtype=torch.int32, pin_memory=True)
+    o_chars = torch.empty(chars_size + 64, dtype=torch.uint8, pin_memory=True)
+    o_val = torch.empty((rows + 31) // 32 + 1, dtype=torch.int32, pin_memory=True)
+    o_base = np.zeros(n_chunks + 2, dtype=np.uint64)
+    dsts = ((o_off.data_ptr(), o_off.numel()), (o_chars.data_ptr(), o_chars.numel()), o_base, (o_val.data_ptr(), o_val.numel()))
+    e2e_steps = max(2, min(steps, 5))
+    st = None
+    for _ in range(2):
+        st = r2.read_strings_into(0, 0, n_rg, dsts[0], dsts[1], dsts[2], dsts[3])
+    dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        st = r2.read_strings_into(0, 0, n_rg, dsts[0], dsts[1], dsts[2], dsts[3])
+    e2e_ms = dist.allmax((time.perf_counter() - t0) * 1e3 / e2e_steps)
+    if st["chars_size"] != chars_size or not np.array_equal(o_chars.numpy()[:1 << 20], dev_tensor(plan.chars_ptr, 1 << 20, "|u1").cpu().numpy()):
+        raise AssertionError("strings bench e2e: the pipelined read differs from the plan's output")
+    # one plan, nothing overlapped: upload, run, finish, download, sync
+    dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        pq.lib().pqg_buf_write(ctx.h, image, 0, pin_img.data_ptr(), size)
+        plan.run()
+        plan.finish()
+        plan.download(offsets=o_off.data_ptr(), chars=o_chars.data_ptr(), validity=o_val.data_ptr())
+        ctx.sync()
+    serial_ms = dist.allmax((time.perf_counter() - t0) * 1e3 / e2e_steps)
+    res["e2e"] = {"value": bytes_in * dist.world / (e2e_ms * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": e2e_ms,
+                  "h2d_bytes_per_step": int(st["h2d_bytes"]), "d2h_bytes_per_step": int(st["d2h_bytes"]),
+                  "api": "pqr_read_strings_into: pinned file image in, pinned offsets / chars / validity out, one cached plan per row group on two "
+                         "alternating contexts (H2D + size pass of row group k + 1 under the copy pass + D2H of row group k)",
+                  "one_plan_no_overlap_ms": serial_ms, "speedup_vs_one_plan": serial_ms / e2e_ms if e2e_ms else None}
+    r2.close()
+    del pin_img, o_off, o_chars, o_val
     # sample row group against the oracle (+ CPU baseline: the reference's ColumnReader on a bounded sample)
     if dist.rank == 0:
         res["parity"] += "; " + _strings_sample_check(pq, specs, col, plan, tables, rg_rows)

@@ -679,7 +679,7 @@ void ParquetReader::read_strings_into_range(int col_idx, size_t rg0, size_t rg1,
     if (dst.validity) std::memset(dst.validity, 0, vwords * 4);
     StringsReadStats st;
     st.num_slots = slots; st.n_chunks = n_chunks;
-    struct Flight { bool on = false; size_t k = 0; uint64_t char_base = 0, chars_size = 0; } fl[2];
+    struct Flight { bool on = false; size_t k = 0; uint64_t char_base = 0, chars_size = 0; bool direct = false; } fl[2];
     std::string first_error;
     auto land = [&](int lane) { // wait for the lane's row group, merge what needs the host
         Flight& f = fl[lane];
@@ -698,7 +698,11 @@ void ParquetReader::read_strings_into_range(int col_idx, size_t rg0, size_t rg1,
         for (uint64_t c = 0; c < nc; c++) dst.char_bases[chunk_base[f.k] + c] = f.char_base + local[c];
         const bool has_v = pqg_plan_validity(cp.plan) != nullptr;
         if (has_v) st.has_validity = 1;
-        if (dst.validity && n) { // the row group's bits at their place in the range's bitmap
+        if (dst.validity && n && f.direct) {
+            // (the validity words went straight to their place: the row group starts and ends on word boundaries)
+            if (!has_v) std::memset(dst.validity + (row_base[f.k] >> 5), 0xFF, ((n + 31) / 32) * 4);
+            if (n & 31) dst.validity[(row_base[f.k] >> 5) + n / 32] &= (1u << (n & 31)) - 1u;
+        } else if (dst.validity && n) { // the row group's bits at their place in the range's bitmap
             const uint64_t b0 = row_base[f.k];
             const uint32_t sh = static_cast<uint32_t>(b0 & 31);
             uint32_t* out = dst.validity + (b0 >> 5);
@@ -735,7 +739,10 @@ void ParquetReader::read_strings_into_range(int col_idx, size_t rg0, size_t rg1,
         }
         const uint64_t nw = (cp.t.total_slots + 31) / 32;
         uint32_t* vdst = nullptr;
-        if (dst.validity && pqg_plan_validity(cp.plan)) {
+        // row groups that start on a word boundary (and end on one, or end the range) download their validity words in place
+        const bool direct = (row_base[k] & 31) == 0 && ((cp.t.total_slots & 31) == 0 || k + 1 == K);
+        if (dst.validity && pqg_plan_validity(cp.plan) && direct) vdst = dst.validity + (row_base[k] >> 5);
+        else if (dst.validity && pqg_plan_validity(cp.plan)) {
             if (vscratch_words_[lane] < nw + 1) {
                 if (vscratch_[lane]) pqg_host_free(vscratch_[lane]);
                 vscratch_[lane] = static_cast<uint32_t*>(pqg_host_alloc((nw + 1) * 4));
@@ -746,7 +753,7 @@ void ParquetReader::read_strings_into_range(int col_idx, size_t rg0, size_t rg1,
         }
         if (pqg_plan_download(cp.ctx, cp.plan, nullptr, vdst, dst.offsets + row_base[k] + chunk_base[k], dst.chars + char_base) != PQG_OK)
             throw_ctx(cp.ctx, "download");
-        fl[lane] = Flight{true, k, char_base, csize};
+        fl[lane] = Flight{true, k, char_base, csize, direct};
         char_base += csize;
     }
     land(0);
