@@ -20,4 +20,5 @@ python scripts/bench_strings.py 40000000 > gpurun_out/${T}_strings.json 2>> gpur
 python scripts/bench_optional.py 40000000 > gpurun_out/${T}_optional.json 2>> gpurun_out/side.err; echo "optional rc=$?"
 python scripts/bench_foreign.py 40000000 > gpurun_out/${T}_foreign.json 2>> gpurun_out/side.err; echo "foreign rc=$?"
 python scripts/bench_foreign.py 10000000 > gpurun_out/${T}_foreign_10M.json 2>> gpurun_out/side.err; echo "foreign 10M rc=$?"
+python scripts/bench_ext.py 10000000 > gpurun_out/${T}_ext.json 2>> gpurun_out/side.err; echo "ext rc=$?"
 tail -3 gpurun_out/side.err
