@@ -163,14 +163,14 @@ __device__ __forceinline__ void flat_scan_page(const DecodeParams& P, uint32_t e
     // the page's blocks (and checkpoints): a range of the block arrays
     uint32_t blk0 = 0;
     if (l == 0) {
-        blk0 = atomicAdd(&P.flat->nblk, (n + 1023u) >> 10);
-        PQG_ASSERT(blk0 + ((n + 1023u) >> 10) <= P.flat_blk_cap);
+        blk0 = atomicAdd(&P.flat->nblk, static_cast<uint32_t>((static_cast<uint64_t>(n) + 1023u) >> 10));
+        PQG_ASSERT(blk0 + ((static_cast<uint64_t>(n) + 1023u) >> 10) <= P.flat_blk_cap);
         fp.status = n ? 0u : 2u; fp.vpos = 0; fp.bw = 0; fp.nn = n; fp.blk0 = blk0; fp.page = q;
     }
     blk0 = __shfl_sync(0xffffffffu, blk0, 0);
     if (n == 0) return; // nothing to decode, nothing to hand over
     PQG_ASSERT(pd.out_row_base + n <= P.n_slots);
-    if (ck.max_rep > 0 || ck.max_def > 1) { if (l == 0) flat_hand_over(P, fp, q); return; }
+    if (ck.max_rep > 0 || ck.max_def > 1 || n > 0x7fffffffu) { if (l == 0) flat_hand_over(P, fp, q); return; } // (32-bit slot arithmetic below)
     // pages the general kernel stages whole in shared memory (what the tile kernel hands over from writer-shaped files):
     // one mostly empty block each here, a single pass there
     if (n <= 1024u && size <= static_cast<uint32_t>(kSlotBytes)) { if (l == 0) flat_hand_over(P, fp, q); return; }
@@ -338,7 +338,7 @@ __device__ __forceinline__ void flat_rank_page(const DecodeParams& P, uint32_t e
     const uint32_t q = fp.page;
     const pqg_page_desc pd = P.pages[q];
     const uint32_t n = pd.num_values;
-    const uint32_t nblk = (n + 1023u) >> 10;
+    const uint32_t nblk = static_cast<uint32_t>((static_cast<uint64_t>(n) + 1023u) >> 10);
     FlatBlk* blk = P.flat_blk + fp.blk0;
     if (fp.status) { for (uint32_t b = l; b < nblk; b += 32) blk[b].nslots = 0; return; }
     const DevChunk& ck = P.chunks[pd.chunk_idx];
