@@ -32,8 +32,12 @@ __device__ __forceinline__ void warp_copy(uint8_t* dst, const uint8_t* src, uint
     if (done + l < n) dst[done + l] = src[done + l];
 }
 
-// raw SNAPPY block `in[0, n)` -> exactly `expect` bytes at `out`; false: corrupt input (nothing may be assumed about out)
-__device__ __forceinline__ bool warp_snappy(const uint8_t* in, uint32_t n, uint8_t* out, uint32_t expect) {
+// raw SNAPPY block `in[0, n)` -> exactly `expect` bytes at `out`; false: corrupt input (nothing may be assumed about out).
+// `hist` = the warp's kSnappyHist bytes of shared memory: a ring of the most recent output (position p at p & (kSnappyHist - 1)).
+// A copy element reads what the warp itself wrote a moment ago; from global memory that is an L2 round trip per element
+// (the stores went past the L1), from the ring a shared-memory load.  Offsets beyond the ring still go to global memory.
+constexpr uint32_t kSnappyHist = 4096;
+__device__ __forceinline__ bool warp_snappy(const uint8_t* in, uint32_t n, uint8_t* out, uint32_t expect, uint8_t* hist) {
     const uint32_t l = lane_id();
     uint32_t ip = 0, ulen = 0, shift = 0;
     for (;;) { // preamble: uncompressed length, varint
@@ -60,7 +64,13 @@ __device__ __forceinline__ bool warp_snappy(const uint8_t* in, uint32_t n, uint8
                 ip += nb;
             }
             if (len > n - ip || len > expect - op) return false;
-            warp_copy(out + op, in + ip, len);
+            if (len <= 64u) { // short: bytes by lane, to the output and to the ring
+                for (uint32_t i = l; i < len; i += 32) { const uint8_t b = in[ip + i]; out[op + i] = b; hist[(op + i) & (kSnappyHist - 1u)] = b; }
+            } else {
+                warp_copy(out + op, in + ip, len);
+                const uint32_t keep = min(len, kSnappyHist); // the ring only ever needs the last kSnappyHist bytes
+                for (uint32_t i = len - keep + l; i < len; i += 32) hist[(op + i) & (kSnappyHist - 1u)] = in[ip + i];
+            }
             ip += len;
             op += len;
         } else {
@@ -83,17 +93,31 @@ __device__ __forceinline__ bool warp_snappy(const uint8_t* in, uint32_t n, uint8
                 ip += 4u;
             }
             if (off == 0u || off > op || len > expect - op) return false;
-            __syncwarp(); // the bytes written so far, by any lane, are the source
-            const uint8_t* from = out + op - off;
-            for (uint32_t i = l; i < len; i += 32) out[op + i] = __ldcg(from + (i < off ? i : i % off));
+            // (len <= 64: the bytes read all lie in [op - off, op), written before this element; an overlapping copy -- offset <
+            //  length, a repeating pattern -- reads source byte i mod offset)
+            if (off + 64u <= kSnappyHist) { // the source is still in the ring, and the bytes written now do not alias it
+                for (uint32_t i = l; i < len; i += 32) {
+                    const uint8_t b = hist[(op - off + (i < off ? i : i % off)) & (kSnappyHist - 1u)];
+                    out[op + i] = b;
+                    hist[(op + i) & (kSnappyHist - 1u)] = b;
+                }
+            } else {
+                const uint8_t* from = out + op - off;
+                for (uint32_t i = l; i < len; i += 32) {
+                    const uint8_t b = __ldcg(from + (i < off ? i : i % off));
+                    out[op + i] = b;
+                    hist[(op + i) & (kSnappyHist - 1u)] = b;
+                }
+            }
             op += len;
         }
-        __syncwarp();
+        __syncwarp(); // the element's bytes, written by any lane, are the next elements' source
     }
     return op == expect;
 }
 
 __global__ void __launch_bounds__(kThreadsPerCta) k_xform(const uint8_t* src, uint8_t* dst, const XformRec* recs, uint32_t n, DevErr* err) {
+    __shared__ __align__(16) uint8_t s_hist[kWarpsPerCta][kSnappyHist];
     const uint32_t l = lane_id();
     const uint32_t nwarps = gridDim.x * kWarpsPerCta;
     for (uint32_t i = blockIdx.x * kWarpsPerCta + warp_id(); i < n; i += nwarps) {
@@ -133,7 +157,7 @@ __global__ void __launch_bounds__(kThreadsPerCta) k_xform(const uint8_t* src, ui
             const uint32_t codec = (r.kind >> 8) & 0xffu;
             if (codec == PQG_CODEC_UNCOMPRESSED) {
                 if (in_size != out_size) ok = false; else warp_copy(out, in, in_size);
-            } else if (codec == PQG_CODEC_SNAPPY) ok = warp_snappy(in, in_size, out, out_size);
+            } else if (codec == PQG_CODEC_SNAPPY) ok = warp_snappy(in, in_size, out, out_size, s_hist[warp_id()]);
             else ok = false;
         }
         if (!ok && l == 0) report_error(err, r.page, PQG_PAGE_DECOMPRESS);
