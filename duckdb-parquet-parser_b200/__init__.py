@@ -138,7 +138,7 @@ PQG_SYMBOLS = [
     "pqg_plan_chars_size", "pqg_plan_char_bases", "pqg_plan_bytes_in", "pqg_plan_bytes_out", "pqg_plan_download",
     "pqg_regex_compile", "pqg_dfa_free", "pqg_dfa_num_states", "pqg_dfa_match_host", "pqg_regex_scan",
     "pqg_chunk_index", "pqg_page_chunk_index", "pqg_chunk_index_prepare", "pqg_chunk_index_stitch", "pqg_chunk_index_emit",
-    "pqg_chunk_job_ids", "pqg_chunk_job_total_weight", "pqg_chunk_job_free", "pqg_plan_create_ext",
+    "pqg_chunk_job_ids", "pqg_chunk_job_total_weight", "pqg_chunk_job_free", "pqg_plan_create_ext", "pqg_plan_filter",
 ]
 PQR_SYMBOLS = [
     "pqr_last_error", "pqr_open", "pqr_open_memory", "pqr_close", "pqr_num_rows", "pqr_num_row_groups",
@@ -154,6 +154,7 @@ PQR_SYMBOLS = [
 
 PQGEN_SYMBOLS = ["pqgen_last_error", "pqgen_encode", "pqgen_size", "pqgen_emit", "pqgen_write_file", "pqgen_free", "pqgen_string_len", "pqgen_fill_strings"]
 PQGEN_EMAILS, PQGEN_CITY64K = 0, 1
+PQG_CMP_EQ, PQG_CMP_NE, PQG_CMP_LT, PQG_CMP_LE, PQG_CMP_GT, PQG_CMP_GE = range(6)
 
 _lib = None
 
@@ -218,6 +219,7 @@ def _declare(L):
     d("pqg_dfa_num_states", u32, vp)
     d("pqg_dfa_match_host", i32, vp, vp, u64)
     d("pqg_regex_scan", i32, vp, vp, vp, i32, vp, C.POINTER(C.c_float))
+    d("pqg_plan_filter", i32, vp, vp, i32, i32, vp, vp, C.POINTER(C.c_uint64), C.POINTER(C.c_float))
     d("pqg_chunk_index", i32, vp, vp, u64, u64, u32, vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(C.c_float))
     d("pqg_page_chunk_index", i32, vp, vp, u32, u64, vp, vp, vp, u32, C.POINTER(u32))
     d("pqg_chunk_index_prepare", i32, vp, vp, u64, C.POINTER(vp), C.POINTER(C.c_float))
@@ -694,6 +696,16 @@ class Plan:
         lib().pqg_plan_timings(self.h, C.byref(t))
         return dict(dict_ms=t.dict_ms, fixed_ms=t.fixed_ms, str_size_ms=t.str_size_ms, str_copy_ms=t.str_copy_ms,
                     total_ms=t.total_ms, launches=t.launches, general_ms=t.general_ms, tile_launches=t.tile_launches)
+
+    def filter(self, value_type, op, constant, n_slots, want_bits=True):
+        """device-side predicate on the decoded column of n_slots slots (pqg_plan_filter): -> (row bitmap words | None, matches, kernel ms)"""
+        dt = {INT32: np.int32, INT64: np.int64, FLOAT: np.float32, DOUBLE: np.float64}[value_type]
+        c = np.array([constant], dtype=dt)
+        bits = np.zeros((n_slots + 31) // 32 + 1, dtype=np.uint32) if want_bits else None
+        cnt, ms = C.c_uint64(0), C.c_float(0)
+        self.ctx.check(lib().pqg_plan_filter(self.ctx.h, self.h, value_type, op, c.ctypes.data, bits.ctypes.data if want_bits else None,
+                                             C.byref(cnt), C.byref(ms)))
+        return bits, cnt.value, ms.value
 
     def timings_avg(self, last_n=0):
         t, n = Timings(), C.c_uint32(0)

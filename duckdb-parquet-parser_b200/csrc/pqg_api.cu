@@ -1175,6 +1175,7 @@ int ctx_device(const pqg_ctx* c) { return c->device; }
 void ctx_add_launches(pqg_ctx* c, uint32_t n) { c->launches += n; }
 int ctx_fail(pqg_ctx* c, int code, const std::string& m) { return fail(c, code, m); }
 bool plan_is_str(const pqg_plan* p) { return p->is_str; }
+int plan_width(const pqg_plan* p) { return p->is_bool ? 1 : p->width; }
 bool plan_ran(const pqg_plan* p) { return p->ran; }
 bool plan_run_pending(const pqg_plan* p) { return p->run_pending; }
 bool plan_regex_tile_sync(const pqg_plan* p) { return p->regex_tile_sync; }

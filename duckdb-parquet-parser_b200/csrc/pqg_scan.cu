@@ -39,6 +39,7 @@ int ctx_device(const pqg_ctx* c);
 void ctx_add_launches(pqg_ctx* c, uint32_t n);
 int ctx_fail(pqg_ctx* c, int code, const std::string& m);
 bool plan_is_str(const pqg_plan* p);
+int plan_width(const pqg_plan* p);
 bool plan_ran(const pqg_plan* p);
 bool plan_run_pending(const pqg_plan* p);
 bool plan_regex_tile_sync(const pqg_plan* p);
@@ -831,6 +832,38 @@ cudaError_t chain_emit(ChainJob& J, Src src, uint32_t id_base) {
     return cudaGetLastError();
 }
 
+// ---- device-resident consumer: a comparison predicate over a decoded fixed-width column ----------------
+// bit per slot = value <op> constant, nulls never match; one value per lane, a word of the bitmap per warp step
+template <typename T>
+__global__ void __launch_bounds__(256) k_filter(const T* values, const uint32_t* validity, uint64_t n, int op, T c, uint32_t* bits, unsigned long long* count) {
+    const uint64_t nwords = (n + 31) / 32;
+    const uint32_t l = threadIdx.x & 31u;
+    unsigned long long local = 0;
+    for (uint64_t w = (static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; w < nwords; w += (static_cast<uint64_t>(gridDim.x) * blockDim.x) >> 5) {
+        const uint64_t i = w * 32 + l;
+        bool m = false;
+        if (i < n) {
+            const T v = values[i];
+            m = op == PQG_CMP_EQ ? v == c : op == PQG_CMP_NE ? v != c : op == PQG_CMP_LT ? v < c : op == PQG_CMP_LE ? v <= c : op == PQG_CMP_GT ? v > c : v >= c;
+        }
+        uint32_t word = __ballot_sync(0xffffffffu, m);
+        if (validity) word &= validity[w];
+        if (l == 0) { bits[w] = word; local += __popc(word); }
+    }
+    if (l == 0 && local) atomicAdd(count, local);
+}
+
+template <typename T>
+static cudaError_t run_filter(const void* values, const uint32_t* validity, uint64_t n, int op, const void* constant, uint32_t* bits,
+                              unsigned long long* count, int sm_count, cudaStream_t s) {
+    T c;
+    std::memcpy(&c, constant, sizeof(T));
+    const uint64_t warps = (n + 31) / 32;
+    const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(std::max<uint64_t>((warps + 7) / 8, 1), static_cast<uint64_t>(sm_count) * 16u));
+    k_filter<T><<<grid, 256, 0, s>>>(static_cast<const T*>(values), validity, n, op, c, bits, count);
+    return cudaGetLastError();
+}
+
 } // namespace
 } // namespace pqg
 
@@ -839,6 +872,49 @@ using namespace pqg;
 #define CUF(ctx, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return ctx_fail(ctx, PQG_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
 
 extern "C" {
+
+int pqg_plan_filter(pqg_ctx* ctx, pqg_plan* plan, int value_type, int op, const void* constant, uint32_t* row_bits, uint64_t* n_match, float* kernel_ms) {
+    if (!ctx || !plan || !constant) return ctx_fail(ctx, PQG_ERR_ARG, "pqg_plan_filter: bad argument");
+    if (plan_is_str(plan) || !plan_ran(plan) || plan_run_pending(plan))
+        return ctx_fail(ctx, PQG_ERR_ARG, "pqg_plan_filter: the plan must be a decoded (run + finished) fixed-width plan");
+    if (op < PQG_CMP_EQ || op > PQG_CMP_GE) return ctx_fail(ctx, PQG_ERR_ARG, "pqg_plan_filter: unknown comparison");
+    const int width = plan_width(plan);
+    const int want = (value_type == PQG_INT32 || value_type == PQG_FLOAT) ? 4 : (value_type == PQG_INT64 || value_type == PQG_DOUBLE) ? 8 : 0;
+    if (!want || want != width) return ctx_fail(ctx, PQG_ERR_ARG, "pqg_plan_filter: value_type must be INT32 / INT64 / FLOAT / DOUBLE and match the plan's value width");
+    CUF(ctx, cudaSetDevice(ctx_device(ctx)));
+    cudaStream_t s = ctx_stream(ctx);
+    const uint64_t n = plan_slots(plan), words = (n + 31) / 32;
+    DevMem mem(s);
+    uint32_t* d_bits = nullptr;
+    unsigned long long* d_count = nullptr;
+    CUF(ctx, mem.alloc(&d_bits, words + 1));
+    CUF(ctx, mem.alloc(&d_count, 1));
+    CUF(ctx, cudaMemsetAsync(d_count, 0, 8, s));
+    EventPair ev;
+    CUF(ctx, ev.create());
+    CUF(ctx, cudaEventRecord(ev.e0, s));
+    const void* vals = pqg_plan_values(plan);
+    const uint32_t* validity = pqg_plan_validity(plan);
+    cudaError_t e = cudaSuccess;
+    if (n) {
+        switch (value_type) {
+            case PQG_INT32: e = run_filter<int32_t>(vals, validity, n, op, constant, d_bits, d_count, ctx_sm_count(ctx), s); break;
+            case PQG_INT64: e = run_filter<int64_t>(vals, validity, n, op, constant, d_bits, d_count, ctx_sm_count(ctx), s); break;
+            case PQG_FLOAT: e = run_filter<float>(vals, validity, n, op, constant, d_bits, d_count, ctx_sm_count(ctx), s); break;
+            default: e = run_filter<double>(vals, validity, n, op, constant, d_bits, d_count, ctx_sm_count(ctx), s); break;
+        }
+    }
+    CUF(ctx, e);
+    ctx_add_launches(ctx, 1);
+    CUF(ctx, cudaEventRecord(ev.e1, s));
+    unsigned long long h_count = 0;
+    CUF(ctx, cudaMemcpyAsync(&h_count, d_count, 8, cudaMemcpyDeviceToHost, s));
+    if (row_bits && words) CUF(ctx, cudaMemcpyAsync(row_bits, d_bits, words * 4, cudaMemcpyDeviceToHost, s));
+    CUF(ctx, cudaStreamSynchronize(s));
+    if (n_match) *n_match = h_count;
+    if (kernel_ms) { float ms = 0; cudaEventElapsedTime(&ms, ev.e0, ev.e1); *kernel_ms = ms; }
+    return PQG_OK;
+}
 
 int pqg_regex_scan(pqg_ctx* ctx, pqg_plan* plan, const pqg_dfa* dfa, int neg, uint32_t* page_bits, float* kernel_ms) {
     if (!ctx || !plan || !dfa || !page_bits) return ctx_fail(ctx, PQG_ERR_ARG, "pqg_regex_scan: bad argument");

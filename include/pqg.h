@@ -279,6 +279,16 @@ PQG_API uint64_t pqg_plan_bytes_out(const pqg_plan* plan); /* algorithmic output
 PQG_API int pqg_plan_download(pqg_ctx* ctx, const pqg_plan* plan, void* values, uint32_t* validity,
                               uint32_t* offsets, uint8_t* chars);
 
+/* ---- device-resident consumer: predicate on a decoded column ------------- */
+/* Rows of a decoded (run + finished) fixed-width plan whose value compares true against a constant -- the decoded column
+ * never leaves the device, one bit per slot comes back (row_bits: ceil(slots / 32) host words, may be NULL) together with
+ * the number of matches.  value_type: PQG_INT32 / PQG_INT64 / PQG_FLOAT / PQG_DOUBLE, must match the plan's value width;
+ * `constant` points at one value of that type; nulls never match; NaN compares like IEEE (only != is true).  Synchronous.
+ * The reference has no counterpart (it materialises Values on the host). */
+enum { PQG_CMP_EQ = 0, PQG_CMP_NE = 1, PQG_CMP_LT = 2, PQG_CMP_LE = 3, PQG_CMP_GT = 4, PQG_CMP_GE = 5 };
+PQG_API int pqg_plan_filter(pqg_ctx* ctx, pqg_plan* plan, int value_type, int op, const void* constant,
+                            uint32_t* row_bits, uint64_t* n_match, float* kernel_ms);
+
 /* ---- regex page pruning: replaces the parser's --regex-column mode (README.md:54-64) -- */
 /* RE2-syntax subset compiled on the host to a byte DFA; unsupported syntax is rejected
  * with an explicit message in err (PQG_ERR_REGEX).  No device needed. */

@@ -191,3 +191,46 @@ def test_cli_tools(pq, oracle, files):
         assert out.returncode == 0 and "email" in out.stdout and "data pages" in out.stdout
     finally:
         oracle.close(ho)
+
+
+def test_device_side_predicate_on_decoded_columns(pq):
+    """pqg_plan_filter (device-resident consumer): value <op> constant over the decoded column on the device,
+    nulls never match; against numpy on the same column"""
+    rng = np.random.default_rng(8)
+    n = 300_001
+    isn = (rng.random(n) < 0.2).astype(np.uint8)
+    i64 = rng.integers(-50, 50, size=n, dtype=np.int64)
+    f64 = rng.random(n) * 100 - 50  # (distinct values: a PLAIN column -- the generator refuses NaN in a dictionary)
+    f64[::50] = 1.25
+    f64[::97] = np.nan
+    i32 = rng.integers(-5, 5, size=n, dtype=np.int32)
+    g = pq.generate([("a", pq.INT64, 1, -1), ("b", pq.DOUBLE, 1, -1), ("c", pq.INT32, 0, -1)],
+                    [dict(fixed=i64, is_null=isn), dict(fixed=f64, is_null=isn), dict(fixed=i32)], [100_000, 100_000, 100_001])
+    img = g.to_numpy()
+    g.free()
+    r = pq.Reader(data=img)
+    ctx = pq.Context(0)
+    buf = ctx.upload(img.ctypes.data, img.size)
+    valid = isn == 0
+    ops = {pq.PQG_CMP_EQ: np.equal, pq.PQG_CMP_NE: np.not_equal, pq.PQG_CMP_LT: np.less, pq.PQG_CMP_LE: np.less_equal,
+           pq.PQG_CMP_GT: np.greater, pq.PQG_CMP_GE: np.greater_equal}
+    try:
+        for col, (vt, data, ok, c) in enumerate(((pq.INT64, i64, valid, 7), (pq.DOUBLE, f64, valid, 1.25), (pq.INT32, i32, np.ones(n, bool), -2))):
+            plan = ctx.plan(buf, r.column_tables(col, -1))
+            plan.run()
+            plan.finish()
+            for op, fn in ops.items():
+                with np.errstate(invalid="ignore"):
+                    exp = fn(data, c) & ok
+                bits, cnt, ms = plan.filter(vt, op, c, n)
+                got = ((bits[np.arange(n) >> 5] >> (np.arange(n) & 31).astype(np.uint32)) & 1).astype(bool)
+                assert cnt == int(exp.sum()), (col, op)
+                assert np.array_equal(got, exp), (col, op)
+                assert plan.filter(vt, op, c, n, want_bits=False)[1] == cnt
+            with pytest.raises(pq.PqgError, match="value width"):
+                plan.filter(pq.INT32 if vt != pq.INT32 else pq.INT64, pq.PQG_CMP_EQ, 1, n)
+            plan.destroy()
+    finally:
+        ctx.buf_free(buf)
+        ctx.close()
+        r.close()
