@@ -539,15 +539,17 @@ CachedPlan& ParquetReader::cached_plan_range(int col_idx, size_t rg0, size_t rg1
     static const uint32_t widths[] = {1, 4, 8, 12, 4, 8, 0, 0};
     cp->width = widths[static_cast<int>(cp->type) & 7];
     cp->t = column_tables_range(col_idx, rg0, rg1);
-    if (cp->t.ext) throw std::runtime_error("compressed / DATA_PAGE_V2 chunks (extensions) decode through read_column / read_column_columnar, not the pipelined reads");
+    if (cp->t.ext && dict_indices) throw std::runtime_error("dictionary-form reads do not cover compressed / DATA_PAGE_V2 chunks (extensions)");
     cp->img = pack_column(cp->t, file_size_);
     cp->ctx = lane ? Device::get(device_).ctx2() : Device::get(device_).ctx();
     if (cp->t.chunks.empty()) { auto& ref = *cp; plans_[key] = std::move(cp); return ref; }
     if (pqg_buf_alloc(cp->ctx, cp->img.size, &cp->buf) != PQG_OK) throw_ctx(cp->ctx, "device image");
     auto create = dict_indices ? pqg_plan_create_dict_indices : pqg_plan_create;
-    if (create(cp->ctx, cp->buf, cp->t.chunks.data(), static_cast<uint32_t>(cp->t.chunks.size()), cp->t.pages.data(),
-               static_cast<uint32_t>(cp->t.pages.size()), &cp->plan) != PQG_OK)
-        throw std::runtime_error(pqg_last_error(cp->ctx));
+    const int crc = cp->t.ext ? pqg_plan_create_ext(cp->ctx, cp->buf, cp->t.chunks.data(), static_cast<uint32_t>(cp->t.chunks.size()), cp->t.pages.data(),
+                                                    static_cast<uint32_t>(cp->t.pages.size()), cp->t.page_ext.data(), cp->t.chunk_ext.data(), &cp->plan)
+                              : create(cp->ctx, cp->buf, cp->t.chunks.data(), static_cast<uint32_t>(cp->t.chunks.size()), cp->t.pages.data(),
+                                       static_cast<uint32_t>(cp->t.pages.size()), &cp->plan);
+    if (crc != PQG_OK) throw std::runtime_error(pqg_last_error(cp->ctx));
     if (dict_indices) cp->width = 4;
     for (size_t c = 0; c < cp->img.ranges.size(); c++) {
         const Range& r = cp->img.ranges[c];
@@ -613,6 +615,7 @@ void ParquetReader::read_columns_into(const int* col_idx, int n_cols, int row_gr
 
 void ParquetReader::run_pipelined(const std::vector<CachedPlan*>& cps, const ColumnDst* dsts, ColumnReadStats* stats) {
     // enqueue every column (asynchronous), then wait column by column
+    std::vector<int> ext_no_validity; // extension columns enqueued without a validity bitmap (see below)
     for (int i = 0; i < static_cast<int>(cps.size()); i++) {
         CachedPlan& cp = *cps[static_cast<size_t>(i)];
         if (!cp.plan) continue;
@@ -621,6 +624,16 @@ void ParquetReader::run_pipelined(const std::vector<CachedPlan*>& cps, const Col
         if (has_validity && dsts[i].validity) {
             if (dsts[i].validity_cap < (cp.t.total_slots + 31) / 32) throw std::runtime_error("read_columns_into: validity buffer too small");
             vdst = dsts[i].validity;
+        }
+        if (cp.t.ext) {
+            // compressed / DATA_PAGE_V2 chunks (extensions): the page rewrite needs the whole image, so this column runs as
+            // upload -> rewrite + decode -> download on the context's stream (asynchronous; other columns proceed meanwhile)
+            for (const pqg_h2d_range& r : cp.ranges)
+                if (pqg_buf_write(cp.ctx, cp.buf, r.image_off, r.host, r.len) != PQG_OK) throw_ctx(cp.ctx, "upload");
+            if (pqg_plan_run(cp.ctx, cp.plan) != PQG_OK) throw_ctx(cp.ctx, "decode");
+            if (pqg_plan_download(cp.ctx, cp.plan, dsts[i].values, vdst, nullptr, nullptr) != PQG_OK) throw_ctx(cp.ctx, "download");
+            ext_no_validity.push_back(has_validity ? -1 : i);
+            continue;
         }
         if (pqg_plan_run_pipelined(cp.ctx, cp.plan, cp.buf, cp.ranges.data(), static_cast<uint32_t>(cp.ranges.size()),
                                    dsts[i].values, vdst) != PQG_OK) throw_ctx(cp.ctx, "decode");
@@ -636,6 +649,9 @@ void ParquetReader::run_pipelined(const std::vector<CachedPlan*>& cps, const Col
             int rc = pqg_plan_finish(cp.ctx, cp.plan, &pe);
             if (rc != PQG_OK && first_error.empty()) first_error = pqg_last_error(cp.ctx);
             st.has_validity = pqg_plan_validity(cp.plan) != nullptr;
+            // (pqg_plan_finish added a validity bitmap and decoded again: the values already copied out are stale)
+            if (st.has_validity && std::find(ext_no_validity.begin(), ext_no_validity.end(), i) != ext_no_validity.end() && first_error.empty())
+                first_error = "out-of-range dictionary index in a REQUIRED column chunk (a null in the reference): decode this column through read_column";
             st.bytes_in = pqg_plan_bytes_in(cp.plan);
             st.bytes_out = pqg_plan_bytes_out(cp.plan);
             st.h2d_bytes = cp.h2d_bytes;

@@ -109,8 +109,9 @@ PQG_API pqr_reader* pqr_open_memory(const uint8_t* data, uint64_t size, int devi
 PQG_API void pqr_close(pqr_reader* r);
 /* Beyond the reference, off by default: SNAPPY-compressed chunks and DATA_PAGE_V2 pages of flat columns decode
  * through pqr_read_column* (pqg_plan_create_ext) instead of failing with "Only uncompressed parquet files are supported" /
- * PQG_ERR_UNSUPPORTED like the reference refuses or skips them (src/reader/column_reader.cpp:13-15,66-67).  The pipelined
- * reads and the table exports keep refusing such chunks. */
+ * PQG_ERR_UNSUPPORTED like the reference refuses or skips them (src/reader/column_reader.cpp:13-15,66-67).  The streaming
+ * reads (pqr_read_columns_into, pqr_read_strings_into) take such chunks without per-chunk overlap; the table exports and the
+ * dictionary-form reads keep refusing them. */
 PQG_API void pqr_set_extensions(pqr_reader* r, int on);
 
 PQG_API int64_t pqr_num_rows(const pqr_reader* r);

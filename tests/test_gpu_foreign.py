@@ -324,9 +324,35 @@ def test_extensions_snappy_and_data_page_v2_against_pyarrow(pq, tmp_path, varian
         if v2:
             with pytest.raises(pq.PqgError, match="encoding RLE is not supported"):
                 r.read_column("b")
-        # what the extension does not cover says so
-        with pytest.raises(pq.PqgError, match="pipelined|not exported"):
-            r.read_columns_into([0], [(0, 0, 0, 0)])
+        # the streaming reads take the same plans (upload -> rewrite + decode -> download per column, no per-chunk overlap)
+        cols = [c for c in range(r.num_columns) if r.column_info(c)["type"] in (pq.INT32, pq.INT64, pq.FLOAT, pq.DOUBLE)]
+        vals = [np.zeros(n * 8, dtype=np.uint8) for _ in cols]
+        masks = [np.zeros((n + 31) // 32 + 1, dtype=np.uint32) for _ in cols]
+        st = r.read_columns_into(cols, [(v.ctypes.data, v.size, m.ctypes.data, m.size) for v, m in zip(vals, masks)])
+        for c, v, m, s_ in zip(cols, vals, masks, st):
+            exp = r.read_column(r.column_info(c)["name"])
+            w = s_["width"]
+            valid = ~exp["is_null"].astype(bool)
+            pad = np.zeros((n, 8), dtype=np.uint8)
+            pad[:, :w] = v[: n * w].reshape(n, w)
+            assert np.array_equal(pad.view(np.uint64).reshape(n)[valid], exp["fixed"][valid]), (variant, c)
+            if s_["has_validity"]:
+                gv = ((m[np.arange(n) >> 5] >> (np.arange(n) & 31).astype(np.uint32)) & 1).astype(bool)
+                assert np.array_equal(gv, valid), (variant, c)
+        # ... and so does the pipelined string read
+        sc = r.find_column("strn")
+        whole = r.read_column("strn")
+        nrg = r.num_row_groups
+        offs = np.zeros(n + 4 * nrg + 8, dtype=np.uint32)
+        chars = np.zeros(len(whole["chars"]) + 16, dtype=np.uint8)
+        bases = np.zeros(4 * nrg + 2, dtype=np.uint64)
+        vmask = np.zeros((n + 31) // 32 + 1, dtype=np.uint32)
+        st = r.read_strings_into(sc, 0, nrg, offs, chars, bases, vmask)
+        assert st["num_slots"] == n and st["chars_size"] == len(whole["chars"])
+        assert chars[:st["chars_size"]].tobytes() == whole["chars"].tobytes()
+        # table exports keep refusing what a plain pqg_plan_create cannot decode
+        with pytest.raises(pq.PqgError, match="not exported"):
+            r.column_tables(0, -1)
     finally:
         r.close()
 
