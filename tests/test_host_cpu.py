@@ -252,3 +252,37 @@ def test_thrift_skip_of_bool_lists_and_hostile_counts(pq):
     # a count far beyond the buffer is a corrupt footer, not a 2^31-iteration loop
     with pytest.raises(pq.PqgError):
         pq.Reader(data=np.frombuffer(_thrift_file(4, declared_len=(1 << 31) - 1), dtype=np.uint8))
+
+
+def test_extension_tables_are_host_side_only(pq, tmp_path):
+    """the opt-in extensions (SNAPPY / DATA_PAGE_V2) are a reader-internal path: the table exports, which feed a plain
+    pqg_plan_create, keep refusing such chunks -- with the reference's message by default, by name with extensions on"""
+    pa = pytest.importorskip("pyarrow")
+    pqa = pytest.importorskip("pyarrow.parquet")
+    rng = np.random.default_rng(5)
+    n = 3000
+    t = pa.table({"i": pa.array(rng.integers(0, 100, size=n), type=pa.int64())})
+    snappy, zstd, v2 = (str(tmp_path / f"{k}.parquet") for k in ("snappy", "zstd", "v2"))
+    pqa.write_table(t, snappy, compression="SNAPPY", data_page_version="1.0")
+    pqa.write_table(t, zstd, compression="ZSTD", data_page_version="1.0")
+    pqa.write_table(t, v2, compression="NONE", data_page_version="2.0")
+    for path, default_msg, ext_msg in ((snappy, "Only uncompressed parquet files are supported", "not exported"),
+                                       (zstd, "Only uncompressed parquet files are supported", "SNAPPY-compressed parquet files are supported .*ZSTD"),
+                                       (v2, None, "not exported")):
+        r = pq.Reader(path)
+        try:
+            assert r.num_rows == n
+            if default_msg:
+                with pytest.raises(pq.PqgError, match=default_msg):
+                    r.column_tables(0, -1)
+            else:  # V2 pages are listed (flagged) so that plan creation can refuse them
+                _, _, pages, npg, _ = r.column_tables(0, -1)
+                assert npg >= 1 and all(pages[k].flags & pq.PQG_PAGE_FLAG_V2 for k in range(npg))
+        finally:
+            r.close()
+        r = pq.Reader(path, extensions=True)
+        try:
+            with pytest.raises(pq.PqgError, match=ext_msg):
+                r.column_tables(0, -1)
+        finally:
+            r.close()
