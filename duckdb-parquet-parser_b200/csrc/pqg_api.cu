@@ -844,7 +844,8 @@ static int fixed_subrun(pqg_ctx* ctx, pqg_plan* p, uint32_t c0, uint32_t c1, boo
     //  whatever shows up -- instead of three launches over an empty list)
     if (e == cudaSuccess && p->flat_on && (P.slow_hi > P.slow_lo || (P.tile_hi > P.tile_lo && p->tile_handover_seen != 0))) {
         p->flat_ran = true;
-        e = launch_flat_pages(P, p->width, ctx->sm_count, any_dict, p->max_dict_n <= 0xffffu, s);
+        // (dictionary-form plans keep no device dictionary but their pages carry indices all the same: index buffers needed)
+        e = launch_flat_pages(P, p->width, ctx->sm_count, any_dict || p->identity, p->max_dict_n <= 0xffffu, s);
         launches += static_cast<int>(flat_launches());
         Pg.slow_hi = Pg.slow_lo;
         Pg.slow_append = P.flat_append;

@@ -391,3 +391,32 @@ def test_extensions_refuse_other_codecs_and_report_corrupt_snappy(pq, tmp_path):
             assert "decompress" in str(e) or "ByteBuffer" in str(e) or "page" in str(e)
     finally:
         r.close()
+
+
+def test_dictionary_form_read_of_big_foreign_pages_with_nulls(pq, tmp_path):
+    """dictionary-form read (indices instead of strings) of a pyarrow dictionary column whose pages hold thousands of slots
+    and nulls: those pages take the block decode (pqg_flat.cu), which for such plans emits the index itself"""
+    rng = np.random.default_rng(31)
+    n = 150_000
+    words = np.array([f"w{v:05d}" for v in rng.integers(0, 3000, size=n)], dtype=object)
+    t = pa.table({"s": pa.array(words, mask=rng.random(n) < 0.3, type=pa.string())})
+    path = write(str(tmp_path / "dictform.parquet"), t, data_page_size=64 * 1024, row_group_size=60_000)
+    r = pq.Reader(path)
+    try:
+        exp = r.read_column("s")
+        idx, val, st = r.read_dictionary_indices(0)
+        assert st["num_slots"] == n
+        valid = ((val[np.arange(n) >> 5] >> (np.arange(n) & 31).astype(np.uint32)) & 1).astype(bool)
+        assert np.array_equal(~valid, exp["is_null"].astype(bool))
+        assert not idx[~valid].any()
+        exp_off, exp_chars = exp["str_off"].astype(np.int64), exp["chars"].tobytes()
+        row = 0
+        for rg in range(r.num_row_groups):
+            nr = r.row_group_num_rows(rg)
+            off, chars = r.chunk_dictionary(0, rg)
+            got = [chars[off[k]:off[k + 1]] for k in idx[row:row + nr][valid[row:row + nr]]]
+            want = [exp_chars[exp_off[i]:exp_off[i + 1]] for i in range(row, row + nr) if valid[i]]
+            assert got == want, rg
+            row += nr
+    finally:
+        r.close()
