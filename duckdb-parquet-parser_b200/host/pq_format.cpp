@@ -420,6 +420,13 @@ void append_chunk_tables(ColumnTables& t, const std::vector<PageRecord>& pages, 
                          bool extensions, CompressionCodec codec) {
     const uint32_t pcodec = static_cast<uint32_t>(codec); // PQG_CODEC_* share the format's numbering for 0 / 1
     if (extensions && codec != CompressionCodec::UNCOMPRESSED) t.ext = true;
+    // (one entry per page: grow once -- a 100 M-row PLAIN column has 780 K pages; the extension records only where they are used)
+    auto grow = [](auto& v, size_t extra) { // (geometric: the tables of a column are appended chunk by chunk)
+        if (v.capacity() < v.size() + extra) v.reserve(std::max(v.size() + extra, v.capacity() * 2));
+    };
+    grow(t.pages, pages.size());
+    grow(t.page_row_group, pages.size());
+    if (extensions) grow(t.page_ext, pages.size());
     auto open_chunk = [&](const PageRecord* dict) {
         pqg_chunk_desc c;
         std::memset(&c, 0, sizeof(c));
@@ -435,14 +442,14 @@ void append_chunk_tables(ColumnTables& t, const std::vector<PageRecord>& pages, 
             c.dict_num_values = dict->num_values < 0 ? 0u : static_cast<uint32_t>(dict->num_values);
         }
         t.chunks.push_back(c);
-        t.chunk_ext.push_back(pqg_chunk_ext{dict ? dict->uncompressed_size : 0u, dict ? pcodec : 0u});
+        if (extensions) t.chunk_ext.push_back(pqg_chunk_ext{dict ? dict->uncompressed_size : 0u, dict ? pcodec : 0u});
     };
     bool opened = false;
     for (const PageRecord& r : pages) {
         if (r.type == PageType::DICTIONARY_PAGE) {
             // a new dictionary replaces the previous one for the following data pages
             // (column_reader.cpp:48-54): start a new table chunk
-            if (opened && t.chunks.back().n_pages == 0) { t.chunks.pop_back(); t.chunk_ext.pop_back(); }
+            if (opened && t.chunks.back().n_pages == 0) { t.chunks.pop_back(); if (extensions) t.chunk_ext.pop_back(); }
             open_chunk(&r);
             opened = true;
         } else if (r.type == PageType::DATA_PAGE) {
@@ -458,7 +465,7 @@ void append_chunk_tables(ColumnTables& t, const std::vector<PageRecord>& pages, 
             p.flags = PQG_PAGE_FLAGS(r.encoding == Encoding::PLAIN_DICTIONARY || r.encoding == Encoding::RLE_DICTIONARY, static_cast<int32_t>(r.encoding));
             if (max_def == 1 && max_rep == 0) p.flags |= PQG_PAGE_FLAG_LEVELS_SEEN | (r.one_level_run ? PQG_PAGE_FLAG_NO_NULLS : 0u);
             t.pages.push_back(p);
-            t.page_ext.push_back(pqg_page_ext{r.uncompressed_size, 0u, 0u, pcodec << 8});
+            if (extensions) t.page_ext.push_back(pqg_page_ext{r.uncompressed_size, 0u, 0u, pcodec << 8});
             t.page_row_group.push_back(rg);
             c.n_pages++;
             c.num_values += p.num_values;
@@ -495,13 +502,13 @@ void append_chunk_tables(ColumnTables& t, const std::vector<PageRecord>& pages, 
             p.chunk_idx = static_cast<uint32_t>(t.chunks.size() - 1);
             p.flags = PQG_PAGE_FLAG_V2 | PQG_PAGE_FLAGS(false, static_cast<int32_t>(r.encoding));
             t.pages.push_back(p);
-            t.page_ext.push_back(pqg_page_ext{0u, 0u, 0u, 0u});
+            if (extensions) t.page_ext.push_back(pqg_page_ext{0u, 0u, 0u, 0u});
             t.page_row_group.push_back(rg);
             t.chunks.back().n_pages++;
         }
         // INDEX_PAGE / unknown: skipped like the reference (column_reader.cpp:66-67)
     }
-    if (opened && t.chunks.back().n_pages == 0) { t.chunks.pop_back(); t.chunk_ext.pop_back(); }
+    if (opened && t.chunks.back().n_pages == 0) { t.chunks.pop_back(); if (extensions) t.chunk_ext.pop_back(); }
 }
 
 } // namespace pqg
